@@ -1,0 +1,193 @@
+/*
+ * oscen_b200.h — C ABI of the B200-native, voice-batched engine for Oscen's signal-graph
+ * evaluation loop (the generated `process()` / `process_block()` walk).
+ *
+ * The reference (reedrosenbluth/oscen @ 8061f7d5) has NO FFI boundary on this path: nodes are
+ * monomorphised and inlined into the struct `graph!` generates.  The boundary honoured here is
+ * therefore the API surface that struct exposes to its host.  Each entry point
+ * cites the generated/reference interface it replaces (paths relative to the reference repo):
+ *
+ *   oscen_b200_create          G::new() + G::init(sr)              oscen-graph-compiler/src/codegen/mod.rs:1309-1350
+ *   oscen_b200_set_value       `g.<value> = v` / set_<v>_immediate  codegen/mod.rs:959-975
+ *   oscen_b200_set_value_ramp  set_<v>_with_ramp(v, frames)         codegen/mod.rs:948-957
+ *   oscen_b200_push_events     <event>.try_push(EventInstance{..})  oscen-lib/src/graph/types.rs:183-188
+ *   oscen_b200_push_midi       midi_in.try_push(raw_midi_event(..)) examples/fm-synth/src/main.rs:157-165
+ *   oscen_b200_stream_in       writing `<in>_block[..]`             codegen/emit_frame.rs:33-41
+ *   oscen_b200_process_block   G::process_block(frames)             codegen/mod.rs:755-872
+ *   oscen_b200_read_instance_out  reading `<out>_block[..]`         codegen/emit_frame.rs:44-52
+ *   oscen_b200_read_voice_out  (parity hook: `voices[i].audio_out`) codegen/emit_node.rs:463-466
+ *   oscen_b200_read_mix        Σ over instances of `<out>_block` (the bank's mix bus; new)
+ *   oscen_b200_latency_samples G::latency_samples()                 codegen/mod.rs:644-716
+ *
+ * Conventions: every call returns 0 on success or a negative OSCEN_B200_E_* code and never
+ * unwinds across the boundary; the caller owns host buffers, the engine owns device buffers;
+ * no callbacks; one caller thread per engine at a time (mirrors `&mut self`: the engine is
+ * Send, not Sync).  `process*` in the reference are infallible; here a failure can only be a
+ * CUDA/NCCL error or an argument error, reported through the return code and last_error.
+ *
+ * Data layout: per-voice state is SoA `[field][voice]` in HBM; streams are `[frame][voice]`
+ * (voice fastest) so a warp touches 128 contiguous bytes.
+ */
+#ifndef OSCEN_B200_H
+#define OSCEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSCEN_B200_ABI_VERSION 1
+#define OSCEN_B200_MAX_BLOCK 512u          /* DEFAULT_MAX_BLOCK_SIZE, oscen-lib/src/graph/types.rs:12 */
+#define OSCEN_B200_MAX_EVENTS_PER_ENDPOINT 32u /* MAX_STATIC_EVENTS_PER_ENDPOINT, graph/types.rs:18 */
+
+/* graph kinds: the reference graphs on the hot path */
+enum {
+    OSCEN_B200_GRAPH_FM_VOICE = 0,    /* FMVoice x N, instance = FMGraph voice sum   examples/fm-synth/src/fm_voice.rs:6-156 */
+    OSCEN_B200_GRAPH_TWIN_PEAKS = 1,  /* TwinPeaksGraph (2 x LP18Filter, a - b)       examples/nih-twin-peaks/src/lib.rs:15-48 */
+    OSCEN_B200_GRAPH_SAT_1X = 2,      /* SatGraph_1x                                  examples/oversampled-saturator/src/main.rs:64-80 */
+    OSCEN_B200_GRAPH_SAT_4X = 3,      /* SatGraph_4x (4x inner loop + SincDownFir<4>) */
+    OSCEN_B200_GRAPH_EPIANO = 4,      /* ElectricPianoVoiceNode x N, instance = sum -> Tremolo -> Frame<2>  examples/electric-piano/src/main.rs:33-97 */
+    OSCEN_B200_GRAPH_SYNTH = 5,       /* README `Synth`: sine LFO -> saw PolyBLEP -> TptFilter   README.md:24-53 */
+    OSCEN_B200_GRAPH_SYNTH_ADSR = 6,  /* README `Synth` + AdsrEnvelope -> Gain(vca) (wiring of benches/static_vs_runtime.rs:57-59) */
+    OSCEN_B200_GRAPH_COUNT = 7
+};
+
+/* value-input ids (declaration order of the reference graph's `input x: value` lines) */
+enum { /* FM_VOICE, fm_voice.rs:10-48 */
+    OSCEN_B200_FM_FREQUENCY = 0, OSCEN_B200_FM_OP3_RATIO, OSCEN_B200_FM_OP3_LEVEL, OSCEN_B200_FM_OP3_FEEDBACK,
+    OSCEN_B200_FM_OP3_ATTACK, OSCEN_B200_FM_OP3_DECAY, OSCEN_B200_FM_OP3_SUSTAIN, OSCEN_B200_FM_OP3_RELEASE,
+    OSCEN_B200_FM_OP2_RATIO, OSCEN_B200_FM_OP2_LEVEL, OSCEN_B200_FM_OP2_FEEDBACK,
+    OSCEN_B200_FM_OP2_ATTACK, OSCEN_B200_FM_OP2_DECAY, OSCEN_B200_FM_OP2_SUSTAIN, OSCEN_B200_FM_OP2_RELEASE,
+    OSCEN_B200_FM_OP1_RATIO, OSCEN_B200_FM_OP1_ATTACK, OSCEN_B200_FM_OP1_DECAY, OSCEN_B200_FM_OP1_SUSTAIN,
+    OSCEN_B200_FM_OP1_RELEASE, OSCEN_B200_FM_ROUTE, OSCEN_B200_FM_FILTER_CUTOFF, OSCEN_B200_FM_FILTER_RESONANCE,
+    OSCEN_B200_FM_FILTER_ATTACK, OSCEN_B200_FM_FILTER_DECAY, OSCEN_B200_FM_FILTER_SUSTAIN,
+    OSCEN_B200_FM_FILTER_RELEASE, OSCEN_B200_FM_FILTER_ENV_AMOUNT, OSCEN_B200_FM_N_INPUTS
+};
+enum { OSCEN_B200_TWIN_CUTOFF_A = 0, OSCEN_B200_TWIN_CUTOFF_B, OSCEN_B200_TWIN_RESONANCE, OSCEN_B200_TWIN_N_INPUTS };
+enum { OSCEN_B200_SAT_FREQUENCY = 0, OSCEN_B200_SAT_AMPLITUDE, OSCEN_B200_SAT_N_INPUTS };   /* osc.frequency / osc.amplitude */
+enum { /* EPIANO: [0] per voice; [1..6] voice params; [7..8] instance (tremolo), read from the instance's first voice */
+    OSCEN_B200_EP_FREQUENCY = 0, OSCEN_B200_EP_BRIGHTNESS, OSCEN_B200_EP_VELOCITY_SCALING, OSCEN_B200_EP_DECAY_RATE,
+    OSCEN_B200_EP_HARMONIC_DECAY, OSCEN_B200_EP_KEY_SCALING, OSCEN_B200_EP_RELEASE_RATE,
+    OSCEN_B200_EP_VIBRATO_INTENSITY, OSCEN_B200_EP_VIBRATO_SPEED, OSCEN_B200_EP_N_INPUTS
+};
+enum { OSCEN_B200_SYNTH_MOD_FREQ = 0, OSCEN_B200_SYNTH_MOD_DEPTH, OSCEN_B200_SYNTH_CARRIER_FREQ, OSCEN_B200_SYNTH_CUTOFF,
+       OSCEN_B200_SYNTH_ATTACK, OSCEN_B200_SYNTH_DECAY, OSCEN_B200_SYNTH_SUSTAIN, OSCEN_B200_SYNTH_RELEASE };
+#define OSCEN_B200_MAX_INPUTS 28u
+
+/* input_id of a gate event in oscen_b200_event; any other id must be a value-input id and
+   means "set that value input of that voice at exactly that frame" (how MidiVoiceHandler's
+   `frequency` value output reaches a voice, oscen-lib/src/midi.rs:82-88,92-104) */
+#define OSCEN_B200_EVENT_GATE 0xFFFFFFFFu
+
+/* EventInstance{frame_offset, payload: Scalar(v)} addressed to one voice
+   (oscen-lib/src/graph/types.rs:133-137); gate: scalar > 0 = velocity / note on, <= 0 = off */
+typedef struct {
+    uint32_t voice;
+    uint32_t frame_offset;
+    uint32_t input_id;
+    float    scalar;
+} oscen_b200_event;
+
+/* error codes */
+enum {
+    OSCEN_B200_OK = 0,
+    OSCEN_B200_E_ARG = -1,          /* bad argument (id/range/size)                      */
+    OSCEN_B200_E_STATE = -2,        /* call not valid in this state (e.g. ramp on a non-uniform input) */
+    OSCEN_B200_E_CUDA = -3,         /* CUDA runtime error; see oscen_b200_last_error      */
+    OSCEN_B200_E_NCCL = -4,         /* NCCL error / NCCL not loadable                     */
+    OSCEN_B200_E_NOMEM = -5,
+    OSCEN_B200_E_NO_DEVICE = -6     /* no CUDA device: the engine has NO CPU fallback     */
+};
+
+/* execution plans */
+enum {
+    OSCEN_B200_PLAN_FUSED = 0,      /* one kernel per graph: whole voice in registers       */
+    OSCEN_B200_PLAN_NODES = 1       /* one kernel per node in topological order, streams in HBM, replayed as a CUDA graph */
+};
+/* output retention flags */
+enum {
+    OSCEN_B200_KEEP_VOICE_OUT = 1,     /* keep per-voice `audio_out` [frame][voice] (parity hook) */
+    OSCEN_B200_KEEP_INSTANCE_OUT = 2   /* keep per-instance `<out>_block` [frame][instance][ch]   */
+};
+
+typedef struct oscen_b200_engine oscen_b200_engine;
+
+typedef struct {
+    uint32_t graph_kind;            /* OSCEN_B200_GRAPH_*                                    */
+    uint32_t n_voices;              /* voices rendered by THIS engine (its shard)            */
+    uint32_t voices_per_instance;   /* N of `voices = [Voice::new(); N]`; divides 128        */
+    float    sample_rate;           /* G::init(sample_rate)                                  */
+    int32_t  device;                /* CUDA device ordinal                                   */
+    uint32_t plan;                  /* OSCEN_B200_PLAN_*                                     */
+    uint32_t keep;                  /* OSCEN_B200_KEEP_* flags                               */
+    uint32_t reserved;
+} oscen_b200_config;
+
+int  oscen_b200_abi_version(void);
+int  oscen_b200_device_count(void);
+
+int  oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out);
+void oscen_b200_destroy(oscen_b200_engine *e);
+const char *oscen_b200_last_error(const oscen_b200_engine *e);   /* e may be NULL: last create error */
+
+/* value inputs.  broadcast != 0: v[0] to `count` voices; else v[i] to voice first_voice+i.
+   Setting every voice to one value keeps the input "uniform" (a single ValueRampState can
+   then ramp it, as for a graph-level `[ramp: N]` input). */
+int  oscen_b200_set_value(oscen_b200_engine *e, uint32_t input_id, uint32_t first_voice, uint32_t count,
+                          const float *v, int broadcast);
+int  oscen_b200_set_value_ramp(oscen_b200_engine *e, uint32_t input_id, float target, uint32_t frames);
+
+/* events for the NEXT process_block; frame_offset >= frames of that block are dropped, more
+   than 32 events per voice per block are dropped (ArrayVec<_,32>::try_push) */
+int  oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, size_t n);
+/* raw MIDI into instance `instance`'s MidiParser -> VoiceAllocator<N> -> MidiVoiceHandler chain
+   (host-side integer logic; emits per-voice frequency + gate events) */
+int  oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame_offset,
+                          const uint8_t *bytes, uint32_t len);
+
+/* stream input block [frames][n_voices] f32 for the NEXT process_block (TWIN_PEAKS audio_in).
+   is_device != 0: `src` is a device pointer on the engine's device (no copy is made; it must
+   stay valid until process_block returns). */
+int  oscen_b200_stream_in(oscen_b200_engine *e, uint32_t input_id, const float *src, uint32_t frames,
+                          int is_device);
+/* synthetic stream input generated on device: audio_in[f][v] = U[-1,1) from a 64-bit LCG
+   seeded (seed + global_voice_index), continuing across blocks */
+int  oscen_b200_stream_in_lcg(oscen_b200_engine *e, uint32_t input_id, uint64_t seed, uint32_t voice_offset);
+
+int  oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames /* <= 512 */);
+int  oscen_b200_synchronize(oscen_b200_engine *e);
+
+/* outputs of the LAST block.  dst layouts: voice_out [frame][count]; instance_out
+   [frame][count][channels]; mix [frame][channels] (sum over this engine's instances, and over
+   all ranks once oscen_b200_comm_init was called). */
+int  oscen_b200_read_voice_out(oscen_b200_engine *e, float *dst, uint32_t first_voice, uint32_t count);
+int  oscen_b200_read_instance_out(oscen_b200_engine *e, float *dst, uint32_t first_instance, uint32_t count);
+int  oscen_b200_read_mix(oscen_b200_engine *e, float *dst);
+
+uint32_t oscen_b200_channels(const oscen_b200_engine *e);
+uint32_t oscen_b200_latency_samples(const oscen_b200_engine *e);
+uint32_t oscen_b200_n_inputs(uint32_t graph_kind);
+size_t   oscen_b200_state_bytes_per_voice(const oscen_b200_engine *e);
+/* raw SoA state download: dst[field * n_voices + voice], tests only */
+int  oscen_b200_state_download(oscen_b200_engine *e, void *dst, size_t cap);
+
+/* counters: kernels launched by this engine since create; bytes copied H2D / D2H */
+typedef struct {
+    uint64_t kernel_launches, graph_launches, h2d_bytes, d2h_bytes, blocks, events_dropped;
+} oscen_b200_stats;
+int  oscen_b200_get_stats(const oscen_b200_engine *e, oscen_b200_stats *out);
+/* device time of the last block's compute kernels, CUDA events on the engine stream (ms) */
+int  oscen_b200_last_block_ms(oscen_b200_engine *e, float *ms);
+int  oscen_b200_enable_timing(oscen_b200_engine *e, int on);
+
+/* multi-GPU: voices are sharded across ranks (one engine per GPU per process); the only
+   exchange is the mix-bus all-reduce.  id is an ncclUniqueId (128 bytes) from rank 0. */
+int  oscen_b200_comm_unique_id(void *id128);
+int  oscen_b200_comm_init(oscen_b200_engine *e, int rank, int n_ranks, const void *id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSCEN_B200_H */

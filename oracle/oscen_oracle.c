@@ -985,9 +985,9 @@ void orc_bank_destroy(orc_bank *b) {
     free(b->stream_in); free(b->voice_out); free(b->inst_out); free(b);
 }
 uint32_t orc_bank_channels(const orc_bank *b) { return b->channels; }
-/* latency_samples(): Down edges report at the source rate / factor (codegen/mod.rs:644-716);
-   SincDownFir<4> = 33 high-rate samples -> ceil(33/4) outer frames */
-uint32_t orc_bank_latency(const orc_bank *b) { return b->kind == K_SAT4 ? (33 + 3) / 4 : 0; }
+/* latency_samples(): Down edges report at the source rate / factor (codegen/emit_struct.rs:533-566);
+   SincDownFir<4> = 33 high-rate samples / factor 4 (integer division, emit_struct.rs:549-553) */
+uint32_t orc_bank_latency(const orc_bank *b) { return b->kind == K_SAT4 ? 33 / 4 : 0; }
 void orc_bank_set_threads(orc_bank *b, int n) { b->n_threads = n < 1 ? 1 : n; }
 
 int orc_bank_set_value(orc_bank *b, uint32_t id, uint32_t first, uint32_t count, const float *v, int bc) {

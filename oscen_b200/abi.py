@@ -1,0 +1,226 @@
+"""ctypes binding to the engine's C ABI (include/oscen_b200.h) — the host-side Python mirror used
+by tests and bench.py.  It never falls back to a CPU implementation: if the shared library or a
+CUDA device is missing, it raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "lib", "liboscen_b200.so")
+
+ABI_VERSION = 1
+MAX_BLOCK = 512
+EVENT_GATE = 0xFFFFFFFF
+(GRAPH_FM_VOICE, GRAPH_TWIN_PEAKS, GRAPH_SAT_1X, GRAPH_SAT_4X, GRAPH_EPIANO, GRAPH_SYNTH,
+ GRAPH_SYNTH_ADSR) = range(7)
+PLAN_FUSED, PLAN_NODES = 0, 1
+KEEP_VOICE_OUT, KEEP_INSTANCE_OUT = 1, 2
+
+# every symbol include/oscen_b200.h declares
+SYMBOLS = [
+    "oscen_b200_abi_version", "oscen_b200_device_count", "oscen_b200_create", "oscen_b200_destroy",
+    "oscen_b200_last_error", "oscen_b200_set_value", "oscen_b200_set_value_ramp", "oscen_b200_push_events",
+    "oscen_b200_push_midi", "oscen_b200_stream_in", "oscen_b200_stream_in_lcg", "oscen_b200_process_block",
+    "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
+    "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
+    "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
+    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_comm_unique_id", "oscen_b200_comm_init",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("graph_kind", C.c_uint32), ("n_voices", C.c_uint32), ("voices_per_instance", C.c_uint32),
+                ("sample_rate", C.c_float), ("device", C.c_int32), ("plan", C.c_uint32), ("keep", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class Event(C.Structure):
+    _fields_ = [("voice", C.c_uint32), ("frame_offset", C.c_uint32), ("input_id", C.c_uint32),
+                ("scalar", C.c_float)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "graph_launches", "h2d_bytes", "d2h_bytes",
+                                          "blocks", "events_dropped")]
+
+
+EVENT_DTYPE = np.dtype([("voice", "<u4"), ("frame_offset", "<u4"), ("input_id", "<u4"), ("scalar", "<f4")])
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library (built by oscen_b200.build); raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise RuntimeError(f"{LIB} is missing: run `python -m oscen_b200.build` (there is no fallback)")
+    L = C.CDLL(LIB)
+    vp, u32, f32p = C.c_void_p, C.c_uint32, C.c_void_p
+    L.oscen_b200_abi_version.restype = C.c_int
+    L.oscen_b200_device_count.restype = C.c_int
+    L.oscen_b200_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.oscen_b200_destroy.argtypes = [vp]
+    L.oscen_b200_destroy.restype = None
+    L.oscen_b200_last_error.argtypes = [vp]
+    L.oscen_b200_last_error.restype = C.c_char_p
+    L.oscen_b200_set_value.argtypes = [vp, u32, u32, u32, f32p, C.c_int]
+    L.oscen_b200_set_value_ramp.argtypes = [vp, u32, C.c_float, u32]
+    L.oscen_b200_push_events.argtypes = [vp, vp, C.c_size_t]
+    L.oscen_b200_push_midi.argtypes = [vp, u32, u32, vp, u32]
+    L.oscen_b200_stream_in.argtypes = [vp, u32, vp, u32, C.c_int]
+    L.oscen_b200_stream_in_lcg.argtypes = [vp, u32, C.c_uint64, u32]
+    L.oscen_b200_process_block.argtypes = [vp, u32]
+    L.oscen_b200_synchronize.argtypes = [vp]
+    L.oscen_b200_read_voice_out.argtypes = [vp, f32p, u32, u32]
+    L.oscen_b200_read_instance_out.argtypes = [vp, f32p, u32, u32]
+    L.oscen_b200_read_mix.argtypes = [vp, f32p]
+    L.oscen_b200_channels.argtypes = [vp]
+    L.oscen_b200_channels.restype = u32
+    L.oscen_b200_latency_samples.argtypes = [vp]
+    L.oscen_b200_latency_samples.restype = u32
+    L.oscen_b200_n_inputs.argtypes = [u32]
+    L.oscen_b200_n_inputs.restype = u32
+    L.oscen_b200_state_bytes_per_voice.argtypes = [vp]
+    L.oscen_b200_state_bytes_per_voice.restype = C.c_size_t
+    L.oscen_b200_state_download.argtypes = [vp, vp, C.c_size_t]
+    L.oscen_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.oscen_b200_last_block_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.oscen_b200_enable_timing.argtypes = [vp, C.c_int]
+    L.oscen_b200_comm_unique_id.argtypes = [vp]
+    L.oscen_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine = one GPU = one shard of voices.  Method names follow the C ABI."""
+
+    def __init__(self, graph_kind, n_voices, voices_per_instance=1, sample_rate=48000.0, device=0,
+                 plan=PLAN_FUSED, keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT):
+        self.L = load()
+        cfg = Config(graph_kind, n_voices, voices_per_instance, sample_rate, device, plan, keep, 0)
+        h = C.c_void_p()
+        rc = self.L.oscen_b200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"oscen_b200_create rc={rc}: {self.L.oscen_b200_last_error(None).decode()}")
+        self.h = h
+        self.kind, self.n_voices, self.vpi = graph_kind, n_voices, voices_per_instance
+        self.n_instances = n_voices // voices_per_instance
+        self.channels = self.L.oscen_b200_channels(h)
+        self.frames = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.oscen_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} rc={rc}: {self.L.oscen_b200_last_error(self.h).decode()}")
+
+    def set_value(self, input_id, values, first_voice=0, count=None):
+        a = np.ascontiguousarray(np.atleast_1d(np.asarray(values, dtype=np.float32)))
+        if count is None:
+            count = self.n_voices - first_voice if a.size == 1 else a.size
+        self._chk(self.L.oscen_b200_set_value(self.h, input_id, first_voice, count, a.ctypes.data,
+                                              1 if a.size == 1 else 0), "set_value")
+
+    def set_value_ramp(self, input_id, target, frames):
+        self._chk(self.L.oscen_b200_set_value_ramp(self.h, input_id, float(target), int(frames)), "set_value_ramp")
+
+    def push_events(self, events):
+        """events: structured ndarray (EVENT_DTYPE) or iterable of (voice, frame_offset, input_id, scalar)"""
+        if isinstance(events, np.ndarray) and events.dtype == EVENT_DTYPE:
+            arr = np.ascontiguousarray(events)
+        else:
+            ev = list(events)
+            if not ev:
+                return
+            arr = np.array([(int(v), int(f), int(i), float(s)) for v, f, i, s in ev], dtype=EVENT_DTYPE)
+        if arr.size:
+            self._chk(self.L.oscen_b200_push_events(self.h, arr.ctypes.data, arr.size), "push_events")
+
+    def push_midi(self, instance, frame_offset, data):
+        b = (C.c_uint8 * len(data))(*data)
+        self._chk(self.L.oscen_b200_push_midi(self.h, instance, frame_offset, b, len(data)), "push_midi")
+
+    def stream_in(self, input_id, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] == self.n_voices
+        self._chk(self.L.oscen_b200_stream_in(self.h, input_id, a.ctypes.data, a.shape[0], 0), "stream_in")
+
+    def stream_in_lcg(self, input_id, seed, voice_offset=0):
+        self._chk(self.L.oscen_b200_stream_in_lcg(self.h, input_id, seed, voice_offset), "stream_in_lcg")
+
+    def process_block(self, frames):
+        self._chk(self.L.oscen_b200_process_block(self.h, frames), "process_block")
+        self.frames = frames
+
+    def synchronize(self):
+        self._chk(self.L.oscen_b200_synchronize(self.h), "synchronize")
+
+    def read_voice_out(self, first_voice=0, count=None):
+        count = self.n_voices - first_voice if count is None else count
+        out = np.empty((self.frames, count), dtype=np.float32)
+        self._chk(self.L.oscen_b200_read_voice_out(self.h, out.ctypes.data, first_voice, count), "read_voice_out")
+        return out
+
+    def read_instance_out(self, first=0, count=None):
+        count = self.n_instances - first if count is None else count
+        out = np.empty((self.frames, count, self.channels), dtype=np.float32)
+        self._chk(self.L.oscen_b200_read_instance_out(self.h, out.ctypes.data, first, count), "read_instance_out")
+        return out
+
+    def read_mix(self, out=None):
+        if out is None:
+            out = np.empty((self.frames, self.channels), dtype=np.float32)
+        self._chk(self.L.oscen_b200_read_mix(self.h, out.ctypes.data), "read_mix")
+        return out
+
+    def latency_samples(self):
+        return self.L.oscen_b200_latency_samples(self.h)
+
+    def state_download(self):
+        nb = self.L.oscen_b200_state_bytes_per_voice(self.h)
+        out = np.empty((nb // 4, self.n_voices), dtype=np.float32)
+        self._chk(self.L.oscen_b200_state_download(self.h, out.ctypes.data, out.nbytes), "state_download")
+        return out
+
+    def stats(self):
+        s = Stats()
+        self._chk(self.L.oscen_b200_get_stats(self.h, C.byref(s)), "get_stats")
+        return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    def enable_timing(self, on=True):
+        self._chk(self.L.oscen_b200_enable_timing(self.h, 1 if on else 0), "enable_timing")
+
+    def last_block_ms(self):
+        ms = C.c_float()
+        self._chk(self.L.oscen_b200_last_block_ms(self.h, C.byref(ms)), "last_block_ms")
+        return ms.value
+
+    def comm_init(self, rank, n_ranks, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._chk(self.L.oscen_b200_comm_init(self.h, rank, n_ranks, buf), "comm_init")
+
+
+def comm_unique_id() -> bytes:
+    L = load()
+    buf = C.create_string_buffer(128)
+    rc = L.oscen_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise EngineError(f"comm_unique_id rc={rc}: {L.oscen_b200_last_error(None).decode()}")
+    return buf.raw

@@ -1,0 +1,761 @@
+/*
+ * engine.cu — the B200-native voice-batched engine behind include/oscen_b200.h.
+ *
+ * One engine = one GPU = one shard of voices.  Host side: value inputs / ramps / events / MIDI
+ * front bookkeeping that mirrors what the generated graph struct does between blocks
+ * (oscen-graph-compiler/src/codegen/mod.rs:755-976).  Device side: the fused per-graph kernels
+ * (kernel_fm.cuh, kernel_others.cuh) or the node-granular CUDA-graph plan (kernel_nodes.cuh).
+ * There is NO CPU rendering path: without a CUDA device create() fails with E_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/oscen_b200.h"
+#include "engine_types.h"
+#include "kernel_fm.cuh"
+#include "kernel_nodes.cuh"
+#include "kernel_others.cuh"
+#include "midi_front.hpp"
+
+using namespace oscen;
+
+static_assert(sizeof(Event) == sizeof(oscen_b200_event), "event layout");
+static_assert(kMaxInputs == OSCEN_B200_MAX_INPUTS, "input count");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const uint32_t kNInputs[OSCEN_B200_GRAPH_COUNT] = {28, 3, 2, 2, 9, 4, 8};
+const uint32_t kNState[OSCEN_B200_GRAPH_COUNT] = {FM_NSTATE, TW_NSTATE, SAT_NSTATE, SAT_NSTATE, EP_NSTATE, SY_NSTATE, SY_NSTATE};
+/* defaults of the reference graphs' value inputs (fm_voice.rs:10-48; nih-twin-peaks lib.rs:21-23;
+   oversampled-saturator main.rs:71; electric-piano main.rs:39-46; README.md:28-31) */
+const float kDefaults[OSCEN_B200_GRAPH_COUNT][kMaxInputs] = {
+    {440.0f, 3.0f, 0.5f, 0.0f, 0.01f, 0.1f, 0.7f, 0.3f, 2.0f, 0.5f, 0.0f, 0.01f, 0.1f, 0.7f, 0.3f,
+     1.0f, 0.01f, 0.2f, 0.8f, 0.5f, 0.0f, 2000.0f, 0.707f, 0.01f, 0.2f, 0.5f, 0.3f, 0.0f},
+    {1000.0f, 1900.0f, 0.54f},
+    {2000.0f, 0.6f},
+    {2000.0f, 0.6f},
+    {440.0f, 30.0f, 50.0f, 90.0f, 70.0f, 50.0f, 40.0f, 0.3f, 5.0f},
+    {5.0f, 0.2f, 440.0f, 1200.0f},
+    {5.0f, 0.2f, 440.0f, 1200.0f, 0.01f, 0.2f, 0.7f, 0.3f},
+};
+
+/* ValueRampState, oscen-lib/src/graph/types.rs:300-373 */
+struct Ramp {
+    float current = 0, target = 0, increment = 0;
+    uint32_t remaining = 0;
+    void set_immediate(float v) { current = v; target = v; increment = 0; remaining = 0; }
+    void set_with_ramp(float t, uint32_t frames) {
+        if (frames == 0) { set_immediate(t); return; }
+        target = t; increment = (t - current) / (float)frames; remaining = frames;
+    }
+    void tick() {
+        if (remaining > 0) {
+            remaining -= 1;
+            if (remaining == 0) { current = target; increment = 0; }
+            else current += increment;
+        }
+    }
+};
+
+/* NCCL through dlopen: single-GPU use needs no NCCL at all */
+struct Id128 { char b[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool nccl_load(std::string &err) {
+    if (g_nccl.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) { g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { err = "NCCL symbols missing"; return false; }
+    return true;
+}
+
+}  // namespace
+
+struct oscen_b200_engine {
+    oscen_b200_config cfg{};
+    uint32_t n_inputs = 0, n_state = 0, n_inst = 0, channels = 1, n_cta = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    /* value inputs */
+    float uni[kMaxInputs] = {};
+    bool uniform[kMaxInputs] = {};
+    bool ramped[kMaxInputs] = {};
+    Ramp ramps[kMaxInputs];
+    float *d_pv = nullptr;
+    float *d_ptab = nullptr, *h_ptab = nullptr;
+
+    /* state */
+    float *d_state = nullptr, *d_inst_state = nullptr;
+
+    /* events */
+    std::vector<Event> pending;
+    std::vector<uint32_t> seqs;
+    std::vector<MidiFront> midi;
+    uint32_t seq = 0;
+    Event *d_events = nullptr, *h_events = nullptr;
+    size_t events_cap = 0;
+    BlockCtl *d_ctl = nullptr, *h_ctl = nullptr;
+
+    /* stream input */
+    float *d_stream_in = nullptr;
+    size_t stream_in_cap = 0;
+    const float *stream_in_ptr = nullptr;
+    uint32_t stream_in_frames = 0;
+    bool lcg_on = false;
+    unsigned long long lcg_seed = 0;
+    uint32_t voice_offset = 0;
+
+    /* outputs */
+    float *d_voice_out = nullptr, *d_inst_out = nullptr, *d_mix_partial = nullptr, *d_mix = nullptr;
+    float *h_mix = nullptr;
+    uint32_t last_frames = 0;
+
+    /* node plan */
+    std::vector<float *> d_streams;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_kernels = 0;
+
+    /* multi-GPU */
+    void *comm = nullptr;
+    int rank = 0, n_ranks = 1;
+
+    /* stats / timing */
+    oscen_b200_stats stats{};
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+namespace {
+
+#define CK(e, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t _s = (call);                                                           \
+        if (_s != cudaSuccess) {                                                           \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_s);                 \
+            return OSCEN_B200_E_CUDA;                                                      \
+        }                                                                                  \
+    } while (0)
+
+int arg_error(oscen_b200_engine *e, const char *msg) { e->err = msg; return OSCEN_B200_E_ARG; }
+
+/* initial SoA state of one voice after G::new() + G::init(sr) */
+std::vector<uint32_t> initial_state(uint32_t kind, float sr) {
+    std::vector<float> s(kNState[kind], 0.0f);
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto adsr = [&](uint32_t base) { s[base + 0] = 0.0f; s[base + 1] = 0.0f; s[base + 2] = 0.0f; s[base + 3] = 1.0f; };
+    auto tpt = [&](uint32_t base, float cutoff, float q) {
+        TptState t; tpt_init(t, sr, cutoff, q);
+        s[base + 0] = t.z0; s[base + 1] = t.z1; s[base + 2] = t.cur_cutoff; s[base + 3] = t.cur_q;
+        s[base + 4] = t.h; s[base + 5] = t.g; s[base + 6] = t.k;
+    };
+    switch (kind) {
+    case OSCEN_B200_GRAPH_FM_VOICE:
+        adsr(FM_E3); adsr(FM_E2); adsr(FM_E1); adsr(FM_EF);
+        tpt(FM_TPT, 2000.0f, 0.707f);
+        break;
+    case OSCEN_B200_GRAPH_TWIN_PEAKS: {
+        const float cut[2] = {1000.0f, 1900.0f};
+        for (int k = 0; k < 2; ++k) {
+            Lp18State f; lp18_init(f, cut[k], 0.54f, sr);
+            const uint32_t b = k ? TW_B : TW_A;
+            s[b + 0] = f.z0; s[b + 1] = f.z1; s[b + 2] = f.z2; s[b + 3] = f.g; s[b + 4] = f.h;
+            s[b + 5] = f.last_cutoff; s[b + 6] = f.last_fmod; s[b + 7] = f.last_resonance; s[b + 8] = f.resonance;
+        }
+    } break;
+    case OSCEN_B200_GRAPH_SAT_1X: case OSCEN_B200_GRAPH_SAT_4X: break;
+    case OSCEN_B200_GRAPH_EPIANO:
+        for (int i = 0; i < 32; ++i) { s[EP_ORE + i] = 1.0f; s[EP_MRE + i] = 1.0f; }
+        s[EP_STEP] = 64.0f;
+        break;
+    default:
+        tpt(SY_TPT, 1200.0f, 0.707f);
+        adsr(SY_ENV);
+        break;
+    }
+    std::vector<uint32_t> out(s.size());
+    for (size_t i = 0; i < s.size(); ++i) out[i] = bits(s[i]);
+    /* ADSR stage/rem are integer fields: Idle(0), 0 */
+    return out;
+}
+
+int fill_row(oscen_b200_engine *e, uint32_t input, uint32_t first, uint32_t count, float value) {
+    uint32_t bits; memcpy(&bits, &value, 4);
+    const uint32_t grid = std::min<uint32_t>((count + 255) / 256, 1184);
+    fill_u32_kernel<<<grid, 256, 0, e->stream>>>((uint32_t *)(e->d_pv + (size_t)input * e->cfg.n_voices + first), count, bits);
+    e->stats.kernel_launches++;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+void fill_args(oscen_b200_engine *e, KernelArgs &a) {
+    memset(&a, 0, sizeof a);
+    a.n_voices = e->cfg.n_voices; a.vpi = e->cfg.voices_per_instance; a.n_inst = e->n_inst; a.channels = e->channels;
+    a.voice_offset = e->voice_offset; a.lcg_seed = e->lcg_seed;
+    a.state = e->d_state; a.pv = e->d_pv; a.events = e->d_events; a.ptab = e->d_ptab; a.ctl = e->d_ctl;
+    a.stream_in = e->stream_in_ptr;
+    a.voice_out = e->d_voice_out; a.inst_out = e->d_inst_out; a.inst_state = e->d_inst_state;
+    a.mix_partial = e->d_mix_partial;
+    for (uint32_t i = 0; i < kMaxInputs; ++i) a.u.p[i] = e->uni[i];
+    a.u.sr = e->cfg.sample_rate;
+    if (e->cfg.graph_kind == OSCEN_B200_GRAPH_FM_VOICE) {
+        const float *p = e->uni;
+        adsr_derive(a.u.env[0], p[I_OP3_A], p[I_OP3_D], p[I_OP3_R], a.u.sr);
+        adsr_derive(a.u.env[1], p[I_OP2_A], p[I_OP2_D], p[I_OP2_R], a.u.sr);
+        adsr_derive(a.u.env[2], p[I_OP1_A], p[I_OP1_D], p[I_OP1_R], a.u.sr);
+        adsr_derive(a.u.env[3], p[I_F_A], p[I_F_D], p[I_F_R], a.u.sr);
+    }
+}
+
+constexpr size_t kSatDyn = (kTileF * kCta + 2 * 24 * kCta) * sizeof(float);
+constexpr size_t kEpDyn = (EP_NSTATE * kCta + kTileF * kTileW + kTileF * kCta * 2) * sizeof(float);
+
+/* ---- fused plan: one graph kernel + the mix-bus reduction */
+int launch_fused(oscen_b200_engine *e, bool general) {
+    KernelArgs a; fill_args(e, a);
+    const uint32_t grid = e->n_cta;
+    switch (e->cfg.graph_kind) {
+    case OSCEN_B200_GRAPH_FM_VOICE:
+        if (general) fm_voice_kernel<true><<<grid, kCta, 0, e->stream>>>(a);
+        else fm_voice_kernel<false><<<grid, kCta, 0, e->stream>>>(a);
+        break;
+    case OSCEN_B200_GRAPH_TWIN_PEAKS: twin_peaks_kernel<<<grid, kCta, 0, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_SAT_1X: sat_kernel<1><<<grid, kCta, kSatDyn, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_SAT_4X: sat_kernel<4><<<grid, kCta, kSatDyn, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kCta, kEpDyn, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); break;
+    default: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); break;
+    }
+    e->stats.kernel_launches++;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+/* ---- node plan (FM_VOICE): the generated topological order as a launch sequence.
+   stream buffers: 0 env3 1 env2 2 env1 3 env_filter 4 filter_env_gain 5 cutoff_mod 6 op3 7 route_a
+   8 route_b 9 op2 10 mixer 11 op1 12 filter 13 output_gain */
+int launch_fm_nodes(oscen_b200_engine *e) {
+    const uint32_t grid = e->n_cta;
+    auto base = [&](uint32_t state_base) {
+        NodeArgs n{};
+        n.n_voices = e->cfg.n_voices; n.state_base = state_base; n.ctl = e->d_ctl; n.events = e->d_events;
+        n.ptab = e->d_ptab; n.pv = e->d_pv; n.state = e->d_state; n.sr = e->cfg.sample_rate;
+        for (int k = 0; k < 4; ++k) { n.pid[k] = kNoInput; n.cst[k] = 0.0f; }
+        return n;
+    };
+    float **S = e->d_streams.data();
+    auto adsr = [&](uint32_t sb, uint32_t a0, uint32_t out) {
+        NodeArgs n = base(sb); n.pid[0] = a0; n.pid[1] = a0 + 1; n.pid[2] = a0 + 2; n.pid[3] = a0 + 3; n.out0 = S[out];
+        adsr_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++;
+    };
+    adsr(FM_E3, I_OP3_A, 0); adsr(FM_E2, I_OP2_A, 1); adsr(FM_E1, I_OP1_A, 2); adsr(FM_EF, I_F_A, 3);
+    { NodeArgs n = base(0); n.in0 = S[3]; n.pid[0] = I_ENV_AMT; n.out0 = S[4];                 /* filter_env_gain */
+      ew_node_kernel<EW_GAIN><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[4]; n.pid[0] = I_CUTOFF; n.out0 = S[5];                  /* cutoff_mod */
+      ew_node_kernel<EW_ADD_VALUE><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(FM_OP3); n.in0 = nullptr; n.in1 = S[0]; n.out0 = S[6];                 /* op3_osc */
+      n.pid[0] = I_FREQ; n.pid[1] = I_OP3_RATIO; n.pid[2] = I_OP3_FB; n.pid[3] = I_OP3_LEVEL;
+      fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[6]; n.pid[0] = I_ROUTE; n.out0 = S[7]; n.out1 = S[8];     /* op3_route */
+      ew_node_kernel<EW_CROSSFADE><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(FM_OP2); n.in0 = S[7]; n.in1 = S[1]; n.out0 = S[9];                    /* op2_osc */
+      n.pid[0] = I_FREQ; n.pid[1] = I_OP2_RATIO; n.pid[2] = I_OP2_FB; n.pid[3] = I_OP2_LEVEL;
+      fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[9]; n.in1 = S[8]; n.out0 = S[10];                        /* op1_mod_mixer */
+      ew_node_kernel<EW_MIXER><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(FM_OP1); n.in0 = S[10]; n.in1 = S[2]; n.out0 = S[11];                  /* op1_osc */
+      n.pid[0] = I_FREQ; n.pid[1] = I_OP1_RATIO; n.cst[2] = 0.0f; n.cst[3] = 1.0f;            /* feedback, level unconnected */
+      fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(FM_TPT); n.in0 = S[11]; n.in1 = S[5]; n.pid[0] = I_RES; n.out0 = S[12]; /* filter */
+      tpt_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[12]; n.cst[0] = 0.3f; n.out0 = S[13];                    /* output_gain */
+      ew_node_kernel<EW_GAIN><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { KernelArgs a; fill_args(e, a); a.voice_out = nullptr;                                   /* voices.audio_out -> audio_out */
+      instance_mix_node_kernel<<<grid, kCta, 0, e->stream>>>(a, S[13]); e->stats.kernel_launches++; }
+    { const uint32_t g = 296;
+      commit_value_events_kernel<<<g, 256, 0, e->stream>>>(e->d_pv, e->d_events, e->d_ctl, e->cfg.n_voices, e->n_inputs);
+      e->stats.kernel_launches++; }
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+int launch_mix_reduce(oscen_b200_engine *e, uint32_t frames) {
+    mix_reduce_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta, e->channels, e->d_ctl);
+    (void)frames;
+    e->stats.kernel_launches++;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+/* ======================================================================== C ABI == */
+extern "C" {
+
+int oscen_b200_abi_version(void) { return OSCEN_B200_ABI_VERSION; }
+
+int oscen_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+uint32_t oscen_b200_n_inputs(uint32_t kind) { return kind < OSCEN_B200_GRAPH_COUNT ? kNInputs[kind] : 0; }
+
+const char *oscen_b200_last_error(const oscen_b200_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+void oscen_b200_destroy(oscen_b200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    for (float *p : e->d_streams) cudaFree(p);
+    cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
+    cudaFree(e->d_events); cudaFree(e->d_ctl); cudaFree(e->d_stream_in);
+    cudaFree(e->d_voice_out); cudaFree(e->d_inst_out); cudaFree(e->d_mix_partial); cudaFree(e->d_mix);
+    cudaFreeHost(e->h_ptab); cudaFreeHost(e->h_events); cudaFreeHost(e->h_ctl); cudaFreeHost(e->h_mix);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return OSCEN_B200_E_ARG; }
+    *out = nullptr;
+    if (cfg->graph_kind >= OSCEN_B200_GRAPH_COUNT || cfg->n_voices == 0 || cfg->voices_per_instance == 0 ||
+        kCta % cfg->voices_per_instance != 0 || cfg->n_voices % cfg->voices_per_instance != 0 ||
+        !(cfg->sample_rate > 0.0f) || cfg->plan > OSCEN_B200_PLAN_NODES) {
+        g_create_error = "bad config (graph kind / voices / voices_per_instance must divide 128 and n_voices / sample rate / plan)";
+        return OSCEN_B200_E_ARG;
+    }
+    if (cfg->plan == OSCEN_B200_PLAN_NODES && cfg->graph_kind != OSCEN_B200_GRAPH_FM_VOICE) {
+        g_create_error = "PLAN_NODES is implemented for GRAPH_FM_VOICE only"; return OSCEN_B200_E_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device: oscen_b200 has no CPU fallback"; return OSCEN_B200_E_NO_DEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return OSCEN_B200_E_ARG; }
+
+    oscen_b200_engine *e = new oscen_b200_engine();
+    e->cfg = *cfg;
+    const uint32_t kind = cfg->graph_kind, n = cfg->n_voices;
+    e->n_inputs = kNInputs[kind]; e->n_state = kNState[kind];
+    e->n_inst = n / cfg->voices_per_instance;
+    e->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2 : 1;
+    e->n_cta = (n + kCta - 1) / kCta;
+    int rc = [&]() -> int {
+        CK(e, cudaSetDevice(cfg->device));
+        CK(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        CK(e, cudaMalloc(&e->d_pv, (size_t)e->n_inputs * n * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
+        CK(e, cudaMallocHost(&e->h_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_state, (size_t)e->n_state * n * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_inst_state, (size_t)e->n_inst * sizeof(float)));
+        CK(e, cudaMemsetAsync(e->d_inst_state, 0, (size_t)e->n_inst * sizeof(float), e->stream));
+        CK(e, cudaMalloc(&e->d_ctl, sizeof(BlockCtl)));
+        CK(e, cudaMallocHost(&e->h_ctl, sizeof(BlockCtl)));
+        memset(e->h_ctl, 0, sizeof(BlockCtl));
+        CK(e, cudaMemcpyAsync(e->d_ctl, e->h_ctl, sizeof(BlockCtl), cudaMemcpyHostToDevice, e->stream));
+        e->events_cap = 1024;
+        CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
+        CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
+        if (cfg->keep & OSCEN_B200_KEEP_VOICE_OUT) CK(e, cudaMalloc(&e->d_voice_out, (size_t)kMaxBlock * n * sizeof(float)));
+        if (cfg->keep & OSCEN_B200_KEEP_INSTANCE_OUT) CK(e, cudaMalloc(&e->d_inst_out, (size_t)kMaxBlock * e->n_inst * e->channels * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_mix_partial, (size_t)e->n_cta * kMaxBlock * e->channels * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
+        CK(e, cudaMemsetAsync(e->d_mix, 0, (size_t)kMaxBlock * e->channels * sizeof(float), e->stream));
+        CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
+        CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1));
+        if (cfg->plan == OSCEN_B200_PLAN_NODES) {
+            e->d_streams.resize(14, nullptr);
+            for (auto &p : e->d_streams) CK(e, cudaMalloc(&p, (size_t)kMaxBlock * n * sizeof(float)));
+        }
+        CK(e, cudaFuncSetAttribute(sat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
+        CK(e, cudaFuncSetAttribute(sat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
+        CK(e, cudaFuncSetAttribute(epiano_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEpDyn));
+        /* new() + init(sr): default inputs, initial node state */
+        for (uint32_t i = 0; i < kMaxInputs; ++i) {
+            e->uni[i] = kDefaults[kind][i]; e->uniform[i] = true; e->ramped[i] = false;
+            e->ramps[i].set_immediate(e->uni[i]);
+        }
+        for (uint32_t i = 0; i < e->n_inputs; ++i) { int r = fill_row(e, i, 0, n, e->uni[i]); if (r) return r; }
+        std::vector<uint32_t> init = initial_state(kind, cfg->sample_rate);
+        uint32_t *d_init = nullptr;
+        CK(e, cudaMalloc(&d_init, init.size() * sizeof(uint32_t)));
+        CK(e, cudaMemcpyAsync(d_init, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        init_state_kernel<<<1184, 256, 0, e->stream>>>((uint32_t *)e->d_state, d_init, e->n_state, n);
+        e->stats.kernel_launches++;
+        CK(e, cudaGetLastError());
+        CK(e, cudaStreamSynchronize(e->stream));
+        cudaFree(d_init);
+        return 0;
+    }();
+    if (rc) { g_create_error = e->err; oscen_b200_destroy(e); return rc; }
+    e->midi.assign(e->n_inst, MidiFront((int)cfg->voices_per_instance));
+    *out = e;
+    return 0;
+}
+
+int oscen_b200_set_value(oscen_b200_engine *e, uint32_t id, uint32_t first, uint32_t count, const float *v, int broadcast) {
+    if (!e || !v) return OSCEN_B200_E_ARG;
+    if (id >= e->n_inputs || (uint64_t)first + count > e->cfg.n_voices || count == 0) return arg_error(e, "set_value: id/range");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const bool all = broadcast && first == 0 && count == e->cfg.n_voices;
+    if (e->ramped[id] && !all) { e->err = "set_value: a ramped input is one ValueRampState (uniform)"; return OSCEN_B200_E_STATE; }
+    if (broadcast) {
+        int r = fill_row(e, id, first, count, v[0]); if (r) return r;
+    } else {
+        /* the copy must complete before the caller's buffer goes away */
+        CK(e, cudaMemcpyAsync(e->d_pv + (size_t)id * e->cfg.n_voices + first, v, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        e->stats.h2d_bytes += (uint64_t)count * sizeof(float);
+    }
+    if (all) { e->uni[id] = v[0]; e->uniform[id] = true; e->ramps[id].set_immediate(v[0]); }
+    else e->uniform[id] = false;
+    return 0;
+}
+
+/* set_<v>_with_ramp: no-op when the target is unchanged (codegen/mod.rs:948-957) */
+int oscen_b200_set_value_ramp(oscen_b200_engine *e, uint32_t id, float target, uint32_t frames) {
+    if (!e) return OSCEN_B200_E_ARG;
+    if (id >= e->n_inputs) return arg_error(e, "set_value_ramp: id");
+    if (!e->uniform[id]) { e->err = "set_value_ramp: input is not uniform"; return OSCEN_B200_E_STATE; }
+    e->ramped[id] = true;
+    if (target != e->ramps[id].target) {
+        e->ramps[id].set_with_ramp(target, frames);
+        if (frames == 0) {                      /* set_immediate */
+            CK(e, cudaSetDevice(e->cfg.device));
+            e->uni[id] = target;
+            return fill_row(e, id, 0, e->cfg.n_voices, target);
+        }
+    }
+    return 0;
+}
+
+int oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, size_t n) {
+    if (!e || (!ev && n)) return OSCEN_B200_E_ARG;
+    for (size_t i = 0; i < n; ++i) {
+        if (ev[i].voice >= e->cfg.n_voices) return arg_error(e, "push_events: voice out of range");
+        if (ev[i].input_id != kEventGate && ev[i].input_id >= e->n_inputs) return arg_error(e, "push_events: input id");
+    }
+    for (size_t i = 0; i < n; ++i) {
+        e->pending.push_back(Event{ev[i].voice, ev[i].frame_offset, ev[i].input_id, ev[i].scalar});
+        e->seqs.push_back(e->seq++);
+    }
+    return 0;
+}
+
+int oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame_offset, const uint8_t *bytes, uint32_t len) {
+    if (!e || !bytes) return OSCEN_B200_E_ARG;
+    if (instance >= e->n_inst) return arg_error(e, "push_midi: instance out of range");
+    if (!e->midi[instance].push(frame_offset, bytes, len, e->seq++)) e->stats.events_dropped++;
+    return 0;
+}
+
+int oscen_b200_stream_in(oscen_b200_engine *e, uint32_t id, const float *src, uint32_t frames, int is_device) {
+    if (!e || !src) return OSCEN_B200_E_ARG;
+    if (e->cfg.graph_kind != OSCEN_B200_GRAPH_TWIN_PEAKS || id != 0 || frames == 0 || frames > kMaxBlock)
+        return arg_error(e, "stream_in: only TWIN_PEAKS audio_in (id 0), frames <= 512");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t nfl = (size_t)frames * e->cfg.n_voices;
+    if (is_device) {
+        e->stream_in_ptr = src;
+    } else {
+        if (e->stream_in_cap < nfl) {
+            CK(e, cudaStreamSynchronize(e->stream));
+            cudaFree(e->d_stream_in); e->d_stream_in = nullptr;
+            CK(e, cudaMalloc(&e->d_stream_in, nfl * sizeof(float)));
+            e->stream_in_cap = nfl;
+        }
+        CK(e, cudaMemcpyAsync(e->d_stream_in, src, nfl * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        e->stats.h2d_bytes += nfl * sizeof(float);
+        e->stream_in_ptr = e->d_stream_in;
+    }
+    e->stream_in_frames = frames;
+    e->lcg_on = false;
+    return 0;
+}
+
+__global__ void lcg_seed_kernel(float *state, uint32_t n, unsigned long long seed, uint32_t voice_offset) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const unsigned long long s = lcg_seed_state(seed + (unsigned long long)(voice_offset + v));
+    state[(size_t)(TW_LCG + 0) * n + v] = __uint_as_float((uint32_t)(s & 0xffffffffull));
+    state[(size_t)(TW_LCG + 1) * n + v] = __uint_as_float((uint32_t)(s >> 32));
+}
+
+int oscen_b200_stream_in_lcg(oscen_b200_engine *e, uint32_t id, uint64_t seed, uint32_t voice_offset) {
+    if (!e) return OSCEN_B200_E_ARG;
+    if (e->cfg.graph_kind != OSCEN_B200_GRAPH_TWIN_PEAKS || id != 0) return arg_error(e, "stream_in_lcg: only TWIN_PEAKS audio_in");
+    CK(e, cudaSetDevice(e->cfg.device));
+    e->lcg_seed = seed; e->voice_offset = voice_offset; e->lcg_on = true;
+    lcg_seed_kernel<<<(e->cfg.n_voices + 255) / 256, 256, 0, e->stream>>>(e->d_state, e->cfg.n_voices, seed, voice_offset);
+    e->stats.kernel_launches++;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
+    if (!e) return OSCEN_B200_E_ARG;
+    if (frames == 0 || frames > kMaxBlock) return arg_error(e, "process_block: frames must be 1..512");
+    const uint32_t kind = e->cfg.graph_kind, n = e->cfg.n_voices, vpi = e->cfg.voices_per_instance;
+    if (kind == OSCEN_B200_GRAPH_TWIN_PEAKS && !e->lcg_on && e->stream_in_ptr && e->stream_in_frames < frames)
+        return arg_error(e, "process_block: stream_in block shorter than frames");
+    CK(e, cudaSetDevice(e->cfg.device));
+
+    /* ---- MIDI front -> per-voice events */
+    std::vector<VoiceEvent> ve;
+    for (uint32_t i = 0; i < e->n_inst; ++i) {
+        if (e->midi[i].pending.empty()) continue;
+        ve.clear();
+        e->midi[i].run(frames, ve);
+        for (const VoiceEvent &x : ve) {
+            e->pending.push_back(Event{i * vpi + x.voice_in_instance, x.frame, x.is_gate ? kEventGate : 0u, x.value});
+            e->seqs.push_back(e->seq++);
+        }
+    }
+    /* ---- stage events: drop those beyond the block; cap 32 gate events per voice; sort */
+    std::vector<uint32_t> order;
+    order.reserve(e->pending.size());
+    for (uint32_t i = 0; i < e->pending.size(); ++i) {
+        if (e->pending[i].frame < frames) order.push_back(i); else e->stats.events_dropped++;
+    }
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        const Event &a = e->pending[x], &b = e->pending[y];
+        if (a.voice != b.voice) return a.voice < b.voice;
+        if (a.frame != b.frame) return a.frame < b.frame;
+        return e->seqs[x] < e->seqs[y];
+    });
+    uint32_t n_ev = 0;
+    bool general = false;
+    {
+        if (order.size() > e->events_cap) {
+            CK(e, cudaStreamSynchronize(e->stream));
+            cudaFree(e->d_events); cudaFreeHost(e->h_events);
+            e->events_cap = order.size() * 2;
+            CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
+            CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        }
+        /* the pinned staging buffer may still be in flight from the previous block */
+        if (!order.empty()) CK(e, cudaStreamSynchronize(e->stream));
+        uint32_t cur_voice = 0xFFFFFFFFu, gates = 0;
+        for (uint32_t idx : order) {
+            const Event &x = e->pending[idx];
+            if (x.voice != cur_voice) { cur_voice = x.voice; gates = 0; }
+            if (x.input_id == kEventGate) {
+                if (gates >= OSCEN_B200_MAX_EVENTS_PER_ENDPOINT) { e->stats.events_dropped++; continue; }
+                ++gates;
+            } else if (x.input_id != 0u || kind != OSCEN_B200_GRAPH_FM_VOICE) {
+                general = true;
+            }
+            if (x.input_id != kEventGate) e->uniform[x.input_id] = false;
+            e->h_events[n_ev++] = x;
+        }
+    }
+    e->pending.clear(); e->seqs.clear();
+
+    /* ---- ramps: tick_ramps() once per frame (codegen/mod.rs:878-914) */
+    uint32_t ramp_mask = 0;
+    for (uint32_t i = 0; i < e->n_inputs; ++i)
+        if (e->ramped[i] && e->ramps[i].remaining > 0) ramp_mask |= 1u << i;
+    if (ramp_mask) {
+        CK(e, cudaStreamSynchronize(e->stream));
+        for (uint32_t f = 0; f < frames; ++f)
+            for (uint32_t i = 0; i < e->n_inputs; ++i) if ((ramp_mask >> i) & 1u) {
+                e->ramps[i].tick();
+                e->h_ptab[(size_t)f * kMaxInputs + i] = e->ramps[i].current;
+            }
+        CK(e, cudaMemcpyAsync(e->d_ptab, e->h_ptab, (size_t)frames * kMaxInputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += (uint64_t)frames * kMaxInputs * sizeof(float);
+        general = true;
+    }
+    for (uint32_t i = 1; i < e->n_inputs; ++i) if (!e->uniform[i]) general = true;
+    if (kind != OSCEN_B200_GRAPH_FM_VOICE) general = true;
+
+    /* ---- per-block control + events to the device */
+    e->h_ctl->frames = frames; e->h_ctl->n_events = n_ev; e->h_ctl->ramp_mask = ramp_mask; e->h_ctl->lcg_on = e->lcg_on ? 1u : 0u;
+    if (n_ev) {
+        CK(e, cudaMemcpyAsync(e->d_events, e->h_events, (size_t)n_ev * sizeof(Event), cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += (uint64_t)n_ev * sizeof(Event);
+    }
+    {
+        /* BlockCtl is tiny: copy by value through a kernel-parameter-free memcpy from pageable-safe staging */
+        BlockCtl ctl = *e->h_ctl;
+        CK(e, cudaMemcpyAsync(e->d_ctl, &ctl, sizeof ctl, cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += sizeof ctl;
+    }
+
+    if (e->timing) CK(e, cudaEventRecord(e->ev0, e->stream));
+    int rc = 0;
+    if (e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
+        rc = launch_fused(e, general); if (rc) return rc;
+        rc = launch_mix_reduce(e, frames); if (rc) return rc;
+    } else {
+        /* the launch sequence is captured once and replayed: per-block words live in BlockCtl */
+        if (!e->graph_exec) {
+            cudaGraph_t g = nullptr;
+            CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            const uint64_t before = e->stats.kernel_launches;
+            rc = launch_fm_nodes(e);
+            if (!rc) rc = launch_mix_reduce(e, frames);
+            cudaError_t s = cudaStreamEndCapture(e->stream, &g);
+            e->graph_kernels = e->stats.kernel_launches - before;
+            e->stats.kernel_launches = before;
+            if (rc) return rc;
+            CK(e, s);
+            CK(e, cudaGraphInstantiate(&e->graph_exec, g, 0));
+            cudaGraphDestroy(g);
+        }
+        CK(e, cudaGraphLaunch(e->graph_exec, e->stream));
+        e->stats.graph_launches++;
+        e->stats.kernel_launches += e->graph_kernels;
+    }
+    if (e->comm) {
+        const int r = g_nccl.AllReduce(e->d_mix, e->d_mix, (size_t)frames * e->channels, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, e->stream);
+        if (r != 0) { e->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return OSCEN_B200_E_NCCL; }
+    }
+    if (e->timing) { CK(e, cudaEventRecord(e->ev1, e->stream)); e->ev_valid = true; }
+    /* ramp-driven inputs end the block at their last per-frame value */
+    if (ramp_mask) {
+        for (uint32_t i = 0; i < e->n_inputs; ++i) if ((ramp_mask >> i) & 1u) {
+            e->uni[i] = e->ramps[i].current;
+            rc = fill_row(e, i, 0, n, e->uni[i]); if (rc) return rc;
+        }
+    }
+    e->last_frames = frames;
+    e->stats.blocks++;
+    return 0;
+}
+
+int oscen_b200_synchronize(oscen_b200_engine *e) {
+    if (!e) return OSCEN_B200_E_ARG;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int oscen_b200_read_voice_out(oscen_b200_engine *e, float *dst, uint32_t first, uint32_t count) {
+    if (!e || !dst) return OSCEN_B200_E_ARG;
+    const float *src = e->cfg.plan == OSCEN_B200_PLAN_NODES ? e->d_streams[13] : e->d_voice_out;
+    if (!src) { e->err = "read_voice_out: engine created without KEEP_VOICE_OUT"; return OSCEN_B200_E_STATE; }
+    if ((uint64_t)first + count > e->cfg.n_voices || count == 0) return arg_error(e, "read_voice_out: range");
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaMemcpy2DAsync(dst, (size_t)count * sizeof(float), src + first, (size_t)e->cfg.n_voices * sizeof(float),
+                            (size_t)count * sizeof(float), e->last_frames, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->stats.d2h_bytes += (uint64_t)count * e->last_frames * sizeof(float);
+    return 0;
+}
+
+int oscen_b200_read_instance_out(oscen_b200_engine *e, float *dst, uint32_t first, uint32_t count) {
+    if (!e || !dst) return OSCEN_B200_E_ARG;
+    if (!e->d_inst_out) { e->err = "read_instance_out: engine created without KEEP_INSTANCE_OUT"; return OSCEN_B200_E_STATE; }
+    if ((uint64_t)first + count > e->n_inst || count == 0) return arg_error(e, "read_instance_out: range");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t ch = e->channels;
+    CK(e, cudaMemcpy2DAsync(dst, (size_t)count * ch * sizeof(float), e->d_inst_out + (size_t)first * ch,
+                            (size_t)e->n_inst * ch * sizeof(float), (size_t)count * ch * sizeof(float), e->last_frames,
+                            cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->stats.d2h_bytes += (uint64_t)count * ch * e->last_frames * sizeof(float);
+    return 0;
+}
+
+int oscen_b200_read_mix(oscen_b200_engine *e, float *dst) {
+    if (!e || !dst) return OSCEN_B200_E_ARG;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t bytes = (size_t)e->last_frames * e->channels * sizeof(float);
+    CK(e, cudaMemcpyAsync(e->h_mix, e->d_mix, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    memcpy(dst, e->h_mix, bytes);
+    e->stats.d2h_bytes += bytes;
+    return 0;
+}
+
+uint32_t oscen_b200_channels(const oscen_b200_engine *e) { return e ? e->channels : 0; }
+
+/* latency_samples(): sum over Down edges of kernel latency / factor
+   (codegen/emit_struct.rs:533-566); SincDownFir<4> reports 33 high-rate samples */
+uint32_t oscen_b200_latency_samples(const oscen_b200_engine *e) {
+    return (e && e->cfg.graph_kind == OSCEN_B200_GRAPH_SAT_4X) ? 33u / 4u : 0u;
+}
+
+size_t oscen_b200_state_bytes_per_voice(const oscen_b200_engine *e) { return e ? (size_t)e->n_state * sizeof(float) : 0; }
+
+int oscen_b200_state_download(oscen_b200_engine *e, void *dst, size_t cap) {
+    if (!e || !dst) return OSCEN_B200_E_ARG;
+    const size_t bytes = (size_t)e->n_state * e->cfg.n_voices * sizeof(float);
+    if (cap < bytes) return arg_error(e, "state_download: buffer too small");
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaMemcpyAsync(dst, e->d_state, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->stats.d2h_bytes += bytes;
+    return 0;
+}
+
+int oscen_b200_get_stats(const oscen_b200_engine *e, oscen_b200_stats *out) {
+    if (!e || !out) return OSCEN_B200_E_ARG;
+    *out = e->stats;
+    return 0;
+}
+
+int oscen_b200_enable_timing(oscen_b200_engine *e, int on) { if (!e) return OSCEN_B200_E_ARG; e->timing = on != 0; e->ev_valid = false; return 0; }
+
+int oscen_b200_last_block_ms(oscen_b200_engine *e, float *ms) {
+    if (!e || !ms) return OSCEN_B200_E_ARG;
+    if (!e->ev_valid) { e->err = "last_block_ms: timing not enabled"; return OSCEN_B200_E_STATE; }
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaEventSynchronize(e->ev1));
+    CK(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return 0;
+}
+
+int oscen_b200_comm_unique_id(void *id128) {
+    std::string err;
+    if (!id128) return OSCEN_B200_E_ARG;
+    if (!nccl_load(err)) { g_create_error = err; return OSCEN_B200_E_NCCL; }
+    const int r = g_nccl.GetUniqueId(id128);
+    if (r != 0) { g_create_error = "ncclGetUniqueId failed"; return OSCEN_B200_E_NCCL; }
+    return 0;
+}
+
+int oscen_b200_comm_init(oscen_b200_engine *e, int rank, int n_ranks, const void *id128) {
+    if (!e || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return OSCEN_B200_E_ARG;
+    if (!nccl_load(e->err)) return OSCEN_B200_E_NCCL;
+    CK(e, cudaSetDevice(e->cfg.device));
+    Id128 id; memcpy(&id, id128, sizeof id);
+    const int r = g_nccl.CommInitRank(&e->comm, n_ranks, id, rank);
+    if (r != 0) { e->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); e->comm = nullptr; return OSCEN_B200_E_NCCL; }
+    e->rank = rank; e->n_ranks = n_ranks;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    return 0;
+}
+
+}  /* extern "C" */

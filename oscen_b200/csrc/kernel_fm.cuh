@@ -1,0 +1,179 @@
+/*
+ * kernel_fm.cuh — FMVoice (examples/fm-synth/src/fm_voice.rs:6-156) as ONE kernel:
+ * one thread renders one voice for the whole block with all 14 nodes' state in registers,
+ * walking the nodes in the generated topological order:
+ *   env3, env2, env1, env_filter, filter_env_gain, cutoff_mod, op3_osc, op3_route, op2_osc,
+ *   op1_mod_mixer, op1_osc, filter, output_gain.
+ * HBM traffic per block: state (29 words) in + out, the per-voice frequency, and whatever
+ * outputs the engine was asked to keep.
+ *
+ * GENERAL=false: every value input except `frequency` is uniform and constant over the block
+ *   (uniform values and the ADSR step data come from the kernel-argument constant bank).
+ * GENERAL=true : any input may be per-voice, ramped per frame (ptab) or set by a value event.
+ */
+#pragma once
+#include "kernels_common.cuh"
+
+namespace oscen {
+
+enum : uint32_t {   /* == OSCEN_B200_FM_* */
+    I_FREQ = 0, I_OP3_RATIO, I_OP3_LEVEL, I_OP3_FB, I_OP3_A, I_OP3_D, I_OP3_S, I_OP3_R,
+    I_OP2_RATIO, I_OP2_LEVEL, I_OP2_FB, I_OP2_A, I_OP2_D, I_OP2_S, I_OP2_R,
+    I_OP1_RATIO, I_OP1_A, I_OP1_D, I_OP1_S, I_OP1_R, I_ROUTE,
+    I_CUTOFF, I_RES, I_F_A, I_F_D, I_F_S, I_F_R, I_ENV_AMT, I_FM_N
+};
+
+OSC_D void adsr_load(AdsrState &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
+    s.stage = __float_as_uint(st[(size_t)(base + 0) * n + v]);
+    s.rem = __float_as_uint(st[(size_t)(base + 1) * n + v]);
+    s.level = st[(size_t)(base + 2) * n + v];
+    s.vel = st[(size_t)(base + 3) * n + v];
+}
+OSC_D void adsr_store(const AdsrState &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
+    st[(size_t)(base + 0) * n + v] = __uint_as_float(s.stage);
+    st[(size_t)(base + 1) * n + v] = __uint_as_float(s.rem);
+    st[(size_t)(base + 2) * n + v] = s.level;
+    st[(size_t)(base + 3) * n + v] = s.vel;
+}
+OSC_D void tpt_load(TptState &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
+    s.z0 = st[(size_t)(base + 0) * n + v]; s.z1 = st[(size_t)(base + 1) * n + v];
+    s.cur_cutoff = st[(size_t)(base + 2) * n + v]; s.cur_q = st[(size_t)(base + 3) * n + v];
+    s.h = st[(size_t)(base + 4) * n + v]; s.g = st[(size_t)(base + 5) * n + v];
+    s.k = st[(size_t)(base + 6) * n + v];
+}
+OSC_D void tpt_store(const TptState &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
+    st[(size_t)(base + 0) * n + v] = s.z0; st[(size_t)(base + 1) * n + v] = s.z1;
+    st[(size_t)(base + 2) * n + v] = s.cur_cutoff; st[(size_t)(base + 3) * n + v] = s.cur_q;
+    st[(size_t)(base + 4) * n + v] = s.h; st[(size_t)(base + 5) * n + v] = s.g;
+    st[(size_t)(base + 6) * n + v] = s.k;
+}
+
+template <bool GENERAL>
+__global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ KernelArgs a) {
+    __shared__ float tile[kTileF * kTileW];
+    __shared__ float isum[kTileF * kCta];
+
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * kCta + threadIdx.x;
+    const bool active = v < n;
+    const uint32_t vs = active ? v : 0u;
+    const uint32_t frames = a.ctl->frames;
+    const uint32_t ramp_mask = GENERAL ? a.ctl->ramp_mask : 0u;
+    const float sr = a.u.sr;
+    const uint32_t col = tile_col(threadIdx.x, a.vpi);
+
+    /* ---- value inputs */
+    float P[I_FM_N];
+#pragma unroll
+    for (uint32_t i = 0; i < I_FM_N; ++i) P[i] = GENERAL ? a.pv[(size_t)i * n + vs] : a.u.p[i];
+    if (!GENERAL) P[I_FREQ] = a.pv[vs];
+
+    /* ---- state */
+    AdsrState e3, e2, e1, ef;
+    adsr_load(e3, a.state, FM_E3, n, vs); adsr_load(e2, a.state, FM_E2, n, vs);
+    adsr_load(e1, a.state, FM_E1, n, vs); adsr_load(ef, a.state, FM_EF, n, vs);
+    FmOpState op3, op2, op1;
+    op3.phase = a.state[(size_t)(FM_OP3 + 0) * n + vs]; op3.prev = a.state[(size_t)(FM_OP3 + 1) * n + vs];
+    op2.phase = a.state[(size_t)(FM_OP2 + 0) * n + vs]; op2.prev = a.state[(size_t)(FM_OP2 + 1) * n + vs];
+    op1.phase = a.state[(size_t)(FM_OP1 + 0) * n + vs]; op1.prev = a.state[(size_t)(FM_OP1 + 1) * n + vs];
+    fmop_reset_cache(op3); fmop_reset_cache(op2); fmop_reset_cache(op1);
+    TptState tp;
+    tpt_load(tp, a.state, FM_TPT, n, vs);
+
+    AdsrDerived d3, d2, d1, df;
+    if (GENERAL) {
+        adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
+        adsr_derive(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
+        adsr_derive(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
+        adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
+    } else {
+        d3 = a.u.env[0]; d2 = a.u.env[1]; d1 = a.u.env[2]; df = a.u.env[3];
+    }
+
+    EventCursor ec;
+    ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+
+    for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
+        const uint32_t fe = min(kTileF, frames - f0);
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const uint32_t f = f0 + ff;
+            float y = 0.0f;
+            if (active) {
+                if (GENERAL && ramp_mask) {               /* ramped inputs read `.current` */
+                    const float *row = a.ptab + (size_t)f * kMaxInputs;
+#pragma unroll
+                    for (uint32_t i = 0; i < I_FM_N; ++i)
+                        if ((ramp_mask >> i) & 1u) P[i] = row[i];
+                }
+                if (ec.due(f)) {
+                    const uint32_t j = ec.end_of_frame(f);
+                    /* value edges are assigned before process_event_inputs() */
+                    for (uint32_t k = ec.i; k < j; ++k) {
+                        const Event e = ec.ev[k];
+                        if (e.input_id != kEventGate) {
+                            if (GENERAL) {
+#pragma unroll
+                                for (uint32_t i = 0; i < I_FM_N; ++i) if (e.input_id == i) P[i] = e.scalar;
+                            } else {
+                                P[I_FREQ] = e.scalar;       /* host guarantees id == frequency */
+                            }
+                            a.pv[(size_t)e.input_id * n + v] = e.scalar;
+                        }
+                    }
+                    if (GENERAL) {
+                        if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
+                        if (adsr_derived_stale(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R])) adsr_derive(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
+                        if (adsr_derived_stale(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R])) adsr_derive(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
+                        if (adsr_derived_stale(df, P[I_F_A], P[I_F_D], P[I_F_R])) adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
+                    }
+                    for (uint32_t k = ec.i; k < j; ++k) {
+                        const Event e = ec.ev[k];
+                        if (e.input_id == kEventGate) {   /* gate -> env3, env2, env1, env_filter */
+                            adsr_on_gate(e3, e.scalar, P[I_OP3_A], P[I_OP3_R], d3);
+                            adsr_on_gate(e2, e.scalar, P[I_OP2_A], P[I_OP2_R], d2);
+                            adsr_on_gate(e1, e.scalar, P[I_OP1_A], P[I_OP1_R], d1);
+                            adsr_on_gate(ef, e.scalar, P[I_F_A], P[I_F_R], df);
+                        }
+                    }
+                    ec.advance(j);
+                } else if (GENERAL && ramp_mask) {
+                    if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
+                    if (adsr_derived_stale(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R])) adsr_derive(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
+                    if (adsr_derived_stale(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R])) adsr_derive(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
+                    if (adsr_derived_stale(df, P[I_F_A], P[I_F_D], P[I_F_R])) adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
+                }
+
+                /* ---- the walk (one frame) */
+                const float env3 = adsr_process(e3, P[I_OP3_S], d3);
+                const float env2 = adsr_process(e2, P[I_OP2_S], d2);
+                const float env1 = adsr_process(e1, P[I_OP1_S], d1);
+                const float envf = adsr_process(ef, P[I_F_S], df);
+                const float feg = envf * P[I_ENV_AMT];                 /* filter_env_gain: Gain */
+                const float cutoff = feg + P[I_CUTOFF];                /* cutoff_mod: AddValue  */
+                const float o3 = fmop_process(op3, P[I_FREQ], P[I_OP3_RATIO], 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL], sr);
+                const float mix = clampf(P[I_ROUTE], 0.0f, 1.0f);      /* op3_route: Crossfade  */
+                const float xa = o3 * (1.0f - mix);
+                const float xb = o3 * mix;
+                const float o2 = fmop_process(op2, P[I_FREQ], P[I_OP2_RATIO], xa, P[I_OP2_FB], env2, P[I_OP2_LEVEL], sr);
+                const float pm1 = o2 + xb;                             /* op1_mod_mixer: Mixer  */
+                const float o1 = fmop_process(op1, P[I_FREQ], P[I_OP1_RATIO], pm1, 0.0f, env1, 1.0f, sr);
+                const float lp = tpt_process(tp, o1, cutoff, P[I_RES], 0.0f, sr);
+                y = lp * 0.3f;                                         /* output_gain: Gain(0.3) */
+                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
+            }
+            tile[ff * kTileW + col] = y;
+        }
+        tile_flush_mono(a, tile, isum, f0, fe);
+    }
+
+    if (active) {
+        adsr_store(e3, a.state, FM_E3, n, v); adsr_store(e2, a.state, FM_E2, n, v);
+        adsr_store(e1, a.state, FM_E1, n, v); adsr_store(ef, a.state, FM_EF, n, v);
+        a.state[(size_t)(FM_OP3 + 0) * n + v] = op3.phase; a.state[(size_t)(FM_OP3 + 1) * n + v] = op3.prev;
+        a.state[(size_t)(FM_OP2 + 0) * n + v] = op2.phase; a.state[(size_t)(FM_OP2 + 1) * n + v] = op2.prev;
+        a.state[(size_t)(FM_OP1 + 0) * n + v] = op1.phase; a.state[(size_t)(FM_OP1 + 1) * n + v] = op1.prev;
+        tpt_store(tp, a.state, FM_TPT, n, v);
+    }
+}
+
+}  // namespace oscen

@@ -1,0 +1,419 @@
+/*
+ * kernel_others.cuh — fused one-thread-per-voice kernels for the other reference graphs on
+ * the hot path: TwinPeaksGraph, SatGraph_{1x,4x}, README Synth (+ADSR), ElectricPiano.
+ * Same structure as kernel_fm.cuh; value inputs are always read per voice (few inputs).
+ */
+#pragma once
+#include "kernels_common.cuh"
+#include "kernel_fm.cuh"
+
+namespace oscen {
+
+/* shared prologue for the small graphs: load NP per-voice inputs, apply ramps / value events */
+template <uint32_t NP>
+struct SmallParams {
+    float P[NP];
+    OSC_D void load(const KernelArgs &a, uint32_t vs) {
+#pragma unroll
+        for (uint32_t i = 0; i < NP; ++i) P[i] = a.pv[(size_t)i * a.n_voices + vs];
+    }
+    OSC_D void ramps(const KernelArgs &a, uint32_t ramp_mask, uint32_t f) {
+        if (ramp_mask) {
+            const float *row = a.ptab + (size_t)f * kMaxInputs;
+#pragma unroll
+            for (uint32_t i = 0; i < NP; ++i) if ((ramp_mask >> i) & 1u) P[i] = row[i];
+        }
+    }
+    OSC_D void value_event(const KernelArgs &a, const Event &e, uint32_t v) {
+#pragma unroll
+        for (uint32_t i = 0; i < NP; ++i) if (e.input_id == i) P[i] = e.scalar;
+        if (e.input_id < NP) a.pv[(size_t)e.input_id * a.n_voices + v] = e.scalar;
+    }
+};
+
+/* 64-bit LCG noise of oscen-lib/tests/realtime_safety.rs:21-33 */
+OSC_HD unsigned long long lcg_seed_state(unsigned long long seed) {
+    return seed * 2862933555777941757ull + 3037000493ull;
+}
+OSC_HD float lcg_next(unsigned long long &state) {
+    state = state * 6364136223846793005ull + 1442695040888963407ull;
+    return (float)(uint32_t)(state >> 33) / 2147483648.0f - 1.0f;
+}
+
+/* ============================================================== TwinPeaksGraph ==== */
+/* examples/nih-twin-peaks/src/lib.rs:15-48: audio_in -> filter_a, filter_b; out = a - b */
+OSC_D void lp18_load(Lp18State &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
+    s.z0 = st[(size_t)(base + 0) * n + v]; s.z1 = st[(size_t)(base + 1) * n + v];
+    s.z2 = st[(size_t)(base + 2) * n + v]; s.g = st[(size_t)(base + 3) * n + v];
+    s.h = st[(size_t)(base + 4) * n + v]; s.last_cutoff = st[(size_t)(base + 5) * n + v];
+    s.last_fmod = st[(size_t)(base + 6) * n + v]; s.last_resonance = st[(size_t)(base + 7) * n + v];
+    s.resonance = st[(size_t)(base + 8) * n + v];
+}
+OSC_D void lp18_store(const Lp18State &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
+    st[(size_t)(base + 0) * n + v] = s.z0; st[(size_t)(base + 1) * n + v] = s.z1;
+    st[(size_t)(base + 2) * n + v] = s.z2; st[(size_t)(base + 3) * n + v] = s.g;
+    st[(size_t)(base + 4) * n + v] = s.h; st[(size_t)(base + 5) * n + v] = s.last_cutoff;
+    st[(size_t)(base + 6) * n + v] = s.last_fmod; st[(size_t)(base + 7) * n + v] = s.last_resonance;
+    st[(size_t)(base + 8) * n + v] = s.resonance;
+}
+
+__global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant__ KernelArgs a) {
+    __shared__ float tile[kTileF * kTileW];
+    __shared__ float isum[kTileF * kCta];
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * kCta + threadIdx.x;
+    const bool active = v < n;
+    const uint32_t vs = active ? v : 0u;
+    const uint32_t frames = a.ctl->frames, ramp_mask = a.ctl->ramp_mask;
+    const bool lcg_on = a.ctl->lcg_on != 0u;
+    const float sr = a.u.sr;
+    const uint32_t col = tile_col(threadIdx.x, a.vpi);
+
+    SmallParams<3> prm; prm.load(a, vs);
+    Lp18State fa, fb;
+    lp18_load(fa, a.state, TW_A, n, vs); lp18_load(fb, a.state, TW_B, n, vs);
+    unsigned long long lcg = (unsigned long long)__float_as_uint(a.state[(size_t)(TW_LCG + 0) * n + vs]) |
+                             ((unsigned long long)__float_as_uint(a.state[(size_t)(TW_LCG + 1) * n + vs]) << 32);
+    EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+
+    for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
+        const uint32_t fe = min(kTileF, frames - f0);
+        for (uint32_t g0 = 0; g0 < fe; g0 += 8) {
+            float xin[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {            /* 8 independent loads in flight */
+                const uint32_t f = f0 + g0 + k;
+                xin[k] = (active && !lcg_on && a.stream_in != nullptr && g0 + k < fe)
+                             ? __ldg(a.stream_in + (size_t)f * n + v) : 0.0f;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t ff = g0 + k, f = f0 + ff;
+                if (ff < fe) {
+                    float y = 0.0f;
+                    if (active) {
+                        prm.ramps(a, ramp_mask, f);
+                        if (ec.due(f)) {
+                            const uint32_t j = ec.end_of_frame(f);
+                            for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
+                            ec.advance(j);
+                        }
+                        const float x = lcg_on ? lcg_next(lcg) : xin[k];
+                        const float ya = lp18_process(fa, x, prm.P[0], 0.0f, prm.P[2], sr);
+                        const float yb = lp18_process(fb, x, prm.P[1], 0.0f, prm.P[2], sr);
+                        y = ya - yb;
+                        if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
+                    }
+                    tile[ff * kTileW + col] = y;
+                }
+            }
+        }
+        tile_flush_mono(a, tile, isum, f0, fe);
+    }
+    if (active) {
+        lp18_store(fa, a.state, TW_A, n, v); lp18_store(fb, a.state, TW_B, n, v);
+        a.state[(size_t)(TW_LCG + 0) * n + v] = __uint_as_float((uint32_t)(lcg & 0xffffffffull));
+        a.state[(size_t)(TW_LCG + 1) * n + v] = __uint_as_float((uint32_t)(lcg >> 32));
+    }
+}
+
+/* ============================================================== SatGraph_{1x,4x} === */
+/* examples/oversampled-saturator/src/main.rs:64-80; multirate body codegen/emit_frame.rs:114-176 */
+template <int FACTOR>
+__global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ KernelArgs a) {
+    __shared__ float tile[kTileF * kTileW];
+    extern __shared__ float dyn[];                         /* isum [32*128] | h1 [24*128] | h2 [24*128] */
+    float *isum = dyn;
+    float *h1 = dyn + kTileF * kCta + threadIdx.x;
+    float *h2 = h1 + 24 * kCta;
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * kCta + threadIdx.x;
+    const bool active = v < n;
+    const uint32_t vs = active ? v : 0u;
+    const uint32_t frames = a.ctl->frames, ramp_mask = a.ctl->ramp_mask;
+    const float sr_inner = a.u.sr * (float)FACTOR;         /* `* N` nodes: sample_rate * N */
+    const uint32_t col = tile_col(threadIdx.x, a.vpi);
+
+    SmallParams<2> prm; prm.load(a, vs);
+    float phase = a.state[(size_t)SAT_PHASE * n + vs];
+    uint32_t head1 = 23u, head2 = 23u;                     /* chronological order, newest last */
+    if (FACTOR == 4) {
+        for (uint32_t i = 0; i < 24; ++i) {
+            h1[i * kCta] = a.state[(size_t)(SAT_H1 + i) * n + vs];
+            h2[i * kCta] = a.state[(size_t)(SAT_H2 + i) * n + vs];
+        }
+    }
+    EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+
+    for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
+        const uint32_t fe = min(kTileF, frames - f0);
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const uint32_t f = f0 + ff;
+            float y = 0.0f;
+            if (active) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) {
+                    const uint32_t j = ec.end_of_frame(f);
+                    for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
+                    ec.advance(j);
+                }
+                if (FACTOR == 1) {
+                    const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
+                    y = hardclip_process(o);
+                } else {
+                    float buf[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
+                        buf[i] = hardclip_process(o);
+                    }
+                    /* SincDownFir<4>::downsample: stage 0 twice, stage 1 once (sinc_fir.rs:233-249) */
+                    const float s0 = hb_down_step(h1, kCta, head1, buf[0], buf[1]);
+                    const float s1 = hb_down_step(h1, kCta, head1, buf[2], buf[3]);
+                    y = hb_down_step(h2, kCta, head2, s0, s1);
+                }
+                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
+            }
+            tile[ff * kTileW + col] = y;
+        }
+        tile_flush_mono(a, tile, isum, f0, fe);
+    }
+    if (active) {
+        a.state[(size_t)SAT_PHASE * n + v] = phase;
+        if (FACTOR == 4) {
+            for (uint32_t i = 0; i < 24; ++i) {            /* store oldest -> newest */
+                a.state[(size_t)(SAT_H1 + i) * n + v] = h1[((head1 + 1u + i) % 24u) * kCta];
+                a.state[(size_t)(SAT_H2 + i) * n + v] = h2[((head2 + 1u + i) % 24u) * kCta];
+            }
+        }
+    }
+}
+
+/* ===================================================== README Synth (+ ADSR vca) ==== */
+/* README.md:24-53; ADSR -> Gain wiring as oscen-lib/benches/static_vs_runtime.rs:57-59 */
+template <bool WITH_ADSR>
+__global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ KernelArgs a) {
+    __shared__ float tile[kTileF * kTileW];
+    __shared__ float isum[kTileF * kCta];
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * kCta + threadIdx.x;
+    const bool active = v < n;
+    const uint32_t vs = active ? v : 0u;
+    const uint32_t frames = a.ctl->frames, ramp_mask = a.ctl->ramp_mask;
+    const float sr = a.u.sr;
+    const uint32_t col = tile_col(threadIdx.x, a.vpi);
+
+    SmallParams<8> prm; prm.load(a, vs);
+    float ph_mod = a.state[(size_t)SY_MOD * n + vs], ph_car = a.state[(size_t)SY_CAR * n + vs];
+    TptState tp; tpt_load(tp, a.state, SY_TPT, n, vs);
+    AdsrState env; adsr_load(env, a.state, SY_ENV, n, vs);
+    AdsrDerived d;
+    adsr_derive(d, prm.P[4], prm.P[5], prm.P[7], sr);
+    EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+
+    for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
+        const uint32_t fe = min(kTileF, frames - f0);
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const uint32_t f = f0 + ff;
+            float y = 0.0f;
+            if (active) {
+                prm.ramps(a, ramp_mask, f);
+                uint32_t j = ec.i;
+                const bool due = ec.due(f);
+                if (due) {
+                    j = ec.end_of_frame(f);
+                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
+                }
+                if (WITH_ADSR && adsr_derived_stale(d, prm.P[4], prm.P[5], prm.P[7])) adsr_derive(d, prm.P[4], prm.P[5], prm.P[7], sr);
+                if (due) {
+                    if (WITH_ADSR)
+                        for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
+                            adsr_on_gate(env, ec.ev[q].scalar, prm.P[4], prm.P[7], d);
+                    ec.advance(j);
+                }
+                const float m = polyblep_process<WAVE_SINE>(ph_mod, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr);
+                const float c = polyblep_process<WAVE_SAW>(ph_car, 0.0f, prm.P[2], m, 0.5f, 0.5f, sr);
+                const float lp = tpt_process(tp, c, prm.P[3], 0.707f, 0.0f, sr);
+                if (WITH_ADSR) {
+                    const float g = adsr_process(env, prm.P[6], d);
+                    y = lp * g;                                  /* vca: Gain */
+                } else {
+                    y = lp;
+                }
+                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
+            }
+            tile[ff * kTileW + col] = y;
+        }
+        tile_flush_mono(a, tile, isum, f0, fe);
+    }
+    if (active) {
+        a.state[(size_t)SY_MOD * n + v] = ph_mod; a.state[(size_t)SY_CAR * n + v] = ph_car;
+        tpt_store(tp, a.state, SY_TPT, n, v);
+        adsr_store(env, a.state, SY_ENV, n, v);
+    }
+}
+
+/* ================================================================ ElectricPiano ==== */
+/* examples/electric-piano/src/electric_piano_voice.rs (AmplitudeSource, OscillatorBank,
+   ElectricPianoVoiceNode), tremolo.rs, main.rs:33-97 (16 voices -> sum -> Tremolo -> Frame<2>).
+   Per-voice state (259 words) lives in a [field][thread] shared-memory tile for the block. */
+__constant__ float kEpVel0[32] = { 0.02f, 0.05f };
+__constant__ float kEpVel127[32] = {
+    0.150869f, 0.385766f, 0.215543f, 0.117811f, 0.100411f, 0.0128637f, 0.0288844f, 0.00243388f,
+    0.00963092f, 0.0035634f, 0.00256945f, 0.00184799f, 0.000399878f, 0.000660576f, 3.00995e-05f,
+    0.00021866f, 9.33705e-05f, 0.000177973f, 0.0002545f, 0.000323602f, 0.000779045f, 0.000116569f,
+    0.000772873f, 0.000364486f, 0.000248027f, 0.00018236f, 3.27292e-05f, 6.64988e-05f,
+    0.0f, 0.0f, 0.0f, 0.0f };
+
+/* AmplitudeSource::on_gate, electric_piano_voice.rs:241-320 (note_pitch stays 60.0) */
+OSC_D void ep_amp_on_gate(float *S, float scalar, const float *P) {
+#define EPS(field, i) S[((field) + (i)) * kCta]
+    if (scalar > 0.0f) {
+        const float velocity = scalar;
+        const float note = 60.0f;
+        const float base_decay_rate = (100.0f - P[3]) / 40000.0f;
+        const float harmonic_scaling = 1.0f - ((100.0f - P[4]) / 200000.0f);
+        const float scaling_multiplier = (48.0f - note) / 12.0f;
+        const float key_scaling_factor = scaling_multiplier * (P[5] * 0.02f);
+        const float adjusted = (key_scaling_factor > 0.0f)
+            ? 1.0f - (base_decay_rate / (1.0f + key_scaling_factor))
+            : 1.0f - (base_decay_rate * (1.0f - key_scaling_factor));
+        float scaling = 1.0f;
+        const float rv = 0.999f - ((100.0f - P[6]) / 1000.0f);
+        float bs = -0.2f + (0.8f * (P[1] * 0.01f));
+        bs += velocity * P[2] * 0.01f * 0.5f;
+        for (int i = 0; i < 32; ++i) {
+            EPS(EP_DEC, i) = adjusted * scaling; scaling *= harmonic_scaling;
+            EPS(EP_REL, i) = rv;
+            float amp = (kEpVel127[i] * velocity) + (kEpVel0[i] * (1.0f - velocity));
+            amp *= 1.0f + bs * (float)i;
+            EPS(EP_CUR, i) = amp;
+        }
+        EPS(EP_RELEASED, 0) = 0.0f; EPS(EP_STEP, 0) = 0.0f;
+    } else {
+        EPS(EP_RELEASED, 0) = 1.0f; EPS(EP_STEP, 0) = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(kCta) epiano_kernel(const __grid_constant__ KernelArgs a) {
+    extern __shared__ float dyn[];          /* S [EP_NSTATE][128] | tile [32][192] | isum [32*128*2] */
+    float *S = dyn + threadIdx.x;
+    float *tile = dyn + EP_NSTATE * kCta;
+    float *isum = tile + kTileF * kTileW;
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * kCta + threadIdx.x;
+    const bool active = v < n;
+    const uint32_t vs = active ? v : 0u;
+    const uint32_t frames = a.ctl->frames, ramp_mask = a.ctl->ramp_mask;
+    const float sr = a.u.sr;
+    const uint32_t vpi = a.vpi;
+    const uint32_t col = tile_col(threadIdx.x, vpi);
+
+    SmallParams<9> prm; prm.load(a, vs);
+    for (uint32_t i = 0; i < EP_NSTATE; ++i) S[i * kCta] = a.state[(size_t)i * n + vs];
+    EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+    /* instance-level tremolo: thread i < ipc owns instance blockIdx*ipc + i */
+    const uint32_t ipc = kCta / vpi;
+    const uint32_t my_inst = blockIdx.x * ipc + threadIdx.x;
+    float trem_phase = (threadIdx.x < ipc && my_inst < a.n_inst) ? a.inst_state[my_inst] : 0.0f;
+
+    for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
+        const uint32_t fe = min(kTileF, frames - f0);
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const uint32_t f = f0 + ff;
+            float y = 0.0f;
+            if (active) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) {
+                    const uint32_t j = ec.end_of_frame(f);
+                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
+                    /* gate -> amplitude_source.gate (handled before its process()) */
+                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate) ep_amp_on_gate(S, ec.ev[q].scalar, prm.P);
+                    /* AmplitudeSource::process happens between the two on_gate calls in the walk,
+                       but OscillatorBank::on_gate only resets the oscillators: order-independent */
+                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate && ec.ev[q].scalar > 0.0f)
+                        for (int i = 0; i < 32; ++i) { EPS(EP_ORE, i) = 1.0f; EPS(EP_OIM, i) = 0.0f; }
+                    ec.advance(j);
+                }
+                /* AmplitudeSource::process, electric_piano_voice.rs:322-351 */
+                uint32_t step = (uint32_t)EPS(EP_STEP, 0);
+                const bool released = EPS(EP_RELEASED, 0) != 0.0f;
+                if (step == 0u) {
+                    for (int i = 0; i < 32; ++i)
+                        EPS(EP_TGT, i) = EPS(EP_CUR, i) * (released ? EPS(EP_REL, i) : EPS(EP_DEC, i));
+                }
+                if (step < 64u) {
+                    const float t = (float)(step + 1u) / 64.0f;
+                    for (int i = 0; i < 32; ++i)
+                        EPS(EP_CUR, i) = EPS(EP_CUR, i) * (1.0f - t) + EPS(EP_TGT, i) * t;
+                    step += 1u;
+                } else {
+                    for (int i = 0; i < 32; ++i) EPS(EP_CUR, i) = EPS(EP_TGT, i);
+                    step = 0u;
+                }
+                EPS(EP_STEP, 0) = (float)step;
+                /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
+                const float freq = prm.P[0];
+                if (freq > 0.0f && !(fabsf(EPS(EP_LASTF, 0) - freq) < 0.01f)) {
+                    EPS(EP_LASTF, 0) = freq;
+                    const float nyquist = sr * 0.5f;
+                    for (int i = 0; i < 32; ++i) {
+                        const float hf = freq * (float)(i + 1);
+                        if (hf < nyquist) {
+                            const float angle = 2.0f * kPi * hf / sr;
+                            EPS(EP_MRE, i) = om_cosf(angle); EPS(EP_MIM, i) = om_sinf(angle);
+                        } else { EPS(EP_MRE, i) = 1.0f; EPS(EP_MIM, i) = 0.0f; }
+                    }
+                    for (int i = 0; i < 32; ++i) { EPS(EP_ORE, i) = 1.0f; EPS(EP_OIM, i) = 0.0f; }
+                }
+                float sum = 0.0f;
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const float re = EPS(EP_ORE, i), im = EPS(EP_OIM, i);
+                    const float mr = EPS(EP_MRE, i), mi = EPS(EP_MIM, i);
+                    const float nr = re * mr - im * mi;
+                    const float ni = re * mi + im * mr;
+                    EPS(EP_ORE, i) = nr; EPS(EP_OIM, i) = ni;
+                    sum += ni * EPS(EP_CUR, i);
+                }
+                y = sum * 3.0f;
+                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
+            }
+            tile[ff * kTileW + col] = y;
+        }
+        /* ---- flush: instance sum (index order) -> Tremolo (sequential in time) -> Frame<2> */
+        __syncthreads();
+        if (threadIdx.x < ipc) {
+            const uint32_t i = threadIdx.x;
+            const uint32_t c0 = tile_col(i * vpi, vpi);
+            /* instance-level inputs are read from the instance's first voice */
+            const float depth = a.pv[(size_t)7 * n + min((blockIdx.x * ipc + i) * vpi, n - 1)];
+            const float rate = a.pv[(size_t)8 * n + min((blockIdx.x * ipc + i) * vpi, n - 1)];
+            for (uint32_t ff = 0; ff < fe; ++ff) {
+                const float *row = tile + ff * kTileW;
+                float s = 0.0f;
+                for (uint32_t j = 0; j < vpi; ++j) s = s + row[c0 + j];
+                float l, r;
+                tremolo_process(trem_phase, s, rate, depth, sr, l, r);
+                isum[(ff * kCta + i) * 2 + 0] = l; isum[(ff * kCta + i) * 2 + 1] = r;
+                if (a.inst_out != nullptr && my_inst < a.n_inst) {
+                    a.inst_out[((size_t)(f0 + ff) * a.n_inst + my_inst) * 2 + 0] = l;
+                    a.inst_out[((size_t)(f0 + ff) * a.n_inst + my_inst) * 2 + 1] = r;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < fe * 2u) {                       /* mix partial: in-order over the CTA's instances */
+            const uint32_t ff = threadIdx.x >> 1, c = threadIdx.x & 1u;
+            float s = 0.0f;
+            for (uint32_t i = 0; i < ipc; ++i) s = s + isum[(ff * kCta + i) * 2 + c];
+            a.mix_partial[((size_t)blockIdx.x * kMaxBlock + f0 + ff) * 2 + c] = s;
+        }
+        __syncthreads();
+    }
+    if (active) for (uint32_t i = 0; i < EP_NSTATE; ++i) a.state[(size_t)i * n + v] = S[i * kCta];
+    if (threadIdx.x < ipc && my_inst < a.n_inst) a.inst_state[my_inst] = trem_phase;
+#undef EPS
+}
+
+}  // namespace oscen

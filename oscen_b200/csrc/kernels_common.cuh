@@ -1,0 +1,116 @@
+/*
+ * kernels_common.cuh — pieces shared by every graph kernel: event lookup, per-voice value
+ * inputs, the shared-memory output tile with in-order instance sums and the deterministic
+ * mix-bus partials.
+ */
+#pragma once
+#include "engine_types.h"
+
+namespace oscen {
+
+/* first event of `voice` in the (voice, frame, seq)-sorted list */
+OSC_D uint32_t event_lower_bound(const Event *ev, uint32_t n, uint32_t voice) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ev[mid].voice < voice) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+struct EventCursor {
+    const Event *ev;
+    uint32_t n, i, voice, next_frame;
+    OSC_D void init(const Event *e, uint32_t n_events, uint32_t v) {
+        ev = e; n = n_events; voice = v;
+        i = n_events ? event_lower_bound(e, n_events, v) : 0u;
+        next_frame = (i < n && ev[i].voice == v) ? ev[i].frame : 0xFFFFFFFFu;
+    }
+    OSC_D bool due(uint32_t f) const { return f == next_frame; }
+    /* events of this voice at frame f: [i, end) ; advance() moves past them */
+    OSC_D uint32_t end_of_frame(uint32_t f) const {
+        uint32_t j = i;
+        while (j < n && ev[j].voice == voice && ev[j].frame == f) ++j;
+        return j;
+    }
+    OSC_D void advance(uint32_t j) {
+        i = j;
+        next_frame = (i < n && ev[i].voice == voice) ? ev[i].frame : 0xFFFFFFFFu;
+    }
+};
+
+/* column of voice-in-CTA `t` in the padded tile row: one pad word per instance so that the
+   in-order instance sum (stride vpi) is bank-conflict free */
+OSC_D uint32_t tile_col(uint32_t t, uint32_t vpi) { return vpi > 1u ? t + t / vpi : t; }
+
+/*
+ * Flush one tile of per-voice outputs (mono):
+ *   inst_out[f][instance] = sum over the instance's voices in index order (sequential f32
+ *     fold == `.iter().map(|n| n.audio_out).sum()`, codegen/emit_node.rs:463-466)
+ *   mix_partial[cta][f]   = fixed-shape sum of this CTA's instance outputs
+ * tile: [kTileF][kTileW] voice outputs, isum: [kTileF][kCta] scratch.  All threads call.
+ */
+OSC_D void tile_flush_mono(const KernelArgs &a, const float *tile, float *isum, uint32_t f0, uint32_t fe) {
+    const uint32_t vpi = a.vpi;
+    const uint32_t ipc = kCta / vpi;                       /* instances per CTA */
+    const uint32_t inst0 = blockIdx.x * ipc;
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < fe * ipc; t += kCta) {
+        const uint32_t ff = t / ipc, i = t % ipc;
+        const float *row = tile + ff * kTileW;
+        float s = 0.0f;
+        const uint32_t c0 = tile_col(i * vpi, vpi);
+        for (uint32_t j = 0; j < vpi; ++j) s = s + row[c0 + j];
+        isum[ff * kCta + i] = s;
+        if (a.inst_out != nullptr && inst0 + i < a.n_inst)
+            a.inst_out[(size_t)(f0 + ff) * a.n_inst + inst0 + i] = s;
+    }
+    __syncthreads();
+    /* mix partial: 4 threads per frame, each folds a quarter of the instances in order,
+       then ((q0+q1)+q2)+q3 — fixed shape, run-to-run deterministic */
+    {
+        const uint32_t ff = threadIdx.x >> 2, qd = threadIdx.x & 3u;
+        float s = 0.0f;
+        if (ff < fe) {
+            const uint32_t per = (ipc + 3u) / 4u;
+            const uint32_t b = qd * per, e = min(b + per, ipc);
+            for (uint32_t i = b; i < e; ++i) s = s + isum[ff * kCta + i];
+        }
+        const float s1 = __shfl_down_sync(0xffffffffu, s, 1);
+        const float s2 = __shfl_down_sync(0xffffffffu, s, 2);
+        const float s3 = __shfl_down_sync(0xffffffffu, s, 3);
+        if (qd == 0 && ff < fe)
+            a.mix_partial[(size_t)blockIdx.x * kMaxBlock + f0 + ff] = ((s + s1) + s2) + s3;
+    }
+    __syncthreads();
+}
+
+/* final mix bus: mix[f][c] = fixed-shape sum over CTAs of mix_partial[cta][f][c] */
+__global__ void mix_reduce_kernel(const float *__restrict__ partial, float *__restrict__ mix,
+                                  uint32_t n_cta, uint32_t channels, const BlockCtl *ctl) {
+    __shared__ float red[256];
+    const uint32_t fc = blockIdx.x;                        /* frame*channels + c */
+    if (fc >= ctl->frames * channels) return;
+    float s = 0.0f;
+    for (uint32_t c = threadIdx.x; c < n_cta; c += 256) s = s + partial[(size_t)c * kMaxBlock * channels + fc];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mix[fc] = red[0];
+}
+
+__global__ void fill_u32_kernel(uint32_t *dst, size_t n, uint32_t value) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = value;
+}
+/* state[f][v] = init[f] */
+__global__ void init_state_kernel(uint32_t *state, const uint32_t *init, uint32_t n_fields, uint32_t n_voices) {
+    const size_t n = (size_t)n_fields * n_voices;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        state[i] = init[i / n_voices];
+}
+
+}  // namespace oscen

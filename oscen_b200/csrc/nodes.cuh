@@ -1,0 +1,350 @@
+/*
+ * nodes.cuh — device-side node bodies of the oscen hot path, one inline function per
+ * reference `SignalProcessor::process()`, written for
+ * "one thread = one voice, state in registers for the whole block".
+ *
+ * Parity rules: compiled with -fmad=false (rustc never fuses a*b+c),
+ * IEEE division/sqrt, no fast-math; transcendentals from om_math.h (glibc-faithful).
+ * Where the reference recomputes a pure function of unchanged inputs every sample (ADSR step
+ * counts / one-pole coefficients, FM phase increment, TPT clamp ratios) the value is cached
+ * and recomputed only when its inputs change — result-identical, not an approximation.
+ *
+ * Citations: path:line under the reference repo (reedrosenbluth/oscen @ 8061f7d5).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "om_math.h"
+
+namespace oscen {
+
+#define OSC_HD __host__ __device__ __forceinline__
+#define OSC_D __device__ __forceinline__
+
+constexpr float kPi = 3.14159265358979323846f;    /* std::f32::consts::PI  */
+constexpr float kTau = 6.28318530717958647692f;   /* std::f32::consts::TAU */
+
+/* f32::clamp: two compares, NaN propagates */
+OSC_HD float clampf(float x, float lo, float hi) {
+    if (x < lo) x = lo;
+    if (x > hi) x = hi;
+    return x;
+}
+/* `x as u32`: truncating, saturating, NaN -> 0 */
+OSC_HD uint32_t f32_as_u32(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2uint_rz(x);
+#else
+    if (!(x == x) || x <= 0.0f) return 0u;
+    if (x >= 4294967296.0f) return 4294967295u;
+    return (uint32_t)x;
+#endif
+}
+OSC_HD uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+OSC_HD uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+/* f32::rem_euclid(1.0): fmodf(x,1) is exact and equals x - trunc(x) (sign of zero kept) */
+OSC_HD float rem_euclid1(float x) {
+    float r = x - truncf(x);
+    if (r == 0.0f) r = copysignf(0.0f, x);
+    return (r < 0.0f) ? r + 1.0f : r;
+}
+/* f32::fract */
+OSC_HD float fractf(float x) { return x - truncf(x); }
+
+/* ================================================================= AdsrEnvelope == */
+/* oscen-lib/src/envelope/adsr.rs */
+enum : uint32_t { ST_IDLE = 0, ST_ATTACK = 1, ST_DECAY = 2, ST_SUSTAIN = 3, ST_RELEASE = 4 };
+constexpr float kAdsrMinTime = 1.0e-5f;      /* adsr.rs:5 */
+constexpr float kAdsrCurveK = 4.6051702f;    /* adsr.rs:8 */
+
+/* live state (what survives from one frame to the next; everything else in the reference
+   struct is recomputed before use inside process(), see DESIGN.md "dead state") */
+struct AdsrState {
+    uint32_t stage, rem;
+    float level, vel;
+};
+/* recalculate_cached_steps(), adsr.rs:117-134 — a pure function of (attack, decay, release, sr) */
+struct AdsrDerived {
+    float attack, decay, release;     /* the raw inputs these were derived from */
+    uint32_t a_n, d_n, r_n;
+    float a_k, d_k;
+};
+OSC_HD void adsr_derive(AdsrDerived &d, float attack, float decay, float release, float sample_rate) {
+    float sr = fmaxf(sample_rate, 1.0f);
+    d.attack = attack; d.decay = decay; d.release = release;
+    d.a_n = umax(f32_as_u32(fmaxf(attack, kAdsrMinTime) * sr), 1u);
+    d.d_n = umax(f32_as_u32(fmaxf(decay, kAdsrMinTime) * sr), 1u);
+    d.r_n = umax(f32_as_u32(fmaxf(release, kAdsrMinTime) * sr), 1u);
+    d.a_k = 1.0f - om_expf(-kAdsrCurveK / (float)d.a_n);
+    d.d_k = 1.0f - om_expf(-kAdsrCurveK / (float)d.d_n);
+}
+OSC_HD bool adsr_derived_stale(const AdsrDerived &d, float attack, float decay, float release) {
+    return !(d.attack == attack && d.decay == decay && d.release == release);
+}
+/* handle_gate_event(), adsr.rs:252-273.  `d` must be derived from THIS frame's inputs
+   (edges are assigned before process_event_inputs(), codegen/emit_node.rs:365-379).
+   set_stage(Attack|Decay|Release) always finds samples >= 1, so it reduces to the two stores
+   below; the release increment it computes is recomputed in process() before its first use. */
+OSC_D void adsr_on_gate(AdsrState &s, float velocity, float attack_raw, float release_raw,
+                        const AdsrDerived &d) {
+    if (velocity > 0.0f) {
+        s.vel = clampf(velocity, 0.0f, 1.0f);
+        if (attack_raw <= kAdsrMinTime) { s.level = 1.0f; s.stage = ST_DECAY; s.rem = d.d_n; }
+        else { s.stage = ST_ATTACK; s.rem = d.a_n; }
+    } else if (release_raw <= kAdsrMinTime) {
+        s.stage = ST_IDLE; s.level = 0.0f; s.rem = 0u;
+    } else {
+        s.stage = ST_RELEASE; s.rem = d.r_n;
+    }
+}
+/* process(), adsr.rs:84-115 (apply_parameters + update_sustain_level), :209-250 (process_stage),
+   :175-207 (complete_stage).  Returns `output`. */
+OSC_D float adsr_process(AdsrState &s, float sustain_in, const AdsrDerived &d) {
+    const float sustain = clampf(sustain_in, 0.0f, 1.0f);
+    const float sus = clampf(sustain * s.vel, 0.0f, 1.0f);
+    if (s.rem > 0u) {                                   /* adsr.rs:95-106 */
+        if (s.stage == ST_ATTACK) s.rem = umax(umin(s.rem, d.a_n), 1u);
+        else if (s.stage == ST_DECAY) s.rem = umax(umin(s.rem, d.d_n), 1u);
+        else if (s.stage == ST_RELEASE) s.rem = umax(umin(s.rem, d.r_n), 1u);
+    }
+    if (s.stage == ST_ATTACK) {
+        if (s.rem > 0u) {
+            s.level += (1.0f - s.level) * d.a_k;
+            s.rem -= 1u;
+            s.level = clampf(s.level, 0.0f, 1.0f);
+        }
+        if (s.rem == 0u) { s.level = 1.0f; s.stage = ST_DECAY; s.rem = d.d_n; }
+    } else if (s.stage == ST_DECAY) {
+        if (s.rem > 0u) {
+            s.level += (sus - s.level) * d.d_k;
+            s.rem -= 1u;
+            s.level = clampf(s.level, 0.0f, 1.0f);
+        }
+        if (s.rem == 0u) { s.level = sus; s.stage = ST_SUSTAIN; }
+    } else if (s.stage == ST_RELEASE) {
+        if (s.rem > 0u) {
+            /* update_release_increment(), adsr.rs:159-173 — recomputed every sample */
+            const float cur = clampf(s.level, 0.0f, 1.0f);
+            const float inc = (cur <= 0.0f) ? 0.0f : -cur / (float)s.rem;
+            s.level += inc;
+            s.rem -= 1u;
+            s.level = clampf(s.level, 0.0f, 1.0f);
+        }
+        if (s.rem == 0u) { s.level = 0.0f; s.stage = ST_IDLE; }
+    } else if (s.stage == ST_SUSTAIN) {
+        s.level = sus;
+    } else {
+        s.level = 0.0f;
+    }
+    return s.level;
+}
+
+/* =================================================================== FmOperator == */
+/* examples/fm-synth/src/nodes/fm_operator.rs:58-76 */
+struct FmOpState {
+    float phase, prev;
+    float freq_c, inc_c;      /* cache: phase_inc = frequency / sample_rate (not persisted) */
+};
+OSC_D void fmop_reset_cache(FmOpState &s) { s.freq_c = __int_as_float(0x7fc00000); s.inc_c = 0.0f; }
+OSC_D float fmop_process(FmOpState &s, float base_freq, float ratio, float phase_mod, float feedback,
+                         float envelope, float level, float sample_rate) {
+    const float frequency = base_freq * ratio;
+    const float feedback_mod = s.prev * feedback;
+    const float total_phase_mod = phase_mod + feedback_mod;
+    const float phase_rad = (s.phase + total_phase_mod) * kTau;
+    const float out = om_sinf(phase_rad) * envelope * level;
+    s.prev = out;
+    if (!(frequency == s.freq_c)) { s.freq_c = frequency; s.inc_c = frequency / sample_rate; }
+    s.phase += s.inc_c;
+    s.phase = fractf(s.phase);
+    return out;
+}
+
+/* ==================================================================== TptFilter == */
+/* oscen-lib/src/filters/tpt/mod.rs:69-123 */
+struct TptState {
+    float z0, z1, cur_cutoff, cur_q, h, g, k;
+};
+OSC_HD void tpt_update_coefficients(TptState &s, float sample_rate, float cutoff, float q) {
+    const float nyquist = sample_rate * 0.5f - FLT_EPSILON;
+    const float freq = clampf(cutoff, 20.0f, nyquist);
+    const float period = 0.5f / sample_rate;
+    const float f = (2.0f * sample_rate) * om_tanf(2.0f * kPi * freq * period) * period;
+    const float inv_q = 1.0f / q;
+    s.h = 1.0f / (1.0f + inv_q * f + f * f);
+    s.g = f;
+    s.k = s.g + inv_q;
+    s.cur_cutoff = cutoff;
+    s.cur_q = q;
+}
+/* TptFilter::new(cutoff,q) then set_sample_rate(sr) + prepare(): mod.rs:46-67,129-131 */
+OSC_HD void tpt_init(TptState &s, float sample_rate, float cutoff, float q) {
+    s.z0 = 0.0f; s.z1 = 0.0f;
+    tpt_update_coefficients(s, 44100.0f, cutoff, q);
+    tpt_update_coefficients(s, sample_rate, cutoff, q);
+}
+OSC_D float tpt_process(TptState &s, float input, float cutoff_in, float q_in, float f_mod,
+                        float sample_rate) {
+    const float nyquist = sample_rate * 0.5f - FLT_EPSILON;
+    const float max_cutoff = fminf(nyquist, 20000.0f);
+    const float cutoff_base = clampf(cutoff_in, 20.0f, max_cutoff);
+    const float q = clampf(q_in, 0.1f, 10.0f);
+    const float modulation = clampf(f_mod, -1.0f, 1.0f);
+    float cutoff;
+    if (modulation == 0.0f) {
+        /* factor = clamp(1, 20/cb <= 1, max/cb >= 1) = 1 and cb*1 = cb: skip the two divisions */
+        cutoff = cutoff_base;
+    } else {
+        const float min_factor = 20.0f / cutoff_base;
+        const float max_factor = max_cutoff / cutoff_base;
+        const float factor = clampf(1.0f + modulation, min_factor, max_factor);
+        cutoff = clampf(cutoff_base * factor, 20.0f, max_cutoff);
+    }
+    if (fabsf(cutoff - s.cur_cutoff) > FLT_EPSILON || fabsf(q - s.cur_q) > FLT_EPSILON)
+        tpt_update_coefficients(s, sample_rate, cutoff, q);
+    const float high = (input - s.z0 * s.k - s.z1) * s.h;
+    const float band = high * s.g + s.z0;
+    const float low = band * s.g + s.z1;
+    s.z0 = high * s.g + band;
+    s.z1 = band * s.g + low;
+    return low;
+}
+
+/* =========================================================== PolyBlepOscillator == */
+/* oscen-lib/src/oscillators/mod.rs:139-233 */
+enum : int { WAVE_SINE = 0, WAVE_SAW = 1, WAVE_SQUARE = 2, WAVE_TRIANGLE = 3 };
+OSC_D float poly_blep(float t, float dt) {
+    if (dt <= FLT_EPSILON) return 0.0f;
+    if (t < dt) { const float x = t / dt; return x + x - x * x - 1.0f; }
+    if (t > 1.0f - dt) { const float x = (t - 1.0f) / dt; return x * x + x + x + 1.0f; }
+    return 0.0f;
+}
+OSC_D float poly_blamp(float t, float dt) {
+    if (dt <= FLT_EPSILON) return 0.0f;
+    if (t < dt) { const float x = t / dt - 1.0f; return -(x * x * x) / 3.0f; }
+    if (t > 1.0f - dt) { const float x = (t - 1.0f) / dt + 1.0f; return (x * x * x) / 3.0f; }
+    return 0.0f;
+}
+template <int WAVE>
+OSC_D float polyblep_process(float &phase_state, float phase_mod, float frequency_in, float frequency_mod,
+                             float amplitude, float pulse_width_in, float sample_rate) {
+    const float frequency = fmaxf(frequency_in * (1.0f + frequency_mod), 0.0f);
+    float pulse_width = clampf(pulse_width_in, 0.0001f, 0.9999f);
+    const float phase = rem_euclid1(phase_state + phase_mod);
+    const float freq_per_sample = frequency / fmaxf(sample_rate, FLT_EPSILON);
+    const float dt = fminf(freq_per_sample, 1.0f);
+    if (pulse_width <= 0.0f) pulse_width = 0.0001f;
+    float value;
+    if (frequency >= sample_rate * 0.25f) {
+        value = om_sinf(phase * kTau);
+    } else if (WAVE == WAVE_SINE) {
+        value = om_sinf(phase * kTau);
+    } else if (WAVE == WAVE_SAW) {
+        float y = 2.0f * phase - 1.0f;
+        y -= poly_blep(phase, dt);
+        value = y;
+    } else if (WAVE == WAVE_SQUARE) {
+        float y = (phase < pulse_width) ? 1.0f : -1.0f;
+        y += poly_blep(phase, dt);
+        const float t = rem_euclid1(phase + 1.0f - pulse_width);
+        y -= poly_blep(t, dt);
+        value = y;
+    } else {
+        float y = 4.0f * phase;
+        if (y >= 3.0f) y -= 4.0f;
+        else if (y > 1.0f) y = 2.0f - y;
+        const float t1 = rem_euclid1(phase + 0.25f);
+        const float t2 = rem_euclid1(phase + 0.75f);
+        value = y + 4.0f * dt * (poly_blamp(t1, dt) - poly_blamp(t2, dt));
+    }
+    value = value * amplitude;
+    phase_state = rem_euclid1(phase_state + freq_per_sample);
+    return value;
+}
+
+/* =================================================================== LP18Filter == */
+/* examples/nih-twin-peaks/src/lp18_filter.rs:62-107 */
+struct Lp18State {
+    float z0, z1, z2, g, h;
+    float last_cutoff, last_fmod, last_resonance, resonance;
+};
+OSC_HD void lp18_update_cutoff(Lp18State &s, float cutoff, float fmod, float sample_rate) {
+    const float modulated = cutoff + fmod;
+    const float fc = clampf(modulated / sample_rate, 0.001f, 0.33f);
+    s.g = om_tanf(kPi * fc);
+}
+/* LP18Filter::new(cutoff,res) + set_sample_rate + prepare(): lp18_filter.rs:44-60,74-77 */
+OSC_HD void lp18_init(Lp18State &s, float cutoff, float resonance, float sample_rate) {
+    s.z0 = s.z1 = s.z2 = 0.0f;
+    s.resonance = clampf(resonance, 0.0f, 0.99f);
+    s.last_cutoff = cutoff; s.last_fmod = 0.0f; s.last_resonance = resonance;
+    lp18_update_cutoff(s, cutoff, 0.0f, sample_rate);
+    s.h = 2.0f * s.resonance;
+}
+OSC_D float lp18_process(Lp18State &s, float input, float cutoff, float fmod, float resonance_in,
+                         float sample_rate) {
+    s.resonance = resonance_in;                       /* value edge assigned before process() */
+    if (cutoff != s.last_cutoff || fmod != s.last_fmod) {
+        s.last_cutoff = cutoff; s.last_fmod = fmod;
+        lp18_update_cutoff(s, cutoff, fmod, sample_rate);
+    }
+    if (s.resonance != s.last_resonance) {
+        s.last_resonance = s.resonance;
+        s.resonance = clampf(s.resonance, 0.0f, 0.99f);
+        s.h = 2.0f * s.resonance;
+    }
+    const float hp = (input - s.h * s.z0 - s.z1 - s.z2) / (1.0f + s.g);
+    const float bp1 = s.g * hp + s.z0;
+    s.z0 = om_tanhf(bp1);
+    const float bp2 = s.g * bp1 + s.z1;
+    s.z1 = bp2;
+    const float lp = s.g * bp2 + s.z2;
+    s.z2 = lp;
+    return lp;
+}
+
+/* ===================================================================== HardClip == */
+/* examples/oversampled-saturator/src/main.rs:55-62 */
+OSC_D float hardclip_process(float input) {
+    const float driven = input * 1.5f;
+    return clampf(driven, -0.7f, 0.7f);
+}
+
+/* ======================================================= Halfband2xDownStage::step == */
+/* oscen-lib/src/resample/sinc_fir.rs:113-138, taps resample/coeffs.rs:17-27.
+   `hist` is this thread's 24-slot ring (stride `stride` floats: one column of a
+   [24][threads] shared-memory tile, conflict-free); `head` as in the reference. */
+constexpr float kHb0 = -3.8558514e-5f, kHb1 = 1.2218465e-3f, kHb2 = -7.2854808e-3f,
+                kHb3 = 2.6409210e-2f, kHb4 = -7.8128843e-2f, kHb5 = 3.0782697e-1f;
+constexpr float kHbCenter = 0.4999897f;
+OSC_D float hb_down_step(float *hist, int stride, uint32_t &head, float x0, float x1) {
+    head = (head + 1u) % 24u; hist[head * stride] = x0;
+    head = (head + 1u) % 24u; hist[head * stride] = x1;
+#define OSC_HB_AT(d) hist[((head + 24u - 1u - (uint32_t)(d)) % 24u) * stride]
+    float acc = OSC_HB_AT(11) * kHbCenter;
+    acc = acc + (OSC_HB_AT(0) + OSC_HB_AT(22)) * kHb0;
+    acc = acc + (OSC_HB_AT(2) + OSC_HB_AT(20)) * kHb1;
+    acc = acc + (OSC_HB_AT(4) + OSC_HB_AT(18)) * kHb2;
+    acc = acc + (OSC_HB_AT(6) + OSC_HB_AT(16)) * kHb3;
+    acc = acc + (OSC_HB_AT(8) + OSC_HB_AT(14)) * kHb4;
+    acc = acc + (OSC_HB_AT(10) + OSC_HB_AT(12)) * kHb5;
+#undef OSC_HB_AT
+    return acc;
+}
+
+/* ====================================================================== Tremolo == */
+/* examples/electric-piano/src/tremolo.rs:41-61 */
+OSC_D void tremolo_process(float &phase, float input, float rate, float depth, float sample_rate,
+                           float &out_l, float &out_r) {
+    const float lfo = om_sinf(phase * 2.0f * kPi);
+    const float scaled_depth = depth / 3.0f;
+    const float pan = 0.5f + lfo * scaled_depth;
+    out_l = input * pan;
+    out_r = input * (1.0f - pan);
+    const float inc = rate / sample_rate;
+    phase = fractf(phase + inc);
+}
+
+}  // namespace oscen

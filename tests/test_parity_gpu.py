@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerance: |gpu - ref| <= 1e-6 + 1e-5*|ref| (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from parity_util import assert_close, lcg_ints, lcg_noise, lcg_uniform, seq_sum_f32
+
+pytestmark = pytest.mark.gpu
+
+GATE = O.EV_GATE
+
+
+def engine(kind, n, vpi=1, plan=0, keep=3, sr=48000.0):
+    from oscen_b200 import abi
+    return abi.Engine(kind, n, vpi, sr, 0, plan, keep)
+
+
+def both(kind, n, vpi=1, plan=0, sr=48000.0):
+    return O.OracleBank(kind, n, vpi, sr), engine(kind, n, vpi, plan, 3, sr)
+
+
+def drive(banks, fn):
+    outs = []
+    for b in banks:
+        outs.append(fn(b))
+    return outs
+
+
+def compare_banks(ref, gpu, what, check_inst=True):
+    stats = assert_close(gpu.read_voice_out(), ref.read_voice_out(), what + " voice_out")
+    if check_inst:
+        assert_close(gpu.read_instance_out(), ref.read_instance_out(), what + " instance_out")
+    mref = ref.read_mix().astype(np.float64)
+    mgpu = gpu.read_mix().astype(np.float64)
+    # the mix bus is summed in a different (tree) order: tolerance scaled by sum |instance|
+    scale = np.abs(ref.read_instance_out().astype(np.float64)).sum(axis=1)
+    assert (np.abs(mgpu - mref) <= 1e-6 + 2e-6 * scale).all(), what + " mix"
+    return stats
+
+
+# --------------------------------------------------------------- config 1: the anchor
+@pytest.mark.parametrize("chunks", [[512, 512], [256, 256, 256, 256], [100, 412, 512]])
+@pytest.mark.parametrize("variant", ["defaults", "feedback"])
+def test_fm_voice_anchor_1_voice_1024_frames(chunks, variant):
+    ref, gpu = both(O.K_FM, 1, 1)
+    for b in (ref, gpu):
+        b.set_value(0, 440.0)
+        if variant == "feedback":
+            b.set_value(3, 0.3); b.set_value(10, 0.2); b.set_value(20, 0.5); b.set_value(27, 1500.0)
+    pos = 0
+    outs = {id(ref): [], id(gpu): []}
+    for frames in chunks:
+        for b in (ref, gpu):
+            ev = []
+            if pos <= 0 < pos + frames:
+                ev.append((0, 0 - pos, GATE, 1.0))
+            if pos <= 768 < pos + frames:
+                ev.append((0, 768 - pos, GATE, 0.0))
+            b.push_events(ev)
+            b.process_block(frames)
+            outs[id(b)].append(b.read_voice_out())
+        pos += frames
+    yr, yg = np.concatenate(outs[id(ref)]), np.concatenate(outs[id(gpu)])
+    assert np.abs(yr).max() > 0.05
+    max_err, exact = assert_close(yg, yr, f"FM anchor {variant} {chunks}")
+    print(f"anchor {variant} {chunks}: max_err={max_err:.3e} bit_exact={exact:.4f}")
+
+
+def _fm_bank_script(b, n, blocks=4, frames=256):
+    notes = 36 + lcg_ints(n, 1, 60)
+    freq = (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32)
+    vel = (0.25 + 0.75 * lcg_uniform(n, 2)).astype(np.float32)
+    on = lcg_ints(n, 3, frames)
+    off = lcg_ints(n, 4, frames)
+    b.set_value(0, freq)
+    outs_v, outs_i, outs_m = [], [], []
+    for bi in range(blocks):
+        if bi == 0:
+            b.push_events([(v, int(on[v]), GATE, float(vel[v])) for v in range(n)])
+        if bi == 1:
+            b.set_value_ramp(2, 0.8, 300)       # op3_level ramp spanning two blocks
+            b.set_value_ramp(27, 900.0, 100)    # filter_env_amount: tanf every sample while it moves
+        if bi == 2:
+            b.push_events([(v, int(off[v]), GATE, 0.0) for v in range(0, n, 2)])
+            b.push_events([(v, 7, 0, float(freq[v] * 1.5)) for v in range(1, n, 4)])   # frame-accurate retune
+        b.process_block(frames)
+        outs_v.append(b.read_voice_out()); outs_i.append(b.read_instance_out()); outs_m.append(b.read_mix())
+    return np.concatenate(outs_v), np.concatenate(outs_i), np.concatenate(outs_m)
+
+
+@pytest.mark.parametrize("plan", [0, 1])
+def test_fm_bank_1024_voices_events_ramps(plan):
+    n, vpi = 1024, 8
+    ref, gpu = both(O.K_FM, n, vpi, plan)
+    (vr, ir, mr), (vg, ig, mg) = drive((ref, gpu), lambda b: _fm_bank_script(b, n))
+    assert np.abs(vr).max() > 0.05
+    max_err, exact = assert_close(vg, vr, f"FM bank plan={plan} voice_out")
+    assert_close(ig, ir, f"FM bank plan={plan} instance_out")
+    scale = np.abs(ir.astype(np.float64)).sum(axis=1)
+    assert (np.abs(mg.astype(np.float64) - mr.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()
+    # instance_out is the in-order f32 fold of its voices (codegen/emit_node.rs:463-466): exact
+    fold = seq_sum_f32(vg.reshape(vg.shape[0], n // vpi, vpi), axis=2)
+    assert np.array_equal(fold, ig[:, :, 0])
+    print(f"FM bank plan={plan}: max_err={max_err:.3e} bit_exact={exact:.4f}")
+
+
+def test_fm_node_plan_equals_fused_plan_bitwise():
+    n, vpi = 512, 8
+    a, b = engine(O.K_FM, n, vpi, plan=0), engine(O.K_FM, n, vpi, plan=1)
+    (va, ia, ma), (vb, ib, mb) = drive((a, b), lambda e: _fm_bank_script(e, n, blocks=3))
+    assert np.array_equal(va, vb) and np.array_equal(ia, ib) and np.array_equal(ma, mb)
+
+
+def test_fm_per_voice_params_general_kernel():
+    n, vpi = 256, 8
+    ref, gpu = both(O.K_FM, n, vpi)
+    rng = np.random.default_rng(5)
+    ratios = rng.choice([0.5, 1.0, 2.0, 3.0, 7.0], size=n).astype(np.float32)
+    attacks = rng.uniform(0.0, 0.05, size=n).astype(np.float32)
+    attacks[::7] = 0.0                                       # attack <= 1e-5 -> straight to Decay
+    rel = rng.uniform(0.0, 0.02, size=n).astype(np.float32)
+    rel[::5] = 0.0                                           # release <= 1e-5 -> straight to Idle
+    fb = rng.uniform(0.0, 0.4, size=n).astype(np.float32)
+
+    def script(b):
+        b.set_value(1, ratios); b.set_value(4, attacks); b.set_value(16, attacks)
+        b.set_value(19, rel); b.set_value(7, rel); b.set_value(3, fb)
+        b.set_value(0, (110.0 * (1 + np.arange(n) % 12)).astype(np.float32))
+        out = []
+        b.push_events([(v, v % 64, GATE, 0.9) for v in range(n)])
+        b.process_block(384); out.append(b.read_voice_out())
+        b.push_events([(v, (3 * v) % 200, GATE, 0.0) for v in range(n)])
+        b.process_block(512); out.append(b.read_voice_out())
+        b.push_events([(v, 0, GATE, 0.4) for v in range(0, n, 3)])       # retrigger at frame 0
+        b.process_block(128); out.append(b.read_voice_out())
+        return np.concatenate(out)
+
+    yr, yg = drive((ref, gpu), script)
+    assert_close(yg, yr, "FM per-voice params")
+
+
+def test_fm_graph_midi_front_matches():
+    n, vpi = 64, 8
+    ref, gpu = both(O.K_FM, n, vpi)
+
+    def script(b):
+        out = []
+        for inst in range(n // vpi):
+            b.push_midi(inst, 3 + inst, [0x90, 48 + inst, 100])
+            b.push_midi(inst, 40, [0x90, 55 + inst, 64])
+            b.push_midi(inst, 40, [0x90, 60, 1])
+        b.process_block(256); out.append(b.read_instance_out())
+        for inst in range(n // vpi):
+            b.push_midi(inst, 10, [0x80, 48 + inst, 0])
+            b.push_midi(inst, 200, [0x90, 60, 0])             # note-on vel 0 == note-off
+            for k in range(9):                                 # steal voices: 9 more notes on an 8-voice instance
+                b.push_midi(inst, 100 + k, [0x90, 70 + k, 90])
+        b.process_block(256); out.append(b.read_instance_out())
+        b.process_block(256); out.append(b.read_instance_out())
+        return np.concatenate(out)
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.abs(yr).max() > 0.01
+    assert_close(yg, yr, "FM MIDI front")
+
+
+def test_events_beyond_block_are_dropped_and_queue_cap():
+    ref, gpu = both(O.K_FM, 8, 8)
+
+    def script(b):
+        b.push_events([(0, 300, GATE, 1.0)])                   # beyond a 256-frame block: dropped
+        b.push_events([(1, 5, GATE, 1.0)])
+        b.process_block(256)
+        return b.read_voice_out()
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.abs(yr[:, 0]).max() == 0.0 and np.abs(yg[:, 0]).max() == 0.0
+    assert_close(yg, yr, "dropped events")
+
+
+# --------------------------------------------------------------- the other reference graphs
+def test_twin_peaks_host_stream():
+    n = 300
+    ref, gpu = both(O.K_TWIN, n, 1)
+    x = np.stack([lcg_noise(512, 1000 + v) for v in range(n)], axis=1)
+
+    def script(b):
+        out = []
+        b.stream_in(0, x[:256]); b.process_block(256); out.append(b.read_voice_out())
+        b.set_value(0, (800.0 + 10.0 * np.arange(n)).astype(np.float32))
+        b.set_value_ramp(2, 0.8, 64)
+        b.stream_in(0, x[256:]); b.process_block(256); out.append(b.read_voice_out())
+        return np.concatenate(out)
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.abs(yr).max() > 0.01
+    max_err, exact = assert_close(yg, yr, "TwinPeaks")
+    print(f"twin peaks: max_err={max_err:.3e} bit_exact={exact:.4f}")
+
+
+def test_twin_peaks_device_lcg_equals_host_noise():
+    n = 130
+    ref, gpu = both(O.K_TWIN, n, 1)
+    x = np.stack([lcg_noise(256, 1000 + 7 + v) for v in range(n)], axis=1)
+    ref.stream_in(0, x); ref.process_block(256)
+    gpu.stream_in_lcg(0, 1000, 7); gpu.process_block(256)
+    assert_close(gpu.read_voice_out(), ref.read_voice_out(), "TwinPeaks LCG")
+
+
+@pytest.mark.parametrize("kind", [O.K_SAT1, O.K_SAT4])
+def test_saturator(kind):
+    n = 200
+    ref, gpu = both(kind, n, 1)
+    f = (2000.0 * (0.5 + lcg_uniform(n, 5))).astype(np.float32)
+
+    def script(b):
+        b.set_value(0, f)
+        out = []
+        for frames in (256, 100, 156):
+            b.process_block(frames); out.append(b.read_voice_out())
+        return np.concatenate(out)
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.abs(yr).max() > 0.3
+    max_err, exact = assert_close(yg, yr, f"Sat kind={kind}")
+    assert gpu.latency_samples() == (8 if kind == O.K_SAT4 else 0)
+    print(f"sat {kind}: max_err={max_err:.3e} bit_exact={exact:.4f}")
+
+
+@pytest.mark.parametrize("kind", [O.K_SYNTH, O.K_SYNTH_ADSR])
+def test_readme_synth(kind):
+    n = 96
+    ref, gpu = both(kind, n, 1)
+
+    def script(b):
+        b.set_value(2, (55.0 * (1 + np.arange(n))).astype(np.float32))      # up to 5.3 kHz carriers
+        b.set_value(3, (300.0 + 200.0 * np.arange(n)).astype(np.float32))  # cutoffs 300 .. 19 kHz+
+        out = []
+        if kind == O.K_SYNTH_ADSR:
+            b.push_events([(v, v, GATE, 0.8) for v in range(n)])
+        b.process_block(512); out.append(b.read_voice_out())
+        b.set_value_ramp(0, 9.0, 200)
+        if kind == O.K_SYNTH_ADSR:
+            b.push_events([(v, 2 * v, GATE, 0.0) for v in range(n)])
+        b.process_block(512); out.append(b.read_voice_out())
+        return np.concatenate(out)
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.abs(yr).max() > 0.05
+    assert_close(yg, yr, f"Synth kind={kind}")
+
+
+def test_electric_piano_16_voice_instances():
+    n, vpi = 64, 16
+    ref, gpu = both(O.K_EPIANO, n, vpi)
+
+    def script(b):
+        out_v, out_i = [], []
+        for inst in range(n // vpi):
+            for k in range(5):
+                b.push_midi(inst, 2 * k + inst, [0x90, 40 + 7 * k + inst, 60 + 10 * k])
+        for _ in range(4):
+            b.process_block(512); out_v.append(b.read_voice_out()); out_i.append(b.read_instance_out())
+        for inst in range(n // vpi):
+            b.push_midi(inst, 5, [0x80, 40 + inst, 0])
+        b.set_value(3, 60.0)
+        for _ in range(2):
+            b.process_block(512); out_v.append(b.read_voice_out()); out_i.append(b.read_instance_out())
+        return np.concatenate(out_v), np.concatenate(out_i)
+
+    (vr, ir), (vg, ig) = drive((ref, gpu), script)
+    assert np.abs(ir).max() > 1e-3 and np.abs(ir[..., 0] - ir[..., 1]).max() > 1e-6
+    assert_close(vg, vr, "EPiano voice_out")
+    max_err, exact = assert_close(ig, ir, "EPiano instance_out (stereo)")
+    print(f"epiano: max_err={max_err:.3e} bit_exact={exact:.4f}")
+
+
+# --------------------------------------------------------------- invariants at full size
+def test_block_split_invariance_on_gpu():
+    n, vpi = 256, 8
+    a, b = engine(O.K_FM, n, vpi), engine(O.K_FM, n, vpi)
+    ev_on = [(v, (5 * v) % 200, GATE, 0.7) for v in range(n)]
+    a.push_events(ev_on); a.process_block(256); ya = a.read_voice_out()
+    y = []
+    b.push_events([e for e in ev_on if e[1] < 100]); b.process_block(100); y.append(b.read_voice_out())
+    b.push_events([(v, f - 100, i, s) for (v, f, i, s) in ev_on if f >= 100]); b.process_block(156); y.append(b.read_voice_out())
+    assert np.array_equal(ya, np.concatenate(y))
+
+
+def test_config2_full_size_65536_voices_properties():
+    """BASELINE config 2 at full size: oracle on a slice, exact fold / silence / determinism on all"""
+    n, vpi, frames = 65536, 8, 256
+    gpu = engine(O.K_FM, n, vpi)
+    notes = 36 + (np.arange(n) * 7) % 60
+    freq = (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32)
+    on = (np.arange(n) * 13) % frames
+    gpu.set_value(0, freq)
+    from oscen_b200 import abi
+    ev = np.zeros(n, dtype=abi.EVENT_DTYPE)
+    ev["voice"] = np.arange(n); ev["frame_offset"] = on; ev["input_id"] = GATE; ev["scalar"] = 0.5
+    gpu.push_events(ev)
+    gpu.process_block(frames)
+    v0 = gpu.read_voice_out(); i0 = gpu.read_instance_out()[:, :, 0]; m0 = gpu.read_mix()[:, 0]
+    # silent before each voice's gate-on frame
+    before = np.arange(frames)[:, None] < on[None, :]
+    assert np.all(v0[before] == 0.0)
+    assert np.array_equal(seq_sum_f32(v0.reshape(frames, n // vpi, vpi), axis=2), i0)
+    assert np.allclose(m0, i0.astype(np.float64).sum(axis=1), rtol=1e-4, atol=1e-3)
+    # slice parity: voices are independent, so an oracle bank of the first 64 voices must agree
+    ref = O.OracleBank(O.K_FM, 64, 8)
+    ref.set_value(0, freq[:64])
+    ref.push_events([(v, int(on[v]), GATE, 0.5) for v in range(64)])
+    ref.process_block(frames)
+    assert_close(v0[:, :64], ref.read_voice_out(), "config-2 slice")
+    # determinism: a second engine renders the identical bits
+    g2 = engine(O.K_FM, n, vpi)
+    g2.set_value(0, freq); g2.push_events(ev); g2.process_block(frames)
+    assert np.array_equal(g2.read_mix()[:, 0], m0)
+    assert np.array_equal(g2.read_voice_out(first_voice=n - 128, count=128), v0[:, n - 128:])

@@ -181,6 +181,11 @@ int  oscen_b200_get_stats(const oscen_b200_engine *e, oscen_b200_stats *out);
 /* device time of the last block's compute kernels, CUDA events on the engine stream (ms) */
 int  oscen_b200_last_block_ms(oscen_b200_engine *e, float *ms);
 int  oscen_b200_enable_timing(oscen_b200_engine *e, int on);
+/* device time of the last block's graph kernel alone (fused plan) / node sequence (node plan) */
+int  oscen_b200_last_kernel_ms(oscen_b200_engine *e, float *ms);
+/* benchmarking aid: overwrite a 256 MiB scratch buffer on the engine stream so the next block
+   starts with a cold L2 (126 MB) */
+int  oscen_b200_l2_flush(oscen_b200_engine *e);
 
 /* multi-GPU: voices are sharded across ranks (one engine per GPU per process); the only
    exchange is the mix-bus all-reduce.  id is an ncclUniqueId (128 bytes) from rank 0. */

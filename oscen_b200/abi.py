@@ -25,7 +25,7 @@ SYMBOLS = [
     "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
-    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_comm_unique_id", "oscen_b200_comm_init",
+    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init",
 ]
 
 
@@ -89,6 +89,8 @@ def load():
     L.oscen_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.oscen_b200_last_block_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.oscen_b200_enable_timing.argtypes = [vp, C.c_int]
+    L.oscen_b200_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.oscen_b200_l2_flush.argtypes = [vp]
     L.oscen_b200_comm_unique_id.argtypes = [vp]
     L.oscen_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     _lib = L
@@ -211,6 +213,14 @@ class Engine:
         ms = C.c_float()
         self._chk(self.L.oscen_b200_last_block_ms(self.h, C.byref(ms)), "last_block_ms")
         return ms.value
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._chk(self.L.oscen_b200_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
+        return ms.value
+
+    def l2_flush(self):
+        self._chk(self.L.oscen_b200_l2_flush(self.h), "l2_flush")
 
     def comm_init(self, rank, n_ranks, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

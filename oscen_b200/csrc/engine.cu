@@ -144,7 +144,8 @@ struct oscen_b200_engine {
     /* stats / timing */
     oscen_b200_stats stats{};
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
+    uint32_t *d_flush = nullptr;
     bool ev_valid = false;
 };
 
@@ -339,6 +340,8 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     cudaFreeHost(e->h_ptab); cudaFreeHost(e->h_events); cudaFreeHost(e->h_ctl); cudaFreeHost(e->h_mix);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->evk) cudaEventDestroy(e->evk);
+    cudaFree(e->d_flush);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -390,7 +393,7 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         CK(e, cudaMalloc(&e->d_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
         CK(e, cudaMemsetAsync(e->d_mix, 0, (size_t)kMaxBlock * e->channels * sizeof(float), e->stream));
         CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
-        CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1));
+        CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1)); CK(e, cudaEventCreate(&e->evk));
         if (cfg->plan == OSCEN_B200_PLAN_NODES) {
             e->d_streams.resize(14, nullptr);
             for (auto &p : e->d_streams) CK(e, cudaMalloc(&p, (size_t)kMaxBlock * n * sizeof(float)));
@@ -616,6 +619,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     int rc = 0;
     if (e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
         rc = launch_fused(e, general); if (rc) return rc;
+        if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         rc = launch_mix_reduce(e, frames); if (rc) return rc;
     } else {
         /* the launch sequence is captured once and replayed: per-block words live in BlockCtl */
@@ -634,6 +638,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             cudaGraphDestroy(g);
         }
         CK(e, cudaGraphLaunch(e->graph_exec, e->stream));
+        if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         e->stats.graph_launches++;
         e->stats.kernel_launches += e->graph_kernels;
     }
@@ -734,6 +739,25 @@ int oscen_b200_last_block_ms(oscen_b200_engine *e, float *ms) {
     CK(e, cudaSetDevice(e->cfg.device));
     CK(e, cudaEventSynchronize(e->ev1));
     CK(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return 0;
+}
+
+int oscen_b200_last_kernel_ms(oscen_b200_engine *e, float *ms) {
+    if (!e || !ms) return OSCEN_B200_E_ARG;
+    if (!e->ev_valid) { e->err = "last_kernel_ms: timing not enabled"; return OSCEN_B200_E_STATE; }
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaEventSynchronize(e->evk));
+    CK(e, cudaEventElapsedTime(ms, e->ev0, e->evk));
+    return 0;
+}
+
+int oscen_b200_l2_flush(oscen_b200_engine *e) {
+    if (!e) return OSCEN_B200_E_ARG;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const size_t words = (size_t)64 << 20;                 /* 256 MiB */
+    if (!e->d_flush) CK(e, cudaMalloc(&e->d_flush, words * sizeof(uint32_t)));
+    fill_u32_kernel<<<1184, 256, 0, e->stream>>>(e->d_flush, words, (uint32_t)e->stats.blocks);
+    CK(e, cudaGetLastError());
     return 0;
 }
 

@@ -173,6 +173,11 @@ class OracleBank:
 
     def push_events(self, events):
         """events: iterable of (voice, frame_offset, input_id, scalar)"""
+        if isinstance(events, np.ndarray) and events.dtype.itemsize == 16:      # same layout as orc_event
+            arr = np.ascontiguousarray(events)
+            if arr.size:
+                self._chk(self.L.orc_bank_push_events(self.h, arr.ctypes.data, arr.size), "push_events")
+            return
         ev = list(events)
         if not ev:
             return

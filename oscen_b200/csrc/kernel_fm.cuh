@@ -76,7 +76,13 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
     op3.phase = a.state[(size_t)(FM_OP3 + 0) * n + vs]; op3.prev = a.state[(size_t)(FM_OP3 + 1) * n + vs];
     op2.phase = a.state[(size_t)(FM_OP2 + 0) * n + vs]; op2.prev = a.state[(size_t)(FM_OP2 + 1) * n + vs];
     op1.phase = a.state[(size_t)(FM_OP1 + 0) * n + vs]; op1.prev = a.state[(size_t)(FM_OP1 + 1) * n + vs];
-    fmop_reset_cache(op3); fmop_reset_cache(op2); fmop_reset_cache(op1);
+#define OSC_FM_INCS()                                                        \
+    do {                                                                     \
+        op3.inc = fmop_phase_inc(P[I_FREQ], P[I_OP3_RATIO], sr);             \
+        op2.inc = fmop_phase_inc(P[I_FREQ], P[I_OP2_RATIO], sr);             \
+        op1.inc = fmop_phase_inc(P[I_FREQ], P[I_OP1_RATIO], sr);             \
+    } while (0)
+    OSC_FM_INCS();
     TptState tp;
     tpt_load(tp, a.state, FM_TPT, n, vs);
 
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
 #pragma unroll
                     for (uint32_t i = 0; i < I_FM_N; ++i)
                         if ((ramp_mask >> i) & 1u) P[i] = row[i];
+                    if (ramp_mask & ((1u << I_FREQ) | (1u << I_OP3_RATIO) | (1u << I_OP2_RATIO) | (1u << I_OP1_RATIO))) OSC_FM_INCS();
                 }
                 if (ec.due(f)) {
                     const uint32_t j = ec.end_of_frame(f);
@@ -135,6 +142,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                             adsr_on_gate(ef, e.scalar, P[I_F_A], P[I_F_R], df);
                         }
                     }
+                    OSC_FM_INCS();
                     ec.advance(j);
                 } else if (GENERAL && ramp_mask) {
                     if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
@@ -150,13 +158,13 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                 const float envf = adsr_process(ef, P[I_F_S], df);
                 const float feg = envf * P[I_ENV_AMT];                 /* filter_env_gain: Gain */
                 const float cutoff = feg + P[I_CUTOFF];                /* cutoff_mod: AddValue  */
-                const float o3 = fmop_process(op3, P[I_FREQ], P[I_OP3_RATIO], 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL], sr);
+                const float o3 = fmop_process(op3, 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL]);
                 const float mix = clampf(P[I_ROUTE], 0.0f, 1.0f);      /* op3_route: Crossfade  */
                 const float xa = o3 * (1.0f - mix);
                 const float xb = o3 * mix;
-                const float o2 = fmop_process(op2, P[I_FREQ], P[I_OP2_RATIO], xa, P[I_OP2_FB], env2, P[I_OP2_LEVEL], sr);
+                const float o2 = fmop_process(op2, xa, P[I_OP2_FB], env2, P[I_OP2_LEVEL]);
                 const float pm1 = o2 + xb;                             /* op1_mod_mixer: Mixer  */
-                const float o1 = fmop_process(op1, P[I_FREQ], P[I_OP1_RATIO], pm1, 0.0f, env1, 1.0f, sr);
+                const float o1 = fmop_process(op1, pm1, 0.0f, env1, 1.0f);
                 const float lp = tpt_process(tp, o1, cutoff, P[I_RES], 0.0f, sr);
                 y = lp * 0.3f;                                         /* output_gain: Gain(0.3) */
                 if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;

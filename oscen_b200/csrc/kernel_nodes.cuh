@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
     OSC_NODE_PROLOGUE(4)
     FmOpState s;
     s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
-    fmop_reset_cache(s);
+    s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
         float pm[kPF], en[kPF];
 #pragma unroll
@@ -107,9 +107,9 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
             if (f < frames) {
-                prm.ramps(a, ramp_mask, f);
-                if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                a.out0[(size_t)f * n + v] = fmop_process(s, prm.P[0], prm.P[1], pm[k], prm.P[2], en[k], prm.P[3], a.sr);
+                if (ramp_mask) { prm.ramps(a, ramp_mask, f); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
+                if (ec.due(f)) { ec.advance(prm.events(a, ec, f)); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
+                a.out0[(size_t)f * n + v] = fmop_process(s, pm[k], prm.P[2], en[k], prm.P[3]);
             }
         }
     }

@@ -104,60 +104,59 @@ OSC_D void adsr_on_gate(AdsrState &s, float velocity, float attack_raw, float re
 OSC_D float adsr_process(AdsrState &s, float sustain_in, const AdsrDerived &d) {
     const float sustain = clampf(sustain_in, 0.0f, 1.0f);
     const float sus = clampf(sustain * s.vel, 0.0f, 1.0f);
-    if (s.rem > 0u) {                                   /* adsr.rs:95-106 */
-        if (s.stage == ST_ATTACK) s.rem = umax(umin(s.rem, d.a_n), 1u);
-        else if (s.stage == ST_DECAY) s.rem = umax(umin(s.rem, d.d_n), 1u);
-        else if (s.stage == ST_RELEASE) s.rem = umax(umin(s.rem, d.r_n), 1u);
-    }
-    if (s.stage == ST_ATTACK) {
-        if (s.rem > 0u) {
-            s.level += (1.0f - s.level) * d.a_k;
-            s.rem -= 1u;
-            s.level = clampf(s.level, 0.0f, 1.0f);
+    const uint32_t st = s.stage;
+    const bool isA = st == ST_ATTACK, isD = st == ST_DECAY, isR = st == ST_RELEASE;
+    uint32_t rem = s.rem;
+    float level = s.level;
+    if (isA | isD | isR) {
+        /* adsr.rs:95-106: clamp the countdown to the (possibly changed) stage length */
+        const uint32_t lim = isA ? d.a_n : (isD ? d.d_n : d.r_n);
+        if (rem > 0u) {
+            rem = umax(umin(rem, lim), 1u);
+            float delta;
+            if (isR) {
+                /* update_release_increment(), adsr.rs:159-173 -- recomputed every sample */
+                const float cur = clampf(level, 0.0f, 1.0f);
+                delta = (cur <= 0.0f) ? 0.0f : -cur / (float)rem;
+            } else {
+                /* one-pole approach: level += (target - level) * coeff (adsr.rs:213,223) */
+                const float tgt = isA ? 1.0f : sus;
+                const float k = isA ? d.a_k : d.d_k;
+                delta = (tgt - level) * k;
+            }
+            level = clampf(level + delta, 0.0f, 1.0f);
+            rem -= 1u;
         }
-        if (s.rem == 0u) { s.level = 1.0f; s.stage = ST_DECAY; s.rem = d.d_n; }
-    } else if (s.stage == ST_DECAY) {
-        if (s.rem > 0u) {
-            s.level += (sus - s.level) * d.d_k;
-            s.rem -= 1u;
-            s.level = clampf(s.level, 0.0f, 1.0f);
+        if (rem == 0u) {                                 /* complete_stage(), adsr.rs:175-207 */
+            level = isA ? 1.0f : (isD ? sus : 0.0f);
+            s.stage = isA ? ST_DECAY : (isD ? ST_SUSTAIN : ST_IDLE);
+            rem = isA ? d.d_n : 0u;
         }
-        if (s.rem == 0u) { s.level = sus; s.stage = ST_SUSTAIN; }
-    } else if (s.stage == ST_RELEASE) {
-        if (s.rem > 0u) {
-            /* update_release_increment(), adsr.rs:159-173 — recomputed every sample */
-            const float cur = clampf(s.level, 0.0f, 1.0f);
-            const float inc = (cur <= 0.0f) ? 0.0f : -cur / (float)s.rem;
-            s.level += inc;
-            s.rem -= 1u;
-            s.level = clampf(s.level, 0.0f, 1.0f);
-        }
-        if (s.rem == 0u) { s.level = 0.0f; s.stage = ST_IDLE; }
-    } else if (s.stage == ST_SUSTAIN) {
-        s.level = sus;
     } else {
-        s.level = 0.0f;
+        level = (st == ST_SUSTAIN) ? sus : 0.0f;
     }
-    return s.level;
+    s.rem = rem;
+    s.level = level;
+    return level;
 }
 
 /* =================================================================== FmOperator == */
 /* examples/fm-synth/src/nodes/fm_operator.rs:58-76 */
 struct FmOpState {
     float phase, prev;
-    float freq_c, inc_c;      /* cache: phase_inc = frequency / sample_rate (not persisted) */
+    float inc;                /* phase_inc = (base_freq * ratio) / sample_rate; recomputed by the
+                                 caller whenever base_freq or ratio changes (not persisted) */
 };
-OSC_D void fmop_reset_cache(FmOpState &s) { s.freq_c = __int_as_float(0x7fc00000); s.inc_c = 0.0f; }
-OSC_D float fmop_process(FmOpState &s, float base_freq, float ratio, float phase_mod, float feedback,
-                         float envelope, float level, float sample_rate) {
-    const float frequency = base_freq * ratio;
+OSC_D float fmop_phase_inc(float base_freq, float ratio, float sample_rate) {
+    return (base_freq * ratio) / sample_rate;
+}
+OSC_D float fmop_process(FmOpState &s, float phase_mod, float feedback, float envelope, float level) {
     const float feedback_mod = s.prev * feedback;
     const float total_phase_mod = phase_mod + feedback_mod;
     const float phase_rad = (s.phase + total_phase_mod) * kTau;
-    const float out = om_sinf(phase_rad) * envelope * level;
+    const float out = om_sinf_u(phase_rad) * envelope * level;
     s.prev = out;
-    if (!(frequency == s.freq_c)) { s.freq_c = frequency; s.inc_c = frequency / sample_rate; }
-    s.phase += s.inc_c;
+    s.phase += s.inc;
     s.phase = fractf(s.phase);
     return out;
 }
@@ -238,9 +237,9 @@ OSC_D float polyblep_process(float &phase_state, float phase_mod, float frequenc
     if (pulse_width <= 0.0f) pulse_width = 0.0001f;
     float value;
     if (frequency >= sample_rate * 0.25f) {
-        value = om_sinf(phase * kTau);
+        value = om_sinf_u(phase * kTau);
     } else if (WAVE == WAVE_SINE) {
-        value = om_sinf(phase * kTau);
+        value = om_sinf_u(phase * kTau);
     } else if (WAVE == WAVE_SAW) {
         float y = 2.0f * phase - 1.0f;
         y -= poly_blep(phase, dt);
@@ -338,7 +337,7 @@ OSC_D float hb_down_step(float *hist, int stride, uint32_t &head, float x0, floa
 /* examples/electric-piano/src/tremolo.rs:41-61 */
 OSC_D void tremolo_process(float &phase, float input, float rate, float depth, float sample_rate,
                            float &out_l, float &out_r) {
-    const float lfo = om_sinf(phase * 2.0f * kPi);
+    const float lfo = om_sinf_u(phase * 2.0f * kPi);
     const float scaled_depth = depth / 3.0f;
     const float pan = 0.5f + lfo * scaled_depth;
     out_l = input * pan;

@@ -252,6 +252,60 @@ OM_HD float om_cosf(float y) {
     return y - y;
 }
 
+/* ---- branch-free forms for the kernels' inner loops --------------------------------------
+ * Same arithmetic as om_sinf / om_cosf (so the same bits as glibc), reorganised so that a warp
+ * whose lanes land in different quadrants does not execute three divergent paths:
+ *  - |y| < 0.75 takes reduce_fast too: there n = 0 and fma(-0.0, hpi, x) = x exactly, and for
+ *    |y| < 2^-12 the polynomial rounds back to y (x^3/6 is < 1/6 ulp);
+ *  - table[1] (quadrants 2,3) negates every cosine coefficient and sign[] negates x for the
+ *    sine polynomial; both polynomials are odd-symmetric under that negation in round-to-
+ *    nearest, so the result is the table[0] polynomial negated iff (n & 2);
+ *  - the sine and cosine polynomials share one 2-DMUL + 4-DFMA schedule with per-lane selected
+ *    constants (lane-select instead of branch).
+ * tests/csrc/check_om_math.cpp sweeps them against glibc (bit-exact). */
+OM_HD double om_sel(bool c, double a, double b) { return c ? a : b; }
+/* sinf for |y| < 120 (top12 < 0x42f); else the general routine */
+OM_HD float om_sinf_u(float y) {
+    const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
+    if (top >= 0x42f) return om_sinf(y);
+    double x = (double)y;
+    double r = x * OM_HPI_INV;
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = OM_MADD(-(double)n, OM_HPI, x);
+    const bool odd = (n & 1) != 0;
+    const double x2 = x * x;
+    const double a = om_sel(odd, x2, x) * x2;
+    const double p = OM_MADD(x2, om_sel(odd, OM_C4, OM_S3), om_sel(odd, OM_C3, OM_S2));
+    const double b = a * x2;
+    const double c1 = OM_MADD(x2, OM_C1, OM_C0);
+    const double q = om_sel(odd, c1, x);
+    const double sc = OM_MADD(a, om_sel(odd, OM_C2, OM_S1), q);
+    const float res = (float)OM_MADD(b, p, sc);
+    return (n & 2) ? -res : res;
+}
+OM_HD float om_cosf_u(float y) {
+    const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
+    if (top >= 0x42f) return om_cosf(y);
+    if (top < 0x398) return 1.0f;
+    double x = (double)y;
+    double r = x * OM_HPI_INV;
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = OM_MADD(-(double)n, OM_HPI, x);
+    const bool odd = ((n ^ 1) & 1) != 0;          /* sinf_poly(.., n ^ 1) */
+    const double x2 = x * x;
+    const double a = om_sel(odd, x2, x) * x2;
+    const double p = OM_MADD(x2, om_sel(odd, OM_C4, OM_S3), om_sel(odd, OM_C3, OM_S2));
+    const double b = a * x2;
+    const double c1 = OM_MADD(x2, OM_C1, OM_C0);
+    const double q = om_sel(odd, c1, x);
+    const double sc = OM_MADD(a, om_sel(odd, OM_C2, OM_S1), q);
+    const float res = (float)OM_MADD(b, p, sc);
+    /* even quadrant (cos poly): table sign from (n & 2); odd quadrant (sine poly on x*sign[n&3]):
+       sign[] = {1,-1,-1,1} */
+    const bool neg = odd ? ((n & 2) != 0) : (((n & 3) == 1) || ((n & 3) == 2));
+    return neg ? -res : res;
+}
+
 OM_HD float om_asfloat(uint32_t u) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(u);

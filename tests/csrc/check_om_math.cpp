@@ -56,6 +56,8 @@ int main(int argc, char **argv) {
     report("expf[|x|<=104]", sweep([](float x) { return om_expf(x); }, [](float x) { return expf(x); }, 0, F104, stride, nt));
     report("sinf[|x|<120]", sweep([](float x) { return om_sinf(x); }, [](float x) { return sinf(x); }, 0, F120 - 1, stride, nt));
     report("cosf[|x|<120]", sweep([](float x) { return om_cosf(x); }, [](float x) { return cosf(x); }, 0, F120 - 1, stride, nt));
+    report("sinf_u[all]", sweep([](float x) { return om_sinf_u(x); }, [](float x) { return sinf(x); }, 0, FINF - 1, stride, nt));
+    report("cosf_u[all]", sweep([](float x) { return om_cosf_u(x); }, [](float x) { return cosf(x); }, 0, FINF - 1, stride, nt));
     report("sinf[120<=|x|<inf]", sweep([](float x) { return om_sinf(x); }, [](float x) { return sinf(x); }, F120, FINF - 1, stride, nt));
     report("cosf[120<=|x|<inf]", sweep([](float x) { return om_cosf(x); }, [](float x) { return cosf(x); }, F120, FINF - 1, stride, nt));
     const uint32_t F2 = 0x40000000u, F12 = 0x41400000u;

@@ -117,7 +117,7 @@ typedef struct oscen_b200_engine oscen_b200_engine;
 typedef struct {
     uint32_t graph_kind;            /* OSCEN_B200_GRAPH_*                                    */
     uint32_t n_voices;              /* voices rendered by THIS engine (its shard)            */
-    uint32_t voices_per_instance;   /* N of `voices = [Voice::new(); N]`; divides 128        */
+    uint32_t voices_per_instance;   /* N of `voices = [Voice::new(); N]`; power of two <= 64 */
     float    sample_rate;           /* G::init(sample_rate)                                  */
     int32_t  device;                /* CUDA device ordinal                                   */
     uint32_t plan;                  /* OSCEN_B200_PLAN_*                                     */

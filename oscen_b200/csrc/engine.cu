@@ -350,9 +350,9 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
     if (!cfg || !out) { g_create_error = "null argument"; return OSCEN_B200_E_ARG; }
     *out = nullptr;
     if (cfg->graph_kind >= OSCEN_B200_GRAPH_COUNT || cfg->n_voices == 0 || cfg->voices_per_instance == 0 ||
-        kCta % cfg->voices_per_instance != 0 || cfg->n_voices % cfg->voices_per_instance != 0 ||
+        kCta % cfg->voices_per_instance != 0 || (cfg->voices_per_instance & (cfg->voices_per_instance - 1)) != 0 || cfg->n_voices % cfg->voices_per_instance != 0 ||
         !(cfg->sample_rate > 0.0f) || cfg->plan > OSCEN_B200_PLAN_NODES) {
-        g_create_error = "bad config (graph kind / voices / voices_per_instance must divide 128 and n_voices / sample rate / plan)";
+        g_create_error = "bad config (graph kind / voices / voices_per_instance must be a power of two <= 64 dividing n_voices / sample rate / plan)";
         return OSCEN_B200_E_ARG;
     }
     if (cfg->plan == OSCEN_B200_PLAN_NODES && cfg->graph_kind != OSCEN_B200_GRAPH_FM_VOICE) {

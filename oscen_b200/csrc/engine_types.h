@@ -11,9 +11,10 @@ namespace oscen {
 
 constexpr uint32_t kMaxInputs = 28;
 constexpr uint32_t kMaxBlock = 512;
-constexpr uint32_t kCta = 128;           /* voices per CTA (one thread = one voice) */
+constexpr uint32_t kCta = 64;            /* voices per CTA (one thread = one voice): small CTAs balance
+                                            148 SMs even at 65 536 voices (1024 CTAs, 6.9 per SM) */
 constexpr uint32_t kTileF = 32;          /* frames per shared-memory output tile */
-constexpr uint32_t kTileW = 192;         /* padded tile row: 128 + 128/vpi (vpi >= 2) <= 192 */
+constexpr uint32_t kTileW = kCta + kCta / 2;   /* padded tile row: kCta + kCta/vpi (vpi >= 2) */
 constexpr uint32_t kEventGate = 0xFFFFFFFFu;
 
 struct Event {                           /* == oscen_b200_event */

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
         adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
     } else {
         d3 = a.u.env[0]; d2 = a.u.env[1]; d1 = a.u.env[2]; df = a.u.env[3];
+        adsr_pin(d3); adsr_pin(d2); adsr_pin(d1); adsr_pin(df);
     }
 
     EventCursor ec;

@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(kCta) epiano_kernel(const __grid_constant__ Ke
             }
         }
         __syncthreads();
-        if (threadIdx.x < fe * 2u) {                       /* mix partial: in-order over the CTA's instances */
-            const uint32_t ff = threadIdx.x >> 1, c = threadIdx.x & 1u;
+        for (uint32_t t = threadIdx.x; t < fe * 2u; t += kCta) {   /* mix partial: in-order over the CTA's instances */
+            const uint32_t ff = t >> 1, c = t & 1u;
             float s = 0.0f;
             for (uint32_t i = 0; i < ipc; ++i) s = s + isum[(ff * kCta + i) * 2 + c];
             a.mix_partial[((size_t)blockIdx.x * kMaxBlock + f0 + ff) * 2 + c] = s;

@@ -55,8 +55,9 @@ OSC_D void tile_flush_mono(const KernelArgs &a, const float *tile, float *isum, 
     const uint32_t ipc = kCta / vpi;                       /* instances per CTA */
     const uint32_t inst0 = blockIdx.x * ipc;
     __syncthreads();
+    const uint32_t ipc_shift = 31u - (uint32_t)__clz((int)ipc);          /* ipc is a power of two */
     for (uint32_t t = threadIdx.x; t < fe * ipc; t += kCta) {
-        const uint32_t ff = t / ipc, i = t % ipc;
+        const uint32_t ff = t >> ipc_shift, i = t & (ipc - 1u);
         const float *row = tile + ff * kTileW;
         float s = 0.0f;
         const uint32_t c0 = tile_col(i * vpi, vpi);
@@ -66,21 +67,22 @@ OSC_D void tile_flush_mono(const KernelArgs &a, const float *tile, float *isum, 
             a.inst_out[(size_t)(f0 + ff) * a.n_inst + inst0 + i] = s;
     }
     __syncthreads();
-    /* mix partial: 4 threads per frame, each folds a quarter of the instances in order,
-       then ((q0+q1)+q2)+q3 — fixed shape, run-to-run deterministic */
+    /* mix partial: kCta/kTileF threads per frame, each folds its share of the instances in order,
+       then the shares are folded in lane order - fixed shape, run-to-run deterministic */
     {
-        const uint32_t ff = threadIdx.x >> 2, qd = threadIdx.x & 3u;
+        constexpr uint32_t TPF = kCta / kTileF;
+        const uint32_t ff = threadIdx.x / TPF, qd = threadIdx.x % TPF;
         float s = 0.0f;
         if (ff < fe) {
-            const uint32_t per = (ipc + 3u) / 4u;
+            const uint32_t per = (ipc + TPF - 1u) / TPF;
             const uint32_t b = qd * per, e = min(b + per, ipc);
             for (uint32_t i = b; i < e; ++i) s = s + isum[ff * kCta + i];
         }
-        const float s1 = __shfl_down_sync(0xffffffffu, s, 1);
-        const float s2 = __shfl_down_sync(0xffffffffu, s, 2);
-        const float s3 = __shfl_down_sync(0xffffffffu, s, 3);
+        float tot = s;
+#pragma unroll
+        for (uint32_t k = 1; k < TPF; ++k) tot = tot + __shfl_down_sync(0xffffffffu, s, k);
         if (qd == 0 && ff < fe)
-            a.mix_partial[(size_t)blockIdx.x * kMaxBlock + f0 + ff] = ((s + s1) + s2) + s3;
+            a.mix_partial[(size_t)blockIdx.x * kMaxBlock + f0 + ff] = tot;
     }
     __syncthreads();
 }

@@ -50,8 +50,16 @@ OSC_HD float rem_euclid1(float x) {
     if (r == 0.0f) r = copysignf(0.0f, x);
     return (r < 0.0f) ? r + 1.0f : r;
 }
-/* f32::fract */
-OSC_HD float fractf(float x) { return x - truncf(x); }
+/* f32::fract = x - trunc(x).  For 0 <= x < 2 (every phase accumulator in normal operation)
+   trunc(x) is 0 or 1, which avoids the slow-pipe FRND; other inputs take the general form. */
+OSC_HD float fractf(float x) {
+    if (x >= 0.0f && x < 2.0f) return (x >= 1.0f) ? x - 1.0f : x - 0.0f;
+    return x - truncf(x);
+}
+/* keep a loop-invariant value in a register (stops the compiler from re-loading it from the
+   constant bank inside the frame loop, where LDC latency is exposed) */
+OSC_D float pin(float x) { asm volatile("" : "+f"(x)); return x; }
+OSC_D uint32_t pin(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 
 /* ================================================================= AdsrEnvelope == */
 /* oscen-lib/src/envelope/adsr.rs */
@@ -79,6 +87,9 @@ OSC_HD void adsr_derive(AdsrDerived &d, float attack, float decay, float release
     d.r_n = umax(f32_as_u32(fmaxf(release, kAdsrMinTime) * sr), 1u);
     d.a_k = 1.0f - om_expf(-kAdsrCurveK / (float)d.a_n);
     d.d_k = 1.0f - om_expf(-kAdsrCurveK / (float)d.d_n);
+}
+OSC_D void adsr_pin(AdsrDerived &d) {
+    d.a_n = pin(d.a_n); d.d_n = pin(d.d_n); d.r_n = pin(d.r_n); d.a_k = pin(d.a_k); d.d_k = pin(d.d_k);
 }
 OSC_HD bool adsr_derived_stale(const AdsrDerived &d, float attack, float decay, float release) {
     return !(d.attack == attack && d.decay == decay && d.release == release);

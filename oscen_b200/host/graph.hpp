@@ -1,0 +1,130 @@
+/*
+ * graph.hpp — C++ host-side mirror of the API surface Oscen's `graph!` macro generates
+ * (oscen-graph-compiler/src/codegen/mod.rs:1292-1392), for the graphs on the hot path, on top of
+ * the C ABI in include/oscen_b200.h.  It exists because the reference's host language (Rust,
+ * nightly) is not available in this build environment; INTEGRATION.md shows the equivalent Rust
+ * shim.  Names follow the generated struct: new()/init() -> constructor, `set_<input>`,
+ * `set_<input>_with_ramp`, `<event>.try_push`, `process_block(frames)`, `<out>_block`.
+ *
+ * A `Bank<...>` owns N independent instances of one generated graph (what N separate
+ * `FMGraph::new()` values would be), rendered together on one B200.
+ * Header-only; link with oscen_b200/lib/liboscen_b200.so.  Throws std::runtime_error on a
+ * non-zero ABI return (the reference's process* are infallible; an error here is a CUDA error
+ * or a misuse).
+ */
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/oscen_b200.h"
+
+namespace oscen_b200 {
+
+inline void check(int rc, oscen_b200_engine *e, const char *what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + oscen_b200_last_error(e));
+}
+
+/* EventInstance { frame_offset, payload: Scalar(v) } for one voice's `gate` input */
+struct GateEvent { uint32_t voice, frame_offset; float velocity; };
+
+class Bank {
+public:
+    Bank(uint32_t graph_kind, uint32_t instances, uint32_t voices_per_instance, float sample_rate,
+         int device = 0, uint32_t plan = OSCEN_B200_PLAN_FUSED,
+         uint32_t keep = OSCEN_B200_KEEP_INSTANCE_OUT)
+        : instances_(instances), vpi_(voices_per_instance) {
+        oscen_b200_config cfg{};
+        cfg.graph_kind = graph_kind; cfg.n_voices = instances * voices_per_instance;
+        cfg.voices_per_instance = voices_per_instance; cfg.sample_rate = sample_rate;   /* G::init(sr) */
+        cfg.device = device; cfg.plan = plan; cfg.keep = keep;
+        int rc = oscen_b200_create(&cfg, &e_);
+        if (rc != 0) throw std::runtime_error(std::string("oscen_b200_create: ") + oscen_b200_last_error(nullptr));
+        channels_ = oscen_b200_channels(e_);
+    }
+    ~Bank() { oscen_b200_destroy(e_); }
+    Bank(const Bank &) = delete;
+    Bank &operator=(const Bank &) = delete;
+
+    /* `g.<value> = v` on every instance */
+    void set_value(uint32_t input, float v) { check(oscen_b200_set_value(e_, input, 0, instances_ * vpi_, &v, 1), e_, "set_value"); }
+    /* per-voice values (e.g. MidiVoiceHandler::frequency) */
+    void set_values(uint32_t input, const std::vector<float> &v, uint32_t first_voice = 0) {
+        check(oscen_b200_set_value(e_, input, first_voice, (uint32_t)v.size(), v.data(), 0), e_, "set_value");
+    }
+    /* set_<v>_with_ramp(value, frames) */
+    void set_value_with_ramp(uint32_t input, float v, uint32_t frames) { check(oscen_b200_set_value_ramp(e_, input, v, frames), e_, "set_value_ramp"); }
+    /* gate.try_push(EventInstance{frame_offset, Scalar(velocity)}) */
+    void push_gates(const std::vector<GateEvent> &g) {
+        std::vector<oscen_b200_event> ev(g.size());
+        for (size_t i = 0; i < g.size(); ++i) ev[i] = {g[i].voice, g[i].frame_offset, OSCEN_B200_EVENT_GATE, g[i].velocity};
+        check(oscen_b200_push_events(e_, ev.data(), ev.size()), e_, "push_events");
+    }
+    /* midi_in.try_push(raw_midi_event(bytes)) on one instance */
+    void push_midi(uint32_t instance, uint32_t frame_offset, const uint8_t bytes[3]) {
+        check(oscen_b200_push_midi(e_, instance, frame_offset, bytes, 3), e_, "push_midi");
+    }
+    /* writing `audio_in_block` of every instance: [frames][voices] */
+    void stream_in(const float *host, uint32_t frames) { check(oscen_b200_stream_in(e_, 0, host, frames, 0), e_, "stream_in"); }
+
+    void process_block(uint32_t frames) { check(oscen_b200_process_block(e_, frames), e_, "process_block"); frames_ = frames; }
+
+    /* `<out>_block` of instances [first, first+count): [frames][count][channels] */
+    std::vector<float> out_block(uint32_t first = 0, uint32_t count = 0) {
+        if (count == 0) count = instances_ - first;
+        std::vector<float> out((size_t)frames_ * count * channels_);
+        check(oscen_b200_read_instance_out(e_, out.data(), first, count), e_, "read_instance_out");
+        return out;
+    }
+    /* the bank's mix bus: [frames][channels] */
+    std::vector<float> mix() {
+        std::vector<float> out((size_t)frames_ * channels_);
+        check(oscen_b200_read_mix(e_, out.data()), e_, "read_mix");
+        return out;
+    }
+    uint32_t latency_samples() const { return oscen_b200_latency_samples(e_); }
+    uint32_t channels() const { return channels_; }
+    oscen_b200_engine *raw() { return e_; }
+
+    static constexpr uint32_t MAX_BLOCK_SIZE = OSCEN_B200_MAX_BLOCK;   /* Self::MAX_BLOCK_SIZE */
+
+private:
+    oscen_b200_engine *e_ = nullptr;
+    uint32_t instances_, vpi_, channels_ = 1, frames_ = 0;
+};
+
+/* FMGraph x N: examples/fm-synth/src/lib.rs:22-131 (8 voices per instance, ramped level /
+   feedback / route / cutoff / resonance / env_amount inputs with 2205-frame default ramps) */
+class FMGraphBank : public Bank {
+public:
+    FMGraphBank(uint32_t instances, float sample_rate, int device = 0)
+        : Bank(OSCEN_B200_GRAPH_FM_VOICE, instances, 8, sample_rate, device) {}
+    static constexpr uint32_t DEFAULT_RAMP = 2205;
+    /* set_<v>(value): ramp over the declared default duration for `[ramp: 2205]` inputs */
+    void set_op3_level(float v) { set_value_with_ramp(OSCEN_B200_FM_OP3_LEVEL, v, DEFAULT_RAMP); }
+    void set_op3_feedback(float v) { set_value_with_ramp(OSCEN_B200_FM_OP3_FEEDBACK, v, DEFAULT_RAMP); }
+    void set_op2_level(float v) { set_value_with_ramp(OSCEN_B200_FM_OP2_LEVEL, v, DEFAULT_RAMP); }
+    void set_op2_feedback(float v) { set_value_with_ramp(OSCEN_B200_FM_OP2_FEEDBACK, v, DEFAULT_RAMP); }
+    void set_route(float v) { set_value_with_ramp(OSCEN_B200_FM_ROUTE, v, DEFAULT_RAMP); }
+    void set_filter_cutoff(float v) { set_value_with_ramp(OSCEN_B200_FM_FILTER_CUTOFF, v, DEFAULT_RAMP); }
+    void set_filter_resonance(float v) { set_value_with_ramp(OSCEN_B200_FM_FILTER_RESONANCE, v, DEFAULT_RAMP); }
+    void set_filter_env_amount(float v) { set_value_with_ramp(OSCEN_B200_FM_FILTER_ENV_AMOUNT, v, DEFAULT_RAMP); }
+    /* plain value inputs: direct field assignment in the reference (main.rs:168-194) */
+    void set_op3_ratio(float v) { set_value(OSCEN_B200_FM_OP3_RATIO, v); }
+    void set_op2_ratio(float v) { set_value(OSCEN_B200_FM_OP2_RATIO, v); }
+    void set_op3_attack(float v) { set_value(OSCEN_B200_FM_OP3_ATTACK, v); }
+    void set_op3_release(float v) { set_value(OSCEN_B200_FM_OP3_RELEASE, v); }
+};
+
+/* TwinPeaksGraph x N: examples/nih-twin-peaks/src/lib.rs:15-48 */
+class TwinPeaksBank : public Bank {
+public:
+    TwinPeaksBank(uint32_t instances, float sample_rate, int device = 0)
+        : Bank(OSCEN_B200_GRAPH_TWIN_PEAKS, instances, 1, sample_rate, device) {}
+    void set_cutoff_a(float v) { set_value(OSCEN_B200_TWIN_CUTOFF_A, v); }
+    void set_cutoff_b(float v) { set_value(OSCEN_B200_TWIN_CUTOFF_B, v); }
+    void set_resonance(float v) { set_value(OSCEN_B200_TWIN_RESONANCE, v); }
+};
+
+}  // namespace oscen_b200

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -95,6 +96,7 @@ bool nccl_load(std::string &err) {
 struct oscen_b200_engine {
     oscen_b200_config cfg{};
     uint32_t n_inputs = 0, n_state = 0, n_inst = 0, channels = 1, n_cta = 0;
+    uint32_t n_cta_mix = 0;          /* CTAs that wrote mix partials in the last block */
     cudaStream_t stream = nullptr;
     std::string err;
 
@@ -237,6 +239,7 @@ constexpr size_t kEpDyn = (EP_NSTATE * kCta + kTileF * kTileW + kTileF * kCta * 
 int launch_fused(oscen_b200_engine *e, bool general) {
     KernelArgs a; fill_args(e, a);
     const uint32_t grid = e->n_cta;
+    e->n_cta_mix = grid;
     switch (e->cfg.graph_kind) {
     case OSCEN_B200_GRAPH_FM_VOICE:
         if (general) fm_voice_kernel<true><<<grid, kCta, 0, e->stream>>>(a);
@@ -294,7 +297,7 @@ int launch_fm_nodes(oscen_b200_engine *e) {
     { NodeArgs n = base(0); n.in0 = S[12]; n.cst[0] = 0.3f; n.out0 = S[13];                    /* output_gain */
       ew_node_kernel<EW_GAIN><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
     { KernelArgs a; fill_args(e, a); a.voice_out = nullptr;                                   /* voices.audio_out -> audio_out */
-      instance_mix_node_kernel<<<grid, kCta, 0, e->stream>>>(a, S[13]); e->stats.kernel_launches++; }
+      instance_mix_node_kernel<<<grid, kCta, 0, e->stream>>>(a, S[13]); e->stats.kernel_launches++; e->n_cta_mix = grid; }
     { const uint32_t g = 296;
       commit_value_events_kernel<<<g, 256, 0, e->stream>>>(e->d_pv, e->d_events, e->d_ctl, e->cfg.n_voices, e->n_inputs);
       e->stats.kernel_launches++; }
@@ -303,7 +306,7 @@ int launch_fm_nodes(oscen_b200_engine *e) {
 }
 
 int launch_mix_reduce(oscen_b200_engine *e, uint32_t frames) {
-    mix_reduce_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta, e->channels, e->d_ctl);
+    mix_reduce_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta_mix, e->channels, e->d_ctl);
     (void)frames;
     e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
@@ -371,6 +374,7 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
     e->n_inst = n / cfg->voices_per_instance;
     e->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2 : 1;
     e->n_cta = (n + kCta - 1) / kCta;
+    e->n_cta_mix = e->n_cta;
     int rc = [&]() -> int {
         CK(e, cudaSetDevice(cfg->device));
         CK(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

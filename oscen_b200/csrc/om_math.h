@@ -265,9 +265,16 @@ OM_HD float om_cosf(float y) {
  * tests/csrc/check_om_math.cpp sweeps them against glibc (bit-exact). */
 OM_HD double om_sel(bool c, double a, double b) { return c ? a : b; }
 /* sinf for |y| < 120 (top12 < 0x42f); else the general routine */
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ float om_sinf_slow(float y) { return om_sinf(y); }   /* |y| >= 120: cold */
+static __device__ __noinline__ float om_cosf_slow(float y) { return om_cosf(y); }
+#else
+static inline float om_sinf_slow(float y) { return om_sinf(y); }
+static inline float om_cosf_slow(float y) { return om_cosf(y); }
+#endif
 OM_HD float om_sinf_u(float y) {
     const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
-    if (top >= 0x42f) return om_sinf(y);
+    if (top >= 0x42f) return om_sinf_slow(y);
     double x = (double)y;
     double r = x * OM_HPI_INV;
     const int n = ((int32_t)r + 0x800000) >> 24;
@@ -285,7 +292,7 @@ OM_HD float om_sinf_u(float y) {
 }
 OM_HD float om_cosf_u(float y) {
     const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
-    if (top >= 0x42f) return om_cosf(y);
+    if (top >= 0x42f) return om_cosf_slow(y);
     if (top < 0x398) return 1.0f;
     double x = (double)y;
     double r = x * OM_HPI_INV;

@@ -313,8 +313,14 @@ def main():
         alg_bytes = n * FRAMES * MODEL_N_BYTES
         model = "N (node-granular): 4*(14 W + 14 R) + (2*116 + P)/256 bytes per voice-sample"
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel at this
+    # size (profiles/r01_ncu_fm_fused_v2.md: dram__bytes_read.sum 7.92 MB + dram__bytes_write.sum 0:
+    # the outputs and the written-back state of a 24 MB working set are still in the 126 MB L2 when the
+    # kernel ends); null for configurations that were not captured
+    traffic = 7920896 if (args.plan == "fused" and n == 65536) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": kernel, "kernel_ms": k_ms,
+                "traffic": traffic, "traffic_source": "profiles/r01_ncu_fm_fused_v2.md" if traffic else None,
+                "peak_source": peak_src, "kernel": kernel, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "byte_model": model,
                 "model_n_equivalent_frac": (MODEL_N_BYTES * n * FRAMES / (k_ms * 1e-3) / 1e9) / peak,
                 "note": "the fused kernel is FP32/FP64-issue bound, not HBM bound; see DESIGN.md and profiles/"}

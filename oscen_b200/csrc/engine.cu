@@ -119,6 +119,7 @@ struct oscen_b200_engine {
     Event *d_events = nullptr, *h_events = nullptr;
     size_t events_cap = 0;
     BlockCtl *d_ctl = nullptr, *h_ctl = nullptr;
+    BlockCtl ctl_on_device{};
 
     /* stream input */
     float *d_stream_in = nullptr;
@@ -136,8 +137,8 @@ struct oscen_b200_engine {
 
     /* node plan */
     std::vector<float *> d_streams;
-    cudaGraphExec_t graph_exec = nullptr;
-    uint64_t graph_kernels = 0;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   /* [0] no value events, [1] with */
+    uint64_t graph_kernels[2] = {0, 0};
 
     /* multi-GPU */
     void *comm = nullptr;
@@ -233,7 +234,7 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
 }
 
 constexpr size_t kSatDyn = (kTileF * kCta + 2 * 24 * kCta) * sizeof(float);
-constexpr size_t kEpDyn = (EP_NSTATE * kCta + kTileF * kTileW + kTileF * kCta * 2) * sizeof(float);
+constexpr size_t kEpDyn = (kTileF * kCta + kTileF * kTileW + kTileF * kCta * 2) * sizeof(float);
 
 /* ---- fused plan: one graph kernel + the mix-bus reduction */
 int launch_fused(oscen_b200_engine *e, bool general) {
@@ -260,7 +261,7 @@ int launch_fused(oscen_b200_engine *e, bool general) {
 /* ---- node plan (FM_VOICE): the generated topological order as a launch sequence.
    stream buffers: 0 env3 1 env2 2 env1 3 env_filter 4 filter_env_gain 5 cutoff_mod 6 op3 7 route_a
    8 route_b 9 op2 10 mixer 11 op1 12 filter 13 output_gain */
-int launch_fm_nodes(oscen_b200_engine *e) {
+int launch_fm_nodes(oscen_b200_engine *e, bool value_events) {
     const uint32_t grid = e->n_cta;
     auto base = [&](uint32_t state_base) {
         NodeArgs n{};
@@ -270,32 +271,43 @@ int launch_fm_nodes(oscen_b200_engine *e) {
         return n;
     };
     float **S = e->d_streams.data();
-    auto adsr = [&](uint32_t sb, uint32_t a0, uint32_t out) {
+    /* stateless nodes: float4 stream form unless this block carries value events (per-voice,
+       per-frame changes of a value input need the serial per-voice form) */
+    const bool vec = !value_events && (e->cfg.n_voices % 4u == 0u);
+    const uint32_t vgrid = 148u * 8u;
+    auto adsr_args = [&](uint32_t sb, uint32_t a0, uint32_t out) {
         NodeArgs n = base(sb); n.pid[0] = a0; n.pid[1] = a0 + 1; n.pid[2] = a0 + 2; n.pid[3] = a0 + 3; n.out0 = S[out];
-        adsr_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++;
+        return n;
     };
-    adsr(FM_E3, I_OP3_A, 0); adsr(FM_E2, I_OP2_A, 1); adsr(FM_E1, I_OP1_A, 2); adsr(FM_EF, I_F_A, 3);
-    { NodeArgs n = base(0); n.in0 = S[3]; n.pid[0] = I_ENV_AMT; n.out0 = S[4];                 /* filter_env_gain */
-      ew_node_kernel<EW_GAIN><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[4]; n.pid[0] = I_CUTOFF; n.out0 = S[5];                  /* cutoff_mod */
-      ew_node_kernel<EW_ADD_VALUE><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    {   /* env3, env2, env1, env_filter: one launch for the node type */
+        NodeArgs4 a4;
+        a4.n[0] = adsr_args(FM_E3, I_OP3_A, 0); a4.n[1] = adsr_args(FM_E2, I_OP2_A, 1);
+        a4.n[2] = adsr_args(FM_E1, I_OP1_A, 2); a4.n[3] = adsr_args(FM_EF, I_F_A, 3);
+        adsr_node_kernel<<<dim3(grid, 4), kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++;
+    }
+#define OSC_EW(OP, ARGS)                                                                   \
+    do {                                                                                   \
+        if (vec) ew_node_vec_kernel<OP><<<vgrid, 256, 0, e->stream>>>(ARGS);               \
+        else ew_node_kernel<OP><<<grid, kCta, 0, e->stream>>>(ARGS);                       \
+        e->stats.kernel_launches++;                                                        \
+    } while (0)
+    { NodeArgs n = base(0); n.in0 = S[3]; n.pid[0] = I_ENV_AMT; n.out0 = S[4]; OSC_EW(EW_GAIN, n); }        /* filter_env_gain */
+    { NodeArgs n = base(0); n.in0 = S[4]; n.pid[0] = I_CUTOFF; n.out0 = S[5]; OSC_EW(EW_ADD_VALUE, n); }    /* cutoff_mod */
     { NodeArgs n = base(FM_OP3); n.in0 = nullptr; n.in1 = S[0]; n.out0 = S[6];                 /* op3_osc */
       n.pid[0] = I_FREQ; n.pid[1] = I_OP3_RATIO; n.pid[2] = I_OP3_FB; n.pid[3] = I_OP3_LEVEL;
       fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[6]; n.pid[0] = I_ROUTE; n.out0 = S[7]; n.out1 = S[8];     /* op3_route */
-      ew_node_kernel<EW_CROSSFADE><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[6]; n.pid[0] = I_ROUTE; n.out0 = S[7]; n.out1 = S[8]; OSC_EW(EW_CROSSFADE, n); }   /* op3_route */
     { NodeArgs n = base(FM_OP2); n.in0 = S[7]; n.in1 = S[1]; n.out0 = S[9];                    /* op2_osc */
       n.pid[0] = I_FREQ; n.pid[1] = I_OP2_RATIO; n.pid[2] = I_OP2_FB; n.pid[3] = I_OP2_LEVEL;
       fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[9]; n.in1 = S[8]; n.out0 = S[10];                        /* op1_mod_mixer */
-      ew_node_kernel<EW_MIXER><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[9]; n.in1 = S[8]; n.out0 = S[10]; OSC_EW(EW_MIXER, n); }                        /* op1_mod_mixer */
     { NodeArgs n = base(FM_OP1); n.in0 = S[10]; n.in1 = S[2]; n.out0 = S[11];                  /* op1_osc */
       n.pid[0] = I_FREQ; n.pid[1] = I_OP1_RATIO; n.cst[2] = 0.0f; n.cst[3] = 1.0f;            /* feedback, level unconnected */
       fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
     { NodeArgs n = base(FM_TPT); n.in0 = S[11]; n.in1 = S[5]; n.pid[0] = I_RES; n.out0 = S[12]; /* filter */
       tpt_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[12]; n.cst[0] = 0.3f; n.out0 = S[13];                    /* output_gain */
-      ew_node_kernel<EW_GAIN><<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
+    { NodeArgs n = base(0); n.in0 = S[12]; n.cst[0] = 0.3f; n.out0 = S[13]; OSC_EW(EW_GAIN, n); }                    /* output_gain */
+#undef OSC_EW
     { KernelArgs a; fill_args(e, a); a.voice_out = nullptr;                                   /* voices.audio_out -> audio_out */
       instance_mix_node_kernel<<<grid, kCta, 0, e->stream>>>(a, S[13]); e->stats.kernel_launches++; e->n_cta_mix = grid; }
     { const uint32_t g = 296;
@@ -335,7 +347,7 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    for (auto &g : e->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (float *p : e->d_streams) cudaFree(p);
     cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
     cudaFree(e->d_events); cudaFree(e->d_ctl); cudaFree(e->d_stream_in);
@@ -560,7 +572,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         return e->seqs[x] < e->seqs[y];
     });
     uint32_t n_ev = 0;
-    bool general = false;
+    bool general = false, has_value_events = false;
     {
         if (order.size() > e->events_cap) {
             CK(e, cudaStreamSynchronize(e->stream));
@@ -568,7 +580,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             e->events_cap = order.size() * 2;
             CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
             CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
-            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
         }
         /* the pinned staging buffer may still be in flight from the previous block */
         if (!order.empty()) CK(e, cudaStreamSynchronize(e->stream));
@@ -582,7 +594,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             } else if (x.input_id != 0u || kind != OSCEN_B200_GRAPH_FM_VOICE) {
                 general = true;
             }
-            if (x.input_id != kEventGate) e->uniform[x.input_id] = false;
+            if (x.input_id != kEventGate) { e->uniform[x.input_id] = false; has_value_events = true; }
             e->h_events[n_ev++] = x;
         }
     }
@@ -612,11 +624,11 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         CK(e, cudaMemcpyAsync(e->d_events, e->h_events, (size_t)n_ev * sizeof(Event), cudaMemcpyHostToDevice, e->stream));
         e->stats.h2d_bytes += (uint64_t)n_ev * sizeof(Event);
     }
-    {
-        /* BlockCtl is tiny: copy by value through a kernel-parameter-free memcpy from pageable-safe staging */
-        BlockCtl ctl = *e->h_ctl;
-        CK(e, cudaMemcpyAsync(e->d_ctl, &ctl, sizeof ctl, cudaMemcpyHostToDevice, e->stream));
-        e->stats.h2d_bytes += sizeof ctl;
+    if (memcmp(&e->ctl_on_device, e->h_ctl, sizeof(BlockCtl)) != 0) {
+        /* BlockCtl only travels when it changed (steady-state blocks have no events / ramps) */
+        e->ctl_on_device = *e->h_ctl;
+        CK(e, cudaMemcpyAsync(e->d_ctl, &e->ctl_on_device, sizeof(BlockCtl), cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += sizeof(BlockCtl);
     }
 
     if (e->timing) CK(e, cudaEventRecord(e->ev0, e->stream));
@@ -626,36 +638,38 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         rc = launch_mix_reduce(e, frames); if (rc) return rc;
     } else {
-        /* the launch sequence is captured once and replayed: per-block words live in BlockCtl */
-        if (!e->graph_exec) {
+        /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
+        const int gi = has_value_events ? 1 : 0;
+        if (!e->graph_exec[gi]) {
             cudaGraph_t g = nullptr;
             CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t before = e->stats.kernel_launches;
-            rc = launch_fm_nodes(e);
+            rc = launch_fm_nodes(e, has_value_events);
             if (!rc) rc = launch_mix_reduce(e, frames);
             cudaError_t s = cudaStreamEndCapture(e->stream, &g);
-            e->graph_kernels = e->stats.kernel_launches - before;
+            e->graph_kernels[gi] = e->stats.kernel_launches - before;
             e->stats.kernel_launches = before;
             if (rc) return rc;
             CK(e, s);
-            CK(e, cudaGraphInstantiate(&e->graph_exec, g, 0));
+            CK(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
             cudaGraphDestroy(g);
         }
-        CK(e, cudaGraphLaunch(e->graph_exec, e->stream));
+        CK(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         e->stats.graph_launches++;
-        e->stats.kernel_launches += e->graph_kernels;
+        e->stats.kernel_launches += e->graph_kernels[gi];
     }
     if (e->comm) {
         const int r = g_nccl.AllReduce(e->d_mix, e->d_mix, (size_t)frames * e->channels, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, e->stream);
         if (r != 0) { e->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return OSCEN_B200_E_NCCL; }
     }
     if (e->timing) { CK(e, cudaEventRecord(e->ev1, e->stream)); e->ev_valid = true; }
-    /* ramp-driven inputs end the block at their last per-frame value */
+    /* ramp-driven inputs end the block at their last per-frame value; the per-voice row is only
+       read again once the input has stopped ramping, so it is refilled when the ramp completes */
     if (ramp_mask) {
         for (uint32_t i = 0; i < e->n_inputs; ++i) if ((ramp_mask >> i) & 1u) {
             e->uni[i] = e->ramps[i].current;
-            rc = fill_row(e, i, 0, n, e->uni[i]); if (rc) return rc;
+            if (e->ramps[i].remaining == 0) { rc = fill_row(e, i, 0, n, e->uni[i]); if (rc) return rc; }
         }
     }
     e->last_frames = frames;
@@ -782,7 +796,7 @@ int oscen_b200_comm_init(oscen_b200_engine *e, int rank, int n_ranks, const void
     const int r = g_nccl.CommInitRank(&e->comm, n_ranks, id, rank);
     if (r != 0) { e->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); e->comm = nullptr; return OSCEN_B200_E_NCCL; }
     e->rank = rank; e->n_ranks = n_ranks;
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }
 

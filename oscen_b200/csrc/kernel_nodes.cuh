@@ -68,8 +68,12 @@ struct NodeParams {
     NodeParams<NP> prm; prm.load(a, v);                                                   \
     EventCursor ec; ec.init(a.events, a.ctl->n_events, v);
 
-/* AdsrEnvelope node: pid = {attack, decay, sustain, release}; out0 = output */
-__global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__ NodeArgs a) {
+/* AdsrEnvelope node type: pid = {attack, decay, sustain, release}; out0 = output.
+   One launch renders every AdsrEnvelope node of the graph (blockIdx.y = node): the nodes are
+   mutually independent sources, and 4x the warps hide the serial recurrence's latency. */
+struct NodeArgs4 { NodeArgs n[4]; };
+__global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    const NodeArgs &a = args.n[blockIdx.y];
     OSC_NODE_PROLOGUE(4)
     AdsrState s; adsr_load(s, a.state, a.state_base, n, v);
     AdsrDerived d; adsr_derive(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__
                 adsr_on_gate(s, ec.ev[q].scalar, prm.P[0], prm.P[3], d);
             ec.advance(j);
         }
-        a.out0[(size_t)f * n + v] = adsr_process(s, prm.P[2], d);
+        __stcs(a.out0 + (size_t)f * n + v, adsr_process(s, prm.P[2], d));
     }
     adsr_store(s, a.state, a.state_base, n, v);
 }
@@ -95,24 +99,30 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
     FmOpState s;
     s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
     s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
+    /* software pipeline: the loads of chunk k+1 are in flight while chunk k is computed */
+    float pm[kPF], en[kPF], pm_n[kPF], en_n[kPF];
+#define OSC_FMOP_LOAD(PM, EN, F0)                                                             \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                    \
+        const uint32_t f = (F0) + k;                                                          \
+        PM[k] = (a.in0 != nullptr && f < frames) ? __ldcs(a.in0 + (size_t)f * n + v) : 0.0f;  \
+        EN[k] = (f < frames) ? __ldcs(a.in1 + (size_t)f * n + v) : 0.0f;                      \
+    }
+    OSC_FMOP_LOAD(pm, en, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        float pm[kPF], en[kPF];
-#pragma unroll
-        for (uint32_t k = 0; k < kPF; ++k) {
-            const uint32_t f = f0 + k;
-            pm[k] = (a.in0 != nullptr && f < frames) ? __ldg(a.in0 + (size_t)f * n + v) : 0.0f;
-            en[k] = (f < frames) ? __ldg(a.in1 + (size_t)f * n + v) : 0.0f;
-        }
+        OSC_FMOP_LOAD(pm_n, en_n, f0 + kPF)
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
             if (f < frames) {
                 if (ramp_mask) { prm.ramps(a, ramp_mask, f); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
                 if (ec.due(f)) { ec.advance(prm.events(a, ec, f)); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
-                a.out0[(size_t)f * n + v] = fmop_process(s, pm[k], prm.P[2], en[k], prm.P[3]);
+                __stcs(a.out0 + (size_t)f * n + v, fmop_process(s, pm[k], prm.P[2], en[k], prm.P[3]));
             }
         }
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) { pm[k] = pm_n[k]; en[k] = en_n[k]; }
     }
+#undef OSC_FMOP_LOAD
     a.state[(size_t)(a.state_base + 0) * n + v] = s.phase; a.state[(size_t)(a.state_base + 1) * n + v] = s.prev;
 }
 
@@ -120,24 +130,29 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
 __global__ void __launch_bounds__(kCta) tpt_node_kernel(const __grid_constant__ NodeArgs a) {
     OSC_NODE_PROLOGUE(1)
     TptState s; tpt_load(s, a.state, a.state_base, n, v);
+    float x[kPF], c[kPF], x_n[kPF], c_n[kPF];
+#define OSC_TPT_LOAD(X, C, F0)                                                                \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                    \
+        const uint32_t f = (F0) + k;                                                          \
+        X[k] = (f < frames) ? __ldcs(a.in0 + (size_t)f * n + v) : 0.0f;                       \
+        C[k] = (f < frames) ? __ldcs(a.in1 + (size_t)f * n + v) : 0.0f;                       \
+    }
+    OSC_TPT_LOAD(x, c, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        float x[kPF], c[kPF];
-#pragma unroll
-        for (uint32_t k = 0; k < kPF; ++k) {
-            const uint32_t f = f0 + k;
-            x[k] = (f < frames) ? __ldg(a.in0 + (size_t)f * n + v) : 0.0f;
-            c[k] = (f < frames) ? __ldg(a.in1 + (size_t)f * n + v) : 0.0f;
-        }
+        OSC_TPT_LOAD(x_n, c_n, f0 + kPF)
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
             if (f < frames) {
                 prm.ramps(a, ramp_mask, f);
                 if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                a.out0[(size_t)f * n + v] = tpt_process(s, x[k], c[k], prm.P[0], 0.0f, a.sr);
+                __stcs(a.out0 + (size_t)f * n + v, tpt_process(s, x[k], c[k], prm.P[0], 0.0f, a.sr));
             }
         }
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) { x[k] = x_n[k]; c[k] = c_n[k]; }
     }
+#undef OSC_TPT_LOAD
     tpt_store(s, a.state, a.state_base, n, v);
 }
 
@@ -169,6 +184,41 @@ __global__ void __launch_bounds__(kCta) ew_node_kernel(const __grid_constant__ N
                     a.out1[(size_t)f * n + v] = x[k] * mix;
                 }
             }
+        }
+    }
+}
+
+/* Stateless nodes, vectorised: when the block carries no value events every element (frame, voice)
+   is independent, so the kernel is a float4 grid-stride stream over [frames x voices] — the
+   HBM-bound form (two 16-byte loads, one or two 16-byte stores per thread-iteration).  Requires
+   n_voices % 4 == 0.  The value input is per voice (pv row) unless it is ramping this block
+   (then one scalar per frame from ptab). */
+template <int OP>
+__global__ void __launch_bounds__(256) ew_node_vec_kernel(const __grid_constant__ NodeArgs a) {
+    const uint32_t n4 = a.n_voices >> 2;
+    const uint32_t frames = a.ctl->frames, ramp_mask = a.ctl->ramp_mask;
+    const size_t total = (size_t)frames * n4;
+    const bool has_p = a.pid[0] != kNoInput;
+    const bool ramped = has_p && ((ramp_mask >> a.pid[0]) & 1u);
+    const float4 *in0 = reinterpret_cast<const float4 *>(a.in0);
+    const float4 *in1 = reinterpret_cast<const float4 *>(a.in1);
+    const float4 *pv = has_p ? reinterpret_cast<const float4 *>(a.pv + (size_t)a.pid[0] * a.n_voices) : nullptr;
+    float4 *out0 = reinterpret_cast<float4 *>(a.out0);
+    float4 *out1 = reinterpret_cast<float4 *>(a.out1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t f = (uint32_t)(i / n4), v4 = (uint32_t)(i - (size_t)f * n4);
+        const float4 x = __ldcs(in0 + i);
+        float4 p;
+        if (!has_p) p = make_float4(a.cst[0], a.cst[0], a.cst[0], a.cst[0]);
+        else if (ramped) { const float r = a.ptab[(size_t)f * kMaxInputs + a.pid[0]]; p = make_float4(r, r, r, r); }
+        else p = __ldg(pv + v4);
+        if (OP == EW_GAIN) { __stcs(out0 + i, make_float4(x.x * p.x, x.y * p.y, x.z * p.z, x.w * p.w)); }
+        else if (OP == EW_ADD_VALUE) { __stcs(out0 + i, make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w)); }
+        else if (OP == EW_MIXER) { const float4 y = __ldcs(in1 + i); __stcs(out0 + i, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w)); }
+        else {
+            const float4 m = make_float4(clampf(p.x, 0.0f, 1.0f), clampf(p.y, 0.0f, 1.0f), clampf(p.z, 0.0f, 1.0f), clampf(p.w, 0.0f, 1.0f));
+            __stcs(out0 + i, make_float4(x.x * (1.0f - m.x), x.y * (1.0f - m.y), x.z * (1.0f - m.z), x.w * (1.0f - m.w)));
+            __stcs(out1 + i, make_float4(x.x * m.x, x.y * m.y, x.z * m.z, x.w * m.w));
         }
     }
 }

@@ -265,12 +265,13 @@ __constant__ float kEpVel127[32] = {
     0.000772873f, 0.000364486f, 0.000248027f, 0.00018236f, 3.27292e-05f, 6.64988e-05f,
     0.0f, 0.0f, 0.0f, 0.0f };
 
-/* AmplitudeSource::on_gate, electric_piano_voice.rs:241-320 (note_pitch stays 60.0) */
-OSC_D void ep_amp_on_gate(float *S, float scalar, const float *P) {
-#define EPS(field, i) S[((field) + (i)) * kCta]
+#define EPS(field, i) S[(size_t)((field) + (i)) * n_stride]
+/* AmplitudeSource::on_gate for the harmonics [h0, h0+8) of one voice (registers) */
+OSC_D void ep_gate_chunk(float *S, size_t n_stride, uint32_t h0, float scalar, const float *P, float (&cur)[8], float (&ore)[8],
+                         float (&oim)[8], bool &released, uint32_t &step) {
     if (scalar > 0.0f) {
         const float velocity = scalar;
-        const float note = 60.0f;
+        const float note = 60.0f;                                   /* note_pitch is never updated */
         const float base_decay_rate = (100.0f - P[3]) / 40000.0f;
         const float harmonic_scaling = 1.0f - ((100.0f - P[4]) / 200000.0f);
         const float scaling_multiplier = (48.0f - note) / 12.0f;
@@ -278,27 +279,39 @@ OSC_D void ep_amp_on_gate(float *S, float scalar, const float *P) {
         const float adjusted = (key_scaling_factor > 0.0f)
             ? 1.0f - (base_decay_rate / (1.0f + key_scaling_factor))
             : 1.0f - (base_decay_rate * (1.0f - key_scaling_factor));
-        float scaling = 1.0f;
+        float scaling = 1.0f;                                       /* scaling *= harmonic_scaling, i times */
+        for (uint32_t i = 0; i < h0; ++i) scaling *= harmonic_scaling;
         const float rv = 0.999f - ((100.0f - P[6]) / 1000.0f);
         float bs = -0.2f + (0.8f * (P[1] * 0.01f));
         bs += velocity * P[2] * 0.01f * 0.5f;
-        for (int i = 0; i < 32; ++i) {
-            EPS(EP_DEC, i) = adjusted * scaling; scaling *= harmonic_scaling;
-            EPS(EP_REL, i) = rv;
-            float amp = (kEpVel127[i] * velocity) + (kEpVel0[i] * (1.0f - velocity));
-            amp *= 1.0f + bs * (float)i;
-            EPS(EP_CUR, i) = amp;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            EPS(EP_DEC, h0 + i) = adjusted * scaling; scaling *= harmonic_scaling;
+            EPS(EP_REL, h0 + i) = rv;
+            float amp = (kEpVel127[h0 + i] * velocity) + (kEpVel0[h0 + i] * (1.0f - velocity));
+            amp *= 1.0f + bs * (float)(h0 + i);
+            cur[i] = amp;
+            ore[i] = 1.0f; oim[i] = 0.0f;                           /* OscillatorBank::on_gate */
         }
-        EPS(EP_RELEASED, 0) = 0.0f; EPS(EP_STEP, 0) = 0.0f;
+        released = false; step = 0u;
     } else {
-        EPS(EP_RELEASED, 0) = 1.0f; EPS(EP_STEP, 0) = 0.0f;
+        released = true; step = 0u;
     }
 }
 
-__global__ void __launch_bounds__(kCta) epiano_kernel(const __grid_constant__ KernelArgs a) {
-    extern __shared__ float dyn[];          /* S [EP_NSTATE][128] | tile [32][192] | isum [32*128*2] */
-    float *S = dyn + threadIdx.x;
-    float *tile = dyn + EP_NSTATE * kCta;
+/*
+ * One thread = one voice; the 259-word state sits in a [field][thread] shared-memory tile for the
+ * block.  The 32 harmonics are processed in 4 chunks of 8 held in REGISTERS across a 32-frame
+ * tile (chunk-major inside the tile): per frame and chunk, 8 lerps + 8 complex rotations run out
+ * of registers, and the running output sum is carried through a per-thread accumulator row so the
+ * f32 additions happen in exactly the reference order sum += osc[i].imag * amp[i], i = 0..31.
+ * The per-frame control flow (interpolation step, release flag, gate / value events, multiplier
+ * refresh) is replayed identically by every chunk pass.
+ */
+__global__ void __launch_bounds__(kCta, 6) epiano_kernel(const __grid_constant__ KernelArgs a) {
+    extern __shared__ float dyn[];          /* acc [kTileF][kCta] | tile [kTileF][kTileW] | isum [kTileF*kCta*2] */
+    float *acc = dyn + threadIdx.x;
+    float *tile = dyn + kTileF * kCta;
     float *isum = tile + kTileF * kTileW;
     const uint32_t n = a.n_voices;
     const uint32_t v = blockIdx.x * kCta + threadIdx.x;
@@ -310,75 +323,95 @@ __global__ void __launch_bounds__(kCta) epiano_kernel(const __grid_constant__ Ke
     const uint32_t col = tile_col(threadIdx.x, vpi);
 
     SmallParams<9> prm; prm.load(a, vs);
-    for (uint32_t i = 0; i < EP_NSTATE; ++i) S[i * kCta] = a.state[(size_t)i * n + vs];
+    /* the 259-word voice state stays in HBM/L2 as SoA rows; each chunk pass pulls its 48 words into
+       registers per 32-frame tile (coalesced: a warp reads 128 contiguous bytes per field) */
+    float *S = a.state + vs;
+    const size_t n_stride = n;
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
-    /* instance-level tremolo: thread i < ipc owns instance blockIdx*ipc + i */
     const uint32_t ipc = kCta / vpi;
     const uint32_t my_inst = blockIdx.x * ipc + threadIdx.x;
     float trem_phase = (threadIdx.x < ipc && my_inst < a.n_inst) ? a.inst_state[my_inst] : 0.0f;
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        for (uint32_t ff = 0; ff < fe; ++ff) {
-            const uint32_t f = f0 + ff;
-            float y = 0.0f;
-            if (active) {
-                prm.ramps(a, ramp_mask, f);
-                if (ec.due(f)) {
-                    const uint32_t j = ec.end_of_frame(f);
-                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
-                    /* gate -> amplitude_source.gate (handled before its process()) */
-                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate) ep_amp_on_gate(S, ec.ev[q].scalar, prm.P);
-                    /* AmplitudeSource::process happens between the two on_gate calls in the walk,
-                       but OscillatorBank::on_gate only resets the oscillators: order-independent */
-                    for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate && ec.ev[q].scalar > 0.0f)
-                        for (int i = 0; i < 32; ++i) { EPS(EP_ORE, i) = 1.0f; EPS(EP_OIM, i) = 0.0f; }
-                    ec.advance(j);
+        if (active) {
+            const uint32_t step0 = (uint32_t)EPS(EP_STEP, 0);
+            const bool rel0 = EPS(EP_RELEASED, 0) != 0.0f;
+            const float lastf0 = EPS(EP_LASTF, 0);
+            const SmallParams<9> prm0 = prm;
+            const EventCursor ec0 = ec;
+            uint32_t step = step0; bool released = rel0; float lastf = lastf0;
+            for (uint32_t h0 = 0; h0 < 32u; h0 += 8u) {
+                float cur[8], tgt[8], ore[8], oim[8], mre[8], mim[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    cur[i] = EPS(EP_CUR, h0 + i); tgt[i] = EPS(EP_TGT, h0 + i);
+                    ore[i] = EPS(EP_ORE, h0 + i); oim[i] = EPS(EP_OIM, h0 + i);
+                    mre[i] = EPS(EP_MRE, h0 + i); mim[i] = EPS(EP_MIM, h0 + i);
                 }
-                /* AmplitudeSource::process, electric_piano_voice.rs:322-351 */
-                uint32_t step = (uint32_t)EPS(EP_STEP, 0);
-                const bool released = EPS(EP_RELEASED, 0) != 0.0f;
-                if (step == 0u) {
-                    for (int i = 0; i < 32; ++i)
-                        EPS(EP_TGT, i) = EPS(EP_CUR, i) * (released ? EPS(EP_REL, i) : EPS(EP_DEC, i));
-                }
-                if (step < 64u) {
-                    const float t = (float)(step + 1u) / 64.0f;
-                    for (int i = 0; i < 32; ++i)
-                        EPS(EP_CUR, i) = EPS(EP_CUR, i) * (1.0f - t) + EPS(EP_TGT, i) * t;
-                    step += 1u;
-                } else {
-                    for (int i = 0; i < 32; ++i) EPS(EP_CUR, i) = EPS(EP_TGT, i);
-                    step = 0u;
-                }
-                EPS(EP_STEP, 0) = (float)step;
-                /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
-                const float freq = prm.P[0];
-                if (freq > 0.0f && !(fabsf(EPS(EP_LASTF, 0) - freq) < 0.01f)) {
-                    EPS(EP_LASTF, 0) = freq;
-                    const float nyquist = sr * 0.5f;
-                    for (int i = 0; i < 32; ++i) {
-                        const float hf = freq * (float)(i + 1);
-                        if (hf < nyquist) {
-                            const float angle = 2.0f * kPi * hf / sr;
-                            EPS(EP_MRE, i) = om_cosf(angle); EPS(EP_MIM, i) = om_sinf(angle);
-                        } else { EPS(EP_MRE, i) = 1.0f; EPS(EP_MIM, i) = 0.0f; }
+                step = step0; released = rel0; lastf = lastf0; prm = prm0; ec = ec0;
+                for (uint32_t ff = 0; ff < fe; ++ff) {
+                    const uint32_t f = f0 + ff;
+                    prm.ramps(a, ramp_mask, f);
+                    if (ec.due(f)) {
+                        const uint32_t j = ec.end_of_frame(f);
+                        for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
+                        for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
+                            ep_gate_chunk(S, n_stride, h0, ec.ev[q].scalar, prm.P, cur, ore, oim, released, step);
+                        ec.advance(j);
                     }
-                    for (int i = 0; i < 32; ++i) { EPS(EP_ORE, i) = 1.0f; EPS(EP_OIM, i) = 0.0f; }
+                    /* AmplitudeSource::process, electric_piano_voice.rs:322-351 */
+                    if (step == 0u) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) tgt[i] = cur[i] * (released ? EPS(EP_REL, h0 + i) : EPS(EP_DEC, h0 + i));
+                    }
+                    if (step < 64u) {
+                        const float t = (float)(step + 1u) / 64.0f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cur[i] = cur[i] * (1.0f - t) + tgt[i] * t;
+                        step += 1u;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cur[i] = tgt[i];
+                        step = 0u;
+                    }
+                    /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
+                    const float freq = prm.P[0];
+                    if (freq > 0.0f && !(fabsf(lastf - freq) < 0.01f)) {
+                        lastf = freq;
+                        const float nyquist = sr * 0.5f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float hf = freq * (float)(h0 + i + 1);
+                            if (hf < nyquist) {
+                                const float angle = 2.0f * kPi * hf / sr;
+                                mre[i] = om_cosf_u(angle); mim[i] = om_sinf_u(angle);
+                            } else { mre[i] = 1.0f; mim[i] = 0.0f; }
+                            ore[i] = 1.0f; oim[i] = 0.0f;
+                        }
+                    }
+                    float sum = (h0 == 0u) ? 0.0f : acc[ff * kCta];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float nr = ore[i] * mre[i] - oim[i] * mim[i];
+                        const float ni = ore[i] * mim[i] + oim[i] * mre[i];
+                        ore[i] = nr; oim[i] = ni;
+                        sum += ni * cur[i];
+                    }
+                    acc[ff * kCta] = sum;
                 }
-                float sum = 0.0f;
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) {
-                    const float re = EPS(EP_ORE, i), im = EPS(EP_OIM, i);
-                    const float mr = EPS(EP_MRE, i), mi = EPS(EP_MIM, i);
-                    const float nr = re * mr - im * mi;
-                    const float ni = re * mi + im * mr;
-                    EPS(EP_ORE, i) = nr; EPS(EP_OIM, i) = ni;
-                    sum += ni * EPS(EP_CUR, i);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    EPS(EP_CUR, h0 + i) = cur[i]; EPS(EP_TGT, h0 + i) = tgt[i];
+                    EPS(EP_ORE, h0 + i) = ore[i]; EPS(EP_OIM, h0 + i) = oim[i];
+                    EPS(EP_MRE, h0 + i) = mre[i]; EPS(EP_MIM, h0 + i) = mim[i];
                 }
-                y = sum * 3.0f;
-                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
             }
+            EPS(EP_STEP, 0) = (float)step; EPS(EP_RELEASED, 0) = released ? 1.0f : 0.0f; EPS(EP_LASTF, 0) = lastf;
+        }
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const float y = active ? acc[ff * kCta] * 3.0f : 0.0f;       /* output scaling */
+            if (active && a.voice_out != nullptr) a.voice_out[(size_t)(f0 + ff) * n + v] = y;
             tile[ff * kTileW + col] = y;
         }
         /* ---- flush: instance sum (index order) -> Tremolo (sequential in time) -> Frame<2> */
@@ -386,10 +419,12 @@ __global__ void __launch_bounds__(kCta) epiano_kernel(const __grid_constant__ Ke
         if (threadIdx.x < ipc) {
             const uint32_t i = threadIdx.x;
             const uint32_t c0 = tile_col(i * vpi, vpi);
-            /* instance-level inputs are read from the instance's first voice */
-            const float depth = a.pv[(size_t)7 * n + min((blockIdx.x * ipc + i) * vpi, n - 1)];
-            const float rate = a.pv[(size_t)8 * n + min((blockIdx.x * ipc + i) * vpi, n - 1)];
+            const uint32_t v_first = min((blockIdx.x * ipc + i) * vpi, n - 1u);   /* instance-level inputs: first voice */
+            const float depth0 = a.pv[(size_t)7 * n + v_first];
+            const float rate0 = a.pv[(size_t)8 * n + v_first];
             for (uint32_t ff = 0; ff < fe; ++ff) {
+                const float depth = ((ramp_mask >> 7) & 1u) ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + 7] : depth0;
+                const float rate = ((ramp_mask >> 8) & 1u) ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + 8] : rate0;
                 const float *row = tile + ff * kTileW;
                 float s = 0.0f;
                 for (uint32_t j = 0; j < vpi; ++j) s = s + row[c0 + j];
@@ -411,7 +446,6 @@ __global__ void __launch_bounds__(kCta) epiano_kernel(const __grid_constant__ Ke
         }
         __syncthreads();
     }
-    if (active) for (uint32_t i = 0; i < EP_NSTATE; ++i) a.state[(size_t)i * n + v] = S[i * kCta];
     if (threadIdx.x < ipc && my_inst < a.n_inst) a.inst_state[my_inst] = trem_phase;
 #undef EPS
 }

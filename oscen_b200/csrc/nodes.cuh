@@ -307,7 +307,7 @@ OSC_D float lp18_process(Lp18State &s, float input, float cutoff, float fmod, fl
     }
     const float hp = (input - s.h * s.z0 - s.z1 - s.z2) / (1.0f + s.g);
     const float bp1 = s.g * hp + s.z0;
-    s.z0 = om_tanhf(bp1);
+    s.z0 = om_tanhf_u(bp1);
     const float bp2 = s.g * bp1 + s.z1;
     s.z1 = bp2;
     const float lp = s.g * bp2 + s.z2;

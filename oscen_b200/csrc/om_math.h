@@ -504,4 +504,66 @@ OM_HD float om_tanhf(float x) {
     return (jx >> 31) ? -z : z;
 }
 
+/* ---- tanhf, lane-select form for the kernels (same bits as om_tanhf / glibc) ---------------
+ * expm1f's argument reduction is one formula for every k (k = 0 and k = +-1 are the general
+ * `hi = x - k*ln2_hi, lo = k*ln2_lo` with exact products), so only k itself and the final
+ * reconstruction are selected per lane; a warp whose lanes fall in different |x| bands no longer
+ * serialises three code paths.  Domain handled here: 2^-55 <= |x| < 22 with the expm1f argument
+ * in (-2, 0] (|x| < 1) or [2, 44) (|x| >= 1); everything else defers to om_tanhf. */
+OM_HD float om_tanhf_u(float x) {
+    const uint32_t jx = om_asuint(x), ix = jx & 0x7fffffffu;
+    if (ix >= 0x41b00000u || ix < 0x24000000u) return om_tanhf(x);     /* |x| >= 22, tiny, 0, inf, nan */
+    const float one = 1.0f, ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f,
+                invln2 = 1.4426950216e+00f, Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f,
+                Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
+    const bool big = ix >= 0x3f800000u;                                /* |x| >= 1 */
+    const float ax = fabsf(x);
+    float a = big ? 2.0f * ax : -2.0f * ax;                            /* expm1f argument */
+    const uint32_t ha = om_asuint(a) & 0x7fffffffu;
+    if (ha >= 0x4195b844u) return om_tanhf(x);                         /* |a| >= 27 ln2: cold */
+    /* k */
+    int32_t k;
+    if (ha > 0x3eb17218u) {
+        const int32_t kg = (int32_t)(invln2 * a + (big ? 0.5f : -0.5f));
+        k = (ha < 0x3F851592u) ? (big ? 1 : -1) : kg;
+    } else k = 0;
+    const bool tiny = ha < 0x33000000u;                                /* |a| < 2^-25: expm1f(a) = a */
+    const float t0 = (float)k;
+    const float hi = a - t0 * ln2_hi;
+    const float lo = t0 * ln2_lo;
+    const float xr = hi - lo;
+    const float c = (hi - xr) - lo;
+    const float hfx = 0.5f * xr;
+    const float hxs = xr * hfx;
+    const float r1 = one + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
+    const float tt = 3.0f - r1 * hfx;
+    float e = hxs * ((r1 - tt) / (6.0f - xr * tt));
+    float em1;
+    if (k == 0) {
+        em1 = xr - (xr * e - hxs);
+    } else {
+        e = (xr * (e - c) - c);
+        e -= hxs;
+        if (k == -1) em1 = 0.5f * (xr - e) - 0.5f;
+        else if (k == 1) em1 = (xr < -0.25f) ? -2.0f * (e - (xr + 0.5f)) : one + 2.0f * (xr - e);
+        else if (k <= -2 || k > 56) {
+            float y = one - (e - xr);
+            y = om_asfloat(om_asuint(y) + ((uint32_t)k << 23));
+            em1 = y - one;
+        } else if (k < 23) {
+            const float t1 = om_asfloat(0x3f800000u - (0x1000000u >> k));
+            float y = t1 - (e - xr);
+            em1 = om_asfloat(om_asuint(y) + ((uint32_t)k << 23));
+        } else {
+            const float t1 = om_asfloat((uint32_t)(0x7f - k) << 23);
+            float y = xr - (e + t1);
+            y += one;
+            em1 = om_asfloat(om_asuint(y) + ((uint32_t)k << 23));
+        }
+    }
+    if (tiny) em1 = a;
+    const float z = big ? one - 2.0f / (em1 + 2.0f) : -em1 / (em1 + 2.0f);
+    return (jx >> 31) ? -z : z;
+}
+
 #endif /* OSCEN_B200_OM_MATH_H */

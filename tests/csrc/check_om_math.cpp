@@ -62,6 +62,7 @@ int main(int argc, char **argv) {
     report("cosf[120<=|x|<inf]", sweep([](float x) { return om_cosf(x); }, [](float x) { return cosf(x); }, F120, FINF - 1, stride, nt));
     const uint32_t F2 = 0x40000000u, F12 = 0x41400000u;
     report("tanf[|x|<=2]", sweep([](float x) { return om_tanf(x); }, [](float x) { return tanf(x); }, 0, F2, stride, nt));
+    report("tanhf_u[|x|<=32]", sweep([](float x) { return om_tanhf_u(x); }, [](float x) { return tanhf(x); }, 0, 0x42000000u, stride, nt));
     report("tanhf[|x|<=12]", sweep([](float x) { return om_tanhf(x); }, [](float x) { return tanhf(x); }, 0, F12, stride, nt));
     // ADSR domain: 1 - exp(-K/n) for integer n (adsr.rs:132-133)
     {

@@ -28,7 +28,8 @@ def results(tmp_path_factory):
 
 
 @pytest.mark.parametrize("name", ["expf[|x|<=104]", "sinf[|x|<120]", "cosf[|x|<120]",
-                                  "sinf[120<=|x|<inf]", "cosf[120<=|x|<inf]", "tanhf[|x|<=12]",
+                                  "sinf[120<=|x|<inf]", "cosf[120<=|x|<inf]", "tanhf[|x|<=12]", "tanhf_u[|x|<=32]",
+                                  "sinf_u[all]", "cosf_u[all]",
                                   "expf[adsr"])
 def test_bit_exact_against_glibc(results, name):
     n, bad, _ = results[name]

@@ -1011,6 +1011,13 @@ int orc_bank_push_events(orc_bank *b, const orc_event *ev, size_t n) {
     for (size_t i = 0; i < n; ++i) {
         uint32_t v = ev[i].voice;
         if (v >= b->n_voices) return -1;
+        if (ev[i].input_id == ORC_EV_GATE) {
+            /* the voice's `gate` input is a 32-slot StaticEventQueue: try_push on a full queue drops
+               (graph/types.rs:18,183-188) */
+            uint32_t g = 0;
+            for (uint32_t k = 0; k < b->npend[v]; ++k) if (b->pend[v][k].input_id == ORC_EV_GATE) ++g;
+            if (g >= MAXQ) continue;
+        }
         if (b->npend[v] == b->cpend[v]) {
             b->cpend[v] = b->cpend[v] ? b->cpend[v] * 2 : 4;
             b->pend[v] = realloc(b->pend[v], b->cpend[v] * sizeof(vev));

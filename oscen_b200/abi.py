@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "lib", "liboscen_b200.so")
+LIB = os.environ.get("OSCEN_B200_LIB") or os.path.join(HERE, "lib", "liboscen_b200.so")   # env override: A/B of two builds
 
 ABI_VERSION = 1
 MAX_BLOCK = 512

@@ -559,12 +559,12 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             e->seqs.push_back(e->seq++);
         }
     }
-    /* ---- stage events: drop those beyond the block; cap 32 gate events per voice; sort */
-    std::vector<uint32_t> order;
-    order.reserve(e->pending.size());
-    for (uint32_t i = 0; i < e->pending.size(); ++i) {
-        if (e->pending[i].frame < frames) order.push_back(i); else e->stats.events_dropped++;
-    }
+    /* ---- stage events.  Reference semantics: every pushed gate event takes a slot of the voice's
+       32-slot queue in PUSH order (try_push on a full ArrayVec drops, graph/types.rs:183-188), then
+       process_block stages the queue sorted by frame_offset and never reaches offsets >= frames
+       (codegen/mod.rs:836-872).  Value events are field assignments: no cap. */
+    std::vector<uint32_t> order(e->pending.size());
+    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
         const Event &a = e->pending[x], &b = e->pending[y];
         if (a.voice != b.voice) return a.voice < b.voice;
@@ -584,18 +584,33 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         }
         /* the pinned staging buffer may still be in flight from the previous block */
         if (!order.empty()) CK(e, cudaStreamSynchronize(e->stream));
-        uint32_t cur_voice = 0xFFFFFFFFu, gates = 0;
-        for (uint32_t idx : order) {
-            const Event &x = e->pending[idx];
-            if (x.voice != cur_voice) { cur_voice = x.voice; gates = 0; }
-            if (x.input_id == kEventGate) {
-                if (gates >= OSCEN_B200_MAX_EVENTS_PER_ENDPOINT) { e->stats.events_dropped++; continue; }
-                ++gates;
-            } else if (x.input_id != 0u || kind != OSCEN_B200_GRAPH_FM_VOICE) {
-                general = true;
+        std::vector<uint32_t> gate_seqs;
+        size_t g0 = 0;
+        while (g0 < order.size()) {
+            size_t g1 = g0;
+            const uint32_t voice = e->pending[order[g0]].voice;
+            gate_seqs.clear();
+            while (g1 < order.size() && e->pending[order[g1]].voice == voice) {
+                if (e->pending[order[g1]].input_id == kEventGate) gate_seqs.push_back(e->seqs[order[g1]]);
+                ++g1;
             }
-            if (x.input_id != kEventGate) { e->uniform[x.input_id] = false; has_value_events = true; }
-            e->h_events[n_ev++] = x;
+            uint32_t seq_limit = 0xFFFFFFFFu;                  /* gates pushed at or after this seq found the queue full */
+            if (gate_seqs.size() > OSCEN_B200_MAX_EVENTS_PER_ENDPOINT) {
+                std::nth_element(gate_seqs.begin(), gate_seqs.begin() + OSCEN_B200_MAX_EVENTS_PER_ENDPOINT, gate_seqs.end());
+                seq_limit = gate_seqs[OSCEN_B200_MAX_EVENTS_PER_ENDPOINT];
+            }
+            for (size_t k = g0; k < g1; ++k) {
+                const uint32_t idx = order[k];
+                const Event &x = e->pending[idx];
+                if (x.input_id == kEventGate && e->seqs[idx] >= seq_limit) { e->stats.events_dropped++; continue; }
+                if (x.frame >= frames) { e->stats.events_dropped++; continue; }
+                if (x.input_id != kEventGate) {
+                    e->uniform[x.input_id] = false; has_value_events = true;
+                    if (x.input_id != 0u || kind != OSCEN_B200_GRAPH_FM_VOICE) general = true;
+                }
+                e->h_events[n_ev++] = x;
+            }
+            g0 = g1;
         }
     }
     e->pending.clear(); e->seqs.clear();

@@ -97,6 +97,17 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
         adsr_pin(d3); adsr_pin(d2); adsr_pin(d1); adsr_pin(df);
     }
 
+    /* FAST variant: sustain and the stage lengths cannot change inside the block, so the
+       sustain-level / countdown-clamp part of update_sustain_level() runs at block start and after
+       gate events only (see adsr_refresh) */
+    AdsrHot h3, h2, h1, hf;
+#define OSC_FM_REFRESH()                                                    \
+    do {                                                                    \
+        adsr_refresh(e3, h3, P[I_OP3_S], d3); adsr_refresh(e2, h2, P[I_OP2_S], d2); \
+        adsr_refresh(e1, h1, P[I_OP1_S], d1); adsr_refresh(ef, hf, P[I_F_S], df);   \
+    } while (0)
+    OSC_FM_REFRESH();
+
     EventCursor ec;
     ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
 
@@ -144,6 +155,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                         }
                     }
                     OSC_FM_INCS();
+                    if (!GENERAL) OSC_FM_REFRESH();
                     ec.advance(j);
                 } else if (GENERAL && ramp_mask) {
                     if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
@@ -153,10 +165,10 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                 }
 
                 /* ---- the walk (one frame) */
-                const float env3 = adsr_process(e3, P[I_OP3_S], d3);
-                const float env2 = adsr_process(e2, P[I_OP2_S], d2);
-                const float env1 = adsr_process(e1, P[I_OP1_S], d1);
-                const float envf = adsr_process(ef, P[I_F_S], df);
+                const float env3 = adsr_process_t<GENERAL>(e3, h3, P[I_OP3_S], d3);
+                const float env2 = adsr_process_t<GENERAL>(e2, h2, P[I_OP2_S], d2);
+                const float env1 = adsr_process_t<GENERAL>(e1, h1, P[I_OP1_S], d1);
+                const float envf = adsr_process_t<GENERAL>(ef, hf, P[I_F_S], df);
                 const float feg = envf * P[I_ENV_AMT];                 /* filter_env_gain: Gain */
                 const float cutoff = feg + P[I_CUTOFF];                /* cutoff_mod: AddValue  */
                 const float o3 = fmop_process(op3, 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL]);

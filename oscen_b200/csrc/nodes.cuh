@@ -111,19 +111,35 @@ OSC_D void adsr_on_gate(AdsrState &s, float velocity, float attack_raw, float re
     }
 }
 /* process(), adsr.rs:84-115 (apply_parameters + update_sustain_level), :209-250 (process_stage),
-   :175-207 (complete_stage).  Returns `output`. */
-OSC_D float adsr_process(AdsrState &s, float sustain_in, const AdsrDerived &d) {
+   :175-207 (complete_stage).  Returns `output`.
+
+   Two parts of update_sustain_level() are pure functions of values that only change at known
+   points, so they are split out as adsr_refresh() and the per-frame body can skip them
+   (REFRESH=false) when the caller guarantees it calls adsr_refresh() at block start and after
+   every gate event / change of sustain or of the derived step counts:
+     * sustain_level = clamp(clamp(sustain) * velocity)          (inputs: sustain, velocity)
+     * samples_remaining = max(min(samples_remaining, stage_len), 1)  — idempotent while the stage
+       lengths are unchanged: the countdown only decreases or is reset to exactly a stage length. */
+struct AdsrHot { float sus; };
+OSC_D void adsr_refresh(AdsrState &s, AdsrHot &h, float sustain_in, const AdsrDerived &d) {
     const float sustain = clampf(sustain_in, 0.0f, 1.0f);
-    const float sus = clampf(sustain * s.vel, 0.0f, 1.0f);
+    h.sus = clampf(sustain * s.vel, 0.0f, 1.0f);
+    if (s.rem > 0u) {
+        if (s.stage == ST_ATTACK) s.rem = umax(umin(s.rem, d.a_n), 1u);
+        else if (s.stage == ST_DECAY) s.rem = umax(umin(s.rem, d.d_n), 1u);
+        else if (s.stage == ST_RELEASE) s.rem = umax(umin(s.rem, d.r_n), 1u);
+    }
+}
+template <bool REFRESH>
+OSC_D float adsr_process_t(AdsrState &s, AdsrHot &h, float sustain_in, const AdsrDerived &d) {
+    if (REFRESH) adsr_refresh(s, h, sustain_in, d);
+    const float sus = h.sus;
     const uint32_t st = s.stage;
     const bool isA = st == ST_ATTACK, isD = st == ST_DECAY, isR = st == ST_RELEASE;
     uint32_t rem = s.rem;
     float level = s.level;
     if (isA | isD | isR) {
-        /* adsr.rs:95-106: clamp the countdown to the (possibly changed) stage length */
-        const uint32_t lim = isA ? d.a_n : (isD ? d.d_n : d.r_n);
         if (rem > 0u) {
-            rem = umax(umin(rem, lim), 1u);
             float delta;
             if (isR) {
                 /* update_release_increment(), adsr.rs:159-173 -- recomputed every sample */
@@ -149,6 +165,10 @@ OSC_D float adsr_process(AdsrState &s, float sustain_in, const AdsrDerived &d) {
     s.rem = rem;
     s.level = level;
     return level;
+}
+OSC_D float adsr_process(AdsrState &s, float sustain_in, const AdsrDerived &d) {
+    AdsrHot h;
+    return adsr_process_t<true>(s, h, sustain_in, d);
 }
 
 /* =================================================================== FmOperator == */

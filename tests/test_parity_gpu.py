@@ -319,3 +319,78 @@ def test_config2_full_size_65536_voices_properties():
     g2.set_value(0, freq); g2.push_events(ev); g2.process_block(frames)
     assert np.array_equal(g2.read_mix()[:, 0], m0)
     assert np.array_equal(g2.read_voice_out(first_voice=n - 128, count=128), v0[:, n - 128:])
+
+
+# --------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("n,vpi", [(8, 8), (72, 8), (130, 1), (96, 2), (48, 16), (4, 4)])
+@pytest.mark.parametrize("frames", [1, 7, 512])
+def test_ragged_sizes_and_block_lengths(n, vpi, frames):
+    """voice counts that do not fill a CTA, every supported instance size, 1-frame and max blocks"""
+    ref, gpu = both(O.K_FM, n, vpi)
+
+    def script(b):
+        b.set_value(0, (100.0 + 37.0 * np.arange(n)).astype(np.float32))
+        out = []
+        b.push_events([(v, min(frames - 1, v % 5), GATE, 0.6) for v in range(n)])
+        for _ in range(3):
+            b.process_block(frames)
+            out.append((b.read_voice_out(), b.read_instance_out(), b.read_mix()))
+        return out
+
+    ro, go = drive((ref, gpu), script)
+    for (vr, ir, mr), (vg, ig, mg) in zip(ro, go):
+        assert np.array_equal(vg, vr) and np.array_equal(ig, ir)
+        assert np.allclose(mg, mr, rtol=1e-5, atol=1e-5)
+
+
+def test_gate_queue_overflow_drops_like_try_push():
+    """ArrayVec<_, 32>::try_push: the 33rd gate event of a voice in one block is dropped"""
+    ref, gpu = both(O.K_FM, 8, 8)
+
+    def script(b):
+        ev = [(0, k, GATE, 0.9 if k % 2 == 0 else 0.0) for k in range(40)]      # 40 alternating gates on voice 0
+        b.push_events(ev)
+        b.process_block(64)
+        return b.read_voice_out()
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.array_equal(yg, yr)
+    assert gpu.stats()["events_dropped"] >= 8
+
+
+def test_value_input_api_errors_and_state():
+    from oscen_b200 import abi
+    e = engine(O.K_FM, 16, 8)
+    with pytest.raises(abi.EngineError):
+        e.set_value(99, 1.0)                                  # bad input id
+    with pytest.raises(abi.EngineError):
+        e.push_events([(16, 0, GATE, 1.0)])                    # voice out of range
+    with pytest.raises(abi.EngineError):
+        e.process_block(513)                                   # > MAX_BLOCK
+    e.set_value(1, np.linspace(1.0, 2.0, 16).astype(np.float32))   # op3_ratio now per voice
+    with pytest.raises(abi.EngineError):
+        e.set_value_ramp(1, 3.0, 100)                          # a ramp is one ValueRampState: needs a uniform input
+    e.set_value(1, 2.0)                                        # uniform again
+    e.set_value_ramp(1, 3.0, 100)
+    e.process_block(32)
+    st = e.state_download()
+    assert st.shape == (29, 16) and np.isfinite(st).all()
+    s = e.stats()
+    assert s["blocks"] == 1 and s["kernel_launches"] > 0
+
+
+def test_same_frame_note_on_and_off_and_retrigger():
+    ref, gpu = both(O.K_FM, 8, 8)
+
+    def script(b):
+        out = []
+        b.push_midi(0, 10, [0x90, 60, 100]); b.push_midi(0, 10, [0x80, 60, 0])     # on and off in one frame
+        b.push_midi(0, 20, [0x90, 64, 90]); b.push_midi(0, 21, [0x90, 64, 30])     # same note twice
+        b.process_block(128); out.append(b.read_voice_out())
+        b.push_midi(0, 0, [0x80, 64, 0])
+        b.process_block(128); out.append(b.read_voice_out())
+        return np.concatenate(out)
+
+    yr, yg = drive((ref, gpu), script)
+    assert np.abs(yr).max() > 1e-3
+    assert np.array_equal(yg, yr)

@@ -165,7 +165,7 @@ def run_oracle(n_voices, budget_s, threads, wl_total):
     return blocks * n_voices * FRAMES / dt, blocks, dt
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, out):
     if rank != 0:
         return
     import oracle_lib as O
@@ -192,10 +192,38 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C restatement of the reference CPU path (oracle/); the Rust crate needs nightly cargo + un-vendored crates, absent here",
     }
-    print(json.dumps(line), flush=True)
+    out.emit(line)
+
+
+class QuietStdout:
+    """fd 1 -> stderr while the run is in progress (NCCL and friends print banners to stdout);
+    the one JSON line goes to the real stdout"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
+    with QuietStdout() as out:
+        run(out)
+
+
+def run(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -203,6 +231,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voices", type=int, default=VOICES_DEFAULT, help="voices PER GPU (weak scaling)")
     ap.add_argument("--plan", default="fused", choices=["fused", "nodes"])
+    ap.add_argument("--mix", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 mix-bus exchange: fused reduce+exchange kernel over NVLink peer memory, or ncclAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
@@ -211,9 +241,10 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, rank, world, out)
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -234,6 +265,22 @@ def main():
             idt = torch.frombuffer(bytearray(abi.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
         eng.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+        mix_mode = "nccl"
+        if args.mix == "p2p" and args.plan == "fused":
+            try:
+                mine = torch.frombuffer(bytearray(eng.comm_p2p_export(world)), dtype=torch.uint8).cuda()
+                allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+                dist.all_gather(allh, mine)
+                eng.comm_p2p_import(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+                mix_mode = "p2p"
+            except abi.EngineError as ex:          # IPC not available: NCCL stays in place
+                print(f"[rank {rank}] p2p mix exchange unavailable ({ex}); using NCCL", file=sys.stderr)
+            ok = torch.tensor([1 if mix_mode == "p2p" else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and mix_mode == "p2p":
+                raise SystemExit("p2p import succeeded on some ranks only")
+    if world == 1:
+        mix_mode = "local"
     wl = Workload(n * world, rank * n, n)
     mix = np.empty((FRAMES, 1), dtype=np.float32)
 
@@ -331,7 +378,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "fm-synth FMVoice bank, 65536 voices (8192 FMGraph instances x 8) per GPU, 48 kHz, 256-frame blocks (BASELINE configs[1])",
                    "voices_per_gpu": n, "voices_total": n * world, "frames": FRAMES, "sample_rate": SR, "plan": args.plan,
-                   "parallelism": f"voice-sharded x{world}, NCCL all-reduce of the mix bus" if world > 1 else "single GPU",
+                   "parallelism": (f"voice-sharded x{world}, mix bus: " + ("fused reduce+exchange kernel over NVLink peer memory" if mix_mode == "p2p" else "ncclAllReduce")) if world > 1 else "single GPU",
                    "l2": "flushed between steps (256 MiB write on the engine stream, outside the per-step CUDA-event bracket; inside the e2e host-clock region)",
                    "timing": "sum of per-step CUDA-event times on the engine stream, max over ranks"},
         "realtime_voices": value / SR,
@@ -346,7 +393,7 @@ def main():
                                 "sample": f"first 2048 voices of the bank x {blocks} blocks of 256 frames ({dt:.1f} s), {cores} threads",
                                 "single_thread": v_one, "cpu": cpu_model()}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

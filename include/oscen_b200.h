@@ -191,6 +191,15 @@ int  oscen_b200_l2_flush(oscen_b200_engine *e);
    exchange is the mix-bus all-reduce.  id is an ncclUniqueId (128 bytes) from rank 0. */
 int  oscen_b200_comm_unique_id(void *id128);
 int  oscen_b200_comm_init(oscen_b200_engine *e, int rank, int n_ranks, const void *id128);
+/* NVLink peer-memory mix bus (preferred over NCCL for this <= 4 KB message): every rank exports
+   a CUDA-IPC handle of its exchange buffer (64 bytes), the host all-gathers the handles, every
+   rank imports all of them.  Afterwards process_block ends with ONE kernel that reduces the
+   rank's partials, stores the result into every peer's buffer over NVLink, raises a per-block
+   flag, waits for the peers' flags and folds the ranks' contributions in rank order
+   (deterministic).  n_ranks <= 16. */
+#define OSCEN_B200_IPC_HANDLE_BYTES 64
+int  oscen_b200_comm_p2p_export(oscen_b200_engine *e, int n_ranks, void *handle64);
+int  oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, const void *handles /* n_ranks x 64 */);
 
 #ifdef __cplusplus
 }

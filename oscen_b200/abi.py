@@ -25,7 +25,7 @@ SYMBOLS = [
     "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
-    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init",
+    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import",
 ]
 
 
@@ -93,6 +93,8 @@ def load():
     L.oscen_b200_l2_flush.argtypes = [vp]
     L.oscen_b200_comm_unique_id.argtypes = [vp]
     L.oscen_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.oscen_b200_comm_p2p_export.argtypes = [vp, C.c_int, vp]
+    L.oscen_b200_comm_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
     _lib = L
     return L
 
@@ -225,6 +227,17 @@ class Engine:
     def comm_init(self, rank, n_ranks, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._chk(self.L.oscen_b200_comm_init(self.h, rank, n_ranks, buf), "comm_init")
+
+
+    def comm_p2p_export(self, n_ranks) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._chk(self.L.oscen_b200_comm_p2p_export(self.h, n_ranks, buf), "comm_p2p_export")
+        return buf.raw
+
+    def comm_p2p_import(self, rank, n_ranks, handles: bytes):
+        assert len(handles) == 64 * n_ranks
+        buf = C.create_string_buffer(handles, len(handles))
+        self._chk(self.L.oscen_b200_comm_p2p_import(self.h, rank, n_ranks, buf), "comm_p2p_import")
 
 
 def comm_unique_id() -> bytes:

@@ -143,6 +143,12 @@ struct oscen_b200_engine {
     /* multi-GPU */
     void *comm = nullptr;
     int rank = 0, n_ranks = 1;
+    /* NVLink peer-memory mix bus */
+    float *d_xchg = nullptr;
+    PeerTable peers{};
+    bool p2p = false;
+    uint32_t xchg_seq = 0;
+    uint32_t *d_p2p_error = nullptr;
 
     /* stats / timing */
     oscen_b200_stats stats{};
@@ -347,6 +353,8 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    if (e->p2p) for (int r = 0; r < e->n_ranks; ++r) if (r != e->rank && e->peers.peer[r]) cudaIpcCloseMemHandle(e->peers.peer[r]);
+    cudaFree(e->d_xchg); cudaFree(e->d_p2p_error);
     for (auto &g : e->graph_exec) if (g) cudaGraphExecDestroy(g);
     for (float *p : e->d_streams) cudaFree(p);
     cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
@@ -651,7 +659,16 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     if (e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
         rc = launch_fused(e, general); if (rc) return rc;
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
-        rc = launch_mix_reduce(e, frames); if (rc) return rc;
+        if (e->p2p) {
+            /* compute (partial reduction) + exchange over NVLink peer memory in one kernel */
+            e->xchg_seq += 1;
+            mix_exchange_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta_mix, e->channels, e->d_ctl,
+                                                            e->peers, (uint32_t)e->rank, (uint32_t)e->n_ranks, e->xchg_seq, e->d_p2p_error + 1, e->d_p2p_error);
+            e->stats.kernel_launches++;
+            CK(e, cudaGetLastError());
+        } else {
+            rc = launch_mix_reduce(e, frames); if (rc) return rc;
+        }
     } else {
         /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
         const int gi = has_value_events ? 1 : 0;
@@ -674,7 +691,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         e->stats.graph_launches++;
         e->stats.kernel_launches += e->graph_kernels[gi];
     }
-    if (e->comm) {
+    if (e->comm && !(e->p2p && e->cfg.plan == OSCEN_B200_PLAN_FUSED)) {
         const int r = g_nccl.AllReduce(e->d_mix, e->d_mix, (size_t)frames * e->channels, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, e->stream);
         if (r != 0) { e->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return OSCEN_B200_E_NCCL; }
     }
@@ -791,6 +808,38 @@ int oscen_b200_l2_flush(oscen_b200_engine *e) {
     if (!e->d_flush) CK(e, cudaMalloc(&e->d_flush, words * sizeof(uint32_t)));
     fill_u32_kernel<<<1184, 256, 0, e->stream>>>(e->d_flush, words, (uint32_t)e->stats.blocks);
     CK(e, cudaGetLastError());
+    return 0;
+}
+
+int oscen_b200_comm_p2p_export(oscen_b200_engine *e, int n_ranks, void *handle64) {
+    if (!e || !handle64 || n_ranks < 1 || n_ranks > (int)kMaxRanks) return OSCEN_B200_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == OSCEN_B200_IPC_HANDLE_BYTES, "ipc handle size");
+    CK(e, cudaSetDevice(e->cfg.device));
+    if (!e->d_xchg) {
+        CK(e, cudaMalloc(&e->d_xchg, kXchgBytes));
+        CK(e, cudaMemset(e->d_xchg, 0, kXchgBytes));
+        CK(e, cudaMalloc(&e->d_p2p_error, 2 * sizeof(uint32_t)));      /* [0] error flag, [1] CTA arrival counter */
+        CK(e, cudaMemset(e->d_p2p_error, 0, 2 * sizeof(uint32_t)));
+    }
+    cudaIpcMemHandle_t h;
+    CK(e, cudaIpcGetMemHandle(&h, e->d_xchg));
+    memcpy(handle64, &h, sizeof h);
+    return 0;
+}
+
+int oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, const void *handles) {
+    if (!e || !handles || n_ranks < 1 || n_ranks > (int)kMaxRanks || rank < 0 || rank >= n_ranks) return OSCEN_B200_E_ARG;
+    if (!e->d_xchg) { e->err = "comm_p2p_import: call comm_p2p_export first"; return OSCEN_B200_E_STATE; }
+    CK(e, cudaSetDevice(e->cfg.device));
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) { e->peers.peer[r] = e->d_xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * sizeof h, sizeof h);
+        void *p = nullptr;
+        CK(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->peers.peer[r] = (float *)p;
+    }
+    e->rank = rank; e->n_ranks = n_ranks; e->p2p = true; e->xchg_seq = 0;
     return 0;
 }
 

@@ -104,6 +104,77 @@ __global__ void mix_reduce_kernel(const float *__restrict__ partial, float *__re
     if (threadIdx.x == 0) mix[fc] = red[0];
 }
 
+/*
+ * Mix bus over NVLink peer memory: compute step (fixed-shape reduction of this rank's CTA
+ * partials, one output element per CTA) fused with the exchange: each CTA stores its element into
+ * every rank's buffer; the last CTA to finish raises the block's flag on every rank, waits for the
+ * peers' flags and folds the ranks' contributions in rank order.
+ *   xchg layout per rank: data[2 parity][kMaxRanks][1024] floats, then flags[2][kMaxRanks] u32.
+ *   peers[r] = rank r's xchg buffer mapped into this process (peers[rank] = local).
+ * A rank can only be two blocks ahead of a peer after that peer finished reading the older
+ * block (it needs the peer's flag of the block in between), so two parities suffice.
+ */
+constexpr uint32_t kMaxRanks = 16;
+constexpr uint32_t kXchgFloats = 2u * kMaxRanks * 1024u;
+constexpr size_t kXchgBytes = (size_t)kXchgFloats * sizeof(float) + 2u * kMaxRanks * sizeof(uint32_t);
+struct PeerTable { float *peer[kMaxRanks]; };
+
+__global__ void __launch_bounds__(256) mix_exchange_kernel(const float *__restrict__ partial, float *__restrict__ mix,
+                                                             uint32_t n_cta, uint32_t channels, const BlockCtl *ctl,
+                                                             const __grid_constant__ PeerTable peers, uint32_t rank,
+                                                             uint32_t n_ranks, uint32_t seq, uint32_t *counter,
+                                                             uint32_t *error_flag) {
+    __shared__ float red[256];
+    __shared__ uint32_t is_last;
+    const uint32_t count = ctl->frames * channels;
+    const uint32_t parity = seq & 1u;
+    const uint32_t fc = blockIdx.x;                        /* one output element per CTA, as mix_reduce_kernel */
+    /* 1. compute: fixed-shape reduction of this rank's CTA partials for element fc */
+    if (fc < count) {
+        float s = 0.0f;
+        for (uint32_t c = threadIdx.x; c < n_cta; c += 256) s = s + partial[(size_t)c * kMaxBlock * channels + fc];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (uint32_t w = 128; w > 0; w >>= 1) {
+            if (threadIdx.x < w) red[threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + w];
+            __syncthreads();
+        }
+        /* 2. exchange: the element goes straight into every rank's buffer (NVLink peer stores) */
+        if (threadIdx.x < n_ranks)
+            peers.peer[threadIdx.x][((size_t)parity * kMaxRanks + rank) * 1024u + fc] = red[0];
+    }
+    /* 3. the last CTA to finish publishes this block's flag and completes the collective */
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                            /* this CTA's peer stores before the count */
+        const uint32_t prev = atomicAdd(counter, 1u);
+        is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+        if (is_last) { *counter = 0u; __threadfence_system(); }
+    }
+    __syncthreads();
+    if (!is_last) return;
+    if (threadIdx.x < n_ranks) {
+        uint32_t *pf = reinterpret_cast<uint32_t *>(peers.peer[threadIdx.x] + kXchgFloats) + parity * kMaxRanks + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf), "r"(seq) : "memory");
+        const uint32_t *mf = reinterpret_cast<const uint32_t *>(peers.peer[rank] + kXchgFloats) + parity * kMaxRanks + threadIdx.x;
+        uint32_t got = 0, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mf) : "memory");
+            if (got == seq) break;
+            __nanosleep(32);
+        } while (++spins < (1u << 24));                     /* bounded: a dead peer must not hang the GPU */
+        if (got != seq) *error_flag = 1u;
+    }
+    __syncthreads();
+    /* 4. fold the ranks' contributions in rank order (identical bits on every rank) */
+    const float *mine = peers.peer[rank] + (size_t)parity * kMaxRanks * 1024u;
+    for (uint32_t k = threadIdx.x; k < count; k += 256) {
+        float s = 0.0f;
+        for (uint32_t r = 0; r < n_ranks; ++r) s = s + __ldcv(mine + (size_t)r * 1024u + k);
+        mix[k] = s;
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t *dst, size_t n, uint32_t value) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = value;

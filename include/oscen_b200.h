@@ -173,6 +173,12 @@ size_t   oscen_b200_state_bytes_per_voice(const oscen_b200_engine *e);
 /* raw SoA state download: dst[field * n_voices + voice], tests only */
 int  oscen_b200_state_download(oscen_b200_engine *e, void *dst, size_t cap);
 
+/* node plan of a graph kind as text, one launch per line ("k: NodeType [node, node]"): the
+   topological order the plan compiler derives (Kahn over the stream edges, like
+   oscen-graph-compiler/src/ir/lower.rs:1015-1085).  Returns the number of launches (>0), or a
+   negative code for graphs that only have a fused kernel.  Needs no GPU. */
+int  oscen_b200_plan_describe(uint32_t graph_kind, char *dst, size_t cap);
+
 /* counters: kernels launched by this engine since create; bytes copied H2D / D2H */
 typedef struct {
     uint64_t kernel_launches, graph_launches, h2d_bytes, d2h_bytes, blocks, events_dropped;

@@ -25,7 +25,7 @@ SYMBOLS = [
     "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
-    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import",
+    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_plan_describe",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
     L.oscen_b200_comm_unique_id.argtypes = [vp]
     L.oscen_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.oscen_b200_comm_p2p_export.argtypes = [vp, C.c_int, vp]
+    L.oscen_b200_plan_describe.argtypes = [u32, C.c_char_p, C.c_size_t]
     L.oscen_b200_comm_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
     _lib = L
     return L
@@ -238,6 +239,20 @@ class Engine:
         assert len(handles) == 64 * n_ranks
         buf = C.create_string_buffer(handles, len(handles))
         self._chk(self.L.oscen_b200_comm_p2p_import(self.h, rank, n_ranks, buf), "comm_p2p_import")
+
+
+def plan_describe(graph_kind):
+    """the node plan as a list of (node_type, [node names]) launches; raises for fused-only graphs"""
+    L = load()
+    buf = C.create_string_buffer(4096)
+    rc = L.oscen_b200_plan_describe(graph_kind, buf, 4096)
+    if rc <= 0:
+        raise EngineError(f"plan_describe rc={rc}")
+    out = []
+    for line in buf.value.decode().strip().splitlines():
+        head, names = line.split(" [")
+        out.append((head.split(": ", 1)[1], [x.strip() for x in names.rstrip("]").split(",")]))
+    return out
 
 
 def comm_unique_id() -> bytes:

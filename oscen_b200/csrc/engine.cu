@@ -22,6 +22,7 @@
 #include "kernel_fm.cuh"
 #include "kernel_nodes.cuh"
 #include "kernel_others.cuh"
+#include "graphs.hpp"
 #include "midi_front.hpp"
 
 using namespace oscen;
@@ -136,6 +137,11 @@ struct oscen_b200_engine {
     uint32_t last_frames = 0;
 
     /* node plan */
+    plan::Graph graph;
+    plan::Plan plan;
+    float *final_stream = nullptr;
+    const float *captured_in = nullptr;      /* graph-input pointer / LCG mode baked into the captured CUDA graphs */
+    bool captured_lcg = false;
     std::vector<float *> d_streams;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   /* [0] no value events, [1] with */
     uint64_t graph_kernels[2] = {0, 0};
@@ -264,61 +270,79 @@ int launch_fused(oscen_b200_engine *e, bool general) {
     return 0;
 }
 
-/* ---- node plan (FM_VOICE): the generated topological order as a launch sequence.
-   stream buffers: 0 env3 1 env2 2 env1 3 env_filter 4 filter_env_gain 5 cutoff_mod 6 op3 7 route_a
-   8 route_b 9 op2 10 mixer 11 op1 12 filter 13 output_gain */
-int launch_fm_nodes(oscen_b200_engine *e, bool value_events) {
-    const uint32_t grid = e->n_cta;
-    auto base = [&](uint32_t state_base) {
-        NodeArgs n{};
-        n.n_voices = e->cfg.n_voices; n.state_base = state_base; n.ctl = e->d_ctl; n.events = e->d_events;
-        n.ptab = e->d_ptab; n.pv = e->d_pv; n.state = e->d_state; n.sr = e->cfg.sample_rate;
-        for (int k = 0; k < 4; ++k) { n.pid[k] = kNoInput; n.cst[k] = 0.0f; }
-        return n;
-    };
+/* ---- node plan: the compiled launch sequence (plan.hpp) — one launch per node type per ready wave */
+template <int OP>
+void launch_ew(oscen_b200_engine *e, const NodeArgs &n, bool vec) {
+    if (vec) ew_node_vec_kernel<OP><<<148u * 8u, 256, 0, e->stream>>>(n);
+    else { NodeArgs4 a4{}; a4.n[0] = n; ew_node_kernel<OP><<<dim3(e->n_cta, 1), kCta, 0, e->stream>>>(a4); }
+    e->stats.kernel_launches++;
+}
+
+int launch_plan(oscen_b200_engine *e, bool value_events) {
+    const plan::Graph &g = e->graph;
+    const plan::Plan &p = e->plan;
     float **S = e->d_streams.data();
-    /* stateless nodes: float4 stream form unless this block carries value events (per-voice,
-       per-frame changes of a value input need the serial per-voice form) */
-    const bool vec = !value_events && (e->cfg.n_voices % 4u == 0u);
-    const uint32_t vgrid = 148u * 8u;
-    auto adsr_args = [&](uint32_t sb, uint32_t a0, uint32_t out) {
-        NodeArgs n = base(sb); n.pid[0] = a0; n.pid[1] = a0 + 1; n.pid[2] = a0 + 2; n.pid[3] = a0 + 3; n.out0 = S[out];
-        return n;
-    };
-    {   /* env3, env2, env1, env_filter: one launch for the node type */
-        NodeArgs4 a4;
-        a4.n[0] = adsr_args(FM_E3, I_OP3_A, 0); a4.n[1] = adsr_args(FM_E2, I_OP2_A, 1);
-        a4.n[2] = adsr_args(FM_E1, I_OP1_A, 2); a4.n[3] = adsr_args(FM_EF, I_F_A, 3);
-        adsr_node_kernel<<<dim3(grid, 4), kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++;
+    const uint32_t grid = e->n_cta, n = e->cfg.n_voices;
+    const bool vec = !value_events && (n % 4u == 0u);
+    /* the graph's stream input: host/device block, or generated by the LCG source node */
+    const float *gin = nullptr;
+    if (e->cfg.graph_kind == OSCEN_B200_GRAPH_TWIN_PEAKS) {
+        if (e->lcg_on) {
+            lcg_source_kernel<<<grid, kCta, 0, e->stream>>>(e->d_state, S[p.n_streams], e->d_ctl, n);
+            e->stats.kernel_launches++;
+            gin = S[p.n_streams];
+        } else gin = e->stream_in_ptr;
     }
-#define OSC_EW(OP, ARGS)                                                                   \
-    do {                                                                                   \
-        if (vec) ew_node_vec_kernel<OP><<<vgrid, 256, 0, e->stream>>>(ARGS);               \
-        else ew_node_kernel<OP><<<grid, kCta, 0, e->stream>>>(ARGS);                       \
-        e->stats.kernel_launches++;                                                        \
-    } while (0)
-    { NodeArgs n = base(0); n.in0 = S[3]; n.pid[0] = I_ENV_AMT; n.out0 = S[4]; OSC_EW(EW_GAIN, n); }        /* filter_env_gain */
-    { NodeArgs n = base(0); n.in0 = S[4]; n.pid[0] = I_CUTOFF; n.out0 = S[5]; OSC_EW(EW_ADD_VALUE, n); }    /* cutoff_mod */
-    { NodeArgs n = base(FM_OP3); n.in0 = nullptr; n.in1 = S[0]; n.out0 = S[6];                 /* op3_osc */
-      n.pid[0] = I_FREQ; n.pid[1] = I_OP3_RATIO; n.pid[2] = I_OP3_FB; n.pid[3] = I_OP3_LEVEL;
-      fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[6]; n.pid[0] = I_ROUTE; n.out0 = S[7]; n.out1 = S[8]; OSC_EW(EW_CROSSFADE, n); }   /* op3_route */
-    { NodeArgs n = base(FM_OP2); n.in0 = S[7]; n.in1 = S[1]; n.out0 = S[9];                    /* op2_osc */
-      n.pid[0] = I_FREQ; n.pid[1] = I_OP2_RATIO; n.pid[2] = I_OP2_FB; n.pid[3] = I_OP2_LEVEL;
-      fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[9]; n.in1 = S[8]; n.out0 = S[10]; OSC_EW(EW_MIXER, n); }                        /* op1_mod_mixer */
-    { NodeArgs n = base(FM_OP1); n.in0 = S[10]; n.in1 = S[2]; n.out0 = S[11];                  /* op1_osc */
-      n.pid[0] = I_FREQ; n.pid[1] = I_OP1_RATIO; n.cst[2] = 0.0f; n.cst[3] = 1.0f;            /* feedback, level unconnected */
-      fmop_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(FM_TPT); n.in0 = S[11]; n.in1 = S[5]; n.pid[0] = I_RES; n.out0 = S[12]; /* filter */
-      tpt_node_kernel<<<grid, kCta, 0, e->stream>>>(n); e->stats.kernel_launches++; }
-    { NodeArgs n = base(0); n.in0 = S[12]; n.cst[0] = 0.3f; n.out0 = S[13]; OSC_EW(EW_GAIN, n); }                    /* output_gain */
-#undef OSC_EW
-    { KernelArgs a; fill_args(e, a); a.voice_out = nullptr;                                   /* voices.audio_out -> audio_out */
-      instance_mix_node_kernel<<<grid, kCta, 0, e->stream>>>(a, S[13]); e->stats.kernel_launches++; e->n_cta_mix = grid; }
-    { const uint32_t g = 296;
-      commit_value_events_kernel<<<g, 256, 0, e->stream>>>(e->d_pv, e->d_events, e->d_ctl, e->cfg.n_voices, e->n_inputs);
-      e->stats.kernel_launches++; }
+    auto resolve = [&](const plan::StreamRef &r) -> float * {
+        if (r.node == plan::kNone) return nullptr;
+        if (r.node == plan::kGraphInput) return const_cast<float *>(gin);
+        return S[p.first_stream[r.node] + r.port];
+    };
+    auto args_of = [&](int idx) {
+        const plan::Node &nd = g.nodes[idx];
+        NodeArgs a{};
+        a.n_voices = n; a.state_base = nd.state_base; a.ctl = e->d_ctl; a.events = e->d_events;
+        a.ptab = e->d_ptab; a.pv = e->d_pv; a.state = e->d_state; a.sr = e->cfg.sample_rate;
+        a.in0 = resolve(nd.in[0]); a.in1 = resolve(nd.in[1]);
+        a.out0 = S[p.first_stream[idx]];
+        a.out1 = plan::n_outputs(nd.type) > 1 ? S[p.first_stream[idx] + 1] : nullptr;
+        for (int k = 0; k < 4; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
+        return a;
+    };
+    for (const plan::Launch &l : p.launches) {
+        NodeArgs4 a4{};
+        const uint32_t cnt = (uint32_t)l.nodes.size();
+        for (uint32_t k = 0; k < cnt; ++k) a4.n[k] = args_of(l.nodes[k]);
+        const dim3 g2(grid, cnt);
+        switch (l.type) {
+        case plan::NodeType::Adsr: adsr_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::FmOperator: fmop_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::Tpt: tpt_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::PolyBlepSine: polyblep_node_kernel<WAVE_SINE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::PolyBlepSaw: polyblep_node_kernel<WAVE_SAW><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::Lp18: lp18_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        default:
+            for (uint32_t k = 0; k < cnt; ++k) {                       /* stateless nodes: one stream kernel each */
+                const NodeArgs &a = a4.n[k];
+                switch (l.type) {
+                case plan::NodeType::Gain:
+                    if (a.in1 != nullptr) launch_ew<EW_MUL>(e, a, vec); else launch_ew<EW_GAIN>(e, a, vec);
+                    break;
+                case plan::NodeType::AddValue: launch_ew<EW_ADD_VALUE>(e, a, vec); break;
+                case plan::NodeType::Mixer: launch_ew<EW_MIXER>(e, a, vec); break;
+                case plan::NodeType::Sub: launch_ew<EW_SUB>(e, a, vec); break;
+                case plan::NodeType::Crossfade: launch_ew<EW_CROSSFADE>(e, a, vec); break;
+                default: launch_ew<EW_HARDCLIP>(e, a, vec); break;
+                }
+            }
+            break;
+        }
+    }
+    e->final_stream = S[p.first_stream[g.output.node] + g.output.port];
+    { KernelArgs a; fill_args(e, a); a.voice_out = nullptr;           /* voices.audio_out -> audio_out */
+      instance_mix_node_kernel<<<grid, kCta, 0, e->stream>>>(a, e->final_stream); e->stats.kernel_launches++; e->n_cta_mix = grid; }
+    commit_value_events_kernel<<<296, 256, 0, e->stream>>>(e->d_pv, e->d_events, e->d_ctl, n, e->n_inputs);
+    e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
     return 0;
 }
@@ -378,8 +402,13 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         g_create_error = "bad config (graph kind / voices / voices_per_instance must be a power of two <= 64 dividing n_voices / sample rate / plan)";
         return OSCEN_B200_E_ARG;
     }
-    if (cfg->plan == OSCEN_B200_PLAN_NODES && cfg->graph_kind != OSCEN_B200_GRAPH_FM_VOICE) {
-        g_create_error = "PLAN_NODES is implemented for GRAPH_FM_VOICE only"; return OSCEN_B200_E_ARG;
+    plan::Graph pg; plan::Plan pp;
+    if (cfg->plan == OSCEN_B200_PLAN_NODES) {
+        std::string perr;
+        if (!plan::for_kind(cfg->graph_kind, pg)) {
+            g_create_error = "PLAN_NODES: this graph (multirate / array streams) only has a fused kernel"; return OSCEN_B200_E_ARG;
+        }
+        if (!plan::compile(pg, pp, perr)) { g_create_error = "PLAN_NODES: " + perr; return OSCEN_B200_E_ARG; }
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -419,8 +448,10 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
         CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1)); CK(e, cudaEventCreate(&e->evk));
         if (cfg->plan == OSCEN_B200_PLAN_NODES) {
-            e->d_streams.resize(14, nullptr);
+            e->graph = pg; e->plan = pp;
+            e->d_streams.resize((size_t)pp.n_streams + 1, nullptr);      /* + 1: device-generated graph input */
             for (auto &p : e->d_streams) CK(e, cudaMalloc(&p, (size_t)kMaxBlock * n * sizeof(float)));
+            e->final_stream = e->d_streams[pp.first_stream[pg.output.node] + pg.output.port];
         }
         CK(e, cudaFuncSetAttribute(sat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
         CK(e, cudaFuncSetAttribute(sat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
@@ -672,11 +703,15 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     } else {
         /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
         const int gi = has_value_events ? 1 : 0;
+        if (e->captured_in != e->stream_in_ptr || e->captured_lcg != e->lcg_on) {
+            for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+            e->captured_in = e->stream_in_ptr; e->captured_lcg = e->lcg_on;
+        }
         if (!e->graph_exec[gi]) {
             cudaGraph_t g = nullptr;
             CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t before = e->stats.kernel_launches;
-            rc = launch_fm_nodes(e, has_value_events);
+            rc = launch_plan(e, has_value_events);
             if (!rc) rc = launch_mix_reduce(e, frames);
             cudaError_t s = cudaStreamEndCapture(e->stream, &g);
             e->graph_kernels[gi] = e->stats.kernel_launches - before;
@@ -718,7 +753,7 @@ int oscen_b200_synchronize(oscen_b200_engine *e) {
 
 int oscen_b200_read_voice_out(oscen_b200_engine *e, float *dst, uint32_t first, uint32_t count) {
     if (!e || !dst) return OSCEN_B200_E_ARG;
-    const float *src = e->cfg.plan == OSCEN_B200_PLAN_NODES ? e->d_streams[13] : e->d_voice_out;
+    const float *src = e->cfg.plan == OSCEN_B200_PLAN_NODES ? e->final_stream : e->d_voice_out;
     if (!src) { e->err = "read_voice_out: engine created without KEEP_VOICE_OUT"; return OSCEN_B200_E_STATE; }
     if ((uint64_t)first + count > e->cfg.n_voices || count == 0) return arg_error(e, "read_voice_out: range");
     CK(e, cudaSetDevice(e->cfg.device));
@@ -809,6 +844,16 @@ int oscen_b200_l2_flush(oscen_b200_engine *e) {
     fill_u32_kernel<<<1184, 256, 0, e->stream>>>(e->d_flush, words, (uint32_t)e->stats.blocks);
     CK(e, cudaGetLastError());
     return 0;
+}
+
+int oscen_b200_plan_describe(uint32_t graph_kind, char *dst, size_t cap) {
+    if (!dst || cap == 0) return OSCEN_B200_E_ARG;
+    plan::Graph g; plan::Plan p; std::string err;
+    if (!plan::for_kind(graph_kind, g) || !plan::compile(g, p, err)) { dst[0] = 0; return OSCEN_B200_E_ARG; }
+    const std::string s = plan::describe(g, p);
+    if (s.size() + 1 > cap) return OSCEN_B200_E_ARG;
+    memcpy(dst, s.c_str(), s.size() + 1);
+    return (int)p.launches.size();
 }
 
 int oscen_b200_comm_p2p_export(oscen_b200_engine *e, int n_ranks, void *handle64) {

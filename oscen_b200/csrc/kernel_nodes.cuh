@@ -1,17 +1,21 @@
 /*
  * kernel_nodes.cuh — the node-granular plan: ONE kernel per node type over
  * [voices x frames_per_block], inter-node streams materialised in HBM as [frame][voice] f32,
- * per-node state SoA in HBM, launched in the graph compiler's topological order
- * (oscen-graph-compiler/src/ir/lower.rs:1015-1085) and replayed as a CUDA graph.
+ * per-node state SoA in HBM, launched in the plan compiler's topological order (plan.hpp,
+ * mirroring oscen-graph-compiler/src/ir/lower.rs:1015-1085) and replayed as a CUDA graph.
  * This is the HBM-bound formulation BASELINE.md's byte model N describes.
  *
- * Every node kernel is "one thread = one voice, serial in time" (each stateful node is a
- * nonlinear / time-varying recurrence; a parallel scan would change the rounding order), with
- * stream inputs prefetched 8 frames deep so a warp keeps 8 x 128 B loads in flight per input.
+ * Stateful nodes are "one thread = one voice, serial in time" (each is a nonlinear / time-varying
+ * recurrence; a parallel scan would change the rounding order).  All ready nodes of one type
+ * share a launch (blockIdx.y = node) so the serial recurrences of independent nodes overlap.
+ * Stream inputs are software-pipelined 8 frames ahead (the loads of chunk k+1 are in flight while
+ * chunk k is computed).  Stateless nodes are float4 grid-stride streams unless the block carries
+ * value events.
  */
 #pragma once
 #include "kernels_common.cuh"
 #include "kernel_fm.cuh"
+#include "kernel_others.cuh"
 
 namespace oscen {
 
@@ -32,6 +36,7 @@ struct NodeArgs {
     float cst[4];
     float sr;
 };
+struct NodeArgs4 { NodeArgs n[4]; };        /* blockIdx.y selects the node */
 
 template <uint32_t NP>
 struct NodeParams {
@@ -52,7 +57,7 @@ struct NodeParams {
 #pragma unroll
         for (uint32_t k = 0; k < NP; ++k) if (e.input_id == a.pid[k]) P[k] = e.scalar;
     }
-    /* apply this frame's value events; returns the [i, j) event range of the frame */
+    /* apply this frame's value events; returns the end of the frame's event range */
     OSC_D uint32_t events(const NodeArgs &a, EventCursor &ec, uint32_t f) {
         const uint32_t j = ec.end_of_frame(f);
         for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) value_event(a, ec.ev[q]);
@@ -61,6 +66,7 @@ struct NodeParams {
 };
 
 #define OSC_NODE_PROLOGUE(NP)                                                             \
+    const NodeArgs &a = args.n[blockIdx.y];                                               \
     const uint32_t n = a.n_voices;                                                        \
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;                             \
     if (v >= n) return;                                                                   \
@@ -68,12 +74,16 @@ struct NodeParams {
     NodeParams<NP> prm; prm.load(a, v);                                                   \
     EventCursor ec; ec.init(a.events, a.ctl->n_events, v);
 
-/* AdsrEnvelope node type: pid = {attack, decay, sustain, release}; out0 = output.
-   One launch renders every AdsrEnvelope node of the graph (blockIdx.y = node): the nodes are
-   mutually independent sources, and 4x the warps hide the serial recurrence's latency. */
-struct NodeArgs4 { NodeArgs n[4]; };
+/* two-input software pipeline: A/B hold chunk k, A_N/B_N receive chunk k+1 */
+#define OSC_LOAD2(A, B, PA, PB, F0)                                                                     \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                              \
+        const uint32_t f_ = (F0) + k;                                                                   \
+        A[k] = ((PA) != nullptr && f_ < frames) ? __ldcs((PA) + (size_t)f_ * n + v) : 0.0f;             \
+        B[k] = ((PB) != nullptr && f_ < frames) ? __ldcs((PB) + (size_t)f_ * n + v) : 0.0f;             \
+    }
+
+/* ---- AdsrEnvelope: pid = {attack, decay, sustain, release}; out0 = output */
 __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__ NodeArgs4 args) {
-    const NodeArgs &a = args.n[blockIdx.y];
     OSC_NODE_PROLOGUE(4)
     AdsrState s; adsr_load(s, a.state, a.state_base, n, v);
     AdsrDerived d; adsr_derive(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
@@ -93,23 +103,16 @@ __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__
     adsr_store(s, a.state, a.state_base, n, v);
 }
 
-/* FmOperator node: in0 = phase_mod (nullable), in1 = envelope; pid = {base_freq, ratio, feedback, level} */
-__global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__ NodeArgs a) {
+/* ---- FmOperator: in0 = phase_mod (nullable), in1 = envelope; pid = {base_freq, ratio, feedback, level} */
+__global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__ NodeArgs4 args) {
     OSC_NODE_PROLOGUE(4)
     FmOpState s;
     s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
     s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
-    /* software pipeline: the loads of chunk k+1 are in flight while chunk k is computed */
     float pm[kPF], en[kPF], pm_n[kPF], en_n[kPF];
-#define OSC_FMOP_LOAD(PM, EN, F0)                                                             \
-    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                    \
-        const uint32_t f = (F0) + k;                                                          \
-        PM[k] = (a.in0 != nullptr && f < frames) ? __ldcs(a.in0 + (size_t)f * n + v) : 0.0f;  \
-        EN[k] = (f < frames) ? __ldcs(a.in1 + (size_t)f * n + v) : 0.0f;                      \
-    }
-    OSC_FMOP_LOAD(pm, en, 0u)
+    OSC_LOAD2(pm, en, a.in0, a.in1, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        OSC_FMOP_LOAD(pm_n, en_n, f0 + kPF)
+        OSC_LOAD2(pm_n, en_n, a.in0, a.in1, f0 + kPF)
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
@@ -122,75 +125,131 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) { pm[k] = pm_n[k]; en[k] = en_n[k]; }
     }
-#undef OSC_FMOP_LOAD
     a.state[(size_t)(a.state_base + 0) * n + v] = s.phase; a.state[(size_t)(a.state_base + 1) * n + v] = s.prev;
 }
 
-/* TptFilter node: in0 = input, in1 = cutoff stream; pid = {q} */
-__global__ void __launch_bounds__(kCta) tpt_node_kernel(const __grid_constant__ NodeArgs a) {
-    OSC_NODE_PROLOGUE(1)
+/* ---- TptFilter: in0 = input, in1 = cutoff stream (nullable: then the value input pid[1] feeds the
+        `cutoff` stream endpoint, a broadcast per frame); pid = {q, cutoff} */
+__global__ void __launch_bounds__(kCta) tpt_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(2)
     TptState s; tpt_load(s, a.state, a.state_base, n, v);
+    const bool cut_stream = a.in1 != nullptr;
     float x[kPF], c[kPF], x_n[kPF], c_n[kPF];
-#define OSC_TPT_LOAD(X, C, F0)                                                                \
-    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                    \
-        const uint32_t f = (F0) + k;                                                          \
-        X[k] = (f < frames) ? __ldcs(a.in0 + (size_t)f * n + v) : 0.0f;                       \
-        C[k] = (f < frames) ? __ldcs(a.in1 + (size_t)f * n + v) : 0.0f;                       \
-    }
-    OSC_TPT_LOAD(x, c, 0u)
+    OSC_LOAD2(x, c, a.in0, a.in1, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        OSC_TPT_LOAD(x_n, c_n, f0 + kPF)
+        OSC_LOAD2(x_n, c_n, a.in0, a.in1, f0 + kPF)
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
             if (f < frames) {
                 prm.ramps(a, ramp_mask, f);
                 if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                __stcs(a.out0 + (size_t)f * n + v, tpt_process(s, x[k], c[k], prm.P[0], 0.0f, a.sr));
+                __stcs(a.out0 + (size_t)f * n + v, tpt_process(s, x[k], cut_stream ? c[k] : prm.P[1], prm.P[0], 0.0f, a.sr));
             }
         }
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) { x[k] = x_n[k]; c[k] = c_n[k]; }
     }
-#undef OSC_TPT_LOAD
     tpt_store(s, a.state, a.state_base, n, v);
 }
 
-/* stateless nodes: Gain (in*param | in*const), AddValue (in+param), Mixer (a+b), Crossfade */
-enum : int { EW_GAIN = 0, EW_ADD_VALUE = 1, EW_MIXER = 2, EW_CROSSFADE = 3 };
-template <int OP>
-__global__ void __launch_bounds__(kCta) ew_node_kernel(const __grid_constant__ NodeArgs a) {
-    OSC_NODE_PROLOGUE(1)
+/* ---- PolyBlepOscillator: in0 = frequency_mod (nullable); pid = {frequency, amplitude} */
+template <int WAVE>
+__global__ void __launch_bounds__(kCta) polyblep_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(2)
+    float phase = a.state[(size_t)a.state_base * n + v];
+    float fm[kPF], dummy[kPF], fm_n[kPF], dummy_n[kPF];
+    const float *no_stream = nullptr;
+    OSC_LOAD2(fm, dummy, a.in0, no_stream, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        float x[kPF], y[kPF];
-#pragma unroll
-        for (uint32_t k = 0; k < kPF; ++k) {
-            const uint32_t f = f0 + k;
-            x[k] = (f < frames) ? __ldg(a.in0 + (size_t)f * n + v) : 0.0f;
-            y[k] = (OP == EW_MIXER && f < frames) ? __ldg(a.in1 + (size_t)f * n + v) : 0.0f;
-        }
+        OSC_LOAD2(fm_n, dummy_n, a.in0, no_stream, f0 + kPF)
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
             if (f < frames) {
                 prm.ramps(a, ramp_mask, f);
                 if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                if (OP == EW_GAIN) a.out0[(size_t)f * n + v] = x[k] * prm.P[0];          /* gain/mod.rs:30-35 */
-                else if (OP == EW_ADD_VALUE) a.out0[(size_t)f * n + v] = x[k] + prm.P[0]; /* add_value.rs:33-35 */
-                else if (OP == EW_MIXER) a.out0[(size_t)f * n + v] = x[k] + y[k];        /* mixer.rs:32-34 */
-                else {                                                                    /* crossfade.rs:39-44 */
-                    const float mix = clampf(prm.P[0], 0.0f, 1.0f);
-                    a.out0[(size_t)f * n + v] = x[k] * (1.0f - mix);
-                    a.out1[(size_t)f * n + v] = x[k] * mix;
-                }
+                __stcs(a.out0 + (size_t)f * n + v, polyblep_process<WAVE>(phase, 0.0f, prm.P[0], fm[k], prm.P[1], 0.5f, a.sr));
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) fm[k] = fm_n[k];
+    }
+    a.state[(size_t)a.state_base * n + v] = phase;
+}
+
+/* ---- LP18Filter: in0 = input; pid = {cutoff, resonance} */
+__global__ void __launch_bounds__(kCta) lp18_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(2)
+    Lp18State s; lp18_load(s, a.state, a.state_base, n, v);
+    float x[kPF], dummy[kPF], x_n[kPF], dummy_n[kPF];
+    const float *no_stream = nullptr;
+    OSC_LOAD2(x, dummy, a.in0, no_stream, 0u)
+    for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
+        OSC_LOAD2(x_n, dummy_n, a.in0, no_stream, f0 + kPF)
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) {
+            const uint32_t f = f0 + k;
+            if (f < frames) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+                __stcs(a.out0 + (size_t)f * n + v, lp18_process(s, x[k], prm.P[0], 0.0f, prm.P[1], a.sr));
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) x[k] = x_n[k];
+    }
+    lp18_store(s, a.state, a.state_base, n, v);
+}
+
+/* ---- stateless nodes */
+enum : int {
+    EW_GAIN = 0,        /* Gain: in0 * (value | constant)        gain/mod.rs:30-35      */
+    EW_ADD_VALUE = 1,   /* AddValue: in0 + value                 add_value.rs:33-35     */
+    EW_MIXER = 2,       /* Mixer: in0 + in1                      mixer.rs:32-34         */
+    EW_CROSSFADE = 3,   /* Crossfade: in0*(1-mix), in0*mix       crossfade.rs:39-44     */
+    EW_MUL = 4,         /* Gain with a stream on `gain`: in0 * in1                       */
+    EW_SUB = 5,         /* expression edge a - b                 codegen/mod.rs:433-472 */
+    EW_HARDCLIP = 6,    /* HardClip                              oversampled-saturator main.rs:55-62 */
+};
+template <int OP>
+OSC_D void ew_apply(float x, float y, float p, float &o0, float &o1) {
+    o1 = 0.0f;
+    if (OP == EW_GAIN) o0 = x * p;
+    else if (OP == EW_ADD_VALUE) o0 = x + p;
+    else if (OP == EW_MIXER) o0 = x + y;
+    else if (OP == EW_MUL) o0 = x * y;
+    else if (OP == EW_SUB) o0 = x - y;
+    else if (OP == EW_HARDCLIP) o0 = hardclip_process(x);
+    else { const float mix = clampf(p, 0.0f, 1.0f); o0 = x * (1.0f - mix); o1 = x * mix; }
+}
+template <int OP> OSC_HD constexpr bool ew_two_inputs() { return OP == EW_MIXER || OP == EW_MUL || OP == EW_SUB; }
+
+/* serial per-voice form (used when the block carries value events) */
+template <int OP>
+__global__ void __launch_bounds__(kCta) ew_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(1)
+    for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
+        float x[kPF], y[kPF];
+        const float *pb = ew_two_inputs<OP>() ? a.in1 : nullptr;
+        OSC_LOAD2(x, y, a.in0, pb, f0)
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) {
+            const uint32_t f = f0 + k;
+            if (f < frames) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+                float o0, o1;
+                ew_apply<OP>(x[k], y[k], prm.P[0], o0, o1);
+                a.out0[(size_t)f * n + v] = o0;
+                if (OP == EW_CROSSFADE) a.out1[(size_t)f * n + v] = o1;
             }
         }
     }
 }
 
-/* Stateless nodes, vectorised: when the block carries no value events every element (frame, voice)
-   is independent, so the kernel is a float4 grid-stride stream over [frames x voices] — the
-   HBM-bound form (two 16-byte loads, one or two 16-byte stores per thread-iteration).  Requires
+/* vectorised form: without value events every element (frame, voice) is independent, so the
+   node is a float4 grid-stride stream over [frames x voices] — the HBM-bound form.  Requires
    n_voices % 4 == 0.  The value input is per voice (pv row) unless it is ramping this block
    (then one scalar per frame from ptab). */
 template <int OP>
@@ -208,19 +267,30 @@ __global__ void __launch_bounds__(256) ew_node_vec_kernel(const __grid_constant_
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t f = (uint32_t)(i / n4), v4 = (uint32_t)(i - (size_t)f * n4);
         const float4 x = __ldcs(in0 + i);
+        float4 y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (ew_two_inputs<OP>()) y = __ldcs(in1 + i);
         float4 p;
         if (!has_p) p = make_float4(a.cst[0], a.cst[0], a.cst[0], a.cst[0]);
         else if (ramped) { const float r = a.ptab[(size_t)f * kMaxInputs + a.pid[0]]; p = make_float4(r, r, r, r); }
         else p = __ldg(pv + v4);
-        if (OP == EW_GAIN) { __stcs(out0 + i, make_float4(x.x * p.x, x.y * p.y, x.z * p.z, x.w * p.w)); }
-        else if (OP == EW_ADD_VALUE) { __stcs(out0 + i, make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w)); }
-        else if (OP == EW_MIXER) { const float4 y = __ldcs(in1 + i); __stcs(out0 + i, make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w)); }
-        else {
-            const float4 m = make_float4(clampf(p.x, 0.0f, 1.0f), clampf(p.y, 0.0f, 1.0f), clampf(p.z, 0.0f, 1.0f), clampf(p.w, 0.0f, 1.0f));
-            __stcs(out0 + i, make_float4(x.x * (1.0f - m.x), x.y * (1.0f - m.y), x.z * (1.0f - m.z), x.w * (1.0f - m.w)));
-            __stcs(out1 + i, make_float4(x.x * m.x, x.y * m.y, x.z * m.z, x.w * m.w));
-        }
+        float4 o0, o1;
+        ew_apply<OP>(x.x, y.x, p.x, o0.x, o1.x); ew_apply<OP>(x.y, y.y, p.y, o0.y, o1.y);
+        ew_apply<OP>(x.z, y.z, p.z, o0.z, o1.z); ew_apply<OP>(x.w, y.w, p.w, o0.w, o1.w);
+        __stcs(out0 + i, o0);
+        if (OP == EW_CROSSFADE) __stcs(out1 + i, o1);
     }
+}
+
+/* graph input generated on device (TWIN_PEAKS audio_in from the per-voice LCG): a source node */
+__global__ void __launch_bounds__(kCta) lcg_source_kernel(float *state, float *out, const BlockCtl *ctl, uint32_t n) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    unsigned long long lcg = (unsigned long long)__float_as_uint(state[(size_t)(TW_LCG + 0) * n + v]) |
+                             ((unsigned long long)__float_as_uint(state[(size_t)(TW_LCG + 1) * n + v]) << 32);
+    const uint32_t frames = ctl->frames;
+    for (uint32_t f = 0; f < frames; ++f) out[(size_t)f * n + v] = lcg_next(lcg);
+    state[(size_t)(TW_LCG + 0) * n + v] = __uint_as_float((uint32_t)(lcg & 0xffffffffull));
+    state[(size_t)(TW_LCG + 1) * n + v] = __uint_as_float((uint32_t)(lcg >> 32));
 }
 
 /* graph output: voices.audio_out -> audio_out (instance sums in index order) + mix partials */

@@ -1,0 +1,149 @@
+/*
+ * plan.hpp — the node-granular launch plan: a small host-side "graph compiler" back end.
+ *
+ * The reference's `graph!` macro lowers a graph description to IR (nodes, edges), sorts the nodes
+ * topologically with Kahn's algorithm over the non-feedback edges
+ * (oscen-graph-compiler/src/ir/lower.rs:1015-1085) and emits one `process()` call per node in
+ * that order (codegen/mod.rs:499-514).  Here the same description (nodes with their stream
+ * edges and value inputs, as written in the reference graph files) is sorted the same way and
+ * becomes a CUDA-graph launch sequence: one kernel launch per node TYPE per ready wave (all
+ * ready nodes of one type share a launch, blockIdx.y = node), streams in HBM between them.
+ *
+ * Any valid topological order is result-identical because every edge into a node is evaluated
+ * immediately before that node runs; the reference's own order is not even
+ * deterministic across compiles (its ready queue is seeded from a HashMap), ours is: ready
+ * nodes are taken in declaration order.
+ *
+ * Host-only, no CUDA types: unit-tested on CPU through oscen_b200_plan_describe().
+ */
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace oscen {
+namespace plan {
+
+enum class NodeType : uint8_t {
+    Adsr,          /* AdsrEnvelope                     value: attack decay sustain release; event: gate */
+    FmOperator,    /* FmOperator                       stream: phase_mod, envelope; value: base_freq ratio feedback level */
+    Tpt,           /* TptFilter                        stream: input, cutoff(or value); value: q */
+    PolyBlepSine,  /* PolyBlepOscillator::sine         stream: frequency_mod; value: frequency amplitude */
+    PolyBlepSaw,   /* PolyBlepOscillator::saw */
+    Lp18,          /* LP18Filter                       stream: input; value: cutoff resonance */
+    Gain,          /* Gain: input * gain (gain = value input, constant, or a second stream) */
+    AddValue,      /* AddValue: input + value */
+    Mixer,         /* Mixer: a + b */
+    Sub,           /* compound source expression `a - b` (codegen/mod.rs:433-472) */
+    Crossfade,     /* Crossfade: two outputs */
+    HardClip,      /* HardClip */
+};
+
+constexpr int kGraphInput = -2;      /* stream source: the graph's `audio_in` block */
+constexpr int kNone = -1;
+constexpr uint32_t kNoValue = 0xFFFFFFFFu;
+
+struct StreamRef { int node = kNone; int port = 0; };   /* node index (or kGraphInput / kNone), output port */
+
+struct Node {
+    const char *name;
+    NodeType type;
+    StreamRef in[2];                 /* stream inputs (meaning per type, see above) */
+    uint32_t pid[4];                 /* value-input ids of the graph feeding this node (kNoValue: use cst) */
+    float cst[4];                    /* constructor value for unconnected inputs */
+    uint32_t state_base;             /* first SoA state field of this node (engine_types.h) */
+};
+
+struct Graph {
+    std::vector<Node> nodes;
+    StreamRef output;                /* the stream connected to the graph's audio output */
+};
+
+struct Launch {
+    NodeType type;
+    std::vector<int> nodes;          /* 1..4 node indices rendered by this launch (blockIdx.y) */
+};
+
+struct Plan {
+    std::vector<int> order;          /* topological order (node indices) */
+    std::vector<Launch> launches;    /* grouped by ready wave and type */
+    std::vector<int> first_stream;   /* per node: index of its first output stream buffer */
+    int n_streams = 0;
+};
+
+inline int n_outputs(NodeType t) { return t == NodeType::Crossfade ? 2 : 1; }
+
+/* Kahn's algorithm in waves: wave k holds every node whose producers all sit in earlier waves */
+inline bool compile(const Graph &g, Plan &p, std::string &err) {
+    const int n = (int)g.nodes.size();
+    std::vector<int> indeg(n, 0);
+    std::vector<std::vector<int>> users(n);
+    for (int i = 0; i < n; ++i)
+        for (const StreamRef &r : g.nodes[i].in)
+            if (r.node >= 0) {
+                if (r.node >= n || r.port >= n_outputs(g.nodes[r.node].type)) { err = "bad edge"; return false; }
+                indeg[i]++; users[r.node].push_back(i);
+            }
+    p = Plan();
+    p.first_stream.assign(n, 0);
+    for (int i = 0; i < n; ++i) { p.first_stream[i] = p.n_streams; p.n_streams += n_outputs(g.nodes[i].type); }
+    std::vector<int> ready;
+    for (int i = 0; i < n; ++i) if (indeg[i] == 0) ready.push_back(i);
+    int done = 0;
+    while (!ready.empty()) {
+        std::vector<int> next;
+        /* one launch per node type present in this wave (declaration order inside a launch) */
+        std::vector<bool> taken(ready.size(), false);
+        for (size_t a = 0; a < ready.size(); ++a) {
+            if (taken[a]) continue;
+            Launch l; l.type = g.nodes[ready[a]].type;
+            for (size_t b = a; b < ready.size(); ++b)
+                if (!taken[b] && g.nodes[ready[b]].type == l.type && l.nodes.size() < 4) { l.nodes.push_back(ready[b]); taken[b] = true; }
+            p.launches.push_back(l);
+        }
+        for (int i : ready) {
+            p.order.push_back(i); ++done;
+            for (int u : users[i]) if (--indeg[u] == 0) next.push_back(u);
+        }
+        std::sort(next.begin(), next.end());
+        ready.swap(next);
+    }
+    if (done != n) { err = "cycle in graph (feedback edges are not supported)"; return false; }
+    if (g.output.node < 0 || g.output.node >= n) { err = "graph has no output"; return false; }
+    return true;
+}
+
+inline const char *type_name(NodeType t) {
+    switch (t) {
+    case NodeType::Adsr: return "AdsrEnvelope";
+    case NodeType::FmOperator: return "FmOperator";
+    case NodeType::Tpt: return "TptFilter";
+    case NodeType::PolyBlepSine: return "PolyBlepOscillator::sine";
+    case NodeType::PolyBlepSaw: return "PolyBlepOscillator::saw";
+    case NodeType::Lp18: return "LP18Filter";
+    case NodeType::Gain: return "Gain";
+    case NodeType::AddValue: return "AddValue";
+    case NodeType::Mixer: return "Mixer";
+    case NodeType::Sub: return "Sub(expr)";
+    case NodeType::Crossfade: return "Crossfade";
+    default: return "HardClip";
+    }
+}
+
+/* text form of a compiled plan: "launch k: Type node,node | ..." (for tests and DESIGN.md) */
+inline std::string describe(const Graph &g, const Plan &p) {
+    std::string s;
+    for (size_t k = 0; k < p.launches.size(); ++k) {
+        s += std::to_string(k) + ": " + type_name(p.launches[k].type) + " [";
+        for (size_t j = 0; j < p.launches[k].nodes.size(); ++j) {
+            if (j) s += ", ";
+            s += g.nodes[p.launches[k].nodes[j]].name;
+        }
+        s += "]\n";
+    }
+    return s;
+}
+
+}  // namespace plan
+}  // namespace oscen

@@ -463,3 +463,46 @@ def test_config3_full_size_electric_piano_131072_instances():
     assert np.abs(io).max() > 1e-3 and np.abs(io[..., 0] - io[..., 1]).max() > 1e-6
     mix = gpu.read_mix()
     assert np.isfinite(mix).all() and np.abs(mix).max() > 1.0
+
+
+# --------------------------------------------------------------- plan compiler: node plans of the other graphs
+@pytest.mark.parametrize("kind", [O.K_SYNTH, O.K_SYNTH_ADSR, O.K_SAT1, O.K_TWIN])
+def test_node_plans_match_fused_and_oracle(kind):
+    n = 192
+    ref = O.OracleBank(kind, n, 1)
+    fused, nodes = engine(kind, n, 1, plan=0), engine(kind, n, 1, plan=1)
+    x = np.stack([lcg_noise(512, 77 + v) for v in range(n)], axis=1) if kind == O.K_TWIN else None
+
+    def script(b):
+        out = []
+        if kind in (O.K_SYNTH, O.K_SYNTH_ADSR):
+            b.set_value(2, (80.0 + 9.0 * np.arange(n)).astype(np.float32))
+            b.set_value(3, (400.0 + 50.0 * np.arange(n)).astype(np.float32))
+        elif kind == O.K_SAT1:
+            b.set_value(0, (500.0 + 20.0 * np.arange(n)).astype(np.float32))
+        for blk in range(2):
+            if kind == O.K_TWIN:
+                b.stream_in(0, x[blk * 256:(blk + 1) * 256])
+            if kind == O.K_SYNTH_ADSR:
+                b.push_events([(v, (v + 3 * blk) % 200, GATE, 0.9 if blk == 0 else 0.0) for v in range(n)])
+            if blk == 1 and kind != O.K_SAT1:
+                b.set_value_ramp(0, 7.0 if kind != O.K_TWIN else 1200.0, 100)
+                b.push_events([(5, 40, 1 if kind != O.K_TWIN else 1, 0.3 if kind != O.K_TWIN else 2500.0)])   # a value event
+            b.process_block(256)
+            out.append((b.read_voice_out(), b.read_mix()))
+        return out
+
+    ro, fo, no = drive((ref, fused, nodes), script)
+    for (vr, mr), (vf, mf), (vn, mn) in zip(ro, fo, no):
+        assert np.array_equal(vf, vr) and np.array_equal(vn, vr)
+        assert np.allclose(mn, mr, rtol=1e-5, atol=1e-4)
+
+
+def test_twin_peaks_node_plan_with_device_lcg_source():
+    n = 130
+    fused, nodes = engine(O.K_TWIN, n, 1, plan=0), engine(O.K_TWIN, n, 1, plan=1)
+    for e in (fused, nodes):
+        e.stream_in_lcg(0, 4242, 11)
+    for _ in range(3):
+        fused.process_block(200); nodes.process_block(200)
+        assert np.array_equal(fused.read_voice_out(), nodes.read_voice_out())

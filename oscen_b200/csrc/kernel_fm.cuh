@@ -14,6 +14,16 @@
 #pragma once
 #include "kernels_common.cuh"
 
+/* 1: move the per-voice state rows HBM <-> shared memory with TMA bulk copies (cp.async.bulk +
+   mbarrier) instead of per-thread coalesced loads/stores.  Built, bit-exact, measured SLOWER on
+   B200 (0.2736 vs 0.2652 ms per block at 65 536 voices; 3.76 vs 3.67 ms at 1 M): the state is
+   touched once per 256-frame block (1.4 B/voice-sample), so the extra barrier, the mbarrier wait
+   before the first instruction of the recurrence and the shared-memory round trip cost more than
+   the handful of LDG/STG they replace.  Off by default. */
+#ifndef OSCEN_B200_TMA_STATE
+#define OSCEN_B200_TMA_STATE 0
+#endif
+
 namespace oscen {
 
 enum : uint32_t {   /* == OSCEN_B200_FM_* */
@@ -50,8 +60,10 @@ OSC_D void tpt_store(const TptState &s, float *st, uint32_t base, uint32_t n, ui
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ KernelArgs a) {
-    __shared__ float tile[kTileF * kTileW];
+    __shared__ __align__(128) float tile[kTileF * kTileW];    /* also the TMA staging area for the state rows */
     __shared__ float isum[kTileF * kCta];
+    __shared__ __align__(8) unsigned long long state_bar;
+    static_assert(FM_NSTATE * kCta <= kTileF * kTileW, "state staging fits in the output tile");
 
     const uint32_t n = a.n_voices;
     const uint32_t v = blockIdx.x * kCta + threadIdx.x;
@@ -68,14 +80,21 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
     for (uint32_t i = 0; i < I_FM_N; ++i) P[i] = GENERAL ? a.pv[(size_t)i * n + vs] : a.u.p[i];
     if (!GENERAL) P[I_FREQ] = a.pv[vs];
 
-    /* ---- state */
+    /* ---- state: block-to-block handoff through TMA bulk copies (HBM rows -> smem -> registers) */
+    const float *sp = a.state; uint32_t sn = n, sv = vs;
+#if OSCEN_B200_TMA_STATE
+    const bool staged = state_stage_in(tile, &state_bar, a.state, FM_NSTATE, n, sp, sn, sv, vs);
+#else
+    const bool staged = false;           /* plain coalesced loads: measured 2-3 % faster, see DESIGN.md §4.3 */
+    (void)state_bar;
+#endif
     AdsrState e3, e2, e1, ef;
-    adsr_load(e3, a.state, FM_E3, n, vs); adsr_load(e2, a.state, FM_E2, n, vs);
-    adsr_load(e1, a.state, FM_E1, n, vs); adsr_load(ef, a.state, FM_EF, n, vs);
+    adsr_load(e3, sp, FM_E3, sn, sv); adsr_load(e2, sp, FM_E2, sn, sv);
+    adsr_load(e1, sp, FM_E1, sn, sv); adsr_load(ef, sp, FM_EF, sn, sv);
     FmOpState op3, op2, op1;
-    op3.phase = a.state[(size_t)(FM_OP3 + 0) * n + vs]; op3.prev = a.state[(size_t)(FM_OP3 + 1) * n + vs];
-    op2.phase = a.state[(size_t)(FM_OP2 + 0) * n + vs]; op2.prev = a.state[(size_t)(FM_OP2 + 1) * n + vs];
-    op1.phase = a.state[(size_t)(FM_OP1 + 0) * n + vs]; op1.prev = a.state[(size_t)(FM_OP1 + 1) * n + vs];
+    op3.phase = sp[(size_t)(FM_OP3 + 0) * sn + sv]; op3.prev = sp[(size_t)(FM_OP3 + 1) * sn + sv];
+    op2.phase = sp[(size_t)(FM_OP2 + 0) * sn + sv]; op2.prev = sp[(size_t)(FM_OP2 + 1) * sn + sv];
+    op1.phase = sp[(size_t)(FM_OP1 + 0) * sn + sv]; op1.prev = sp[(size_t)(FM_OP1 + 1) * sn + sv];
 #define OSC_FM_INCS()                                                        \
     do {                                                                     \
         op3.inc = fmop_phase_inc(P[I_FREQ], P[I_OP3_RATIO], sr);             \
@@ -84,7 +103,8 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
     } while (0)
     OSC_FM_INCS();
     TptState tp;
-    tpt_load(tp, a.state, FM_TPT, n, vs);
+    tpt_load(tp, sp, FM_TPT, sn, sv);
+    __syncthreads();                                         /* staging area becomes the output tile */
 
     AdsrDerived d3, d2, d1, df;
     if (GENERAL) {
@@ -187,13 +207,18 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
         tile_flush_mono(a, tile, isum, f0, fe);
     }
 
-    if (active) {
-        adsr_store(e3, a.state, FM_E3, n, v); adsr_store(e2, a.state, FM_E2, n, v);
-        adsr_store(e1, a.state, FM_E1, n, v); adsr_store(ef, a.state, FM_EF, n, v);
-        a.state[(size_t)(FM_OP3 + 0) * n + v] = op3.phase; a.state[(size_t)(FM_OP3 + 1) * n + v] = op3.prev;
-        a.state[(size_t)(FM_OP2 + 0) * n + v] = op2.phase; a.state[(size_t)(FM_OP2 + 1) * n + v] = op2.prev;
-        a.state[(size_t)(FM_OP1 + 0) * n + v] = op1.phase; a.state[(size_t)(FM_OP1 + 1) * n + v] = op1.prev;
-        tpt_store(tp, a.state, FM_TPT, n, v);
+    {
+        float *dp = staged ? tile : a.state;
+        const uint32_t dn = staged ? kCta : n, dv = staged ? threadIdx.x : v;
+        if (active) {
+            adsr_store(e3, dp, FM_E3, dn, dv); adsr_store(e2, dp, FM_E2, dn, dv);
+            adsr_store(e1, dp, FM_E1, dn, dv); adsr_store(ef, dp, FM_EF, dn, dv);
+            dp[(size_t)(FM_OP3 + 0) * dn + dv] = op3.phase; dp[(size_t)(FM_OP3 + 1) * dn + dv] = op3.prev;
+            dp[(size_t)(FM_OP2 + 0) * dn + dv] = op2.phase; dp[(size_t)(FM_OP2 + 1) * dn + dv] = op2.prev;
+            dp[(size_t)(FM_OP1 + 0) * dn + dv] = op1.phase; dp[(size_t)(FM_OP1 + 1) * dn + dv] = op1.prev;
+            tpt_store(tp, dp, FM_TPT, dn, dv);
+        }
+        if (staged) state_stage_out(tile, a.state, FM_NSTATE, n);
     }
 }
 

@@ -158,7 +158,8 @@ template <int WAVE>
 __global__ void __launch_bounds__(kCta) polyblep_node_kernel(const __grid_constant__ NodeArgs4 args) {
     OSC_NODE_PROLOGUE(2)
     float phase = a.state[(size_t)a.state_base * n + v];
-    float fm[kPF], dummy[kPF], fm_n[kPF], dummy_n[kPF];
+    float fm[kPF], fm_n[kPF];
+    [[maybe_unused]] float dummy[kPF], dummy_n[kPF];
     const float *no_stream = nullptr;
     OSC_LOAD2(fm, dummy, a.in0, no_stream, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(kCta) polyblep_node_kernel(const __grid_consta
 __global__ void __launch_bounds__(kCta) lp18_node_kernel(const __grid_constant__ NodeArgs4 args) {
     OSC_NODE_PROLOGUE(2)
     Lp18State s; lp18_load(s, a.state, a.state_base, n, v);
-    float x[kPF], dummy[kPF], x_n[kPF], dummy_n[kPF];
+    float x[kPF], x_n[kPF];
+    [[maybe_unused]] float dummy[kPF], dummy_n[kPF];
     const float *no_stream = nullptr;
     OSC_LOAD2(x, dummy, a.in0, no_stream, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {

@@ -39,6 +39,69 @@ struct EventCursor {
     }
 };
 
+/* ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) for the block-to-block state handoff:
+   a CTA's slice of every SoA state row is 64 voices x 4 B = 256 contiguous bytes; one elected
+   thread moves all rows HBM -> shared memory (completion on an mbarrier) at block start and
+   shared memory -> HBM (bulk async-group) at block end.  Needs 16-byte aligned rows: n_voices % 4 == 0. */
+OSC_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+OSC_D void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+OSC_D void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+OSC_D void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();          /* a lost completion must fault, not hang the GPU */
+    } while (!ok);
+}
+OSC_D void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+OSC_D void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+OSC_D void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+OSC_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* state handoff, load side: after the call `*sp / *sn / *sv` address this thread's state as
+   sp[field * sn + sv] (shared-memory staging when the TMA path is usable, HBM otherwise) */
+OSC_D bool state_stage_in(float *stage /* [n_fields][kCta], 128-B aligned */, unsigned long long *bar, const float *gstate,
+                          uint32_t n_fields, uint32_t n, const float *&sp, uint32_t &sn, uint32_t &sv, uint32_t vs) {
+    const uint32_t v0 = blockIdx.x * kCta;
+    const bool tma_ok = (n % 4u == 0u);
+    if (!tma_ok) { sp = gstate; sn = n; sv = vs; return false; }
+    const uint32_t valid = min(kCta, n - v0);
+    if (threadIdx.x == 0) mbar_init(bar, 1u);
+    __syncthreads();
+    /* one row per thread, all rows in flight at once; thread 0 posts the expected byte count (a
+       complete_tx that lands first just drives the transaction count negative until then) */
+    if (threadIdx.x == 0) mbar_expect_tx(bar, n_fields * valid * 4u);
+    for (uint32_t f = threadIdx.x; f < n_fields; f += kCta) bulk_g2s(stage + f * kCta, gstate + (size_t)f * n + v0, valid * 4u, bar);
+    mbar_wait(bar, 0u);
+    sp = stage; sn = kCta; sv = min(threadIdx.x, valid - 1u);
+    return true;
+}
+/* store side: every thread has written its column of `stage`; one thread streams the rows out */
+OSC_D void state_stage_out(const float *stage, float *gstate, uint32_t n_fields, uint32_t n) {
+    const uint32_t v0 = blockIdx.x * kCta;
+    const uint32_t valid = min(kCta, n - v0);
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x < n_fields) {
+        for (uint32_t f = threadIdx.x; f < n_fields; f += kCta) bulk_s2g(gstate + (size_t)f * n + v0, stage + f * kCta, valid * 4u);
+        bulk_commit_wait();                                /* shared memory must outlive the reads */
+    }
+}
+
 /* column of voice-in-CTA `t` in the padded tile row: one pad word per instance so that the
    in-order instance sum (stride vpi) is bank-conflict free */
 OSC_D uint32_t tile_col(uint32_t t, uint32_t vpi) { return vpi > 1u ? t + t / vpi : t; }

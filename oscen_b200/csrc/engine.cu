@@ -245,7 +245,7 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
     }
 }
 
-constexpr size_t kSatDyn = (kTileF * kCta + 2 * 24 * kCta) * sizeof(float);
+constexpr size_t kSatDyn = (kTileF * kCta + 2 * 48 * kCta) * sizeof(float);
 constexpr size_t kEpDyn = (kTileF * kCta + kTileF * kTileW + kTileF * kCta * 2) * sizeof(float);
 
 /* ---- fused plan: one graph kernel + the mix-bus reduction */

@@ -78,35 +78,30 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        for (uint32_t g0 = 0; g0 < fe; g0 += 8) {
-            float xin[8];
-#pragma unroll
-            for (uint32_t k = 0; k < 8; ++k) {            /* 8 independent loads in flight */
-                const uint32_t f = f0 + g0 + k;
-                xin[k] = (active && !lcg_on && a.stream_in != nullptr && g0 + k < fe)
-                             ? __ldg(a.stream_in + (size_t)f * n + v) : 0.0f;
-            }
-#pragma unroll
-            for (uint32_t k = 0; k < 8; ++k) {
-                const uint32_t ff = g0 + k, f = f0 + ff;
-                if (ff < fe) {
-                    float y = 0.0f;
-                    if (active) {
-                        prm.ramps(a, ramp_mask, f);
-                        if (ec.due(f)) {
-                            const uint32_t j = ec.end_of_frame(f);
-                            for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
-                            ec.advance(j);
-                        }
-                        const float x = lcg_on ? lcg_next(lcg) : xin[k];
-                        const float ya = lp18_process(fa, x, prm.P[0], 0.0f, prm.P[2], sr);
-                        const float yb = lp18_process(fb, x, prm.P[1], 0.0f, prm.P[2], sr);
-                        y = ya - yb;
-                        if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
-                    }
-                    tile[ff * kTileW + col] = y;
+        /* stage this tile's input column in shared memory: 32 independent coalesced loads in flight,
+           then a compact (not unrolled) compute loop — the two LP18 bodies are ~400 instructions */
+        if (active && !lcg_on && a.stream_in != nullptr) {
+#pragma unroll 8
+            for (uint32_t ff = 0; ff < fe; ++ff) isum[ff * kCta + threadIdx.x] = __ldcs(a.stream_in + (size_t)(f0 + ff) * n + v);
+        }
+#pragma unroll 1
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const uint32_t f = f0 + ff;
+            float y = 0.0f;
+            if (active) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) {
+                    const uint32_t j = ec.end_of_frame(f);
+                    for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
+                    ec.advance(j);
                 }
+                const float x = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? isum[ff * kCta + threadIdx.x] : 0.0f);
+                const float ya = lp18_process(fa, x, prm.P[0], 0.0f, prm.P[2], sr);
+                const float yb = lp18_process(fb, x, prm.P[1], 0.0f, prm.P[2], sr);
+                y = ya - yb;
+                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
             }
+            tile[ff * kTileW + col] = y;
         }
         tile_flush_mono(a, tile, isum, f0, fe);
     }
@@ -122,10 +117,10 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
 template <int FACTOR>
 __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ float tile[kTileF * kTileW];
-    extern __shared__ float dyn[];                         /* isum [32*128] | h1 [24*128] | h2 [24*128] */
+    extern __shared__ float dyn[];                         /* isum [32][kCta] | h1 [48][kCta] | h2 [48][kCta] */
     float *isum = dyn;
     float *h1 = dyn + kTileF * kCta + threadIdx.x;
-    float *h2 = h1 + 24 * kCta;
+    float *h2 = h1 + 48 * kCta;
     const uint32_t n = a.n_voices;
     const uint32_t v = blockIdx.x * kCta + threadIdx.x;
     const bool active = v < n;
@@ -139,8 +134,9 @@ __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ Kerne
     uint32_t head1 = 23u, head2 = 23u;                     /* chronological order, newest last */
     if (FACTOR == 4) {
         for (uint32_t i = 0; i < 24; ++i) {
-            h1[i * kCta] = a.state[(size_t)(SAT_H1 + i) * n + vs];
-            h2[i * kCta] = a.state[(size_t)(SAT_H2 + i) * n + vs];
+            const float t1 = a.state[(size_t)(SAT_H1 + i) * n + vs], t2 = a.state[(size_t)(SAT_H2 + i) * n + vs];
+            h1[i * kCta] = t1; h1[(i + 24) * kCta] = t1;
+            h2[i * kCta] = t2; h2[(i + 24) * kCta] = t2;
         }
     }
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);

@@ -61,6 +61,17 @@ OSC_HD float fractf(float x) {
 OSC_D float pin(float x) { asm volatile("" : "+f"(x)); return x; }
 OSC_D uint32_t pin(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 
+/* tanf only runs when a filter coefficient has to be recomputed (parameter changes): on the device
+   it is a real call, so the ~700-instruction fdlibm body is not replicated into every unrolled
+   frame of every kernel (the fused TwinPeaks kernel had grown to 1 MB of SASS and spent most of
+   its time in instruction-cache misses: stall_no_instruction 6.0 per issue) */
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ float tanf_cold(float x) { return om_tanf(x); }
+#define OSC_TANF(x) tanf_cold(x)
+#else
+#define OSC_TANF(x) om_tanf(x)
+#endif
+
 /* ================================================================= AdsrEnvelope == */
 /* oscen-lib/src/envelope/adsr.rs */
 enum : uint32_t { ST_IDLE = 0, ST_ATTACK = 1, ST_DECAY = 2, ST_SUSTAIN = 3, ST_RELEASE = 4 };
@@ -201,7 +212,7 @@ OSC_HD void tpt_update_coefficients(TptState &s, float sample_rate, float cutoff
     const float nyquist = sample_rate * 0.5f - FLT_EPSILON;
     const float freq = clampf(cutoff, 20.0f, nyquist);
     const float period = 0.5f / sample_rate;
-    const float f = (2.0f * sample_rate) * om_tanf(2.0f * kPi * freq * period) * period;
+    const float f = (2.0f * sample_rate) * OSC_TANF(2.0f * kPi * freq * period) * period;
     const float inv_q = 1.0f / q;
     s.h = 1.0f / (1.0f + inv_q * f + f * f);
     s.g = f;
@@ -303,7 +314,7 @@ struct Lp18State {
 OSC_HD void lp18_update_cutoff(Lp18State &s, float cutoff, float fmod, float sample_rate) {
     const float modulated = cutoff + fmod;
     const float fc = clampf(modulated / sample_rate, 0.001f, 0.33f);
-    s.g = om_tanf(kPi * fc);
+    s.g = OSC_TANF(kPi * fc);
 }
 /* LP18Filter::new(cutoff,res) + set_sample_rate + prepare(): lp18_filter.rs:44-60,74-77 */
 OSC_HD void lp18_init(Lp18State &s, float cutoff, float resonance, float sample_rate) {
@@ -344,15 +355,18 @@ OSC_D float hardclip_process(float input) {
 
 /* ======================================================= Halfband2xDownStage::step == */
 /* oscen-lib/src/resample/sinc_fir.rs:113-138, taps resample/coeffs.rs:17-27.
-   `hist` is this thread's 24-slot ring (stride `stride` floats: one column of a
-   [24][threads] shared-memory tile, conflict-free); `head` as in the reference. */
+   `hist` is this thread's ring stored twice, 48 slots (stride `stride` floats: one column of a
+   [48][threads] shared-memory tile, conflict-free); `head` in [0,24) as in the reference. */
 constexpr float kHb0 = -3.8558514e-5f, kHb1 = 1.2218465e-3f, kHb2 = -7.2854808e-3f,
                 kHb3 = 2.6409210e-2f, kHb4 = -7.8128843e-2f, kHb5 = 3.0782697e-1f;
 constexpr float kHbCenter = 0.4999897f;
 OSC_D float hb_down_step(float *hist, int stride, uint32_t &head, float x0, float x1) {
-    head = (head + 1u) % 24u; hist[head * stride] = x0;
-    head = (head + 1u) % 24u; hist[head * stride] = x1;
-#define OSC_HB_AT(d) hist[((head + 24u - 1u - (uint32_t)(d)) % 24u) * stride]
+    /* the ring is stored twice (slot i and i + 24), so x[2m - d] = hist[head + 23 - d] needs no
+       modulo: 13 shared-memory loads with immediate offsets instead of 13 mod-24 index chains */
+    head = (head + 1u == 24u) ? 0u : head + 1u; hist[head * stride] = x0; hist[(head + 24u) * stride] = x0;
+    head = (head + 1u == 24u) ? 0u : head + 1u; hist[head * stride] = x1; hist[(head + 24u) * stride] = x1;
+    const float *h = hist + (head + 23u) * stride;          /* h[-d*stride] = x[2m - d], d = 0..22 */
+#define OSC_HB_AT(d) h[-(int)(d) * stride]
     float acc = OSC_HB_AT(11) * kHbCenter;
     acc = acc + (OSC_HB_AT(0) + OSC_HB_AT(22)) * kHb0;
     acc = acc + (OSC_HB_AT(2) + OSC_HB_AT(20)) * kHb1;

@@ -510,9 +510,14 @@ OM_HD float om_tanhf(float x) {
  * reconstruction are selected per lane; a warp whose lanes fall in different |x| bands no longer
  * serialises three code paths.  Domain handled here: 2^-55 <= |x| < 22 with the expm1f argument
  * in (-2, 0] (|x| < 1) or [2, 44) (|x| >= 1); everything else defers to om_tanhf. */
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ float om_tanhf_slow(float x) { return om_tanhf(x); }   /* cold ranges */
+#else
+static inline float om_tanhf_slow(float x) { return om_tanhf(x); }
+#endif
 OM_HD float om_tanhf_u(float x) {
     const uint32_t jx = om_asuint(x), ix = jx & 0x7fffffffu;
-    if (ix >= 0x41b00000u || ix < 0x24000000u) return om_tanhf(x);     /* |x| >= 22, tiny, 0, inf, nan */
+    if (ix >= 0x41b00000u || ix < 0x24000000u) return om_tanhf_slow(x);     /* |x| >= 22, tiny, 0, inf, nan */
     const float one = 1.0f, ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f,
                 invln2 = 1.4426950216e+00f, Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f,
                 Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
@@ -520,7 +525,7 @@ OM_HD float om_tanhf_u(float x) {
     const float ax = fabsf(x);
     float a = big ? 2.0f * ax : -2.0f * ax;                            /* expm1f argument */
     const uint32_t ha = om_asuint(a) & 0x7fffffffu;
-    if (ha >= 0x4195b844u) return om_tanhf(x);                         /* |a| >= 27 ln2: cold */
+    if (ha >= 0x4195b844u) return om_tanhf_slow(x);                    /* |a| >= 27 ln2: cold */
     /* k */
     int32_t k;
     if (ha > 0x3eb17218u) {

@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
 
     AdsrDerived d3, d2, d1, df;
     if (GENERAL) {
-        adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
-        adsr_derive(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
-        adsr_derive(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
-        adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
+        adsr_derive_r(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
+        adsr_derive_r(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
+        adsr_derive_r(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
+        adsr_derive_r(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
     } else {
         d3 = a.u.env[0]; d2 = a.u.env[1]; d1 = a.u.env[2]; df = a.u.env[3];
         adsr_pin(d3); adsr_pin(d2); adsr_pin(d1); adsr_pin(df);
@@ -160,10 +160,10 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                         }
                     }
                     if (GENERAL) {
-                        if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
-                        if (adsr_derived_stale(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R])) adsr_derive(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
-                        if (adsr_derived_stale(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R])) adsr_derive(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
-                        if (adsr_derived_stale(df, P[I_F_A], P[I_F_D], P[I_F_R])) adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
+                        if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive_r(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
+                        if (adsr_derived_stale(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R])) adsr_derive_r(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
+                        if (adsr_derived_stale(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R])) adsr_derive_r(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
+                        if (adsr_derived_stale(df, P[I_F_A], P[I_F_D], P[I_F_R])) adsr_derive_r(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
                     }
                     for (uint32_t k = ec.i; k < j; ++k) {
                         const Event e = ec.ev[k];
@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                     if (!GENERAL) OSC_FM_REFRESH();
                     ec.advance(j);
                 } else if (GENERAL && ramp_mask) {
-                    if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
-                    if (adsr_derived_stale(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R])) adsr_derive(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
-                    if (adsr_derived_stale(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R])) adsr_derive(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
-                    if (adsr_derived_stale(df, P[I_F_A], P[I_F_D], P[I_F_R])) adsr_derive(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
+                    if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive_r(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);
+                    if (adsr_derived_stale(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R])) adsr_derive_r(d2, P[I_OP2_A], P[I_OP2_D], P[I_OP2_R], sr);
+                    if (adsr_derived_stale(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R])) adsr_derive_r(d1, P[I_OP1_A], P[I_OP1_D], P[I_OP1_R], sr);
+                    if (adsr_derived_stale(df, P[I_F_A], P[I_F_D], P[I_F_R])) adsr_derive_r(df, P[I_F_A], P[I_F_D], P[I_F_R], sr);
                 }
 
                 /* ---- the walk (one frame) */

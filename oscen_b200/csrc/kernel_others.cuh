@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
     TptState tp; tpt_load(tp, a.state, SY_TPT, n, vs);
     AdsrState env; adsr_load(env, a.state, SY_ENV, n, vs);
     AdsrDerived d;
-    adsr_derive(d, prm.P[4], prm.P[5], prm.P[7], sr);
+    adsr_derive_r(d, prm.P[4], prm.P[5], prm.P[7], sr);
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
                     j = ec.end_of_frame(f);
                     for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
                 }
-                if (WITH_ADSR && adsr_derived_stale(d, prm.P[4], prm.P[5], prm.P[7])) adsr_derive(d, prm.P[4], prm.P[5], prm.P[7], sr);
+                if (WITH_ADSR && adsr_derived_stale(d, prm.P[4], prm.P[5], prm.P[7])) adsr_derive_r(d, prm.P[4], prm.P[5], prm.P[7], sr);
                 if (due) {
                     if (WITH_ADSR)
                         for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)

@@ -90,7 +90,14 @@ struct AdsrDerived {
     uint32_t a_n, d_n, r_n;
     float a_k, d_k;
 };
-OSC_HD void adsr_derive(AdsrDerived &d, float attack, float decay, float release, float sample_rate) {
+/* cold (block start / parameter change): a real call on the device so the two expf bodies are not
+   replicated at every call site of the frame loop */
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__
+#else
+static inline
+#endif
+void adsr_derive(AdsrDerived &d, float attack, float decay, float release, float sample_rate) {
     float sr = fmaxf(sample_rate, 1.0f);
     d.attack = attack; d.decay = decay; d.release = release;
     d.a_n = umax(f32_as_u32(fmaxf(attack, kAdsrMinTime) * sr), 1u);
@@ -98,6 +105,13 @@ OSC_HD void adsr_derive(AdsrDerived &d, float attack, float decay, float release
     d.r_n = umax(f32_as_u32(fmaxf(release, kAdsrMinTime) * sr), 1u);
     d.a_k = 1.0f - om_expf(-kAdsrCurveK / (float)d.a_n);
     d.d_k = 1.0f - om_expf(-kAdsrCurveK / (float)d.d_n);
+}
+/* device call sites use this form: only the temporary's address escapes into the out-of-line call,
+   so the caller's copy of the derived data stays in registers */
+OSC_D void adsr_derive_r(AdsrDerived &d, float attack, float decay, float release, float sample_rate) {
+    AdsrDerived t;
+    adsr_derive(t, attack, decay, release, sample_rate);
+    d = t;
 }
 OSC_D void adsr_pin(AdsrDerived &d) {
     d.a_n = pin(d.a_n); d.d_n = pin(d.d_n); d.r_n = pin(d.r_n); d.a_k = pin(d.a_k); d.d_k = pin(d.d_k);

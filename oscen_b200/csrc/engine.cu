@@ -445,7 +445,7 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         CK(e, cudaMalloc(&e->d_mix_partial, (size_t)e->n_cta * kMaxBlock * e->channels * sizeof(float)));
         CK(e, cudaMalloc(&e->d_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
         CK(e, cudaMemsetAsync(e->d_mix, 0, (size_t)kMaxBlock * e->channels * sizeof(float), e->stream));
-        CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
+        CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float) + 16));   /* + peer-timeout flag */
         CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1)); CK(e, cudaEventCreate(&e->evk));
         if (cfg->plan == OSCEN_B200_PLAN_NODES) {
             e->graph = pg; e->plan = pp;
@@ -465,12 +465,15 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         std::vector<uint32_t> init = initial_state(kind, cfg->sample_rate);
         uint32_t *d_init = nullptr;
         CK(e, cudaMalloc(&d_init, init.size() * sizeof(uint32_t)));
-        CK(e, cudaMemcpyAsync(d_init, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-        init_state_kernel<<<1184, 256, 0, e->stream>>>((uint32_t *)e->d_state, d_init, e->n_state, n);
-        e->stats.kernel_launches++;
-        CK(e, cudaGetLastError());
-        CK(e, cudaStreamSynchronize(e->stream));
+        cudaError_t st = cudaMemcpyAsync(d_init, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream);
+        if (st == cudaSuccess) {
+            init_state_kernel<<<1184, 256, 0, e->stream>>>((uint32_t *)e->d_state, d_init, e->n_state, n);
+            e->stats.kernel_launches++;
+            st = cudaGetLastError();
+        }
+        if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
         cudaFree(d_init);
+        CK(e, st);
         return 0;
     }();
     if (rc) { g_create_error = e->err; oscen_b200_destroy(e); return rc; }
@@ -783,9 +786,12 @@ int oscen_b200_read_mix(oscen_b200_engine *e, float *dst) {
     CK(e, cudaSetDevice(e->cfg.device));
     const size_t bytes = (size_t)e->last_frames * e->channels * sizeof(float);
     CK(e, cudaMemcpyAsync(e->h_mix, e->d_mix, bytes, cudaMemcpyDeviceToHost, e->stream));
+    uint32_t *h_flag = reinterpret_cast<uint32_t *>(e->h_mix + (size_t)kMaxBlock * e->channels);
+    if (e->p2p) CK(e, cudaMemcpyAsync(h_flag, e->d_p2p_error, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     memcpy(dst, e->h_mix, bytes);
     e->stats.d2h_bytes += bytes;
+    if (e->p2p && *h_flag != 0u) { e->err = "mix bus: a peer rank did not publish its block (bounded wait expired)"; return OSCEN_B200_E_NCCL; }
     return 0;
 }
 

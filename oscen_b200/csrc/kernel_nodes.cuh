@@ -87,18 +87,22 @@ __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__
     OSC_NODE_PROLOGUE(4)
     AdsrState s; adsr_load(s, a.state, a.state_base, n, v);
     AdsrDerived d; adsr_derive_r(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
+    AdsrHot h; adsr_refresh(s, h, prm.P[2], d);          /* re-run after every event / ramped frame */
     for (uint32_t f = 0; f < frames; ++f) {
-        prm.ramps(a, ramp_mask, f);
         const bool due = ec.due(f);
-        uint32_t j = ec.i;
-        if (due) j = prm.events(a, ec, f);
-        if (adsr_derived_stale(d, prm.P[0], prm.P[1], prm.P[3])) adsr_derive_r(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
-        if (due) {
-            for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
-                adsr_on_gate(s, ec.ev[q].scalar, prm.P[0], prm.P[3], d);
-            ec.advance(j);
+        if (ramp_mask | (uint32_t)due) {
+            prm.ramps(a, ramp_mask, f);
+            uint32_t j = ec.i;
+            if (due) j = prm.events(a, ec, f);
+            if (adsr_derived_stale(d, prm.P[0], prm.P[1], prm.P[3])) adsr_derive_r(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
+            if (due) {
+                for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
+                    adsr_on_gate(s, ec.ev[q].scalar, prm.P[0], prm.P[3], d);
+                ec.advance(j);
+            }
+            adsr_refresh(s, h, prm.P[2], d);
         }
-        __stcs(a.out0 + (size_t)f * n + v, adsr_process(s, prm.P[2], d));
+        __stcs(a.out0 + (size_t)f * n + v, adsr_process_t<false>(s, h, prm.P[2], d));
     }
     adsr_store(s, a.state, a.state_base, n, v);
 }

@@ -277,8 +277,8 @@ def run(out):
                 print(f"[rank {rank}] p2p mix exchange unavailable ({ex}); using NCCL", file=sys.stderr)
             ok = torch.tensor([1 if mix_mode == "p2p" else 0], device="cuda")
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0 and mix_mode == "p2p":
-                raise SystemExit("p2p import succeeded on some ranks only")
+            if int(ok.item()) == 0 and mix_mode == "p2p":      # some rank could not map a peer: all ranks use NCCL
+                eng.comm_p2p_close(); mix_mode = "nccl"
     if world == 1:
         mix_mode = "local"
     wl = Workload(n * world, rank * n, n)

@@ -206,6 +206,9 @@ int  oscen_b200_comm_init(oscen_b200_engine *e, int rank, int n_ranks, const voi
 #define OSCEN_B200_IPC_HANDLE_BYTES 64
 int  oscen_b200_comm_p2p_export(oscen_b200_engine *e, int n_ranks, void *handle64);
 int  oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, const void *handles /* n_ranks x 64 */);
+/* Leave the peer-memory exchange (closes the imported handles); the mix bus falls back to the NCCL
+ * all-reduce of comm_init.  Collective by convention: every rank calls it or none does. */
+int  oscen_b200_comm_p2p_close(oscen_b200_engine *e);
 
 #ifdef __cplusplus
 }

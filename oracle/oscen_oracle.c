@@ -507,6 +507,99 @@ int orc_sinc_up_latency(const orc_sinc_up *u) {
     return u->n_stages == 0 ? 0 : HB_GROUP_DELAY * ((1 << u->n_stages) - 1);
 }
 
+/* ================================================= IIR halfband cascade == */
+/* resample/coeffs.rs:47-54 */
+static const float IIR_A_BETAS[2] = { 0.1355741f, 0.6975849f };
+static const float IIR_B_BETAS[2] = { 0.4253804f, 0.9055601f };
+#define IIR_GROUP_DELAY 2
+#define DENORMAL_THRESHOLD 1e-15f              /* halfband_iir.rs:22 */
+/* frame.rs:87-93 */
+static inline float flush_denormal(float x, float thr) { return fabsf(x) < thr ? 0.0f : x; }
+/* halfband_iir.rs:45-57 (Allpass1::step): returns the pre-snap y */
+static inline float allpass1_step(orc_allpass1 *s, float x) {
+    float y = (x - s->y_prev) * s->a + s->x_prev;
+    s->x_prev = x; s->y_prev = y;
+    s->x_prev = flush_denormal(s->x_prev, DENORMAL_THRESHOLD);
+    s->y_prev = flush_denormal(s->y_prev, DENORMAL_THRESHOLD);
+    return y;
+}
+static void iir_hb_new(orc_iir_hb *h) {            /* halfband_iir.rs:84-96 */
+    memset(h, 0, sizeof *h);
+    h->branch_a[0].a = IIR_A_BETAS[0]; h->branch_a[1].a = IIR_A_BETAS[1];
+    h->branch_b[0].a = IIR_B_BETAS[0]; h->branch_b[1].a = IIR_B_BETAS[1];
+}
+/* halfband_iir.rs:104-116 */
+static void iir_hb_step_up(orc_iir_hb *h, float x, float out[2]) {
+    float a = x; for (int k = 0; k < 2; ++k) a = allpass1_step(&h->branch_a[k], a);
+    float b = x; for (int k = 0; k < 2; ++k) b = allpass1_step(&h->branch_b[k], b);
+    out[0] = a; out[1] = b;
+}
+/* halfband_iir.rs:124-136 */
+static float iir_hb_step_down(orc_iir_hb *h, float x0, float x1) {
+    float a = x0; for (int k = 0; k < 2; ++k) a = allpass1_step(&h->branch_a[k], a);
+    float b = h->prev_odd_in; for (int k = 0; k < 2; ++k) b = allpass1_step(&h->branch_b[k], b);
+    h->prev_odd_in = x1;
+    return (a + b) * 0.5f;
+}
+void orc_iir_up_new(orc_iir_up *u, int n) {
+    memset(u, 0, sizeof *u); u->n = n; u->n_stages = log2_pow2(n);
+    for (int s = 0; s < u->n_stages; ++s) iir_hb_new(&u->stages[s]);
+}
+/* halfband_iir.rs:173-190 */
+void orc_iir_up_process(orc_iir_up *u, float x, float *out) {
+    float buf[8] = {0}, next[8] = {0};
+    int len = 1; buf[0] = x;
+    for (int s = 0; s < u->n_stages; ++s) {
+        for (int i = 0; i < len; ++i) {
+            float pair[2]; iir_hb_step_up(&u->stages[s], buf[i], pair);
+            next[2 * i] = pair[0]; next[2 * i + 1] = pair[1];
+        }
+        len *= 2;
+        for (int i = 0; i < len; ++i) buf[i] = next[i];
+    }
+    for (int i = 0; i < u->n; ++i) out[i] = buf[i];
+}
+int orc_iir_up_latency(const orc_iir_up *u) {      /* halfband_iir.rs:192-203 */
+    return u->n_stages == 0 ? 0 : IIR_GROUP_DELAY * ((1 << u->n_stages) - 1);
+}
+void orc_iir_down_new(orc_iir_down *d, int n) { orc_iir_up_new(d, n); }
+/* halfband_iir.rs:235-251 */
+float orc_iir_down_process(orc_iir_down *d, const float *xs) {
+    float buf[8] = {0};
+    for (int i = 0; i < d->n; ++i) buf[i] = xs[i];
+    int len = d->n;
+    for (int s = 0; s < d->n_stages; ++s) {
+        float next[8] = {0};
+        int half = len / 2;
+        for (int i = 0; i < half; ++i) next[i] = iir_hb_step_down(&d->stages[s], buf[2 * i], buf[2 * i + 1]);
+        len = half;
+        for (int i = 0; i < len; ++i) buf[i] = next[i];
+    }
+    return buf[0];
+}
+int orc_iir_down_latency(const orc_iir_down *d) { return orc_iir_up_latency(d); }
+
+/* ======================================================== linear / latch == */
+void orc_linear_up_new(orc_linear_up *u, int n) { u->prev = 0.0f; u->n = n; }
+/* linear.rs:23-32 */
+void orc_linear_up_process(orc_linear_up *u, float x, float *out) {
+    float n_inv = 1.0f / (float)u->n;
+    float delta = x - u->prev;
+    for (int i = 0; i < u->n; ++i) out[i] = u->prev + delta * ((float)i * n_inv);
+    u->prev = x;
+}
+/* linear.rs:59-66 */
+float orc_linear_down_process(int n, const float *xs) {
+    float acc = 0.0f;
+    for (int i = 0; i < n; ++i) acc = acc + xs[i];
+    return acc * (1.0f / (float)n);
+}
+int orc_linear_up_latency(int n) { return n; }                 /* linear.rs:33-36 */
+int orc_linear_down_latency(int n) { return (n - 1) / 2; }     /* linear.rs:67-70 */
+/* latch.rs:17-23, 45-49 */
+void orc_latch_up_process(int n, float x, float *out) { for (int i = 0; i < n; ++i) out[i] = x; }
+float orc_latch_down_process(int n, const float *xs) { (void)n; return xs[0]; }
+
 /* ==================================================================== MIDI == */
 /* midi.rs:69-72 */
 float orc_midi_note_to_freq(uint8_t note) {
@@ -698,10 +791,14 @@ static void ep_tremolo_process(ep_tremolo *t) {
 }
 
 /* ================================================================== graphs == */
-enum { K_FM = 0, K_TWIN = 1, K_SAT1 = 2, K_SAT4 = 3, K_EPIANO = 4, K_SYNTH = 5, K_SYNTH_ADSR = 6, K_COUNT };
+enum { K_FM = 0, K_TWIN = 1, K_SAT1 = 2, K_SAT4 = 3, K_EPIANO = 4, K_SYNTH = 5, K_SYNTH_ADSR = 6,
+       K_CLIP_REF = 7, K_CLIP_OS = 8 /* .. 19: 8 + policy*3 + (log2 factor - 1) */, K_COUNT = 20 };
+static int kind_is_clip(uint32_t k) { return k >= K_CLIP_REF && k < K_COUNT; }
+static int clip_policy(uint32_t k) { return (int)(k - K_CLIP_OS) / 3; }
+static int clip_factor(uint32_t k) { return k == K_CLIP_REF ? 1 : 2 << ((k - K_CLIP_OS) % 3); }
 #define MAX_IN 28
 #define MAXQ 32            /* MAX_STATIC_EVENTS_PER_ENDPOINT, graph/types.rs:18 */
-static const int N_INPUTS[K_COUNT] = { 28, 3, 2, 2, 9, 4, 8 };
+static const int N_INPUTS[K_COUNT] = { 28, 3, 2, 2, 9, 4, 8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 /* default values of the value inputs (fm_voice.rs:10-48; nih-twin-peaks lib.rs:21-23;
    oversampled-saturator main.rs:71 saw(2000,.6); electric-piano main.rs:39-46 + 440;
    README.md:28-31) */
@@ -845,6 +942,40 @@ static void sat_process(sat_voice *v, const float *in) {
     v->audio_out = orc_sinc_down_process(&v->down, buf);
 }
 
+typedef struct {          /* ClipRef / ClipOversampled{,Iir}: oscen-lib/tests/multirate_graph.rs:282-325;
+                             HardClip here is clamp(+-0.7) with no drive (multirate_graph.rs:35-40) */
+    int policy, factor;
+    orc_sinc_up sup; orc_sinc_down sdown; orc_iir_up iup; orc_iir_down idown; orc_linear_up lup;
+    float clip_in, clip_out, out;
+} clip_voice;
+static void clip_new(clip_voice *v, int policy, int factor) {
+    memset(v, 0, sizeof *v); v->policy = policy; v->factor = factor;
+    orc_sinc_up_new(&v->sup, factor); orc_sinc_down_new(&v->sdown, factor);
+    orc_iir_up_new(&v->iup, factor); orc_iir_down_new(&v->idown, factor);
+    orc_linear_up_new(&v->lup, factor);
+}
+/* multirate body, codegen/emit_frame.rs:114-176: up-edge warm-up (emit_frame.rs:254-307), N inner
+   ticks {write, process, capture} (:388-461), down finalize (:474-514) */
+static void clip_process(clip_voice *v, float input) {
+    if (v->factor == 1) { v->clip_in = input; v->clip_out = clampf(v->clip_in, -0.7f, 0.7f); v->out = v->clip_out; return; }
+    float up[8], down[8];
+    switch (v->policy) {
+    case ORC_POLICY_SINC: orc_sinc_up_process(&v->sup, input, up); break;
+    case ORC_POLICY_SINC_IIR: orc_iir_up_process(&v->iup, input, up); break;
+    case ORC_POLICY_LINEAR: orc_linear_up_process(&v->lup, input, up); break;
+    default: orc_latch_up_process(v->factor, input, up); break;
+    }
+    for (int i = 0; i < v->factor; ++i) {
+        v->clip_in = up[i]; v->clip_out = clampf(v->clip_in, -0.7f, 0.7f); down[i] = v->clip_out;
+    }
+    switch (v->policy) {
+    case ORC_POLICY_SINC: v->out = orc_sinc_down_process(&v->sdown, down); break;
+    case ORC_POLICY_SINC_IIR: v->out = orc_iir_down_process(&v->idown, down); break;
+    case ORC_POLICY_LINEAR: v->out = orc_linear_down_process(v->factor, down); break;
+    default: v->out = orc_latch_down_process(v->factor, down); break;
+    }
+}
+
 typedef struct {          /* ElectricPianoVoiceNode: electric_piano_voice.rs:362-402 */
     ep_amp amp; ep_bank bank; float output;
 } ep_voice;
@@ -931,7 +1062,8 @@ static size_t kind_voice_size(uint32_t k) {
     case K_TWIN: return sizeof(twin_voice);
     case K_SAT1: case K_SAT4: return sizeof(sat_voice);
     case K_EPIANO: return sizeof(ep_voice);
-    default: return sizeof(synth_voice);
+    case K_SYNTH: case K_SYNTH_ADSR: return sizeof(synth_voice);
+    default: return sizeof(clip_voice);
     }
 }
 #define VOICE(b, v) ((void *)((b)->voices + (size_t)(v) * (b)->voice_size))
@@ -967,7 +1099,8 @@ orc_bank *orc_bank_create(uint32_t kind, uint32_t n_voices, uint32_t vpi, float 
         case K_SAT4: sat_new(p, 4); sat_init(p, sr); break;
         case K_EPIANO: ep_voice_new(p); ep_voice_init(p, sr); break;
         case K_SYNTH: synth_new(p, 0); synth_init(p, sr); break;
-        default: synth_new(p, 1); synth_init(p, sr); break;
+        case K_SYNTH_ADSR: synth_new(p, 1); synth_init(p, sr); break;
+        default: clip_new(p, kind == K_CLIP_REF ? 0 : clip_policy(kind), clip_factor(kind)); break;
         }
     }
     for (uint32_t i = 0; i < b->n_inst; ++i) {
@@ -987,7 +1120,21 @@ void orc_bank_destroy(orc_bank *b) {
 uint32_t orc_bank_channels(const orc_bank *b) { return b->channels; }
 /* latency_samples(): Down edges report at the source rate / factor (codegen/emit_struct.rs:533-566);
    SincDownFir<4> = 33 high-rate samples / factor 4 (integer division, emit_struct.rs:549-553) */
-uint32_t orc_bank_latency(const orc_bank *b) { return b->kind == K_SAT4 ? 33 / 4 : 0; }
+uint32_t orc_bank_latency(const orc_bank *b) {
+    if (b->kind == K_SAT4) return 33 / 4;
+    if (kind_is_clip(b->kind) && b->kind != K_CLIP_REF) {
+        const clip_voice *v = (const clip_voice *)b->voices;
+        int lat;
+        switch (v->policy) {
+        case ORC_POLICY_SINC: lat = orc_sinc_down_latency(&v->sdown); break;
+        case ORC_POLICY_SINC_IIR: lat = orc_iir_down_latency(&v->idown); break;
+        case ORC_POLICY_LINEAR: lat = orc_linear_down_latency(v->factor); break;
+        default: lat = 0; break;
+        }
+        return (uint32_t)(lat / v->factor);
+    }
+    return 0;
+}
 void orc_bank_set_threads(orc_bank *b, int n) { b->n_threads = n < 1 ? 1 : n; }
 
 int orc_bank_set_value(orc_bank *b, uint32_t id, uint32_t first, uint32_t count, const float *v, int bc) {
@@ -1041,7 +1188,7 @@ int orc_bank_push_midi(orc_bank *b, uint32_t inst, uint32_t frame, const uint8_t
     return 0;
 }
 int orc_bank_stream_in(orc_bank *b, uint32_t id, const float *src, uint32_t frames) {
-    if (b->kind != K_TWIN || id != 0 || frames > 512) return -1;
+    if ((b->kind != K_TWIN && !kind_is_clip(b->kind)) || id != 0 || frames > 512) return -1;
     free(b->stream_in);
     b->stream_in = malloc((size_t)frames * b->n_voices * sizeof(float));
     memcpy(b->stream_in, src, (size_t)frames * b->n_voices * sizeof(float));
@@ -1137,7 +1284,9 @@ static void render_instance(orc_bank *b, uint32_t inst, uint32_t frames, const f
                          out = ((twin_voice *)p)->audio_out; break;
             case K_SAT1: case K_SAT4: sat_process(p, in); out = ((sat_voice *)p)->audio_out; break;
             case K_EPIANO: ep_voice_process(p, in, gates[v], ngates[v]); out = ((ep_voice *)p)->output; break;
-            default: synth_process(p, in, gates[v], ngates[v]); out = ((synth_voice *)p)->audio_out; break;
+            case K_SYNTH: case K_SYNTH_ADSR: synth_process(p, in, gates[v], ngates[v]); out = ((synth_voice *)p)->audio_out; break;
+            default: clip_process(p, b->stream_in ? b->stream_in[(size_t)f * b->n_voices + gv] : 0.0f);
+                     out = ((clip_voice *)p)->out; break;
             }
             b->voice_out[(size_t)f * b->n_voices + gv] = out;
             /* array -> scalar: .iter().map().sum(), sequential in index order (emit_node.rs:463-466) */
@@ -1167,7 +1316,7 @@ static void *render_thread(void *arg) {
 }
 int orc_bank_process_block(orc_bank *b, uint32_t frames) {
     if (frames > 512) return -1;
-    if (b->kind == K_TWIN && b->stream_in && b->stream_frames < frames) return -1;
+    if ((b->kind == K_TWIN || kind_is_clip(b->kind)) && b->stream_in && b->stream_frames < frames) return -1;
     /* tick_ramps once per frame (codegen/mod.rs:878-914); table of .current per frame */
     float *ramp_tab = calloc((size_t)MAX_IN * 512, sizeof(float));
     for (uint32_t f = 0; f < frames; ++f)

@@ -133,6 +133,28 @@ void  orc_sinc_up_new(orc_sinc_up *u, int n);
 void  orc_sinc_up_process(orc_sinc_up *u, float x, float *out);
 int   orc_sinc_up_latency(const orc_sinc_up *u);
 
+/* ------------------------------- IIR halfband / linear / latch resamplers -- */
+/* oscen-lib/src/resample/halfband_iir.rs:24-262, coeffs.rs:36-54 */
+typedef struct { float a, x_prev, y_prev; } orc_allpass1;                       /* Allpass1 */
+typedef struct { orc_allpass1 branch_a[2], branch_b[2]; float prev_odd_in; } orc_iir_hb;   /* IirHalfband2x */
+typedef struct { orc_iir_hb stages[3]; int n_stages; int n; } orc_iir_up, orc_iir_down;
+void  orc_iir_up_new(orc_iir_up *u, int n);            /* n in {1,2,4,8} */
+void  orc_iir_up_process(orc_iir_up *u, float x, float *out);
+int   orc_iir_up_latency(const orc_iir_up *u);
+void  orc_iir_down_new(orc_iir_down *d, int n);
+float orc_iir_down_process(orc_iir_down *d, const float *xs);
+int   orc_iir_down_latency(const orc_iir_down *d);
+/* oscen-lib/src/resample/linear.rs:11-74 */
+typedef struct { float prev; int n; } orc_linear_up;
+void  orc_linear_up_new(orc_linear_up *u, int n);
+void  orc_linear_up_process(orc_linear_up *u, float x, float *out);
+float orc_linear_down_process(int n, const float *xs);
+int   orc_linear_up_latency(int n);
+int   orc_linear_down_latency(int n);
+/* oscen-lib/src/resample/latch.rs:6-54 */
+void  orc_latch_up_process(int n, float x, float *out);
+float orc_latch_down_process(int n, const float *xs);
+
 /* ------------------------------------------------------- MIDI + voices --- */
 /* oscen-lib/src/midi.rs:69-72, 147-224; voice_allocator.rs:29-150 */
 float orc_midi_note_to_freq(uint8_t note);
@@ -186,6 +208,11 @@ int    orc_bank_read_mix(const orc_bank *b, float *dst);
 uint32_t orc_bank_channels(const orc_bank *b);
 uint32_t orc_bank_latency(const orc_bank *b);
 void   orc_bank_set_threads(orc_bank *b, int n_threads);
+/* graph kinds 7..19: the cross-rate clipper graphs of oscen-lib/tests/multirate_graph.rs:282-325
+   (ClipRef; ClipOversampled / ClipOversampledIir and their [linear] / [latch] policy variants) */
+#define ORC_GRAPH_CLIP_REF 7u
+#define ORC_GRAPH_CLIP_OS(policy, log2_factor) (8u + (policy) * 3u + ((log2_factor) - 1u))
+enum { ORC_POLICY_SINC = 0, ORC_POLICY_SINC_IIR = 1, ORC_POLICY_LINEAR = 2, ORC_POLICY_LATCH = 3 };
 #define ORC_EV_GATE 0xFFFFFFFFu   /* orc_event.input_id of a gate event; else a value input id */
 
 #ifdef __cplusplus

@@ -25,7 +25,7 @@ SYMBOLS = [
     "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
-    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_plan_describe",
+    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
 ]
 
 
@@ -96,6 +96,7 @@ def load():
     L.oscen_b200_comm_p2p_export.argtypes = [vp, C.c_int, vp]
     L.oscen_b200_plan_describe.argtypes = [u32, C.c_char_p, C.c_size_t]
     L.oscen_b200_comm_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.oscen_b200_comm_p2p_close.argtypes = [vp]
     _lib = L
     return L
 
@@ -239,6 +240,9 @@ class Engine:
         assert len(handles) == 64 * n_ranks
         buf = C.create_string_buffer(handles, len(handles))
         self._chk(self.L.oscen_b200_comm_p2p_import(self.h, rank, n_ranks, buf), "comm_p2p_import")
+
+    def comm_p2p_close(self):
+        self._chk(self.L.oscen_b200_comm_p2p_close(self.h), "comm_p2p_close")
 
 
 def plan_describe(graph_kind):

@@ -891,6 +891,20 @@ int oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, cons
         e->peers.peer[r] = (float *)p;
     }
     e->rank = rank; e->n_ranks = n_ranks; e->p2p = true; e->xchg_seq = 0;
+    for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    return 0;
+}
+
+int oscen_b200_comm_p2p_close(oscen_b200_engine *e) {
+    if (!e) return OSCEN_B200_E_ARG;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < (int)kMaxRanks; ++r) {
+        if (e->p2p && r != e->rank && e->peers.peer[r]) cudaIpcCloseMemHandle(e->peers.peer[r]);
+        e->peers.peer[r] = nullptr;
+    }
+    e->p2p = false;
+    for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }
 

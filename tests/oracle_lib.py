@@ -15,6 +15,14 @@ SO = os.path.join(ORACLE_DIR, "liboscen_oracle.so")
 
 EV_GATE = 0xFFFFFFFF
 (K_FM, K_TWIN, K_SAT1, K_SAT4, K_EPIANO, K_SYNTH, K_SYNTH_ADSR) = range(7)
+K_CLIP_REF = 7
+(POLICY_SINC, POLICY_SINC_IIR, POLICY_LINEAR, POLICY_LATCH) = range(4)
+
+
+def k_clip_os(policy, factor):
+    """graph kind of the ClipOversampled family (oscen-lib/tests/multirate_graph.rs:295-325)"""
+    return 8 + policy * 3 + ({2: 1, 4: 2, 8: 3}[factor] - 1)
+
 
 
 def build(force=False):
@@ -76,6 +84,22 @@ class SincUp(C.Structure):
     _fields_ = [("stages", HbUp * 3), ("n_stages", C.c_int), ("n", C.c_int)]
 
 
+class Allpass1(C.Structure):
+    _fields_ = [("a", C.c_float), ("x_prev", C.c_float), ("y_prev", C.c_float)]
+
+
+class IirHb(C.Structure):
+    _fields_ = [("branch_a", Allpass1 * 2), ("branch_b", Allpass1 * 2), ("prev_odd_in", C.c_float)]
+
+
+class IirResampler(C.Structure):
+    _fields_ = [("stages", IirHb * 3), ("n_stages", C.c_int), ("n", C.c_int)]
+
+
+class LinearUp(C.Structure):
+    _fields_ = [("prev", C.c_float), ("n", C.c_int)]
+
+
 class VoiceAlloc(C.Structure):
     _fields_ = [("num_voices", C.c_int), ("active", C.c_uint8 * 24), ("released", C.c_uint8 * 24),
                 ("note", C.c_int * 24), ("age", C.c_uint32 * 24), ("current_age", C.c_uint32)]
@@ -113,6 +137,15 @@ def lib():
         L.orc_ramp_set_immediate.argtypes = [C.c_void_p, C.c_float]
         L.orc_ramp_set_with_ramp.argtypes = [C.c_void_p, C.c_float, C.c_uint32]
         L.orc_sinc_up_process.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_iir_up_process.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_iir_down_process.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_iir_down_process.restype = C.c_float
+        L.orc_linear_up_process.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_linear_down_process.argtypes = [C.c_int, C.c_void_p]
+        L.orc_linear_down_process.restype = C.c_float
+        L.orc_latch_up_process.argtypes = [C.c_int, C.c_float, C.c_void_p]
+        L.orc_latch_down_process.argtypes = [C.c_int, C.c_void_p]
+        L.orc_latch_down_process.restype = C.c_float
         L.orc_bank_create.restype = C.c_void_p
         L.orc_bank_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
         L.orc_bank_destroy.argtypes = [C.c_void_p]

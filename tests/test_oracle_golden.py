@@ -309,6 +309,160 @@ def test_sinc_fir_latency():
     assert L.orc_sinc_down_latency(C.byref(_down(1))) == 0
 
 
+# ---- (9b) latch / linear / IIR-halfband resamplers, oscen-lib/tests/resample_kernels.rs:3-152,246-350,413-467
+def test_latch_resamplers_exact_values():
+    out2, out4 = (C.c_float * 2)(), (C.c_float * 4)()
+    L.orc_latch_up_process(2, 1.0, out2); assert list(out2) == [1.0, 1.0]
+    L.orc_latch_up_process(2, -0.25, out2); assert list(out2) == [-0.25, -0.25]
+    L.orc_latch_up_process(4, 0.5, out4); assert list(out4) == [0.5] * 4
+    assert L.orc_latch_down_process(2, (C.c_float * 2)(1.0, 2.0)) == 1.0
+    assert L.orc_latch_down_process(2, (C.c_float * 2)(3.0, 4.0)) == 3.0
+    assert L.orc_latch_down_process(4, (C.c_float * 4)(10.0, 11.0, 12.0, 13.0)) == 10.0
+
+
+def _lin(n):
+    u = O.LinearUp()
+    L.orc_linear_up_new(C.byref(u), n)
+    return u
+
+
+def test_linear_resamplers_reference_values():
+    u, out = _lin(2), (C.c_float * 2)()
+    L.orc_linear_up_process(C.byref(u), 0.0, out)
+    L.orc_linear_up_process(C.byref(u), 1.0, out)
+    assert abs(out[0] - 0.0) < 1e-6 and abs(out[1] - 0.5) < 1e-6
+    L.orc_linear_up_process(C.byref(u), 2.0, out)
+    assert abs(out[0] - 1.0) < 1e-6 and abs(out[1] - 1.5) < 1e-6
+    u4, out4 = _lin(4), (C.c_float * 4)()
+    L.orc_linear_up_process(C.byref(u4), 0.7, out4)
+    L.orc_linear_up_process(C.byref(u4), 0.7, out4)
+    assert all(abs(v - 0.7) < 1e-6 for v in out4)
+    assert [L.orc_linear_up_latency(n) for n in (2, 4, 8)] == [2, 4, 8]
+    assert [L.orc_linear_down_latency(n) for n in (2, 4, 8)] == [0, 1, 3]
+    # impulse peak of LinearUp<4> lands at dest index == latency (resample_kernels.rs:108-126)
+    u4, resp = _lin(4), []
+    for x in (1.0, 0.0):
+        L.orc_linear_up_process(C.byref(u4), x, out4); resp += list(out4)
+    assert int(np.argmax(resp)) == 4
+    assert abs(L.orc_linear_down_process(2, (C.c_float * 2)(1.0, 3.0)) - 2.0) < 1e-6
+    assert abs(L.orc_linear_down_process(4, (C.c_float * 4)(1.0, 2.0, 3.0, 4.0)) - 2.5) < 1e-6
+
+
+def _iir(n):
+    u, d = O.IirResampler(), O.IirResampler()
+    L.orc_iir_up_new(C.byref(u), n); L.orc_iir_down_new(C.byref(d), n)
+    return u, d
+
+
+def test_iir_halfband_dc_gain_stopband_latency():
+    u, d = _iir(2)
+    out = (C.c_float * 2)()
+    for _ in range(1000):
+        L.orc_iir_up_process(C.byref(u), 0.5, out)
+    assert abs(out[0] - 0.5) < 5e-3 and abs(out[1] - 0.5) < 5e-3
+    y = 0.0
+    for _ in range(1000):
+        y = L.orc_iir_down_process(C.byref(d), (C.c_float * 2)(0.5, 0.5))
+    assert abs(y - 0.5) < 5e-3
+    _, d = _iir(2)
+    peak, two_pi = 0.0, f32(2.0) * f32(math.pi)
+    for m in range(4096):
+        x0 = math.sin(float(f32(f32(two_pi * f32(0.4)) * f32(2 * m))))
+        x1 = math.sin(float(f32(f32(two_pi * f32(0.4)) * f32(2 * m + 1))))
+        y = L.orc_iir_down_process(C.byref(d), (C.c_float * 2)(x0, x1))
+        if m > 256:
+            peak = max(peak, abs(y))
+    assert -20.0 * math.log10(max(peak, 1e-12)) > 40.0
+    assert L.orc_iir_up_latency(C.byref(_iir(2)[0])) < L.orc_sinc_up_latency(C.byref(_up(2)))
+    assert [L.orc_iir_down_latency(C.byref(_iir(n)[1])) for n in (1, 2, 4, 8)] == [0, 2, 6, 14]
+
+
+def test_iir_halfband_state_snaps_to_exact_zero_after_silence():
+    u, d = _iir(8)
+    out = (C.c_float * 8)()
+    for _ in range(100):
+        L.orc_iir_up_process(C.byref(u), 0.1, out)
+    for _ in range(1000):
+        L.orc_iir_up_process(C.byref(u), 0.0, out)
+    assert list(out) == [0.0] * 8
+    y = 0.0
+    for _ in range(100):
+        y = L.orc_iir_down_process(C.byref(d), (C.c_float * 8)(*([0.1] * 8)))
+    for _ in range(1000):
+        y = L.orc_iir_down_process(C.byref(d), (C.c_float * 8)())
+    assert y == 0.0
+
+
+def _iir_roundtrip_err(n, f, warmup):
+    u, d = _iir(n)
+    buf = (C.c_float * n)()
+    lag = (L.orc_iir_up_latency(C.byref(u)) + L.orc_iir_down_latency(C.byref(d))) // n
+    max_err, two_pi = 0.0, f32(2.0) * f32(math.pi)
+    for i in range(1024):
+        x = f32(math.sin(float(f32(f32(two_pi * f32(f)) * f32(i)))))
+        L.orc_iir_up_process(C.byref(u), float(x), buf)
+        y = L.orc_iir_down_process(C.byref(d), buf)
+        if i > warmup and i >= lag:
+            want = math.sin(float(f32(f32(two_pi * f32(f)) * f32(i - lag))))
+            max_err = max(max_err, abs(y - want))
+    return max_err
+
+
+def test_iir_halfband_passband_flat():
+    e4, e8 = _iir_roundtrip_err(4, 0.03, 256), _iir_roundtrip_err(8, 0.03, 256)
+    assert e4 < 0.1 and e8 < 0.15
+    # the reference records its observed values in comments (resample_kernels.rs:416,446)
+    assert abs(e4 - 0.030) < 0.005, e4
+    assert abs(e8 - 0.059) < 0.005, e8
+
+
+# ---- (9c) ClipRef / ClipOversampled / ClipOversampledIir graphs, oscen-lib/tests/multirate_graph.rs:282-436
+def _bin_magnitude(x, freq):
+    i = np.arange(len(x), dtype=np.float64)
+    ph = 2.0 * math.pi * freq * i
+    return math.hypot(float((x * np.cos(ph)).sum()), float((x * np.sin(ph)).sum())) / len(x)
+
+
+def _clip_graph_output(kind, total=4096, block=256):
+    b = O.OracleBank(kind, 1, 1)
+    n = np.arange(total, dtype=np.float32)
+    x = (np.float32(0.9) * np.sin(np.float32(2.0 * math.pi) * np.float32(0.2) * n)).astype(np.float32)
+    out = []
+    for s in range(0, total, block):
+        b.stream_in(0, x[s:s + block, None])
+        b.process_block(block)
+        out.append(b.read_voice_out()[:, 0].copy())
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("policy", [O.POLICY_SINC, O.POLICY_SINC_IIR])
+def test_hardclip_4x_has_less_aliasing_than_1x(policy):
+    a = _clip_graph_output(O.K_CLIP_REF)[512:]
+    b = _clip_graph_output(O.k_clip_os(policy, 4))[512:]
+    one_x = _bin_magnitude(a, 0.4) / max(_bin_magnitude(a, 0.2), 1e-9)
+    four_x = _bin_magnitude(b, 0.4) / max(_bin_magnitude(b, 0.2), 1e-9)
+    assert four_x < one_x * 0.5, (four_x, one_x)
+
+
+def test_clip_graph_latencies():
+    # latency_samples(): sum over Down edges of latency / factor (codegen/emit_struct.rs:533-566)
+    want = {(O.POLICY_SINC, 2): 11 // 2, (O.POLICY_SINC, 4): 33 // 4, (O.POLICY_SINC, 8): 77 // 8,
+            (O.POLICY_SINC_IIR, 2): 1, (O.POLICY_SINC_IIR, 4): 6 // 4, (O.POLICY_SINC_IIR, 8): 14 // 8,
+            (O.POLICY_LINEAR, 2): 0, (O.POLICY_LINEAR, 4): 0, (O.POLICY_LINEAR, 8): 0,
+            (O.POLICY_LATCH, 2): 0, (O.POLICY_LATCH, 4): 0, (O.POLICY_LATCH, 8): 0}
+    for (p, f), w in want.items():
+        b = O.OracleBank(O.k_clip_os(p, f), 1, 1)
+        assert L.orc_bank_latency(b.h) == w, (p, f)
+    assert L.orc_bank_latency(O.OracleBank(O.K_CLIP_REF, 1, 1).h) == 0
+
+
+def test_clip_latch_equals_reference_clipper():
+    # [latch] up then [latch] down around a memoryless node is the 1x graph exactly
+    a = _clip_graph_output(O.K_CLIP_REF, 512)
+    for f in (2, 4, 8):
+        assert np.array_equal(a, _clip_graph_output(O.k_clip_os(O.POLICY_LATCH, f), 512))
+
+
 # ---- (8) block == per-sample, oscen-lib/tests/block_processing_test.rs:23-286
 def _script(bank, frames_list, per_sample):
     """gate on at frame 5 of block 0, value event + ramp in block 1, gate off in block 2"""

@@ -51,8 +51,25 @@ enum {
     OSCEN_B200_GRAPH_EPIANO = 4,      /* ElectricPianoVoiceNode x N, instance = sum -> Tremolo -> Frame<2>  examples/electric-piano/src/main.rs:33-97 */
     OSCEN_B200_GRAPH_SYNTH = 5,       /* README `Synth`: sine LFO -> saw PolyBLEP -> TptFilter   README.md:24-53 */
     OSCEN_B200_GRAPH_SYNTH_ADSR = 6,  /* README `Synth` + AdsrEnvelope -> Gain(vca) (wiring of benches/static_vs_runtime.rs:57-59) */
-    OSCEN_B200_GRAPH_COUNT = 7
+    /* cross-rate graphs: per-voice stream input -> Up edge -> HardClip `* N` -> Down edge
+       (oscen-lib/tests/multirate_graph.rs:282-325).  HardClip here is
+       clamp(+-0.7) with no drive (multirate_graph.rs:35-40). */
+    OSCEN_B200_GRAPH_CLIP_REF = 7,    /* ClipRef: input -> clip -> out at 1x           multirate_graph.rs:282-293 */
+    OSCEN_B200_GRAPH_CLIP_OS_BASE = 8,/* 8..19 = OSCEN_B200_GRAPH_CLIP_OS(policy, log2_factor), below */
+    OSCEN_B200_GRAPH_COUNT = 20
 };
+/* connection policy of both cross-rate edges (`[sinc]`, `[sinc_iir]`, `[linear]`, `[latch]`,
+   oscen-graph-compiler/src/ast.rs ConnectionPolicy; resampler kernels oscen-lib/src/resample/) */
+enum {
+    OSCEN_B200_POLICY_SINC = 0,       /* SincUpFir<N> / SincDownFir<N>          resample/sinc_fir.rs:146-266 */
+    OSCEN_B200_POLICY_SINC_IIR = 1,   /* IirHalfbandUp<N> / IirHalfbandDown<N>  resample/halfband_iir.rs:146-262 */
+    OSCEN_B200_POLICY_LINEAR = 2,     /* LinearUp<N> / LinearDown<N>            resample/linear.rs:11-74 */
+    OSCEN_B200_POLICY_LATCH = 3       /* LatchUp<N> / LatchDown<N>              resample/latch.rs:6-54 */
+};
+/* ClipOversampled (`clip = HardClip::new() * N`, N = 2^log2_factor in {2,4,8}) with `policy` on both edges;
+   OSCEN_B200_GRAPH_CLIP_OS(OSCEN_B200_POLICY_SINC, 2) is the reference's ClipOversampled,
+   (OSCEN_B200_POLICY_SINC_IIR, 2) its ClipOversampledIir. */
+#define OSCEN_B200_GRAPH_CLIP_OS(policy, log2_factor) (8u + (uint32_t)(policy) * 3u + ((uint32_t)(log2_factor) - 1u))
 
 /* value-input ids (declaration order of the reference graph's `input x: value` lines) */
 enum { /* FM_VOICE, fm_voice.rs:10-48 */
@@ -147,7 +164,8 @@ int  oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, si
 int  oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame_offset,
                           const uint8_t *bytes, uint32_t len);
 
-/* stream input block [frames][n_voices] f32 for the NEXT process_block (TWIN_PEAKS audio_in).
+/* stream input block [frames][n_voices] f32 for the NEXT process_block (TWIN_PEAKS audio_in,
+   CLIP_* input).
    is_device != 0: `src` is a device pointer on the engine's device (no copy is made; it must
    stay valid until process_block returns). */
 int  oscen_b200_stream_in(oscen_b200_engine *e, uint32_t input_id, const float *src, uint32_t frames,

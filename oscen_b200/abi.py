@@ -14,6 +14,16 @@ MAX_BLOCK = 512
 EVENT_GATE = 0xFFFFFFFF
 (GRAPH_FM_VOICE, GRAPH_TWIN_PEAKS, GRAPH_SAT_1X, GRAPH_SAT_4X, GRAPH_EPIANO, GRAPH_SYNTH,
  GRAPH_SYNTH_ADSR) = range(7)
+GRAPH_CLIP_REF = 7
+POLICY_SINC, POLICY_SINC_IIR, POLICY_LINEAR, POLICY_LATCH = range(4)
+GRAPH_COUNT = 20
+
+
+def graph_clip_os(policy, factor):
+    """OSCEN_B200_GRAPH_CLIP_OS(policy, log2 factor): ClipOversampled with `policy` on both cross-rate edges"""
+    return 8 + policy * 3 + ({2: 1, 4: 2, 8: 3}[factor] - 1)
+
+
 PLAN_FUSED, PLAN_NODES = 0, 1
 KEEP_VOICE_OUT, KEEP_INSTANCE_OUT = 1, 2
 

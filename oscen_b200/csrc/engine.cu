@@ -22,6 +22,7 @@
 #include "kernel_fm.cuh"
 #include "kernel_nodes.cuh"
 #include "kernel_others.cuh"
+#include "kernel_resample.cuh"
 #include "graphs.hpp"
 #include "midi_front.hpp"
 
@@ -34,11 +35,19 @@ namespace {
 
 thread_local std::string g_create_error;
 
-const uint32_t kNInputs[OSCEN_B200_GRAPH_COUNT] = {28, 3, 2, 2, 9, 4, 8};
-const uint32_t kNState[OSCEN_B200_GRAPH_COUNT] = {FM_NSTATE, TW_NSTATE, SAT_NSTATE, SAT_NSTATE, EP_NSTATE, SY_NSTATE, SY_NSTATE};
+const uint32_t kNInputs[7] = {28, 3, 2, 2, 9, 4, 8};       /* clip graphs: no value inputs */
+bool is_clip(uint32_t kind) { return kind >= OSCEN_B200_GRAPH_CLIP_REF && kind < OSCEN_B200_GRAPH_COUNT; }
+int clip_policy(uint32_t kind) { return kind == OSCEN_B200_GRAPH_CLIP_REF ? POL_LATCH : (int)(kind - OSCEN_B200_GRAPH_CLIP_OS_BASE) / 3; }
+int clip_log2f(uint32_t kind) { return kind == OSCEN_B200_GRAPH_CLIP_REF ? 0 : 1 + (int)(kind - OSCEN_B200_GRAPH_CLIP_OS_BASE) % 3; }
+bool has_stream_in(uint32_t kind) { return kind == OSCEN_B200_GRAPH_TWIN_PEAKS || is_clip(kind); }
+uint32_t lcg_field(uint32_t kind) { return kind == OSCEN_B200_GRAPH_TWIN_PEAKS ? (uint32_t)TW_LCG : (uint32_t)CL_LCG; }
+uint32_t n_state_of(uint32_t kind) {
+    static const uint32_t k[7] = {FM_NSTATE, TW_NSTATE, SAT_NSTATE, SAT_NSTATE, EP_NSTATE, SY_NSTATE, SY_NSTATE};
+    return is_clip(kind) ? clip_n_state(clip_policy(kind), clip_log2f(kind)) : k[kind];
+}
 /* defaults of the reference graphs' value inputs (fm_voice.rs:10-48; nih-twin-peaks lib.rs:21-23;
    oversampled-saturator main.rs:71; electric-piano main.rs:39-46; README.md:28-31) */
-const float kDefaults[OSCEN_B200_GRAPH_COUNT][kMaxInputs] = {
+const float kDefaults[7][kMaxInputs] = {
     {440.0f, 3.0f, 0.5f, 0.0f, 0.01f, 0.1f, 0.7f, 0.3f, 2.0f, 0.5f, 0.0f, 0.01f, 0.1f, 0.7f, 0.3f,
      1.0f, 0.01f, 0.2f, 0.8f, 0.5f, 0.0f, 2000.0f, 0.707f, 0.01f, 0.2f, 0.5f, 0.3f, 0.0f},
     {1000.0f, 1900.0f, 0.54f},
@@ -179,7 +188,7 @@ int arg_error(oscen_b200_engine *e, const char *msg) { e->err = msg; return OSCE
 
 /* initial SoA state of one voice after G::new() + G::init(sr) */
 std::vector<uint32_t> initial_state(uint32_t kind, float sr) {
-    std::vector<float> s(kNState[kind], 0.0f);
+    std::vector<float> s(n_state_of(kind), 0.0f);
     auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
     auto adsr = [&](uint32_t base) { s[base + 0] = 0.0f; s[base + 1] = 0.0f; s[base + 2] = 0.0f; s[base + 3] = 1.0f; };
     auto tpt = [&](uint32_t base, float cutoff, float q) {
@@ -206,10 +215,11 @@ std::vector<uint32_t> initial_state(uint32_t kind, float sr) {
         for (int i = 0; i < 32; ++i) { s[EP_ORE + i] = 1.0f; s[EP_MRE + i] = 1.0f; }
         s[EP_STEP] = 64.0f;
         break;
-    default:
+    case OSCEN_B200_GRAPH_SYNTH: case OSCEN_B200_GRAPH_SYNTH_ADSR:
         tpt(SY_TPT, 1200.0f, 0.707f);
         adsr(SY_ENV);
         break;
+    default: break;                                        /* clip graphs: resampler state starts at zero */
     }
     std::vector<uint32_t> out(s.size());
     for (size_t i = 0; i < s.size(); ++i) out[i] = bits(s[i]);
@@ -248,6 +258,32 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
 constexpr size_t kSatDyn = (kTileF * kCta + 2 * 48 * kCta) * sizeof(float);
 constexpr size_t kEpDyn = (kTileF * kCta + kTileF * kTileW + kTileF * kCta * 2) * sizeof(float);
 
+/* the cross-rate clipper family: one instantiation per (policy, log2 factor) */
+template <int P, int L>
+void clip_launch_one(oscen_b200_engine *e, const KernelArgs &a, uint32_t grid, bool set_attr) {
+    if (set_attr) cudaFuncSetAttribute(clip_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_dyn_bytes(P, L));
+    else clip_kernel<P, L><<<grid, kCta, clip_dyn_bytes(P, L), e->stream>>>(a);
+}
+template <int P>
+void clip_launch_policy(oscen_b200_engine *e, const KernelArgs &a, uint32_t grid, int l, bool set_attr) {
+    switch (l) {
+    case 1: clip_launch_one<P, 1>(e, a, grid, set_attr); break;
+    case 2: clip_launch_one<P, 2>(e, a, grid, set_attr); break;
+    default: clip_launch_one<P, 3>(e, a, grid, set_attr); break;
+    }
+}
+void launch_clip(oscen_b200_engine *e, const KernelArgs &a, uint32_t grid, bool set_attr = false) {
+    const uint32_t kind = e->cfg.graph_kind;
+    const int l = clip_log2f(kind);
+    if (l == 0) { clip_launch_one<POL_LATCH, 0>(e, a, grid, set_attr); return; }
+    switch (clip_policy(kind)) {
+    case POL_SINC: clip_launch_policy<POL_SINC>(e, a, grid, l, set_attr); break;
+    case POL_SINC_IIR: clip_launch_policy<POL_SINC_IIR>(e, a, grid, l, set_attr); break;
+    case POL_LINEAR: clip_launch_policy<POL_LINEAR>(e, a, grid, l, set_attr); break;
+    default: clip_launch_policy<POL_LATCH>(e, a, grid, l, set_attr); break;
+    }
+}
+
 /* ---- fused plan: one graph kernel + the mix-bus reduction */
 int launch_fused(oscen_b200_engine *e, bool general) {
     KernelArgs a; fill_args(e, a);
@@ -263,7 +299,8 @@ int launch_fused(oscen_b200_engine *e, bool general) {
     case OSCEN_B200_GRAPH_SAT_4X: sat_kernel<4><<<grid, kCta, kSatDyn, e->stream>>>(a); break;
     case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kCta, kEpDyn, e->stream>>>(a); break;
     case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); break;
-    default: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_SYNTH_ADSR: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); break;
+    default: launch_clip(e, a, grid); break;
     }
     e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
@@ -368,7 +405,7 @@ int oscen_b200_device_count(void) {
     return n;
 }
 
-uint32_t oscen_b200_n_inputs(uint32_t kind) { return kind < OSCEN_B200_GRAPH_COUNT ? kNInputs[kind] : 0; }
+uint32_t oscen_b200_n_inputs(uint32_t kind) { return kind < 7 ? kNInputs[kind] : 0; }
 
 const char *oscen_b200_last_error(const oscen_b200_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
@@ -419,7 +456,7 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
     oscen_b200_engine *e = new oscen_b200_engine();
     e->cfg = *cfg;
     const uint32_t kind = cfg->graph_kind, n = cfg->n_voices;
-    e->n_inputs = kNInputs[kind]; e->n_state = kNState[kind];
+    e->n_inputs = kind < 7 ? kNInputs[kind] : 0u; e->n_state = n_state_of(kind);
     e->n_inst = n / cfg->voices_per_instance;
     e->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2 : 1;
     e->n_cta = (n + kCta - 1) / kCta;
@@ -427,7 +464,7 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
     int rc = [&]() -> int {
         CK(e, cudaSetDevice(cfg->device));
         CK(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        CK(e, cudaMalloc(&e->d_pv, (size_t)e->n_inputs * n * sizeof(float)));
+        CK(e, cudaMalloc(&e->d_pv, (size_t)std::max<uint32_t>(e->n_inputs, 1u) * n * sizeof(float)));
         CK(e, cudaMalloc(&e->d_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
         CK(e, cudaMallocHost(&e->h_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
         CK(e, cudaMalloc(&e->d_state, (size_t)e->n_state * n * sizeof(float)));
@@ -456,9 +493,10 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         CK(e, cudaFuncSetAttribute(sat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
         CK(e, cudaFuncSetAttribute(sat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
         CK(e, cudaFuncSetAttribute(epiano_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEpDyn));
+        if (is_clip(kind)) { KernelArgs none{}; launch_clip(e, none, 0, true); CK(e, cudaGetLastError()); }
         /* new() + init(sr): default inputs, initial node state */
         for (uint32_t i = 0; i < kMaxInputs; ++i) {
-            e->uni[i] = kDefaults[kind][i]; e->uniform[i] = true; e->ramped[i] = false;
+            e->uni[i] = kind < 7 ? kDefaults[kind][i] : 0.0f; e->uniform[i] = true; e->ramped[i] = false;
             e->ramps[i].set_immediate(e->uni[i]);
         }
         for (uint32_t i = 0; i < e->n_inputs; ++i) { int r = fill_row(e, i, 0, n, e->uni[i]); if (r) return r; }
@@ -540,8 +578,8 @@ int oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame
 
 int oscen_b200_stream_in(oscen_b200_engine *e, uint32_t id, const float *src, uint32_t frames, int is_device) {
     if (!e || !src) return OSCEN_B200_E_ARG;
-    if (e->cfg.graph_kind != OSCEN_B200_GRAPH_TWIN_PEAKS || id != 0 || frames == 0 || frames > kMaxBlock)
-        return arg_error(e, "stream_in: only TWIN_PEAKS audio_in (id 0), frames <= 512");
+    if (!has_stream_in(e->cfg.graph_kind) || id != 0 || frames == 0 || frames > kMaxBlock)
+        return arg_error(e, "stream_in: only graphs with a stream input (TWIN_PEAKS audio_in, CLIP_* input; id 0), frames <= 512");
     CK(e, cudaSetDevice(e->cfg.device));
     const size_t nfl = (size_t)frames * e->cfg.n_voices;
     if (is_device) {
@@ -563,20 +601,20 @@ int oscen_b200_stream_in(oscen_b200_engine *e, uint32_t id, const float *src, ui
     return 0;
 }
 
-__global__ void lcg_seed_kernel(float *state, uint32_t n, unsigned long long seed, uint32_t voice_offset) {
+__global__ void lcg_seed_kernel(float *state, uint32_t n, unsigned long long seed, uint32_t voice_offset, uint32_t field) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const unsigned long long s = lcg_seed_state(seed + (unsigned long long)(voice_offset + v));
-    state[(size_t)(TW_LCG + 0) * n + v] = __uint_as_float((uint32_t)(s & 0xffffffffull));
-    state[(size_t)(TW_LCG + 1) * n + v] = __uint_as_float((uint32_t)(s >> 32));
+    state[(size_t)(field + 0) * n + v] = __uint_as_float((uint32_t)(s & 0xffffffffull));
+    state[(size_t)(field + 1) * n + v] = __uint_as_float((uint32_t)(s >> 32));
 }
 
 int oscen_b200_stream_in_lcg(oscen_b200_engine *e, uint32_t id, uint64_t seed, uint32_t voice_offset) {
     if (!e) return OSCEN_B200_E_ARG;
-    if (e->cfg.graph_kind != OSCEN_B200_GRAPH_TWIN_PEAKS || id != 0) return arg_error(e, "stream_in_lcg: only TWIN_PEAKS audio_in");
+    if (!has_stream_in(e->cfg.graph_kind) || id != 0) return arg_error(e, "stream_in_lcg: this graph has no stream input");
     CK(e, cudaSetDevice(e->cfg.device));
     e->lcg_seed = seed; e->voice_offset = voice_offset; e->lcg_on = true;
-    lcg_seed_kernel<<<(e->cfg.n_voices + 255) / 256, 256, 0, e->stream>>>(e->d_state, e->cfg.n_voices, seed, voice_offset);
+    lcg_seed_kernel<<<(e->cfg.n_voices + 255) / 256, 256, 0, e->stream>>>(e->d_state, e->cfg.n_voices, seed, voice_offset, lcg_field(e->cfg.graph_kind));
     e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
     return 0;
@@ -586,7 +624,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     if (!e) return OSCEN_B200_E_ARG;
     if (frames == 0 || frames > kMaxBlock) return arg_error(e, "process_block: frames must be 1..512");
     const uint32_t kind = e->cfg.graph_kind, n = e->cfg.n_voices, vpi = e->cfg.voices_per_instance;
-    if (kind == OSCEN_B200_GRAPH_TWIN_PEAKS && !e->lcg_on && e->stream_in_ptr && e->stream_in_frames < frames)
+    if (has_stream_in(kind) && !e->lcg_on && e->stream_in_ptr && e->stream_in_frames < frames)
         return arg_error(e, "process_block: stream_in block shorter than frames");
     CK(e, cudaSetDevice(e->cfg.device));
 
@@ -800,7 +838,19 @@ uint32_t oscen_b200_channels(const oscen_b200_engine *e) { return e ? e->channel
 /* latency_samples(): sum over Down edges of kernel latency / factor
    (codegen/emit_struct.rs:533-566); SincDownFir<4> reports 33 high-rate samples */
 uint32_t oscen_b200_latency_samples(const oscen_b200_engine *e) {
-    return (e && e->cfg.graph_kind == OSCEN_B200_GRAPH_SAT_4X) ? 33u / 4u : 0u;
+    if (!e) return 0u;
+    const uint32_t kind = e->cfg.graph_kind;
+    if (kind == OSCEN_B200_GRAPH_SAT_4X) return 33u / 4u;
+    if (is_clip(kind) && clip_log2f(kind) > 0) {
+        const uint32_t l = (uint32_t)clip_log2f(kind), factor = 1u << l;
+        switch (clip_policy(kind)) {
+        case POL_SINC: return 11u * (factor - 1u) / factor;          /* sinc_fir.rs:250-260 */
+        case POL_SINC_IIR: return 2u * (factor - 1u) / factor;       /* halfband_iir.rs:253-262 */
+        case POL_LINEAR: return ((factor - 1u) / 2u) / factor;       /* linear.rs:67-70 */
+        default: return 0u;                                          /* latch.rs:50-53 */
+        }
+    }
+    return 0u;
 }
 
 size_t oscen_b200_state_bytes_per_voice(const oscen_b200_engine *e) { return e ? (size_t)e->n_state * sizeof(float) : 0; }

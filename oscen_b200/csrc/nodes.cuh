@@ -392,6 +392,50 @@ OSC_D float hb_down_step(float *hist, int stride, uint32_t &head, float x0, floa
     return acc;
 }
 
+/* ========================================================= Halfband2xUpStage::step == */
+/* oscen-lib/src/resample/sinc_fir.rs:54-79.  `hist`: this thread's 12-slot ring stored twice
+   (24 slots, stride `stride`), `head` in [0,12) as in the reference: x[n - d] = hist[head + 12 - d]. */
+OSC_D void hb_up_step(float *hist, int stride, uint32_t &head, float x, float &out0, float &out1) {
+    head = (head + 1u == 12u) ? 0u : head + 1u; hist[head * stride] = x; hist[(head + 12u) * stride] = x;
+    const float *h = hist + (head + 12u) * stride;          /* h[-d*stride] = x[n - d], d = 0..11 */
+#define OSC_UP_AT(d) h[-(int)(d) * stride]
+    out1 = OSC_UP_AT(5) * (2.0f * kHbCenter);
+    float acc = 0.0f;
+    acc = acc + (OSC_UP_AT(0) + OSC_UP_AT(11)) * kHb0;
+    acc = acc + (OSC_UP_AT(1) + OSC_UP_AT(10)) * kHb1;
+    acc = acc + (OSC_UP_AT(2) + OSC_UP_AT(9)) * kHb2;
+    acc = acc + (OSC_UP_AT(3) + OSC_UP_AT(8)) * kHb3;
+    acc = acc + (OSC_UP_AT(4) + OSC_UP_AT(7)) * kHb4;
+    acc = acc + (OSC_UP_AT(5) + OSC_UP_AT(6)) * kHb5;
+#undef OSC_UP_AT
+    out0 = acc * 2.0f;
+}
+
+/* ===================================================================== IirHalfband2x == */
+/* oscen-lib/src/resample/halfband_iir.rs:24-143, coeffs.rs:47-54 */
+constexpr float kIirA0 = 0.1355741f, kIirA1 = 0.6975849f, kIirB0 = 0.4253804f, kIirB1 = 0.9055601f;
+constexpr float kDenormalThreshold = 1e-15f;               /* halfband_iir.rs:22 */
+OSC_D float flush_denormal(float x) { return fabsf(x) < kDenormalThreshold ? 0.0f : x; }   /* frame.rs:87-93 */
+struct Allpass1 { float x_prev, y_prev; };
+/* Allpass1::step (halfband_iir.rs:45-57): the returned y is the pre-snap value */
+OSC_D float allpass1_step(Allpass1 &s, float a, float x) {
+    const float y = (x - s.y_prev) * a + s.x_prev;
+    s.x_prev = flush_denormal(x);
+    s.y_prev = flush_denormal(y);
+    return y;
+}
+struct IirHb { Allpass1 a0, a1, b0, b1; float prev_odd_in; };
+OSC_D void iir_hb_step_up(IirHb &h, float x, float &out0, float &out1) {         /* halfband_iir.rs:104-116 */
+    out0 = allpass1_step(h.a1, kIirA1, allpass1_step(h.a0, kIirA0, x));
+    out1 = allpass1_step(h.b1, kIirB1, allpass1_step(h.b0, kIirB0, x));
+}
+OSC_D float iir_hb_step_down(IirHb &h, float x0, float x1) {                      /* halfband_iir.rs:124-136 */
+    const float a = allpass1_step(h.a1, kIirA1, allpass1_step(h.a0, kIirA0, x0));
+    const float b = allpass1_step(h.b1, kIirB1, allpass1_step(h.b0, kIirB0, h.prev_odd_in));
+    h.prev_odd_in = x1;
+    return (a + b) * 0.5f;
+}
+
 /* ====================================================================== Tremolo == */
 /* examples/electric-piano/src/tremolo.rs:41-61 */
 OSC_D void tremolo_process(float &phase, float input, float rate, float depth, float sample_rate,

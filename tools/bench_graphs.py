@@ -28,6 +28,14 @@ CASES = [
     ("epiano 131072 instances x 16 voices (config 3, reference polyphony)", abi.GRAPH_EPIANO, 131072 * 16, 16, 0, 259),
     ("epiano 131072 instances x 8 voices (config 3 as worded)", abi.GRAPH_EPIANO, 131072 * 8, 8, 0, 259),
     ("synth_adsr 1048576 voices (osc+filter+env)", abi.GRAPH_SYNTH_ADSR, 1048576, 1, 0, 13),
+    # cross-rate clipper graphs: per-voice input stream read from HBM, per-voice output kept (8 B/voice-sample)
+    ("clip_ref 1x 1048576 voices, stream in+out", abi.GRAPH_CLIP_REF, 1048576, 1, 4, 2),
+    ("clip_os sinc 4x 1048576 voices, stream in+out (ClipOversampled)", abi.graph_clip_os(abi.POLICY_SINC, 4), 1048576, 1, 4, 74),
+    ("clip_os sinc_iir 4x 1048576 voices, stream in+out (ClipOversampledIir)", abi.graph_clip_os(abi.POLICY_SINC_IIR, 4), 1048576, 1, 4, 36),
+    ("clip_os sinc 8x 1048576 voices, stream in+out", abi.graph_clip_os(abi.POLICY_SINC, 8), 1048576, 1, 4, 110),
+    ("clip_os sinc_iir 8x 1048576 voices, stream in+out", abi.graph_clip_os(abi.POLICY_SINC_IIR, 8), 1048576, 1, 4, 53),
+    ("clip_os linear 4x 1048576 voices, stream in+out", abi.graph_clip_os(abi.POLICY_LINEAR, 4), 1048576, 1, 4, 3),
+    ("clip_os latch 4x 1048576 voices, stream in+out", abi.graph_clip_os(abi.POLICY_LATCH, 4), 1048576, 1, 4, 2),
 ]
 
 
@@ -37,12 +45,12 @@ def main():
     for name, kind, n, vpi, in_bytes, nstate in CASES:
         if only and only not in name:
             continue
-        keep = abi.KEEP_INSTANCE_OUT if vpi > 1 else 0
+        is_clip = kind >= abi.GRAPH_CLIP_REF
+        keep = abi.KEEP_INSTANCE_OUT if vpi > 1 else (abi.KEEP_VOICE_OUT if is_clip else 0)
         e = abi.Engine(kind, n, vpi, 48000.0, 0, abi.PLAN_FUSED, keep)
         rng = np.random.default_rng(1)
-        if kind == abi.GRAPH_TWIN_PEAKS:
+        if kind == abi.GRAPH_TWIN_PEAKS or is_clip:
             if in_bytes:
-                import ctypes as C
                 x = rng.uniform(-1, 1, size=(FRAMES, n)).astype(np.float32)
                 e.stream_in(0, x)
             else:
@@ -66,7 +74,8 @@ def main():
         k_ms = float(np.mean(ms))
         ch = e.channels
         bytes_f = n * (2 * nstate * 4 + 4 * abi.load().oscen_b200_n_inputs(kind)) + n * FRAMES * in_bytes \
-            + ((n // vpi) * FRAMES * 4 * ch if keep else 0) + ((n + 63) // 64) * FRAMES * 4 * ch
+            + ((n // vpi) * FRAMES * 4 * ch if keep & abi.KEEP_INSTANCE_OUT else 0) + (n * FRAMES * 4 if keep & abi.KEEP_VOICE_OUT else 0) \
+            + ((n + 63) // 64) * FRAMES * 4 * ch
         print(json.dumps({"graph": name, "voices": n, "frames": FRAMES, "kernel_ms": k_ms,
                           "voice_samples_per_s": n * FRAMES / (k_ms * 1e-3),
                           "realtime_voices_48k": n * FRAMES / (k_ms * 1e-3) / 48000.0,

@@ -87,41 +87,93 @@ class Workload:
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """SM clock and clock-event (throttle) reasons DURING the timed region (B200_PROFILING.md's clocks
+    line).  In-process NVML polling every ~4 ms (the timed region of the default run is only tens of
+    milliseconds; an `nvidia-smi -lms` child needs seconds to start on an 8-GPU box and then misses
+    it); falls back to the nvidia-smi loop when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, uuid=None):
         super().__init__(daemon=True)
-        self.device = device
-        self.rows = []
+        self.device, self.uuid = device, uuid
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.source = None
+        self._stop_flag = threading.Event()
+        self._ready = threading.Event()
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, self.uuid.encode()):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(u); break
+                except Exception:
+                    h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        self.source = "nvml"
+        self._ready.set()
+        while not self._stop_flag.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))); self.mx.append(mx)
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            for name, bit in names:
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.004)
+
+    def _smi_loop(self):
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+        self.source = "nvidia-smi"
+        for line in self.proc.stdout:
+            self._ready.set()
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except (ValueError, IndexError):
+                continue
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+            self._nvml_loop()
         except Exception:
-            pass
+            try:
+                self._smi_loop()
+            except Exception:
+                pass
+        self._ready.set()
+
+    def begin(self):
+        """start sampling and wait until the first sample can arrive, then drop what was seen while idle"""
+        self.start()
+        self._ready.wait(timeout=10.0)
+        self.sm.clear(); self.mx.clear(); self.reasons.clear()
 
     def stop(self):
+        self._stop_flag.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
+        sm, mx = list(self.sm), list(self.mx)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def measured_peaks():
@@ -303,7 +355,11 @@ def run(out):
         wl.apply(eng, b, abi.EVENT_DTYPE, abi.EVENT_GATE)
         eng.l2_flush(); eng.process_block(FRAMES)
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid); sampler.begin()
     st0 = eng.stats()
     step_ms, kern_ms = [], []
     t_wall0 = time.perf_counter()

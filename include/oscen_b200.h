@@ -164,6 +164,21 @@ int  oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, si
 int  oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame_offset,
                           const uint8_t *bytes, uint32_t len);
 
+/* Device-side MIDI front: the same semantics as n calls of oscen_b200_push_midi in
+   array order, but MidiParser -> VoiceAllocator<N> -> MidiVoiceHandler run on the GPU, one thread
+   per instance (oscen-lib/src/midi.rs:82-224, voice_allocator.rs:57-136), and write the per-voice
+   gate / frequency events directly into the device event list — no host loop over instances.
+   An engine uses EITHER push_midi (host front) OR push_midi_batch (device front) for its lifetime
+   (the allocator state lives on one side); mixing returns OSCEN_B200_E_STATE, as does combining
+   push_midi_batch with oscen_b200_push_events in one block.  voices_per_instance <= 16. */
+typedef struct {
+    uint32_t instance;
+    uint32_t frame_offset;
+    uint8_t  bytes[3];
+    uint8_t  len;
+} oscen_b200_midi_msg;
+int  oscen_b200_push_midi_batch(oscen_b200_engine *e, const oscen_b200_midi_msg *msgs, size_t n);
+
 /* stream input block [frames][n_voices] f32 for the NEXT process_block (TWIN_PEAKS audio_in,
    CLIP_* input).
    is_device != 0: `src` is a device pointer on the engine's device (no copy is made; it must

@@ -31,7 +31,7 @@ KEEP_VOICE_OUT, KEEP_INSTANCE_OUT = 1, 2
 SYMBOLS = [
     "oscen_b200_abi_version", "oscen_b200_device_count", "oscen_b200_create", "oscen_b200_destroy",
     "oscen_b200_last_error", "oscen_b200_set_value", "oscen_b200_set_value_ramp", "oscen_b200_push_events",
-    "oscen_b200_push_midi", "oscen_b200_stream_in", "oscen_b200_stream_in_lcg", "oscen_b200_process_block",
+    "oscen_b200_push_midi", "oscen_b200_push_midi_batch", "oscen_b200_stream_in", "oscen_b200_stream_in_lcg", "oscen_b200_process_block",
     "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
@@ -56,6 +56,7 @@ class Stats(C.Structure):
 
 
 EVENT_DTYPE = np.dtype([("voice", "<u4"), ("frame_offset", "<u4"), ("input_id", "<u4"), ("scalar", "<f4")])
+MIDI_DTYPE = np.dtype([("instance", "<u4"), ("frame_offset", "<u4"), ("bytes", "u1", (3,)), ("len", "u1")])   # oscen_b200_midi_msg
 
 _lib = None
 
@@ -80,6 +81,7 @@ def load():
     L.oscen_b200_set_value_ramp.argtypes = [vp, u32, C.c_float, u32]
     L.oscen_b200_push_events.argtypes = [vp, vp, C.c_size_t]
     L.oscen_b200_push_midi.argtypes = [vp, u32, u32, vp, u32]
+    L.oscen_b200_push_midi_batch.argtypes = [vp, vp, C.c_size_t]
     L.oscen_b200_stream_in.argtypes = [vp, u32, vp, u32, C.c_int]
     L.oscen_b200_stream_in_lcg.argtypes = [vp, u32, C.c_uint64, u32]
     L.oscen_b200_process_block.argtypes = [vp, u32]
@@ -172,6 +174,20 @@ class Engine:
     def push_midi(self, instance, frame_offset, data):
         b = (C.c_uint8 * len(data))(*data)
         self._chk(self.L.oscen_b200_push_midi(self.h, instance, frame_offset, b, len(data)), "push_midi")
+
+    def push_midi_batch(self, msgs):
+        """device-side MIDI front: structured ndarray (MIDI_DTYPE) or iterable of (instance, frame_offset, bytes)"""
+        if not (isinstance(msgs, np.ndarray) and msgs.dtype == MIDI_DTYPE):
+            rows = list(msgs)
+            arr = np.zeros(len(rows), dtype=MIDI_DTYPE)
+            for k, (inst, frame, data) in enumerate(rows):
+                data = list(data)[:3]
+                arr[k]["instance"], arr[k]["frame_offset"], arr[k]["len"] = inst, frame, len(data)
+                arr[k]["bytes"][:len(data)] = data
+            msgs = arr
+        msgs = np.ascontiguousarray(msgs)
+        if msgs.size:
+            self._chk(self.L.oscen_b200_push_midi_batch(self.h, msgs.ctypes.data, msgs.size), "push_midi_batch")
 
     def stream_in(self, input_id, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32)

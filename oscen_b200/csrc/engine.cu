@@ -25,6 +25,7 @@
 #include "kernel_resample.cuh"
 #include "graphs.hpp"
 #include "midi_front.hpp"
+#include "midi_device.cuh"
 
 using namespace oscen;
 
@@ -124,7 +125,17 @@ struct oscen_b200_engine {
     /* events */
     std::vector<Event> pending;
     std::vector<uint32_t> seqs;
-    std::vector<MidiFront> midi;
+    std::vector<MidiFront> midi;         /* host front, allocated on the first push_midi */
+    /* device-side MIDI front (midi_device.cuh): per-voice allocator / handler state and scratch */
+    int midi_mode = 0;                   /* 0 unset, 1 host front, 2 device front (exclusive per engine) */
+    std::vector<MidiMsg> midi_batch;     /* this block's messages, push order */
+    MidiMsg *d_midi_msgs = nullptr;
+    uint32_t *d_midi_keys_in = nullptr, *d_midi_keys = nullptr, *d_midi_idx_in = nullptr, *d_midi_idx = nullptr;
+    size_t midi_cap = 0;
+    void *d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    uint32_t *d_alloc_word = nullptr, *d_alloc_age = nullptr, *d_alloc_cur_age = nullptr;
+    int *d_h_note = nullptr; float *d_h_freq = nullptr, *d_note_freq = nullptr;
+    uint32_t *d_ev_count = nullptr, *d_ev_offset = nullptr, *d_midi_dropped = nullptr;
     uint32_t seq = 0;
     Event *d_events = nullptr, *h_events = nullptr;
     size_t events_cap = 0;
@@ -426,6 +437,10 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evk) cudaEventDestroy(e->evk);
     cudaFree(e->d_flush);
+    cudaFree(e->d_midi_msgs); cudaFree(e->d_midi_keys_in); cudaFree(e->d_midi_keys); cudaFree(e->d_midi_idx_in); cudaFree(e->d_midi_idx);
+    cudaFree(e->d_cub_tmp); cudaFree(e->d_alloc_word); cudaFree(e->d_alloc_age); cudaFree(e->d_alloc_cur_age);
+    cudaFree(e->d_h_note); cudaFree(e->d_h_freq); cudaFree(e->d_note_freq);
+    cudaFree(e->d_ev_count); cudaFree(e->d_ev_offset); cudaFree(e->d_midi_dropped);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -515,7 +530,6 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         return 0;
     }();
     if (rc) { g_create_error = e->err; oscen_b200_destroy(e); return rc; }
-    e->midi.assign(e->n_inst, MidiFront((int)cfg->voices_per_instance));
     *out = e;
     return 0;
 }
@@ -572,7 +586,107 @@ int oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, siz
 int oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame_offset, const uint8_t *bytes, uint32_t len) {
     if (!e || !bytes) return OSCEN_B200_E_ARG;
     if (instance >= e->n_inst) return arg_error(e, "push_midi: instance out of range");
+    if (e->cfg.voices_per_instance > (uint32_t)kMaxPolyVoices) return arg_error(e, "push_midi: VoiceAllocator holds at most 24 voices (voice_allocator.rs:5)");
+    if (e->midi_mode == 2) { e->err = "push_midi: this engine runs the device-side MIDI front (push_midi_batch)"; return OSCEN_B200_E_STATE; }
+    if (e->midi_mode == 0) { e->midi.assign(e->n_inst, MidiFront((int)e->cfg.voices_per_instance)); e->midi_mode = 1; }
     if (!e->midi[instance].push(frame_offset, bytes, len, e->seq++)) e->stats.events_dropped++;
+    return 0;
+}
+
+namespace {
+/* device front: state after VoiceAllocator::new / MidiVoiceHandler::new (voice_allocator.rs:44-55, midi.rs:52-66) */
+int midi_device_init(oscen_b200_engine *e) {
+    const uint32_t n = e->cfg.n_voices;
+    CK(e, cudaMalloc(&e->d_alloc_word, (size_t)n * 4)); CK(e, cudaMalloc(&e->d_alloc_age, (size_t)n * 4));
+    CK(e, cudaMalloc(&e->d_alloc_cur_age, (size_t)e->n_inst * 4));
+    CK(e, cudaMalloc(&e->d_h_note, (size_t)n * 4)); CK(e, cudaMalloc(&e->d_h_freq, (size_t)n * 4));
+    CK(e, cudaMalloc(&e->d_ev_count, (size_t)n * 4)); CK(e, cudaMalloc(&e->d_ev_offset, (size_t)n * 4));
+    CK(e, cudaMalloc(&e->d_note_freq, 256 * sizeof(float))); CK(e, cudaMalloc(&e->d_midi_dropped, 4));
+    CK(e, cudaMemsetAsync(e->d_alloc_word, 0, (size_t)n * 4, e->stream));
+    CK(e, cudaMemsetAsync(e->d_alloc_age, 0, (size_t)n * 4, e->stream));
+    CK(e, cudaMemsetAsync(e->d_alloc_cur_age, 0, (size_t)e->n_inst * 4, e->stream));
+    CK(e, cudaMemsetAsync(e->d_h_note, 0xFF, (size_t)n * 4, e->stream));               /* current_note = -1 */
+    CK(e, cudaMemsetAsync(e->d_midi_dropped, 0, 4, e->stream));
+    uint32_t bits440; const float f440 = 440.0f; memcpy(&bits440, &f440, 4);
+    fill_u32_kernel<<<std::min<uint32_t>((n + 255) / 256, 1184), 256, 0, e->stream>>>((uint32_t *)e->d_h_freq, n, bits440);
+    e->stats.kernel_launches++;
+    float tab[256];
+    for (int i = 0; i < 256; ++i) tab[i] = midi_note_to_freq((uint8_t)i);               /* host libm powf, as the host front */
+    CK(e, cudaMemcpyAsync(e->d_note_freq, tab, sizeof tab, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* run the device front for this block: fills d_events (sorted by voice, frame, order) and BlockCtl.n_events */
+int midi_device_run(oscen_b200_engine *e, uint32_t frames) {
+    const uint32_t n = e->cfg.n_voices, nm = (uint32_t)e->midi_batch.size();
+    if (nm > e->midi_cap) {
+        CK(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_midi_msgs); cudaFree(e->d_midi_keys_in); cudaFree(e->d_midi_keys); cudaFree(e->d_midi_idx_in); cudaFree(e->d_midi_idx);
+        cudaFree(e->d_cub_tmp); e->d_cub_tmp = nullptr;
+        e->midi_cap = (size_t)nm * 2;
+        CK(e, cudaMalloc(&e->d_midi_msgs, e->midi_cap * sizeof(MidiMsg)));
+        CK(e, cudaMalloc(&e->d_midi_keys_in, e->midi_cap * 4)); CK(e, cudaMalloc(&e->d_midi_keys, e->midi_cap * 4));
+        CK(e, cudaMalloc(&e->d_midi_idx_in, e->midi_cap * 4)); CK(e, cudaMalloc(&e->d_midi_idx, e->midi_cap * 4));
+        size_t t_sort = 0, t_scan = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t_sort, e->d_midi_keys_in, e->d_midi_keys, e->d_midi_idx_in, e->d_midi_idx, (int)e->midi_cap, 0, 32, e->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, t_scan, e->d_ev_count, e->d_ev_offset, (int)n, e->stream);
+        e->cub_tmp_bytes = std::max(t_sort, t_scan);
+        CK(e, cudaMalloc(&e->d_cub_tmp, e->cub_tmp_bytes));
+    }
+    /* every message yields at most a gate and a frequency event */
+    if ((size_t)nm * 2 > e->events_cap) {
+        CK(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_events); cudaFreeHost(e->h_events);
+        e->events_cap = (size_t)nm * 4;
+        CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
+        CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
+        for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    }
+    /* pageable source: the copy is staged by the runtime before the call returns */
+    CK(e, cudaMemcpyAsync(e->d_midi_msgs, e->midi_batch.data(), (size_t)nm * sizeof(MidiMsg), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += (uint64_t)nm * sizeof(MidiMsg);
+    midi_keys_kernel<<<(nm + 255) / 256, 256, 0, e->stream>>>(e->d_midi_msgs, nm, e->d_midi_keys_in, e->d_midi_idx_in);
+    int bits = 1; while ((1ull << bits) < (unsigned long long)e->n_inst) ++bits;
+    size_t tmp = e->cub_tmp_bytes;
+    CK(e, cub::DeviceRadixSort::SortPairs(e->d_cub_tmp, tmp, e->d_midi_keys_in, e->d_midi_keys, e->d_midi_idx_in, e->d_midi_idx, (int)nm, 0, bits, e->stream));
+    CK(e, cudaMemsetAsync(e->d_ev_count, 0, (size_t)n * 4, e->stream));
+    MidiFrontArgs a{};
+    a.msgs = e->d_midi_msgs; a.keys = e->d_midi_keys; a.idx = e->d_midi_idx;
+    a.n_msgs = nm; a.n_inst = e->n_inst; a.vpi = e->cfg.voices_per_instance; a.frames = frames;
+    a.alloc_word = e->d_alloc_word; a.alloc_age = e->d_alloc_age; a.alloc_cur_age = e->d_alloc_cur_age;
+    a.h_note = e->d_h_note; a.h_freq = e->d_h_freq; a.note_freq = e->d_note_freq;
+    a.ev_count = e->d_ev_count; a.ev_offset = e->d_ev_offset; a.events = e->d_events; a.dropped = e->d_midi_dropped;
+    const uint32_t grid = (e->n_inst + 127) / 128;
+    midi_front_kernel<false><<<grid, 128, 0, e->stream>>>(a);
+    tmp = e->cub_tmp_bytes;
+    CK(e, cub::DeviceScan::ExclusiveSum(e->d_cub_tmp, tmp, e->d_ev_count, e->d_ev_offset, (int)n, e->stream));
+    midi_front_kernel<true><<<grid, 128, 0, e->stream>>>(a);
+    midi_finish_kernel<<<1, 1, 0, e->stream>>>(e->d_ev_count, e->d_ev_offset, n, e->d_ctl);
+    e->stats.kernel_launches += 4;
+    CK(e, cudaGetLastError());
+    e->midi_batch.clear();
+    return 0;
+}
+}  // namespace
+
+int oscen_b200_push_midi_batch(oscen_b200_engine *e, const oscen_b200_midi_msg *msgs, size_t n) {
+    static_assert(sizeof(MidiMsg) == sizeof(oscen_b200_midi_msg), "midi message layout");
+    if (!e || (!msgs && n)) return OSCEN_B200_E_ARG;
+    if (e->cfg.voices_per_instance > (uint32_t)kDevMaxPoly) return arg_error(e, "push_midi_batch: voices_per_instance must be <= 16");
+    if (e->midi_mode == 1) { e->err = "push_midi_batch: this engine runs the host-side MIDI front (push_midi)"; return OSCEN_B200_E_STATE; }
+    for (size_t i = 0; i < n; ++i) if (msgs[i].instance >= e->n_inst) return arg_error(e, "push_midi_batch: instance out of range");
+    CK(e, cudaSetDevice(e->cfg.device));
+    if (e->midi_mode == 0) { const int r = midi_device_init(e); if (r) return r; e->midi_mode = 2; }
+    const size_t at = e->midi_batch.size();
+    e->midi_batch.resize(at + n);
+    for (size_t i = 0; i < n; ++i) {
+        MidiMsg m{};
+        m.instance = msgs[i].instance; m.frame = msgs[i].frame_offset;
+        m.len = msgs[i].len > 3 ? 3 : msgs[i].len;                                     /* RawMidiMessage::new, midi.rs:15-22 */
+        for (uint32_t k = 0; k < m.len; ++k) m.bytes[k] = msgs[i].bytes[k];
+        e->midi_batch[at + i] = m;
+    }
     return 0;
 }
 
@@ -628,9 +742,14 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         return arg_error(e, "process_block: stream_in block shorter than frames");
     CK(e, cudaSetDevice(e->cfg.device));
 
+    const bool device_midi = e->midi_mode == 2 && !e->midi_batch.empty();
+    if (device_midi && !e->pending.empty()) {
+        e->err = "process_block: push_events and push_midi_batch in the same block are not supported";
+        return OSCEN_B200_E_STATE;
+    }
     /* ---- MIDI front -> per-voice events */
     std::vector<VoiceEvent> ve;
-    for (uint32_t i = 0; i < e->n_inst; ++i) {
+    for (uint32_t i = 0; i < (e->midi_mode == 1 ? e->n_inst : 0u); ++i) {
         if (e->midi[i].pending.empty()) continue;
         ve.clear();
         e->midi[i].run(frames, ve);
@@ -710,6 +829,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         e->stats.h2d_bytes += (uint64_t)frames * kMaxInputs * sizeof(float);
         general = true;
     }
+    if (device_midi) { e->uniform[0] = false; has_value_events = true; }               /* per-voice `frequency` value events */
     for (uint32_t i = 1; i < e->n_inputs; ++i) if (!e->uniform[i]) general = true;
     if (kind != OSCEN_B200_GRAPH_FM_VOICE) general = true;
 
@@ -726,6 +846,12 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         e->stats.h2d_bytes += sizeof(BlockCtl);
     }
 
+    if (device_midi) {
+        /* the device front writes the event list and BlockCtl.n_events itself; the host's copy of
+           BlockCtl is stale afterwards, so the next block uploads it again */
+        const int r = midi_device_run(e, frames); if (r) return r;
+        e->ctl_on_device.n_events = 0xFFFFFFFFu;
+    }
     if (e->timing) CK(e, cudaEventRecord(e->ev0, e->stream));
     int rc = 0;
     if (e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
@@ -869,6 +995,12 @@ int oscen_b200_state_download(oscen_b200_engine *e, void *dst, size_t cap) {
 int oscen_b200_get_stats(const oscen_b200_engine *e, oscen_b200_stats *out) {
     if (!e || !out) return OSCEN_B200_E_ARG;
     *out = e->stats;
+    if (e->d_midi_dropped) {                               /* messages the device front found a full queue for */
+        uint32_t d = 0;
+        cudaSetDevice(e->cfg.device);
+        if (cudaStreamSynchronize(e->stream) == cudaSuccess &&
+            cudaMemcpy(&d, e->d_midi_dropped, 4, cudaMemcpyDeviceToHost) == cudaSuccess) out->events_dropped += d;
+    }
     return 0;
 }
 

@@ -571,3 +571,94 @@ def test_clip_oversampled_full_size_1m_voices_round_trip_properties():
             ref.stream_in(0, x[b * frames:(b + 1) * frames]); ref.process_block(frames)
             assert np.array_equal(outs[b][idx], ref.read_voice_out()), (first, b)
     assert np.abs(outs[1][0]).max() < 1.2
+
+
+# --------------------------------------------------------------- device-side MIDI front (SURVEY §8f.2)
+def _random_midi(rng, n_inst, frames, per_inst_max, n_notes):
+    """[(instance, frame, bytes)] in push order: note-ons, note-offs, velocity-0 note-ons, controller noise,
+    some instances above the 32-slot queue, some offsets beyond the block"""
+    msgs = []
+    for inst in range(n_inst):
+        for _ in range(int(rng.integers(0, per_inst_max + 1))):
+            frame = int(rng.integers(0, frames + 30))
+            note = int(rng.integers(40, 40 + n_notes))
+            r = rng.random()
+            if r < 0.55:
+                data = [0x90 | int(rng.integers(0, 16)), note, int(rng.integers(1, 128))]
+            elif r < 0.85:
+                data = [0x80, note, 0]
+            elif r < 0.93:
+                data = [0x90, note, 0]
+            elif r < 0.97:
+                data = [0xB0, 7, 100]
+            else:
+                data = [0x90, note]                                  # short message: ignored by the parser
+            msgs.append((inst, frame, data))
+    order = rng.permutation(len(msgs))                               # interleave instances in push order
+    return [msgs[i] for i in order]
+
+
+@pytest.mark.parametrize("kind,vpi", [(O.K_FM, 8), (O.K_EPIANO, 16), (O.K_FM, 2)])
+def test_device_midi_front_matches_oracle_and_host_front(kind, vpi):
+    n_inst = 96
+    n = n_inst * vpi
+    ref = O.OracleBank(kind, n, vpi)
+    host = engine(kind, n, vpi)
+    dev = engine(kind, n, vpi)
+    rng = np.random.default_rng(11)
+    for blk, frames in enumerate((256, 100, 512, 256)):
+        msgs = _random_midi(rng, n_inst, frames, 40 if blk == 0 else 6, 2 * vpi)
+        for inst, frame, data in msgs:
+            ref.push_midi(inst, frame, data); host.push_midi(inst, frame, data)
+        dev.push_midi_batch(msgs)
+        for b in (ref, host, dev):
+            b.process_block(frames)
+        yr, yh, yd = ref.read_voice_out(), host.read_voice_out(), dev.read_voice_out()
+        assert np.array_equal(yh, yd), (blk, "device front != host front")
+        assert_close(yd, yr, f"device MIDI front block {blk}")
+        assert_close(dev.read_instance_out(), ref.read_instance_out(), f"device MIDI front instance_out block {blk}")
+    assert np.abs(yr).max() > 1e-3
+    assert dev.stats()["events_dropped"] == host.stats()["events_dropped"] > 0
+
+
+def test_device_midi_front_mode_is_exclusive():
+    from oscen_b200 import abi
+    e = engine(O.K_FM, 16, 8)
+    e.push_midi(0, 0, [0x90, 60, 100])
+    with pytest.raises(abi.EngineError):
+        e.push_midi_batch([(0, 0, [0x90, 62, 100])])
+    e2 = engine(O.K_FM, 16, 8)
+    e2.push_midi_batch([(1, 3, [0x90, 62, 100])])
+    with pytest.raises(abi.EngineError):
+        e2.push_midi(0, 0, [0x90, 60, 100])
+    e2.push_events([(0, 0, GATE, 1.0)])
+    with pytest.raises(abi.EngineError):
+        e2.process_block(64)
+
+
+def test_device_midi_front_full_size_epiano_131072_instances():
+    """config 3 polyphony: 131 072 ElectricPiano instances x 16 voices take a chord each through the
+    device-side front (no host loop over instances); slices are checked against the oracle"""
+    from oscen_b200 import abi
+    n_inst, vpi, frames = 131072, 16, 256
+    gpu = engine(O.K_EPIANO, n_inst * vpi, vpi, keep=2)
+    rng = np.random.default_rng(5)
+    k = 3
+    msgs = np.zeros(n_inst * k, dtype=abi.MIDI_DTYPE)
+    msgs["instance"] = np.repeat(np.arange(n_inst), k)
+    msgs["frame_offset"] = rng.integers(0, frames, size=n_inst * k)
+    msgs["bytes"][:, 0] = 0x90
+    msgs["bytes"][:, 1] = rng.integers(36, 96, size=n_inst * k)
+    msgs["bytes"][:, 2] = rng.integers(1, 128, size=n_inst * k)
+    msgs["len"] = 3
+    offs = msgs.copy(); offs["bytes"][:, 0] = 0x80; offs["frame_offset"] = rng.integers(0, frames, size=n_inst * k)
+    gpu.push_midi_batch(msgs); gpu.process_block(frames); y0 = gpu.read_instance_out().copy()
+    gpu.push_midi_batch(offs); gpu.process_block(frames); y1 = gpu.read_instance_out().copy()
+    assert np.isfinite(y0).all() and np.abs(y0).max() > 1e-3
+    for first in (0, n_inst - 8):
+        ref = O.OracleBank(O.K_EPIANO, 8 * vpi, vpi)
+        for blk, (m, want) in enumerate(((msgs, y0), (offs, y1))):
+            for row in m[first * k:(first + 8) * k]:
+                ref.push_midi(int(row["instance"]) - first, int(row["frame_offset"]), [int(x) for x in row["bytes"]])
+            ref.process_block(frames)
+            assert_close(want[:, first:first + 8], ref.read_instance_out(), f"epiano device MIDI slice {first} block {blk}")

@@ -56,7 +56,8 @@ enum {
        clamp(+-0.7) with no drive (multirate_graph.rs:35-40). */
     OSCEN_B200_GRAPH_CLIP_REF = 7,    /* ClipRef: input -> clip -> out at 1x           multirate_graph.rs:282-293 */
     OSCEN_B200_GRAPH_CLIP_OS_BASE = 8,/* 8..19 = OSCEN_B200_GRAPH_CLIP_OS(policy, log2_factor), below */
-    OSCEN_B200_GRAPH_COUNT = 20
+    OSCEN_B200_GRAPH_CUSTOM = 20,     /* a graph compiled from `graph!` DSL text: oscen_b200_graph_compile + oscen_b200_create_from_graph */
+    OSCEN_B200_GRAPH_COUNT = 21
 };
 /* connection policy of both cross-rate edges (`[sinc]`, `[sinc_iir]`, `[linear]`, `[latch]`,
    oscen-graph-compiler/src/ast.rs ConnectionPolicy; resampler kernels oscen-lib/src/resample/) */
@@ -211,6 +212,42 @@ int  oscen_b200_state_download(oscen_b200_engine *e, void *dst, size_t cap);
    oscen-graph-compiler/src/ir/lower.rs:1015-1085).  Returns the number of launches (>0), or a
    negative code for graphs that only have a fused kernel.  Needs no GPU. */
 int  oscen_b200_plan_describe(uint32_t graph_kind, char *dst, size_t cap);
+
+/* ---- the `graph!` DSL front end --------------------------------------------------
+ * Replaces, at run time, what the reference does at Rust compile time: oscen_graph_compiler::compile
+ * (oscen-graph-compiler/src/lib.rs:22-34) = parse_graph_def (parse.rs:195-241) -> ir::lower (ir/lower.rs)
+ * -> dead-node pass (ir/passes/dead_nodes.rs) -> Kahn sort (ir/lower.rs:1015-1085) -> codegen.  The text
+ * is the body of a `graph! { ... }` invocation (with or without the `graph! { }` wrapper): `name:`,
+ * `input` / `output` declarations in both spellings, `node` / `nodes { }`, `connection` /
+ * `connections { }`, compound sources (+ - * /, parentheses, .tanh() .abs() .clamp(a,b) .min(a) .max(a)).
+ * The result is a node plan (one kernel launch per node type per ready wave, streams in HBM, replayed
+ * as a CUDA graph).  Node types with kernels: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator
+ * (sine/saw/square/triangle), LP18Filter, Gain, AddValue, Mixer, Crossfade, HardClip.  Constructs the node
+ * plan cannot express are compile ERRORS with a line:column, never silently dropped: node rates
+ * (`* N`), node arrays (`[T; N]`: voices_per_instance is the array axis), nested graphs, `-> [N] ->`
+ * feedback edges, `external` assets, typed (array / Frame<N>) endpoints, free-function calls.
+ * Value inputs get ids in declaration order (oscen_b200_graph_input_id); the graph's event input carries
+ * gate events (OSCEN_B200_EVENT_GATE) to every AdsrEnvelope it is connected to; the graph's stream input
+ * is oscen_b200_stream_in id 0.  Compiling needs no GPU. */
+typedef struct oscen_b200_graph oscen_b200_graph;
+/* err (optional) receives "line:col: message" on failure */
+int  oscen_b200_graph_compile(const char *dsl_text, oscen_b200_graph **out, char *err, size_t err_cap);
+void oscen_b200_graph_free(oscen_b200_graph *g);
+/* text form: inputs with defaults / ranges / ramps, stream + event input names, output, state words per
+   voice, then the launch plan "k: NodeType [node, node]".  Returns the number of launches. */
+int  oscen_b200_graph_describe(const oscen_b200_graph *g, char *dst, size_t cap);
+uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g);
+int  oscen_b200_graph_input_id(const oscen_b200_graph *g, const char *name);          /* >= 0, or OSCEN_B200_E_ARG */
+typedef struct {
+    char     name[64];
+    float    default_value;
+    uint32_t has_range; float range_min, range_max; uint32_t logarithmic;   /* `[min..max, log]` */
+    uint32_t ramp_frames;            /* `ramp: N`: frames set_<v>() ramps over (codegen/mod.rs:917-976); 0 = plain field */
+} oscen_b200_input_info;
+int  oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t input_id, oscen_b200_input_info *out);
+/* G::new() + G::init(sr) for n_voices instances of the compiled graph.  cfg->graph_kind must be
+   OSCEN_B200_GRAPH_CUSTOM and cfg->plan OSCEN_B200_PLAN_NODES.  The graph object may be freed afterwards. */
+int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out);
 
 /* counters: kernels launched by this engine since create; bytes copied H2D / D2H */
 typedef struct {

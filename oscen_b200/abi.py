@@ -16,7 +16,8 @@ EVENT_GATE = 0xFFFFFFFF
  GRAPH_SYNTH_ADSR) = range(7)
 GRAPH_CLIP_REF = 7
 POLICY_SINC, POLICY_SINC_IIR, POLICY_LINEAR, POLICY_LATCH = range(4)
-GRAPH_COUNT = 20
+GRAPH_CUSTOM = 20
+GRAPH_COUNT = 21
 
 
 def graph_clip_os(policy, factor):
@@ -36,6 +37,8 @@ SYMBOLS = [
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
     "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
+    "oscen_b200_graph_compile", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
+    "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
 ]
 
 
@@ -53,6 +56,11 @@ class Event(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "graph_launches", "h2d_bytes", "d2h_bytes",
                                           "blocks", "events_dropped")]
+
+
+class InputInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("default_value", C.c_float), ("has_range", C.c_uint32), ("range_min", C.c_float),
+                ("range_max", C.c_float), ("logarithmic", C.c_uint32), ("ramp_frames", C.c_uint32)]
 
 
 EVENT_DTYPE = np.dtype([("voice", "<u4"), ("frame_offset", "<u4"), ("input_id", "<u4"), ("scalar", "<f4")])
@@ -109,6 +117,15 @@ def load():
     L.oscen_b200_plan_describe.argtypes = [u32, C.c_char_p, C.c_size_t]
     L.oscen_b200_comm_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
     L.oscen_b200_comm_p2p_close.argtypes = [vp]
+    L.oscen_b200_graph_compile.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.oscen_b200_graph_free.argtypes = [vp]
+    L.oscen_b200_graph_free.restype = None
+    L.oscen_b200_graph_describe.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.oscen_b200_graph_n_inputs.argtypes = [vp]
+    L.oscen_b200_graph_n_inputs.restype = u32
+    L.oscen_b200_graph_input_id.argtypes = [vp, C.c_char_p]
+    L.oscen_b200_graph_input_info.argtypes = [vp, u32, C.POINTER(InputInfo)]
+    L.oscen_b200_create_from_graph.argtypes = [vp, C.POINTER(Config), C.POINTER(vp)]
     _lib = L
     return L
 
@@ -117,15 +134,74 @@ class EngineError(RuntimeError):
     pass
 
 
+class GraphCompileError(ValueError):
+    """`line:col: message` from the DSL front end"""
+
+
+class Graph:
+    """A `graph!` description compiled to a node plan (oscen_b200_graph_compile).  Needs no GPU."""
+
+    def __init__(self, dsl_text):
+        self.L = load()
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = self.L.oscen_b200_graph_compile(dsl_text.encode(), C.byref(h), err, len(err))
+        if rc != 0:
+            raise GraphCompileError(err.value.decode())
+        self.h = h
+        self.n_inputs = self.L.oscen_b200_graph_n_inputs(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.oscen_b200_graph_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.oscen_b200_graph_describe(self.h, buf, len(buf))
+        if n < 0:
+            raise EngineError(f"graph_describe rc={n}")
+        return buf.value.decode()
+
+    def launches(self):
+        """the launch plan lines of describe(): ["0: AdsrEnvelope [env3, env2]", ...]"""
+        return [l for l in self.describe().splitlines() if l[:1].isdigit()]
+
+    def input_id(self, name):
+        i = self.L.oscen_b200_graph_input_id(self.h, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def input_info(self, input_id):
+        info = InputInfo()
+        if self.L.oscen_b200_graph_input_info(self.h, input_id, C.byref(info)) != 0:
+            raise KeyError(input_id)
+        return {"name": info.name.decode(), "default": info.default_value,
+                "range": (info.range_min, info.range_max) if info.has_range else None,
+                "log": bool(info.logarithmic), "ramp": info.ramp_frames}
+
+
 class Engine:
     """One engine = one GPU = one shard of voices.  Method names follow the C ABI."""
 
     def __init__(self, graph_kind, n_voices, voices_per_instance=1, sample_rate=48000.0, device=0,
-                 plan=PLAN_FUSED, keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT):
+                 plan=PLAN_FUSED, keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT, graph=None):
         self.L = load()
-        cfg = Config(graph_kind, n_voices, voices_per_instance, sample_rate, device, plan, keep, 0)
         h = C.c_void_p()
-        rc = self.L.oscen_b200_create(C.byref(cfg), C.byref(h))
+        if graph is not None:          # a DSL-compiled graph: always the node plan
+            graph_kind, plan = GRAPH_CUSTOM, PLAN_NODES
+            cfg = Config(graph_kind, n_voices, voices_per_instance, sample_rate, device, plan, keep, 0)
+            rc = self.L.oscen_b200_create_from_graph(graph.h, C.byref(cfg), C.byref(h))
+        else:
+            cfg = Config(graph_kind, n_voices, voices_per_instance, sample_rate, device, plan, keep, 0)
+            rc = self.L.oscen_b200_create(C.byref(cfg), C.byref(h))
         if rc != 0:
             raise EngineError(f"oscen_b200_create rc={rc}: {self.L.oscen_b200_last_error(None).decode()}")
         self.h = h
@@ -133,6 +209,14 @@ class Engine:
         self.n_instances = n_voices // voices_per_instance
         self.channels = self.L.oscen_b200_channels(h)
         self.frames = 0
+
+    @classmethod
+    def from_graph(cls, graph, n_voices, voices_per_instance=1, sample_rate=48000.0, device=0,
+                   keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT):
+        """G::new() + G::init(sample_rate) for n_voices instances of a DSL-compiled graph (text or Graph)"""
+        if isinstance(graph, str):
+            graph = Graph(graph)
+        return cls(GRAPH_CUSTOM, n_voices, voices_per_instance, sample_rate, device, PLAN_NODES, keep, graph=graph)
 
     def close(self):
         if getattr(self, "h", None):

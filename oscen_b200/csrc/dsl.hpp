@@ -1,0 +1,846 @@
+/*
+ * dsl.hpp — front end of the plan compiler: the reference's `graph!` DSL, as text, to a node plan.
+ *
+ * The reference compiles a `graph! { ... }` block at Rust compile time
+ * (oscen-graph-compiler/src/lib.rs:22-34): parse (parse.rs) -> lower to IR with type checks
+ * (ir/lower.rs:351-656) -> dead-node removal (ir/passes/dead_nodes.rs) -> Kahn sort
+ * (ir/lower.rs:1015-1085) -> Rust code that calls every node's process() per frame.  Here the same
+ * text is compiled at run time into a plan::Graph (plan.hpp): one node-kernel launch per node type
+ * per ready wave, streams in HBM, replayed as a CUDA graph (kernel_nodes.cuh).
+ *
+ * Grammar accepted (parse.rs:195-1110): `name: X;`, `input`/`output` declarations in both
+ * spellings (`input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];` and
+ * `input value cutoff = 3000.0;`), `node x = T::ctor(args);` / `nodes { ... }`,
+ * `connection a -> b;` / `connections { ... }`, compound sources with + - * / and parentheses,
+ * f32 methods tanh/abs/clamp/min/max, optional `[policy]` prefixes, an optional surrounding
+ * `graph! { }`.  Semantics kept: kind compatibility (lower.rs:1157-1165: Stream->Stream,
+ * Value->Value, Event->Event, Value->Stream), auto-summing stream fan-in in statement order
+ * (codegen/emit_node.rs:153-174: connect the first source, accumulate the rest), last write wins
+ * on value endpoints, constructor arguments stay on unconnected endpoints, nodes that do not
+ * reach an output are dropped.
+ *
+ * Not compiled to a node plan (reported as errors, never silently ignored): `* N` / `/ N` rates
+ * (multirate graphs run as fused kernels, kernel_resample.cuh), node arrays `[T; N]` (the engine's
+ * voices_per_instance is the array axis), nested graphs, `-> [N] ->` feedback edges, `external`
+ * assets, free-function calls in sources (they name user Rust code).
+ *
+ * Host-only C++, no CUDA types: unit-tested on the CPU through oscen_b200_graph_compile().
+ */
+#pragma once
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "plan.hpp"
+
+namespace oscen {
+namespace dsl {
+
+/* ------------------------------------------------------------------------------ lexer -- */
+struct Tok {
+    enum Kind { Ident, Num, Str, Punct, End } kind = End;
+    std::string s;
+    float num = 0.0f;
+    bool is_int = false;
+    int line = 1, col = 1;
+};
+
+struct Error {
+    std::string msg;
+    int line = 0, col = 0;
+    bool set = false;
+    void at(const Tok &t, const std::string &m) { if (!set) { set = true; msg = m; line = t.line; col = t.col; } }
+    std::string text() const { return std::to_string(line) + ":" + std::to_string(col) + ": " + msg; }
+};
+
+inline bool lex(const char *src, std::vector<Tok> &out, Error &err) {
+    int line = 1, col = 1;
+    const char *p = src;
+    auto adv = [&](int n) { for (int i = 0; i < n; ++i) { if (*p == '\n') { ++line; col = 1; } else ++col; ++p; } };
+    while (*p) {
+        if (isspace((unsigned char)*p)) { adv(1); continue; }
+        if (p[0] == '/' && p[1] == '/') { while (*p && *p != '\n') adv(1); continue; }
+        if (p[0] == '/' && p[1] == '*') {
+            Tok t; t.line = line; t.col = col;
+            adv(2);
+            while (*p && !(p[0] == '*' && p[1] == '/')) adv(1);
+            if (!*p) { err.at(t, "unterminated block comment"); return false; }
+            adv(2); continue;
+        }
+        Tok t; t.line = line; t.col = col;
+        if (isalpha((unsigned char)*p) || *p == '_') {
+            const char *q = p;
+            while (isalnum((unsigned char)*q) || *q == '_') ++q;
+            t.kind = Tok::Ident; t.s.assign(p, q); adv((int)(q - p));
+        } else if (isdigit((unsigned char)*p)) {
+            /* Rust numeric literal: digits with `_`, optional fraction, exponent, type suffix.
+               `20.0..20000.0` must not swallow the range dots. */
+            const char *q = p;
+            std::string txt;
+            bool is_int = true;
+            auto digits = [&]() { while (isdigit((unsigned char)*q) || *q == '_') { if (*q != '_') txt += *q; ++q; } };
+            digits();
+            if (q[0] == '.' && q[1] != '.' && !(isalpha((unsigned char)q[1]) || q[1] == '_')) { is_int = false; txt += '.'; ++q; digits(); }
+            if ((*q == 'e' || *q == 'E') && (isdigit((unsigned char)q[1]) || ((q[1] == '+' || q[1] == '-') && isdigit((unsigned char)q[2])))) {
+                is_int = false; txt += *q++; if (*q == '+' || *q == '-') txt += *q++; digits();
+            }
+            if (!strncmp(q, "f32", 3) || !strncmp(q, "f64", 3)) { is_int = false; q += 3; }
+            else if (!strncmp(q, "usize", 5)) q += 5;
+            else if (!strncmp(q, "u32", 3) || !strncmp(q, "i32", 3) || !strncmp(q, "u64", 3) || !strncmp(q, "i64", 3)) q += 3;
+            t.kind = Tok::Num; t.s = txt; t.is_int = is_int;
+            t.num = strtof(txt.c_str(), nullptr);        /* decimal -> nearest f32, as rustc rounds an f32 literal */
+            adv((int)(q - p));
+        } else if (*p == '"') {
+            const char *q = p + 1;
+            while (*q && *q != '"') { if (*q == '\\' && q[1]) ++q; ++q; }
+            if (!*q) { err.at(t, "unterminated string literal"); return false; }
+            t.kind = Tok::Str; t.s.assign(p + 1, q); adv((int)(q - p) + 1);
+        } else {
+            t.kind = Tok::Punct;
+            if ((p[0] == '-' && p[1] == '>') || (p[0] == ':' && p[1] == ':') || (p[0] == '.' && p[1] == '.')) { t.s.assign(p, 2); adv(2); }
+            else if (strchr("{}[]();:,=-+*/.<>!", *p)) { t.s.assign(p, 1); adv(1); }
+            else { err.at(t, std::string("unexpected character `") + *p + "`"); return false; }
+        }
+        out.push_back(t);
+    }
+    Tok e; e.kind = Tok::End; e.line = line; e.col = col; out.push_back(e);
+    return true;
+}
+
+/* -------------------------------------------------------------------------------- AST -- */
+enum class Kind { Stream, Value, Event, Asset };
+inline const char *kind_name(Kind k) { return k == Kind::Stream ? "Stream" : k == Kind::Value ? "Value" : k == Kind::Event ? "Event" : "Asset"; }
+
+struct Expr {
+    enum K { Ident, Field, Method, Binary, Literal, Call } k = Ident;
+    std::string name;                      /* Ident: name; Field: field; Method: method; Call: function path */
+    std::unique_ptr<Expr> a, b;            /* Field/Method: a = receiver; Binary: a (op) b */
+    char op = 0;
+    float lit = 0.0f;
+    std::vector<float> args;               /* Method: literal arguments */
+    Tok at;
+};
+using ExprP = std::unique_ptr<Expr>;
+
+struct InputDecl { Kind kind; std::string name; bool has_def = false; float def = 0.0f; plan::ValueInput spec; Tok at; };
+struct OutputDecl { Kind kind; std::string name; Tok at; };
+struct NodeDecl { std::string name, type, ctor; std::vector<float> args; bool args_ok = true; int array = 0; int rate = 0; Tok at; };
+struct Conn { std::string policy; ExprP src, dst; int via = 0; /* 0 none, 1 samples, 2 node */ Tok at; };
+struct Ast {
+    std::string name;
+    std::vector<InputDecl> inputs;
+    std::vector<OutputDecl> outputs;
+    std::vector<NodeDecl> nodes;
+    std::vector<Conn> conns;
+};
+
+/* ----------------------------------------------------------------------------- parser -- */
+class Parser {
+public:
+    Parser(const std::vector<Tok> &t, Error &e) : toks(t), err(e) {}
+
+    bool parse(Ast &ast) {
+        /* optional `graph! { ... }` wrapper, so a macro invocation can be pasted as is */
+        bool wrapped = false;
+        if (is_ident("graph") && peek(1).kind == Tok::Punct && peek(1).s == "!" && peek(2).s == "{") { pos += 3; wrapped = true; }
+        while (!err.set && cur().kind != Tok::End && !(wrapped && is_punct("}"))) item(ast);
+        if (!err.set && wrapped) expect("}");
+        if (!err.set && cur().kind != Tok::End) err.at(cur(), "unexpected tokens after the graph body");
+        return !err.set;
+    }
+
+private:
+    const std::vector<Tok> &toks;
+    Error &err;
+    size_t pos = 0;
+
+    const Tok &cur() const { return toks[pos]; }
+    const Tok &peek(size_t n) const { return toks[std::min(pos + n, toks.size() - 1)]; }
+    bool is_punct(const char *s) const { return cur().kind == Tok::Punct && cur().s == s; }
+    bool is_ident(const char *s) const { return cur().kind == Tok::Ident && cur().s == s; }
+    bool accept(const char *s) { if (is_punct(s)) { ++pos; return true; } return false; }
+    bool expect(const char *s) {
+        if (accept(s)) return true;
+        err.at(cur(), std::string("expected `") + s + "`" + (cur().kind == Tok::End ? " before the end of the graph" : ", found `" + cur().s + "`"));
+        return false;
+    }
+    bool ident(std::string &out, const char *what) {
+        if (cur().kind != Tok::Ident) { err.at(cur(), std::string("expected ") + what); return false; }
+        out = cur().s; ++pos; return true;
+    }
+    bool endpoint_kind(const std::string &s, Kind &k) {
+        if (s == "stream") k = Kind::Stream; else if (s == "value") k = Kind::Value;
+        else if (s == "event") k = Kind::Event; else if (s == "asset") k = Kind::Asset; else return false;
+        return true;
+    }
+    /* skip a balanced token run up to (not including) a top-level `;` — type annotations etc. */
+    void skip_to_semicolon() {
+        int depth = 0;
+        while (cur().kind != Tok::End) {
+            if (cur().kind == Tok::Punct) {
+                if (cur().s == "{" || cur().s == "[" || cur().s == "(") ++depth;
+                else if (cur().s == "}" || cur().s == "]" || cur().s == ")") --depth;
+                else if (cur().s == ";" && depth <= 0) return;
+            }
+            ++pos;
+        }
+    }
+    bool number(float &v) {
+        bool neg = false;
+        if (is_punct("-")) { neg = true; ++pos; }
+        if (cur().kind != Tok::Num) { err.at(cur(), "expected a numeric literal"); return false; }
+        v = neg ? -cur().num : cur().num; ++pos;
+        return true;
+    }
+
+    void item(Ast &ast) {
+        const Tok t = cur();
+        if (t.kind != Tok::Ident) { err.at(t, "expected `input`, `output`, `node`, `nodes`, `connection` or `connections`"); return; }
+        if (t.s == "name" && peek(1).kind == Tok::Punct && peek(1).s == ":") {
+            pos += 2;
+            if (!ast.inputs.empty() || !ast.outputs.empty() || !ast.nodes.empty() || !ast.conns.empty() || !ast.name.empty()) {
+                err.at(t, "`name:` must be the first item of the graph"); return;
+            }
+            if (ident(ast.name, "the graph name")) expect(";");
+        } else if (t.s == "nih_params") { ++pos; expect(";");
+        } else if (t.s == "input") { ++pos; input_decl(ast);
+        } else if (t.s == "output") { ++pos; output_decl(ast);
+        } else if (t.s == "external") { err.at(t, "`external` asset slots are not supported by the node plan");
+        } else if (t.s == "node" || t.s == "nodes") {
+            ++pos;
+            if (accept("{")) { while (!err.set && !is_punct("}") && cur().kind != Tok::End) { if (accept(";")) continue; node_decl(ast); } expect("}"); }
+            else node_decl(ast);
+        } else if (t.s == "connection" || t.s == "connections") {
+            ++pos;
+            if (accept("{")) { while (!err.set && !is_punct("}") && cur().kind != Tok::End) { if (accept(";")) continue; conn_stmt(ast); } expect("}"); }
+            else conn_stmt(ast);
+        } else err.at(t, "unknown graph item `" + t.s + "`");
+    }
+
+    /* parse.rs:386-445 */
+    void input_decl(Ast &ast) {
+        InputDecl d; d.at = cur();
+        std::string first;
+        if (!ident(first, "an input name or endpoint kind")) return;
+        if (accept(":")) {
+            std::string k;
+            if (!ident(k, "an endpoint kind (stream, value, event)")) return;
+            if (!endpoint_kind(k, d.kind)) { err.at(d.at, "unknown endpoint kind `" + k + "`"); return; }
+            d.name = first;
+        } else {
+            if (!endpoint_kind(first, d.kind)) { err.at(d.at, "unknown endpoint kind `" + first + "`"); return; }
+            if (!ident(d.name, "an input name")) return;
+        }
+        if (accept(":")) {                                   /* `: Type` annotation (array / frame payloads) */
+            err.at(cur(), "typed endpoints (`: [f32; N]`, `: Frame<N>`) are not supported by the node plan: streams are mono f32");
+            return;
+        }
+        if (accept("=")) {
+            if (!number(d.def)) return;
+            d.has_def = true;
+            if (is_punct("[") || is_punct("{")) param_spec(d.spec);
+        }
+        d.spec.name = d.name; d.spec.def = d.def;
+        if (expect(";")) ast.inputs.push_back(std::move(d));
+    }
+    /* `[min..max, log, ramp: N]` (ast.rs:175-187) or the brace form `{ range: a..b, unit: " Hz", ... }` (parse.rs:299-384);
+       range / curve / ramp are kept, the NIH-plug display fields are skipped */
+    void param_spec(plan::ValueInput &s) {
+        const bool brace = is_punct("{");
+        ++pos;
+        const char *close = brace ? "}" : "]";
+        while (!err.set && !is_punct(close) && cur().kind != Tok::End) {
+            if (cur().kind == Tok::Num || is_punct("-")) {
+                float lo, hi;
+                if (!number(lo) || !expect("..") || !number(hi)) return;
+                s.has_range = true; s.lo = lo; s.hi = hi;
+            } else if (cur().kind == Tok::Ident) {
+                const std::string key = cur().s; ++pos;
+                if (key == "log") s.log = true;
+                else if (key == "linear") s.log = false;
+                else if (key == "range" && accept(":")) {
+                    float lo, hi;
+                    if (!number(lo) || !expect("..") || !number(hi)) return;
+                    s.has_range = true; s.lo = lo; s.hi = hi;
+                } else if (key == "ramp" && accept(":")) {
+                    if (cur().kind != Tok::Num || !cur().is_int) { err.at(cur(), "`ramp:` expects a frame count"); return; }
+                    s.ramp = (uint32_t)strtoul(cur().s.c_str(), nullptr, 10); ++pos;
+                } else if (accept(":")) {                    /* center / unit / smoother / step / name / group */
+                    if (cur().kind == Tok::Str) ++pos; else { float v; if (!number(v)) return; }
+                } else { err.at(cur(), "unknown parameter-spec entry `" + key + "`"); return; }
+            } else { err.at(cur(), "malformed parameter spec"); return; }
+            if (!accept(",")) break;
+        }
+        expect(close);
+    }
+    /* parse.rs:640-672 */
+    void output_decl(Ast &ast) {
+        OutputDecl d; d.at = cur();
+        std::string first;
+        if (!ident(first, "an output name or endpoint kind")) return;
+        if (accept(":")) {
+            std::string k;
+            if (!ident(k, "an endpoint kind (stream, value, event)")) return;
+            if (!endpoint_kind(k, d.kind)) { err.at(d.at, "unknown endpoint kind `" + k + "`"); return; }
+            d.name = first;
+        } else {
+            if (!endpoint_kind(first, d.kind)) { err.at(d.at, "unknown endpoint kind `" + first + "`"); return; }
+            if (!ident(d.name, "an output name")) return;
+        }
+        if (accept(":")) { err.at(cur(), "typed endpoints (`: [f32; N]`, `: Frame<N>`) are not supported by the node plan: streams are mono f32"); return; }
+        if (expect(";")) ast.outputs.push_back(std::move(d));
+    }
+    /* `<name> = <constructor> [* N | / N];` (parse.rs:679-710); constructor = `Type::method(args)`,
+       `Type<G>::method(args)` or the array form `[ctor; N]` */
+    void node_decl(Ast &ast) {
+        NodeDecl d; d.at = cur();
+        if (!ident(d.name, "a node name") || !expect("=")) return;
+        const bool array = accept("[");
+        std::string seg;
+        if (!ident(seg, "a node constructor (`Type::new(...)`)")) return;
+        std::vector<std::string> path{seg};
+        for (;;) {
+            if (is_punct("<")) {                             /* generic arguments: kept out of the type name */
+                int depth = 0;
+                do { if (is_punct("<")) ++depth; else if (is_punct(">")) --depth; ++pos; } while (depth > 0 && cur().kind != Tok::End);
+            }
+            if (!accept("::")) break;
+            if (is_punct("<")) continue;                     /* turbofish */
+            if (!ident(seg, "a path segment")) return;
+            path.push_back(seg);
+        }
+        if (path.size() < 2) { err.at(d.at, "node constructor must be `Type::method(...)`"); return; }
+        d.ctor = path.back(); d.type = path[path.size() - 2];
+        if (!expect("(")) return;
+        while (!err.set && !is_punct(")") && cur().kind != Tok::End) {
+            float v;
+            if (cur().kind == Tok::Num || is_punct("-")) { if (!number(v)) return; d.args.push_back(v); }
+            else { d.args_ok = false; int depth = 0;            /* a non-literal argument: reported when the node is lowered */
+                   while (cur().kind != Tok::End && !(depth == 0 && (is_punct(",") || is_punct(")")))) {
+                       if (is_punct("(") || is_punct("[")) ++depth; else if (is_punct(")") || is_punct("]")) --depth; ++pos; } }
+            if (!accept(",")) break;
+        }
+        if (!expect(")")) return;
+        if (array) {
+            if (!expect(";")) return;
+            if (cur().kind != Tok::Num || !cur().is_int) { err.at(cur(), "array size must be an integer literal"); return; }
+            d.array = (int)strtol(cur().s.c_str(), nullptr, 10); ++pos;
+            if (!expect("]")) return;
+        }
+        if (is_punct("*") || is_punct("/")) {                /* parse.rs:460-488: power-of-two rate factor */
+            const bool up = is_punct("*"); ++pos;
+            if (cur().kind != Tok::Num || !cur().is_int) { err.at(cur(), "rate factor must be an integer literal in {1, 2, 4, 8}"); return; }
+            const int n = (int)strtol(cur().s.c_str(), nullptr, 10);
+            if (n != 1 && n != 2 && n != 4 && n != 8) { err.at(cur(), "rate factor must be in {1, 2, 4, 8}"); return; }
+            ++pos;
+            d.rate = n == 1 ? 0 : (up ? n : -n);
+        }
+        if (expect(";")) ast.nodes.push_back(std::move(d));
+    }
+    /* `[<policy>] <source> -> <dest>;` or `<source> -> [N | name] -> <dest>;` (parse.rs:931-980) */
+    void conn_stmt(Ast &ast) {
+        Conn c; c.at = cur();
+        if (is_punct("[")) {
+            ++pos;
+            if (!ident(c.policy, "a connection policy (latch, linear, sinc, sinc_iir)")) return;
+            if (c.policy != "latch" && c.policy != "linear" && c.policy != "sinc" && c.policy != "sinc_iir") { err.at(c.at, "unknown connection policy `" + c.policy + "`"); return; }
+            if (!expect("]")) return;
+        }
+        c.src = additive();
+        if (err.set || !expect("->")) return;
+        if (is_punct("[")) {
+            ++pos;
+            if (cur().kind == Tok::Num) c.via = 1; else if (cur().kind == Tok::Ident) c.via = 2;
+            else { err.at(cur(), "expected a sample count or a node name inside `-> [ ] ->`"); return; }
+            ++pos;
+            if (!expect("]") || !expect("->")) return;
+        }
+        c.dst = additive();
+        if (err.set) return;
+        if (expect(";")) ast.conns.push_back(std::move(c));
+    }
+    /* parse.rs:989-1029: + - below * /, left associative; a `-` that starts `->` ends the expression */
+    ExprP additive() {
+        ExprP l = multiplicative();
+        while (!err.set && (is_punct("+") || is_punct("-"))) {
+            ExprP e(new Expr); e->k = Expr::Binary; e->op = cur().s[0]; e->at = cur(); ++pos;
+            e->a = std::move(l); e->b = multiplicative(); l = std::move(e);
+        }
+        return l;
+    }
+    ExprP multiplicative() {
+        ExprP l = primary();
+        while (!err.set && (is_punct("*") || is_punct("/"))) {
+            ExprP e(new Expr); e->k = Expr::Binary; e->op = cur().s[0]; e->at = cur(); ++pos;
+            e->a = std::move(l); e->b = primary(); l = std::move(e);
+        }
+        return l;
+    }
+    ExprP primary() {
+        ExprP e(new Expr); e->at = cur();
+        if (accept("(")) { e = additive(); expect(")"); return postfix(std::move(e)); }
+        if (cur().kind == Tok::Num) { e->k = Expr::Literal; e->lit = cur().num; ++pos; return e; }
+        if (cur().kind != Tok::Ident) { err.at(cur(), "expected a connection endpoint or expression"); return e; }
+        std::string path = cur().s; ++pos;
+        bool multi = false;
+        while (is_punct("::")) {
+            ++pos; multi = true;
+            if (is_punct("<")) { int depth = 0; do { if (is_punct("<")) ++depth; else if (is_punct(">")) --depth; ++pos; } while (depth > 0 && cur().kind != Tok::End); continue; }
+            std::string seg; if (!ident(seg, "a path segment")) return e;
+            path += "::" + seg;
+        }
+        if (is_punct("(")) {                                 /* free-function call: names user Rust code */
+            e->k = Expr::Call; e->name = path;
+            int depth = 0;
+            do { if (is_punct("(")) ++depth; else if (is_punct(")")) --depth; ++pos; } while (depth > 0 && cur().kind != Tok::End);
+            return e;
+        }
+        if (multi) { err.at(e->at, "`" + path + "` is not an endpoint (endpoints are `node.field`)"); return e; }
+        e->k = Expr::Ident; e->name = path;
+        return postfix(std::move(e));
+    }
+    ExprP postfix(ExprP e) {
+        for (;;) {
+            if (is_punct("[")) { err.at(cur(), "array-indexed endpoints (`voices[i]`) are not supported by the node plan"); return e; }
+            if (!is_punct(".")) return e;
+            ++pos;
+            ExprP f(new Expr); f->at = cur();
+            if (!ident(f->name, "a field or method name")) return e;
+            f->a = std::move(e);
+            if (accept("(")) {
+                f->k = Expr::Method;
+                while (!err.set && !is_punct(")") && cur().kind != Tok::End) { float v; if (!number(v)) return f; f->args.push_back(v); if (!accept(",")) break; }
+                expect(")");
+            } else f->k = Expr::Field;
+            e = std::move(f);
+        }
+    }
+};
+
+/* -------------------------------------------------------------------- node registry -- */
+struct Endpoint { const char *name; Kind kind; bool is_out; int slot; /* in: stream index or value slot; out: port */ int standin; float def; };
+struct TypeInfo {
+    const char *type;
+    std::vector<Endpoint> eps;
+    bool stateful;
+};
+
+/* endpoints as the reference structs declare them (#[input(..)] / #[output(..)] fields):
+   oscen-lib/src/{envelope/adsr.rs:20-38, filters/tpt/mod.rs:12-24, oscillators/mod.rs:88-103, gain/mod.rs:5-12},
+   examples/fm-synth/src/nodes/{fm_operator.rs:12-31, crossfade.rs:8-18, mixer.rs:4-12, add_value.rs:5-13},
+   examples/nih-twin-peaks/src/lp18_filter.rs:7-42, examples/oversampled-saturator/src/main.rs:31-38.
+   `standin` = parameter slot read when a stream input has no stream source; `def` = the field's constructor default. */
+inline const TypeInfo *type_info(const std::string &type) {
+    static const std::vector<TypeInfo> reg = {
+        {"AdsrEnvelope", {{"gate", Kind::Event, false, 0, -1, 0}, {"attack", Kind::Value, false, 0, -1, 0}, {"decay", Kind::Value, false, 1, -1, 0},
+                          {"sustain", Kind::Value, false, 2, -1, 0}, {"release", Kind::Value, false, 3, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"FmOperator", {{"base_freq", Kind::Value, false, 0, -1, 440.0f}, {"ratio", Kind::Value, false, 1, -1, 1.0f}, {"feedback", Kind::Value, false, 2, -1, 0},
+                        {"level", Kind::Value, false, 3, -1, 1.0f}, {"phase_mod", Kind::Stream, false, 0, 4, 0}, {"envelope", Kind::Stream, false, 1, 5, 1.0f},
+                        {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"TptFilter", {{"q", Kind::Value, false, 0, -1, 0}, {"input", Kind::Stream, false, 0, 3, 0}, {"cutoff", Kind::Stream, false, 1, 1, 0},
+                       {"f_mod", Kind::Stream, false, 2, 2, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"PolyBlepOscillator", {{"frequency", Kind::Value, false, 0, -1, 0}, {"amplitude", Kind::Value, false, 1, -1, 0}, {"pulse_width", Kind::Value, false, 2, -1, 0.5f},
+                                {"frequency_mod", Kind::Stream, false, 0, 3, 0}, {"phase_mod", Kind::Stream, false, 1, 4, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"LP18Filter", {{"cutoff", Kind::Value, false, 0, -1, 0}, {"resonance", Kind::Value, false, 1, -1, 0}, {"fmod", Kind::Value, false, 2, -1, 0},
+                        {"input", Kind::Stream, false, 0, 3, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"Gain", {{"input", Kind::Stream, false, 0, -1, 0}, {"gain", Kind::Stream, false, 1, 0, 1.0f}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
+        {"AddValue", {{"input", Kind::Stream, false, 0, -1, 0}, {"value", Kind::Value, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
+        {"Mixer", {{"input_a", Kind::Stream, false, 0, -1, 0}, {"input_b", Kind::Stream, false, 1, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
+        {"Crossfade", {{"input", Kind::Stream, false, 0, -1, 0}, {"mix", Kind::Value, false, 0, -1, 0}, {"output_a", Kind::Stream, true, 0, -1, 0},
+                       {"output_b", Kind::Stream, true, 1, -1, 0}}, false},
+        {"HardClip", {{"input", Kind::Stream, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
+    };
+    for (const TypeInfo &t : reg) if (type == t.type) return &t;
+    return nullptr;
+}
+
+/* --------------------------------------------------------------------------- lowering -- */
+struct Operand {
+    enum K { None, Stream, Value, Const } k = None;
+    plan::StreamRef s;
+    uint32_t pid = plan::kNoValue;
+    float c = 0.0f;
+    Kind kind() const { return k == Stream ? Kind::Stream : Kind::Value; }
+};
+
+class Lowering {
+public:
+    Lowering(const Ast &a, plan::Graph &out, Error &e) : ast(a), g(out), err(e) {}
+
+    bool run() {
+        g = plan::Graph();
+        g.name = ast.name;
+        /* ---- graph endpoints */
+        for (const InputDecl &d : ast.inputs) {
+            if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
+            names[d.name] = 'i';
+            switch (d.kind) {
+            case Kind::Value:
+                if (g.inputs.size() >= 28) { err.at(d.at, "more than 28 value inputs (OSCEN_B200_MAX_INPUTS)"); return false; }
+                value_id[d.name] = (uint32_t)g.inputs.size(); g.inputs.push_back(d.spec); break;
+            case Kind::Stream:
+                if (!g.stream_input.empty()) { err.at(d.at, "the node plan takes one stream input per graph (`" + g.stream_input + "` is already declared)"); return false; }
+                g.stream_input = d.name; break;
+            case Kind::Event:
+                if (!g.event_input.empty()) { err.at(d.at, "the node plan takes one event input per graph (`" + g.event_input + "` is already declared)"); return false; }
+                g.event_input = d.name; break;
+            default: err.at(d.at, "asset inputs are not supported by the node plan"); return false;
+            }
+        }
+        for (const OutputDecl &d : ast.outputs) {
+            if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
+            if (d.kind != Kind::Stream) { err.at(d.at, std::string("the node plan renders stream outputs only (`") + d.name + "` is " + kind_name(d.kind) + ")"); return false; }
+            if (!g.output_name.empty()) { err.at(d.at, "the node plan renders one stream output per graph (`" + g.output_name + "` is already declared)"); return false; }
+            names[d.name] = 'o'; g.output_name = d.name;
+        }
+        if (g.output_name.empty()) { Tok t; err.at(t, "graph declares no stream output"); return false; }
+        /* ---- nodes */
+        for (const NodeDecl &d : ast.nodes) if (!node(d)) return false;
+        /* ---- connections, in statement order */
+        in_terms.assign(g.nodes.size(), std::vector<std::vector<Operand>>(plan::kMaxStreamIn));
+        for (const Conn &c : ast.conns) if (!connection(c)) return false;
+        /* ---- fan-in: one source = plain copy, more = connect the first, accumulate the rest */
+        const size_t n_decl = ast.nodes.size();              /* synthesised expression nodes follow the declared ones */
+        for (size_t i = 0; i < n_decl; ++i)
+            for (int k = 0; k < plan::kMaxStreamIn; ++k) if (!in_terms[i][k].empty() && !bind_stream_input((int)i, k)) return false;
+        /* stateless nodes read their stream inputs unconditionally: an unconnected one holds its constructor default */
+        for (size_t i = 0; i < n_decl; ++i) {
+            if (info[i]->stateful) continue;
+            for (const Endpoint &ep : info[i]->eps) {
+                if (ep.is_out || ep.kind != Kind::Stream || ep.standin >= 0 || g.nodes[i].in[ep.slot].node != plan::kNone) continue;
+                Operand c; c.k = Operand::Const; c.c = ep.def;
+                const plan::StreamRef r = materialise(c, g.nodes[i].name + "." + ep.name + " (unconnected)").s;
+                g.nodes[i].in[ep.slot] = r;
+            }
+        }
+        if (out_terms.empty()) { Tok t; err.at(t, "nothing is connected to the output `" + g.output_name + "`"); return false; }
+        Operand o = sum_terms(out_terms, g.output_name);
+        if (o.k != Operand::Stream || o.s.node < 0) o = materialise(o, g.output_name);   /* a bare value / graph input copied to the output */
+        g.output = o.s;
+        if (!drop_dead_nodes()) return false;
+        /* ---- SoA state layout: nodes in declaration order */
+        uint32_t base = 0;
+        for (plan::Node &nd : g.nodes) { nd.state_base = base; base += plan::n_state_words(nd.type); }
+        g.n_state = base;
+        return !err.set;
+    }
+
+private:
+    const Ast &ast;
+    plan::Graph &g;
+    Error &err;
+    std::map<std::string, char> names;                 /* 'i' input, 'o' output, 'n' node */
+    std::map<std::string, uint32_t> value_id;
+    std::map<std::string, int> node_id;
+    std::vector<const TypeInfo *> info;                /* per plan node (nullptr for synthesised nodes) */
+    std::vector<std::vector<std::vector<Operand>>> in_terms;   /* [node][stream input] -> sources in statement order */
+    std::vector<Operand> out_terms;
+
+    bool node(const NodeDecl &d) {
+        if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
+        if (d.array) { err.at(d.at, "node arrays (`[T; N]`) are not compiled to a node plan: the engine's voices_per_instance is the array axis"); return false; }
+        if (d.rate) { err.at(d.at, "`* N` / `/ N` node rates are not compiled to a node plan (multirate graphs run as fused kernels)"); return false; }
+        const TypeInfo *ti = type_info(d.type);
+        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (the node plan has kernels for AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, LP18Filter, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
+        if (!d.args_ok) { err.at(d.at, "constructor arguments of `" + d.name + "` must be numeric literals"); return false; }
+        plan::Node n{};
+        n.name = d.name; n.gate = false;
+        for (int k = 0; k < plan::kMaxParams; ++k) { n.pid[k] = plan::kNoValue; n.cst[k] = 0.0f; }
+        for (const Endpoint &ep : ti->eps) if (!ep.is_out && ep.kind != Kind::Event) {
+            const int slot = ep.kind == Kind::Value ? ep.slot : ep.standin;
+            if (slot >= 0) n.cst[slot] = ep.def;
+        }
+        auto ctor = [&](const char *name, size_t n_args) {
+            if (d.ctor != name) return false;
+            if (d.args.size() != n_args) err.at(d.at, d.type + "::" + name + " takes " + std::to_string(n_args) + " argument(s), found " + std::to_string(d.args.size()));
+            return true;
+        };
+        const std::string &t = d.type;
+        bool ok = false;
+        if (t == "AdsrEnvelope") { n.type = plan::NodeType::Adsr; if ((ok = ctor("new", 4)) && !err.set) for (int k = 0; k < 4; ++k) n.cst[k] = d.args[k]; }
+        else if (t == "FmOperator") { n.type = plan::NodeType::FmOperator; ok = ctor("new", 0); }
+        else if (t == "TptFilter") {
+            n.type = plan::NodeType::Tpt;
+            if ((ok = ctor("new", 2)) && !err.set) { n.cst[1] = d.args[0]; n.cst[0] = d.args[1]; n.init[0] = d.args[0]; n.init[1] = d.args[1]; }
+        } else if (t == "PolyBlepOscillator") {
+            struct { const char *c; plan::NodeType nt; } waves[] = {{"sine", plan::NodeType::PolyBlepSine}, {"saw", plan::NodeType::PolyBlepSaw},
+                                                                  {"square", plan::NodeType::PolyBlepSquare}, {"triangle", plan::NodeType::PolyBlepTriangle}};
+            for (auto &w : waves) if (d.ctor == w.c) { n.type = w.nt; ok = ctor(w.c, 2); }
+            if (ok && !err.set) { n.cst[0] = d.args[0]; n.cst[1] = d.args[1]; }
+        } else if (t == "LP18Filter") {
+            n.type = plan::NodeType::Lp18;
+            if ((ok = ctor("new", 2)) && !err.set) {
+                float r = d.args[1]; if (r < 0.0f) r = 0.0f; if (r > 0.99f) r = 0.99f;     /* LP18Filter::new clamps the field, not last_resonance */
+                n.cst[0] = d.args[0]; n.cst[1] = r; n.init[0] = d.args[0]; n.init[1] = d.args[1];
+            }
+        } else if (t == "Gain") { n.type = plan::NodeType::Gain; if ((ok = ctor("new", 1)) && !err.set) n.cst[0] = d.args[0]; }
+        else if (t == "AddValue") { n.type = plan::NodeType::AddValue; if ((ok = ctor("new", 1)) && !err.set) n.cst[0] = d.args[0]; }
+        else if (t == "Mixer") { n.type = plan::NodeType::Mixer; ok = ctor("new", 0); }
+        else if (t == "Crossfade") { n.type = plan::NodeType::Crossfade; ok = ctor("new", 0); }
+        else if (t == "HardClip") { n.type = plan::NodeType::HardClip; ok = ctor("new", 0); }
+        if (err.set) return false;
+        if (!ok) { err.at(d.at, "unknown constructor `" + d.type + "::" + d.ctor + "`"); return false; }
+        names[d.name] = 'n'; node_id[d.name] = (int)g.nodes.size();
+        g.nodes.push_back(n); info.push_back(ti);
+        return true;
+    }
+
+    const Endpoint *find_ep(int node, const std::string &name) const {
+        for (const Endpoint &ep : info[node]->eps) if (name == ep.name) return &ep;
+        return nullptr;
+    }
+    int add_synth(plan::Node n) {
+        g.nodes.push_back(n); info.push_back(nullptr);
+        if (in_terms.size() < g.nodes.size()) in_terms.resize(g.nodes.size(), std::vector<std::vector<Operand>>(plan::kMaxStreamIn));
+        return (int)g.nodes.size() - 1;
+    }
+    plan::Node blank(const std::string &name, plan::NodeType t, plan::ExprOp op) {
+        plan::Node n{};
+        n.name = name; n.type = t; n.op = op; n.gate = false;
+        for (int k = 0; k < plan::kMaxParams; ++k) { n.pid[k] = plan::kNoValue; n.cst[k] = 0.0f; }
+        return n;
+    }
+    static Operand stream_of(int node, int port = 0) { Operand o; o.k = Operand::Stream; o.s.node = node; o.s.port = port; return o; }
+
+    /* a value (graph input or literal) read as a stream: one broadcast per frame */
+    Operand materialise(const Operand &v, const std::string &label) {
+        if (v.k == Operand::Stream && v.s.node >= 0) return v;
+        plan::Node n = blank(label, plan::NodeType::Expr, plan::ExprOp::Value);
+        if (v.k == Operand::Stream) {                        /* the graph's stream input copied through: x + 0 would change -0.0, so copy = x * 1 */
+            n.op = plan::ExprOp::MulSV; n.in[0] = v.s; n.cst[0] = 1.0f;
+        } else if (v.k == Operand::Value) n.pid[0] = v.pid; else n.cst[0] = v.c;
+        return stream_of(add_synth(n));
+    }
+    Operand binary(char op, const Operand &l, const Operand &r, const std::string &label, const Tok &at) {
+        using O = plan::ExprOp;
+        const bool ls = l.k == Operand::Stream, rs = r.k == Operand::Stream;
+        if (!ls && !rs) {
+            if (l.k == Operand::Const && r.k == Operand::Const) {     /* literal (op) literal: one f32 operation, folded */
+                Operand o; o.k = Operand::Const;
+                o.c = op == '+' ? l.c + r.c : op == '-' ? l.c - r.c : op == '*' ? l.c * r.c : l.c / r.c;
+                return o;
+            }
+            return binary(op, materialise(l, label + " (lhs)"), r, label, at);
+        }
+        plan::Node n = blank(label, plan::NodeType::Expr, O::None);
+        if (ls && rs) {
+            n.op = op == '+' ? O::AddSS : op == '-' ? O::SubSS : op == '*' ? O::MulSS : O::DivSS;
+            n.in[0] = l.s; n.in[1] = r.s;
+        } else {
+            const Operand &s = ls ? l : r, &v = ls ? r : l;
+            /* a + v == v + a and a * v == v * a bit for bit; - and / keep their operand order */
+            if (op == '+') n.op = O::AddSV; else if (op == '*') n.op = O::MulSV;
+            else if (op == '-') n.op = ls ? O::SubSV : O::SubVS; else n.op = ls ? O::DivSV : O::DivVS;
+            n.in[0] = s.s;
+            if (v.k == Operand::Value) n.pid[0] = v.pid; else n.cst[0] = v.c;
+        }
+        (void)at;
+        return stream_of(add_synth(n));
+    }
+    std::string text_of(const Expr &e) const {
+        switch (e.k) {
+        case Expr::Ident: return e.name;
+        case Expr::Field: return text_of(*e.a) + "." + e.name;
+        case Expr::Method: { std::string s = text_of(*e.a) + "." + e.name + "(";
+            for (size_t i = 0; i < e.args.size(); ++i) { if (i) s += ", "; char b[32]; snprintf(b, sizeof b, "%g", (double)e.args[i]); s += b; }
+            return s + ")"; }
+        case Expr::Binary: return text_of(*e.a) + " " + e.op + " " + text_of(*e.b);
+        case Expr::Literal: { char b[32]; snprintf(b, sizeof b, "%g", (double)e.lit); return b; }
+        default: return e.name + "(..)";
+        }
+    }
+    /* source expression -> operand (lower.rs:1182-: lower_expr; kinds per endpoint_kind_of, lower.rs:937-959) */
+    bool source(const Expr &e, Operand &out, bool &is_event) {
+        is_event = false;
+        switch (e.k) {
+        case Expr::Literal: out.k = Operand::Const; out.c = e.lit; return true;
+        case Expr::Ident: {
+            auto it = names.find(e.name);
+            if (it == names.end()) { err.at(e.at, "cannot resolve the source of this connection (unknown node or endpoint name `" + e.name + "`?)"); return false; }
+            if (it->second == 'o') { err.at(e.at, "graph output `" + e.name + "` cannot be a connection source"); return false; }
+            if (it->second == 'n') { err.at(e.at, "`" + e.name + "` is a node: name one of its outputs (`" + e.name + ".output`)"); return false; }
+            if (e.name == g.stream_input) { out.k = Operand::Stream; out.s.node = plan::kGraphInput; out.s.port = 0; return true; }
+            if (e.name == g.event_input) { is_event = true; return true; }
+            out.k = Operand::Value; out.pid = value_id[e.name]; return true;
+        }
+        case Expr::Field: {
+            if (e.a->k != Expr::Ident || !node_id.count(e.a->name)) {
+                err.at(e.at, "cannot resolve the source of this connection (unknown node or endpoint name `" + text_of(*e.a) + "`?)"); return false;
+            }
+            const int nid = node_id[e.a->name];
+            const Endpoint *ep = find_ep(nid, e.name);
+            if (!ep) { err.at(e.at, "node `" + e.a->name + "` has no endpoint `" + e.name + "`"); return false; }
+            if (!ep->is_out) { err.at(e.at, "`" + e.a->name + "." + e.name + "` is an input: it cannot be a connection source"); return false; }
+            out = stream_of(nid, ep->slot); return true;
+        }
+        case Expr::Binary: {
+            Operand l, r; bool le, re;
+            if (!source(*e.a, l, le) || !source(*e.b, r, re)) return false;
+            if (le || re) { err.at(e.at, "event endpoints cannot take part in arithmetic"); return false; }
+            out = binary(e.op, l, r, text_of(e), e.at); return true;
+        }
+        case Expr::Method: {
+            using O = plan::ExprOp;
+            Operand x; bool xe;
+            if (!source(*e.a, x, xe)) return false;
+            if (xe) { err.at(e.at, "event endpoints cannot take part in arithmetic"); return false; }
+            struct { const char *m; O op; size_t n_args; } ms[] = {{"tanh", O::Tanh, 0}, {"abs", O::Abs, 0}, {"clamp", O::Clamp, 2}, {"min", O::MinV, 1}, {"max", O::MaxV, 1}};
+            for (auto &m : ms) if (e.name == m.m) {
+                if (e.args.size() != m.n_args) { err.at(e.at, "f32::" + e.name + " takes " + std::to_string(m.n_args) + " literal argument(s)"); return false; }
+                plan::Node n = blank(text_of(e), plan::NodeType::Expr, m.op);
+                n.in[0] = materialise(x, text_of(*e.a)).s;
+                for (size_t i = 0; i < e.args.size(); ++i) n.cst[i] = e.args[i];
+                out = stream_of(add_synth(n)); return true;
+            }
+            err.at(e.at, "method `." + e.name + "()` is not supported in a connection source (tanh, abs, clamp, min, max are)"); return false;
+        }
+        default:
+            err.at(e.at, "free function `" + e.name + "` in a connection source names Rust code: not supported by the node plan"); return false;
+        }
+    }
+
+    bool connection(const Conn &c) {
+        if (c.via) { err.at(c.at, "`-> [..] ->` feedback edges are not compiled to a node plan (nodes render whole blocks; a cycle needs the per-sample walk)"); return false; }
+        Operand src; bool src_event = false;
+        if (!source(*c.src, src, src_event)) return false;
+        const Kind sk = src_event ? Kind::Event : src.kind();
+        const Expr &d = *c.dst;
+        auto mismatch = [&](Kind dk) {
+            err.at(c.at, std::string("Type mismatch in connection: source is ") + kind_name(sk) + " but destination expects " + kind_name(dk));
+            return false;
+        };
+        if (d.k == Expr::Ident) {
+            auto it = names.find(d.name);
+            if (it == names.end() || it->second != 'o') {
+                err.at(d.at, it == names.end() ? "cannot resolve the destination of this connection (unknown node or endpoint name `" + d.name + "`?)"
+                                               : "`" + d.name + "` is not a graph output: it cannot be a connection destination");
+                return false;
+            }
+            if (sk == Kind::Event) return mismatch(Kind::Stream);
+            out_terms.push_back(src);
+            return true;
+        }
+        if (d.k != Expr::Field || d.a->k != Expr::Ident || !node_id.count(d.a->name)) {
+            err.at(d.at, "cannot resolve the destination of this connection (unknown node or endpoint name `" + text_of(d) + "`?)"); return false;
+        }
+        const int nid = node_id[d.a->name];
+        const Endpoint *ep = find_ep(nid, d.name);
+        if (!ep) { err.at(d.at, "node `" + d.a->name + "` has no endpoint `" + d.name + "`"); return false; }
+        if (ep->is_out) { err.at(d.at, "`" + d.a->name + "." + d.name + "` is an output: it cannot be a connection destination"); return false; }
+        plan::Node &n = g.nodes[nid];
+        switch (ep->kind) {
+        case Kind::Event:
+            if (sk != Kind::Event) return mismatch(Kind::Event);
+            n.gate = true; return true;
+        case Kind::Value:
+            if (sk != Kind::Value) return mismatch(Kind::Value);
+            if (src.k == Operand::Stream) { err.at(c.at, "a computed value into a value endpoint is not supported by the node plan (connect a graph input or a literal)"); return false; }
+            /* plain field assignment every frame: the last statement wins */
+            if (src.k == Operand::Value) { n.pid[ep->slot] = src.pid; } else { n.pid[ep->slot] = plan::kNoValue; n.cst[ep->slot] = src.c; }
+            return true;
+        default:
+            if (sk == Kind::Event) return mismatch(Kind::Stream);
+            in_terms[nid][ep->slot].push_back(src);
+            return true;
+        }
+    }
+
+    /* codegen/emit_node.rs:153-174: dst = s0; dst += s1; ... (left fold in statement order) */
+    Operand sum_terms(const std::vector<Operand> &terms, const std::string &label) {
+        Operand acc = terms[0];
+        for (size_t i = 1; i < terms.size(); ++i) {
+            Tok t;
+            acc = binary('+', acc, terms[i], label + " (fan-in)", t);
+            if (acc.k == Operand::Stream && acc.s.node >= 0 && g.nodes[acc.s.node].op == plan::ExprOp::AddSS) {
+                g.nodes[acc.s.node].type = plan::NodeType::Mixer; g.nodes[acc.s.node].op = plan::ExprOp::None;
+            }
+        }
+        return acc;
+    }
+    bool bind_stream_input(int nid, int k) {
+        const Endpoint *ep = nullptr;
+        for (const Endpoint &e : info[nid]->eps) if (!e.is_out && e.kind == Kind::Stream && e.slot == k) ep = &e;
+        const std::string label = g.nodes[nid].name + "." + ep->name;
+        const Operand o = sum_terms(in_terms[nid][k], label);
+        if (o.k == Operand::Stream) { g.nodes[nid].in[k] = o.s; return true; }
+        if (ep->standin >= 0) {                              /* Value -> Stream edge: the kernel broadcasts the value per frame */
+            plan::Node &n = g.nodes[nid];
+            if (o.k == Operand::Value) n.pid[ep->standin] = o.pid; else { n.pid[ep->standin] = plan::kNoValue; n.cst[ep->standin] = o.c; }
+            return true;
+        }
+        g.nodes[nid].in[k] = materialise(o, label).s;
+        return true;
+    }
+
+    /* ir/passes/dead_nodes.rs: reverse BFS from the output; everything else is dropped */
+    bool drop_dead_nodes() {
+        const int n = (int)g.nodes.size();
+        std::vector<char> live(n, 0);
+        std::vector<int> stack{g.output.node};
+        while (!stack.empty()) {
+            const int i = stack.back(); stack.pop_back();
+            if (i < 0 || live[i]) continue;
+            live[i] = 1;
+            for (const plan::StreamRef &r : g.nodes[i].in) if (r.node >= 0) stack.push_back(r.node);
+        }
+        std::vector<int> remap(n, -1);
+        std::vector<plan::Node> kept;
+        for (int i = 0; i < n; ++i) if (live[i]) { remap[i] = (int)kept.size(); kept.push_back(g.nodes[i]); }
+        for (plan::Node &nd : kept) for (plan::StreamRef &r : nd.in) if (r.node >= 0) r.node = remap[r.node];
+        g.output.node = remap[g.output.node];
+        g.nodes.swap(kept);
+        return true;
+    }
+};
+
+/* text -> plan::Graph; on failure `error` holds "line:col: message" */
+inline bool compile(const char *text, plan::Graph &g, std::string &error) {
+    Error err;
+    std::vector<Tok> toks;
+    if (!text) { error = "0:0: null graph text"; return false; }
+    if (!lex(text, toks, err)) { error = err.text(); return false; }
+    Ast ast;
+    Parser p(toks, err);
+    if (!p.parse(ast)) { error = err.text(); return false; }
+    Lowering l(ast, g, err);
+    if (!l.run()) { error = err.text(); return false; }
+    return true;
+}
+
+/* text form of a compiled graph: inputs, then the launch plan (for tests and tools) */
+inline std::string describe(const plan::Graph &g, const plan::Plan &p) {
+    std::string s = "graph " + (g.name.empty() ? std::string("<anonymous>") : g.name) + "\n";
+    for (size_t i = 0; i < g.inputs.size(); ++i) {
+        char b[160];
+        snprintf(b, sizeof b, "input %zu: %s = %.9g", i, g.inputs[i].name.c_str(), (double)g.inputs[i].def);
+        s += b;
+        if (g.inputs[i].has_range) { snprintf(b, sizeof b, " [%.9g..%.9g%s]", (double)g.inputs[i].lo, (double)g.inputs[i].hi, g.inputs[i].log ? ", log" : ""); s += b; }
+        if (g.inputs[i].ramp) s += " ramp " + std::to_string(g.inputs[i].ramp);
+        s += "\n";
+    }
+    if (!g.stream_input.empty()) s += "stream input: " + g.stream_input + "\n";
+    if (!g.event_input.empty()) s += "event input: " + g.event_input + "\n";
+    s += "output: " + g.output_name + " <- " + g.nodes[g.output.node].name + "\n";
+    s += "state words per voice: " + std::to_string(g.n_state) + "\n";
+    for (size_t k = 0; k < p.launches.size(); ++k) {
+        const plan::Launch &l = p.launches[k];
+        s += std::to_string(k) + ": " + plan::type_name(l.type);
+        s += " [";
+        for (size_t j = 0; j < l.nodes.size(); ++j) {
+            if (j) s += ", ";
+            const plan::Node &nd = g.nodes[l.nodes[j]];
+            s += nd.name;
+            if (nd.type == plan::NodeType::Expr) s += std::string(" {") + plan::op_name(nd.op) + "}";
+        }
+        s += "]\n";
+    }
+    return s;
+}
+
+}  // namespace dsl
+}  // namespace oscen

@@ -24,6 +24,7 @@
 #include "kernel_others.cuh"
 #include "kernel_resample.cuh"
 #include "graphs.hpp"
+#include "dsl.hpp"
 #include "midi_front.hpp"
 #include "midi_device.cuh"
 
@@ -37,7 +38,7 @@ namespace {
 thread_local std::string g_create_error;
 
 const uint32_t kNInputs[7] = {28, 3, 2, 2, 9, 4, 8};       /* clip graphs: no value inputs */
-bool is_clip(uint32_t kind) { return kind >= OSCEN_B200_GRAPH_CLIP_REF && kind < OSCEN_B200_GRAPH_COUNT; }
+bool is_clip(uint32_t kind) { return kind >= OSCEN_B200_GRAPH_CLIP_REF && kind < OSCEN_B200_GRAPH_CUSTOM; }
 int clip_policy(uint32_t kind) { return kind == OSCEN_B200_GRAPH_CLIP_REF ? POL_LATCH : (int)(kind - OSCEN_B200_GRAPH_CLIP_OS_BASE) / 3; }
 int clip_log2f(uint32_t kind) { return kind == OSCEN_B200_GRAPH_CLIP_REF ? 0 : 1 + (int)(kind - OSCEN_B200_GRAPH_CLIP_OS_BASE) % 3; }
 bool has_stream_in(uint32_t kind) { return kind == OSCEN_B200_GRAPH_TWIN_PEAKS || is_clip(kind); }
@@ -104,6 +105,12 @@ bool nccl_load(std::string &err) {
 
 }  // namespace
 
+/* a compiled `graph!` description (dsl.hpp): host-only, shareable between engines */
+struct oscen_b200_graph {
+    plan::Graph g;
+    plan::Plan p;
+};
+
 struct oscen_b200_engine {
     oscen_b200_config cfg{};
     uint32_t n_inputs = 0, n_state = 0, n_inst = 0, channels = 1, n_cta = 0;
@@ -156,6 +163,10 @@ struct oscen_b200_engine {
     float *h_mix = nullptr;
     uint32_t last_frames = 0;
 
+    bool has_stream_in = false;          /* the graph declares a per-voice stream input */
+    uint32_t lcg_field = 0;              /* first of the two state words of the device-side input LCG */
+    std::vector<uint32_t> custom_init;   /* DSL-compiled graph: initial SoA state of one voice */
+
     /* node plan */
     plan::Graph graph;
     plan::Plan plan;
@@ -198,8 +209,8 @@ namespace {
 int arg_error(oscen_b200_engine *e, const char *msg) { e->err = msg; return OSCEN_B200_E_ARG; }
 
 /* initial SoA state of one voice after G::new() + G::init(sr) */
-std::vector<uint32_t> initial_state(uint32_t kind, float sr) {
-    std::vector<float> s(n_state_of(kind), 0.0f);
+std::vector<uint32_t> initial_state(uint32_t kind, float sr, const plan::Graph *custom, uint32_t n_state) {
+    std::vector<float> s(n_state, 0.0f);
     auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
     auto adsr = [&](uint32_t base) { s[base + 0] = 0.0f; s[base + 1] = 0.0f; s[base + 2] = 0.0f; s[base + 3] = 1.0f; };
     auto tpt = [&](uint32_t base, float cutoff, float q) {
@@ -229,6 +240,20 @@ std::vector<uint32_t> initial_state(uint32_t kind, float sr) {
     case OSCEN_B200_GRAPH_SYNTH: case OSCEN_B200_GRAPH_SYNTH_ADSR:
         tpt(SY_TPT, 1200.0f, 0.707f);
         adsr(SY_ENV);
+        break;
+    case OSCEN_B200_GRAPH_CUSTOM:
+        /* G::new() builds every node from its constructor expression, G::init(sr) = set_sample_rate + prepare()
+           (codegen/mod.rs:1309-1350); only filters and envelopes hold non-zero state afterwards */
+        for (const plan::Node &nd : custom->nodes) {
+            if (nd.type == plan::NodeType::Adsr) adsr(nd.state_base);
+            else if (nd.type == plan::NodeType::Tpt) tpt(nd.state_base, nd.init[0], nd.init[1]);
+            else if (nd.type == plan::NodeType::Lp18) {
+                Lp18State f; lp18_init(f, nd.init[0], nd.init[1], sr);
+                const uint32_t b = nd.state_base;
+                s[b + 0] = f.z0; s[b + 1] = f.z1; s[b + 2] = f.z2; s[b + 3] = f.g; s[b + 4] = f.h;
+                s[b + 5] = f.last_cutoff; s[b + 6] = f.last_fmod; s[b + 7] = f.last_resonance; s[b + 8] = f.resonance;
+            }
+        }
         break;
     default: break;                                        /* clip graphs: resampler state starts at zero */
     }
@@ -334,9 +359,9 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
     const bool vec = !value_events && (n % 4u == 0u);
     /* the graph's stream input: host/device block, or generated by the LCG source node */
     const float *gin = nullptr;
-    if (e->cfg.graph_kind == OSCEN_B200_GRAPH_TWIN_PEAKS) {
+    if (e->has_stream_in) {
         if (e->lcg_on) {
-            lcg_source_kernel<<<grid, kCta, 0, e->stream>>>(e->d_state, S[p.n_streams], e->d_ctl, n);
+            lcg_source_kernel<<<grid, kCta, 0, e->stream>>>(e->d_state, S[p.n_streams], e->d_ctl, n, e->lcg_field);
             e->stats.kernel_launches++;
             gin = S[p.n_streams];
         } else gin = e->stream_in_ptr;
@@ -351,10 +376,11 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         NodeArgs a{};
         a.n_voices = n; a.state_base = nd.state_base; a.ctl = e->d_ctl; a.events = e->d_events;
         a.ptab = e->d_ptab; a.pv = e->d_pv; a.state = e->d_state; a.sr = e->cfg.sample_rate;
-        a.in0 = resolve(nd.in[0]); a.in1 = resolve(nd.in[1]);
+        a.in0 = resolve(nd.in[0]); a.in1 = resolve(nd.in[1]); a.in2 = resolve(nd.in[2]);
         a.out0 = S[p.first_stream[idx]];
         a.out1 = plan::n_outputs(nd.type) > 1 ? S[p.first_stream[idx] + 1] : nullptr;
-        for (int k = 0; k < 4; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
+        for (int k = 0; k < plan::kMaxParams; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
+        a.gate = nd.gate ? 1u : 0u; a.q = nd.cst[1];
         return a;
     };
     for (const plan::Launch &l : p.launches) {
@@ -368,6 +394,8 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         case plan::NodeType::Tpt: tpt_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::PolyBlepSine: polyblep_node_kernel<WAVE_SINE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::PolyBlepSaw: polyblep_node_kernel<WAVE_SAW><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::PolyBlepSquare: polyblep_node_kernel<WAVE_SQUARE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::PolyBlepTriangle: polyblep_node_kernel<WAVE_TRIANGLE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::Lp18: lp18_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         default:
             for (uint32_t k = 0; k < cnt; ++k) {                       /* stateless nodes: one stream kernel each */
@@ -380,6 +408,26 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
                 case plan::NodeType::Mixer: launch_ew<EW_MIXER>(e, a, vec); break;
                 case plan::NodeType::Sub: launch_ew<EW_SUB>(e, a, vec); break;
                 case plan::NodeType::Crossfade: launch_ew<EW_CROSSFADE>(e, a, vec); break;
+                case plan::NodeType::Expr:
+                    switch (g.nodes[l.nodes[k]].op) {
+                    case plan::ExprOp::AddSS: launch_ew<EW_MIXER>(e, a, vec); break;
+                    case plan::ExprOp::SubSS: launch_ew<EW_SUB>(e, a, vec); break;
+                    case plan::ExprOp::MulSS: launch_ew<EW_MUL>(e, a, vec); break;
+                    case plan::ExprOp::DivSS: launch_ew<EW_DIV>(e, a, vec); break;
+                    case plan::ExprOp::AddSV: launch_ew<EW_ADD_VALUE>(e, a, vec); break;
+                    case plan::ExprOp::SubSV: launch_ew<EW_SUBV>(e, a, vec); break;
+                    case plan::ExprOp::MulSV: launch_ew<EW_GAIN>(e, a, vec); break;
+                    case plan::ExprOp::DivSV: launch_ew<EW_DIVV>(e, a, vec); break;
+                    case plan::ExprOp::SubVS: launch_ew<EW_RSUBV>(e, a, vec); break;
+                    case plan::ExprOp::DivVS: launch_ew<EW_RDIVV>(e, a, vec); break;
+                    case plan::ExprOp::Value: launch_ew<EW_VALUE>(e, a, vec); break;
+                    case plan::ExprOp::Tanh: launch_ew<EW_TANH>(e, a, vec); break;
+                    case plan::ExprOp::Abs: launch_ew<EW_ABS>(e, a, vec); break;
+                    case plan::ExprOp::Clamp: launch_ew<EW_CLAMP>(e, a, vec); break;
+                    case plan::ExprOp::MinV: launch_ew<EW_MINV>(e, a, vec); break;
+                    default: launch_ew<EW_MAXV>(e, a, vec); break;
+                    }
+                    break;
                 default: launch_ew<EW_HARDCLIP>(e, a, vec); break;
                 }
             }
@@ -445,9 +493,12 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     delete e;
 }
 
-int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
+static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *custom, oscen_b200_engine **out) {
     if (!cfg || !out) { g_create_error = "null argument"; return OSCEN_B200_E_ARG; }
     *out = nullptr;
+    if ((custom == nullptr) != (cfg->graph_kind != OSCEN_B200_GRAPH_CUSTOM)) {
+        g_create_error = "OSCEN_B200_GRAPH_CUSTOM engines are created with oscen_b200_create_from_graph (and only those)"; return OSCEN_B200_E_ARG;
+    }
     if (cfg->graph_kind >= OSCEN_B200_GRAPH_COUNT || cfg->n_voices == 0 || cfg->voices_per_instance == 0 ||
         kCta % cfg->voices_per_instance != 0 || (cfg->voices_per_instance & (cfg->voices_per_instance - 1)) != 0 || cfg->n_voices % cfg->voices_per_instance != 0 ||
         !(cfg->sample_rate > 0.0f) || cfg->plan > OSCEN_B200_PLAN_NODES) {
@@ -455,7 +506,10 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         return OSCEN_B200_E_ARG;
     }
     plan::Graph pg; plan::Plan pp;
-    if (cfg->plan == OSCEN_B200_PLAN_NODES) {
+    if (custom) {
+        if (cfg->plan != OSCEN_B200_PLAN_NODES) { g_create_error = "a DSL-compiled graph runs as a node plan: set plan = OSCEN_B200_PLAN_NODES"; return OSCEN_B200_E_ARG; }
+        pg = custom->g; pp = custom->p;
+    } else if (cfg->plan == OSCEN_B200_PLAN_NODES) {
         std::string perr;
         if (!plan::for_kind(cfg->graph_kind, pg)) {
             g_create_error = "PLAN_NODES: this graph (multirate / array streams) only has a fused kernel"; return OSCEN_B200_E_ARG;
@@ -471,7 +525,15 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
     oscen_b200_engine *e = new oscen_b200_engine();
     e->cfg = *cfg;
     const uint32_t kind = cfg->graph_kind, n = cfg->n_voices;
-    e->n_inputs = kind < 7 ? kNInputs[kind] : 0u; e->n_state = n_state_of(kind);
+    e->has_stream_in = custom ? !pg.stream_input.empty() : has_stream_in(kind);
+    if (custom) {
+        e->n_inputs = (uint32_t)pg.inputs.size();
+        e->lcg_field = pg.n_state; e->n_state = pg.n_state + (e->has_stream_in ? 2u : 0u);
+        if (e->n_state == 0) e->n_state = 1;                      /* stateless graph: keep the allocation non-empty */
+    } else {
+        e->n_inputs = kind < 7 ? kNInputs[kind] : 0u; e->n_state = n_state_of(kind);
+        e->lcg_field = e->has_stream_in ? lcg_field(kind) : 0u;
+    }
     e->n_inst = n / cfg->voices_per_instance;
     e->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2 : 1;
     e->n_cta = (n + kCta - 1) / kCta;
@@ -511,11 +573,12 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
         if (is_clip(kind)) { KernelArgs none{}; launch_clip(e, none, 0, true); CK(e, cudaGetLastError()); }
         /* new() + init(sr): default inputs, initial node state */
         for (uint32_t i = 0; i < kMaxInputs; ++i) {
-            e->uni[i] = kind < 7 ? kDefaults[kind][i] : 0.0f; e->uniform[i] = true; e->ramped[i] = false;
+            e->uni[i] = kind < 7 ? kDefaults[kind][i] : (custom && i < pg.inputs.size() ? pg.inputs[i].def : 0.0f);
+            e->uniform[i] = true; e->ramped[i] = false;
             e->ramps[i].set_immediate(e->uni[i]);
         }
         for (uint32_t i = 0; i < e->n_inputs; ++i) { int r = fill_row(e, i, 0, n, e->uni[i]); if (r) return r; }
-        std::vector<uint32_t> init = initial_state(kind, cfg->sample_rate);
+        std::vector<uint32_t> init = initial_state(kind, cfg->sample_rate, custom ? &pg : nullptr, e->n_state);
         uint32_t *d_init = nullptr;
         CK(e, cudaMalloc(&d_init, init.size() * sizeof(uint32_t)));
         cudaError_t st = cudaMemcpyAsync(d_init, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream);
@@ -532,6 +595,53 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) {
     if (rc) { g_create_error = e->err; oscen_b200_destroy(e); return rc; }
     *out = e;
     return 0;
+}
+
+int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) { return create_impl(cfg, nullptr, out); }
+
+/* ---- graph! DSL front end (dsl.hpp): text -> node plan; needs no GPU until create_from_graph */
+int oscen_b200_graph_compile(const char *text, oscen_b200_graph **out, char *err, size_t err_cap) {
+    if (err && err_cap) err[0] = 0;
+    if (!text || !out) return OSCEN_B200_E_ARG;
+    *out = nullptr;
+    oscen_b200_graph *g = new oscen_b200_graph();
+    std::string msg;
+    bool ok = dsl::compile(text, g->g, msg);
+    if (ok && !plan::compile(g->g, g->p, msg)) { ok = false; msg = "0:0: " + msg; }
+    if (!ok) {
+        if (err && err_cap) { strncpy(err, msg.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+        delete g;
+        return OSCEN_B200_E_ARG;
+    }
+    *out = g;
+    return 0;
+}
+void oscen_b200_graph_free(oscen_b200_graph *g) { delete g; }
+int oscen_b200_graph_describe(const oscen_b200_graph *g, char *dst, size_t cap) {
+    if (!g || !dst || cap == 0) return OSCEN_B200_E_ARG;
+    const std::string s = dsl::describe(g->g, g->p);
+    if (s.size() + 1 > cap) return OSCEN_B200_E_ARG;
+    memcpy(dst, s.c_str(), s.size() + 1);
+    return (int)g->p.launches.size();
+}
+uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g) { return g ? (uint32_t)g->g.inputs.size() : 0u; }
+int oscen_b200_graph_input_id(const oscen_b200_graph *g, const char *name) {
+    if (!g || !name) return OSCEN_B200_E_ARG;
+    for (size_t i = 0; i < g->g.inputs.size(); ++i) if (g->g.inputs[i].name == name) return (int)i;
+    return OSCEN_B200_E_ARG;
+}
+int oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t id, oscen_b200_input_info *out) {
+    if (!g || !out || id >= g->g.inputs.size()) return OSCEN_B200_E_ARG;
+    const plan::ValueInput &v = g->g.inputs[id];
+    memset(out, 0, sizeof *out);
+    strncpy(out->name, v.name.c_str(), sizeof(out->name) - 1);
+    out->default_value = v.def; out->has_range = v.has_range ? 1u : 0u; out->range_min = v.lo; out->range_max = v.hi;
+    out->logarithmic = v.log ? 1u : 0u; out->ramp_frames = v.ramp;
+    return 0;
+}
+int oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out) {
+    if (!g) { g_create_error = "null graph"; return OSCEN_B200_E_ARG; }
+    return create_impl(cfg, g, out);
 }
 
 int oscen_b200_set_value(oscen_b200_engine *e, uint32_t id, uint32_t first, uint32_t count, const float *v, int broadcast) {
@@ -692,7 +802,7 @@ int oscen_b200_push_midi_batch(oscen_b200_engine *e, const oscen_b200_midi_msg *
 
 int oscen_b200_stream_in(oscen_b200_engine *e, uint32_t id, const float *src, uint32_t frames, int is_device) {
     if (!e || !src) return OSCEN_B200_E_ARG;
-    if (!has_stream_in(e->cfg.graph_kind) || id != 0 || frames == 0 || frames > kMaxBlock)
+    if (!e->has_stream_in || id != 0 || frames == 0 || frames > kMaxBlock)
         return arg_error(e, "stream_in: only graphs with a stream input (TWIN_PEAKS audio_in, CLIP_* input; id 0), frames <= 512");
     CK(e, cudaSetDevice(e->cfg.device));
     const size_t nfl = (size_t)frames * e->cfg.n_voices;
@@ -725,10 +835,10 @@ __global__ void lcg_seed_kernel(float *state, uint32_t n, unsigned long long see
 
 int oscen_b200_stream_in_lcg(oscen_b200_engine *e, uint32_t id, uint64_t seed, uint32_t voice_offset) {
     if (!e) return OSCEN_B200_E_ARG;
-    if (!has_stream_in(e->cfg.graph_kind) || id != 0) return arg_error(e, "stream_in_lcg: this graph has no stream input");
+    if (!e->has_stream_in || id != 0) return arg_error(e, "stream_in_lcg: this graph has no stream input");
     CK(e, cudaSetDevice(e->cfg.device));
     e->lcg_seed = seed; e->voice_offset = voice_offset; e->lcg_on = true;
-    lcg_seed_kernel<<<(e->cfg.n_voices + 255) / 256, 256, 0, e->stream>>>(e->d_state, e->cfg.n_voices, seed, voice_offset, lcg_field(e->cfg.graph_kind));
+    lcg_seed_kernel<<<(e->cfg.n_voices + 255) / 256, 256, 0, e->stream>>>(e->d_state, e->cfg.n_voices, seed, voice_offset, e->lcg_field);
     e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
     return 0;
@@ -738,7 +848,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     if (!e) return OSCEN_B200_E_ARG;
     if (frames == 0 || frames > kMaxBlock) return arg_error(e, "process_block: frames must be 1..512");
     const uint32_t kind = e->cfg.graph_kind, n = e->cfg.n_voices, vpi = e->cfg.voices_per_instance;
-    if (has_stream_in(kind) && !e->lcg_on && e->stream_in_ptr && e->stream_in_frames < frames)
+    if (e->has_stream_in && !e->lcg_on && e->stream_in_ptr && e->stream_in_frames < frames)
         return arg_error(e, "process_block: stream_in block shorter than frames");
     CK(e, cudaSetDevice(e->cfg.device));
 

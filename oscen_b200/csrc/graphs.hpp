@@ -16,8 +16,11 @@ inline Node make(const char *name, NodeType t, StreamRef a, StreamRef b, uint32_
                  float c0, float c1, float c2, float c3, uint32_t state_base) {
     Node n{};
     n.name = name; n.type = t; n.in[0] = a; n.in[1] = b;
+    for (int k = 0; k < kMaxParams; ++k) { n.pid[k] = kNoValue; n.cst[k] = 0.0f; }
     n.pid[0] = p0; n.pid[1] = p1; n.pid[2] = p2; n.pid[3] = p3;
     n.cst[0] = c0; n.cst[1] = c1; n.cst[2] = c2; n.cst[3] = c3;
+    if (t == NodeType::PolyBlepSine || t == NodeType::PolyBlepSaw) n.cst[2] = 0.5f;    /* pulse_width, oscillators/mod.rs:116 */
+    if (t == NodeType::FmOperator) n.cst[5] = 1.0f;                                     /* envelope, fm_operator.rs:41 */
     n.state_base = state_base;
     return n;
 }

@@ -30,11 +30,16 @@ struct NodeArgs {
     const float *ptab;
     const float *pv;
     float *state;
-    const float *in0, *in1;
+    const float *in0, *in1, *in2;
     float *out0, *out1;
-    uint32_t pid[4];                        /* value-input ids feeding this node (kNoInput: use cst) */
-    float cst[4];
+    uint32_t pid[8];                        /* value-input ids feeding this node's parameter slots (kNoInput: use cst): the
+                                               node's value endpoints first, then the stand-ins of its stream endpoints, read
+                                               when the stream pointer is null — an unconnected endpoint keeps its constructor
+                                               value, a Value -> Stream edge broadcasts the value input per frame (plan.hpp) */
+    float cst[8];
     float sr;
+    uint32_t gate;                          /* AdsrEnvelope: gate events are connected to this node */
+    float q;                                /* stateless nodes: second literal (x.clamp(p, q)) */
 };
 struct NodeArgs4 { NodeArgs n[4]; };        /* blockIdx.y selects the node */
 
@@ -81,6 +86,11 @@ struct NodeParams {
         A[k] = ((PA) != nullptr && f_ < frames) ? __ldcs((PA) + (size_t)f_ * n + v) : 0.0f;             \
         B[k] = ((PB) != nullptr && f_ < frames) ? __ldcs((PB) + (size_t)f_ * n + v) : 0.0f;             \
     }
+#define OSC_LOAD1(A, PA, F0)                                                                            \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                              \
+        const uint32_t f_ = (F0) + k;                                                                   \
+        A[k] = ((PA) != nullptr && f_ < frames) ? __ldcs((PA) + (size_t)f_ * n + v) : 0.0f;             \
+    }
 
 /* ---- AdsrEnvelope: pid = {attack, decay, sustain, release}; out0 = output */
 __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__ NodeArgs4 args) {
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__
             if (due) j = prm.events(a, ec, f);
             if (adsr_derived_stale(d, prm.P[0], prm.P[1], prm.P[3])) adsr_derive_r(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
             if (due) {
-                for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
+                for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate && a.gate)
                     adsr_on_gate(s, ec.ev[q].scalar, prm.P[0], prm.P[3], d);
                 ec.advance(j);
             }
@@ -107,9 +117,11 @@ __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__
     adsr_store(s, a.state, a.state_base, n, v);
 }
 
-/* ---- FmOperator: in0 = phase_mod (nullable), in1 = envelope; pid = {base_freq, ratio, feedback, level} */
+/* ---- FmOperator: in0 = phase_mod, in1 = envelope (either nullable: then slot 4 / 5 stands in);
+        pid = {base_freq, ratio, feedback, level, phase_mod, envelope} */
 __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__ NodeArgs4 args) {
-    OSC_NODE_PROLOGUE(4)
+    OSC_NODE_PROLOGUE(6)
+    const bool pm_stream = a.in0 != nullptr, en_stream = a.in1 != nullptr;
     FmOpState s;
     s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
     s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
             if (f < frames) {
                 if (ramp_mask) { prm.ramps(a, ramp_mask, f); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
                 if (ec.due(f)) { ec.advance(prm.events(a, ec, f)); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
-                __stcs(a.out0 + (size_t)f * n + v, fmop_process(s, pm[k], prm.P[2], en[k], prm.P[3]));
+                __stcs(a.out0 + (size_t)f * n + v, fmop_process(s, pm_stream ? pm[k] : prm.P[4], prm.P[2], en_stream ? en[k] : prm.P[5], prm.P[3]));
             }
         }
 #pragma unroll
@@ -132,60 +144,82 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
     a.state[(size_t)(a.state_base + 0) * n + v] = s.phase; a.state[(size_t)(a.state_base + 1) * n + v] = s.prev;
 }
 
-/* ---- TptFilter: in0 = input, in1 = cutoff stream (nullable: then the value input pid[1] feeds the
-        `cutoff` stream endpoint, a broadcast per frame); pid = {q, cutoff} */
+/* ---- TptFilter: in0 = input, in1 = cutoff, in2 = f_mod (each nullable: then the slot stands in, e.g. a
+        value input feeding the `cutoff` stream endpoint is a broadcast per frame); pid = {q, cutoff, f_mod, input} */
 __global__ void __launch_bounds__(kCta) tpt_node_kernel(const __grid_constant__ NodeArgs4 args) {
-    OSC_NODE_PROLOGUE(2)
+    OSC_NODE_PROLOGUE(4)
     TptState s; tpt_load(s, a.state, a.state_base, n, v);
-    const bool cut_stream = a.in1 != nullptr;
+    const bool in_stream = a.in0 != nullptr, cut_stream = a.in1 != nullptr, fm_stream = a.in2 != nullptr;
     float x[kPF], c[kPF], x_n[kPF], c_n[kPF];
     OSC_LOAD2(x, c, a.in0, a.in1, 0u)
-    for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        OSC_LOAD2(x_n, c_n, a.in0, a.in1, f0 + kPF)
+    if (!fm_stream) {
+        for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
+            OSC_LOAD2(x_n, c_n, a.in0, a.in1, f0 + kPF)
 #pragma unroll
-        for (uint32_t k = 0; k < kPF; ++k) {
-            const uint32_t f = f0 + k;
-            if (f < frames) {
-                prm.ramps(a, ramp_mask, f);
-                if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                __stcs(a.out0 + (size_t)f * n + v, tpt_process(s, x[k], cut_stream ? c[k] : prm.P[1], prm.P[0], 0.0f, a.sr));
+            for (uint32_t k = 0; k < kPF; ++k) {
+                const uint32_t f = f0 + k;
+                if (f < frames) {
+                    prm.ramps(a, ramp_mask, f);
+                    if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+                    __stcs(a.out0 + (size_t)f * n + v, tpt_process(s, in_stream ? x[k] : prm.P[3], cut_stream ? c[k] : prm.P[1], prm.P[0], prm.P[2], a.sr));
+                }
             }
-        }
 #pragma unroll
-        for (uint32_t k = 0; k < kPF; ++k) { x[k] = x_n[k]; c[k] = c_n[k]; }
+            for (uint32_t k = 0; k < kPF; ++k) { x[k] = x_n[k]; c[k] = c_n[k]; }
+        }
+    } else {
+        float m[kPF], m_n[kPF];
+        OSC_LOAD1(m, a.in2, 0u)
+        for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
+            OSC_LOAD2(x_n, c_n, a.in0, a.in1, f0 + kPF)
+            OSC_LOAD1(m_n, a.in2, f0 + kPF)
+#pragma unroll
+            for (uint32_t k = 0; k < kPF; ++k) {
+                const uint32_t f = f0 + k;
+                if (f < frames) {
+                    prm.ramps(a, ramp_mask, f);
+                    if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+                    __stcs(a.out0 + (size_t)f * n + v, tpt_process(s, in_stream ? x[k] : prm.P[3], cut_stream ? c[k] : prm.P[1], prm.P[0], m[k], a.sr));
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < kPF; ++k) { x[k] = x_n[k]; c[k] = c_n[k]; m[k] = m_n[k]; }
+        }
     }
     tpt_store(s, a.state, a.state_base, n, v);
 }
 
-/* ---- PolyBlepOscillator: in0 = frequency_mod (nullable); pid = {frequency, amplitude} */
+/* ---- PolyBlepOscillator: in0 = frequency_mod, in1 = phase_mod (nullable: slots 3 / 4 stand in);
+        pid = {frequency, amplitude, pulse_width, frequency_mod, phase_mod} */
 template <int WAVE>
 __global__ void __launch_bounds__(kCta) polyblep_node_kernel(const __grid_constant__ NodeArgs4 args) {
-    OSC_NODE_PROLOGUE(2)
+    OSC_NODE_PROLOGUE(5)
     float phase = a.state[(size_t)a.state_base * n + v];
-    float fm[kPF], fm_n[kPF];
-    [[maybe_unused]] float dummy[kPF], dummy_n[kPF];
-    const float *no_stream = nullptr;
-    OSC_LOAD2(fm, dummy, a.in0, no_stream, 0u)
+    const bool fm_stream = a.in0 != nullptr, pm_stream = a.in1 != nullptr;
+    float fm[kPF], fm_n[kPF], pm[kPF], pm_n[kPF];
+    OSC_LOAD2(fm, pm, a.in0, a.in1, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
-        OSC_LOAD2(fm_n, dummy_n, a.in0, no_stream, f0 + kPF)
+        OSC_LOAD2(fm_n, pm_n, a.in0, a.in1, f0 + kPF)
 #pragma unroll
         for (uint32_t k = 0; k < kPF; ++k) {
             const uint32_t f = f0 + k;
             if (f < frames) {
                 prm.ramps(a, ramp_mask, f);
                 if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                __stcs(a.out0 + (size_t)f * n + v, polyblep_process<WAVE>(phase, 0.0f, prm.P[0], fm[k], prm.P[1], 0.5f, a.sr));
+                __stcs(a.out0 + (size_t)f * n + v, polyblep_process<WAVE>(phase, pm_stream ? pm[k] : prm.P[4], prm.P[0], fm_stream ? fm[k] : prm.P[3],
+                                                                         prm.P[1], prm.P[2], a.sr));
             }
         }
 #pragma unroll
-        for (uint32_t k = 0; k < kPF; ++k) fm[k] = fm_n[k];
+        for (uint32_t k = 0; k < kPF; ++k) { fm[k] = fm_n[k]; pm[k] = pm_n[k]; }
     }
     a.state[(size_t)a.state_base * n + v] = phase;
 }
 
-/* ---- LP18Filter: in0 = input; pid = {cutoff, resonance} */
+/* ---- LP18Filter: in0 = input (nullable: slot 3 stands in); pid = {cutoff, resonance, fmod, input} */
 __global__ void __launch_bounds__(kCta) lp18_node_kernel(const __grid_constant__ NodeArgs4 args) {
-    OSC_NODE_PROLOGUE(2)
+    OSC_NODE_PROLOGUE(4)
+    const bool in_stream = a.in0 != nullptr;
     Lp18State s; lp18_load(s, a.state, a.state_base, n, v);
     float x[kPF], x_n[kPF];
     [[maybe_unused]] float dummy[kPF], dummy_n[kPF];
@@ -199,7 +233,7 @@ __global__ void __launch_bounds__(kCta) lp18_node_kernel(const __grid_constant__
             if (f < frames) {
                 prm.ramps(a, ramp_mask, f);
                 if (ec.due(f)) ec.advance(prm.events(a, ec, f));
-                __stcs(a.out0 + (size_t)f * n + v, lp18_process(s, x[k], prm.P[0], 0.0f, prm.P[1], a.sr));
+                __stcs(a.out0 + (size_t)f * n + v, lp18_process(s, in_stream ? x[k] : prm.P[3], prm.P[0], prm.P[2], prm.P[1], a.sr));
             }
         }
 #pragma unroll
@@ -217,9 +251,22 @@ enum : int {
     EW_MUL = 4,         /* Gain with a stream on `gain`: in0 * in1                       */
     EW_SUB = 5,         /* expression edge a - b                 codegen/mod.rs:433-472 */
     EW_HARDCLIP = 6,    /* HardClip                              oversampled-saturator main.rs:55-62 */
+    /* the remaining operators of compound connection sources (plan::ExprOp; the reference emits them as
+       Rust expressions evaluated per frame, codegen/mod.rs:433-472): one f32 rounding each, like the Rust */
+    EW_DIV = 7,         /* a / b */
+    EW_SUBV = 8,        /* a - v */
+    EW_RSUBV = 9,       /* v - a */
+    EW_DIVV = 10,       /* a / v */
+    EW_RDIVV = 11,      /* v / a */
+    EW_VALUE = 12,      /* a value input or literal read as a stream (Value -> Stream edge) */
+    EW_TANH = 13,       /* f32::tanh */
+    EW_ABS = 14,        /* f32::abs */
+    EW_CLAMP = 15,      /* f32::clamp(p, q) */
+    EW_MINV = 16,       /* f32::min(p): minNum */
+    EW_MAXV = 17,       /* f32::max(p): maxNum */
 };
 template <int OP>
-OSC_D void ew_apply(float x, float y, float p, float &o0, float &o1) {
+OSC_D void ew_apply(float x, float y, float p, float q, float &o0, float &o1) {
     o1 = 0.0f;
     if (OP == EW_GAIN) o0 = x * p;
     else if (OP == EW_ADD_VALUE) o0 = x + p;
@@ -227,9 +274,21 @@ OSC_D void ew_apply(float x, float y, float p, float &o0, float &o1) {
     else if (OP == EW_MUL) o0 = x * y;
     else if (OP == EW_SUB) o0 = x - y;
     else if (OP == EW_HARDCLIP) o0 = hardclip_process(x);
+    else if (OP == EW_DIV) o0 = x / y;
+    else if (OP == EW_SUBV) o0 = x - p;
+    else if (OP == EW_RSUBV) o0 = p - x;
+    else if (OP == EW_DIVV) o0 = x / p;
+    else if (OP == EW_RDIVV) o0 = p / x;
+    else if (OP == EW_VALUE) o0 = p;
+    else if (OP == EW_TANH) o0 = om_tanhf_u(x);
+    else if (OP == EW_ABS) o0 = fabsf(x);
+    else if (OP == EW_CLAMP) o0 = clampf(x, p, q);
+    else if (OP == EW_MINV) o0 = fminf(x, p);
+    else if (OP == EW_MAXV) o0 = fmaxf(x, p);
     else { const float mix = clampf(p, 0.0f, 1.0f); o0 = x * (1.0f - mix); o1 = x * mix; }
 }
-template <int OP> OSC_HD constexpr bool ew_two_inputs() { return OP == EW_MIXER || OP == EW_MUL || OP == EW_SUB; }
+template <int OP> OSC_HD constexpr bool ew_two_inputs() { return OP == EW_MIXER || OP == EW_MUL || OP == EW_SUB || OP == EW_DIV; }
+template <int OP> OSC_HD constexpr bool ew_no_inputs() { return OP == EW_VALUE; }
 
 /* serial per-voice form (used when the block carries value events) */
 template <int OP>
@@ -246,7 +305,7 @@ __global__ void __launch_bounds__(kCta) ew_node_kernel(const __grid_constant__ N
                 prm.ramps(a, ramp_mask, f);
                 if (ec.due(f)) ec.advance(prm.events(a, ec, f));
                 float o0, o1;
-                ew_apply<OP>(x[k], y[k], prm.P[0], o0, o1);
+                ew_apply<OP>(x[k], y[k], prm.P[0], a.q, o0, o1);
                 a.out0[(size_t)f * n + v] = o0;
                 if (OP == EW_CROSSFADE) a.out1[(size_t)f * n + v] = o1;
             }
@@ -272,7 +331,8 @@ __global__ void __launch_bounds__(256) ew_node_vec_kernel(const __grid_constant_
     float4 *out1 = reinterpret_cast<float4 *>(a.out1);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t f = (uint32_t)(i / n4), v4 = (uint32_t)(i - (size_t)f * n4);
-        const float4 x = __ldcs(in0 + i);
+        float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (!ew_no_inputs<OP>()) x = __ldcs(in0 + i);
         float4 y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (ew_two_inputs<OP>()) y = __ldcs(in1 + i);
         float4 p;
@@ -280,23 +340,23 @@ __global__ void __launch_bounds__(256) ew_node_vec_kernel(const __grid_constant_
         else if (ramped) { const float r = a.ptab[(size_t)f * kMaxInputs + a.pid[0]]; p = make_float4(r, r, r, r); }
         else p = __ldg(pv + v4);
         float4 o0, o1;
-        ew_apply<OP>(x.x, y.x, p.x, o0.x, o1.x); ew_apply<OP>(x.y, y.y, p.y, o0.y, o1.y);
-        ew_apply<OP>(x.z, y.z, p.z, o0.z, o1.z); ew_apply<OP>(x.w, y.w, p.w, o0.w, o1.w);
+        ew_apply<OP>(x.x, y.x, p.x, a.q, o0.x, o1.x); ew_apply<OP>(x.y, y.y, p.y, a.q, o0.y, o1.y);
+        ew_apply<OP>(x.z, y.z, p.z, a.q, o0.z, o1.z); ew_apply<OP>(x.w, y.w, p.w, a.q, o0.w, o1.w);
         __stcs(out0 + i, o0);
         if (OP == EW_CROSSFADE) __stcs(out1 + i, o1);
     }
 }
 
 /* graph input generated on device (TWIN_PEAKS audio_in from the per-voice LCG): a source node */
-__global__ void __launch_bounds__(kCta) lcg_source_kernel(float *state, float *out, const BlockCtl *ctl, uint32_t n) {
+__global__ void __launch_bounds__(kCta) lcg_source_kernel(float *state, float *out, const BlockCtl *ctl, uint32_t n, uint32_t field) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
-    unsigned long long lcg = (unsigned long long)__float_as_uint(state[(size_t)(TW_LCG + 0) * n + v]) |
-                             ((unsigned long long)__float_as_uint(state[(size_t)(TW_LCG + 1) * n + v]) << 32);
+    unsigned long long lcg = (unsigned long long)__float_as_uint(state[(size_t)(field + 0) * n + v]) |
+                             ((unsigned long long)__float_as_uint(state[(size_t)(field + 1) * n + v]) << 32);
     const uint32_t frames = ctl->frames;
     for (uint32_t f = 0; f < frames; ++f) out[(size_t)f * n + v] = lcg_next(lcg);
-    state[(size_t)(TW_LCG + 0) * n + v] = __uint_as_float((uint32_t)(lcg & 0xffffffffull));
-    state[(size_t)(TW_LCG + 1) * n + v] = __uint_as_float((uint32_t)(lcg >> 32));
+    state[(size_t)(field + 0) * n + v] = __uint_as_float((uint32_t)(lcg & 0xffffffffull));
+    state[(size_t)(field + 1) * n + v] = __uint_as_float((uint32_t)(lcg >> 32));
 }
 
 /* graph output: voices.audio_out -> audio_out (instance sums in index order) + mix partials */

@@ -28,17 +28,34 @@ namespace plan {
 enum class NodeType : uint8_t {
     Adsr,          /* AdsrEnvelope                     value: attack decay sustain release; event: gate */
     FmOperator,    /* FmOperator                       stream: phase_mod, envelope; value: base_freq ratio feedback level */
-    Tpt,           /* TptFilter                        stream: input, cutoff(or value); value: q */
-    PolyBlepSine,  /* PolyBlepOscillator::sine         stream: frequency_mod; value: frequency amplitude */
+    Tpt,           /* TptFilter                        stream: input, cutoff, f_mod; value: q */
+    PolyBlepSine,  /* PolyBlepOscillator::sine         stream: frequency_mod, phase_mod; value: frequency amplitude pulse_width */
     PolyBlepSaw,   /* PolyBlepOscillator::saw */
-    Lp18,          /* LP18Filter                       stream: input; value: cutoff resonance */
+    PolyBlepSquare,
+    PolyBlepTriangle,
+    Lp18,          /* LP18Filter                       stream: input; value: cutoff resonance fmod */
     Gain,          /* Gain: input * gain (gain = value input, constant, or a second stream) */
     AddValue,      /* AddValue: input + value */
-    Mixer,         /* Mixer: a + b */
+    Mixer,         /* Mixer: a + b; also the auto-summing stream fan-in (emit_node.rs:153-174) */
     Sub,           /* compound source expression `a - b` (codegen/mod.rs:433-472) */
     Crossfade,     /* Crossfade: two outputs */
     HardClip,      /* HardClip */
+    Expr,          /* one operator of a compound source expression; `op` says which (ExprOp) */
 };
+
+/* operators of compound connection sources (`a.x * gain + offset -> out`, `x.tanh() -> ...`):
+   x = in[0], y = in[1] (stream), p = value input / literal (pid[0] / cst[0]), q = cst[1] */
+enum class ExprOp : uint8_t {
+    None,
+    AddSS, SubSS, MulSS, DivSS,               /* stream (op) stream */
+    AddSV, SubSV, MulSV, DivSV,               /* stream (op) value  */
+    SubVS, DivVS,                             /* value (op) stream  */
+    Value,                                    /* a value (graph input / literal) read as a stream */
+    Tanh, Abs, Clamp, MinV, MaxV,             /* f32 methods: x.tanh(), x.abs(), x.clamp(p, q), x.min(p), x.max(p) */
+};
+
+constexpr int kMaxStreamIn = 3;
+constexpr int kMaxParams = 8;
 
 constexpr int kGraphInput = -2;      /* stream source: the graph's `audio_in` block */
 constexpr int kNone = -1;
@@ -47,17 +64,36 @@ constexpr uint32_t kNoValue = 0xFFFFFFFFu;
 struct StreamRef { int node = kNone; int port = 0; };   /* node index (or kGraphInput / kNone), output port */
 
 struct Node {
-    const char *name;
+    std::string name;
     NodeType type;
-    StreamRef in[2];                 /* stream inputs (meaning per type, see above) */
-    uint32_t pid[4];                 /* value-input ids of the graph feeding this node (kNoValue: use cst) */
-    float cst[4];                    /* constructor value for unconnected inputs */
+    StreamRef in[kMaxStreamIn];      /* stream inputs (meaning per type, see above) */
+    uint32_t pid[kMaxParams];        /* value-input ids of the graph feeding this node's parameter slots (kNoValue: use cst).
+                                        Slots [0, n_value) are the node's value endpoints; the slots after them are the
+                                        stand-ins of its stream endpoints, read when in[k] is unconnected (constructor
+                                        default) or fed by a graph VALUE input (Value -> Stream edge: a broadcast) */
+    float cst[kMaxParams];           /* constructor value for unconnected slots */
     uint32_t state_base;             /* first SoA state field of this node (engine_types.h) */
+    bool gate = true;                /* AdsrEnvelope: the graph's gate event input is connected */
+    ExprOp op = ExprOp::None;
+    float init[2] = {0.0f, 0.0f};    /* constructor arguments that seed the node's state (TptFilter / LP18Filter: cutoff, q) */
+};
+
+/* a value input of a DSL-compiled graph (`input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];`) */
+struct ValueInput {
+    std::string name;
+    float def = 0.0f;
+    bool has_range = false; float lo = 0.0f, hi = 0.0f; bool log = false;
+    uint32_t ramp = 0;               /* `ramp: N` frames of set_<v>() smoothing (codegen/mod.rs:917-976); 0 = plain f32 field */
 };
 
 struct Graph {
+    std::string name;
     std::vector<Node> nodes;
     StreamRef output;                /* the stream connected to the graph's audio output */
+    /* DSL-compiled graphs only (dsl.hpp); the built-in graph kinds keep their tables in engine.cu */
+    std::vector<ValueInput> inputs;
+    std::string stream_input, event_input, output_name;
+    uint32_t n_state = 0;
 };
 
 struct Launch {
@@ -73,6 +109,17 @@ struct Plan {
 };
 
 inline int n_outputs(NodeType t) { return t == NodeType::Crossfade ? 2 : 1; }
+/* SoA state words per voice of a node type (engine_types.h / nodes.cuh state structs) */
+inline uint32_t n_state_words(NodeType t) {
+    switch (t) {
+    case NodeType::Adsr: return 4;            /* stage, rem, level, vel */
+    case NodeType::FmOperator: return 2;      /* phase, prev */
+    case NodeType::Tpt: return 7;             /* z0 z1 cur_cutoff cur_q h g k */
+    case NodeType::PolyBlepSine: case NodeType::PolyBlepSaw: case NodeType::PolyBlepSquare: case NodeType::PolyBlepTriangle: return 1;
+    case NodeType::Lp18: return 9;
+    default: return 0;
+    }
+}
 
 /* Kahn's algorithm in waves: wave k holds every node whose producers all sit in earlier waves */
 inline bool compile(const Graph &g, Plan &p, std::string &err) {
@@ -121,6 +168,9 @@ inline const char *type_name(NodeType t) {
     case NodeType::Tpt: return "TptFilter";
     case NodeType::PolyBlepSine: return "PolyBlepOscillator::sine";
     case NodeType::PolyBlepSaw: return "PolyBlepOscillator::saw";
+    case NodeType::PolyBlepSquare: return "PolyBlepOscillator::square";
+    case NodeType::PolyBlepTriangle: return "PolyBlepOscillator::triangle";
+    case NodeType::Expr: return "Expr";
     case NodeType::Lp18: return "LP18Filter";
     case NodeType::Gain: return "Gain";
     case NodeType::AddValue: return "AddValue";
@@ -129,6 +179,12 @@ inline const char *type_name(NodeType t) {
     case NodeType::Crossfade: return "Crossfade";
     default: return "HardClip";
     }
+}
+
+inline const char *op_name(ExprOp o) {
+    static const char *const names[] = {"", "a + b", "a - b", "a * b", "a / b", "a + v", "a - v", "a * v", "a / v", "v - a", "v / a",
+                                        "value", "tanh", "abs", "clamp", "min", "max"};
+    return names[(int)o];
 }
 
 /* text form of a compiled plan: "launch k: Type node,node | ..." (for tests and DESIGN.md) */

@@ -1,0 +1,207 @@
+"""CPU tests of the `graph!` DSL front end (oscen_b200/csrc/dsl.hpp through the C ABI): parsing of
+both declaration spellings, lowering rules (kind compatibility, fan-in, last-write-wins, constructor
+defaults, dead nodes), the launch plans of the reference graphs, and the compile errors — the
+counterpart of the reference's compiler tests (oscen-graph-compiler/tests/{lower,accumulation,
+expr_lowering}.rs) and compile-fail UI tests (oscen-macros/tests/ui/*.rs).  No GPU needed."""
+import os
+import re
+
+import pytest
+
+from oscen_b200 import abi
+
+GRAPHS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "graphs")
+
+
+def text(name):
+    with open(os.path.join(GRAPHS, name)) as f:
+        return f.read()
+
+
+def groups(lines):
+    """launch lines -> list of node-name lists (type label dropped)"""
+    out = []
+    for l in lines:
+        names = re.search(r"\[(.*)\]", l).group(1)
+        out.append([re.sub(r" \{.*\}$", "", n.strip()) for n in names.split(", ")])
+    return out
+
+
+def builtin_plan(kind):
+    import ctypes as C
+    L = abi.load()
+    buf = C.create_string_buffer(4096)
+    n = L.oscen_b200_plan_describe(kind, buf, len(buf))
+    assert n > 0
+    return buf.value.decode().strip().splitlines()
+
+
+@pytest.mark.parametrize("file,kind", [("fm_voice.graph", abi.GRAPH_FM_VOICE), ("synth.graph", abi.GRAPH_SYNTH),
+                                       ("synth_adsr.graph", abi.GRAPH_SYNTH_ADSR), ("sat_1x.graph", abi.GRAPH_SAT_1X)])
+def test_reference_graphs_compile_to_the_builtin_launch_plans(file, kind):
+    g = abi.Graph(text(file))
+    assert g.launches() == builtin_plan(kind)
+
+
+def test_twin_peaks_plan_and_expression_edge():
+    g = abi.Graph(text("twin_peaks.graph"))
+    want = groups(builtin_plan(abi.GRAPH_TWIN_PEAKS))
+    assert groups(g.launches()) == want == [["filter_a", "filter_b"], ["filter_a.output - filter_b.output"]]
+    d = g.describe()
+    assert "stream input: audio_in" in d and "{a - b}" in d and "state words per voice: 18" in d
+
+
+def test_fm_voice_inputs_follow_declaration_order():
+    g = abi.Graph(text("fm_voice.graph"))
+    assert g.n_inputs == 28
+    assert g.input_id("frequency") == 0 and g.input_id("op3_ratio") == 1 and g.input_id("route") == 20
+    assert g.input_id("filter_env_amount") == 27
+    assert g.input_info(21) == {"name": "filter_cutoff", "default": 2000.0, "range": None, "log": False, "ramp": 0}
+    with pytest.raises(KeyError):
+        g.input_id("gate")                      # the event input is not a value input
+    d = g.describe()
+    assert "event input: gate" in d and "state words per voice: 29" in d
+    # the four envelopes share one launch, so do op-independent stateless nodes of one wave
+    assert g.launches()[0] == "0: AdsrEnvelope [env3, env2, env1, env_filter]"
+
+
+def test_param_spec_forms():
+    g = abi.Graph("""
+        input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];
+        input value q = 0.707 [0.1..10.0];
+        input volume: value = 0.8 { range: 0.0..1.0, unit: " dB", smoother: 50.0, name: "Vol", group: "Out", ramp: 64 };
+        input detune: value = -0.5 [-1.0..1.0, linear];
+        input big: value = 2_000.5f32;
+        input tiny: value = 1e-3;
+        output stream out;
+        node f = TptFilter::new(1000.0, 0.7);
+        node o = PolyBlepOscillator::saw(220.0, 1.0);
+        connection o.output -> f.input; connection cutoff -> f.cutoff; connection q -> f.q;
+        connection f.output * volume -> out;
+    """)
+    assert g.input_info(0) == {"name": "cutoff", "default": 3000.0, "range": (20.0, 20000.0), "log": True, "ramp": 1323}
+    assert g.input_info(1)["range"] == (pytest.approx(0.1), 10.0) and g.input_info(1)["ramp"] == 0
+    assert g.input_info(2)["range"] == (0.0, 1.0) and g.input_info(2)["ramp"] == 64
+    assert g.input_info(3)["default"] == -0.5 and g.input_info(3)["log"] is False
+    assert g.input_info(4)["default"] == 2000.5 and g.input_info(5)["default"] == pytest.approx(1e-3)
+
+
+def test_fan_in_sums_in_statement_order_and_dead_nodes_are_dropped():
+    g = abi.Graph("""
+        name: FanIn;
+        input bias: value = 0.25;
+        output out: stream;
+        nodes {
+            a = PolyBlepOscillator::sine(100.0, 1.0);
+            b = PolyBlepOscillator::saw(200.0, 1.0);
+            c = PolyBlepOscillator::square(300.0, 1.0);
+            unused = PolyBlepOscillator::triangle(50.0, 1.0);
+            sink = Gain::new(1.0);
+            f = TptFilter::new(500.0, 0.7);
+        }
+        connections {
+            a.output -> f.input;
+            b.output -> f.input;
+            c.output -> f.input;
+            bias -> f.input;
+            unused.output -> sink.input;
+            f.output -> out;
+            a.output -> out;
+        }
+    """)
+    d = g.describe()
+    assert "unused" not in d and "sink" not in d
+    gr = groups(g.launches())
+    # ((a + b) + c) + bias into the filter: two Mixer launches (stream + stream) then stream + value
+    flat = [n for grp in gr for n in grp]
+    assert flat.count("f.input (fan-in)") == 3 and flat.count("out (fan-in)") == 1
+    assert flat.index("a") < flat.index("f.input (fan-in)") < flat.index("f") < flat.index("out (fan-in)")
+    assert "state words per voice: 10" in d           # 3 oscillator phases + TptFilter(7); the dead oscillator holds none
+
+
+def test_value_endpoint_last_write_wins_and_constructor_defaults():
+    g = abi.Graph("""
+        input x: value = 1.0;
+        input y: value = 2.0;
+        output stream out;
+        node o = PolyBlepOscillator::saw(220.0, 0.5);
+        connection x -> o.frequency;
+        connection y -> o.frequency;
+        connection 0.25 -> o.amplitude;
+        connection o.output -> out;
+    """)
+    assert g.launches() == ["0: PolyBlepOscillator::saw [o]"]
+
+
+ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
+
+
+@pytest.mark.parametrize("src,frag", [
+    ("output stream out; node x = Foo::new(); connection x.output -> out;", "unknown node type `Foo`"),
+    ("output stream out; node g = Gain::new(1.0); connection g.output -> g.input; connection g.output -> out;", "cycle in graph"),
+    ("input gate: event; output stream out; node f = TptFilter::new(100.0, 0.7); connection gate -> f.input; connection f.output -> out;",
+     "Type mismatch in connection: source is Event but destination expects Stream"),
+    ("output stream out; node o = PolyBlepOscillator::saw(1.0, 1.0); node e = AdsrEnvelope::new(0.1, 0.1, 0.5, 0.1); "
+     "connection o.output -> e.attack; connection e.output -> out;",
+     "Type mismatch in connection: source is Stream but destination expects Value"),
+    ("input v: value = 1.0; output stream out; node e = AdsrEnvelope::new(0.1, 0.1, 0.5, 0.1); connection v -> e.gate; connection e.output -> out;",
+     "Type mismatch in connection: source is Value but destination expects Event"),
+    ("output stream out; node o = PolyBlepOscillator::saw(2_000.0, 0.6) * 4; connection o.output -> out;", "node rates are not compiled"),
+    ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6) * 3; connection o.output -> out;", "rate factor must be in {1, 2, 4, 8}"),
+    ("output stream out; node v = [PolyBlepOscillator::saw(2000.0, 0.6); 4]; connection v.output -> out;", "node arrays"),
+    ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6)\n connection o.output -> out;", "2:2: expected `;`"),
+    (ONE_OSC + "connection o.output -> [4] -> out;", "feedback edges"),
+    (ONE_OSC + "connection o.outptu -> out;", "node `o` has no endpoint `outptu`"),
+    (ONE_OSC + "connection osc.output -> out;", "cannot resolve the source"),
+    (ONE_OSC + "connection o.output -> nowhere;", "cannot resolve the destination"),
+    (ONE_OSC + "connection o.frequency -> out;", "is an input: it cannot be a connection source"),
+    (ONE_OSC + "node p = PolyBlepOscillator::saw(1.0, 1.0); connection p.output -> o.output; connection o.output -> out;",
+     "is an output: it cannot be a connection destination"),
+    ("output stream out; node o = PolyBlepOscillator::saw(2000.0); connection o.output -> out;", "takes 2 argument(s), found 1"),
+    ("output stream out; node o = PolyBlepOscillator::pulse(2000.0, 1.0); connection o.output -> out;", "unknown constructor `PolyBlepOscillator::pulse`"),
+    (ONE_OSC + "node o = Gain::new(1.0); connection o.output -> out;", "duplicate name `o`"),
+    (ONE_OSC + "connection half(o.output) -> out;", "free function `half`"),
+    (ONE_OSC + "connection o.output.sqrt() -> out;", "method `.sqrt()` is not supported"),
+    ("node o = PolyBlepOscillator::saw(2000.0, 0.6);", "declares no stream output"),
+    (ONE_OSC, "nothing is connected to the output"),
+    ("output stream out; output stream out2; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "one stream output per graph"),
+    ("output stream out; input a: stream; input b: stream; connection a -> out;", "one stream input per graph"),
+    ("input audio: stream: Frame<2>; output stream out; connection audio -> out;", "typed endpoints"),
+    ("output stream out; external ir: AudioAsset; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "`external` asset slots"),
+    ("output stream out; name: Late; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "`name:` must be the first item"),
+    (ONE_OSC + "connection [cubic] o.output -> out;", "unknown connection policy `cubic`"),
+    ("output stream out; /* never closed", "unterminated block comment"),
+    (ONE_OSC + "connection o.output -> out; @", "unexpected character `@`"),
+])
+def test_compile_errors(src, frag):
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(src)
+    msg = str(ei.value)
+    assert frag in msg, msg
+    assert re.match(r"^\d+:\d+: ", msg), msg          # every diagnostic carries line:col
+
+
+def test_expressions_lower_to_one_operator_per_launch():
+    g = abi.Graph("""
+        input gain: value = 0.5;
+        input offset: value = 0.1;
+        output stream out;
+        node osc = PolyBlepOscillator::sine(440.0, 1.0);
+        node lfo = PolyBlepOscillator::sine(2.0, 1.0);
+        connection (osc.output * gain + offset) / (lfo.output + 2.0) - 1.0 / lfo.output.abs().max(0.25) -> out;
+    """)
+    ops = re.findall(r"\{([^}]*)\}", g.describe())
+    assert sorted(ops) == sorted(["a * v", "a + v", "a + v", "a / b", "abs", "max", "v / a", "a - b"])
+    # literal (op) literal is folded with f32 arithmetic
+    g2 = abi.Graph("output stream out; node o = PolyBlepOscillator::sine(1.0, 1.0); connection o.output * (0.5 * 0.25) -> out;")
+    assert re.findall(r"\{([^}]*)\}", g2.describe()) == ["a * v"]
+
+
+def test_graph_objects_are_independent_of_the_gpu():
+    # compiling needs no device; creating an engine from it does (and fails loudly without one)
+    g = abi.Graph(text("synth.graph"))
+    import conftest
+    if not conftest.HAS_GPU:
+        with pytest.raises(abi.EngineError) as ei:
+            abi.Engine.from_graph(g, 64)
+        assert "no CUDA device" in str(ei.value)

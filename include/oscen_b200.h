@@ -116,7 +116,8 @@ enum {
     OSCEN_B200_E_CUDA = -3,         /* CUDA runtime error; see oscen_b200_last_error      */
     OSCEN_B200_E_NCCL = -4,         /* NCCL error / NCCL not loadable                     */
     OSCEN_B200_E_NOMEM = -5,
-    OSCEN_B200_E_NO_DEVICE = -6     /* no CUDA device: the engine has NO CPU fallback     */
+    OSCEN_B200_E_NO_DEVICE = -6,    /* no CUDA device: the engine has NO CPU fallback     */
+    OSCEN_B200_E_JIT = -7           /* run-time compilation of a generated kernel failed (NVRTC missing / compile error) */
 };
 
 /* execution plans */
@@ -246,8 +247,18 @@ typedef struct {
 } oscen_b200_input_info;
 int  oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t input_id, oscen_b200_input_info *out);
 /* G::new() + G::init(sr) for n_voices instances of the compiled graph.  cfg->graph_kind must be
-   OSCEN_B200_GRAPH_CUSTOM and cfg->plan OSCEN_B200_PLAN_NODES.  The graph object may be freed afterwards. */
+   OSCEN_B200_GRAPH_CUSTOM.  cfg->plan selects how it runs:
+     OSCEN_B200_PLAN_NODES  the node plan (one kernel per node type per ready wave, CUDA graph);
+     OSCEN_B200_PLAN_FUSED  ONE kernel generated for this graph (every node inlined in topological order,
+                            streams in registers — what `graph!` emits as Rust, codegen/mod.rs:499-572, emitted
+                            here as CUDA) and compiled at create time with NVRTC for sm_100a (needs
+                            libnvrtc.so.12 and the engine's device headers next to the library).
+   Both are bit-identical.  The graph object may be freed afterwards. */
 int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out);
+/* the generated CUDA source of PLAN_FUSED (returns its length), and a compile-only check of it with
+   NVRTC (returns the sm_100a cubin size; the compiler log / error goes to `log`).  Neither needs a GPU. */
+int  oscen_b200_graph_codegen(const oscen_b200_graph *g, char *dst, size_t cap);
+int  oscen_b200_graph_jit_check(const oscen_b200_graph *g, char *log, size_t log_cap);
 
 /* counters: kernels launched by this engine since create; bytes copied H2D / D2H */
 typedef struct {

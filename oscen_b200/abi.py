@@ -39,6 +39,7 @@ SYMBOLS = [
     "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
     "oscen_b200_graph_compile", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
+    "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check",
 ]
 
 
@@ -126,6 +127,8 @@ def load():
     L.oscen_b200_graph_input_id.argtypes = [vp, C.c_char_p]
     L.oscen_b200_graph_input_info.argtypes = [vp, u32, C.POINTER(InputInfo)]
     L.oscen_b200_create_from_graph.argtypes = [vp, C.POINTER(Config), C.POINTER(vp)]
+    L.oscen_b200_graph_codegen.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.oscen_b200_graph_jit_check.argtypes = [vp, C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -173,6 +176,22 @@ class Graph:
         """the launch plan lines of describe(): ["0: AdsrEnvelope [env3, env2]", ...]"""
         return [l for l in self.describe().splitlines() if l[:1].isdigit()]
 
+    def codegen(self):
+        """CUDA source of the fused kernel generated for this graph (PLAN_FUSED)"""
+        buf = C.create_string_buffer(1 << 18)
+        n = self.L.oscen_b200_graph_codegen(self.h, buf, len(buf))
+        if n < 0:
+            raise EngineError(f"graph_codegen rc={n}")
+        return buf.value.decode()
+
+    def jit_check(self):
+        """compile the generated kernel with NVRTC for sm_100a (no GPU needed); returns the cubin size"""
+        log = C.create_string_buffer(1 << 16)
+        n = self.L.oscen_b200_graph_jit_check(self.h, log, len(log))
+        if n < 0:
+            raise EngineError(f"graph_jit_check rc={n}: {log.value.decode()}")
+        return n
+
     def input_id(self, name):
         i = self.L.oscen_b200_graph_input_id(self.h, name.encode())
         if i < 0:
@@ -195,8 +214,8 @@ class Engine:
                  plan=PLAN_FUSED, keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT, graph=None):
         self.L = load()
         h = C.c_void_p()
-        if graph is not None:          # a DSL-compiled graph: always the node plan
-            graph_kind, plan = GRAPH_CUSTOM, PLAN_NODES
+        if graph is not None:          # a DSL-compiled graph: node plan, or a generated fused kernel (NVRTC)
+            graph_kind = GRAPH_CUSTOM
             cfg = Config(graph_kind, n_voices, voices_per_instance, sample_rate, device, plan, keep, 0)
             rc = self.L.oscen_b200_create_from_graph(graph.h, C.byref(cfg), C.byref(h))
         else:
@@ -212,11 +231,12 @@ class Engine:
 
     @classmethod
     def from_graph(cls, graph, n_voices, voices_per_instance=1, sample_rate=48000.0, device=0,
-                   keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT):
-        """G::new() + G::init(sample_rate) for n_voices instances of a DSL-compiled graph (text or Graph)"""
+                   keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT, plan=PLAN_NODES):
+        """G::new() + G::init(sample_rate) for n_voices instances of a DSL-compiled graph (text or Graph);
+        plan = PLAN_NODES (node kernels, CUDA graph) or PLAN_FUSED (one generated kernel, NVRTC)"""
         if isinstance(graph, str):
             graph = Graph(graph)
-        return cls(GRAPH_CUSTOM, n_voices, voices_per_instance, sample_rate, device, PLAN_NODES, keep, graph=graph)
+        return cls(GRAPH_CUSTOM, n_voices, voices_per_instance, sample_rate, device, plan, keep, graph=graph)
 
     def close(self):
         if getattr(self, "h", None):

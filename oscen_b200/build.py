@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "liboscen_b200.so")
 SOURCES = ["engine.cu"]
 DEPS = ["engine.cu", "engine_types.h", "nodes.cuh", "om_math.h", "kernels_common.cuh", "kernel_fm.cuh",
-        "kernel_others.cuh", "kernel_resample.cuh", "kernel_nodes.cuh", "midi_front.hpp", "midi_device.cuh", "plan.hpp", "graphs.hpp", "dsl.hpp"]
+        "kernel_others.cuh", "kernel_resample.cuh", "kernel_nodes.cuh", "midi_front.hpp", "midi_device.cuh", "plan.hpp", "graphs.hpp", "dsl.hpp", "codegen.hpp", "jit.hpp", "state_io.cuh", "rtc_prelude.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-cudart", "static"]

@@ -25,6 +25,8 @@
 #include "kernel_resample.cuh"
 #include "graphs.hpp"
 #include "dsl.hpp"
+#include "codegen.hpp"
+#include "jit.hpp"
 #include "midi_front.hpp"
 #include "midi_device.cuh"
 
@@ -37,6 +39,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
+const char *const kJitKernelName = "oscen_b200_generated_kernel";
 const uint32_t kNInputs[7] = {28, 3, 2, 2, 9, 4, 8};       /* clip graphs: no value inputs */
 bool is_clip(uint32_t kind) { return kind >= OSCEN_B200_GRAPH_CLIP_REF && kind < OSCEN_B200_GRAPH_CUSTOM; }
 int clip_policy(uint32_t kind) { return kind == OSCEN_B200_GRAPH_CLIP_REF ? POL_LATCH : (int)(kind - OSCEN_B200_GRAPH_CLIP_OS_BASE) / 3; }
@@ -165,7 +168,7 @@ struct oscen_b200_engine {
 
     bool has_stream_in = false;          /* the graph declares a per-voice stream input */
     uint32_t lcg_field = 0;              /* first of the two state words of the device-side input LCG */
-    std::vector<uint32_t> custom_init;   /* DSL-compiled graph: initial SoA state of one voice */
+    jit::Kernel jit;                     /* DSL-compiled graph, PLAN_FUSED: the kernel codegen.hpp generated, compiled by NVRTC */
 
     /* node plan */
     plan::Graph graph;
@@ -336,6 +339,10 @@ int launch_fused(oscen_b200_engine *e, bool general) {
     case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kCta, kEpDyn, e->stream>>>(a); break;
     case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); break;
     case OSCEN_B200_GRAPH_SYNTH_ADSR: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_CUSTOM: {
+        const int rc = e->jit.launch(grid, kCta, (void *)e->stream, &a);
+        if (rc != 0) { e->err = "cuLaunchKernel (generated kernel): " + jit::driver_error(rc); return OSCEN_B200_E_CUDA; }
+    } break;
     default: launch_clip(e, a, grid); break;
     }
     e->stats.kernel_launches++;
@@ -476,6 +483,7 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     if (e->p2p) for (int r = 0; r < e->n_ranks; ++r) if (r != e->rank && e->peers.peer[r]) cudaIpcCloseMemHandle(e->peers.peer[r]);
     cudaFree(e->d_xchg); cudaFree(e->d_p2p_error);
     for (auto &g : e->graph_exec) if (g) cudaGraphExecDestroy(g);
+    e->jit.unload();
     for (float *p : e->d_streams) cudaFree(p);
     cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
     cudaFree(e->d_events); cudaFree(e->d_ctl); cudaFree(e->d_stream_in);
@@ -506,9 +514,15 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         return OSCEN_B200_E_ARG;
     }
     plan::Graph pg; plan::Plan pp;
+    jit::Kernel jk;
     if (custom) {
-        if (cfg->plan != OSCEN_B200_PLAN_NODES) { g_create_error = "a DSL-compiled graph runs as a node plan: set plan = OSCEN_B200_PLAN_NODES"; return OSCEN_B200_E_ARG; }
         pg = custom->g; pp = custom->p;
+        if (cfg->plan == OSCEN_B200_PLAN_FUSED) {
+            /* generate the fused kernel and compile it for sm_100a before any device memory is taken */
+            jk.source = codegen::fused_kernel_source(pg, pp, kJitKernelName);
+            std::string jerr;
+            if (!jit::compile_cubin(jk.source, jk.cubin, jk.log, jerr)) { g_create_error = "PLAN_FUSED (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }
+        }
     } else if (cfg->plan == OSCEN_B200_PLAN_NODES) {
         std::string perr;
         if (!plan::for_kind(cfg->graph_kind, pg)) {
@@ -561,6 +575,13 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         CK(e, cudaMemsetAsync(e->d_mix, 0, (size_t)kMaxBlock * e->channels * sizeof(float), e->stream));
         CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float) + 16));   /* + peer-timeout flag */
         CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1)); CK(e, cudaEventCreate(&e->evk));
+        if (custom && cfg->plan == OSCEN_B200_PLAN_FUSED) {
+            CK(e, cudaFree(nullptr));                              /* the runtime's primary context is current from here on */
+            e->graph = pg; e->plan = pp;
+            e->jit = std::move(jk);
+            std::string jerr;
+            if (!e->jit.load(kJitKernelName, jerr)) { e->err = "PLAN_FUSED (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }
+        }
         if (cfg->plan == OSCEN_B200_PLAN_NODES) {
             e->graph = pg; e->plan = pp;
             e->d_streams.resize((size_t)pp.n_streams + 1, nullptr);      /* + 1: device-generated graph input */
@@ -638,6 +659,25 @@ int oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t id, oscen_b2
     out->default_value = v.def; out->has_range = v.has_range ? 1u : 0u; out->range_min = v.lo; out->range_max = v.hi;
     out->logarithmic = v.log ? 1u : 0u; out->ramp_frames = v.ramp;
     return 0;
+}
+/* the CUDA source codegen.hpp generates for PLAN_FUSED (inspection / tests); returns its length */
+int oscen_b200_graph_codegen(const oscen_b200_graph *g, char *dst, size_t cap) {
+    if (!g || !dst || cap == 0) return OSCEN_B200_E_ARG;
+    const std::string s = codegen::fused_kernel_source(g->g, g->p, kJitKernelName);
+    if (s.size() + 1 > cap) return OSCEN_B200_E_ARG;
+    memcpy(dst, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+/* compile the generated kernel for sm_100a with NVRTC without loading it (needs no GPU); returns the
+   cubin size in bytes, or OSCEN_B200_E_JIT with the compiler log in `log` */
+int oscen_b200_graph_jit_check(const oscen_b200_graph *g, char *log, size_t log_cap) {
+    if (log && log_cap) log[0] = 0;
+    if (!g) return OSCEN_B200_E_ARG;
+    std::vector<char> cubin; std::string l, err;
+    const bool ok = jit::compile_cubin(codegen::fused_kernel_source(g->g, g->p, kJitKernelName), cubin, l, err);
+    const std::string &msg = ok ? l : err;
+    if (log && log_cap) { strncpy(log, msg.c_str(), log_cap - 1); log[log_cap - 1] = 0; }
+    return ok ? (int)cubin.size() : OSCEN_B200_E_JIT;
 }
 int oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out) {
     if (!g) { g_create_error = "null graph"; return OSCEN_B200_E_ARG; }

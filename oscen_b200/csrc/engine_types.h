@@ -3,7 +3,9 @@
  * state-field maps).  See DESIGN.md "Data layout in HBM".
  */
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <stdint.h>
+#endif
 
 #include "nodes.cuh"
 

@@ -1,0 +1,145 @@
+/*
+ * jit.hpp — run-time compilation of generated fused kernels (codegen.hpp): NVRTC (dlopen'd
+ * libnvrtc.so.12) -> sm_100a cubin -> driver-API module (dlopen'd libcuda.so.1) -> CUfunction
+ * launched on the engine's stream.  Neither library is a link-time dependency: an engine that only
+ * runs the built-in kernels never loads them, and a host without them gets a clean error from
+ * create(), never a different code path.
+ *
+ * Compile flags mirror the in-tree build (oscen_b200/build.py): -arch=sm_100a, --fmad=false (rustc
+ * never contracts a*b+c), IEEE division / sqrt, no fast-math, -lineinfo.  The generated translation
+ * unit includes the engine's own device headers from oscen_b200/csrc (located next to the shared
+ * library, or $OSCEN_B200_CSRC), so the node bodies are the very same functions the hand-written
+ * kernels call.
+ */
+#pragma once
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace oscen {
+namespace jit {
+
+/* ---- NVRTC (subset) */
+struct Nvrtc {
+    void *lib = nullptr;
+    int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    int (*DestroyProgram)(void **) = nullptr;
+    int (*CompileProgram)(void *, int, const char *const *) = nullptr;
+    int (*GetCUBINSize)(void *, size_t *) = nullptr;
+    int (*GetCUBIN)(void *, char *) = nullptr;
+    int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+    int (*GetProgramLog)(void *, char *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+inline Nvrtc &nvrtc() { static Nvrtc n; return n; }
+
+inline bool nvrtc_load(std::string &err) {
+    Nvrtc &n = nvrtc();
+    if (n.lib) return true;
+    const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char *nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (n.lib) break; }
+    if (!n.lib) { err = "NVRTC (libnvrtc.so.12) cannot be loaded: generated fused kernels need it; PLAN_NODES does not"; return false; }
+#define OSC_SYM(field, name) *(void **)(&n.field) = dlsym(n.lib, name)
+    OSC_SYM(CreateProgram, "nvrtcCreateProgram"); OSC_SYM(DestroyProgram, "nvrtcDestroyProgram");
+    OSC_SYM(CompileProgram, "nvrtcCompileProgram"); OSC_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    OSC_SYM(GetCUBIN, "nvrtcGetCUBIN"); OSC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    OSC_SYM(GetProgramLog, "nvrtcGetProgramLog"); OSC_SYM(GetErrorString, "nvrtcGetErrorString");
+#undef OSC_SYM
+    if (!n.CreateProgram || !n.CompileProgram || !n.GetCUBINSize || !n.GetCUBIN) { err = "NVRTC symbols missing"; dlclose(n.lib); n.lib = nullptr; return false; }
+    return true;
+}
+
+/* directory of the engine's device headers: $OSCEN_B200_CSRC, else <dir of this .so>/../csrc */
+inline std::string csrc_dir() {
+    if (const char *e = getenv("OSCEN_B200_CSRC")) return e;
+    Dl_info info;
+    if (dladdr((void *)&csrc_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        const size_t k = p.rfind('/');
+        p = k == std::string::npos ? std::string(".") : p.substr(0, k);
+        return p + "/../csrc";
+    }
+    return "oscen_b200/csrc";
+}
+
+/* source -> sm_100a cubin.  Needs no GPU (the CPU test suite compiles every test graph). */
+inline bool compile_cubin(const std::string &source, std::vector<char> &cubin, std::string &log, std::string &err) {
+    if (!nvrtc_load(err)) return false;
+    Nvrtc &n = nvrtc();
+    void *prog = nullptr;
+    int rc = n.CreateProgram(&prog, source.c_str(), "oscen_b200_generated.cu", 0, nullptr, nullptr);
+    if (rc != 0) { err = std::string("nvrtcCreateProgram: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"); return false; }
+    const std::string inc = "--include-path=" + csrc_dir();
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "--prec-div=true", "--prec-sqrt=true",
+                          "-lineinfo", "-default-device", inc.c_str()};
+    rc = n.CompileProgram(prog, (int)(sizeof opts / sizeof opts[0]), opts);
+    size_t ls = 0;
+    if (n.GetProgramLogSize && n.GetProgramLogSize(prog, &ls) == 0 && ls > 1) { log.resize(ls); n.GetProgramLog(prog, &log[0]); }
+    if (rc != 0) {
+        err = std::string("nvrtcCompileProgram: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error") + "\n" + log;
+        n.DestroyProgram(&prog);
+        return false;
+    }
+    size_t cs = 0;
+    rc = n.GetCUBINSize(prog, &cs);
+    if (rc == 0 && cs) { cubin.resize(cs); rc = n.GetCUBIN(prog, cubin.data()); }
+    n.DestroyProgram(&prog);
+    if (rc != 0 || cubin.empty()) { err = "nvrtcGetCUBIN failed"; return false; }
+    return true;
+}
+
+/* ---- driver API (subset) */
+struct Driver {
+    void *lib = nullptr;
+    int (*ModuleLoadData)(void **, const void *) = nullptr;
+    int (*ModuleUnload)(void *) = nullptr;
+    int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
+    int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
+    int (*GetErrorString)(int, const char **) = nullptr;
+};
+inline Driver &driver() { static Driver d; return d; }
+inline bool driver_load(std::string &err) {
+    Driver &d = driver();
+    if (d.lib) return true;
+    d.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!d.lib) { err = "libcuda.so.1 cannot be loaded"; return false; }
+#define OSC_SYM(field, name) *(void **)(&d.field) = dlsym(d.lib, name)
+    OSC_SYM(ModuleLoadData, "cuModuleLoadData"); OSC_SYM(ModuleUnload, "cuModuleUnload");
+    OSC_SYM(ModuleGetFunction, "cuModuleGetFunction"); OSC_SYM(LaunchKernel, "cuLaunchKernel");
+    OSC_SYM(GetErrorString, "cuGetErrorString");
+#undef OSC_SYM
+    if (!d.ModuleLoadData || !d.ModuleGetFunction || !d.LaunchKernel) { err = "driver API symbols missing"; return false; }
+    return true;
+}
+inline std::string driver_error(int rc) {
+    const char *s = nullptr;
+    if (driver().GetErrorString && driver().GetErrorString(rc, &s) == 0 && s) return s;
+    return "CUDA driver error " + std::to_string(rc);
+}
+
+struct Kernel {
+    void *module = nullptr, *function = nullptr;
+    std::vector<char> cubin;
+    std::string source, log;
+    /* the runtime's primary context must be current on this thread (cudaSetDevice + any runtime call) */
+    bool load(const char *name, std::string &err) {
+        if (!driver_load(err)) return false;
+        int rc = driver().ModuleLoadData(&module, cubin.data());
+        if (rc != 0) { err = "cuModuleLoadData: " + driver_error(rc); return false; }
+        rc = driver().ModuleGetFunction(&function, module, name);
+        if (rc != 0) { err = "cuModuleGetFunction: " + driver_error(rc); return false; }
+        return true;
+    }
+    int launch(unsigned grid, unsigned block, void *stream, void *kernel_args_struct) const {
+        void *params[] = {kernel_args_struct};
+        return driver().LaunchKernel(function, grid, 1, 1, block, 1, 1, 0, stream, params, nullptr);
+    }
+    void unload() { if (module && driver().ModuleUnload) driver().ModuleUnload(module); module = nullptr; function = nullptr; }
+};
+
+}  // namespace jit
+}  // namespace oscen

@@ -13,6 +13,7 @@
  */
 #pragma once
 #include "kernels_common.cuh"
+#include "state_io.cuh"
 
 /* 1: move the per-voice state rows HBM <-> shared memory with TMA bulk copies (cp.async.bulk +
    mbarrier) instead of per-thread coalesced loads/stores.  Built, bit-exact, measured SLOWER on
@@ -32,31 +33,6 @@ enum : uint32_t {   /* == OSCEN_B200_FM_* */
     I_OP1_RATIO, I_OP1_A, I_OP1_D, I_OP1_S, I_OP1_R, I_ROUTE,
     I_CUTOFF, I_RES, I_F_A, I_F_D, I_F_S, I_F_R, I_ENV_AMT, I_FM_N
 };
-
-OSC_D void adsr_load(AdsrState &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
-    s.stage = __float_as_uint(st[(size_t)(base + 0) * n + v]);
-    s.rem = __float_as_uint(st[(size_t)(base + 1) * n + v]);
-    s.level = st[(size_t)(base + 2) * n + v];
-    s.vel = st[(size_t)(base + 3) * n + v];
-}
-OSC_D void adsr_store(const AdsrState &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
-    st[(size_t)(base + 0) * n + v] = __uint_as_float(s.stage);
-    st[(size_t)(base + 1) * n + v] = __uint_as_float(s.rem);
-    st[(size_t)(base + 2) * n + v] = s.level;
-    st[(size_t)(base + 3) * n + v] = s.vel;
-}
-OSC_D void tpt_load(TptState &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
-    s.z0 = st[(size_t)(base + 0) * n + v]; s.z1 = st[(size_t)(base + 1) * n + v];
-    s.cur_cutoff = st[(size_t)(base + 2) * n + v]; s.cur_q = st[(size_t)(base + 3) * n + v];
-    s.h = st[(size_t)(base + 4) * n + v]; s.g = st[(size_t)(base + 5) * n + v];
-    s.k = st[(size_t)(base + 6) * n + v];
-}
-OSC_D void tpt_store(const TptState &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
-    st[(size_t)(base + 0) * n + v] = s.z0; st[(size_t)(base + 1) * n + v] = s.z1;
-    st[(size_t)(base + 2) * n + v] = s.cur_cutoff; st[(size_t)(base + 3) * n + v] = s.cur_q;
-    st[(size_t)(base + 4) * n + v] = s.h; st[(size_t)(base + 5) * n + v] = s.g;
-    st[(size_t)(base + 6) * n + v] = s.k;
-}
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ KernelArgs a) {

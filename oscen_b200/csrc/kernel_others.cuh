@@ -31,32 +31,8 @@ struct SmallParams {
     }
 };
 
-/* 64-bit LCG noise of oscen-lib/tests/realtime_safety.rs:21-33 */
-OSC_HD unsigned long long lcg_seed_state(unsigned long long seed) {
-    return seed * 2862933555777941757ull + 3037000493ull;
-}
-OSC_HD float lcg_next(unsigned long long &state) {
-    state = state * 6364136223846793005ull + 1442695040888963407ull;
-    return (float)(uint32_t)(state >> 33) / 2147483648.0f - 1.0f;
-}
-
 /* ============================================================== TwinPeaksGraph ==== */
 /* examples/nih-twin-peaks/src/lib.rs:15-48: audio_in -> filter_a, filter_b; out = a - b */
-OSC_D void lp18_load(Lp18State &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
-    s.z0 = st[(size_t)(base + 0) * n + v]; s.z1 = st[(size_t)(base + 1) * n + v];
-    s.z2 = st[(size_t)(base + 2) * n + v]; s.g = st[(size_t)(base + 3) * n + v];
-    s.h = st[(size_t)(base + 4) * n + v]; s.last_cutoff = st[(size_t)(base + 5) * n + v];
-    s.last_fmod = st[(size_t)(base + 6) * n + v]; s.last_resonance = st[(size_t)(base + 7) * n + v];
-    s.resonance = st[(size_t)(base + 8) * n + v];
-}
-OSC_D void lp18_store(const Lp18State &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
-    st[(size_t)(base + 0) * n + v] = s.z0; st[(size_t)(base + 1) * n + v] = s.z1;
-    st[(size_t)(base + 2) * n + v] = s.z2; st[(size_t)(base + 3) * n + v] = s.g;
-    st[(size_t)(base + 4) * n + v] = s.h; st[(size_t)(base + 5) * n + v] = s.last_cutoff;
-    st[(size_t)(base + 6) * n + v] = s.last_fmod; st[(size_t)(base + 7) * n + v] = s.last_resonance;
-    st[(size_t)(base + 8) * n + v] = s.resonance;
-}
-
 __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ float tile[kTileF * kTileW];
     __shared__ float isum[kTileF * kCta];

@@ -12,9 +12,13 @@
  * Citations: path:line under the reference repo (reedrosenbluth/oscen @ 8061f7d5).
  */
 #pragma once
+#if defined(__CUDACC_RTC__)
+#include "rtc_prelude.h"
+#else
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
+#endif
 
 #include "om_math.h"
 

@@ -22,9 +22,13 @@
 #ifndef OSCEN_B200_OM_MATH_H
 #define OSCEN_B200_OM_MATH_H
 
+#if defined(__CUDACC_RTC__)
+#include "rtc_prelude.h"
+#else
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#endif
 
 #if defined(__CUDACC__)
 #define OM_HD __host__ __device__ __forceinline__

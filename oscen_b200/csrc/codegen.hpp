@@ -63,6 +63,44 @@ struct Emitter {
         default: return "WAVE_TRIANGLE";
         }
     }
+    /* sample rate a node runs at: inner-rate (`* N`) nodes get sr * N (codegen/emit_struct.rs:578-581) */
+    std::string SR(int i) const {
+        const plan::Node &nd = g.nodes[i];
+        return (nd.rate_log2 > 0 && nd.type != plan::NodeType::Up && nd.type != plan::NodeType::Down) ? "sri" : "sr";
+    }
+    /* multirate frame body phases (codegen/emit_frame.rs:114-176): 0 outer nodes before the inner loop, 1 Up edges,
+       2 inner-rate nodes, 3 Down edges, 4 outer nodes that depend on a Down edge */
+    std::vector<int> phases() const {
+        const int n = (int)g.nodes.size();
+        std::vector<char> tainted(n, 0);
+        bool moved = true;
+        while (moved) {
+            moved = false;
+            for (int i = 0; i < n; ++i) {
+                if (tainted[i]) continue;
+                bool t = g.nodes[i].type == plan::NodeType::Down;
+                for (const plan::StreamRef &r : g.nodes[i].in) if (r.node >= 0 && tainted[r.node]) t = true;
+                if (t) { tainted[i] = 1; moved = true; }
+            }
+        }
+        std::vector<int> ph(n, 0);
+        for (int i = 0; i < n; ++i) {
+            const plan::Node &nd = g.nodes[i];
+            if (nd.type == plan::NodeType::Up) ph[i] = 1;
+            else if (nd.type == plan::NodeType::Down) ph[i] = 3;
+            else if (nd.rate_log2 > 0) ph[i] = 2;
+            else ph[i] = tainted[i] ? 4 : 0;
+        }
+        return ph;
+    }
+    std::string edge_type(int i) const {
+        const plan::Node &nd = g.nodes[i];
+        return std::string(nd.type == plan::NodeType::Up ? "UpEdge<" : "DownEdge<") + std::to_string(nd.policy) + ", " + std::to_string(nd.rate_log2) + ">";
+    }
+    static uint32_t edge_smem_floats(const plan::Node &nd) {
+        if (nd.policy != plan::kPolicySinc) return 0u;
+        return (nd.type == plan::NodeType::Up ? 24u : nd.type == plan::NodeType::Down ? 48u : 0u) * (uint32_t)nd.rate_log2;
+    }
     static bool is_polyblep(plan::NodeType t) {
         return t == plan::NodeType::PolyBlepSine || t == plan::NodeType::PolyBlepSaw || t == plan::NodeType::PolyBlepSquare || t == plan::NodeType::PolyBlepTriangle;
     }
@@ -74,7 +112,9 @@ struct Emitter {
         const bool has_in = !g.stream_input.empty();
         char b[256];
         line(0, "/* generated by oscen_b200 codegen.hpp from graph `" + (g.name.empty() ? std::string("<anonymous>") : g.name) + "` — do not edit */");
-        line(0, "#include \"state_io.cuh\"");
+        const bool multirate = g.inner_log2 > 0;
+        const int NI = 1 << g.inner_log2;
+        line(0, multirate ? "#include \"resample_edges.cuh\"" : "#include \"state_io.cuh\"");
         line(0, "using namespace oscen;");
         snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(kCta) %s(const __grid_constant__ KernelArgs a) {", kernel_name);
         line(0, b);
@@ -88,6 +128,11 @@ struct Emitter {
         line(1, "const float sr = a.u.sr;");
         line(1, "const uint32_t col = tile_col(threadIdx.x, a.vpi);");
         line(1, "(void)sr; (void)ramp_mask;");
+        if (multirate) {
+            line(1, "extern __shared__ float dyn[];                 /* FIR rings of the [sinc] cross-rate edges */");
+            line(1, "const float sri = sr * " + std::to_string(NI) + ".0f;    /* inner-rate nodes: set_sample_rate(sr * N) */");
+            line(1, "(void)sri; (void)dyn;");
+        }
         /* ---- value inputs */
         snprintf(b, sizeof b, "float P[%u];", ni ? ni : 1u); line(1, b);
         for (uint32_t i = 0; i < ni; ++i) {
@@ -95,6 +140,7 @@ struct Emitter {
         }
         if (!ni) line(1, "P[0] = 0.0f;");
         /* ---- node state: HBM -> registers */
+        uint32_t smem_off = 0;
         for (int i = 0; i < n_nodes; ++i) {
             const plan::Node &nd = g.nodes[i];
             const std::string base = std::to_string(nd.state_base) + "u";
@@ -102,14 +148,18 @@ struct Emitter {
             switch (nd.type) {
             case T::Adsr:
                 line(1, "AdsrState " + N(i) + "; adsr_load(" + N(i) + ", a.state, " + base + ", n, vs);");
-                line(1, "AdsrDerived " + D(i) + "; adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", sr);");
+                line(1, "AdsrDerived " + D(i) + "; adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", " + SR(i) + ");");
                 break;
             case T::FmOperator:
                 line(1, "FmOpState " + N(i) + "; " + N(i) + ".phase = a.state[(size_t)(" + base + " + 0u) * n + vs]; " + N(i) + ".prev = a.state[(size_t)(" + base + " + 1u) * n + vs];");
-                line(1, N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", sr);");
+                line(1, N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");");
                 break;
             case T::Tpt: line(1, "TptState " + N(i) + "; tpt_load(" + N(i) + ", a.state, " + base + ", n, vs);"); break;
             case T::Lp18: line(1, "Lp18State " + N(i) + "; lp18_load(" + N(i) + ", a.state, " + base + ", n, vs);"); break;
+            case T::Up: case T::Down:
+                line(1, edge_type(i) + " " + N(i) + "; " + N(i) + ".load(a.state, " + base + ", n, vs, dyn + " + std::to_string(smem_off) + "u * kCta);");
+                smem_off += edge_smem_floats(nd);
+                break;
             default:
                 if (is_polyblep(nd.type)) line(1, "float " + N(i) + " = a.state[(size_t)" + base + " * n + vs];");
                 break;
@@ -170,25 +220,25 @@ struct Emitter {
         line(5, "ec.advance(ev_end);");
         line(4, "}");
         if (has_in) line(4, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
-        /* ---- the walk: nodes in topological order */
-        for (int i : p.order) {
+        /* ---- the walk: nodes in topological order (multirate graphs: per phase, emit_frame.rs:114-176) */
+        auto emit_node = [&](int i, int ind) {
             const plan::Node &nd = g.nodes[i];
             const std::string o = "const float " + S(i) + " = ";
             const std::string cm = "    /* " + nd.name + " */";
             switch (nd.type) {
-            case T::Adsr: line(4, o + "adsr_process(" + N(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm); break;
-            case T::FmOperator: line(4, o + "fmop_process(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ");" + cm); break;
-            case T::Tpt: line(4, o + "tpt_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + IN(i, 1, 1) + ", " + P(i, 0) + ", " + IN(i, 2, 2) + ", sr);" + cm); break;
-            case T::Lp18: line(4, o + "lp18_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + P(i, 0) + ", " + P(i, 2) + ", " + P(i, 1) + ", sr);" + cm); break;
-            case T::Gain: line(4, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
-            case T::AddValue: line(4, o + IN(i, 0, -1) + " + " + P(i, 0) + ";" + cm); break;
-            case T::Mixer: line(4, o + IN(i, 0, -1) + " + " + IN(i, 1, -1) + ";" + cm); break;
-            case T::Sub: line(4, o + IN(i, 0, -1) + " - " + IN(i, 1, -1) + ";" + cm); break;
-            case T::HardClip: line(4, o + "hardclip_process(" + IN(i, 0, -1) + ");" + cm); break;
+            case T::Adsr: line(ind, o + "adsr_process(" + N(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm); break;
+            case T::FmOperator: line(ind, o + "fmop_process(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ");" + cm); break;
+            case T::Tpt: line(ind, o + "tpt_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + IN(i, 1, 1) + ", " + P(i, 0) + ", " + IN(i, 2, 2) + ", " + SR(i) + ");" + cm); break;
+            case T::Lp18: line(ind, o + "lp18_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + P(i, 0) + ", " + P(i, 2) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm); break;
+            case T::Gain: line(ind, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
+            case T::AddValue: line(ind, o + IN(i, 0, -1) + " + " + P(i, 0) + ";" + cm); break;
+            case T::Mixer: line(ind, o + IN(i, 0, -1) + " + " + IN(i, 1, -1) + ";" + cm); break;
+            case T::Sub: line(ind, o + IN(i, 0, -1) + " - " + IN(i, 1, -1) + ";" + cm); break;
+            case T::HardClip: line(ind, o + "hardclip_process(" + IN(i, 0, -1) + ");" + cm); break;
             case T::Crossfade:
-                line(4, "const float m" + std::to_string(i) + " = clampf(" + P(i, 0) + ", 0.0f, 1.0f);");
-                line(4, "const float " + S(i, 0) + " = " + IN(i, 0, -1) + " * (1.0f - m" + std::to_string(i) + ");" + cm);
-                line(4, "const float " + S(i, 1) + " = " + IN(i, 0, -1) + " * m" + std::to_string(i) + ";");
+                line(ind, "const float m" + std::to_string(i) + " = clampf(" + P(i, 0) + ", 0.0f, 1.0f);");
+                line(ind, "const float " + S(i, 0) + " = " + IN(i, 0, -1) + " * (1.0f - m" + std::to_string(i) + ");" + cm);
+                line(ind, "const float " + S(i, 1) + " = " + IN(i, 0, -1) + " * m" + std::to_string(i) + ";");
                 break;
             case T::Expr: {
                 using O = plan::ExprOp;
@@ -212,12 +262,31 @@ struct Emitter {
                 case O::MinV: e = "fminf(" + x + ", " + pv + ")"; break;
                 default: e = "fmaxf(" + x + ", " + pv + ")"; break;
                 }
-                line(4, o + e + ";" + cm);
+                line(ind, o + e + ";" + cm);
             } break;
             default:
-                line(4, o + "polyblep_process<" + wave(nd.type) + ">(" + N(i) + ", " + IN(i, 1, 4) + ", " + P(i, 0) + ", " + IN(i, 0, 3) + ", " + P(i, 1) + ", " + P(i, 2) + ", sr);" + cm);
+                line(ind, o + "polyblep_process<" + wave(nd.type) + ">(" + N(i) + ", " + IN(i, 1, 4) + ", " + P(i, 0) + ", " + IN(i, 0, 3) + ", " + P(i, 1) + ", " + P(i, 2) + ", " + SR(i) + ");" + cm);
                 break;
             }
+        };
+        if (!multirate) {
+            for (int i : p.order) emit_node(i, 4);
+        } else {
+            const std::vector<int> ph = phases();
+            const std::string ns = std::to_string(NI);
+            for (int i : p.order) if (ph[i] == 0) emit_node(i, 4);
+            for (int i : p.order) if (ph[i] == 1) {                       /* step 4: Up-edge warm-up */
+                line(4, "float u" + std::to_string(i) + "[" + ns + "]; " + N(i) + ".up(" + IN(i, 0, -1) + ", u" + std::to_string(i) + ");    /* " + g.nodes[i].name + " */");
+            }
+            for (int i : p.order) if (ph[i] == 3) line(4, "float w" + std::to_string(i) + "[" + ns + "];");      /* step 5: Down accumulators */
+            line(4, "_Pragma(\"unroll\") for (int inner = 0; inner < " + ns + "; ++inner) {    /* step 6: N inner ticks */");
+            for (int i : p.order) if (ph[i] == 1) line(5, "const float " + S(i) + " = u" + std::to_string(i) + "[inner];");
+            for (int i : p.order) if (ph[i] == 2) emit_node(i, 5);
+            for (int i : p.order) if (ph[i] == 3) line(5, "w" + std::to_string(i) + "[inner] = " + IN(i, 0, -1) + ";");
+            line(4, "}");
+            for (int i : p.order) if (ph[i] == 3)                         /* step 7: downsample once per outer tick */
+                line(4, "const float " + S(i) + " = " + N(i) + ".down(w" + std::to_string(i) + ");    /* " + g.nodes[i].name + " */");
+            for (int i : p.order) if (ph[i] == 4) emit_node(i, 4);        /* step 7.5: post-inner outer nodes */
         }
         line(4, "y = " + S(g.output.node, g.output.port) + ";    /* -> " + g.output_name + " */");
         line(4, "if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;");
@@ -238,6 +307,7 @@ struct Emitter {
                 break;
             case T::Tpt: line(2, "tpt_store(" + N(i) + ", a.state, " + base + ", n, v);"); break;
             case T::Lp18: line(2, "lp18_store(" + N(i) + ", a.state, " + base + ", n, v);"); break;
+            case T::Up: case T::Down: line(2, N(i) + ".store(a.state, " + base + ", n, v);"); break;
             default:
                 if (is_polyblep(nd.type)) line(2, "a.state[(size_t)" + base + " * n + v] = " + N(i) + ";");
                 break;
@@ -253,6 +323,13 @@ struct Emitter {
         return s;
     }
 };
+
+/* dynamic shared memory of the generated kernel: the FIR rings of its [sinc] cross-rate edges */
+inline size_t dyn_smem_bytes(const plan::Graph &g) {
+    size_t floats = 0;
+    for (const plan::Node &nd : g.nodes) floats += Emitter::edge_smem_floats(nd);
+    return floats * 64u * sizeof(float);      /* x kCta threads */
+}
 
 inline std::string fused_kernel_source(const plan::Graph &g, const plan::Plan &p, const char *kernel_name = "oscen_b200_generated_kernel") {
     Emitter e(g, p);

@@ -465,6 +465,7 @@ struct Operand {
     plan::StreamRef s;
     uint32_t pid = plan::kNoValue;
     float c = 0.0f;
+    bool cross = false;                  /* the term went through a cross-rate resampler (no fan-in summing) */
     Kind kind() const { return k == Stream ? Kind::Stream : Kind::Value; }
 };
 
@@ -522,10 +523,11 @@ public:
         Operand o = sum_terms(out_terms, g.output_name);
         if (o.k != Operand::Stream || o.s.node < 0) o = materialise(o, g.output_name);   /* a bare value / graph input copied to the output */
         g.output = o.s;
-        if (!drop_dead_nodes()) return false;
+        if (err.set || !drop_dead_nodes()) return false;
+        if (!check_rate_phases()) return false;
         /* ---- SoA state layout: nodes in declaration order */
         uint32_t base = 0;
-        for (plan::Node &nd : g.nodes) { nd.state_base = base; base += plan::n_state_words(nd.type); }
+        for (plan::Node &nd : g.nodes) { nd.state_base = base; base += plan::n_state_words(nd); }
         g.n_state = base;
         return !err.set;
     }
@@ -544,12 +546,18 @@ private:
     bool node(const NodeDecl &d) {
         if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
         if (d.array) { err.at(d.at, "node arrays (`[T; N]`) are not compiled to a node plan: the engine's voices_per_instance is the array axis"); return false; }
-        if (d.rate) { err.at(d.at, "`* N` / `/ N` node rates are not compiled to a node plan (multirate graphs run as fused kernels)"); return false; }
+        if (d.rate < 0) { err.at(d.at, "node undersampling (`/ N`) is not yet supported in v1; only oversampling (`* N`) is implemented"); return false; }
+        int rate_log2 = 0;
+        for (int r = d.rate; r > 1; r >>= 1) ++rate_log2;
+        if (rate_log2) {
+            if (g.inner_log2 && g.inner_log2 != rate_log2) { err.at(d.at, "one oversampling factor per graph: `" + d.name + "` is * " + std::to_string(d.rate) + " but an earlier node is * " + std::to_string(1 << g.inner_log2)); return false; }
+            g.inner_log2 = rate_log2;
+        }
         const TypeInfo *ti = type_info(d.type);
         if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (the node plan has kernels for AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, LP18Filter, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
         if (!d.args_ok) { err.at(d.at, "constructor arguments of `" + d.name + "` must be numeric literals"); return false; }
         plan::Node n{};
-        n.name = d.name; n.gate = false;
+        n.name = d.name; n.gate = false; n.rate_log2 = rate_log2;
         for (int k = 0; k < plan::kMaxParams; ++k) { n.pid[k] = plan::kNoValue; n.cst[k] = 0.0f; }
         for (const Endpoint &ep : ti->eps) if (!ep.is_out && ep.kind != Kind::Event) {
             const int slot = ep.kind == Kind::Value ? ep.slot : ep.standin;
@@ -606,6 +614,13 @@ private:
         return n;
     }
     static Operand stream_of(int node, int port = 0) { Operand o; o.k = Operand::Stream; o.s.node = node; o.s.port = port; return o; }
+    /* log2 of the rate a stream is produced at (0 = the graph's rate); -1 for values and literals, which fit any rate */
+    int rate_of(const Operand &o) const {
+        if (o.k != Operand::Stream) return -1;
+        if (o.s.node < 0) return 0;
+        const plan::Node &n = g.nodes[o.s.node];
+        return n.type == plan::NodeType::Down ? 0 : n.rate_log2;
+    }
 
     /* a value (graph input or literal) read as a stream: one broadcast per frame */
     Operand materialise(const Operand &v, const std::string &label) {
@@ -628,6 +643,11 @@ private:
             return binary(op, materialise(l, label + " (lhs)"), r, label, at);
         }
         plan::Node n = blank(label, plan::NodeType::Expr, O::None);
+        if (ls && rs && rate_of(l) != rate_of(r)) {
+            err.at(at, "v1 does not support arithmetic between streams of different rates; route through an outer-rate node instead");
+            return l;
+        }
+        n.rate_log2 = ls ? rate_of(l) : rate_of(r);
         if (ls && rs) {
             n.op = op == '+' ? O::AddSS : op == '-' ? O::SubSS : op == '*' ? O::MulSS : O::DivSS;
             n.in[0] = l.s; n.in[1] = r.s;
@@ -682,7 +702,7 @@ private:
             Operand l, r; bool le, re;
             if (!source(*e.a, l, le) || !source(*e.b, r, re)) return false;
             if (le || re) { err.at(e.at, "event endpoints cannot take part in arithmetic"); return false; }
-            out = binary(e.op, l, r, text_of(e), e.at); return true;
+            out = binary(e.op, l, r, text_of(e), e.at); return !err.set;
         }
         case Expr::Method: {
             using O = plan::ExprOp;
@@ -693,7 +713,8 @@ private:
             for (auto &m : ms) if (e.name == m.m) {
                 if (e.args.size() != m.n_args) { err.at(e.at, "f32::" + e.name + " takes " + std::to_string(m.n_args) + " literal argument(s)"); return false; }
                 plan::Node n = blank(text_of(e), plan::NodeType::Expr, m.op);
-                n.in[0] = materialise(x, text_of(*e.a)).s;
+                const Operand xs = materialise(x, text_of(*e.a));
+                n.in[0] = xs.s; n.rate_log2 = rate_of(xs);
                 for (size_t i = 0; i < e.args.size(); ++i) n.cst[i] = e.args[i];
                 out = stream_of(add_synth(n)); return true;
             }
@@ -722,6 +743,7 @@ private:
                 return false;
             }
             if (sk == Kind::Event) return mismatch(Kind::Stream);
+            if (!cross_rate(c, src, 0, d.name)) return false;
             out_terms.push_back(src);
             return true;
         }
@@ -745,13 +767,42 @@ private:
             return true;
         default:
             if (sk == Kind::Event) return mismatch(Kind::Stream);
+            if (!cross_rate(c, src, g.nodes[nid].rate_log2, d.a->name + "." + d.name)) return false;
             in_terms[nid][ep->slot].push_back(src);
             return true;
         }
     }
 
+    /* a stream edge whose source and destination run at different rates goes through the connection
+       policy's resampler (ir/lower.rs:741-906: classify_edge_ir; stream edges default to [sinc],
+       value edges latch = plain reads).  One resampler per edge, as the reference keeps one field per edge. */
+    bool cross_rate(const Conn &c, Operand &src, int dst_rate, const std::string &dst_label) {
+        const int sr = rate_of(src);
+        if (sr < 0 || sr == dst_rate) return true;
+        if (sr > 0 && dst_rate > 0) {
+            err.at(c.at, "v1 does not support connections between two differently-rated non-default-rate nodes; route through an outer-rate node instead");
+            return false;
+        }
+        const bool up = sr == 0;
+        const int l = up ? dst_rate : sr;
+        const int policy = c.policy == "sinc_iir" ? plan::kPolicySincIir : c.policy == "linear" ? plan::kPolicyLinear
+                         : c.policy == "latch" ? plan::kPolicyLatch : plan::kPolicySinc;
+        static const char *const pn[] = {"sinc", "sinc_iir", "linear", "latch"};
+        plan::Node n = blank(text_of(*c.src) + " -> " + dst_label + " [" + pn[policy] + (up ? " up x" : " down x") + std::to_string(1 << l) + "]",
+                             up ? plan::NodeType::Up : plan::NodeType::Down, plan::ExprOp::None);
+        n.in[0] = src.s; n.rate_log2 = l; n.policy = policy;
+        src = stream_of(add_synth(n));
+        src.cross = true;
+        return true;
+    }
+
     /* codegen/emit_node.rs:153-174: dst = s0; dst += s1; ... (left fold in statement order) */
     Operand sum_terms(const std::vector<Operand> &terms, const std::string &label) {
+        if (terms.size() > 1) for (const Operand &t : terms) if (t.cross) {
+            Tok at;
+            err.at(at, "fan-in summing supports only same-rate scalar/frame stream sources; saw a cross-rate edge into `" + label + "`");
+            return terms[0];
+        }
         Operand acc = terms[0];
         for (size_t i = 1; i < terms.size(); ++i) {
             Tok t;
@@ -774,6 +825,32 @@ private:
             return true;
         }
         g.nodes[nid].in[k] = materialise(o, label).s;
+        return true;
+    }
+
+    /* multirate frame body (codegen/emit_frame.rs:114-176): outer-rate nodes that feed the oversampled section
+       run before the inner loop, those that depend on a Down edge after it — a node cannot be both */
+    bool check_rate_phases() {
+        const int n = (int)g.nodes.size();
+        g.inner_log2 = 0;
+        for (const plan::Node &nd : g.nodes) if (nd.rate_log2 > 0) g.inner_log2 = nd.rate_log2;
+        if (!g.inner_log2) return true;
+        std::vector<char> tainted(n, 0);                 /* depends (transitively) on a Down edge */
+        bool moved = true;
+        while (moved) {
+            moved = false;
+            for (int i = 0; i < n; ++i) {
+                if (tainted[i]) continue;
+                bool t = g.nodes[i].type == plan::NodeType::Down;
+                for (const plan::StreamRef &r : g.nodes[i].in) if (r.node >= 0 && tainted[r.node]) t = true;
+                if (t) { tainted[i] = 1; moved = true; }
+            }
+        }
+        for (int i = 0; i < n; ++i) if (g.nodes[i].type == plan::NodeType::Up && tainted[i]) {
+            Tok at;
+            err.at(at, "`" + g.nodes[i].name + "`: an outer-rate signal computed from the oversampled section cannot feed it again in the same frame");
+            return false;
+        }
         return true;
     }
 

@@ -520,8 +520,13 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         if (cfg->plan == OSCEN_B200_PLAN_FUSED) {
             /* generate the fused kernel and compile it for sm_100a before any device memory is taken */
             jk.source = codegen::fused_kernel_source(pg, pp, kJitKernelName);
+            jk.dyn_smem = (unsigned)codegen::dyn_smem_bytes(pg);
+            if (jk.dyn_smem > 200u * 1024u) { g_create_error = "PLAN_FUSED (generated kernel): the [sinc] cross-rate edges need more than 200 KB of shared memory per CTA"; return OSCEN_B200_E_ARG; }
             std::string jerr;
             if (!jit::compile_cubin(jk.source, jk.cubin, jk.log, jerr)) { g_create_error = "PLAN_FUSED (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }
+        }
+        else if (pg.inner_log2 > 0) {
+            g_create_error = "PLAN_NODES: a multirate graph (`* N` nodes) runs as a generated kernel: set plan = OSCEN_B200_PLAN_FUSED"; return OSCEN_B200_E_ARG;
         }
     } else if (cfg->plan == OSCEN_B200_PLAN_NODES) {
         std::string perr;
@@ -1117,6 +1122,17 @@ uint32_t oscen_b200_latency_samples(const oscen_b200_engine *e) {
     if (!e) return 0u;
     const uint32_t kind = e->cfg.graph_kind;
     if (kind == OSCEN_B200_GRAPH_SAT_4X) return 33u / 4u;
+    if (kind == OSCEN_B200_GRAPH_CUSTOM) {
+        /* sum over Down edges of the kernel's latency in high-rate samples / factor (codegen/emit_struct.rs:533-566) */
+        uint32_t total = 0;
+        for (const plan::Node &nd : e->graph.nodes) if (nd.type == plan::NodeType::Down) {
+            const uint32_t factor = 1u << nd.rate_log2;
+            const uint32_t lat = nd.policy == plan::kPolicySinc ? 11u * (factor - 1u) : nd.policy == plan::kPolicySincIir ? 2u * (factor - 1u)
+                               : nd.policy == plan::kPolicyLinear ? (factor - 1u) / 2u : 0u;
+            total += lat / factor;
+        }
+        return total;
+    }
     if (is_clip(kind) && clip_log2f(kind) > 0) {
         const uint32_t l = (uint32_t)clip_log2f(kind), factor = 1u << l;
         switch (clip_policy(kind)) {

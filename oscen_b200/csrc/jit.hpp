@@ -100,6 +100,7 @@ struct Driver {
     int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
     int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
     int (*GetErrorString)(int, const char **) = nullptr;
+    int (*FuncSetAttribute)(void *, int, int) = nullptr;
 };
 inline Driver &driver() { static Driver d; return d; }
 inline bool driver_load(std::string &err) {
@@ -110,7 +111,7 @@ inline bool driver_load(std::string &err) {
 #define OSC_SYM(field, name) *(void **)(&d.field) = dlsym(d.lib, name)
     OSC_SYM(ModuleLoadData, "cuModuleLoadData"); OSC_SYM(ModuleUnload, "cuModuleUnload");
     OSC_SYM(ModuleGetFunction, "cuModuleGetFunction"); OSC_SYM(LaunchKernel, "cuLaunchKernel");
-    OSC_SYM(GetErrorString, "cuGetErrorString");
+    OSC_SYM(GetErrorString, "cuGetErrorString"); OSC_SYM(FuncSetAttribute, "cuFuncSetAttribute");
 #undef OSC_SYM
     if (!d.ModuleLoadData || !d.ModuleGetFunction || !d.LaunchKernel) { err = "driver API symbols missing"; return false; }
     return true;
@@ -125,6 +126,7 @@ struct Kernel {
     void *module = nullptr, *function = nullptr;
     std::vector<char> cubin;
     std::string source, log;
+    unsigned dyn_smem = 0;               /* dynamic shared memory per CTA (FIR rings of [sinc] cross-rate edges) */
     /* the runtime's primary context must be current on this thread (cudaSetDevice + any runtime call) */
     bool load(const char *name, std::string &err) {
         if (!driver_load(err)) return false;
@@ -132,11 +134,16 @@ struct Kernel {
         if (rc != 0) { err = "cuModuleLoadData: " + driver_error(rc); return false; }
         rc = driver().ModuleGetFunction(&function, module, name);
         if (rc != 0) { err = "cuModuleGetFunction: " + driver_error(rc); return false; }
+        if (dyn_smem > 0u) {               /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8 (static tiles + rings may pass 48 KB) */
+            if (!driver().FuncSetAttribute) { err = "cuFuncSetAttribute missing"; return false; }
+            rc = driver().FuncSetAttribute(function, 8, (int)dyn_smem);
+            if (rc != 0) { err = "cuFuncSetAttribute(max dynamic shared memory " + std::to_string(dyn_smem) + " B): " + driver_error(rc); return false; }
+        }
         return true;
     }
     int launch(unsigned grid, unsigned block, void *stream, void *kernel_args_struct) const {
         void *params[] = {kernel_args_struct};
-        return driver().LaunchKernel(function, grid, 1, 1, block, 1, 1, 0, stream, params, nullptr);
+        return driver().LaunchKernel(function, grid, 1, 1, block, 1, 1, dyn_smem, stream, params, nullptr);
     }
     void unload() { if (module && driver().ModuleUnload) driver().ModuleUnload(module); module = nullptr; function = nullptr; }
 };

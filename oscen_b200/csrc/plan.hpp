@@ -41,7 +41,10 @@ enum class NodeType : uint8_t {
     Crossfade,     /* Crossfade: two outputs */
     HardClip,      /* HardClip */
     Expr,          /* one operator of a compound source expression; `op` says which (ExprOp) */
+    Up,            /* cross-rate stream edge outer -> inner (`* N` destination): StreamUpsampler of `policy`   */
+    Down,          /* cross-rate stream edge inner -> outer: StreamDownsampler of `policy` (generated kernels only) */
 };
+enum : int { kPolicySinc = 0, kPolicySincIir = 1, kPolicyLinear = 2, kPolicyLatch = 3 };   /* == OSCEN_B200_POLICY_* */
 
 /* operators of compound connection sources (`a.x * gain + offset -> out`, `x.tanh() -> ...`):
    x = in[0], y = in[1] (stream), p = value input / literal (pid[0] / cst[0]), q = cst[1] */
@@ -76,6 +79,8 @@ struct Node {
     bool gate = true;                /* AdsrEnvelope: the graph's gate event input is connected */
     ExprOp op = ExprOp::None;
     float init[2] = {0.0f, 0.0f};    /* constructor arguments that seed the node's state (TptFilter / LP18Filter: cutoff, q) */
+    int rate_log2 = 0;               /* 0: the graph's rate; L: the node runs 2^L times per frame (`= T::new() * N`) at sample rate sr * N */
+    int policy = 0;                  /* Up / Down: connection policy (kPolicy*) */
 };
 
 /* a value input of a DSL-compiled graph (`input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];`) */
@@ -94,6 +99,7 @@ struct Graph {
     std::vector<ValueInput> inputs;
     std::string stream_input, event_input, output_name;
     uint32_t n_state = 0;
+    int inner_log2 = 0;              /* > 0: a multirate graph (one inner rate 2^L per graph); runs as a generated kernel only */
 };
 
 struct Launch {
@@ -110,8 +116,12 @@ struct Plan {
 
 inline int n_outputs(NodeType t) { return t == NodeType::Crossfade ? 2 : 1; }
 /* SoA state words per voice of a node type (engine_types.h / nodes.cuh state structs) */
-inline uint32_t n_state_words(NodeType t) {
-    switch (t) {
+inline uint32_t n_state_words(const Node &nd) {
+    const uint32_t l = (uint32_t)nd.rate_log2;     /* Up / Down: log2 of the edge's factor */
+    switch (nd.type) {
+    /* resampler state per connection policy (resample_edges.cuh; same layout as kernel_resample.cuh) */
+    case NodeType::Up: return nd.policy == kPolicySinc ? 12u * l : nd.policy == kPolicySincIir ? 8u * l : nd.policy == kPolicyLinear ? 1u : 0u;
+    case NodeType::Down: return nd.policy == kPolicySinc ? 24u * l : nd.policy == kPolicySincIir ? 9u * l : 0u;
     case NodeType::Adsr: return 4;            /* stage, rem, level, vel */
     case NodeType::FmOperator: return 2;      /* phase, prev */
     case NodeType::Tpt: return 7;             /* z0 z1 cur_cutoff cur_q h g k */
@@ -171,6 +181,8 @@ inline const char *type_name(NodeType t) {
     case NodeType::PolyBlepSquare: return "PolyBlepOscillator::square";
     case NodeType::PolyBlepTriangle: return "PolyBlepOscillator::triangle";
     case NodeType::Expr: return "Expr";
+    case NodeType::Up: return "UpEdge";
+    case NodeType::Down: return "DownEdge";
     case NodeType::Lp18: return "LP18Filter";
     case NodeType::Gain: return "Gain";
     case NodeType::AddValue: return "AddValue";

@@ -146,7 +146,14 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
      "Type mismatch in connection: source is Stream but destination expects Value"),
     ("input v: value = 1.0; output stream out; node e = AdsrEnvelope::new(0.1, 0.1, 0.5, 0.1); connection v -> e.gate; connection e.output -> out;",
      "Type mismatch in connection: source is Value but destination expects Event"),
-    ("output stream out; node o = PolyBlepOscillator::saw(2_000.0, 0.6) * 4; connection o.output -> out;", "node rates are not compiled"),
+    ("output stream out; node o = PolyBlepOscillator::saw(2_000.0, 0.6) / 2; connection o.output -> out;", "node undersampling (`/ N`) is not yet supported"),
+    ("output stream out; node a = PolyBlepOscillator::saw(1.0, 1.0) * 4; node b = Gain::new(1.0) * 2; connection a.output -> out;", "one oversampling factor per graph"),
+    ("output stream out; node a = PolyBlepOscillator::saw(1.0, 1.0) * 4; node b = PolyBlepOscillator::saw(2.0, 1.0); connection a.output + b.output -> out;",
+     "arithmetic between streams of different rates"),
+    ("output stream out; node a = PolyBlepOscillator::saw(1.0, 1.0) * 4; node b = PolyBlepOscillator::saw(2.0, 1.0) * 4; connection a.output -> out; connection b.output -> out;",
+     "fan-in summing supports only same-rate"),
+    ("output stream out; node a = PolyBlepOscillator::saw(1.0, 1.0) * 2; node f = TptFilter::new(500.0, 0.7); node c = HardClip::new() * 2; "
+     "connection a.output -> f.input; connection f.output -> c.input; connection c.output -> out;", "cannot feed it again in the same frame"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6) * 3; connection o.output -> out;", "rate factor must be in {1, 2, 4, 8}"),
     ("output stream out; node v = [PolyBlepOscillator::saw(2000.0, 0.6); 4]; connection v.output -> out;", "node arrays"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6)\n connection o.output -> out;", "2:2: expected `;`"),
@@ -246,4 +253,53 @@ def test_generated_kernel_for_expression_graph():
     """)
     src = g.codegen()
     assert "om_tanhf_u(" in src and "clampf(" in src and src.count("adsr_on_gate(") == 1
+    assert g.jit_check() > 10000
+
+
+# ------------------------------------------------------------------ multirate graphs (`* N` nodes, cross-rate edges)
+def test_multirate_lowering_inserts_one_resampler_per_cross_rate_edge():
+    g = abi.Graph(text("sat_4x.graph"))
+    d = g.describe()
+    assert g.launches() == ["0: PolyBlepOscillator::saw [osc]", "1: HardClip [clip]", "2: DownEdge [clip.output -> audio_out [sinc down x4]]"]
+    assert "state words per voice: 49" in d                    # phase + SincDownFir<4>: 2 stages x 24 taps (== the built-in SAT layout)
+    src = g.codegen()
+    assert "DownEdge<0, 2>" in src and "const float sri = sr * 4.0f;" in src and 'for (int inner = 0; inner < 4; ++inner)' in src
+    assert src.count(", sri);") == 1                           # only the oscillator sees the inner sample rate
+    assert g.jit_check() > 10000
+
+
+@pytest.mark.parametrize("policy,words", [("sinc", 2 * 12 + 2 * 24), ("sinc_iir", 2 * 8 + 2 * 9), ("linear", 1), ("latch", 0)])
+def test_multirate_policies_default_and_state_words(policy, words):
+    prefix = f"[{policy}] " if policy != "sinc" else ""          # stream edges default to [sinc] (ir/lower.rs refine_kernels)
+    g = abi.Graph(f"""
+        input audio_in: stream; input drive: value = 1.0; output stream out;
+        node g = Gain::new(1.0) * 4;
+        node post = Gain::new(0.5);
+        connection {prefix}audio_in * drive -> g.input;           // the compound source is evaluated at the outer rate, then upsampled
+        connection {prefix}g.output.clamp(-0.7, 0.7) -> post.input;
+        connection post.output -> out;
+    """)
+    d = g.describe()
+    assert f"[{policy} up x4]" in d and f"[{policy} down x4]" in d
+    assert f"state words per voice: {words}" in d
+    src = g.codegen()
+    # phases: outer product -> Up warm-up -> 4 inner ticks (gain, clamp, capture) -> Down finalize -> post gain
+    order = [src.rindex(k) for k in ("x_in * P[0]", ".up(", "for (int inner = 0", "clampf(", ".down(", "/* post */")]
+    assert order == sorted(order)
+    assert g.jit_check() > 10000
+
+
+def test_value_edges_into_inner_nodes_latch():
+    """a value input read by an inner-rate node is a plain field read on every inner tick (Latch, lower.rs refine_kernels)"""
+    g = abi.Graph("""
+        input f: value = 440.0; input gate: event; output stream out;
+        node osc = PolyBlepOscillator::sine(440.0, 1.0) * 2;
+        node env = AdsrEnvelope::new(0.01, 0.1, 0.5, 0.1) * 2;
+        node vca = Gain::new(1.0) * 2;
+        connection f -> osc.frequency; connection gate -> env.gate;
+        connection osc.output -> vca.input; connection env.output -> vca.gain;
+        connection [sinc_iir] vca.output -> out;
+    """)
+    src = g.codegen()
+    assert "adsr_derive_r(d1" in src and ", sri);" in src and "UpEdge" not in src
     assert g.jit_check() > 10000

@@ -15,7 +15,8 @@ from oscen_b200 import abi  # noqa: E402
 
 FRAMES = 256
 CASES = [("fm_voice.graph", abi.GRAPH_FM_VOICE, 8, 0), ("synth_adsr.graph", abi.GRAPH_SYNTH_ADSR, 1, 2),
-         ("twin_peaks.graph", abi.GRAPH_TWIN_PEAKS, 1, None), ("sat_1x.graph", abi.GRAPH_SAT_1X, 1, 0)]
+         ("twin_peaks.graph", abi.GRAPH_TWIN_PEAKS, 1, None), ("sat_1x.graph", abi.GRAPH_SAT_1X, 1, 0),
+         ("sat_4x.graph", abi.GRAPH_SAT_4X, 1, 0)]
 
 
 def run(e, n, freq_id, steps, has_gate, has_in):
@@ -43,7 +44,10 @@ def run(e, n, freq_id, steps, has_gate, has_in):
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    only = sys.argv[3] if len(sys.argv) > 3 else None
     for file, kind, vpi, freq_id in CASES:
+        if only and only not in file:
+            continue
         text = open(os.path.join(ROOT, "tests", "graphs", file)).read()
         g = abi.Graph(text)
         has_gate = "event input:" in g.describe()
@@ -53,7 +57,8 @@ def main():
         t0 = time.perf_counter()
         ways.append(("generated fused kernel (NVRTC)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_FUSED)))
         jit_s = time.perf_counter() - t0
-        ways.append(("node plan (CUDA graph)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_NODES)))
+        if "Edge [" not in g.describe():       # multirate graphs run as generated kernels only
+            ways.append(("node plan (CUDA graph)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_NODES)))
         ways.append(("hand-written fused kernel", abi.Engine(kind, n, vpi, 48000.0, 0, abi.PLAN_FUSED, keep)))
         for name, e in ways:
             k_ms = run(e, n, freq_id, steps, has_gate, has_in)

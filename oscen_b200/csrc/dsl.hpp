@@ -19,10 +19,14 @@
  * on value endpoints, constructor arguments stay on unconnected endpoints, nodes that do not
  * reach an output are dropped.
  *
- * Not compiled to a node plan (reported as errors, never silently ignored): `* N` / `/ N` rates
- * (multirate graphs run as fused kernels, kernel_resample.cuh), node arrays `[T; N]` (the engine's
- * voices_per_instance is the array axis), nested graphs, `-> [N] ->` feedback edges, `external`
- * assets, free-function calls in sources (they name user Rust code).
+ * Multirate: `node = T::new() * N` (N in {2,4,8}, one factor per graph) runs N times per frame at
+ * sample rate sr * N; every stream edge that crosses the rate boundary gets its own resampler node
+ * (Up / Down) of the edge's `[policy]` (default [sinc]; ir/lower.rs:741-906), value edges latch.
+ * Multirate graphs run as generated kernels only (codegen.hpp), not as node plans.
+ *
+ * Reported as errors (never silently ignored): `/ N` rates, mixed factors, node arrays `[T; N]` (the
+ * engine's voices_per_instance is the array axis), nested graphs, `-> [N] ->` feedback edges,
+ * `external` assets, typed endpoints, free-function calls in sources (they name user Rust code).
  *
  * Host-only C++, no CUDA types: unit-tested on the CPU through oscen_b200_graph_compile().
  */

@@ -30,6 +30,10 @@ inline void check(int rc, oscen_b200_engine *e, const char *what) {
 struct GateEvent { uint32_t voice, frame_offset; float velocity; };
 
 class Bank {
+protected:
+    /* for GraphBank: the engine is created from a compiled DSL graph */
+    Bank(uint32_t instances, uint32_t voices_per_instance) : instances_(instances), vpi_(voices_per_instance) {}
+    void adopt(oscen_b200_engine *e) { e_ = e; channels_ = oscen_b200_channels(e_); }
 public:
     Bank(uint32_t graph_kind, uint32_t instances, uint32_t voices_per_instance, float sample_rate,
          int device = 0, uint32_t plan = OSCEN_B200_PLAN_FUSED,
@@ -125,6 +129,53 @@ public:
     void set_cutoff_a(float v) { set_value(OSCEN_B200_TWIN_CUTOFF_A, v); }
     void set_cutoff_b(float v) { set_value(OSCEN_B200_TWIN_CUTOFF_B, v); }
     void set_resonance(float v) { set_value(OSCEN_B200_TWIN_RESONANCE, v); }
+};
+
+/* Any graph, from its `graph!` text: what `graph! { ... }` expands to at Rust compile time is
+   compiled here at run time (oscen_b200_graph_compile: parse -> lower -> plan; PLAN_FUSED additionally
+   generates one CUDA kernel for the graph and compiles it with NVRTC).  Inputs are addressed by the
+   names the DSL declares; `set(name, v)` ramps over the declared `ramp: N` frames like the generated
+   `set_<name>(v)` (codegen/mod.rs:917-976), or assigns when the input has no ramp. */
+class GraphBank : public Bank {
+public:
+    GraphBank(const std::string &dsl_text, uint32_t instances, uint32_t voices_per_instance, float sample_rate, int device = 0,
+              uint32_t plan = OSCEN_B200_PLAN_FUSED, uint32_t keep = OSCEN_B200_KEEP_INSTANCE_OUT)
+        : Bank(instances, voices_per_instance) {
+        char err[1024];
+        if (oscen_b200_graph_compile(dsl_text.c_str(), &g_, err, sizeof err) != 0) throw std::runtime_error(std::string("graph!: ") + err);
+        oscen_b200_config cfg{};
+        cfg.graph_kind = OSCEN_B200_GRAPH_CUSTOM; cfg.n_voices = instances * voices_per_instance;
+        cfg.voices_per_instance = voices_per_instance; cfg.sample_rate = sample_rate;
+        cfg.device = device; cfg.plan = plan; cfg.keep = keep;
+        oscen_b200_engine *e = nullptr;
+        const int rc = oscen_b200_create_from_graph(g_, &cfg, &e);
+        if (rc != 0) { oscen_b200_graph_free(g_); g_ = nullptr; throw std::runtime_error(std::string("oscen_b200_create_from_graph: ") + oscen_b200_last_error(nullptr)); }
+        adopt(e);
+    }
+    ~GraphBank() { oscen_b200_graph_free(g_); }
+    uint32_t input(const std::string &name) const {
+        const int id = oscen_b200_graph_input_id(g_, name.c_str());
+        if (id < 0) throw std::runtime_error("graph has no value input `" + name + "`");
+        return (uint32_t)id;
+    }
+    /* set_<name>(v) */
+    void set(const std::string &name, float v) {
+        const uint32_t id = input(name);
+        oscen_b200_input_info info{};
+        oscen_b200_graph_input_info(g_, id, &info);
+        if (info.ramp_frames) set_value_with_ramp(id, v, info.ramp_frames); else set_value(id, v);
+    }
+    /* set_<name>_immediate(v) / set_<name>_with_ramp(v, frames) */
+    void set_immediate(const std::string &name, float v) { set_value(input(name), v); }
+    void set_with_ramp(const std::string &name, float v, uint32_t frames) { set_value_with_ramp(input(name), v, frames); }
+    std::string describe() const {
+        std::string s(1 << 16, '\0');
+        oscen_b200_graph_describe(g_, &s[0], s.size());
+        s.resize(std::char_traits<char>::length(s.c_str()));
+        return s;
+    }
+private:
+    oscen_b200_graph *g_ = nullptr;
 };
 
 }  // namespace oscen_b200

@@ -238,6 +238,15 @@ void oscen_b200_graph_free(oscen_b200_graph *g);
    voice, then the launch plan "k: NodeType [node, node]".  Returns the number of launches. */
 int  oscen_b200_graph_describe(const oscen_b200_graph *g, char *dst, size_t cap);
 uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g);
+/* Polyphonic graphs.  The text may hold several `graph! { }` blocks; the LAST one is compiled, earlier ones are
+   the graphs it instantiates.  An outer graph of the reference's polyphonic shape (examples/fm-synth/src/lib.rs:
+   22-131: `voices = [Voice::new(); N]` + MidiParser -> VoiceAllocator::<N> -> [MidiVoiceHandler; N], broadcast
+   edges `value -> voices.input`, `voices.output -> out`) compiles to the VOICE graph's plan with
+   voices_per_instance = N: value inputs keep the voice graph's ids but answer to the outer graph's names (with the
+   outer declaration's default / ramp), the MIDI chain enables oscen_b200_push_midi / _push_midi_batch, and the
+   voice sum is the engine's in-order instance fold.  cfg->voices_per_instance must be N or 0 for such a graph. */
+uint32_t oscen_b200_graph_voices_per_instance(const oscen_b200_graph *g);   /* N of the voice array, 1 if not polyphonic */
+int  oscen_b200_graph_has_midi(const oscen_b200_graph *g);
 int  oscen_b200_graph_input_id(const oscen_b200_graph *g, const char *name);          /* >= 0, or OSCEN_B200_E_ARG */
 typedef struct {
     char     name[64];

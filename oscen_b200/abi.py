@@ -39,7 +39,7 @@ SYMBOLS = [
     "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
     "oscen_b200_graph_compile", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
-    "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check",
+    "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
 ]
 
 
@@ -127,6 +127,9 @@ def load():
     L.oscen_b200_graph_input_id.argtypes = [vp, C.c_char_p]
     L.oscen_b200_graph_input_info.argtypes = [vp, u32, C.POINTER(InputInfo)]
     L.oscen_b200_create_from_graph.argtypes = [vp, C.POINTER(Config), C.POINTER(vp)]
+    L.oscen_b200_graph_voices_per_instance.argtypes = [vp]
+    L.oscen_b200_graph_voices_per_instance.restype = u32
+    L.oscen_b200_graph_has_midi.argtypes = [vp]
     L.oscen_b200_graph_codegen.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_jit_check.argtypes = [vp, C.c_char_p, C.c_size_t]
     _lib = L
@@ -153,6 +156,8 @@ class Graph:
             raise GraphCompileError(err.value.decode())
         self.h = h
         self.n_inputs = self.L.oscen_b200_graph_n_inputs(h)
+        self.voices_per_instance = self.L.oscen_b200_graph_voices_per_instance(h)    # N of `voices = [Voice::new(); N]`, else 1
+        self.has_midi = bool(self.L.oscen_b200_graph_has_midi(h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -230,12 +235,15 @@ class Engine:
         self.frames = 0
 
     @classmethod
-    def from_graph(cls, graph, n_voices, voices_per_instance=1, sample_rate=48000.0, device=0,
+    def from_graph(cls, graph, n_voices, voices_per_instance=None, sample_rate=48000.0, device=0,
                    keep=KEEP_VOICE_OUT | KEEP_INSTANCE_OUT, plan=PLAN_NODES):
-        """G::new() + G::init(sample_rate) for n_voices instances of a DSL-compiled graph (text or Graph);
-        plan = PLAN_NODES (node kernels, CUDA graph) or PLAN_FUSED (one generated kernel, NVRTC)"""
+        """G::new() + G::init(sample_rate) for n_voices voices of a DSL-compiled graph (text or Graph);
+        plan = PLAN_NODES (node kernels, CUDA graph) or PLAN_FUSED (one generated kernel, NVRTC).
+        voices_per_instance defaults to the graph's own polyphony (1 unless it holds a voice array)."""
         if isinstance(graph, str):
             graph = Graph(graph)
+        if voices_per_instance is None:
+            voices_per_instance = graph.voices_per_instance
         return cls(GRAPH_CUSTOM, n_voices, voices_per_instance, sample_rate, device, plan, keep, graph=graph)
 
     def close(self):

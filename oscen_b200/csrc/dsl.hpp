@@ -148,12 +148,22 @@ class Parser {
 public:
     Parser(const std::vector<Tok> &t, Error &e) : toks(t), err(e) {}
 
-    bool parse(Ast &ast) {
-        /* optional `graph! { ... }` wrapper, so a macro invocation can be pasted as is */
-        bool wrapped = false;
-        if (is_ident("graph") && peek(1).kind == Tok::Punct && peek(1).s == "!" && peek(2).s == "{") { pos += 3; wrapped = true; }
-        while (!err.set && cur().kind != Tok::End && !(wrapped && is_punct("}"))) item(ast);
-        if (!err.set && wrapped) expect("}");
+    /* one graph body, or several `graph! { ... }` invocations in a row (a voice graph followed by the
+       polyphonic graph that instantiates it, like fm_voice.rs + lib.rs of the fm-synth example) */
+    bool parse(std::vector<Ast> &graphs) {
+        auto wrapper = [&]() { return is_ident("graph") && peek(1).kind == Tok::Punct && peek(1).s == "!" && peek(2).s == "{"; };
+        if (!wrapper()) {
+            graphs.emplace_back();
+            while (!err.set && cur().kind != Tok::End) item(graphs.back());
+            return !err.set;
+        }
+        while (!err.set && wrapper()) {
+            pos += 3;
+            graphs.emplace_back();
+            while (!err.set && cur().kind != Tok::End && !is_punct("}")) item(graphs.back());
+            if (!err.set) expect("}");
+            accept(";");
+        }
         if (!err.set && cur().kind != Tok::End) err.at(cur(), "unexpected tokens after the graph body");
         return !err.set;
     }
@@ -271,10 +281,10 @@ private:
                     float lo, hi;
                     if (!number(lo) || !expect("..") || !number(hi)) return;
                     s.has_range = true; s.lo = lo; s.hi = hi;
-                } else if (key == "ramp" && accept(":")) {
+                } else if (key == "ramp" && (accept(":") || accept("="))) {
                     if (cur().kind != Tok::Num || !cur().is_int) { err.at(cur(), "`ramp:` expects a frame count"); return; }
                     s.ramp = (uint32_t)strtoul(cur().s.c_str(), nullptr, 10); ++pos;
-                } else if (accept(":")) {                    /* center / unit / smoother / step / name / group */
+                } else if (accept(":") || accept("=")) {     /* center / unit / smoother / step / name / group (`key: v` or `key = v`) */
                     if (cur().kind == Tok::Str) ++pos; else { float v; if (!number(v)) return; }
                 } else { err.at(cur(), "unknown parameter-spec entry `" + key + "`"); return; }
             } else { err.at(cur(), "malformed parameter spec"); return; }
@@ -879,16 +889,149 @@ private:
     }
 };
 
-/* text -> plan::Graph; on failure `error` holds "line:col: message" */
+/* ------------------------------------------------------------- polyphonic wrapper -- */
+/* An outer graph of the shape the reference's polyphonic examples have (examples/fm-synth/src/lib.rs:22-131):
+ *     nodes { midi_parser = MidiParser::new(); voice_allocator = VoiceAllocator::<N>::new();
+ *             voice_handlers = [MidiVoiceHandler::new(); N]; voices = [Voice::new(); N]; }
+ * where `Voice` is another graph of the same text.  The reference expands it into N copies of the voice
+ * struct walked in index order (codegen/emit_node.rs:365-379) and sums `voices.<out>` in index order
+ * (:463-466).  Here the voice graph is what gets planned; the array axis becomes the engine's
+ * voices_per_instance, broadcast edges `outer_value -> voices.<input>` become names for the voice's inputs
+ * (with the OUTER declaration's default and ramp), and the MIDI chain selects the engine's MIDI front
+ * (oscen_b200_push_midi / _push_midi_batch: midi.rs:69-224, voice_allocator.rs:57-136). */
+inline const Ast *find_graph(const std::vector<Ast> &all, const std::string &name) {
+    for (const Ast &a : all) if (a.name == name) return &a;
+    return nullptr;
+}
+inline bool is_polyphonic(const Ast &top) {
+    for (const NodeDecl &d : top.nodes) if (d.array > 0) return true;
+    return false;
+}
+inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::Graph &g, Error &err) {
+    const NodeDecl *voices = nullptr, *handlers = nullptr, *alloc = nullptr, *parser = nullptr;
+    for (const NodeDecl &d : top.nodes) {
+        if (d.rate) { err.at(d.at, "node rates on the nodes of a polyphonic graph are not supported (oversample inside the voice graph)"); return false; }
+        if (d.type == "MidiParser" && !d.array) { parser = &d; continue; }
+        if (d.type == "VoiceAllocator" && !d.array) { alloc = &d; continue; }
+        if (d.type == "MidiVoiceHandler" && d.array) { handlers = &d; continue; }
+        if (d.array && find_graph(all, d.type) && !voices) { voices = &d; continue; }
+        err.at(d.at, d.array ? "node array `" + d.name + "`: `" + d.type + "` is not a graph of this text (a polyphonic graph holds ONE array of a voice graph, plus MidiParser / VoiceAllocator / [MidiVoiceHandler; N])"
+                             : "node `" + d.name + "`: a polyphonic graph holds one voice array plus MidiParser / VoiceAllocator / [MidiVoiceHandler; N] only");
+        return false;
+    }
+    if (!voices) { Tok t; err.at(t, "polyphonic graph without a voice array"); return false; }
+    const Ast &voice = *find_graph(all, voices->type);
+    if (is_polyphonic(voice)) { err.at(voices->at, "the voice graph `" + voice.name + "` is itself polyphonic: one level of node arrays is supported"); return false; }
+    if (voices->ctor != "new" || !voices->args.empty()) { err.at(voices->at, "a graph is constructed with `" + voice.name + "::new()`"); return false; }
+    if ((uint32_t)voices->array > 64u || (voices->array & (voices->array - 1)) != 0) { err.at(voices->at, "voice array size must be a power of two <= 64 (the engine folds an instance inside one 64-thread CTA)"); return false; }
+    if (handlers && handlers->array != voices->array) { err.at(handlers->at, "`" + handlers->name + "` and `" + voices->name + "` must have the same array size"); return false; }
+    {
+        Lowering l(voice, g, err);
+        if (!l.run()) return false;
+    }
+    g.vpi = (uint32_t)voices->array;
+    g.midi = parser && alloc && handlers;
+    if ((parser || alloc || handlers) && !g.midi) { Tok t; err.at(t, "the MIDI front needs all of MidiParser, VoiceAllocator and [MidiVoiceHandler; N]"); return false; }
+    const std::string voice_name = g.name;
+    g.name = top.name;
+    std::map<std::string, const InputDecl *> outer_in;
+    std::string outer_out, outer_midi;
+    for (const InputDecl &d : top.inputs) {
+        outer_in[d.name] = &d;
+        if (d.kind == Kind::Event) outer_midi = d.name;
+        else if (d.kind != Kind::Value) { err.at(d.at, "a polyphonic graph takes value inputs (broadcast to the voices) and the MIDI event input"); return false; }
+    }
+    for (const OutputDecl &d : top.outputs) {
+        if (d.kind != Kind::Stream || !outer_out.empty()) { err.at(d.at, "a polyphonic graph has one stream output (the voice sum)"); return false; }
+        outer_out = d.name;
+    }
+    auto voice_value_id = [&](const std::string &name) -> int {
+        for (size_t i = 0; i < g.inputs.size(); ++i) if (g.inputs[i].name == name) return (int)i;
+        return -1;
+    };
+    auto is_node = [&](const Expr &e, const NodeDecl *nd, std::string &field) {
+        if (!nd || e.k != Expr::Field || e.a->k != Expr::Ident || e.a->name != nd->name) return false;
+        field = e.name; return true;
+    };
+    bool freq_wired = false, gate_wired = false, out_wired = false;
+    for (const Conn &c : top.conns) {
+        if (c.via) { err.at(c.at, "feedback edges are not supported in a polyphonic graph"); return false; }
+        std::string sf, df;
+        const Expr &s = *c.src, &d = *c.dst;
+        /* voices.<out> -> out : the in-order voice sum (the engine's instance fold) */
+        if (is_node(s, voices, sf) && d.k == Expr::Ident && d.name == outer_out) {
+            if (sf != g.output_name) { err.at(s.at, "`" + voice.name + "` has no stream output `" + sf + "`"); return false; }
+            out_wired = true; continue;
+        }
+        if (is_node(d, voices, df)) {
+            /* handlers.frequency / handlers.gate -> voices.<input> */
+            if (is_node(s, handlers, sf)) {
+                if (sf == "frequency") {
+                    const int id = voice_value_id(df);
+                    if (id < 0) { err.at(d.at, "`" + voice.name + "` has no value input `" + df + "`"); return false; }
+                    g.midi_freq_input = (uint32_t)id; freq_wired = true; continue;
+                }
+                if (sf == "gate") {
+                    if (df != g.event_input) { err.at(d.at, "`" + voice.name + "` has no event input `" + df + "`"); return false; }
+                    gate_wired = true; continue;
+                }
+                err.at(s.at, "MidiVoiceHandler has no output `" + sf + "` (frequency, gate)"); return false;
+            }
+            /* outer value input (or literal) -> voices.<value input>: broadcast */
+            const int id = voice_value_id(df);
+            if (id < 0) {
+                err.at(d.at, df == g.event_input ? "Type mismatch in connection: source is Value but destination expects Event"
+                                                 : "`" + voice.name + "` has no value input `" + df + "`");
+                return false;
+            }
+            if (s.k == Expr::Literal) { g.inputs[id].def = s.lit; continue; }
+            if (s.k == Expr::Ident && outer_in.count(s.name) && outer_in[s.name]->kind == Kind::Value) {
+                const InputDecl &od = *outer_in[s.name];
+                plan::ValueInput spec = od.spec;              /* the outer declaration rules: default, range, ramp */
+                spec.name = g.inputs[id].name;
+                if (!od.has_def) spec.def = 0.0f;
+                g.inputs[id] = spec;
+                g.aliases.emplace_back(s.name, (uint32_t)id);
+                continue;
+            }
+            err.at(s.at, "only a value input of the outer graph, a literal or a MidiVoiceHandler output can feed `" + voices->name + "." + df + "`"); return false;
+        }
+        /* the MIDI chain itself: midi_in -> parser -> allocator -> handlers */
+        const bool midi_edge =
+            (s.k == Expr::Ident && s.name == outer_midi && is_node(d, parser, df) && df == "midi_in") ||
+            (is_node(s, parser, sf) && is_node(d, alloc, df) && sf == df && (sf == "note_on" || sf == "note_off")) ||
+            (is_node(s, alloc, sf) && sf == "voices" && is_node(d, handlers, df) && (df == "note_on" || df == "note_off"));
+        if (midi_edge) continue;
+        err.at(c.at, "this connection is not part of the polyphonic pattern (MIDI chain, broadcast `value -> voices.input`, `voices.output -> out`)");
+        return false;
+    }
+    if (!out_wired) { Tok t; err.at(t, "`" + voices->name + "." + g.output_name + "` is not connected to the output"); return false; }
+    if (g.midi && !(freq_wired && gate_wired)) { Tok t; err.at(t, "the MIDI front is declared but `" + handlers->name + ".frequency` / `.gate` are not connected to the voices"); return false; }
+    g.output_name = outer_out + " <- sum of " + std::to_string(g.vpi) + " x " + voice_name + "." + g.output_name;
+    return true;
+}
+
+/* text -> plan::Graph; on failure `error` holds "line:col: message".  With several `graph! { }` blocks the
+   LAST one is the graph to run; earlier ones are the graphs it instantiates. */
 inline bool compile(const char *text, plan::Graph &g, std::string &error) {
     Error err;
     std::vector<Tok> toks;
     if (!text) { error = "0:0: null graph text"; return false; }
     if (!lex(text, toks, err)) { error = err.text(); return false; }
-    Ast ast;
+    std::vector<Ast> graphs;
     Parser p(toks, err);
-    if (!p.parse(ast)) { error = err.text(); return false; }
-    Lowering l(ast, g, err);
+    if (!p.parse(graphs)) { error = err.text(); return false; }
+    if (graphs.empty()) { error = "1:1: no graph in the text"; return false; }
+    const Ast &top = graphs.back();
+    if (is_polyphonic(top)) {
+        if (!lower_polyphonic(top, graphs, g, err)) { error = err.text(); return false; }
+        return true;
+    }
+    for (const NodeDecl &d : top.nodes) if (find_graph(graphs, d.type)) {
+        err.at(d.at, "nested graph `" + d.type + "` as a scalar node is not supported (the polyphonic array form `[" + d.type + "::new(); N]` is)");
+        error = err.text(); return false;
+    }
+    Lowering l(top, g, err);
     if (!l.run()) { error = err.text(); return false; }
     return true;
 }
@@ -904,6 +1047,8 @@ inline std::string describe(const plan::Graph &g, const plan::Plan &p) {
         if (g.inputs[i].ramp) s += " ramp " + std::to_string(g.inputs[i].ramp);
         s += "\n";
     }
+    for (const auto &al : g.aliases) s += "alias: " + al.first + " -> input " + std::to_string(al.second) + "\n";
+    if (g.vpi) s += "polyphony: " + std::to_string(g.vpi) + " voices per instance" + (g.midi ? ", MIDI front -> frequency = input " + std::to_string(g.midi_freq_input) + ", gate" : "") + "\n";
     if (!g.stream_input.empty()) s += "stream input: " + g.stream_input + "\n";
     if (!g.event_input.empty()) s += "event input: " + g.event_input + "\n";
     s += "output: " + g.output_name + " <- " + g.nodes[g.output.node].name + "\n";

@@ -166,6 +166,8 @@ struct oscen_b200_engine {
     float *h_mix = nullptr;
     uint32_t last_frames = 0;
 
+    uint32_t midi_freq_input = 0;        /* value input fed by MidiVoiceHandler.frequency */
+    bool midi_ok = true;                 /* the graph has a MIDI front (DSL graphs: only the polyphonic form with the MIDI chain) */
     bool has_stream_in = false;          /* the graph declares a per-voice stream input */
     uint32_t lcg_field = 0;              /* first of the two state words of the device-side input LCG */
     jit::Kernel jit;                     /* DSL-compiled graph, PLAN_FUSED: the kernel codegen.hpp generated, compiled by NVRTC */
@@ -504,6 +506,14 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
 static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *custom, oscen_b200_engine **out) {
     if (!cfg || !out) { g_create_error = "null argument"; return OSCEN_B200_E_ARG; }
     *out = nullptr;
+    oscen_b200_config cfg_local;
+    if (custom && cfg && custom->g.vpi) {
+        /* a polyphonic graph brings its own voices_per_instance (the voice array size); 0 in the config means "the graph's" */
+        if (cfg->voices_per_instance != 0 && cfg->voices_per_instance != custom->g.vpi) {
+            g_create_error = "voices_per_instance must be " + std::to_string(custom->g.vpi) + " (the graph's voice array size) or 0"; return OSCEN_B200_E_ARG;
+        }
+        cfg_local = *cfg; cfg_local.voices_per_instance = custom->g.vpi; cfg = &cfg_local;
+    }
     if ((custom == nullptr) != (cfg->graph_kind != OSCEN_B200_GRAPH_CUSTOM)) {
         g_create_error = "OSCEN_B200_GRAPH_CUSTOM engines are created with oscen_b200_create_from_graph (and only those)"; return OSCEN_B200_E_ARG;
     }
@@ -546,6 +556,7 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
     const uint32_t kind = cfg->graph_kind, n = cfg->n_voices;
     e->has_stream_in = custom ? !pg.stream_input.empty() : has_stream_in(kind);
     if (custom) {
+        e->midi_ok = pg.midi; e->midi_freq_input = pg.midi_freq_input;
         e->n_inputs = (uint32_t)pg.inputs.size();
         e->lcg_field = pg.n_state; e->n_state = pg.n_state + (e->has_stream_in ? 2u : 0u);
         if (e->n_state == 0) e->n_state = 1;                      /* stateless graph: keep the allocation non-empty */
@@ -650,9 +661,12 @@ int oscen_b200_graph_describe(const oscen_b200_graph *g, char *dst, size_t cap) 
     memcpy(dst, s.c_str(), s.size() + 1);
     return (int)g->p.launches.size();
 }
+uint32_t oscen_b200_graph_voices_per_instance(const oscen_b200_graph *g) { return g ? (g->g.vpi ? g->g.vpi : 1u) : 0u; }
+int oscen_b200_graph_has_midi(const oscen_b200_graph *g) { return g && g->g.midi ? 1 : 0; }
 uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g) { return g ? (uint32_t)g->g.inputs.size() : 0u; }
 int oscen_b200_graph_input_id(const oscen_b200_graph *g, const char *name) {
     if (!g || !name) return OSCEN_B200_E_ARG;
+    for (const auto &al : g->g.aliases) if (al.first == name) return (int)al.second;      /* the outer graph's names first */
     for (size_t i = 0; i < g->g.inputs.size(); ++i) if (g->g.inputs[i].name == name) return (int)i;
     return OSCEN_B200_E_ARG;
 }
@@ -741,6 +755,7 @@ int oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, siz
 int oscen_b200_push_midi(oscen_b200_engine *e, uint32_t instance, uint32_t frame_offset, const uint8_t *bytes, uint32_t len) {
     if (!e || !bytes) return OSCEN_B200_E_ARG;
     if (instance >= e->n_inst) return arg_error(e, "push_midi: instance out of range");
+    if (!e->midi_ok) return arg_error(e, "push_midi: this graph declares no MIDI front (midi_in -> MidiParser -> VoiceAllocator -> [MidiVoiceHandler; N])");
     if (e->cfg.voices_per_instance > (uint32_t)kMaxPolyVoices) return arg_error(e, "push_midi: VoiceAllocator holds at most 24 voices (voice_allocator.rs:5)");
     if (e->midi_mode == 2) { e->err = "push_midi: this engine runs the device-side MIDI front (push_midi_batch)"; return OSCEN_B200_E_STATE; }
     if (e->midi_mode == 0) { e->midi.assign(e->n_inst, MidiFront((int)e->cfg.voices_per_instance)); e->midi_mode = 1; }
@@ -812,6 +827,7 @@ int midi_device_run(oscen_b200_engine *e, uint32_t frames) {
     a.alloc_word = e->d_alloc_word; a.alloc_age = e->d_alloc_age; a.alloc_cur_age = e->d_alloc_cur_age;
     a.h_note = e->d_h_note; a.h_freq = e->d_h_freq; a.note_freq = e->d_note_freq;
     a.ev_count = e->d_ev_count; a.ev_offset = e->d_ev_offset; a.events = e->d_events; a.dropped = e->d_midi_dropped;
+    a.freq_input = e->midi_freq_input;
     const uint32_t grid = (e->n_inst + 127) / 128;
     midi_front_kernel<false><<<grid, 128, 0, e->stream>>>(a);
     tmp = e->cub_tmp_bytes;
@@ -828,6 +844,7 @@ int midi_device_run(oscen_b200_engine *e, uint32_t frames) {
 int oscen_b200_push_midi_batch(oscen_b200_engine *e, const oscen_b200_midi_msg *msgs, size_t n) {
     static_assert(sizeof(MidiMsg) == sizeof(oscen_b200_midi_msg), "midi message layout");
     if (!e || (!msgs && n)) return OSCEN_B200_E_ARG;
+    if (!e->midi_ok) return arg_error(e, "push_midi_batch: this graph declares no MIDI front (midi_in -> MidiParser -> VoiceAllocator -> [MidiVoiceHandler; N])");
     if (e->cfg.voices_per_instance > (uint32_t)kDevMaxPoly) return arg_error(e, "push_midi_batch: voices_per_instance must be <= 16");
     if (e->midi_mode == 1) { e->err = "push_midi_batch: this engine runs the host-side MIDI front (push_midi)"; return OSCEN_B200_E_STATE; }
     for (size_t i = 0; i < n; ++i) if (msgs[i].instance >= e->n_inst) return arg_error(e, "push_midi_batch: instance out of range");
@@ -909,7 +926,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         ve.clear();
         e->midi[i].run(frames, ve);
         for (const VoiceEvent &x : ve) {
-            e->pending.push_back(Event{i * vpi + x.voice_in_instance, x.frame, x.is_gate ? kEventGate : 0u, x.value});
+            e->pending.push_back(Event{i * vpi + x.voice_in_instance, x.frame, x.is_gate ? kEventGate : e->midi_freq_input, x.value});
             e->seqs.push_back(e->seq++);
         }
     }
@@ -984,7 +1001,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         e->stats.h2d_bytes += (uint64_t)frames * kMaxInputs * sizeof(float);
         general = true;
     }
-    if (device_midi) { e->uniform[0] = false; has_value_events = true; }               /* per-voice `frequency` value events */
+    if (device_midi) { e->uniform[e->midi_freq_input] = false; has_value_events = true; }               /* per-voice `frequency` value events */
     for (uint32_t i = 1; i < e->n_inputs; ++i) if (!e->uniform[i]) general = true;
     if (kind != OSCEN_B200_GRAPH_FM_VOICE) general = true;
 

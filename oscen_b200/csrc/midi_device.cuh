@@ -47,6 +47,7 @@ struct MidiFrontArgs {
     const uint32_t *ev_offset;           /* [n_voices] exclusive scan of ev_count */
     Event *events;
     uint32_t *dropped;                   /* messages that found the instance's midi_in queue full */
+    uint32_t freq_input;                 /* value-input id MidiVoiceHandler.frequency is connected to (0 for the built-in graphs) */
 };
 
 __global__ void midi_keys_kernel(const MidiMsg *msgs, uint32_t n, uint32_t *keys, uint32_t *idx) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128) midi_front_kernel(const MidiFrontArgs a) 
             for (uint32_t k = 0; k < nq; ++k) if (q_voice[k] == v && q_kind[k] == 2) {
                 if (cur_note[v] == (int)q_note[k]) { emit(v, f, kEventGate, 0.0f); cur_note[v] = -1; }
             }
-            if (touched) emit(v, f, 0u, cur_freq[v]);                                  /* frequency value edge */
+            if (touched) emit(v, f, a.freq_input, cur_freq[v]);                                  /* frequency value edge */
         }
     }
 

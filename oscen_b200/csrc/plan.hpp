@@ -100,6 +100,12 @@ struct Graph {
     std::string stream_input, event_input, output_name;
     uint32_t n_state = 0;
     int inner_log2 = 0;              /* > 0: a multirate graph (one inner rate 2^L per graph); runs as a generated kernel only */
+    /* polyphonic wrapper (`voices = [Voice::new(); N]` in an outer graph, e.g. FMGraph around FMVoice): the voice
+       graph is what is planned; the outer graph contributes the polyphony, the MIDI front and the input names */
+    uint32_t vpi = 0;                /* N of the voice array = the engine's voices_per_instance (0: not polyphonic) */
+    bool midi = false;               /* midi_in -> MidiParser -> VoiceAllocator<N> -> [MidiVoiceHandler; N] feeds the voices */
+    uint32_t midi_freq_input = 0;    /* the voice input `voice_handlers.frequency` is connected to */
+    std::vector<std::pair<std::string, uint32_t>> aliases;   /* outer value-input name -> voice input id (broadcast edges) */
 };
 
 struct Launch {

@@ -155,7 +155,7 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
     ("output stream out; node a = PolyBlepOscillator::saw(1.0, 1.0) * 2; node f = TptFilter::new(500.0, 0.7); node c = HardClip::new() * 2; "
      "connection a.output -> f.input; connection f.output -> c.input; connection c.output -> out;", "cannot feed it again in the same frame"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6) * 3; connection o.output -> out;", "rate factor must be in {1, 2, 4, 8}"),
-    ("output stream out; node v = [PolyBlepOscillator::saw(2000.0, 0.6); 4]; connection v.output -> out;", "node arrays"),
+    ("output stream out; node v = [PolyBlepOscillator::saw(2000.0, 0.6); 4]; connection v.output -> out;", "is not a graph of this text"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6)\n connection o.output -> out;", "2:2: expected `;`"),
     (ONE_OSC + "connection o.output -> [4] -> out;", "feedback edges"),
     (ONE_OSC + "connection o.outptu -> out;", "node `o` has no endpoint `outptu`"),
@@ -303,3 +303,51 @@ def test_value_edges_into_inner_nodes_latch():
     src = g.codegen()
     assert "adsr_derive_r(d1" in src and ", sri);" in src and "UpEdge" not in src
     assert g.jit_check() > 10000
+
+
+def test_stringify_spacing_is_accepted():
+    """Rust's stringify!() of the macro tokens separates most tokens with spaces: the front end lexes tokens, not text"""
+    spaced = ("name : Synth ; input cutoff : value = 1200.0 [20.0 .. 20000.0 , log , ramp : 1323] ; output audio_out : stream ; "
+              "nodes { osc = PolyBlepOscillator :: saw (2_000.0 , 0.5) * 2 ; filter = TptFilter :: new (1200.0 , 0.707) ; } "
+              "connections { [sinc_iir] osc . output -> filter . input ; cutoff -> filter . cutoff ; filter . output . tanh () * 0.5 -> audio_out ; }")
+    g = abi.Graph(spaced)
+    assert g.input_info(0)["ramp"] == 1323 and "[sinc_iir down x2]" in g.describe() and "{tanh}" in g.describe()
+
+
+# ------------------------------------------------------------------ polyphonic graphs (voice arrays + the MIDI front)
+def test_polyphonic_fm_graph_compiles_to_the_voice_plan_with_outer_names():
+    g = abi.Graph(text("fm_voice.graph") + text("fm_graph.graph"))
+    assert g.voices_per_instance == 8 and g.has_midi
+    assert g.launches() == builtin_plan(abi.GRAPH_FM_VOICE)
+    d = g.describe()
+    assert "graph FMGraph" in d and "polyphony: 8 voices per instance, MIDI front -> frequency = input 0, gate" in d
+    assert "sum of 8 x FMVoice.audio_out" in d
+    # ids are the voice graph's (OSCEN_B200_FM_*); names and ramps come from the outer declarations
+    assert g.input_id("op3_ratio") == 1 and g.input_id("filter_cutoff") == 21 and g.input_id("frequency") == 0
+    assert g.input_info(21)["ramp"] == 2205 and g.input_info(21)["range"] == (20.0, 20000.0)
+    assert g.input_info(2)["ramp"] == 2205 and g.input_info(1)["ramp"] == 0
+    assert g.jit_check() > 10000
+
+
+@pytest.mark.parametrize("mutation,frag", [
+    (("voices = [FMVoice::new(); 8];", "voices = [FMVoice::new(); 6];"), "power of two"),
+    (("voice_handlers = [MidiVoiceHandler::new(); 8];", "voice_handlers = [MidiVoiceHandler::new(); 4];"), "same array size"),
+    (("voices = [FMVoice::new(); 8];", "voices = [Unknown::new(); 8];"), "is not a graph of this text"),
+    (("voice_handlers.gate -> voices.gate;", "voice_handlers.gate -> voices.trigger;"), "has no event input `trigger`"),
+    (("route -> voices.route;", "route -> voices.rout;"), "has no value input `rout`"),
+    (("voices.audio_out -> audio_out;", ""), "is not connected to the output"),
+    (("midi_parser = MidiParser::new();", ""), "MIDI front needs all of"),
+    (("route -> voices.route;", "route -> voices.route; op3_ratio -> midi_parser.midi_in;"), "not part of the polyphonic pattern"),
+])
+def test_polyphonic_graph_errors(mutation, frag):
+    outer = text("fm_graph.graph")
+    assert mutation[0] in outer
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(text("fm_voice.graph") + outer.replace(mutation[0], mutation[1]))
+    assert frag in str(ei.value), str(ei.value)
+
+
+def test_nested_scalar_graph_is_reported():
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(text("fm_voice.graph") + "graph! { name: Outer; output stream out; node v = FMVoice::new(); connection v.audio_out -> out; }")
+    assert "nested graph `FMVoice` as a scalar node is not supported" in str(ei.value)

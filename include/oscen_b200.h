@@ -222,11 +222,13 @@ int  oscen_b200_plan_describe(uint32_t graph_kind, char *dst, size_t cap);
  * `input` / `output` declarations in both spellings, `node` / `nodes { }`, `connection` /
  * `connections { }`, compound sources (+ - * /, parentheses, .tanh() .abs() .clamp(a,b) .min(a) .max(a)).
  * The result is a node plan (one kernel launch per node type per ready wave, streams in HBM, replayed
- * as a CUDA graph).  Node types with kernels: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator
- * (sine/saw/square/triangle), LP18Filter, Gain, AddValue, Mixer, Crossfade, HardClip.  Constructs the node
- * plan cannot express are compile ERRORS with a line:column, never silently dropped: node rates
- * (`* N`), node arrays (`[T; N]`: voices_per_instance is the array axis), nested graphs, `-> [N] ->`
- * feedback edges, `external` assets, typed (array / Frame<N>) endpoints, free-function calls.
+ * as a CUDA graph) or one generated fused kernel.  Node types: AdsrEnvelope, FmOperator, TptFilter,
+ * PolyBlepOscillator (sine/saw/square/triangle), LP18Filter, Gain, AddValue, Mixer, Crossfade, HardClip in both
+ * back ends; Oscillator (sine/square/saw), IirLowpass, Delay, `* N` oversampled nodes with [sinc] / [sinc_iir] /
+ * [linear] / [latch] cross-rate edges, and `-> [N] ->` / `-> [delay] ->` feedback edges in generated kernels
+ * (OSCEN_B200_PLAN_FUSED) only.  What cannot be expressed is a compile ERROR with a line:column, never silently
+ * dropped: `/ N` rates, node arrays outside the polyphonic shape (below), nested scalar graphs, `external`
+ * assets, typed (array / Frame<N>) endpoints, free-function calls.
  * Value inputs get ids in declaration order (oscen_b200_graph_input_id); the graph's event input carries
  * gate events (OSCEN_B200_EVENT_GATE) to every AdsrEnvelope it is connected to; the graph's stream input
  * is oscen_b200_stream_in id 0.  Compiling needs no GPU. */

@@ -423,6 +423,114 @@ void orc_lp18_process(orc_lp18 *f) {
     f->output = lp;
 }
 
+/* ============================================================== IirLowpass == */
+/* oscen-lib/src/filters/iir_lowpass/mod.rs:15-166 */
+void orc_iirlp_new(orc_iirlp *f, float cutoff, float q) {
+    memset(f, 0, sizeof *f);
+    f->cutoff = cutoff; f->q = q; f->b0 = 1.0f;
+    f->frames_per_update = 32; f->sample_rate = 44100.0f;
+}
+static void iirlp_update_coefficients(orc_iirlp *f, float sample_rate) {     /* mod.rs:84-101 */
+    float nyquist = sample_rate * 0.5f - FLT_EPSILON;
+    float freq = clampf(f->cutoff, 20.0f, nyquist);
+    float q = fmaxf(f->q, 0.01f);
+    float n = 1.0f / tanf(ORC_PI * freq / sample_rate);
+    float n_squared = n * n;
+    float c1 = 1.0f / (1.0f + 1.0f / q * n + n_squared);
+    f->b0 = c1;
+    f->b1 = c1 * 2.0f;
+    f->b2 = c1;
+    f->a1 = c1 * 2.0f * (1.0f - n_squared);
+    f->a2 = c1 * (1.0f - 1.0f / q * n + n_squared);
+}
+void orc_iirlp_prepare(orc_iirlp *f) { iirlp_update_coefficients(f, f->sample_rate); }
+void orc_iirlp_process(orc_iirlp *f) {                                        /* mod.rs:109-166 */
+    if (f->frame_counter == 0) iirlp_update_coefficients(f, f->sample_rate);
+    f->frame_counter = (f->frame_counter + 1) % f->frames_per_update;
+    float input = f->input;
+    if (fabsf(input) < 1e-15f) input = 0.0f;
+    float output = f->b0 * input + f->v1;
+    f->v1 = f->b1 * input - f->a1 * output + f->v2;
+    f->v2 = f->b2 * input - f->a2 * output;
+    if (fabsf(f->v1) < 1e-15f) f->v1 = 0.0f;
+    if (fabsf(f->v2) < 1e-15f) f->v2 = 0.0f;
+    f->output = output;
+}
+
+/* ============================================================ Delay / RingBuffer == */
+/* oscen-lib/src/ring_buffer/mod.rs:29-202 (BufferMode::PowerOfTwo, the default) */
+static size_t next_pow2(size_t x) { size_t p = 1; while (p < x) p <<= 1; return p; }
+static void ring_alloc(orc_ring *r, size_t size) {
+    free(r->buffer);
+    r->capacity = next_pow2(size < 1 ? 1 : size);
+    r->mask = r->capacity - 1;
+    r->write_pos = 0;
+    r->buffer = (float *)calloc(r->capacity, sizeof(float));
+}
+static void ring_push(orc_ring *r, float v) {
+    r->buffer[r->write_pos] = v;
+    r->write_pos = (r->write_pos + 1) & r->mask;
+}
+static float ring_read_pos(const orc_ring *r, float offset) {                 /* mod.rs:80-91 */
+    float n = (float)r->capacity;
+    float rp = (float)r->write_pos - offset - 1.0f;
+    return fmodf(fmodf(rp, n) + n, n);
+}
+static float ring_get(const orc_ring *r, float offset) {                      /* mod.rs:167-202 */
+    float nn = fmaxf(offset, 0.0f);
+    float fr = nn - truncf(nn);
+    if (fr < 1e-6f || (1.0f - fr) < 1e-6f) {
+        float rd = roundf(nn);
+        size_t os = rd >= 18446744073709551616.0f ? (size_t)-1 : (size_t)rd;  /* `as usize` saturates */
+        size_t idx = ((r->write_pos + r->capacity) - (os % r->capacity) - 1) % r->capacity;
+        return r->buffer[idx];
+    }
+    float rp = ring_read_pos(r, nn);
+    size_t i = (size_t)rp;
+    float f = rp - truncf(rp);
+    if (r->capacity < 4) {                                                    /* get_linear, mod.rs:94-118 */
+        float a = r->buffer[i], b = r->buffer[(i + 1) & r->mask];
+        return fmaf(a, 1.0f - f, b * f);
+    }
+    float v0 = r->buffer[(i - 1) & r->mask], v1 = r->buffer[i], v2 = r->buffer[(i + 1) & r->mask], v3 = r->buffer[(i + 2) & r->mask];
+    float c0 = v1;
+    float c1 = 0.5f * (v2 - v0);
+    float c2 = v0 - 2.5f * v1 + 2.0f * v2 - 0.5f * v3;
+    float c3 = 0.5f * (v3 - v0) + 1.5f * (v1 - v2);
+    return c0 + f * (c1 + f * (c2 + f * c3));
+}
+/* test hooks on the ring itself (ring_buffer/tests.rs) */
+void orc_ring_init(orc_ring *r, size_t size) { memset(r, 0, sizeof *r); ring_alloc(r, size); }
+void orc_ring_push(orc_ring *r, float v) { ring_push(r, v); }
+float orc_ring_get(const orc_ring *r, float offset) { return ring_get(r, offset); }
+void orc_ring_free(orc_ring *r) { free(r->buffer); r->buffer = NULL; }
+
+/* oscen-lib/src/delay/mod.rs:5-86 */
+void orc_delay_new(orc_delay *d, float delay_samples, float feedback) {
+    memset(d, 0, sizeof *d);
+    d->delay_samples = delay_samples; d->feedback = feedback;
+    d->frames_per_update = 32; d->sample_rate = 44100.0f;
+    ring_alloc(&d->ring, 1024);
+}
+void orc_delay_prepare(orc_delay *d) {                                         /* mod.rs:59-69 */
+    float target = 2.0f * d->sample_rate;
+    size_t size = target >= 18446744073709551616.0f ? (size_t)-1 : (target > 0.0f ? (size_t)target : 0);
+    if (size > 88200) size = 88200;
+    ring_alloc(&d->ring, size);
+}
+void orc_delay_process(orc_delay *d) {                                         /* mod.rs:47-85 */
+    if (d->frame_counter == 0) {
+        float max_delay = (float)d->ring.capacity - 1.0f;
+        d->delay_samples = clampf(d->delay_samples, 0.0f, max_delay);
+        d->feedback = clampf(d->feedback, 0.0f, 0.99f);
+    }
+    d->frame_counter = (d->frame_counter + 1) % d->frames_per_update;
+    float delayed = ring_get(&d->ring, d->delay_samples);
+    ring_push(&d->ring, d->input + delayed * d->feedback);
+    d->output = delayed;
+}
+void orc_delay_free(orc_delay *d) { free(d->ring.buffer); d->ring.buffer = NULL; }
+
 /* ===================================================== halfband FIR cascade == */
 /* resample/coeffs.rs:17-27 */
 static const float HB23_HALF[6] = {

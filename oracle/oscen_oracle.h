@@ -119,6 +119,36 @@ void orc_lp18_new(orc_lp18 *f, float cutoff, float resonance);
 void orc_lp18_prepare(orc_lp18 *f);
 void orc_lp18_process(orc_lp18 *f);
 
+/* ----------------------------------------------------------- IirLowpass -- */
+/* oscen-lib/src/filters/iir_lowpass/mod.rs:15-166 */
+typedef struct {
+    float input, cutoff, q, output;
+    float b0, b1, b2, a1, a2, v1, v2;
+    float sample_rate;
+    size_t frame_counter, frames_per_update;
+} orc_iirlp;
+void orc_iirlp_new(orc_iirlp *f, float cutoff, float q);
+void orc_iirlp_prepare(orc_iirlp *f);
+void orc_iirlp_process(orc_iirlp *f);
+
+/* ---------------------------------------------------- Delay / RingBuffer -- */
+/* oscen-lib/src/delay/mod.rs:5-86, ring_buffer/mod.rs:29-202 */
+typedef struct { float *buffer; size_t write_pos, capacity, mask; } orc_ring;
+typedef struct {
+    float input, delay_samples, feedback, output;
+    orc_ring ring;
+    float sample_rate;
+    size_t frames_per_update, frame_counter;
+} orc_delay;
+void  orc_ring_init(orc_ring *r, size_t size);      /* RingBuffer::new(size): PowerOfTwo capacity */
+void  orc_ring_push(orc_ring *r, float v);
+float orc_ring_get(const orc_ring *r, float offset);
+void  orc_ring_free(orc_ring *r);
+void orc_delay_new(orc_delay *d, float delay_samples, float feedback);
+void orc_delay_prepare(orc_delay *d);
+void orc_delay_process(orc_delay *d);
+void orc_delay_free(orc_delay *d);
+
 /* -------------------------------------------------- halfband FIR cascade -- */
 /* oscen-lib/src/resample/sinc_fir.rs:95-266, coeffs.rs:17-34 */
 typedef struct { float history[24]; size_t head; } orc_hb_down;   /* Halfband2xDownStage */

@@ -156,6 +156,20 @@ struct Emitter {
                 break;
             case T::Tpt: line(1, "TptState " + N(i) + "; tpt_load(" + N(i) + ", a.state, " + base + ", n, vs);"); break;
             case T::Lp18: line(1, "Lp18State " + N(i) + "; lp18_load(" + N(i) + ", a.state, " + base + ", n, vs);"); break;
+            case T::IirLowpass:
+                line(1, "IirLpState " + N(i) + "; { const float *st_ = a.state + (size_t)" + base + " * n + vs; " + N(i) + ".b0 = st_[0]; " + N(i) + ".b1 = st_[n]; " + N(i) +
+                        ".b2 = st_[2 * (size_t)n]; " + N(i) + ".a1 = st_[3 * (size_t)n]; " + N(i) + ".a2 = st_[4 * (size_t)n]; " + N(i) + ".v1 = st_[5 * (size_t)n]; " + N(i) +
+                        ".v2 = st_[6 * (size_t)n]; " + N(i) + ".counter = __float_as_uint(st_[7 * (size_t)n]); }");
+                break;
+            case T::OscSine: case T::OscSquare: case T::OscSaw:
+                line(1, "float " + N(i) + " = a.state[(size_t)" + base + " * n + vs];");
+                break;
+            case T::Delay:
+                line(1, "DelayState " + N(i) + "; " + N(i) + ".write_pos = __float_as_uint(a.state[(size_t)(" + base + " + 0u) * n + vs]); " + N(i) +
+                        ".counter = __float_as_uint(a.state[(size_t)(" + base + " + 1u) * n + vs]); " + N(i) + ".output = a.state[(size_t)(" + base + " + 2u) * n + vs];");
+                line(1, "float *ring" + std::to_string(i) + " = a.state + (size_t)(" + base + " + 3u) * n + vs;    /* [" + std::to_string(nd.ring_cap) + " slots][voices] */");
+                line(1, "float " + S(i) + " = " + N(i) + ".output;    /* persists across frames: a feedback edge reads the previous frame's value */");
+                break;
             case T::Up: case T::Down:
                 line(1, edge_type(i) + " " + N(i) + "; " + N(i) + ".load(a.state, " + base + ", n, vs, dyn + " + std::to_string(smem_off) + "u * kCta);");
                 smem_off += edge_smem_floats(nd);
@@ -230,6 +244,15 @@ struct Emitter {
             case T::FmOperator: line(ind, o + "fmop_process(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ");" + cm); break;
             case T::Tpt: line(ind, o + "tpt_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + IN(i, 1, 1) + ", " + P(i, 0) + ", " + IN(i, 2, 2) + ", " + SR(i) + ");" + cm); break;
             case T::Lp18: line(ind, o + "lp18_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + P(i, 0) + ", " + P(i, 2) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm); break;
+            case T::IirLowpass: line(ind, o + "iirlp_process(" + N(i) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm); break;
+            case T::OscSine: case T::OscSquare: case T::OscSaw:
+                line(ind, o + "osc_process<" + (nd.type == T::OscSine ? "OSC_SINE" : nd.type == T::OscSquare ? "OSC_SQUARE" : "OSC_SAW") + ">(" + N(i) + ", " + P(i, 0) + ", " +
+                          IN(i, 0, 2) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm);
+                break;
+            case T::Delay:
+                line(ind, S(i) + " = delay_process<" + (P_is_const(i, 0) ? "false" : "true") + ", " + (P_is_const(i, 1) ? "false" : "true") + ">(" + N(i) + ", ring" + std::to_string(i) +
+                          ", (size_t)n, " + std::to_string(nd.ring_cap) + "u, " + lit(nd.max_delay) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ");" + cm);
+                break;
             case T::Gain: line(ind, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
             case T::AddValue: line(ind, o + IN(i, 0, -1) + " + " + P(i, 0) + ";" + cm); break;
             case T::Mixer: line(ind, o + IN(i, 0, -1) + " + " + IN(i, 1, -1) + ";" + cm); break;
@@ -307,6 +330,15 @@ struct Emitter {
                 break;
             case T::Tpt: line(2, "tpt_store(" + N(i) + ", a.state, " + base + ", n, v);"); break;
             case T::Lp18: line(2, "lp18_store(" + N(i) + ", a.state, " + base + ", n, v);"); break;
+            case T::IirLowpass:
+                line(2, "{ float *st_ = a.state + (size_t)" + base + " * n + v; st_[0] = " + N(i) + ".b0; st_[n] = " + N(i) + ".b1; st_[2 * (size_t)n] = " + N(i) + ".b2; st_[3 * (size_t)n] = " +
+                        N(i) + ".a1; st_[4 * (size_t)n] = " + N(i) + ".a2; st_[5 * (size_t)n] = " + N(i) + ".v1; st_[6 * (size_t)n] = " + N(i) + ".v2; st_[7 * (size_t)n] = __uint_as_float(" + N(i) + ".counter); }");
+                break;
+            case T::OscSine: case T::OscSquare: case T::OscSaw: line(2, "a.state[(size_t)" + base + " * n + v] = " + N(i) + ";"); break;
+            case T::Delay:
+                line(2, "a.state[(size_t)(" + base + " + 0u) * n + v] = __uint_as_float(" + N(i) + ".write_pos); a.state[(size_t)(" + base + " + 1u) * n + v] = __uint_as_float(" + N(i) +
+                        ".counter); a.state[(size_t)(" + base + " + 2u) * n + v] = " + N(i) + ".output;");
+                break;
             case T::Up: case T::Down: line(2, N(i) + ".store(a.state, " + base + ", n, v);"); break;
             default:
                 if (is_polyblep(nd.type)) line(2, "a.state[(size_t)" + base + " * n + v] = " + N(i) + ";");

@@ -24,9 +24,15 @@
  * (Up / Down) of the edge's `[policy]` (default [sinc]; ir/lower.rs:741-906), value edges latch.
  * Multirate graphs run as generated kernels only (codegen.hpp), not as node plans.
  *
- * Reported as errors (never silently ignored): `/ N` rates, mixed factors, node arrays `[T; N]` (the
- * engine's voices_per_instance is the array axis), nested graphs, `-> [N] ->` feedback edges,
- * `external` assets, typed endpoints, free-function calls in sources (they name user Rust code).
+ * Feedback: `src -> [N] -> dst` (a hidden Delay::new(N, 0.0)) and `src -> [name] -> dst` (a declared Delay)
+ * close cycles; the leg out of the delay does not order the walk (ir/lower.rs:560-656, 1015-1085) and reads
+ * what the delay output when it last ran.  Cycles need the per-sample walk: generated kernels only.
+ * Polyphony: a text may hold several `graph! { }` blocks; an outer graph of the reference's polyphonic
+ * shape (voices = [Voice::new(); N] + the MIDI chain) lowers to the voice graph's plan (lower_polyphonic).
+ *
+ * Reported as errors (never silently ignored): `/ N` rates, mixed factors, node arrays outside the
+ * polyphonic shape, nested scalar graphs, `external` assets, typed endpoints, free-function calls in
+ * sources (they name user Rust code).
  *
  * Host-only C++, no CUDA types: unit-tested on the CPU through oscen_b200_graph_compile().
  */
@@ -134,7 +140,7 @@ using ExprP = std::unique_ptr<Expr>;
 struct InputDecl { Kind kind; std::string name; bool has_def = false; float def = 0.0f; plan::ValueInput spec; Tok at; };
 struct OutputDecl { Kind kind; std::string name; Tok at; };
 struct NodeDecl { std::string name, type, ctor; std::vector<float> args; bool args_ok = true; int array = 0; int rate = 0; Tok at; };
-struct Conn { std::string policy; ExprP src, dst; int via = 0; /* 0 none, 1 samples, 2 node */ Tok at; };
+struct Conn { std::string policy; ExprP src, dst; int via = 0; /* 0 none, 1 samples, 2 node */ float via_samples = 0.0f; std::string via_node; Tok at; };
 struct Ast {
     std::string name;
     std::vector<InputDecl> inputs;
@@ -369,7 +375,10 @@ private:
         if (err.set || !expect("->")) return;
         if (is_punct("[")) {
             ++pos;
-            if (cur().kind == Tok::Num) c.via = 1; else if (cur().kind == Tok::Ident) c.via = 2;
+            if (cur().kind == Tok::Num) {
+                if (!cur().is_int) { err.at(cur(), "the sample count of `-> [N] ->` must be an integer literal"); return; }
+                c.via = 1; c.via_samples = cur().num;
+            } else if (cur().kind == Tok::Ident) { c.via = 2; c.via_node = cur().s; }
             else { err.at(cur(), "expected a sample count or a node name inside `-> [ ] ->`"); return; }
             ++pos;
             if (!expect("]") || !expect("->")) return;
@@ -462,6 +471,12 @@ inline const TypeInfo *type_info(const std::string &type) {
                                 {"frequency_mod", Kind::Stream, false, 0, 3, 0}, {"phase_mod", Kind::Stream, false, 1, 4, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
         {"LP18Filter", {{"cutoff", Kind::Value, false, 0, -1, 0}, {"resonance", Kind::Value, false, 1, -1, 0}, {"fmod", Kind::Value, false, 2, -1, 0},
                         {"input", Kind::Stream, false, 0, 3, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"IirLowpass", {{"cutoff", Kind::Value, false, 0, -1, 1000.0f}, {"q", Kind::Value, false, 1, -1, 0.70710678f}, {"input", Kind::Stream, false, 0, 2, 0},
+                        {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"Oscillator", {{"frequency", Kind::Value, false, 0, -1, 0}, {"amplitude", Kind::Value, false, 1, -1, 0}, {"frequency_mod", Kind::Stream, false, 0, 2, 0},
+                        {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        {"Delay", {{"delay_samples", Kind::Value, false, 0, -1, 0}, {"feedback", Kind::Value, false, 1, -1, 0}, {"input", Kind::Stream, false, 0, 2, 0},
+                   {"output", Kind::Stream, true, 0, -1, 0}}, true},
         {"Gain", {{"input", Kind::Stream, false, 0, -1, 0}, {"gain", Kind::Stream, false, 1, 0, 1.0f}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
         {"AddValue", {{"input", Kind::Stream, false, 0, -1, 0}, {"value", Kind::Value, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
         {"Mixer", {{"input_a", Kind::Stream, false, 0, -1, 0}, {"input_b", Kind::Stream, false, 1, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
@@ -480,6 +495,7 @@ struct Operand {
     uint32_t pid = plan::kNoValue;
     float c = 0.0f;
     bool cross = false;                  /* the term went through a cross-rate resampler (no fan-in summing) */
+    bool fb = false;                     /* the outgoing leg of a feedback via: reads the Delay's previous-frame output */
     Kind kind() const { return k == Stream ? Kind::Stream : Kind::Value; }
 };
 
@@ -540,9 +556,7 @@ public:
         if (err.set || !drop_dead_nodes()) return false;
         if (!check_rate_phases()) return false;
         /* ---- SoA state layout: nodes in declaration order */
-        uint32_t base = 0;
-        for (plan::Node &nd : g.nodes) { nd.state_base = base; base += plan::n_state_words(nd); }
-        g.n_state = base;
+        plan::assign_state_layout(g, 48000.0f);      /* provisional: the engine lays the state out again for its sample rate */
         return !err.set;
     }
 
@@ -568,7 +582,7 @@ private:
             g.inner_log2 = rate_log2;
         }
         const TypeInfo *ti = type_info(d.type);
-        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (the node plan has kernels for AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, LP18Filter, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
+        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (known: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, Oscillator, LP18Filter, IirLowpass, Delay, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
         if (!d.args_ok) { err.at(d.at, "constructor arguments of `" + d.name + "` must be numeric literals"); return false; }
         plan::Node n{};
         n.name = d.name; n.gate = false; n.rate_log2 = rate_log2;
@@ -600,6 +614,18 @@ private:
                 float r = d.args[1]; if (r < 0.0f) r = 0.0f; if (r > 0.99f) r = 0.99f;     /* LP18Filter::new clamps the field, not last_resonance */
                 n.cst[0] = d.args[0]; n.cst[1] = r; n.init[0] = d.args[0]; n.init[1] = d.args[1];
             }
+        } else if (t == "IirLowpass") {
+            n.type = plan::NodeType::IirLowpass;
+            if ((ok = ctor("new", 2)) && !err.set) { n.cst[0] = d.args[0]; n.cst[1] = d.args[1]; n.init[0] = d.args[0]; n.init[1] = d.args[1]; }
+        } else if (t == "Oscillator") {
+            struct { const char *c; plan::NodeType nt; } waves[] = {{"sine", plan::NodeType::OscSine}, {"square", plan::NodeType::OscSquare}, {"saw", plan::NodeType::OscSaw}};
+            for (auto &w : waves) if (d.ctor == w.c) { n.type = w.nt; ok = ctor(w.c, 2); }
+            if (ok && !err.set) { n.cst[0] = d.args[0]; n.cst[1] = d.args[1]; }
+        } else if (t == "Delay") {
+            n.type = plan::NodeType::Delay;
+            if (d.ctor == "from_seconds") {                     /* delay/mod.rs:42-45: delay_seconds * sample_rate */
+                if ((ok = ctor("from_seconds", 3)) && !err.set) { n.cst[0] = d.args[0] * d.args[2]; n.cst[1] = d.args[1]; }
+            } else if ((ok = ctor("new", 2)) && !err.set) { n.cst[0] = d.args[0]; n.cst[1] = d.args[1]; }
         } else if (t == "Gain") { n.type = plan::NodeType::Gain; if ((ok = ctor("new", 1)) && !err.set) n.cst[0] = d.args[0]; }
         else if (t == "AddValue") { n.type = plan::NodeType::AddValue; if ((ok = ctor("new", 1)) && !err.set) n.cst[0] = d.args[0]; }
         else if (t == "Mixer") { n.type = plan::NodeType::Mixer; ok = ctor("new", 0); }
@@ -641,7 +667,7 @@ private:
         if (v.k == Operand::Stream && v.s.node >= 0) return v;
         plan::Node n = blank(label, plan::NodeType::Expr, plan::ExprOp::Value);
         if (v.k == Operand::Stream) {                        /* the graph's stream input copied through: x + 0 would change -0.0, so copy = x * 1 */
-            n.op = plan::ExprOp::MulSV; n.in[0] = v.s; n.cst[0] = 1.0f;
+            n.op = plan::ExprOp::MulSV; n.in[0] = v.s; n.fb[0] = v.fb; n.cst[0] = 1.0f;
         } else if (v.k == Operand::Value) n.pid[0] = v.pid; else n.cst[0] = v.c;
         return stream_of(add_synth(n));
     }
@@ -664,13 +690,13 @@ private:
         n.rate_log2 = ls ? rate_of(l) : rate_of(r);
         if (ls && rs) {
             n.op = op == '+' ? O::AddSS : op == '-' ? O::SubSS : op == '*' ? O::MulSS : O::DivSS;
-            n.in[0] = l.s; n.in[1] = r.s;
+            n.in[0] = l.s; n.in[1] = r.s; n.fb[0] = l.fb; n.fb[1] = r.fb;
         } else {
             const Operand &s = ls ? l : r, &v = ls ? r : l;
             /* a + v == v + a and a * v == v * a bit for bit; - and / keep their operand order */
             if (op == '+') n.op = O::AddSV; else if (op == '*') n.op = O::MulSV;
             else if (op == '-') n.op = ls ? O::SubSV : O::SubVS; else n.op = ls ? O::DivSV : O::DivVS;
-            n.in[0] = s.s;
+            n.in[0] = s.s; n.fb[0] = s.fb;
             if (v.k == Operand::Value) n.pid[0] = v.pid; else n.cst[0] = v.c;
         }
         (void)at;
@@ -728,7 +754,7 @@ private:
                 if (e.args.size() != m.n_args) { err.at(e.at, "f32::" + e.name + " takes " + std::to_string(m.n_args) + " literal argument(s)"); return false; }
                 plan::Node n = blank(text_of(e), plan::NodeType::Expr, m.op);
                 const Operand xs = materialise(x, text_of(*e.a));
-                n.in[0] = xs.s; n.rate_log2 = rate_of(xs);
+                n.in[0] = xs.s; n.fb[0] = xs.fb; n.rate_log2 = rate_of(xs);
                 for (size_t i = 0; i < e.args.size(); ++i) n.cst[i] = e.args[i];
                 out = stream_of(add_synth(n)); return true;
             }
@@ -740,9 +766,32 @@ private:
     }
 
     bool connection(const Conn &c) {
-        if (c.via) { err.at(c.at, "`-> [..] ->` feedback edges are not compiled to a node plan (nodes render whole blocks; a cycle needs the per-sample walk)"); return false; }
         Operand src; bool src_event = false;
         if (!source(*c.src, src, src_event)) return false;
+        if (c.via) {
+            /* `src -> [N] -> dst` routes the edge through a hidden Delay::new(N as f32, 0.0), `src -> [name] -> dst` through
+               a declared Delay (ir/lower.rs:560-656): src feeds the delay's input in the normal order; the leg out of the
+               delay does not order the walk, so dst reads what the delay output when it last ran */
+            if (src_event || src.k != Operand::Stream) { err.at(c.at, "a `-> [..] ->` edge carries a stream"); return false; }
+            if (c.dst->k != Expr::Field) { err.at(c.at, "a `-> [..] ->` edge must end at a node input"); return false; }
+            int did;
+            if (c.via == 1) {
+                plan::Node n = blank(text_of(*c.src) + " -> [" + std::to_string((long)c.via_samples) + "]", plan::NodeType::Delay, plan::ExprOp::None);
+                n.cst[0] = c.via_samples; n.cst[1] = 0.0f;
+                n.in[0] = src.s; n.fb[0] = src.fb; n.rate_log2 = rate_of(src) > 0 ? rate_of(src) : 0;
+                did = add_synth(n);
+            } else {
+                if (!node_id.count(c.via_node)) { err.at(c.at, "`-> [" + c.via_node + "] ->`: no such node"); return false; }
+                did = node_id[c.via_node];
+                if (g.nodes[did].type != plan::NodeType::Delay) {
+                    err.at(c.at, "`-> [" + c.via_node + "] ->`: `" + c.via_node + "` does not implement AllowsFeedback (only Delay does)"); return false;
+                }
+                if (rate_of(src) > 0 && rate_of(src) != g.nodes[did].rate_log2) { err.at(c.at, "a feedback edge cannot cross a rate boundary"); return false; }
+                in_terms[did][0].push_back(src);
+            }
+            src = stream_of(did);
+            src.fb = true;
+        }
         const Kind sk = src_event ? Kind::Event : src.kind();
         const Expr &d = *c.dst;
         auto mismatch = [&](Kind dk) {
@@ -757,6 +806,7 @@ private:
                 return false;
             }
             if (sk == Kind::Event) return mismatch(Kind::Stream);
+            if (src.fb) { err.at(c.at, "a `-> [..] ->` edge must end at a node input"); return false; }
             if (!cross_rate(c, src, 0, d.name)) return false;
             out_terms.push_back(src);
             return true;
@@ -804,6 +854,7 @@ private:
         static const char *const pn[] = {"sinc", "sinc_iir", "linear", "latch"};
         plan::Node n = blank(text_of(*c.src) + " -> " + dst_label + " [" + pn[policy] + (up ? " up x" : " down x") + std::to_string(1 << l) + "]",
                              up ? plan::NodeType::Up : plan::NodeType::Down, plan::ExprOp::None);
+        if (src.fb) { err.at(c.at, "a feedback edge cannot cross a rate boundary"); return false; }
         n.in[0] = src.s; n.rate_log2 = l; n.policy = policy;
         src = stream_of(add_synth(n));
         src.cross = true;
@@ -832,7 +883,7 @@ private:
         for (const Endpoint &e : info[nid]->eps) if (!e.is_out && e.kind == Kind::Stream && e.slot == k) ep = &e;
         const std::string label = g.nodes[nid].name + "." + ep->name;
         const Operand o = sum_terms(in_terms[nid][k], label);
-        if (o.k == Operand::Stream) { g.nodes[nid].in[k] = o.s; return true; }
+        if (o.k == Operand::Stream) { g.nodes[nid].in[k] = o.s; g.nodes[nid].fb[k] = o.fb; return true; }
         if (ep->standin >= 0) {                              /* Value -> Stream edge: the kernel broadcasts the value per frame */
             plan::Node &n = g.nodes[nid];
             if (o.k == Operand::Value) n.pid[ep->standin] = o.pid; else { n.pid[ep->standin] = plan::kNoValue; n.cst[ep->standin] = o.c; }

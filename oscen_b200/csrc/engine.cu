@@ -251,9 +251,19 @@ std::vector<uint32_t> initial_state(uint32_t kind, float sr, const plan::Graph *
            (codegen/mod.rs:1309-1350); only filters and envelopes hold non-zero state afterwards */
         for (const plan::Node &nd : custom->nodes) {
             if (nd.type == plan::NodeType::Adsr) adsr(nd.state_base);
-            else if (nd.type == plan::NodeType::Tpt) tpt(nd.state_base, nd.init[0], nd.init[1]);
+            else if (nd.type == plan::NodeType::Tpt) {
+                /* an inner-rate (`* N`) node is initialised at sr * N (codegen/emit_struct.rs:578-581) */
+                TptState t; tpt_init(t, sr * (float)(1 << nd.rate_log2), nd.init[0], nd.init[1]);
+                const uint32_t b = nd.state_base;
+                s[b + 0] = t.z0; s[b + 1] = t.z1; s[b + 2] = t.cur_cutoff; s[b + 3] = t.cur_q; s[b + 4] = t.h; s[b + 5] = t.g; s[b + 6] = t.k;
+            }
+            else if (nd.type == plan::NodeType::IirLowpass) {
+                IirLpState f; iirlp_init(f, sr * (float)(1 << nd.rate_log2), nd.init[0], nd.init[1]);
+                const uint32_t b = nd.state_base;
+                s[b + 0] = f.b0; s[b + 1] = f.b1; s[b + 2] = f.b2; s[b + 3] = f.a1; s[b + 4] = f.a2;       /* v1 v2 frame_counter = 0 */
+            }
             else if (nd.type == plan::NodeType::Lp18) {
-                Lp18State f; lp18_init(f, nd.init[0], nd.init[1], sr);
+                Lp18State f; lp18_init(f, nd.init[0], nd.init[1], sr * (float)(1 << nd.rate_log2));
                 const uint32_t b = nd.state_base;
                 s[b + 0] = f.z0; s[b + 1] = f.z1; s[b + 2] = f.z2; s[b + 3] = f.g; s[b + 4] = f.h;
                 s[b + 5] = f.last_cutoff; s[b + 6] = f.last_fmod; s[b + 7] = f.last_resonance; s[b + 8] = f.resonance;
@@ -527,6 +537,12 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
     jit::Kernel jk;
     if (custom) {
         pg = custom->g; pp = custom->p;
+        plan::assign_state_layout(pg, cfg->sample_rate);          /* Delay rings are sized for this engine's sample rate */
+        if (cfg->plan == OSCEN_B200_PLAN_NODES)
+            for (const plan::Node &nd : pg.nodes) if (!plan::node_plan_has_kernel(nd.type) && nd.type != plan::NodeType::Up && nd.type != plan::NodeType::Down) {
+                g_create_error = std::string("PLAN_NODES: ") + plan::type_name(nd.type) + " (`" + nd.name + "`) runs in generated kernels only: set plan = OSCEN_B200_PLAN_FUSED";
+                return OSCEN_B200_E_ARG;
+            }
         if (cfg->plan == OSCEN_B200_PLAN_FUSED) {
             /* generate the fused kernel and compile it for sm_100a before any device memory is taken */
             jk.source = codegen::fused_kernel_source(pg, pp, kJitKernelName);

@@ -364,6 +364,138 @@ OSC_D float lp18_process(Lp18State &s, float input, float cutoff, float fmod, fl
     return lp;
 }
 
+/* =================================================================== IirLowpass == */
+/* oscen-lib/src/filters/iir_lowpass/mod.rs:15-166: JUCE-style biquad low-pass, Direct Form II Transposed;
+   coefficients are refreshed from (cutoff, q) every 32 frames (frame_counter == 0), not per sample */
+struct IirLpState {
+    float b0, b1, b2, a1, a2, v1, v2;
+    uint32_t counter;
+};
+OSC_HD void iirlp_update_coefficients(IirLpState &s, float sample_rate, float cutoff, float q_in) {
+    const float nyquist = sample_rate * 0.5f - FLT_EPSILON;
+    const float freq = clampf(cutoff, 20.0f, nyquist);
+    const float q = fmaxf(q_in, 0.01f);
+    const float n = 1.0f / OSC_TANF(kPi * freq / sample_rate);
+    const float n_squared = n * n;
+    const float c1 = 1.0f / (1.0f + 1.0f / q * n + n_squared);
+    s.b0 = c1;
+    s.b1 = c1 * 2.0f;
+    s.b2 = c1;
+    s.a1 = c1 * 2.0f * (1.0f - n_squared);
+    s.a2 = c1 * (1.0f - 1.0f / q * n + n_squared);
+}
+/* IirLowpass::new(cutoff, q) + set_sample_rate + prepare(): mod.rs:64-75,150-153 */
+OSC_HD void iirlp_init(IirLpState &s, float sample_rate, float cutoff, float q) {
+    s.v1 = 0.0f; s.v2 = 0.0f; s.counter = 0u;
+    iirlp_update_coefficients(s, sample_rate, cutoff, q);
+}
+OSC_D float iirlp_process(IirLpState &s, float input_in, float cutoff, float q, float sample_rate) {
+    if (s.counter == 0u) iirlp_update_coefficients(s, sample_rate, cutoff, q);
+    s.counter = (s.counter + 1u) % 32u;
+    const float input = fabsf(input_in) < 1e-15f ? 0.0f : input_in;
+    const float output = s.b0 * input + s.v1;
+    s.v1 = s.b1 * input - s.a1 * output + s.v2;
+    s.v2 = s.b2 * input - s.a2 * output;
+    if (fabsf(s.v1) < 1e-15f) s.v1 = 0.0f;
+    if (fabsf(s.v2) < 1e-15f) s.v2 = 0.0f;
+    return output;
+}
+
+/* =================================================================== Oscillator == */
+/* oscen-lib/src/oscillators/mod.rs:7-76: the naive (not band-limited) oscillator; `%` is fmodf */
+enum : int { OSC_SINE = 0, OSC_SQUARE = 1, OSC_SAW = 2 };
+OSC_HD float fmod1(float x) {                          /* x % 1.0: exact, sign of the dividend */
+    float r = x - truncf(x);
+    if (r == 0.0f) r = copysignf(0.0f, x);
+    return r;
+}
+template <int WAVE>
+OSC_D float osc_process(float &phase, float frequency_in, float frequency_mod, float amplitude, float sample_rate) {
+    const float frequency = frequency_in * (1.0f + frequency_mod);
+    const float p = fmod1(phase);
+    float w;
+    if (WAVE == OSC_SINE) {
+        w = om_sinf_u(p * 2.0f * kPi);
+    } else if (WAVE == OSC_SQUARE) {
+        w = p < 0.5f ? 1.0f : -1.0f;
+    } else {
+        const float transition_width = 0.1f;
+        const float raw_saw = 2.0f * p - 1.0f;
+        if (p > (1.0f - transition_width / 2.0f)) {
+            const float t = (p - (1.0f - transition_width / 2.0f)) / (transition_width / 2.0f);
+            w = -1.0f + (1.0f - t * t) * (raw_saw + 1.0f);
+        } else {
+            w = raw_saw;
+        }
+    }
+    const float out = w * amplitude;
+    phase += frequency / sample_rate;
+    phase = fmod1(phase);
+    return out;
+}
+
+/* ======================================================================== Delay == */
+/* oscen-lib/src/delay/mod.rs:5-86 over ring_buffer/mod.rs:29-202 (PowerOfTwo mode).  The ring lives in the
+   voice's SoA state rows (`ring[slot * stride]`, stride = n_voices: slot-major, so voices that share a delay
+   length touch consecutive addresses).  `cap` is a power of two: the reference's capacity
+   next_power_of_two(min((2 * sr) as usize, 88200)) in general, or a smaller ring when the delay is a constant
+   whole number of samples (the exact-sample read path never looks further back than that). */
+struct DelayState {
+    uint32_t write_pos, counter;
+    float output;                                      /* persists: a feedback edge reads last frame's value */
+};
+OSC_HD uint32_t delay_reference_capacity(float sample_rate) {
+    uint32_t size = f32_as_u32(2.0f * sample_rate);
+    if (size > 88200u) size = 88200u;
+    if (size < 1u) size = 1u;
+    uint32_t cap = 1u;
+    while (cap < size) cap <<= 1;
+    return cap;
+}
+/* RingBuffer::get (ring_buffer/mod.rs:167-202) */
+OSC_D float ring_get(const float *ring, size_t stride, uint32_t cap, uint32_t write_pos, float offset) {
+    const uint32_t mask = cap - 1u;
+    const float nn = fmaxf(offset, 0.0f);
+    const float fr = nn - truncf(nn);
+    if (fr < 1e-6f || (1.0f - fr) < 1e-6f) {
+        const float r = roundf(nn);
+        /* `as usize` saturates; (offset_samples % capacity) with a power-of-two capacity */
+        const unsigned long long os = r >= 18446744073709551616.0f ? 0xFFFFFFFFFFFFFFFFull : (unsigned long long)r;
+        const uint32_t idx = ((write_pos + cap) - (uint32_t)(os & (unsigned long long)mask) - 1u) & mask;
+        return ring[(size_t)idx * stride];
+    }
+    const float n = (float)cap;
+    const float rp0 = (float)write_pos - nn - 1.0f;
+    const float rp = fmodf(fmodf(rp0, n) + n, n);
+    const uint32_t i = (uint32_t)rp;
+    const float f = rp - truncf(rp);
+    const float v0 = ring[(size_t)((i - 1u) & mask) * stride], v1 = ring[(size_t)(i & mask) * stride];
+    const float v2 = ring[(size_t)((i + 1u) & mask) * stride], v3 = ring[(size_t)((i + 2u) & mask) * stride];
+    if (cap < 4u) return fmaf(v1, 1.0f - f, v2 * f);     /* get_linear: a.mul_add(1.0 - f, b * f) */
+    const float c0 = v1;
+    const float c1 = 0.5f * (v2 - v0);
+    const float c2 = v0 - 2.5f * v1 + 2.0f * v2 - 0.5f * v3;
+    const float c3 = 0.5f * (v3 - v0) + 1.5f * (v1 - v2);
+    return c0 + f * (c1 + f * (c2 + f * c3));
+}
+/* Delay::process.  CONNECTED_D / CONNECTED_F: the value endpoint is assigned from a graph input every frame, so the
+   clamp of apply_parameter_updates (every 32 frames) only holds for that frame; an unconnected endpoint keeps its
+   clamped constructor value (passed in already clamped). */
+template <bool CONNECTED_D, bool CONNECTED_F>
+OSC_D float delay_process(DelayState &s, float *ring, size_t stride, uint32_t cap, float max_delay,
+                          float input, float delay_samples, float feedback) {
+    if (s.counter == 0u) {
+        if (CONNECTED_D) delay_samples = clampf(delay_samples, 0.0f, max_delay);
+        if (CONNECTED_F) feedback = clampf(feedback, 0.0f, 0.99f);
+    }
+    s.counter = (s.counter + 1u) % 32u;
+    const float delayed = ring_get(ring, stride, cap, s.write_pos, delay_samples);
+    ring[(size_t)s.write_pos * stride] = input + delayed * feedback;
+    s.write_pos = (s.write_pos + 1u) & (cap - 1u);
+    s.output = delayed;
+    return delayed;
+}
+
 /* ===================================================================== HardClip == */
 /* examples/oversampled-saturator/src/main.rs:55-62 */
 OSC_D float hardclip_process(float input) {

@@ -41,6 +41,10 @@ enum class NodeType : uint8_t {
     Crossfade,     /* Crossfade: two outputs */
     HardClip,      /* HardClip */
     Expr,          /* one operator of a compound source expression; `op` says which (ExprOp) */
+    IirLowpass,    /* IirLowpass (JUCE-style biquad)        stream: input; value: cutoff q                      (generated kernels only) */
+    OscSine, OscSquare, OscSaw,   /* the naive Oscillator         stream: frequency_mod; value: frequency amplitude   (generated kernels only) */
+    Delay,         /* Delay over a power-of-two ring        stream: input; value: delay_samples feedback        (generated kernels only);
+                      the one node type a feedback edge (`-> [N] ->`, `-> [name] ->`) may run through (AllowsFeedback) */
     Up,            /* cross-rate stream edge outer -> inner (`* N` destination): StreamUpsampler of `policy`   */
     Down,          /* cross-rate stream edge inner -> outer: StreamDownsampler of `policy` (generated kernels only) */
 };
@@ -70,6 +74,8 @@ struct Node {
     std::string name;
     NodeType type;
     StreamRef in[kMaxStreamIn];      /* stream inputs (meaning per type, see above) */
+    bool fb[kMaxStreamIn] = {false, false, false};   /* the edge into in[k] is the outgoing leg of a feedback via: it reads the Delay's
+                                        output of the PREVIOUS frame and does not order the nodes (ir/lower.rs:1015-1085 skips it) */
     uint32_t pid[kMaxParams];        /* value-input ids of the graph feeding this node's parameter slots (kNoValue: use cst).
                                         Slots [0, n_value) are the node's value endpoints; the slots after them are the
                                         stand-ins of its stream endpoints, read when in[k] is unconnected (constructor
@@ -81,6 +87,8 @@ struct Node {
     float init[2] = {0.0f, 0.0f};    /* constructor arguments that seed the node's state (TptFilter / LP18Filter: cutoff, q) */
     int rate_log2 = 0;               /* 0: the graph's rate; L: the node runs 2^L times per frame (`= T::new() * N`) at sample rate sr * N */
     int policy = 0;                  /* Up / Down: connection policy (kPolicy*) */
+    uint32_t ring_cap = 0;           /* Delay: ring capacity in samples (power of two), set by assign_state_layout() */
+    float max_delay = 0.0f;          /* Delay: the reference ring's capacity - 1 (the clamp of apply_parameter_updates) */
 };
 
 /* a value input of a DSL-compiled graph (`input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];`) */
@@ -133,8 +141,25 @@ inline uint32_t n_state_words(const Node &nd) {
     case NodeType::Tpt: return 7;             /* z0 z1 cur_cutoff cur_q h g k */
     case NodeType::PolyBlepSine: case NodeType::PolyBlepSaw: case NodeType::PolyBlepSquare: case NodeType::PolyBlepTriangle: return 1;
     case NodeType::Lp18: return 9;
+    case NodeType::IirLowpass: return 8;      /* b0 b1 b2 a1 a2 v1 v2 frame_counter */
+    case NodeType::OscSine: case NodeType::OscSquare: case NodeType::OscSaw: return 1;
+    case NodeType::Delay: return 3u + nd.ring_cap;   /* write_pos frame_counter output + the ring */
     default: return 0;
     }
+}
+inline bool node_plan_has_kernel(NodeType t) {
+    return t != NodeType::IirLowpass && t != NodeType::OscSine && t != NodeType::OscSquare && t != NodeType::OscSaw &&
+           t != NodeType::Delay && t != NodeType::Up && t != NodeType::Down;
+}
+/* Delay::prepare (delay/mod.rs:59-69): RingBuffer::new(min((2 * sr) as usize, 88200)) in PowerOfTwo mode */
+inline uint32_t delay_reference_capacity(float sample_rate) {
+    const float t = 2.0f * sample_rate;
+    uint32_t size = !(t > 0.0f) ? 0u : (t >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)t);
+    if (size > 88200u) size = 88200u;
+    if (size < 1u) size = 1u;
+    uint32_t cap = 1u;
+    while (cap < size) cap <<= 1;
+    return cap;
 }
 
 /* Kahn's algorithm in waves: wave k holds every node whose producers all sit in earlier waves */
@@ -143,11 +168,14 @@ inline bool compile(const Graph &g, Plan &p, std::string &err) {
     std::vector<int> indeg(n, 0);
     std::vector<std::vector<int>> users(n);
     for (int i = 0; i < n; ++i)
-        for (const StreamRef &r : g.nodes[i].in)
+        for (int k = 0; k < kMaxStreamIn; ++k) {
+            const StreamRef &r = g.nodes[i].in[k];
             if (r.node >= 0) {
                 if (r.node >= n || r.port >= n_outputs(g.nodes[r.node].type)) { err = "bad edge"; return false; }
+                if (g.nodes[i].fb[k]) continue;          /* the outgoing leg of a feedback via does not order the walk */
                 indeg[i]++; users[r.node].push_back(i);
             }
+        }
     p = Plan();
     p.first_stream.assign(n, 0);
     for (int i = 0; i < n; ++i) { p.first_stream[i] = p.n_streams; p.n_streams += n_outputs(g.nodes[i].type); }
@@ -172,7 +200,7 @@ inline bool compile(const Graph &g, Plan &p, std::string &err) {
         std::sort(next.begin(), next.end());
         ready.swap(next);
     }
-    if (done != n) { err = "cycle in graph (feedback edges are not supported)"; return false; }
+    if (done != n) { err = "cycle in graph: close it through a delay (`a.output -> [N] -> b.input` or `-> [delay_node] ->`)"; return false; }
     if (g.output.node < 0 || g.output.node >= n) { err = "graph has no output"; return false; }
     return true;
 }
@@ -187,6 +215,11 @@ inline const char *type_name(NodeType t) {
     case NodeType::PolyBlepSquare: return "PolyBlepOscillator::square";
     case NodeType::PolyBlepTriangle: return "PolyBlepOscillator::triangle";
     case NodeType::Expr: return "Expr";
+    case NodeType::IirLowpass: return "IirLowpass";
+    case NodeType::OscSine: return "Oscillator::sine";
+    case NodeType::OscSquare: return "Oscillator::square";
+    case NodeType::OscSaw: return "Oscillator::saw";
+    case NodeType::Delay: return "Delay";
     case NodeType::Up: return "UpEdge";
     case NodeType::Down: return "DownEdge";
     case NodeType::Lp18: return "LP18Filter";
@@ -197,6 +230,37 @@ inline const char *type_name(NodeType t) {
     case NodeType::Crossfade: return "Crossfade";
     default: return "HardClip";
     }
+}
+
+/* SoA state layout (nodes in order) for a given sample rate: Delay rings are sized here — the reference capacity
+   in general; a constant whole-sample delay only ever reads `delay` samples back through the exact-sample path
+   (ring_buffer/mod.rs:178-190), so its ring shrinks to the next power of two above it.  Unconnected Delay
+   parameters are clamped like the first apply_parameter_updates() does (delay/mod.rs:47-56). */
+inline void assign_state_layout(Graph &g, float sample_rate) {
+    uint32_t base = 0;
+    for (Node &nd : g.nodes) {
+        if (nd.type == NodeType::Delay) {
+            const float sr = sample_rate * (float)(1 << nd.rate_log2);
+            const uint32_t ref_cap = delay_reference_capacity(sr);
+            nd.max_delay = (float)ref_cap - 1.0f;
+            nd.ring_cap = ref_cap;
+            if (nd.pid[1] == kNoValue) nd.cst[1] = nd.cst[1] < 0.0f ? 0.0f : (nd.cst[1] > 0.99f ? 0.99f : nd.cst[1]);
+            if (nd.pid[0] == kNoValue) {
+                float d = nd.cst[0];
+                d = d < 0.0f ? 0.0f : (d > nd.max_delay ? nd.max_delay : d);     /* NaN stays NaN, as f32::clamp */
+                nd.cst[0] = d;
+                const float fr = d - (float)(uint32_t)d;
+                if (d == d && (fr < 1e-6f || (1.0f - fr) < 1e-6f)) {
+                    const uint32_t whole = (uint32_t)(d + 0.5f);
+                    uint32_t cap = 1u;
+                    while (cap < whole + 1u) cap <<= 1;
+                    if (cap < ref_cap) nd.ring_cap = cap;
+                }
+            }
+        }
+        nd.state_base = base; base += n_state_words(nd);
+    }
+    g.n_state = base;
 }
 
 inline const char *op_name(ExprOp o) {

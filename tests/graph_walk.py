@@ -93,6 +93,32 @@ def lp18(cutoff, res, sr):
     return Node(st, L.orc_lp18_process)
 
 
+def naive_osc(wave, freq, amp, sr):
+    L = O.lib()
+    st = O.NaiveOsc()
+    L.orc_osc_new(C.byref(st), freq, amp, {"sine": 0, "square": 1, "saw": 2}[wave])
+    st.sample_rate = sr
+    return Node(st, L.orc_osc_process)
+
+
+def iirlp(cutoff, q, sr):
+    L = O.lib()
+    st = O.IirLp()
+    L.orc_iirlp_new(C.byref(st), cutoff, q)
+    st.sample_rate = sr
+    L.orc_iirlp_prepare(C.byref(st))
+    return Node(st, L.orc_iirlp_process)
+
+
+def delay(delay_samples, feedback, sr):
+    L = O.lib()
+    st = O.Delay()
+    L.orc_delay_new(C.byref(st), delay_samples, feedback)
+    st.sample_rate = sr
+    L.orc_delay_prepare(C.byref(st))
+    return Node(st, L.orc_delay_process)
+
+
 def render(make_voice, n_voices, frames, values=None, gates=None, stream_in=None):
     """make_voice(v) -> (frame_fn, gate_fn); frame_fn(values_of_voice: dict, x: f32) -> f32 output;
     gate_fn(scalar) handles a gate event BEFORE that frame's process (derive(Node) process_event_inputs).

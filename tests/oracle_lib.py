@@ -68,6 +68,24 @@ class Lp18(C.Structure):
                                   "output")]
 
 
+class IirLp(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("input", "cutoff", "q", "output", "b0", "b1", "b2", "a1", "a2", "v1", "v2",
+                                         "sample_rate")] + [("frame_counter", C.c_size_t), ("frames_per_update", C.c_size_t)]
+
+
+class Ring(C.Structure):
+    _fields_ = [("buffer", C.POINTER(C.c_float)), ("write_pos", C.c_size_t), ("capacity", C.c_size_t), ("mask", C.c_size_t)]
+
+
+class Delay(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("input", "delay_samples", "feedback", "output")] + [("ring", Ring), ("sample_rate", C.c_float),
+                                                                                         ("frames_per_update", C.c_size_t), ("frame_counter", C.c_size_t)]
+
+
+class NaiveOsc(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("phase", "frequency", "frequency_mod", "amplitude", "output")] + [("waveform", C.c_int), ("sample_rate", C.c_float)]
+
+
 class HbDown(C.Structure):
     _fields_ = [("history", C.c_float * 24), ("head", C.c_size_t)]
 
@@ -133,6 +151,13 @@ def lib():
         L.orc_polyblep_new.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int]
         L.orc_polyblep_set_sample_rate.argtypes = [C.c_void_p, C.c_float]
         L.orc_lp18_new.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.orc_iirlp_new.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.orc_delay_new.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.orc_osc_new.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int]
+        L.orc_ring_init.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_ring_push.argtypes = [C.c_void_p, C.c_float]
+        L.orc_ring_get.argtypes = [C.c_void_p, C.c_float]
+        L.orc_ring_get.restype = C.c_float
         L.orc_ramp_new.argtypes = [C.c_void_p, C.c_float]
         L.orc_ramp_set_immediate.argtypes = [C.c_void_p, C.c_float]
         L.orc_ramp_set_with_ramp.argtypes = [C.c_void_p, C.c_float, C.c_uint32]

@@ -157,7 +157,10 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6) * 3; connection o.output -> out;", "rate factor must be in {1, 2, 4, 8}"),
     ("output stream out; node v = [PolyBlepOscillator::saw(2000.0, 0.6); 4]; connection v.output -> out;", "is not a graph of this text"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6)\n connection o.output -> out;", "2:2: expected `;`"),
-    (ONE_OSC + "connection o.output -> [4] -> out;", "feedback edges"),
+    (ONE_OSC + "connection o.output -> [4] -> out;", "must end at a node input"),
+    (ONE_OSC + "node g = Gain::new(1.0); connection o.output -> [g] -> g.input; connection g.output -> out;", "does not implement AllowsFeedback (only Delay does)"),
+    (ONE_OSC + "node g = Gain::new(1.0); connection o.output -> [nowhere] -> g.input; connection g.output -> out;", "no such node"),
+    (ONE_OSC + "node g = Gain::new(1.0); connection o.output -> [1.5] -> g.input; connection g.output -> out;", "must be an integer literal"),
     (ONE_OSC + "connection o.outptu -> out;", "node `o` has no endpoint `outptu`"),
     (ONE_OSC + "connection osc.output -> out;", "cannot resolve the source"),
     (ONE_OSC + "connection o.output -> nowhere;", "cannot resolve the destination"),
@@ -351,3 +354,64 @@ def test_nested_scalar_graph_is_reported():
     with pytest.raises(abi.GraphCompileError) as ei:
         abi.Graph(text("fm_voice.graph") + "graph! { name: Outer; output stream out; node v = FMVoice::new(); connection v.audio_out -> out; }")
     assert "nested graph `FMVoice` as a scalar node is not supported" in str(ei.value)
+
+
+# ------------------------------------------------------------------ feedback edges and the rest of the node library
+FEEDBACK = """
+    name: Echo;
+    input time: value = 480.0;
+    input fb: value = 0.4;
+    output stream out;
+    nodes {
+        osc = Oscillator::saw(220.0, 0.5);
+        echo = Delay::new(480.0, 0.0);
+        lp = IirLowpass::new(3000.0, 0.707);
+        tap = Gain::new(0.5);
+        sum = Mixer::new();
+    }
+    connections {
+        osc.output -> sum.input_a;
+        lp.output * fb -> [echo] -> sum.input_b;
+        time -> echo.delay_samples;
+        sum.output -> lp.input;
+        sum.output -> [1] -> tap.input;
+        sum.output + tap.output -> out;
+    }
+"""
+
+
+def test_feedback_edges_close_cycles_through_delays():
+    g = abi.Graph(FEEDBACK)
+    flat = [n for grp in groups(g.launches()) for n in grp]
+    # the legs OUT of the delays do not order the walk: sum and tap run before the delays they read
+    assert flat.index("sum") < flat.index("lp") < flat.index("lp.output * fb") < flat.index("echo")
+    assert flat.index("tap") < flat.index("sum.output -> [1]")
+    # ring sizes: `time` is connected, so `echo` keeps the reference capacity (131072 at 48 kHz); `-> [1] ->` needs 2 slots
+    assert "state words per voice: %d" % (1 + 8 + (3 + 131072) + (3 + 2)) in g.describe()
+    src = g.codegen()
+    assert "delay_process<true, false>" in src and "delay_process<false, false>" in src and "iirlp_process(" in src and "osc_process<OSC_SAW>" in src
+    assert g.jit_check() > 10000
+    # without the via the same wiring is a cycle
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(FEEDBACK.replace("-> [echo] -> sum.input_b", "-> sum.input_b"))
+    assert "cycle in graph" in str(ei.value)
+
+
+def test_constant_whole_sample_delays_get_small_rings():
+    g = abi.Graph("""
+        output stream out;
+        node o = Oscillator::sine(100.0, 1.0);
+        node d = Delay::new(11025.0, 0.3);              // examples/simple-echo/src/lib.rs:18
+        node e = Delay::from_seconds(0.25, 0.0, 48000.0);
+        node f = Delay::new(10.5, 0.0);                 // fractional: cubic reads depend on the reference capacity
+        connection o.output -> d.input; connection o.output -> e.input; connection o.output -> f.input;
+        connection d.output + e.output + f.output -> out;
+    """)
+    assert "state words per voice: %d" % (1 + (3 + 16384) + (3 + 16384) + (3 + 131072)) in g.describe()
+
+
+def test_node_plan_refuses_generated_only_node_types():
+    g = abi.Graph(FEEDBACK)
+    with pytest.raises(abi.EngineError) as ei:
+        abi.Engine.from_graph(g, 64, plan=abi.PLAN_NODES)
+    assert "runs in generated kernels only" in str(ei.value)

@@ -566,3 +566,97 @@ def test_multithreaded_oracle_is_identical():
         bank.process_block(128)
     assert np.array_equal(a.read_voice_out(), b.read_voice_out())
     assert np.array_equal(a.read_mix(), b.read_mix())
+
+
+# ------------------------------------------------------------------ RingBuffer / Delay / IirLowpass
+def _ring(size):
+    L = O.lib()
+    r = O.Ring()
+    L.orc_ring_init(C.byref(r), size)
+    return L, r
+
+
+def test_ring_buffer_capacity_is_next_power_of_two():
+    """ring_buffer/tests.rs:7-36,236-249 (PowerOfTwo mode, the default the Delay node uses)"""
+    for size, cap in ((5, 8), (8, 8), (9, 16), (17, 32), (0, 1), (40, 64), (10, 16), (88200, 131072)):
+        L, r = _ring(size)
+        assert r.capacity == cap and r.mask == cap - 1 and r.write_pos == 0
+        L.orc_ring_free(C.byref(r))
+
+
+def test_ring_buffer_push_wrap_and_exact_offsets():
+    """ring_buffer/tests.rs:62-86 (push/wrap) and :113-143 (get at whole offsets, wrap past the capacity, negative -> 0)"""
+    L, r = _ring(4)
+    for v in (1.0, 2.0, 3.0, 4.0):
+        L.orc_ring_push(C.byref(r), v)
+    assert r.write_pos == 0 and r.buffer[0] == 1.0 and r.buffer[3] == 4.0
+    L.orc_ring_push(C.byref(r), 5.0)
+    assert r.write_pos == 1 and r.buffer[0] == 5.0 and r.buffer[1] == 2.0
+    L.orc_ring_push(C.byref(r), 6.0)
+    assert r.write_pos == 2 and r.buffer[1] == 6.0
+    # buffer [5, 6, 3, 4], newest = 6
+    for off, want in ((0.0, 6.0), (1.0, 5.0), (2.0, 4.0), (3.0, 3.0), (4.0, 6.0), (-1.0, 6.0), (1.0000005, 5.0), (0.9999995, 5.0)):
+        assert L.orc_ring_get(C.byref(r), off) == want, off
+
+
+def test_ring_buffer_interpolation_goldens():
+    """ring_buffer/tests.rs:146-170 (linear: capacity < 4) and :173-191 (Catmull-Rom: 13.1875 for 4, 8, 16, 1 at f = 0.5)"""
+    L, r = _ring(2)
+    L.orc_ring_push(C.byref(r), 5.0); L.orc_ring_push(C.byref(r), 9.0)          # newest 9, then 5
+    assert abs(L.orc_ring_get(C.byref(r), 0.5) - 7.0) < 1e-6
+    L, r = _ring(8)
+    for v in (0.0, 0.0, 4.0, 8.0, 16.0, 1.0, 0.0, 0.0):                         # write_pos back at 0
+        L.orc_ring_push(C.byref(r), v)
+    # rp = (0 - 3.5 - 1 + 8) % 8 = 3.5: neighbours 4, 8, 16, 1
+    assert abs(L.orc_ring_get(C.byref(r), 3.5) - 13.1875) < 1e-6
+
+
+def test_delay_node_delays_by_whole_samples_and_feeds_back():
+    """delay/mod.rs:71-85: output = ring.get(delay_samples), then push(input + delayed * feedback)"""
+    L = O.lib()
+    d = O.Delay()
+    L.orc_delay_new(C.byref(d), 3.0, 0.5)
+    d.sample_rate = 48000.0
+    L.orc_delay_prepare(C.byref(d))
+    assert d.ring.capacity == 131072                                 # next_power_of_two(min(96000, 88200))
+    out = []
+    for n in range(12):
+        d.input = 1.0 if n == 0 else 0.0
+        L.orc_delay_process(C.byref(d))
+        out.append(d.output)
+    # get(3) reads the sample pushed 4 process() calls earlier; each echo comes back at half the level
+    assert out == [0, 0, 0, 0, 1.0, 0, 0, 0, 0.5, 0, 0, 0]
+    # parameters are clamped on update frames only (every 32nd): feedback 2.0 -> 0.99, delay -5 -> 0
+    L.orc_delay_new(C.byref(d), -5.0, 2.0); d.sample_rate = 44100.0; L.orc_delay_prepare(C.byref(d))
+    L.orc_delay_process(C.byref(d))
+    assert d.delay_samples == 0.0 and abs(d.feedback - 0.99) < 1e-7
+    L.orc_delay_free(C.byref(d))
+
+
+def test_iir_lowpass_reference_tests():
+    """filters/iir_lowpass/mod.rs:176-330: JUCE coefficient formula, DC gain ~1, bounded impulse response, high-Q
+    stability, denormal snap"""
+    L = O.lib()
+    f = O.IirLp()
+    q = np.float32(0.70710678)
+    L.orc_iirlp_new(C.byref(f), 1000.0, q); f.sample_rate = 48000.0; L.orc_iirlp_prepare(C.byref(f))
+    n = np.float32(1.0) / np.float32(math.tan(np.float32(np.float32(np.float32(math.pi) * np.float32(1000.0)) / np.float32(48000.0))))
+    c1 = np.float32(1.0) / (np.float32(1.0) + np.float32(1.0) / q * n + n * n)
+    assert abs(f.b0 - c1) < 1e-6 and abs(f.b1 - 2 * c1) < 1e-6 and abs(f.b2 - c1) < 1e-6
+    assert abs(f.a1 - c1 * 2 * (1 - n * n)) < 1e-5 and abs(f.a2 - c1 * (1 - 1 / q * n + n * n)) < 1e-5
+    f.frames_per_update = 1
+    for _ in range(1000):
+        f.input = 1.0; L.orc_iirlp_process(C.byref(f))
+    assert abs(f.output - 1.0) < 0.01
+    L.orc_iirlp_new(C.byref(f), 2000.0, q); f.sample_rate = 48000.0; L.orc_iirlp_prepare(C.byref(f)); f.frames_per_update = 1
+    outs = []
+    for k in range(8):
+        f.input = 1.0 if k == 0 else 0.0; L.orc_iirlp_process(C.byref(f)); outs.append(f.output)
+    assert outs[0] > 0 and all(abs(x) < 2.0 for x in outs[1:])
+    L.orc_iirlp_new(C.byref(f), 1000.0, 10.0); f.sample_rate = 48000.0; L.orc_iirlp_prepare(C.byref(f)); f.frames_per_update = 1
+    for k in range(100):
+        f.input = 1.0 if k == 0 else 0.0; L.orc_iirlp_process(C.byref(f))
+        assert abs(f.output) < 10.0
+    L.orc_iirlp_new(C.byref(f), 100.0, q); f.sample_rate = 48000.0; L.orc_iirlp_prepare(C.byref(f))
+    f.input = 1e-20; L.orc_iirlp_process(C.byref(f))
+    assert f.output == 0.0

@@ -16,6 +16,7 @@
  */
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -105,8 +106,15 @@ struct Emitter {
         return t == plan::NodeType::PolyBlepSine || t == plan::NodeType::PolyBlepSaw || t == plan::NodeType::PolyBlepSquare || t == plan::NodeType::PolyBlepTriangle;
     }
 
+    /* tuning knobs (A/B measurements: tools/bench_dsl.py under different environments) */
+    static int env_int(const char *name, int def) { const char *e = getenv(name); return e && *e ? atoi(e) : def; }
+    bool hoist_adsr = true;
+    int min_blocks = 8;
+
     std::string run(const char *kernel_name) {
         using T = plan::NodeType;
+        hoist_adsr = env_int("OSCEN_B200_JIT_ADSR_HOIST", 1) != 0;
+        min_blocks = env_int("OSCEN_B200_JIT_MIN_BLOCKS", 8);
         const int n_nodes = (int)g.nodes.size();
         const uint32_t ni = (uint32_t)g.inputs.size();
         const bool has_in = !g.stream_input.empty();
@@ -116,7 +124,9 @@ struct Emitter {
         const int NI = 1 << g.inner_log2;
         line(0, multirate ? "#include \"resample_edges.cuh\"" : "#include \"state_io.cuh\"");
         line(0, "using namespace oscen;");
-        snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(kCta) %s(const __grid_constant__ KernelArgs a) {", kernel_name);
+        /* min_blocks CTAs of 64 threads per SM: 8 caps the kernel at 128 registers per thread, so that the 1024 CTAs of a
+           65 536-voice bank (6.9 per SM) are resident in one wave */
+        snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(kCta, %d) %s(const __grid_constant__ KernelArgs a) {", min_blocks, kernel_name);
         line(0, b);
         line(1, "__shared__ float tile[kTileF * kTileW];");
         line(1, "__shared__ float isum[kTileF * kCta];");
@@ -149,6 +159,9 @@ struct Emitter {
             case T::Adsr:
                 line(1, "AdsrState " + N(i) + "; adsr_load(" + N(i) + ", a.state, " + base + ", n, vs);");
                 line(1, "AdsrDerived " + D(i) + "; adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", " + SR(i) + ");");
+                /* update_sustain_level()'s sustain-level / countdown-clamp part only changes with its inputs: refreshed at block
+                   start and on frames where a value input moved or a gate arrived (nodes.cuh adsr_refresh), not every sample */
+                if (hoist_adsr) line(1, "AdsrHot h" + std::to_string(i) + "; adsr_refresh(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");");
                 break;
             case T::FmOperator:
                 line(1, "FmOpState " + N(i) + "; " + N(i) + ".phase = a.state[(size_t)(" + base + " + 0u) * n + vs]; " + N(i) + ".prev = a.state[(size_t)(" + base + " + 1u) * n + vs];");
@@ -233,6 +246,16 @@ struct Emitter {
         }
         line(5, "ec.advance(ev_end);");
         line(4, "}");
+        {
+            bool any_adsr = false;
+            for (int i = 0; i < n_nodes; ++i) any_adsr |= g.nodes[i].type == T::Adsr;
+            if (any_adsr && hoist_adsr) {
+                line(4, "if (changed) {");
+                for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
+                    line(5, "adsr_refresh(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");");
+                line(4, "}");
+            }
+        }
         if (has_in) line(4, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
         /* ---- the walk: nodes in topological order (multirate graphs: per phase, emit_frame.rs:114-176) */
         auto emit_node = [&](int i, int ind) {
@@ -240,7 +263,10 @@ struct Emitter {
             const std::string o = "const float " + S(i) + " = ";
             const std::string cm = "    /* " + nd.name + " */";
             switch (nd.type) {
-            case T::Adsr: line(ind, o + "adsr_process(" + N(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm); break;
+            case T::Adsr:
+                if (hoist_adsr) line(ind, o + "adsr_process_t<false>(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
+                else line(ind, o + "adsr_process(" + N(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
+                break;
             case T::FmOperator: line(ind, o + "fmop_process(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ");" + cm); break;
             case T::Tpt: line(ind, o + "tpt_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + IN(i, 1, 1) + ", " + P(i, 0) + ", " + IN(i, 2, 2) + ", " + SR(i) + ");" + cm); break;
             case T::Lp18: line(ind, o + "lp18_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + P(i, 0) + ", " + P(i, 2) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm); break;

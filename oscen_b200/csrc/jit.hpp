@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -66,8 +68,23 @@ inline std::string csrc_dir() {
     return "oscen_b200/csrc";
 }
 
-/* source -> sm_100a cubin.  Needs no GPU (the CPU test suite compiles every test graph). */
+/* source -> sm_100a cubin.  Needs no GPU (the CPU test suite compiles every test graph).  Compiled images are kept
+   per process, keyed by the source text: engines of the same graph share one compilation. */
+inline bool compile_cubin_uncached(const std::string &source, std::vector<char> &cubin, std::string &log, std::string &err);
 inline bool compile_cubin(const std::string &source, std::vector<char> &cubin, std::string &log, std::string &err) {
+    static std::mutex mu;
+    static std::map<std::string, std::vector<char>> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(source);
+        if (it != cache.end()) { cubin = it->second; return true; }
+    }
+    if (!compile_cubin_uncached(source, cubin, log, err)) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    cache[source] = cubin;
+    return true;
+}
+inline bool compile_cubin_uncached(const std::string &source, std::vector<char> &cubin, std::string &log, std::string &err) {
     if (!nvrtc_load(err)) return false;
     Nvrtc &n = nvrtc();
     void *prog = nullptr;

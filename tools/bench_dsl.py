@@ -60,6 +60,8 @@ def main():
         if "Edge [" not in g.describe():       # multirate graphs run as generated kernels only
             ways.append(("node plan (CUDA graph)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_NODES)))
         ways.append(("hand-written fused kernel", abi.Engine(kind, n, vpi, 48000.0, 0, abi.PLAN_FUSED, keep)))
+        if os.environ.get("OSCEN_BENCH_WAYS") == "gen":
+            ways = ways[:1]
         for name, e in ways:
             k_ms = run(e, n, freq_id, steps, has_gate, has_in)
             print(json.dumps({"graph": file, "way": name, "voices": n, "frames": FRAMES, "kernel_ms": k_ms,

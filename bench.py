@@ -88,9 +88,12 @@ class Workload:
 
 class ClockSampler(threading.Thread):
     """SM clock and clock-event (throttle) reasons DURING the timed region (B200_PROFILING.md's clocks
-    line).  In-process NVML polling every ~4 ms (the timed region of the default run is only tens of
+    line).  In-process NVML polling every ~10 ms (the timed region of the default run is only tens of
     milliseconds; an `nvidia-smi -lms` child needs seconds to start on an 8-GPU box and then misses
-    it); falls back to the nvidia-smi loop when NVML cannot be loaded."""
+    it); falls back to the nvidia-smi loop when NVML cannot be loaded.  Only rank 0 samples (its own
+    GPU): NVML queries take a driver-wide lock, and with 8 ranks polling at 250 Hz each a few steps per
+    run stalled for 5-15 ms (profiles/r01_diag_8gpu_nvml_sampler.log: 0.41 ms/step with all ranks
+    sampling, 0.29 without)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -131,7 +134,7 @@ class ClockSampler(threading.Thread):
             for name, bit in names:
                 if mask & bit:
                     self.reasons.add(name)
-            time.sleep(0.004)
+            time.sleep(0.010)
 
     def _smi_loop(self):
         self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -359,7 +362,11 @@ def run(out):
         gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         gpu_uuid = None
-    sampler = ClockSampler(local_rank, gpu_uuid); sampler.begin()
+    sampler = ClockSampler(local_rank, gpu_uuid)
+    if rank != 0 or os.environ.get("OSCEN_BENCH_NO_SAMPLER"):   # rank 0 reports the clocks line (env: diagnostics only)
+        sampler.stop = lambda: {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "disabled"}
+    else:
+        sampler.begin()
     st0 = eng.stats()
     step_ms, kern_ms = [], []
     t_wall0 = time.perf_counter()
@@ -370,6 +377,9 @@ def run(out):
         step_ms.append(eng.last_block_ms()); kern_ms.append(eng.last_kernel_ms())
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    if os.environ.get("OSCEN_BENCH_DUMP"):                # diagnostics: per-step device times of every rank
+        with open(f"{os.environ['OSCEN_BENCH_DUMP']}.rank{rank}.json", "w") as f:
+            json.dump({"step_ms": step_ms, "kern_ms": kern_ms, "wall_s": t_wall}, f)
     st1 = eng.stats()
     dev_ms = max_over_ranks(sum(step_ms))
     work = args.steps * n * world * FRAMES

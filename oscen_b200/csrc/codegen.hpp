@@ -309,6 +309,10 @@ struct Emitter {
                 case O::Abs: e = "fabsf(" + x + ")"; break;
                 case O::Clamp: e = "clampf(" + x + ", " + pv + ", " + q + ")"; break;
                 case O::MinV: e = "fminf(" + x + ", " + pv + ")"; break;
+                case O::Sqrt: e = "sqrtf(" + x + ")"; break;
+                case O::Sin: e = "om_sinf(" + x + ")"; break;
+                case O::Cos: e = "om_cosf(" + x + ")"; break;
+                case O::Exp: e = "om_expf(" + x + ")"; break;
                 default: e = "fmaxf(" + x + ", " + pv + ")"; break;
                 }
                 line(ind, o + e + ";" + cm);

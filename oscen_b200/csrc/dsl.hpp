@@ -114,7 +114,12 @@ inline bool lex(const char *src, std::vector<Tok> &out, Error &err) {
             t.kind = Tok::Punct;
             if ((p[0] == '-' && p[1] == '>') || (p[0] == ':' && p[1] == ':') || (p[0] == '.' && p[1] == '.')) { t.s.assign(p, 2); adv(2); }
             else if (strchr("{}[]();:,=-+*/.<>!", *p)) { t.s.assign(p, 1); adv(1); }
-            else { err.at(t, std::string("unexpected character `") + *p + "`"); return false; }
+            else {
+                char shown[8];
+                if ((unsigned char)*p >= 0x20 && (unsigned char)*p < 0x7f) snprintf(shown, sizeof shown, "%c", *p);
+                else snprintf(shown, sizeof shown, "\\x%02x", (unsigned)(unsigned char)*p);      /* keep the diagnostic valid UTF-8 */
+                err.at(t, std::string("unexpected character `") + shown + "`"); return false;
+            }
         }
         out.push_back(t);
     }
@@ -749,7 +754,8 @@ private:
             Operand x; bool xe;
             if (!source(*e.a, x, xe)) return false;
             if (xe) { err.at(e.at, "event endpoints cannot take part in arithmetic"); return false; }
-            struct { const char *m; O op; size_t n_args; } ms[] = {{"tanh", O::Tanh, 0}, {"abs", O::Abs, 0}, {"clamp", O::Clamp, 2}, {"min", O::MinV, 1}, {"max", O::MaxV, 1}};
+            struct { const char *m; O op; size_t n_args; } ms[] = {{"tanh", O::Tanh, 0}, {"abs", O::Abs, 0}, {"clamp", O::Clamp, 2}, {"min", O::MinV, 1}, {"max", O::MaxV, 1},
+                                                                   {"sqrt", O::Sqrt, 0}, {"sin", O::Sin, 0}, {"cos", O::Cos, 0}, {"exp", O::Exp, 0}};
             for (auto &m : ms) if (e.name == m.m) {
                 if (e.args.size() != m.n_args) { err.at(e.at, "f32::" + e.name + " takes " + std::to_string(m.n_args) + " literal argument(s)"); return false; }
                 plan::Node n = blank(text_of(e), plan::NodeType::Expr, m.op);
@@ -758,7 +764,7 @@ private:
                 for (size_t i = 0; i < e.args.size(); ++i) n.cst[i] = e.args[i];
                 out = stream_of(add_synth(n)); return true;
             }
-            err.at(e.at, "method `." + e.name + "()` is not supported in a connection source (tanh, abs, clamp, min, max are)"); return false;
+            err.at(e.at, "method `." + e.name + "()` is not supported in a connection source (tanh, abs, clamp, min, max, sqrt, sin, cos, exp are)"); return false;
         }
         default:
             err.at(e.at, "free function `" + e.name + "` in a connection source names Rust code: not supported by the node plan"); return false;

@@ -444,6 +444,10 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
                     case plan::ExprOp::Abs: launch_ew<EW_ABS>(e, a, vec); break;
                     case plan::ExprOp::Clamp: launch_ew<EW_CLAMP>(e, a, vec); break;
                     case plan::ExprOp::MinV: launch_ew<EW_MINV>(e, a, vec); break;
+                    case plan::ExprOp::Sqrt: launch_ew<EW_SQRT>(e, a, vec); break;
+                    case plan::ExprOp::Sin: launch_ew<EW_SIN>(e, a, vec); break;
+                    case plan::ExprOp::Cos: launch_ew<EW_COS>(e, a, vec); break;
+                    case plan::ExprOp::Exp: launch_ew<EW_EXP>(e, a, vec); break;
                     default: launch_ew<EW_MAXV>(e, a, vec); break;
                     }
                     break;

@@ -264,6 +264,8 @@ enum : int {
     EW_CLAMP = 15,      /* f32::clamp(p, q) */
     EW_MINV = 16,       /* f32::min(p): minNum */
     EW_MAXV = 17,       /* f32::max(p): maxNum */
+    EW_SQRT = 18,       /* f32::sqrt (IEEE) */
+    EW_SIN = 19, EW_COS = 20, EW_EXP = 21,   /* libm sinf / cosf / expf (om_math.h) */
 };
 template <int OP>
 OSC_D void ew_apply(float x, float y, float p, float q, float &o0, float &o1) {
@@ -285,6 +287,10 @@ OSC_D void ew_apply(float x, float y, float p, float q, float &o0, float &o1) {
     else if (OP == EW_CLAMP) o0 = clampf(x, p, q);
     else if (OP == EW_MINV) o0 = fminf(x, p);
     else if (OP == EW_MAXV) o0 = fmaxf(x, p);
+    else if (OP == EW_SQRT) o0 = sqrtf(x);
+    else if (OP == EW_SIN) o0 = om_sinf(x);
+    else if (OP == EW_COS) o0 = om_cosf(x);
+    else if (OP == EW_EXP) o0 = om_expf(x);
     else { const float mix = clampf(p, 0.0f, 1.0f); o0 = x * (1.0f - mix); o1 = x * mix; }
 }
 template <int OP> OSC_HD constexpr bool ew_two_inputs() { return OP == EW_MIXER || OP == EW_MUL || OP == EW_SUB || OP == EW_DIV; }

@@ -59,6 +59,7 @@ enum class ExprOp : uint8_t {
     SubVS, DivVS,                             /* value (op) stream  */
     Value,                                    /* a value (graph input / literal) read as a stream */
     Tanh, Abs, Clamp, MinV, MaxV,             /* f32 methods: x.tanh(), x.abs(), x.clamp(p, q), x.min(p), x.max(p) */
+    Sqrt, Sin, Cos, Exp,                      /* x.sqrt() (IEEE), x.sin() x.cos() x.exp() (libm sinf / cosf / expf, restated in om_math.h) */
 };
 
 constexpr int kMaxStreamIn = 3;
@@ -265,7 +266,7 @@ inline void assign_state_layout(Graph &g, float sample_rate) {
 
 inline const char *op_name(ExprOp o) {
     static const char *const names[] = {"", "a + b", "a - b", "a * b", "a / b", "a + v", "a - v", "a * v", "a / v", "v - a", "v / a",
-                                        "value", "tanh", "abs", "clamp", "min", "max"};
+                                        "value", "tanh", "abs", "clamp", "min", "max", "sqrt", "sin", "cos", "exp"};
     return names[(int)o];
 }
 

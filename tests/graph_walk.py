@@ -16,6 +16,16 @@ _libm.tanhf.restype = C.c_float
 _libm.tanhf.argtypes = [C.c_float]
 
 
+for _fn in ("sinf", "cosf", "expf", "sqrtf"):
+    getattr(_libm, _fn).restype = C.c_float
+    getattr(_libm, _fn).argtypes = [C.c_float]
+
+
+def libm32(name, x):
+    """Rust f32::sin / cos / exp / sqrt -> libm sinf / cosf / expf / sqrtf"""
+    return f32(getattr(_libm, name)(float(x)))
+
+
 def tanh32(x):
     return f32(_libm.tanhf(float(x)))          # Rust f32::tanh -> libm tanhf
 

@@ -171,7 +171,7 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
     ("output stream out; node o = PolyBlepOscillator::pulse(2000.0, 1.0); connection o.output -> out;", "unknown constructor `PolyBlepOscillator::pulse`"),
     (ONE_OSC + "node o = Gain::new(1.0); connection o.output -> out;", "duplicate name `o`"),
     (ONE_OSC + "connection half(o.output) -> out;", "free function `half`"),
-    (ONE_OSC + "connection o.output.sqrt() -> out;", "method `.sqrt()` is not supported"),
+    (ONE_OSC + "connection o.output.powf(2.0) -> out;", "method `.powf()` is not supported"),
     ("node o = PolyBlepOscillator::saw(2000.0, 0.6);", "declares no stream output"),
     (ONE_OSC, "nothing is connected to the output"),
     ("output stream out; output stream out2; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "one stream output per graph"),
@@ -223,7 +223,7 @@ def test_generated_kernel_source_compiles_for_sm_100a(file):
     """NVRTC needs no GPU: every reference graph's generated kernel must compile for sm_100a here"""
     g = abi.Graph(text(file))
     src = g.codegen()
-    assert 'extern "C" __global__ void __launch_bounds__(kCta) oscen_b200_generated_kernel' in src
+    assert 'extern "C" __global__ void __launch_bounds__(kCta, 8) oscen_b200_generated_kernel' in src
     assert '#include "state_io.cuh"' in src and "tile_flush_mono" in src
     assert g.jit_check() > 10000           # cubin bytes
 
@@ -415,3 +415,76 @@ def test_node_plan_refuses_generated_only_node_types():
     with pytest.raises(abi.EngineError) as ei:
         abi.Engine.from_graph(g, 64, plan=abi.PLAN_NODES)
     assert "runs in generated kernels only" in str(ei.value)
+
+
+# ------------------------------------------------------------------ the front end under sanitizers + fuzzing
+@pytest.fixture(scope="module")
+def graphc(tmp_path_factory):
+    """oscen_b200/tools/graphc.cpp (the front end + code generator as a CLI) built with ASan + UBSan"""
+    import subprocess
+    exe = str(tmp_path_factory.mktemp("graphc") / "graphc")
+    root = os.path.dirname(GRAPHS[:-len("/graphs")])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-o", exe, os.path.join(root, "oscen_b200", "tools", "graphc.cpp")])
+    return exe
+
+
+def _run(exe, args, text=None):
+    import subprocess
+    return subprocess.run([exe] + args, input=text, capture_output=True, text=True, timeout=60)
+
+
+def test_graphc_cli_matches_the_library_and_is_sanitizer_clean(graphc):
+    for files in (["fm_voice.graph"], ["synth.graph"], ["twin_peaks.graph"], ["sat_4x.graph"], ["fm_voice.graph", "fm_graph.graph"]):
+        paths = [os.path.join(GRAPHS, f) for f in files]
+        r = _run(graphc, ["--plan"] + paths)
+        assert r.returncode == 0 and r.stderr == "", r.stderr
+        lib = abi.Graph("".join(text(f) + "\n" for f in files))
+        assert r.stdout == lib.describe()
+        c = _run(graphc, ["--cuda"] + paths)
+        assert c.returncode == 0 and c.stderr == "" and c.stdout == lib.codegen()
+    bad = _run(graphc, ["--check", "-"], "output stream out; node x = Foo::new(); connection x.output -> out;")
+    assert bad.returncode == 1 and bad.stderr.startswith("1:25: unknown node type `Foo`")
+    assert _run(graphc, []).returncode == 2
+
+
+def test_front_end_survives_mutated_graphs(graphc):
+    """token-level fuzzing of every test graph (delete / duplicate / swap / replace tokens, truncate): the front end must
+    answer with a plan or a `line:col:` diagnostic — never crash, hang, or trip ASan / UBSan"""
+    import random
+    import re as _re
+    rng = random.Random(20261017)
+    corpus = [text(f) for f in ("fm_voice.graph", "synth_adsr.graph", "twin_peaks.graph", "sat_4x.graph")]
+    corpus.append(text("fm_voice.graph") + text("fm_graph.graph"))
+    corpus.append(FEEDBACK)
+    junk = ["->", "[", "]", "{", "}", "(", ")", ";", ":", "::", "..", ",", "=", "*", "/", "+", "-", ".", "<", ">", "!", "graph", "input", "output",
+            "node", "nodes", "connection", "connections", "value", "stream", "event", "name", "ramp", "0", "8", "1e39", "-0.0", "4294967296",
+            "99999999999999999999", "x", "gate", "Delay::new(1.0, 0.0)", "[sinc]", "[x]", "\"s", "/*", "//", "\x00", "é"]
+    n_ok = n_err = 0
+    for it in range(400):
+        src = rng.choice(corpus)
+        toks = _re.findall(r"\s+|[A-Za-z_][A-Za-z_0-9]*|[0-9][0-9_.eE]*|->|::|\.\.|.", src)
+        for _ in range(rng.randint(1, 6)):
+            k = rng.randrange(len(toks))
+            op = rng.random()
+            if op < 0.3:
+                del toks[k]
+            elif op < 0.5:
+                toks.insert(k, toks[k])
+            elif op < 0.7:
+                j = rng.randrange(len(toks)); toks[k], toks[j] = toks[j], toks[k]
+            elif op < 0.95:
+                toks[k] = rng.choice(junk)
+            else:
+                toks = toks[:k]
+            if not toks:
+                toks = [";"]
+        mutated = "".join(toks).replace("\x00", "")
+        r = _run(graphc, ["--cuda", "-"], mutated)
+        assert r.returncode in (0, 1), (r.returncode, r.stderr[-2000:], mutated[:400])
+        if r.returncode == 1:
+            assert _re.match(r"^\d+:\d+: ", r.stderr), r.stderr[:300]
+            n_err += 1
+        else:
+            n_ok += 1
+    assert n_err > 100 and n_ok > 10, (n_ok, n_err)

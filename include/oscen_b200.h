@@ -235,6 +235,11 @@ int  oscen_b200_plan_describe(uint32_t graph_kind, char *dst, size_t cap);
 typedef struct oscen_b200_graph oscen_b200_graph;
 /* err (optional) receives "line:col: message" on failure */
 int  oscen_b200_graph_compile(const char *dsl_text, oscen_b200_graph **out, char *err, size_t err_cap);
+/* the same, compiling the graph called `graph_name` instead of the last one of the text (NULL / "" = the last).
+   `oversample_variants! { base_name: X; factors: [1, 4]; body: { ... {FACTOR} ... } }` expands to the graphs
+   X_1x, X_4x, ... (oscen-macros/src/oversample_variants_macro.rs:94-139); graphs used as nodes of the chosen
+   graph (`voice = SimpleVoice;`) are inlined. */
+int  oscen_b200_graph_compile_named(const char *dsl_text, const char *graph_name, oscen_b200_graph **out, char *err, size_t err_cap);
 void oscen_b200_graph_free(oscen_b200_graph *g);
 /* text form: inputs with defaults / ranges / ramps, stream + event input names, output, state words per
    voice, then the launch plan "k: NodeType [node, node]".  Returns the number of launches. */

@@ -37,7 +37,7 @@ SYMBOLS = [
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
     "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
-    "oscen_b200_graph_compile", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
+    "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
     "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
 ]
@@ -119,6 +119,7 @@ def load():
     L.oscen_b200_comm_p2p_import.argtypes = [vp, C.c_int, C.c_int, vp]
     L.oscen_b200_comm_p2p_close.argtypes = [vp]
     L.oscen_b200_graph_compile.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.oscen_b200_graph_compile_named.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_free.argtypes = [vp]
     L.oscen_b200_graph_free.restype = None
     L.oscen_b200_graph_describe.argtypes = [vp, C.c_char_p, C.c_size_t]
@@ -147,11 +148,12 @@ class GraphCompileError(ValueError):
 class Graph:
     """A `graph!` description compiled to a node plan (oscen_b200_graph_compile).  Needs no GPU."""
 
-    def __init__(self, dsl_text):
+    def __init__(self, dsl_text, name=None):
+        """compiles the LAST graph of the text, or the one called `name`"""
         self.L = load()
         h = C.c_void_p()
         err = C.create_string_buffer(1024)
-        rc = self.L.oscen_b200_graph_compile(dsl_text.encode(), C.byref(h), err, len(err))
+        rc = self.L.oscen_b200_graph_compile_named(dsl_text.encode(), name.encode() if name else None, C.byref(h), err, len(err))
         if rc != 0:
             raise GraphCompileError(err.value.decode())
         self.h = h

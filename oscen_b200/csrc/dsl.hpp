@@ -127,6 +127,66 @@ inline bool lex(const char *src, std::vector<Tok> &out, Error &err) {
     return true;
 }
 
+/* ---------------------------------------------------------- oversample_variants! -- */
+/* `oversample_variants! { base_name: X; factors: [1, 4]; body: { ... {FACTOR} ... } }` stamps out one graph per
+   factor, named X_1x, X_4x, ..., with every `{FACTOR}` replaced by the factor
+   (oscen-macros/src/oversample_variants_macro.rs:94-139).  Done on the token stream, before parsing. */
+inline bool expand_oversample_variants(std::vector<Tok> &toks, Error &err) {
+    auto is = [&](size_t i, Tok::Kind k, const char *s) { return i < toks.size() && toks[i].kind == k && toks[i].s == s; };
+    std::vector<Tok> out;
+    size_t i = 0;
+    while (i < toks.size()) {
+        if (!(is(i, Tok::Ident, "oversample_variants") && is(i + 1, Tok::Punct, "!") && is(i + 2, Tok::Punct, "{"))) { out.push_back(toks[i++]); continue; }
+        const Tok at = toks[i];
+        size_t j = i + 3;
+        std::string base; std::vector<int> factors; size_t body_lo = 0, body_hi = 0;
+        while (j < toks.size() && !is(j, Tok::Punct, "}")) {
+            if (toks[j].kind != Tok::Ident || !is(j + 1, Tok::Punct, ":")) { err.at(toks[j], "oversample_variants!: expected `base_name:`, `factors:` or `body:`"); return false; }
+            const std::string key = toks[j].s; j += 2;
+            if (key == "base_name") {
+                if (j >= toks.size() || toks[j].kind != Tok::Ident) { err.at(toks[j < toks.size() ? j : toks.size() - 1], "oversample_variants!: `base_name:` expects an identifier"); return false; }
+                base = toks[j++].s;
+            } else if (key == "factors") {
+                if (!is(j, Tok::Punct, "[")) { err.at(toks[j], "oversample_variants!: `factors:` expects `[1, 2, ...]`"); return false; }
+                for (++j; j < toks.size() && !is(j, Tok::Punct, "]"); ++j) {
+                    if (is(j, Tok::Punct, ",")) continue;
+                    if (toks[j].kind != Tok::Num || !toks[j].is_int) { err.at(toks[j], "oversample_variants!: factors are integer literals"); return false; }
+                    factors.push_back((int)strtol(toks[j].s.c_str(), nullptr, 10));
+                }
+                ++j;
+            } else if (key == "body") {
+                if (!is(j, Tok::Punct, "{")) { err.at(toks[j], "oversample_variants!: `body:` expects `{ ... }`"); return false; }
+                int depth = 0; body_lo = j + 1;
+                for (; j < toks.size(); ++j) {
+                    if (is(j, Tok::Punct, "{")) ++depth;
+                    else if (is(j, Tok::Punct, "}") && --depth == 0) break;
+                }
+                if (j >= toks.size()) { err.at(at, "oversample_variants!: unterminated body"); return false; }
+                body_hi = j++;
+            } else { err.at(toks[j - 2], "oversample_variants!: unknown key `" + key + "`"); return false; }
+            if (is(j, Tok::Punct, ";") || is(j, Tok::Punct, ",")) ++j;
+        }
+        if (j >= toks.size()) { err.at(at, "oversample_variants!: missing `}`"); return false; }
+        if (base.empty() || factors.empty() || !body_hi) { err.at(at, "oversample_variants! needs base_name, factors and body"); return false; }
+        for (int f : factors) {
+            auto push = [&](Tok::Kind k, const std::string &s) { Tok t = at; t.kind = k; t.s = s; out.push_back(t); };
+            push(Tok::Ident, "graph"); push(Tok::Punct, "!"); push(Tok::Punct, "{");
+            push(Tok::Ident, "name"); push(Tok::Punct, ":"); push(Tok::Ident, base + "_" + std::to_string(f) + "x"); push(Tok::Punct, ";");
+            for (size_t k = body_lo; k < body_hi; ++k) {
+                if (is(k, Tok::Punct, "{") && is(k + 1, Tok::Ident, "FACTOR") && is(k + 2, Tok::Punct, "}")) {
+                    Tok t = toks[k]; t.kind = Tok::Num; t.s = std::to_string(f); t.num = (float)f; t.is_int = true; out.push_back(t);
+                    k += 2;
+                } else out.push_back(toks[k]);
+            }
+            push(Tok::Punct, "}");
+        }
+        i = j + 1;
+        if (is(i, Tok::Punct, ";")) ++i;
+    }
+    toks.swap(out);
+    return true;
+}
+
 /* -------------------------------------------------------------------------------- AST -- */
 enum class Kind { Stream, Value, Event, Asset };
 inline const char *kind_name(Kind k) { return k == Kind::Stream ? "Stream" : k == Kind::Value ? "Value" : k == Kind::Event ? "Event" : "Asset"; }
@@ -144,7 +204,7 @@ using ExprP = std::unique_ptr<Expr>;
 
 struct InputDecl { Kind kind; std::string name; bool has_def = false; float def = 0.0f; plan::ValueInput spec; Tok at; };
 struct OutputDecl { Kind kind; std::string name; Tok at; };
-struct NodeDecl { std::string name, type, ctor; std::vector<float> args; bool args_ok = true; int array = 0; int rate = 0; Tok at; };
+struct NodeDecl { std::string name, type, ctor; std::vector<float> args; bool args_ok = true; bool bare = false; int array = 0; int rate = 0; Tok at; };
 struct Conn { std::string policy; ExprP src, dst; int via = 0; /* 0 none, 1 samples, 2 node */ float via_samples = 0.0f; std::string via_node; Tok at; };
 struct Ast {
     std::string name;
@@ -339,6 +399,9 @@ private:
             if (!ident(seg, "a path segment")) return;
             path.push_back(seg);
         }
+        if (path.size() == 1 && !is_punct("(")) {             /* `voice = SimpleVoice;`: a graph used as a node */
+            d.type = path[0]; d.ctor = "new"; d.bare = true;
+        } else {
         if (path.size() < 2) { err.at(d.at, "node constructor must be `Type::method(...)`"); return; }
         d.ctor = path.back(); d.type = path[path.size() - 2];
         if (!expect("(")) return;
@@ -351,6 +414,7 @@ private:
             if (!accept(",")) break;
         }
         if (!expect(")")) return;
+        }
         if (array) {
             if (!expect(";")) return;
             if (cur().kind != Tok::Num || !cur().is_int) { err.at(cur(), "array size must be an integer literal"); return; }
@@ -946,6 +1010,161 @@ private:
     }
 };
 
+/* ------------------------------------------------------------------ nested graphs -- */
+/* A graph used as a scalar node of another graph (`voice1 = SimpleVoice;`, oscen-lib/tests/nested_graph_test.rs)
+ * is just another node whose process() the parent calls: the reference inlines the child's generated walk.
+ * Here the child is inlined at the AST level: its nodes join the parent as `<instance>.<node>`, its inputs are
+ * replaced by what the parent connects to them (an unconnected input keeps its declared default), and a parent
+ * source `<instance>.<output>` becomes the child's expression for that output (several -> their sum in statement
+ * order, like any fan-in).  Values stay values, streams stay streams: the kind rules are checked afterwards on
+ * the flattened graph exactly as for a hand-flattened one. */
+inline ExprP clone_expr(const Expr &e) {
+    ExprP c(new Expr);
+    c->k = e.k; c->name = e.name; c->op = e.op; c->lit = e.lit; c->args = e.args; c->at = e.at;
+    if (e.a) c->a = clone_expr(*e.a);
+    if (e.b) c->b = clone_expr(*e.b);
+    return c;
+}
+inline const Ast *find_graph(const std::vector<Ast> &all, const std::string &name) {
+    for (const Ast &a : all) if (a.name == name) return &a;
+    return nullptr;
+}
+inline ExprP sum_exprs(std::vector<ExprP> &terms) {
+    ExprP acc = std::move(terms[0]);
+    for (size_t i = 1; i < terms.size(); ++i) {
+        ExprP b(new Expr); b->k = Expr::Binary; b->op = '+'; b->at = acc->at;
+        b->a = std::move(acc); b->b = std::move(terms[i]); acc = std::move(b);
+    }
+    return acc;
+}
+struct Inliner {
+    const std::vector<Ast> &all;
+    Error &err;
+    int depth = 0;
+
+    /* child source expression -> parent terms: `input` -> the parent's expression for it, `node.x` -> `inst.node.x` */
+    ExprP rewrite_child_source(const Expr &e, const std::string &inst, const Ast &child,
+                               std::map<std::string, std::vector<ExprP>> &bound, bool &dropped) {
+        if (e.k == Expr::Ident) {
+            for (const InputDecl &in : child.inputs) if (in.name == e.name) {
+                auto it = bound.find(e.name);
+                if (it == bound.end() || it->second.empty()) {
+                    if (in.kind == Kind::Event) { dropped = true; return nullptr; }       /* an unconnected event input never fires */
+                    ExprP l(new Expr); l->k = Expr::Literal; l->lit = in.kind == Kind::Value ? in.def : 0.0f; l->at = e.at;
+                    return l;
+                }
+                std::vector<ExprP> terms;
+                if (in.kind == Kind::Stream) for (const ExprP &t : it->second) terms.push_back(clone_expr(*t));   /* fan-in sums */
+                else terms.push_back(clone_expr(*it->second.back()));                                                /* last write wins */
+                return sum_exprs(terms);
+            }
+            return clone_expr(e);
+        }
+        ExprP c(new Expr);
+        c->k = e.k; c->name = e.name; c->op = e.op; c->lit = e.lit; c->args = e.args; c->at = e.at;
+        if (e.k == Expr::Field && e.a && e.a->k == Expr::Ident) {                 /* node.endpoint */
+            c->a.reset(new Expr); c->a->k = Expr::Ident; c->a->name = inst + "." + e.a->name; c->a->at = e.a->at;
+            return c;
+        }
+        if (e.a) { c->a = rewrite_child_source(*e.a, inst, child, bound, dropped); if (!c->a) return nullptr; }
+        if (e.b) { c->b = rewrite_child_source(*e.b, inst, child, bound, dropped); if (!c->b) return nullptr; }
+        return c;
+    }
+    /* parent source: replace `inst.output` by the child's expression(s) for that output */
+    ExprP rewrite_parent_source(const Expr &e, const std::string &inst, std::map<std::string, std::vector<ExprP>> &outs, const Ast &child) {
+        if (e.k == Expr::Field && e.a && e.a->k == Expr::Ident && e.a->name == inst) {
+            auto it = outs.find(e.name);
+            if (it == outs.end() || it->second.empty()) {
+                bool declared = false;
+                for (const OutputDecl &o : child.outputs) declared |= o.name == e.name;
+                err.at(e.at, declared ? "output `" + e.name + "` of `" + child.name + "` has nothing connected to it"
+                                      : "graph `" + child.name + "` has no output `" + e.name + "`");
+                return nullptr;
+            }
+            std::vector<ExprP> terms;
+            for (const ExprP &t : it->second) terms.push_back(clone_expr(*t));
+            return sum_exprs(terms);
+        }
+        ExprP c(new Expr);
+        c->k = e.k; c->name = e.name; c->op = e.op; c->lit = e.lit; c->args = e.args; c->at = e.at;
+        if (e.a) { c->a = rewrite_parent_source(*e.a, inst, outs, child); if (!c->a) return nullptr; }
+        if (e.b) { c->b = rewrite_parent_source(*e.b, inst, outs, child); if (!c->b) return nullptr; }
+        return c;
+    }
+
+    /* returns a copy of `g` with every scalar nested-graph node inlined (recursively) */
+    bool flatten(const Ast &g, Ast &out) {
+        if (++depth > 16) { Tok t; err.at(t, "nested graphs: recursion deeper than 16 levels (a graph that contains itself?)"); return false; }
+        out.name = g.name;
+        for (const InputDecl &d : g.inputs) out.inputs.push_back(d);
+        for (const OutputDecl &d : g.outputs) out.outputs.push_back(d);
+        std::vector<const NodeDecl *> nested;
+        for (const NodeDecl &d : g.nodes) {
+            const Ast *child = d.array ? nullptr : find_graph(all, d.type);
+            if (child && child != &g) nested.push_back(&d); else out.nodes.push_back(d);
+        }
+        std::vector<Conn> conns;
+        for (const Conn &c : g.conns) {
+            Conn k; k.policy = c.policy; k.via = c.via; k.via_samples = c.via_samples; k.via_node = c.via_node; k.at = c.at;
+            k.src = clone_expr(*c.src); k.dst = clone_expr(*c.dst);
+            conns.push_back(std::move(k));
+        }
+        for (const NodeDecl *nd : nested) {
+            if (nd->rate) { err.at(nd->at, "a rate on a nested graph instance is not supported (put `* N` on the nodes inside it)"); return false; }
+            if (nd->ctor != "new" || !nd->args.empty()) { err.at(nd->at, "a graph is instantiated with `" + nd->type + "` or `" + nd->type + "::new()`"); return false; }
+            Ast child;
+            { Inliner sub{all, err, depth}; if (!sub.flatten(*find_graph(all, nd->type), child)) return false; }
+            const std::string &inst = nd->name;
+            /* what the parent connects INTO the instance, per child input (statement order) */
+            std::map<std::string, std::vector<ExprP>> bound;
+            std::vector<Conn> rest;
+            for (Conn &c : conns) {
+                const Expr &d = *c.dst;
+                if (d.k == Expr::Field && d.a->k == Expr::Ident && d.a->name == inst) {
+                    bool is_input = false;
+                    for (const InputDecl &in : child.inputs) is_input |= in.name == d.name;
+                    if (!is_input) { err.at(d.at, "graph `" + child.name + "` has no input `" + d.name + "`"); return false; }
+                    if (c.via) { err.at(c.at, "a `-> [..] ->` edge into a nested graph instance is not supported"); return false; }
+                    bound[d.name].push_back(std::move(c.src));
+                } else rest.push_back(std::move(c));
+            }
+            conns.swap(rest);
+            /* the child's nodes and connections join the parent under `inst.` */
+            for (NodeDecl cn : child.nodes) { cn.name = inst + "." + cn.name; out.nodes.push_back(cn); }
+            std::map<std::string, std::vector<ExprP>> outs;
+            for (const Conn &cc : child.conns) {
+                bool dropped = false;
+                ExprP src = rewrite_child_source(*cc.src, inst, child, bound, dropped);
+                if (dropped) continue;
+                if (!src) return false;
+                if (cc.dst->k == Expr::Ident) {                                       /* -> child output */
+                    bool is_out = false;
+                    for (const OutputDecl &o : child.outputs) is_out |= o.name == cc.dst->name;
+                    if (!is_out) { err.at(cc.dst->at, "cannot resolve the destination of this connection (unknown node or endpoint name `" + cc.dst->name + "`?)"); return false; }
+                    if (cc.via) { err.at(cc.at, "a `-> [..] ->` edge must end at a node input"); return false; }
+                    outs[cc.dst->name].push_back(std::move(src));
+                    continue;
+                }
+                Conn k; k.policy = cc.policy; k.via = cc.via; k.via_samples = cc.via_samples; k.at = cc.at;
+                k.via_node = cc.via == 2 ? inst + "." + cc.via_node : cc.via_node;
+                k.src = std::move(src);
+                k.dst = clone_expr(*cc.dst);
+                if (k.dst->k == Expr::Field && k.dst->a->k == Expr::Ident) k.dst->a->name = inst + "." + k.dst->a->name;
+                conns.push_back(std::move(k));
+            }
+            /* parent sources that read the instance's outputs */
+            for (Conn &c : conns) {
+                ExprP src = rewrite_parent_source(*c.src, inst, outs, child);
+                if (!src) return false;
+                c.src = std::move(src);
+            }
+        }
+        out.conns = std::move(conns);
+        --depth;
+        return true;
+    }
+};
+
 /* ------------------------------------------------------------- polyphonic wrapper -- */
 /* An outer graph of the shape the reference's polyphonic examples have (examples/fm-synth/src/lib.rs:22-131):
  *     nodes { midi_parser = MidiParser::new(); voice_allocator = VoiceAllocator::<N>::new();
@@ -956,10 +1175,6 @@ private:
  * voices_per_instance, broadcast edges `outer_value -> voices.<input>` become names for the voice's inputs
  * (with the OUTER declaration's default and ramp), and the MIDI chain selects the engine's MIDI front
  * (oscen_b200_push_midi / _push_midi_batch: midi.rs:69-224, voice_allocator.rs:57-136). */
-inline const Ast *find_graph(const std::vector<Ast> &all, const std::string &name) {
-    for (const Ast &a : all) if (a.name == name) return &a;
-    return nullptr;
-}
 inline bool is_polyphonic(const Ast &top) {
     for (const NodeDecl &d : top.nodes) if (d.array > 0) return true;
     return false;
@@ -983,7 +1198,10 @@ inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::
     if ((uint32_t)voices->array > 64u || (voices->array & (voices->array - 1)) != 0) { err.at(voices->at, "voice array size must be a power of two <= 64 (the engine folds an instance inside one 64-thread CTA)"); return false; }
     if (handlers && handlers->array != voices->array) { err.at(handlers->at, "`" + handlers->name + "` and `" + voices->name + "` must have the same array size"); return false; }
     {
-        Lowering l(voice, g, err);
+        Ast flat_voice;                                   /* the voice graph may itself use nested graphs */
+        Inliner inl{all, err};
+        if (!inl.flatten(voice, flat_voice)) return false;
+        Lowering l(flat_voice, g, err);
         if (!l.run()) return false;
     }
     g.vpi = (uint32_t)voices->array;
@@ -1070,25 +1288,34 @@ inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::
 
 /* text -> plan::Graph; on failure `error` holds "line:col: message".  With several `graph! { }` blocks the
    LAST one is the graph to run; earlier ones are the graphs it instantiates. */
-inline bool compile(const char *text, plan::Graph &g, std::string &error) {
+inline bool compile(const char *text, plan::Graph &g, std::string &error, const char *top_name = nullptr) {
     Error err;
     std::vector<Tok> toks;
     if (!text) { error = "0:0: null graph text"; return false; }
     if (!lex(text, toks, err)) { error = err.text(); return false; }
+    if (!expand_oversample_variants(toks, err)) { error = err.text(); return false; }
     std::vector<Ast> graphs;
     Parser p(toks, err);
     if (!p.parse(graphs)) { error = err.text(); return false; }
     if (graphs.empty()) { error = "1:1: no graph in the text"; return false; }
-    const Ast &top = graphs.back();
+    const Ast *chosen = &graphs.back();
+    if (top_name && *top_name) {
+        chosen = find_graph(graphs, top_name);
+        if (!chosen) {
+            std::string have;
+            for (const Ast &a : graphs) have += (have.empty() ? "" : ", ") + (a.name.empty() ? std::string("<anonymous>") : a.name);
+            error = "1:1: no graph named `" + std::string(top_name) + "` in the text (it holds: " + have + ")"; return false;
+        }
+    }
+    const Ast &top = *chosen;
     if (is_polyphonic(top)) {
         if (!lower_polyphonic(top, graphs, g, err)) { error = err.text(); return false; }
         return true;
     }
-    for (const NodeDecl &d : top.nodes) if (find_graph(graphs, d.type)) {
-        err.at(d.at, "nested graph `" + d.type + "` as a scalar node is not supported (the polyphonic array form `[" + d.type + "::new(); N]` is)");
-        error = err.text(); return false;
-    }
-    Lowering l(top, g, err);
+    Ast flat;
+    Inliner inl{graphs, err};
+    if (!inl.flatten(top, flat)) { error = err.text(); return false; }
+    Lowering l(flat, g, err);
     if (!l.run()) { error = err.text(); return false; }
     return true;
 }

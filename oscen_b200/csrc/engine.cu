@@ -658,12 +658,15 @@ int oscen_b200_create(const oscen_b200_config *cfg, oscen_b200_engine **out) { r
 
 /* ---- graph! DSL front end (dsl.hpp): text -> node plan; needs no GPU until create_from_graph */
 int oscen_b200_graph_compile(const char *text, oscen_b200_graph **out, char *err, size_t err_cap) {
+    return oscen_b200_graph_compile_named(text, nullptr, out, err, err_cap);
+}
+int oscen_b200_graph_compile_named(const char *text, const char *graph_name, oscen_b200_graph **out, char *err, size_t err_cap) {
     if (err && err_cap) err[0] = 0;
     if (!text || !out) return OSCEN_B200_E_ARG;
     *out = nullptr;
     oscen_b200_graph *g = new oscen_b200_graph();
     std::string msg;
-    bool ok = dsl::compile(text, g->g, msg);
+    bool ok = dsl::compile(text, g->g, msg, graph_name);
     if (ok && !plan::compile(g->g, g->p, msg)) { ok = false; msg = "0:0: " + msg; }
     if (!ok) {
         if (err && err_cap) { strncpy(err, msg.c_str(), err_cap - 1); err[err_cap - 1] = 0; }

@@ -350,12 +350,6 @@ def test_polyphonic_graph_errors(mutation, frag):
     assert frag in str(ei.value), str(ei.value)
 
 
-def test_nested_scalar_graph_is_reported():
-    with pytest.raises(abi.GraphCompileError) as ei:
-        abi.Graph(text("fm_voice.graph") + "graph! { name: Outer; output stream out; node v = FMVoice::new(); connection v.audio_out -> out; }")
-    assert "nested graph `FMVoice` as a scalar node is not supported" in str(ei.value)
-
-
 # ------------------------------------------------------------------ feedback edges and the rest of the node library
 FEEDBACK = """
     name: Echo;
@@ -488,3 +482,116 @@ def test_front_end_survives_mutated_graphs(graphc):
         else:
             n_ok += 1
     assert n_err > 100 and n_ok > 10, (n_ok, n_err)
+
+
+# ------------------------------------------------------------------ nested graphs (a graph used as a scalar node)
+NESTED = """
+graph! {
+    name: EventVoice;
+    input event gate;
+    input value freq = 440.0;
+    input stream fm;
+    output stream audio;
+    nodes {
+        osc = PolyBlepOscillator::sine(440.0, 0.5);
+        envelope = AdsrEnvelope::new(0.01, 0.1, 0.7, 0.3);
+    }
+    connections {
+        gate -> envelope.gate;
+        freq -> osc.frequency;
+        fm -> osc.frequency_mod;
+        osc.output * envelope.output -> audio;
+    }
+}
+graph! {
+    name: DualVoiceSynth;
+    input event gate;
+    input value detune = 1.5;
+    output stream out;
+    nodes {
+        lfo = PolyBlepOscillator::sine(3.0, 0.01);
+        voice1 = EventVoice;
+        voice2 = EventVoice::new();
+    }
+    connections {
+        gate -> voice1.gate;
+        gate -> voice2.gate;
+        220.0 -> voice1.freq;
+        lfo.output -> voice2.fm;
+        lfo.output * detune -> voice2.fm;
+        voice1.audio + voice2.audio * 0.5 -> out;
+    }
+}
+"""
+
+FLAT = """
+    name: DualVoiceSynth;
+    input event gate;
+    input value detune = 1.5;
+    output stream out;
+    nodes {
+        lfo = PolyBlepOscillator::sine(3.0, 0.01);
+        v1osc = PolyBlepOscillator::sine(440.0, 0.5);
+        v1env = AdsrEnvelope::new(0.01, 0.1, 0.7, 0.3);
+        v2osc = PolyBlepOscillator::sine(440.0, 0.5);
+        v2env = AdsrEnvelope::new(0.01, 0.1, 0.7, 0.3);
+    }
+    connections {
+        v1osc.output * v1env.output + v2osc.output * v2env.output * 0.5 -> out;      // the inliner keeps the parent's statements first
+        gate -> v1env.gate;
+        220.0 -> v1osc.frequency;
+        0.0 -> v1osc.frequency_mod;
+        gate -> v2env.gate;
+        440.0 -> v2osc.frequency;
+        lfo.output + lfo.output * detune -> v2osc.frequency_mod;
+    }
+"""
+
+
+def test_nested_graphs_are_inlined_like_a_hand_flattened_graph():
+    """oscen-lib/tests/nested_graph_test.rs: a graph used as a node (both `v = G;` and `v = G::new();`), with event,
+    value and stream inputs; unconnected inputs keep their declared defaults; two sources into a nested stream input sum"""
+    nested, flat = abi.Graph(NESTED), abi.Graph(FLAT)
+    norm = lambda s: s.replace("voice1.osc", "v1osc").replace("voice1.envelope", "v1env").replace("voice2.osc", "v2osc").replace("voice2.envelope", "v2env")
+    assert norm(nested.describe()) == flat.describe()
+    strip = lambda c: re.sub(r"/\*.*?\*/", "", c)                 # the generated kernels differ in comments (node names) only
+    assert strip(nested.codegen()) == strip(flat.codegen())
+    assert nested.jit_check() > 10000
+
+
+@pytest.mark.parametrize("mutation,frag", [
+    (("voice1.audio +", "voice1.sound +"), "graph `EventVoice` has no output `sound`"),
+    (("220.0 -> voice1.freq;", "220.0 -> voice1.pitch;"), "graph `EventVoice` has no input `pitch`"),
+    (("voice2 = EventVoice::new();", "voice2 = EventVoice::new() * 2;"), "a rate on a nested graph instance"),
+    (("voice2 = EventVoice::new();", "voice2 = EventVoice::with(1.0);"), "a graph is instantiated with"),
+    (("lfo.output -> voice2.fm;", "lfo.output -> voice2.freq;"), "source is Stream but destination expects Value"),
+])
+def test_nested_graph_errors(mutation, frag):
+    assert mutation[0] in NESTED
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(NESTED.replace(mutation[0], mutation[1]))
+    assert frag in str(ei.value), str(ei.value)
+
+
+def test_self_nesting_is_reported():
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph("graph! { name: A; output stream o; node b = B; connection b.o -> o; } graph! { name: B; output stream o; node a = A; connection a.o -> o; }")
+    assert "recursion deeper than 16 levels" in str(ei.value)
+
+
+def test_oversample_variants_macro_and_named_graph_selection():
+    src = text("sat_variants.graph")
+    g4 = abi.Graph(src)                                        # the last variant
+    assert "graph SatGraph_4x" in g4.describe() and "[sinc down x4]" in g4.describe()
+    g1 = abi.Graph(src, name="SatGraph_1x")
+    assert g1.launches() == ["0: PolyBlepOscillator::saw [osc]", "1: HardClip [clip]"]
+    assert g4.n_inputs == 0 and g4.jit_check() > 10000
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(src, name="SatGraph_2x")
+    assert "no graph named `SatGraph_2x`" in str(ei.value) and "SatGraph_1x, SatGraph_4x" in str(ei.value)
+    for broken, frag in ((src.replace("factors: [1, 4];", ""), "needs base_name, factors and body"),
+                         (src.replace("factors: [1, 4];", "factors: [1, 3];"), "rate factor must be in {1, 2, 4, 8}"),
+                         (src.replace("base_name: SatGraph;", "base: SatGraph;"), "unknown key `base`")):
+        with pytest.raises(abi.GraphCompileError) as ei:
+            abi.Graph(broken)
+        assert frag in str(ei.value), str(ei.value)

@@ -400,6 +400,7 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         a.out1 = plan::n_outputs(nd.type) > 1 ? S[p.first_stream[idx] + 1] : nullptr;
         for (int k = 0; k < plan::kMaxParams; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
         a.gate = nd.gate ? 1u : 0u; a.q = nd.cst[1];
+        if (nd.type == plan::NodeType::Delay) { a.gate = nd.ring_cap; a.q = nd.max_delay; }
         return a;
     };
     for (const plan::Launch &l : p.launches) {
@@ -416,6 +417,11 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         case plan::NodeType::PolyBlepSquare: polyblep_node_kernel<WAVE_SQUARE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::PolyBlepTriangle: polyblep_node_kernel<WAVE_TRIANGLE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::Lp18: lp18_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::OscSine: osc_node_kernel<OSC_SINE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::OscSquare: osc_node_kernel<OSC_SQUARE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::OscSaw: osc_node_kernel<OSC_SAW><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::IirLowpass: iirlp_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::Delay: delay_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         default:
             for (uint32_t k = 0; k < cnt; ++k) {                       /* stateless nodes: one stream kernel each */
                 const NodeArgs &a = a4.n[k];
@@ -543,8 +549,8 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         pg = custom->g; pp = custom->p;
         plan::assign_state_layout(pg, cfg->sample_rate);          /* Delay rings are sized for this engine's sample rate */
         if (cfg->plan == OSCEN_B200_PLAN_NODES)
-            for (const plan::Node &nd : pg.nodes) if (!plan::node_plan_has_kernel(nd.type) && nd.type != plan::NodeType::Up && nd.type != plan::NodeType::Down) {
-                g_create_error = std::string("PLAN_NODES: ") + plan::type_name(nd.type) + " (`" + nd.name + "`) runs in generated kernels only: set plan = OSCEN_B200_PLAN_FUSED";
+            for (const plan::Node &nd : pg.nodes) for (int k = 0; k < plan::kMaxStreamIn; ++k) if (nd.in[k].node >= 0 && nd.fb[k]) {
+                g_create_error = "PLAN_NODES: the feedback edge into `" + nd.name + "` needs the per-sample walk (node kernels render whole blocks): set plan = OSCEN_B200_PLAN_FUSED";
                 return OSCEN_B200_E_ARG;
             }
         if (cfg->plan == OSCEN_B200_PLAN_FUSED) {

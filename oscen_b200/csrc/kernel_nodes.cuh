@@ -242,6 +242,93 @@ __global__ void __launch_bounds__(kCta) lp18_node_kernel(const __grid_constant__
     lp18_store(s, a.state, a.state_base, n, v);
 }
 
+/* ---- naive Oscillator: in0 = frequency_mod (nullable: slot 2 stands in); pid = {frequency, amplitude, frequency_mod} */
+template <int WAVE>
+__global__ void __launch_bounds__(kCta) osc_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(3)
+    float phase = a.state[(size_t)a.state_base * n + v];
+    const bool fm_stream = a.in0 != nullptr;
+    float fm[kPF], fm_n[kPF];
+    OSC_LOAD1(fm, a.in0, 0u)
+    for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
+        OSC_LOAD1(fm_n, a.in0, f0 + kPF)
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) {
+            const uint32_t f = f0 + k;
+            if (f < frames) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+                __stcs(a.out0 + (size_t)f * n + v, osc_process<WAVE>(phase, prm.P[0], fm_stream ? fm[k] : prm.P[2], prm.P[1], a.sr));
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) fm[k] = fm_n[k];
+    }
+    a.state[(size_t)a.state_base * n + v] = phase;
+}
+
+/* ---- IirLowpass: in0 = input (nullable: slot 2 stands in); pid = {cutoff, q, input} */
+__global__ void __launch_bounds__(kCta) iirlp_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(3)
+    IirLpState s;
+    {
+        const float *st = a.state + (size_t)a.state_base * n + v;
+        s.b0 = st[0]; s.b1 = st[n]; s.b2 = st[2 * (size_t)n]; s.a1 = st[3 * (size_t)n]; s.a2 = st[4 * (size_t)n];
+        s.v1 = st[5 * (size_t)n]; s.v2 = st[6 * (size_t)n]; s.counter = __float_as_uint(st[7 * (size_t)n]);
+    }
+    const bool in_stream = a.in0 != nullptr;
+    float x[kPF], x_n[kPF];
+    OSC_LOAD1(x, a.in0, 0u)
+    for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
+        OSC_LOAD1(x_n, a.in0, f0 + kPF)
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) {
+            const uint32_t f = f0 + k;
+            if (f < frames) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+                __stcs(a.out0 + (size_t)f * n + v, iirlp_process(s, in_stream ? x[k] : prm.P[2], prm.P[0], prm.P[1], a.sr));
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kPF; ++k) x[k] = x_n[k];
+    }
+    {
+        float *st = a.state + (size_t)a.state_base * n + v;
+        st[0] = s.b0; st[n] = s.b1; st[2 * (size_t)n] = s.b2; st[3 * (size_t)n] = s.a1; st[4 * (size_t)n] = s.a2;
+        st[5 * (size_t)n] = s.v1; st[6 * (size_t)n] = s.v2; st[7 * (size_t)n] = __uint_as_float(s.counter);
+    }
+}
+
+/* ---- Delay (no feedback edge through it: a cycle needs the per-sample walk of a generated kernel):
+        in0 = input (nullable: slot 2 stands in); pid = {delay_samples, feedback, input};
+        ring capacity in NodeArgs.gate (a power of two), the reference capacity - 1 in NodeArgs.q */
+__global__ void __launch_bounds__(kCta) delay_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_NODE_PROLOGUE(3)
+    DelayState s;
+    s.write_pos = __float_as_uint(a.state[(size_t)(a.state_base + 0u) * n + v]);
+    s.counter = __float_as_uint(a.state[(size_t)(a.state_base + 1u) * n + v]);
+    s.output = a.state[(size_t)(a.state_base + 2u) * n + v];
+    float *ring = a.state + (size_t)(a.state_base + 3u) * n + v;
+    const uint32_t cap = a.gate;
+    const float max_delay = a.q;
+    const bool in_stream = a.in0 != nullptr, cd = a.pid[0] != kNoInput, cf = a.pid[1] != kNoInput;
+    for (uint32_t f = 0; f < frames; ++f) {
+        prm.ramps(a, ramp_mask, f);
+        if (ec.due(f)) ec.advance(prm.events(a, ec, f));
+        const float x = in_stream ? __ldcs(a.in0 + (size_t)f * n + v) : prm.P[2];
+        float y;
+        if (cd) y = cf ? delay_process<true, true>(s, ring, n, cap, max_delay, x, prm.P[0], prm.P[1])
+                       : delay_process<true, false>(s, ring, n, cap, max_delay, x, prm.P[0], prm.P[1]);
+        else y = cf ? delay_process<false, true>(s, ring, n, cap, max_delay, x, prm.P[0], prm.P[1])
+                    : delay_process<false, false>(s, ring, n, cap, max_delay, x, prm.P[0], prm.P[1]);
+        __stcs(a.out0 + (size_t)f * n + v, y);
+    }
+    a.state[(size_t)(a.state_base + 0u) * n + v] = __uint_as_float(s.write_pos);
+    a.state[(size_t)(a.state_base + 1u) * n + v] = __uint_as_float(s.counter);
+    a.state[(size_t)(a.state_base + 2u) * n + v] = s.output;
+}
+
 /* ---- stateless nodes */
 enum : int {
     EW_GAIN = 0,        /* Gain: in0 * (value | constant)        gain/mod.rs:30-35      */

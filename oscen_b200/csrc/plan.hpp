@@ -41,10 +41,11 @@ enum class NodeType : uint8_t {
     Crossfade,     /* Crossfade: two outputs */
     HardClip,      /* HardClip */
     Expr,          /* one operator of a compound source expression; `op` says which (ExprOp) */
-    IirLowpass,    /* IirLowpass (JUCE-style biquad)        stream: input; value: cutoff q                      (generated kernels only) */
-    OscSine, OscSquare, OscSaw,   /* the naive Oscillator         stream: frequency_mod; value: frequency amplitude   (generated kernels only) */
-    Delay,         /* Delay over a power-of-two ring        stream: input; value: delay_samples feedback        (generated kernels only);
-                      the one node type a feedback edge (`-> [N] ->`, `-> [name] ->`) may run through (AllowsFeedback) */
+    IirLowpass,    /* IirLowpass (JUCE-style biquad)        stream: input; value: cutoff q */
+    OscSine, OscSquare, OscSaw,   /* the naive Oscillator         stream: frequency_mod; value: frequency amplitude */
+    Delay,         /* Delay over a power-of-two ring        stream: input; value: delay_samples feedback;
+                      the one node type a feedback edge (`-> [N] ->`, `-> [name] ->`) may run through (AllowsFeedback);
+                      graphs WITH a feedback edge run as generated kernels only */
     Up,            /* cross-rate stream edge outer -> inner (`* N` destination): StreamUpsampler of `policy`   */
     Down,          /* cross-rate stream edge inner -> outer: StreamDownsampler of `policy` (generated kernels only) */
 };
@@ -148,10 +149,7 @@ inline uint32_t n_state_words(const Node &nd) {
     default: return 0;
     }
 }
-inline bool node_plan_has_kernel(NodeType t) {
-    return t != NodeType::IirLowpass && t != NodeType::OscSine && t != NodeType::OscSquare && t != NodeType::OscSaw &&
-           t != NodeType::Delay && t != NodeType::Up && t != NodeType::Down;
-}
+inline bool node_plan_has_kernel(NodeType t) { return t != NodeType::Up && t != NodeType::Down; }
 /* Delay::prepare (delay/mod.rs:59-69): RingBuffer::new(min((2 * sr) as usize, 88200)) in PowerOfTwo mode */
 inline uint32_t delay_reference_capacity(float sample_rate) {
     const float t = 2.0f * sample_rate;

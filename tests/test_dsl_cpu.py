@@ -404,11 +404,14 @@ def test_constant_whole_sample_delays_get_small_rings():
     assert "state words per voice: %d" % (1 + (3 + 16384) + (3 + 16384) + (3 + 131072)) in g.describe()
 
 
-def test_node_plan_refuses_generated_only_node_types():
+def test_node_plan_refuses_feedback_and_multirate_graphs():
     g = abi.Graph(FEEDBACK)
     with pytest.raises(abi.EngineError) as ei:
         abi.Engine.from_graph(g, 64, plan=abi.PLAN_NODES)
-    assert "runs in generated kernels only" in str(ei.value)
+    assert "needs the per-sample walk" in str(ei.value)
+    with pytest.raises(abi.EngineError) as ei:
+        abi.Engine.from_graph(abi.Graph(text("sat_4x.graph")), 64, plan=abi.PLAN_NODES)
+    assert "multirate" in str(ei.value)
 
 
 # ------------------------------------------------------------------ the front end under sanitizers + fuzzing

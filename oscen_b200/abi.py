@@ -231,6 +231,7 @@ class Engine:
         if rc != 0:
             raise EngineError(f"oscen_b200_create rc={rc}: {self.L.oscen_b200_last_error(None).decode()}")
         self.h = h
+        self.graph = graph             # DSL-compiled graphs: input names, declared ramps
         self.kind, self.n_voices, self.vpi = graph_kind, n_voices, voices_per_instance
         self.n_instances = n_voices // voices_per_instance
         self.channels = self.L.oscen_b200_channels(h)
@@ -269,6 +270,32 @@ class Engine:
             count = self.n_voices - first_voice if a.size == 1 else a.size
         self._chk(self.L.oscen_b200_set_value(self.h, input_id, first_voice, count, a.ctypes.data,
                                               1 if a.size == 1 else 0), "set_value")
+
+    def set(self, name, value):
+        """the generated `set_<name>(value)` of a DSL graph (codegen/mod.rs:917-976): ramps over the input's declared
+        `ramp: N` frames, or assigns when the input has no ramp"""
+        if self.graph is None:
+            raise EngineError("set(name, value) needs an engine created from a DSL graph")
+        i = self.graph.input_id(name)
+        ramp = self.graph.input_info(i)["ramp"]
+        if ramp:
+            self.set_value_ramp(i, value, ramp)
+        else:
+            self.set_value(i, value)
+
+    def render(self, frames, stream_in=None):
+        """BlockRender::render (oscen-lib/src/graph/offline.rs:46-90): any number of frames in chunks of at most
+        MAX_BLOCK; returns the per-voice output [frames][voices] (needs KEEP_VOICE_OUT or the node plan)"""
+        out = np.empty((frames, self.n_voices), dtype=np.float32)
+        pos = 0
+        while pos < frames:
+            chunk = min(MAX_BLOCK, frames - pos)
+            if stream_in is not None:
+                self.stream_in(0, stream_in[pos:pos + chunk])
+            self.process_block(chunk)
+            out[pos:pos + chunk] = self.read_voice_out()
+            pos += chunk
+        return out
 
     def set_value_ramp(self, input_id, target, frames):
         self._chk(self.L.oscen_b200_set_value_ramp(self.h, input_id, float(target), int(frames)), "set_value_ramp")

@@ -87,6 +87,20 @@ public:
         check(oscen_b200_read_mix(e_, out.data()), e_, "read_mix");
         return out;
     }
+    /* BlockRender::render (oscen-lib/src/graph/offline.rs:46-90): `frames` frames in chunks of at most MAX_BLOCK_SIZE;
+       returns the instances' `<out>_block`s back to back: [frames][instances][channels] */
+    std::vector<float> render(uint32_t frames) {
+        std::vector<float> out;
+        out.reserve((size_t)frames * instances_ * channels_);
+        for (uint32_t pos = 0; pos < frames;) {
+            const uint32_t chunk = frames - pos < MAX_BLOCK_SIZE ? frames - pos : MAX_BLOCK_SIZE;
+            process_block(chunk);
+            const std::vector<float> b = out_block();
+            out.insert(out.end(), b.begin(), b.end());
+            pos += chunk;
+        }
+        return out;
+    }
     uint32_t latency_samples() const { return oscen_b200_latency_samples(e_); }
     uint32_t channels() const { return channels_; }
     oscen_b200_engine *raw() { return e_; }

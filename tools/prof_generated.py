@@ -16,7 +16,10 @@ from oscen_b200 import abi  # noqa: E402
 
 n, vpi = 65536, 8
 g = abi.Graph(open(os.path.join(ROOT, "tests", "graphs", "fm_voice.graph")).read())
-e = abi.Engine.from_graph(g, n, vpi, keep=abi.KEEP_INSTANCE_OUT, plan=abi.PLAN_FUSED)
+if len(sys.argv) > 1 and sys.argv[1] == "builtin":      # the hand-written kernel on the identical workload (-k regex:fm_voice_kernel)
+    e = abi.Engine(abi.GRAPH_FM_VOICE, n, vpi, 48000.0, 0, abi.PLAN_FUSED, abi.KEEP_INSTANCE_OUT)
+else:
+    e = abi.Engine.from_graph(g, n, vpi, keep=abi.KEEP_INSTANCE_OUT, plan=abi.PLAN_FUSED)
 rng = np.random.default_rng(1)
 notes = 36 + rng.integers(0, 60, size=n)
 e.set_value(0, (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32))

@@ -598,3 +598,42 @@ def test_oversample_variants_macro_and_named_graph_selection():
         with pytest.raises(abi.GraphCompileError) as ei:
             abi.Graph(broken)
         assert frag in str(ei.value), str(ei.value)
+
+
+# ------------------------------------------------------------------ random graphs (tests/random_graphs.py)
+def test_random_graphs_compile_and_plan_in_topological_order():
+    """300 random acyclic graphs over the whole node library: every one compiles, and in the launch plan every node
+    comes after the nodes it reads (the walk's only ordering requirement)"""
+    import numpy as np
+    import random_graphs as R
+    rng = np.random.default_rng(2026)
+    n_jit = 0
+    for it in range(300):
+        rg = R.make_graph(rng)
+        src = rg.dsl()
+        try:
+            g = abi.Graph(src)
+        except abi.GraphCompileError as ex:
+            raise AssertionError(f"graph {it} does not compile: {ex}\n{src}")
+        flat = [n for grp in groups(g.launches()) for n in grp]
+        pos = {}
+        for k, name in enumerate(flat):
+            pos.setdefault(name, k)
+        for i, nd in enumerate(rg.nodes):
+            if f"n{i}" not in pos:
+                continue                                     # dead node: dropped
+            for ep, srcs in nd["conns"].items():
+                for s in srcs:
+                    stack = [s]
+                    while stack:
+                        e = stack.pop()
+                        if e.kind == "node":
+                            assert pos[f"n{e.args[0]}"] < pos[f"n{i}"], (it, i, e.args[0], src)
+                        elif e.kind in "+-*/":
+                            stack += [e.args[0], e.args[1]]
+                        elif e.kind not in ("value", "lit", "input"):
+                            stack.append(e.args[0])
+        if it % 60 == 0:                                     # a few of the generated kernels through NVRTC
+            assert g.jit_check() > 10000
+            n_jit += 1
+    assert n_jit == 5

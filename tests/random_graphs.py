@@ -33,6 +33,8 @@ class Src:
             return repr(float(f32(a[0])))
         if k == "input":
             return "audio_in"
+        if k == "fb":
+            raise AssertionError("a feedback leg is printed as its own `-> [N] ->` statement")
         if k in "+-*/":
             return f"({a[0].text(g)} {k} {a[1].text(g)})"
         margs = ", ".join(repr(float(f32(x))) for x in a[1])
@@ -40,7 +42,7 @@ class Src:
 
     def is_stream(self):
         k, a = self.kind, self.args
-        if k in ("node", "input"):
+        if k in ("node", "input", "fb"):
             return True
         if k in ("value", "lit"):
             return False
@@ -58,6 +60,8 @@ class Src:
             return f32(a[0])
         if k == "input":
             return xin
+        if k == "fb":                                        # the leg out of a feedback delay: what it output when it last ran
+            return f32(outs["fb"][a[0]].output)
         if k in "+-*/":
             x, y = a[0].eval(outs, vals, xin), a[1].eval(outs, vals, xin)
             with np.errstate(all="ignore"):
@@ -83,6 +87,7 @@ class RandomGraph:
         self.has_input = False
         self.has_gate = False
         self.output = None        # Src
+        self.feedbacks = []       # (source node j, samples N, target node i, endpoint): `nJ.out -> [N] -> nI.ep`, i an ancestor of j (or j itself)
 
     # ---- DSL text
     def dsl(self):
@@ -102,7 +107,11 @@ class RandomGraph:
         for i, nd in enumerate(self.nodes):
             for ep, srcs in nd["conns"].items():
                 for s in srcs:
-                    L.append(f"    {s.text(self)} -> n{i}.{ep};")
+                    if s.kind == "fb":
+                        j, samples, _, _ = self.feedbacks[s.args[0]]
+                        L.append(f"    n{j}.{self.nodes[j]['out']} -> [{samples}] -> n{i}.{ep};")
+                    else:
+                        L.append(f"    {s.text(self)} -> n{i}.{ep};")
         L.append(f"    {self.output.text(self)} -> out;")
         L.append("}")
         return "\n".join(L)
@@ -111,6 +120,7 @@ class RandomGraph:
     def walk(self, n_voices, frames, values, gates, stream_in):
         def make(v):
             objs = [nd["make"]() for nd in self.nodes]
+            fbs = [W.delay(float(samples), 0.0, SR) for (_, samples, _, _) in self.feedbacks]     # Delay::new(N as f32, 0.0)
 
             def gate_fn(s):
                 for nd, o in zip(self.nodes, objs):
@@ -118,7 +128,8 @@ class RandomGraph:
                         o.on_gate(s)
 
             def frame(vals, xin):
-                outs = [None] * len(self.nodes)
+                outs = {k: None for k in range(len(self.nodes))}
+                outs["fb"] = fbs
                 for i, (nd, o) in enumerate(zip(self.nodes, objs)):
                     ins = {}
                     for ep, srcs in nd["conns"].items():
@@ -132,6 +143,9 @@ class RandomGraph:
                                 acc = f32(acc + s.eval(outs, vals, xin))          # fan-in: connect the first, accumulate the rest
                             ins[ep] = acc
                     outs[i] = nd["run"](o, ins)
+                    for k, (j, _, _, _) in enumerate(self.feedbacks):          # the hidden delay runs once its source has
+                        if j == i:
+                            fbs[k].set(input=outs[i]); fbs[k].process()
                 return self.output.eval(outs, vals, xin)
             return frame, gate_fn
         return W.render(make, n_voices, frames, values, gates, stream_in)
@@ -141,7 +155,7 @@ def _stateless(fn):
     return lambda o, ins: fn(ins)
 
 
-def make_graph(rng, n_nodes=None, allow_delay=True):
+def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
     g = RandomGraph()
     n_nodes = n_nodes or int(rng.integers(3, 9))
     n_values = int(rng.integers(0, 4))
@@ -320,6 +334,43 @@ def make_graph(rng, n_nodes=None, allow_delay=True):
         nd["conns"] = {ep: [s for s in srcs if s is not None or ep == "gate"] for ep, srcs in nd["conns"].items()}
         nd["conns"] = {ep: srcs for ep, srcs in nd["conns"].items() if srcs}
         g.nodes.append(nd)
+    # feedback vias: `nJ.out -> [N] -> nI.<stream input>` with I an ancestor of J (or J itself), so the edge closes a cycle
+    if feedback:
+        def ancestors(j):
+            seen, stack = set(), [j]
+            while stack:
+                k = stack.pop()
+                for srcs in g.nodes[k]["conns"].values():
+                    for s0 in srcs:
+                        st = [s0]
+                        while st:
+                            e = st.pop()
+                            if e is None:
+                                continue
+                            if e.kind == "node":
+                                if e.args[0] not in seen:
+                                    seen.add(e.args[0]); stack.append(e.args[0])
+                            elif e.kind in "+-*/":
+                                st += [e.args[0], e.args[1]]
+                            elif e.kind not in ("value", "lit", "input", "fb"):
+                                st.append(e.args[0])
+            return seen
+        stream_eps = {"polyblep": ["frequency_mod", "phase_mod"], "osc": ["frequency_mod"], "tpt": ["input", "f_mod"], "lp18": ["input"],
+                      "iirlp": ["input"], "fmop": ["phase_mod"], "gain": ["input"], "addvalue": ["input"], "mixer": ["input_a", "input_b"],
+                      "crossfade": ["input"], "hardclip": ["input"], "delay": ["input"]}
+        for _ in range(int(rng.integers(1, 3))):
+            j = int(rng.integers(0, n_nodes))
+            cands = sorted(ancestors(j) | {j})
+            cands = [i for i in cands if g.nodes[i]["type"] in stream_eps]
+            if not cands:
+                continue
+            i = cands[int(rng.integers(len(cands)))]
+            eps = stream_eps[g.nodes[i]["type"]]
+            ep = eps[int(rng.integers(len(eps)))]
+            samples = int(rng.integers(1, 6)) if rng.random() < 0.7 else int(rng.integers(6, 70))
+            g.feedbacks.append((j, samples, i, ep))
+            g.nodes[i]["ep_kind"][ep] = "stream"
+            g.nodes[i]["conns"].setdefault(ep, []).append(Src("fb", len(g.feedbacks) - 1))
     # gate connections print as `gate -> nI.gate`
     for nd in g.nodes:
         if "gate" in nd["conns"]:

@@ -35,6 +35,8 @@ class Src:
             return "audio_in"
         if k == "fb":
             raise AssertionError("a feedback leg is printed as its own `-> [N] ->` statement")
+        if k == "cross":
+            raise AssertionError("a cross-rate edge is printed as its own `[policy] src -> dst` statement")
         if k in "+-*/":
             return f"({a[0].text(g)} {k} {a[1].text(g)})"
         margs = ", ".join(repr(float(f32(x))) for x in a[1])
@@ -42,7 +44,7 @@ class Src:
 
     def is_stream(self):
         k, a = self.kind, self.args
-        if k in ("node", "input", "fb"):
+        if k in ("node", "input", "fb", "cross"):
             return True
         if k in ("value", "lit"):
             return False
@@ -62,6 +64,9 @@ class Src:
             return xin
         if k == "fb":                                        # the leg out of a feedback delay: what it output when it last ran
             return f32(outs["fb"][a[0]].output)
+        if k == "cross":                                     # Up edge: this inner tick's sample; Down edge: this frame's result
+            c = outs["cross"][a[0]]
+            return f32(c[outs["tick"]]) if outs["dir"][a[0]] == "up" else f32(c)
         if k in "+-*/":
             x, y = a[0].eval(outs, vals, xin), a[1].eval(outs, vals, xin)
             with np.errstate(all="ignore"):
@@ -88,6 +93,9 @@ class RandomGraph:
         self.has_gate = False
         self.output = None        # Src
         self.feedbacks = []       # (source node j, samples N, target node i, endpoint): `nJ.out -> [N] -> nI.ep`, i an ancestor of j (or j itself)
+        self.rates = []           # per node: log2 of its rate factor (0 = the graph's rate)
+        self.inner_log2 = 0
+        self.cross = []           # cross-rate edges: {"dir": "up" | "down", "policy": str, "src": Src}
 
     # ---- DSL text
     def dsl(self):
@@ -101,7 +109,8 @@ class RandomGraph:
         L.append("output out: stream;")
         L.append("nodes {")
         for i, nd in enumerate(self.nodes):
-            L.append(f"    n{i} = {nd['ctor']};")
+            rate = f" * {1 << self.rates[i]}" if self.rates and self.rates[i] else ""
+            L.append(f"    n{i} = {nd['ctor']}{rate};")
         L.append("}")
         L.append("connections {")
         for i, nd in enumerate(self.nodes):
@@ -110,9 +119,18 @@ class RandomGraph:
                     if s.kind == "fb":
                         j, samples, _, _ = self.feedbacks[s.args[0]]
                         L.append(f"    n{j}.{self.nodes[j]['out']} -> [{samples}] -> n{i}.{ep};")
+                    elif s.kind == "cross":
+                        c = self.cross[s.args[0]]
+                        pol = "" if c["policy"] == "default" else f"[{c['policy']}] "
+                        L.append(f"    {pol}{c['src'].text(self)} -> n{i}.{ep};")
                     else:
                         L.append(f"    {s.text(self)} -> n{i}.{ep};")
-        L.append(f"    {self.output.text(self)} -> out;")
+        if self.output.kind == "cross":
+            c = self.cross[self.output.args[0]]
+            pol = "" if c["policy"] == "default" else f"[{c['policy']}] "
+            L.append(f"    {pol}{c['src'].text(self)} -> out;")
+        else:
+            L.append(f"    {self.output.text(self)} -> out;")
         L.append("}")
         return "\n".join(L)
 
@@ -127,25 +145,79 @@ class RandomGraph:
                     if nd["type"] == "adsr" and "gate" in nd["conns"]:
                         o.on_gate(s)
 
+            import ctypes
+            import oracle_lib as O
+            L = O.lib()
+            N = 1 << self.inner_log2
+            res = []                                          # one resampler per cross-rate edge, like the reference's per-edge fields
+            for c in self.cross:
+                pol = "sinc" if c["policy"] == "default" else c["policy"]
+                if c["dir"] == "up":
+                    if pol == "sinc":
+                        o = O.SincUp(); L.orc_sinc_up_new(ctypes.byref(o), ctypes.c_int(N)); fn = lambda x, out, o=o: L.orc_sinc_up_process(ctypes.byref(o), float(x), out)
+                    elif pol == "sinc_iir":
+                        o = O.IirResampler(); L.orc_iir_up_new(ctypes.byref(o), ctypes.c_int(N)); fn = lambda x, out, o=o: L.orc_iir_up_process(ctypes.byref(o), float(x), out)
+                    elif pol == "linear":
+                        o = O.LinearUp(); L.orc_linear_up_new(ctypes.byref(o), ctypes.c_int(N)); fn = lambda x, out, o=o: L.orc_linear_up_process(ctypes.byref(o), float(x), out)
+                    else:
+                        fn = lambda x, out: L.orc_latch_up_process(N, float(x), out)
+                else:
+                    if pol == "sinc":
+                        o = O.SincDown(); L.orc_sinc_down_new(ctypes.byref(o), ctypes.c_int(N)); fn = lambda xs, o=o: L.orc_sinc_down_process(ctypes.byref(o), xs)
+                    elif pol == "sinc_iir":
+                        o = O.IirResampler(); L.orc_iir_down_new(ctypes.byref(o), ctypes.c_int(N)); fn = lambda xs, o=o: L.orc_iir_down_process(ctypes.byref(o), xs)
+                    elif pol == "linear":
+                        fn = lambda xs: L.orc_linear_down_process(N, xs)
+                    else:
+                        fn = lambda xs: L.orc_latch_down_process(N, xs)
+                res.append(fn)
+
+            def run_node(i, outs, vals, xin):
+                nd, o = self.nodes[i], objs[i]
+                ins = {}
+                for ep, srcs in nd["conns"].items():
+                    if ep == "gate":
+                        continue
+                    if nd["ep_kind"][ep] == "value":
+                        ins[ep] = srcs[-1].eval(outs, vals, xin)              # last write wins
+                    else:
+                        acc = srcs[0].eval(outs, vals, xin)
+                        for s in srcs[1:]:
+                            acc = f32(acc + s.eval(outs, vals, xin))          # fan-in: connect the first, accumulate the rest
+                        ins[ep] = acc
+                outs[i] = nd["run"](o, ins)
+                for k, (j, _, _, _) in enumerate(self.feedbacks):              # the hidden delay runs once its source has
+                    if j == i:
+                        fbs[k].set(input=outs[i]); fbs[k].process()
+
             def frame(vals, xin):
                 outs = {k: None for k in range(len(self.nodes))}
                 outs["fb"] = fbs
-                for i, (nd, o) in enumerate(zip(self.nodes, objs)):
-                    ins = {}
-                    for ep, srcs in nd["conns"].items():
-                        if ep == "gate":
-                            continue
-                        if nd["ep_kind"][ep] == "value":
-                            ins[ep] = srcs[-1].eval(outs, vals, xin)              # last write wins
-                        else:
-                            acc = srcs[0].eval(outs, vals, xin)
-                            for s in srcs[1:]:
-                                acc = f32(acc + s.eval(outs, vals, xin))          # fan-in: connect the first, accumulate the rest
-                            ins[ep] = acc
-                    outs[i] = nd["run"](o, ins)
-                    for k, (j, _, _, _) in enumerate(self.feedbacks):          # the hidden delay runs once its source has
-                        if j == i:
-                            fbs[k].set(input=outs[i]); fbs[k].process()
+                if not self.inner_log2:
+                    for i in range(len(self.nodes)):
+                        run_node(i, outs, vals, xin)
+                    return self.output.eval(outs, vals, xin)
+                # the reference's multirate frame body (codegen/emit_frame.rs:114-176)
+                outs["cross"] = [None] * len(self.cross); outs["dir"] = [c["dir"] for c in self.cross]; outs["tick"] = 0
+                inner = [i for i in range(len(self.nodes)) if self.rates[i]]
+                pre = [i for i in range(len(self.nodes)) if not self.rates[i] and i < inner[0]]
+                post = [i for i in range(len(self.nodes)) if not self.rates[i] and i > inner[0]]
+                for i in pre:
+                    run_node(i, outs, vals, xin)
+                for k, c in enumerate(self.cross):
+                    if c["dir"] == "up":
+                        buf = (ctypes.c_float * N)(); res[k](c["src"].eval(outs, vals, xin), buf); outs["cross"][k] = buf
+                acc = {k: (ctypes.c_float * N)() for k, c in enumerate(self.cross) if c["dir"] == "down"}
+                for tick in range(N):
+                    outs["tick"] = tick
+                    for i in inner:
+                        run_node(i, outs, vals, xin)
+                    for k in acc:
+                        acc[k][tick] = self.cross[k]["src"].eval(outs, vals, xin)
+                for k in acc:
+                    outs["cross"][k] = f32(res[k](acc[k]))
+                for i in post:
+                    run_node(i, outs, vals, xin)
                 return self.output.eval(outs, vals, xin)
             return frame, gate_fn
         return W.render(make, n_voices, frames, values, gates, stream_in)
@@ -155,19 +227,32 @@ def _stateless(fn):
     return lambda o, ins: fn(ins)
 
 
-def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
+def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False, multirate=False):
+    """multirate: nodes [a, b) run at 2^L x the graph's rate (`* N`); every stream edge between the two rates goes through
+    its own resampler of a random connection policy (one source per cross-rate endpoint: no fan-in across rates)"""
     g = RandomGraph()
     n_nodes = n_nodes or int(rng.integers(3, 9))
     n_values = int(rng.integers(0, 4))
     for k in range(n_values):
         g.values[f"p{k}"] = float(f32(rng.uniform(0.1, 0.9)))
     g.has_input = bool(rng.random() < 0.4)
+    g.rates = [0] * n_nodes
+    lo = hi = 0
+    if multirate:
+        g.inner_log2 = int(rng.integers(1, 4))
+        lo = int(rng.integers(0, n_nodes - 1)) if (g.has_input or n_nodes > 3) else 0
+        if lo == 0 and not g.has_input:
+            lo = 0                                              # an inner-rate source node opens the graph
+        hi = int(rng.integers(lo + 1, n_nodes + 1))
+        for i in range(lo, hi):
+            g.rates[i] = g.inner_log2
 
-    def stream_leaf(i):
-        """a stream-kind leaf available to node i (earlier node outputs, the graph's stream input)"""
-        choices = [Src("node", j, ) for j in range(i)]
-        # crossfade has two outputs: pick one through a dedicated Src
-        if g.has_input:
+    def stream_leaf(i, ctx=None):
+        """a stream-kind leaf available to node i (earlier node outputs of ITS rate, the graph's stream input at the outer
+        rate); ctx = (upper node bound, rate) looks at another rate's nodes instead (the source side of a cross-rate edge)"""
+        bound, rate = ctx if ctx is not None else (i, g.rates[i])
+        choices = [Src("node", j, ) for j in range(bound) if g.rates[j] == rate]
+        if g.has_input and rate == 0:
             choices.append(Src("input"))
         if not choices:
             return None
@@ -178,9 +263,9 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
             return Src("value", list(g.values)[int(rng.integers(len(g.values)))])
         return Src("lit", float(f32(rng.uniform(0.05, 1.5))))
 
-    def expr(i, depth=0):
+    def expr(i, depth=0, ctx=None):
         """a stream-kind expression for an input of node i (or None when nothing is available yet)"""
-        s = stream_leaf(i)
+        s = stream_leaf(i, ctx)
         if s is None:
             return None
         r = rng.random()
@@ -188,7 +273,7 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
             return s
         if r < 0.75:
             op = "+-*/"[int(rng.integers(4))]
-            other = expr(i, depth + 1) if rng.random() < 0.5 else value_leaf()
+            other = expr(i, depth + 1, ctx) if rng.random() < 0.5 else value_leaf()
             if other is None:
                 other = value_leaf()
             if op == "/":                                   # keep divisors away from zero: |x| + c
@@ -198,7 +283,7 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
                 a, b = s, other
             return Src(op, a, b)
         m = ["tanh", "abs", "clamp", "min", "max", "sin", "cos", "sqrt"][int(rng.integers(8))]
-        inner = expr(i, depth + 1) or s
+        inner = expr(i, depth + 1, ctx) or s
         if m == "clamp":
             return Src("clamp", inner, (-0.5, 0.6))
         if m in ("min", "max"):
@@ -218,10 +303,22 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
         if i == 0 and not g.has_input and t not in ("polyblep", "osc", "adsr", "fmop"):
             t = "polyblep"                                   # the first node must be a source
         nd = {"type": t, "conns": {}, "out": "output", "ep_kind": {}}
+        sr_i = SR * (1 << g.rates[i])                        # inner-rate nodes: set_sample_rate(sr * N)
 
         def conn(ep, kind, src):
+            if multirate and kind == "stream" and ep not in nd["conns"] and (src is None or rng.random() < 0.35):
+                # the source side of a cross-rate edge: an expression at the OTHER rate (outer nodes before the section for an
+                # inner destination; the section's nodes for an outer destination after it), through its own resampler
+                other = (lo, 0) if g.rates[i] else ((hi, g.inner_log2) if i >= hi else None)
+                xs = expr(i, 1, other) if other is not None else None
+                if xs is not None and xs.is_stream():
+                    g.cross.append({"dir": "up" if g.rates[i] else "down", "src": xs,
+                                    "policy": ["default", "sinc", "sinc_iir", "linear", "latch"][int(rng.integers(5))]})
+                    src = Src("cross", len(g.cross) - 1)
             if src is None:
                 return
+            if multirate and ep in nd["conns"] and (src.kind == "cross" or nd["conns"][ep][0].kind == "cross"):
+                return                                          # no fan-in across rates
             nd["ep_kind"][ep] = kind
             nd["conns"].setdefault(ep, []).append(src)
 
@@ -235,7 +332,7 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
         if t == "polyblep":
             w = WAVES[int(rng.integers(4))]; f = float(f32(rng.uniform(50, 3000))); a = float(f32(rng.uniform(0.2, 1.0)))
             nd["ctor"] = f"PolyBlepOscillator::{w}({f!r}, {a!r})"
-            nd["make"] = lambda w=w, f=f, a=a: W.polyblep(w, f, a, SR)
+            nd["make"] = lambda w=w, f=f, a=a, sr_i=sr_i: W.polyblep(w, f, a, sr_i)
             conn("frequency_mod", "stream", maybe(i, 0.5)); conn("phase_mod", "stream", maybe(i, 0.4))
             value_conn("amplitude", 0.3)
             nd["run"] = lambda o, ins: (o.set(frequency_mod=ins.get("frequency_mod", o.frequency_mod), phase_mod=ins.get("phase_mod", o.phase_mod),
@@ -243,13 +340,13 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
         elif t == "osc":
             w = ["sine", "square", "saw"][int(rng.integers(3))]; f = float(f32(rng.uniform(50, 3000))); a = float(f32(rng.uniform(0.2, 1.0)))
             nd["ctor"] = f"Oscillator::{w}({f!r}, {a!r})"
-            nd["make"] = lambda w=w, f=f, a=a: W.naive_osc(w, f, a, SR)
+            nd["make"] = lambda w=w, f=f, a=a, sr_i=sr_i: W.naive_osc(w, f, a, sr_i)
             conn("frequency_mod", "stream", maybe(i, 0.5)); value_conn("amplitude", 0.3)
             nd["run"] = lambda o, ins: (o.set(frequency_mod=ins.get("frequency_mod", o.frequency_mod), amplitude=ins.get("amplitude", o.amplitude)), o.process())[1]
         elif t == "tpt":
             c = float(f32(rng.uniform(200, 8000))); q = float(f32(rng.uniform(0.3, 4.0)))
             nd["ctor"] = f"TptFilter::new({c!r}, {q!r})"
-            nd["make"] = lambda c=c, q=q: W.tpt(c, q, SR)
+            nd["make"] = lambda c=c, q=q, sr_i=sr_i: W.tpt(c, q, sr_i)
             conn("input", "stream", expr(i)); conn("f_mod", "stream", maybe(i, 0.3))
             if rng.random() < 0.4:
                 e = expr(i)
@@ -261,19 +358,19 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
         elif t == "lp18":
             c = float(f32(rng.uniform(200, 8000))); r = float(f32(rng.uniform(0.0, 0.9)))
             nd["ctor"] = f"LP18Filter::new({c!r}, {r!r})"
-            nd["make"] = lambda c=c, r=r: W.lp18(c, r, SR)
+            nd["make"] = lambda c=c, r=r, sr_i=sr_i: W.lp18(c, r, sr_i)
             conn("input", "stream", expr(i)); value_conn("resonance", 0.3)
             nd["run"] = lambda o, ins: (o.set(input=ins.get("input", o.input), resonance=ins.get("resonance", o.resonance)), o.process())[1]
         elif t == "iirlp":
             c = float(f32(rng.uniform(200, 8000))); q = float(f32(rng.uniform(0.3, 4.0)))
             nd["ctor"] = f"IirLowpass::new({c!r}, {q!r})"
-            nd["make"] = lambda c=c, q=q: W.iirlp(c, q, SR)
+            nd["make"] = lambda c=c, q=q, sr_i=sr_i: W.iirlp(c, q, sr_i)
             conn("input", "stream", expr(i)); value_conn("q", 0.3, 2.0)
             nd["run"] = lambda o, ins: (o.set(input=ins.get("input", o.input), q=ins.get("q", o.q)), o.process())[1]
         elif t == "adsr":
             a_, d_, s_, r_ = (float(f32(x)) for x in (rng.uniform(0.0005, 0.002), rng.uniform(0.0005, 0.003), rng.uniform(0.2, 0.9), rng.uniform(0.0005, 0.002)))
             nd["ctor"] = f"AdsrEnvelope::new({a_!r}, {d_!r}, {s_!r}, {r_!r})"
-            nd["make"] = lambda a_=a_, d_=d_, s_=s_, r_=r_: W.adsr(a_, d_, s_, r_, SR)
+            nd["make"] = lambda a_=a_, d_=d_, s_=s_, r_=r_, sr_i=sr_i: W.adsr(a_, d_, s_, r_, sr_i)
             if rng.random() < 0.8:
                 g.has_gate = True
                 nd["conns"]["gate"] = [None]
@@ -281,7 +378,7 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
             nd["run"] = lambda o, ins: (o.set(sustain=ins.get("sustain", o.sustain)), o.process())[1]
         elif t == "fmop":
             nd["ctor"] = "FmOperator::new()"
-            nd["make"] = lambda: W.fmop(SR)
+            nd["make"] = lambda sr_i=sr_i: W.fmop(sr_i)
             conn("phase_mod", "stream", maybe(i, 0.6)); conn("envelope", "stream", maybe(i, 0.5))
             value_conn("ratio", 0.4, 3.0); value_conn("feedback", 0.4, 0.5); value_conn("level", 0.3)
             conn("base_freq", "value", Src("lit", float(f32(rng.uniform(80, 900)))))
@@ -327,7 +424,7 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
             ds = float(f32(int(rng.integers(0, 40)))) if rng.random() < 0.6 else float(f32(rng.uniform(0.0, 30.0)))
             fb = float(f32(rng.uniform(0.0, 0.7)))
             nd["ctor"] = f"Delay::new({ds!r}, {fb!r})"
-            nd["make"] = lambda ds=ds, fb=fb: W.delay(ds, fb, SR)
+            nd["make"] = lambda ds=ds, fb=fb, sr_i=sr_i: W.delay(ds, fb, sr_i)
             conn("input", "stream", expr(i))
             nd["run"] = lambda o, ins: (o.set(input=ins.get("input", o.input)), o.process())[1]
         # drop inputs that could not be connected (nothing available yet)
@@ -378,7 +475,11 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False):
             nd["ep_kind"]["gate"] = "event"
     # the output: the last node, possibly combined with another one
     out = Src("node", n_nodes - 1)
-    if n_nodes > 1 and rng.random() < 0.5:
+    if multirate:
+        if g.rates[n_nodes - 1]:                             # the graph ends inside the oversampled section: a Down edge to the output
+            g.cross.append({"dir": "down", "src": out, "policy": ["default", "sinc", "sinc_iir", "linear", "latch"][int(rng.integers(5))]})
+            out = Src("cross", len(g.cross) - 1)
+    elif n_nodes > 1 and rng.random() < 0.5:
         out = Src("+", out, Src("*", Src("node", int(rng.integers(0, n_nodes - 1))), Src("lit", 0.5)))
     g.output = out
     return g

@@ -557,6 +557,32 @@ inline const TypeInfo *type_info(const std::string &type) {
     return nullptr;
 }
 
+/* the node library as text, one node type per line: `Type(ctor(args) | ...): endpoint kind [= default], ... -> outputs`
+   (for tools: graphc --nodes, oscen_b200_node_library) */
+inline std::string node_library_text() {
+    static const char *const ctors[][2] = {
+        {"AdsrEnvelope", "new(attack, decay, sustain, release)"}, {"FmOperator", "new()"}, {"TptFilter", "new(cutoff, q)"},
+        {"PolyBlepOscillator", "sine(frequency, amplitude) | saw(..) | square(..) | triangle(..)"},
+        {"LP18Filter", "new(cutoff, resonance)"}, {"IirLowpass", "new(cutoff, q)"}, {"Oscillator", "sine(frequency, amplitude) | square(..) | saw(..)"},
+        {"Delay", "new(delay_samples, feedback) | from_seconds(seconds, feedback, sample_rate)"}, {"Gain", "new(gain)"}, {"AddValue", "new(value)"},
+        {"Mixer", "new()"}, {"Crossfade", "new()"}, {"HardClip", "new()"}};
+    std::string out;
+    for (const auto &c : ctors) {
+        const TypeInfo *ti = type_info(c[0]);
+        if (!ti) continue;
+        out += std::string(c[0]) + "::" + c[1] + "\n";
+        for (const Endpoint &ep : ti->eps) {
+            char b[128];
+            if (ep.is_out) snprintf(b, sizeof b, "    output %s: %s\n", ep.name, "stream");
+            else if (ep.kind == Kind::Event) snprintf(b, sizeof b, "    input  %s: event\n", ep.name);
+            else snprintf(b, sizeof b, "    input  %s: %s (unconnected: %s)\n", ep.name, ep.kind == Kind::Value ? "value" : "stream",
+                          (std::string(c[1]).find(ep.name) != std::string::npos) ? "the constructor argument" : (std::to_string(ep.def).c_str()));
+            out += b;
+        }
+    }
+    return out;
+}
+
 /* --------------------------------------------------------------------------- lowering -- */
 struct Operand {
     enum K { None, Stream, Value, Const } k = None;

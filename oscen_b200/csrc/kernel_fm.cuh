@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
 #if OSCEN_B200_TMA_STATE
     const bool staged = state_stage_in(tile, &state_bar, a.state, FM_NSTATE, n, sp, sn, sv, vs);
 #else
-    const bool staged = false;           /* plain coalesced loads: measured 2-3 % faster, see DESIGN.md §4.3 */
+    const bool staged = false;           /* plain coalesced loads: measured 2-3 % faster, see DESIGN.md §4.4 */
     (void)state_bar;
 #endif
     AdsrState e3, e2, e1, ef;

@@ -1,6 +1,7 @@
 // graphc — the graph compiler as a command-line tool (host only: needs neither CUDA nor a GPU).
 //
 //   graphc [--plan | --cuda | --check] [--graph NAME] file.graph [more.graph ...]
+//   graphc --nodes                      the node library: constructors, endpoints, defaults
 //
 // Concatenates the files (a voice graph followed by the polyphonic graph that instantiates it, say), runs the
 // `graph!` front end (oscen_b200/csrc/dsl.hpp) and prints the lowered plan (--plan, default), the CUDA source of
@@ -22,6 +23,7 @@ int main(int argc, char **argv) {
     int n_files = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
+        if (a == "--nodes") { std::fputs(oscen::dsl::node_library_text().c_str(), stdout); return 0; }     /* the node library the front end knows */
         if (a == "--plan" || a == "--cuda" || a == "--check") { mode = a; continue; }
         if (a == "--graph" && i + 1 < argc) { top = argv[++i]; continue; }     /* compile this graph instead of the last one */
         if (a == "-") { std::stringstream ss; ss << std::cin.rdbuf(); text += ss.str(); ++n_files; continue; }

@@ -637,3 +637,19 @@ def test_random_graphs_compile_and_plan_in_topological_order():
             assert g.jit_check() > 10000
             n_jit += 1
     assert n_jit == 5
+
+
+def test_graphc_lists_the_node_library(graphc):
+    r = _run(graphc, ["--nodes"])
+    assert r.returncode == 0
+    for frag in ("AdsrEnvelope::new(attack, decay, sustain, release)", "input  gate: event", "FmOperator::new()",
+                 "input  envelope: stream (unconnected: 1.000000)", "Delay::new(delay_samples, feedback) | from_seconds",
+                 "input  pulse_width: value (unconnected: 0.500000)", "HardClip::new()"):
+        assert frag in r.stdout, frag
+    # every type the listing names is one the front end accepts, with the listed endpoints
+    for type_name in re.findall(r"^(\w+)::", r.stdout, re.M):
+        ctor = {"AdsrEnvelope": "new(0.1, 0.1, 0.5, 0.1)", "FmOperator": "new()", "TptFilter": "new(1000.0, 0.7)", "PolyBlepOscillator": "sine(1.0, 1.0)",
+                "LP18Filter": "new(1000.0, 0.5)", "IirLowpass": "new(1000.0, 0.7)", "Oscillator": "sine(1.0, 1.0)", "Delay": "new(1.0, 0.0)",
+                "Gain": "new(1.0)", "AddValue": "new(0.0)", "Mixer": "new()", "Crossfade": "new()", "HardClip": "new()"}[type_name]
+        out = "output_a" if type_name == "Crossfade" else "output"
+        abi.Graph(f"output stream o; node n = {type_name}::{ctor}; connection n.{out} -> o;")

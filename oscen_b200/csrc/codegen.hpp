@@ -46,7 +46,11 @@ struct Emitter {
     /* parameter slot k of node i: a value input of the graph, or the constructor's literal */
     std::string P(int i, int k) const {
         const plan::Node &nd = g.nodes[i];
-        return nd.pid[k] != plan::kNoValue ? "P[" + std::to_string(nd.pid[k]) + "]" : lit(nd.cst[k]);
+        if (nd.pid[k] == plan::kNoValue) return lit(nd.cst[k]);
+        /* EXPERIMENT (off by default, round-2 measurement): an input declared uniform-and-static reads the kernel-argument
+           constant bank at every use instead of occupying a register for the whole block */
+        if ((uniform_mask >> nd.pid[k]) & 1u) return "a.u.p[" + std::to_string(nd.pid[k]) + "]";
+        return "P[" + std::to_string(nd.pid[k]) + "]";
     }
     bool P_is_const(int i, int k) const { return g.nodes[i].pid[k] == plan::kNoValue; }
     /* stream input k of node i; `standin` = the parameter slot read when no stream is connected */
@@ -110,11 +114,14 @@ struct Emitter {
     static int env_int(const char *name, int def) { const char *e = getenv(name); return e && *e ? atoi(e) : def; }
     bool hoist_adsr = true;
     int min_blocks = 8;
+    uint32_t uniform_mask = 0;       /* EXPERIMENT: OSCEN_B200_JIT_UNIFORM_MASK=0x... — the caller promises these inputs are uniform over
+                                        the voices and neither ramped nor written by value events while the kernel is in use */
 
     std::string run(const char *kernel_name) {
         using T = plan::NodeType;
         hoist_adsr = env_int("OSCEN_B200_JIT_ADSR_HOIST", 1) != 0;
         min_blocks = env_int("OSCEN_B200_JIT_MIN_BLOCKS", 8);
+        { const char *e = getenv("OSCEN_B200_JIT_UNIFORM_MASK"); uniform_mask = e && *e ? (uint32_t)strtoul(e, nullptr, 0) : 0u; }
         const int n_nodes = (int)g.nodes.size();
         const uint32_t ni = (uint32_t)g.inputs.size();
         const bool has_in = !g.stream_input.empty();
@@ -146,6 +153,7 @@ struct Emitter {
         /* ---- value inputs */
         snprintf(b, sizeof b, "float P[%u];", ni ? ni : 1u); line(1, b);
         for (uint32_t i = 0; i < ni; ++i) {
+            if ((uniform_mask >> i) & 1u) { snprintf(b, sizeof b, "P[%u] = 0.0f;    /* %s: uniform, read from a.u.p[%u] */", i, g.inputs[i].name.c_str(), i); line(1, b); continue; }
             snprintf(b, sizeof b, "P[%u] = a.pv[(size_t)%uu * n + vs];    /* %s */", i, i, g.inputs[i].name.c_str()); line(1, b);
         }
         if (!ni) line(1, "P[0] = 0.0f;");
@@ -209,7 +217,7 @@ struct Emitter {
         if (ni) {
             line(4, "if (ramp_mask) {");
             line(5, "const float *row = a.ptab + (size_t)f * kMaxInputs;");
-            for (uint32_t i = 0; i < ni; ++i) { snprintf(b, sizeof b, "if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i); line(5, b); }
+            for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { snprintf(b, sizeof b, "if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i); line(5, b); }
             line(4, "}");
         }
         /* ---- this frame's events: value edges are assigned before process_event_inputs() */
@@ -220,7 +228,7 @@ struct Emitter {
         line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
         line(6, "const Event e = ec.ev[q];");
         line(6, "if (e.input_id == kEventGate) continue;");
-        for (uint32_t i = 0; i < ni; ++i) { snprintf(b, sizeof b, "if (e.input_id == %uu) P[%u] = e.scalar;", i, i); line(6, b); }
+        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { snprintf(b, sizeof b, "if (e.input_id == %uu) P[%u] = e.scalar;", i, i); line(6, b); }
         snprintf(b, sizeof b, "if (e.input_id < %uu) a.pv[(size_t)e.input_id * n + v] = e.scalar;", ni); line(6, b);
         line(5, "}");
         line(4, "}");

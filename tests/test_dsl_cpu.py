@@ -653,3 +653,42 @@ def test_graphc_lists_the_node_library(graphc):
                 "Gain": "new(1.0)", "AddValue": "new(0.0)", "Mixer": "new()", "Crossfade": "new()", "HardClip": "new()"}[type_name]
         out = "output_a" if type_name == "Crossfade" else "output"
         abi.Graph(f"output stream o; node n = {type_name}::{ctor}; connection n.{out} -> o;")
+
+
+def test_random_feedback_and_multirate_graphs_compile_and_generate_valid_cuda():
+    """the two harder generators of the differential fuzzer (tests/random_graphs.py): every graph compiles; cycles are
+    accepted exactly because they run through vias; multirate graphs get one resampler per cross-rate edge; a sample of
+    the generated kernels goes through NVRTC (no GPU needed)"""
+    import numpy as np
+    import random_graphs as R
+    for it in range(120):
+        rg = R.make_graph(np.random.default_rng(5000 + it), feedback=True)
+        g = abi.Graph(rg.dsl())
+        n_delays = sum(1 for nd in rg.nodes if nd["type"] == "delay") + len(rg.feedbacks)
+        assert len(g.launches()) >= 1 and g.describe().count("-> [") <= len(rg.feedbacks) and g.describe().count("Delay [") <= n_delays
+        if it % 40 == 0:
+            assert g.jit_check() > 10000
+    for it in range(120):
+        rg = R.make_graph(np.random.default_rng(9000 + it), multirate=True)
+        g = abi.Graph(rg.dsl())
+        d = g.describe()
+        live_cross = d.count("UpEdge [") + d.count("DownEdge [")
+        assert live_cross <= len(rg.cross)                        # dead edges are dropped with their nodes, none is invented
+        if any(r for r in rg.rates):
+            with pytest.raises(abi.EngineError):                   # multirate graphs never run as node plans
+                if "Edge [" in d:
+                    abi.Engine.from_graph(g, 8, plan=abi.PLAN_NODES)
+                else:
+                    raise abi.EngineError("no live cross-rate edge")
+        if it % 40 == 0:
+            assert g.jit_check() > 10000
+
+
+def test_c_abi_header_is_valid_c_and_cxx(tmp_path):
+    """include/oscen_b200.h is the drop-in boundary: it must compile as plain C (for cgo / Rust bindgen / ctypes-style
+    consumers) and as C++"""
+    import subprocess
+    root = os.path.dirname(GRAPHS[:-len("/graphs")])
+    hdr = os.path.join(root, "include", "oscen_b200.h")
+    for lang, std in (("c", "-std=c99"), ("c", "-std=c11"), ("c++", "-std=c++17")):
+        subprocess.check_call(["gcc", "-x", lang, std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", hdr])

@@ -36,7 +36,7 @@ def builtin_plan(kind):
     return buf.value.decode().strip().splitlines()
 
 
-@pytest.mark.parametrize("file,kind", [("fm_voice.graph", abi.GRAPH_FM_VOICE), ("synth.graph", abi.GRAPH_SYNTH),
+@pytest.mark.parametrize("file,kind", [("voice_fm3.graph", abi.GRAPH_FM_VOICE), ("synth.graph", abi.GRAPH_SYNTH),
                                        ("synth_adsr.graph", abi.GRAPH_SYNTH_ADSR), ("sat_1x.graph", abi.GRAPH_SAT_1X)])
 def test_reference_graphs_compile_to_the_builtin_launch_plans(file, kind):
     g = abi.Graph(text(file))
@@ -52,7 +52,7 @@ def test_twin_peaks_plan_and_expression_edge():
 
 
 def test_fm_voice_inputs_follow_declaration_order():
-    g = abi.Graph(text("fm_voice.graph"))
+    g = abi.Graph(text("voice_fm3.graph"))
     assert g.n_inputs == 28
     assert g.input_id("frequency") == 0 and g.input_id("op3_ratio") == 1 and g.input_id("route") == 20
     assert g.input_id("filter_env_amount") == 27
@@ -218,7 +218,7 @@ def test_graph_objects_are_independent_of_the_gpu():
 
 
 # ------------------------------------------------------------------ generated fused kernels (codegen.hpp + NVRTC)
-@pytest.mark.parametrize("file", ["fm_voice.graph", "synth.graph", "synth_adsr.graph", "twin_peaks.graph", "sat_1x.graph"])
+@pytest.mark.parametrize("file", ["voice_fm3.graph", "synth.graph", "synth_adsr.graph", "twin_peaks.graph", "sat_1x.graph"])
 def test_generated_kernel_source_compiles_for_sm_100a(file):
     """NVRTC needs no GPU: every reference graph's generated kernel must compile for sm_100a here"""
     g = abi.Graph(text(file))
@@ -229,7 +229,7 @@ def test_generated_kernel_source_compiles_for_sm_100a(file):
 
 
 def test_generated_kernel_walks_nodes_in_topological_order():
-    g = abi.Graph(text("fm_voice.graph"))
+    g = abi.Graph(text("voice_fm3.graph"))
     src = g.codegen()
     order = [m.group(1) for m in re.finditer(r"const float s\d+ = .*/\* (\w+) \*/$", src, re.M)]
     pos = {n: i for i, n in enumerate(order)}
@@ -319,7 +319,7 @@ def test_stringify_spacing_is_accepted():
 
 # ------------------------------------------------------------------ polyphonic graphs (voice arrays + the MIDI front)
 def test_polyphonic_fm_graph_compiles_to_the_voice_plan_with_outer_names():
-    g = abi.Graph(text("fm_voice.graph") + text("fm_graph.graph"))
+    g = abi.Graph(text("voice_fm3.graph") + text("poly_fm8.graph"))
     assert g.voices_per_instance == 8 and g.has_midi
     assert g.launches() == builtin_plan(abi.GRAPH_FM_VOICE)
     d = g.describe()
@@ -338,15 +338,15 @@ def test_polyphonic_fm_graph_compiles_to_the_voice_plan_with_outer_names():
     (("voices = [FMVoice::new(); 8];", "voices = [Unknown::new(); 8];"), "is not a graph of this text"),
     (("voice_handlers.gate -> voices.gate;", "voice_handlers.gate -> voices.trigger;"), "has no event input `trigger`"),
     (("route -> voices.route;", "route -> voices.rout;"), "has no value input `rout`"),
-    (("voices.audio_out -> audio_out;", ""), "is not connected to the output"),
-    (("midi_parser = MidiParser::new();", ""), "MIDI front needs all of"),
-    (("route -> voices.route;", "route -> voices.route; op3_ratio -> midi_parser.midi_in;"), "not part of the polyphonic pattern"),
+    (("connection voices.audio_out -> audio_out;", ""), "is not connected to the output"),
+    (("node midi_parser = MidiParser::new();", ""), "MIDI front needs all of"),
+    (("route -> voices.route;", "route -> voices.route; connection op3_ratio -> midi_parser.midi_in;"), "not part of the polyphonic pattern"),
 ])
 def test_polyphonic_graph_errors(mutation, frag):
-    outer = text("fm_graph.graph")
+    outer = text("poly_fm8.graph")
     assert mutation[0] in outer
     with pytest.raises(abi.GraphCompileError) as ei:
-        abi.Graph(text("fm_voice.graph") + outer.replace(mutation[0], mutation[1]))
+        abi.Graph(text("voice_fm3.graph") + outer.replace(mutation[0], mutation[1]))
     assert frag in str(ei.value), str(ei.value)
 
 
@@ -432,7 +432,7 @@ def _run(exe, args, text=None):
 
 
 def test_graphc_cli_matches_the_library_and_is_sanitizer_clean(graphc):
-    for files in (["fm_voice.graph"], ["synth.graph"], ["twin_peaks.graph"], ["sat_4x.graph"], ["fm_voice.graph", "fm_graph.graph"]):
+    for files in (["voice_fm3.graph"], ["synth.graph"], ["twin_peaks.graph"], ["sat_4x.graph"], ["voice_fm3.graph", "poly_fm8.graph"]):
         paths = [os.path.join(GRAPHS, f) for f in files]
         r = _run(graphc, ["--plan"] + paths)
         assert r.returncode == 0 and r.stderr == "", r.stderr
@@ -451,8 +451,8 @@ def test_front_end_survives_mutated_graphs(graphc):
     import random
     import re as _re
     rng = random.Random(20261017)
-    corpus = [text(f) for f in ("fm_voice.graph", "synth_adsr.graph", "twin_peaks.graph", "sat_4x.graph")]
-    corpus.append(text("fm_voice.graph") + text("fm_graph.graph"))
+    corpus = [text(f) for f in ("voice_fm3.graph", "synth_adsr.graph", "twin_peaks.graph", "sat_4x.graph")]
+    corpus.append(text("voice_fm3.graph") + text("poly_fm8.graph"))
     corpus.append(FEEDBACK)
     junk = ["->", "[", "]", "{", "}", "(", ")", ";", ":", "::", "..", ",", "=", "*", "/", "+", "-", ".", "<", ">", "!", "graph", "input", "output",
             "node", "nodes", "connection", "connections", "value", "stream", "event", "name", "ramp", "0", "8", "1e39", "-0.0", "4294967296",

@@ -14,7 +14,7 @@ from oscen_b200 import abi  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-text = open(os.path.join(ROOT, "tests", "graphs", "fm_voice.graph")).read()
+text = open(os.path.join(ROOT, "tests", "graphs", "voice_fm3.graph")).read()
 rng = np.random.default_rng(1)
 notes = 36 + rng.integers(0, 60, size=n)
 freq = (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32)

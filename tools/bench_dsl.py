@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from oscen_b200 import abi  # noqa: E402
 
 FRAMES = 256
-CASES = [("fm_voice.graph", abi.GRAPH_FM_VOICE, 8, 0), ("synth_adsr.graph", abi.GRAPH_SYNTH_ADSR, 1, 2),
+CASES = [("voice_fm3.graph", abi.GRAPH_FM_VOICE, 8, 0), ("synth_adsr.graph", abi.GRAPH_SYNTH_ADSR, 1, 2),
          ("twin_peaks.graph", abi.GRAPH_TWIN_PEAKS, 1, None), ("sat_1x.graph", abi.GRAPH_SAT_1X, 1, 0),
          ("sat_4x.graph", abi.GRAPH_SAT_4X, 1, 0)]
 

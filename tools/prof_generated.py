@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Workload for an `ncu --set full` capture of a GENERATED kernel: the FMVoice graph from its DSL text
-(tests/graphs/fm_voice.graph), 65 536 voices x 256 frames, steady-state sustain block.
+(tests/graphs/voice_fm3.graph), 65 536 voices x 256 frames, steady-state sustain block.
 
     ncu --set full --clock-control none --import-source on -k regex:oscen_b200_generated_kernel -s 30 -c 1 \
         -o gpurun_out/prof_generated_fm python tools/prof_generated.py
@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from oscen_b200 import abi  # noqa: E402
 
 n, vpi = 65536, 8
-g = abi.Graph(open(os.path.join(ROOT, "tests", "graphs", "fm_voice.graph")).read())
+g = abi.Graph(open(os.path.join(ROOT, "tests", "graphs", "voice_fm3.graph")).read())
 if len(sys.argv) > 1 and sys.argv[1] == "builtin":      # the hand-written kernel on the identical workload (-k regex:fm_voice_kernel)
     e = abi.Engine(abi.GRAPH_FM_VOICE, n, vpi, 48000.0, 0, abi.PLAN_FUSED, abi.KEEP_INSTANCE_OUT)
 else:

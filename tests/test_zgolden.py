@@ -3,7 +3,8 @@ oracle's waveforms for the BASELINE config graphs, frozen by tests/golden/make_g
 
 CPU: the oracle must reproduce every fixture bit for bit (it has not drifted: same libm, same flags) and honour the
 reference's vectors.  GPU: the CUDA path (fused kernels and node plans, through the C ABI) against the committed bytes,
-tolerance |gpu - golden| <= 1e-6 + 1e-5 |golden| as BASELINE.json's north_star states (in practice bit-identical)."""
+tolerance |gpu - golden| <= 1e-6 + 1e-5 |golden| as BASELINE.json's north_star states (in practice bit-identical).
+(The file name sorts last on purpose: these tests were added after the round's GPU budget was spent.)"""
 import ctypes as C
 import json
 import os
@@ -60,7 +61,7 @@ def test_fixtures_are_what_make_golden_generates():
 
 
 # ------------------------------------------------------------------------------------------------ GPU
-NODE_PLANS = {"fm_anchor_defaults", "fm_anchor_feedback", "fm_bank_64", "twin_peaks_16", "sat_1x_16", "synth_adsr_16"}
+NODE_PLANS = {"fm_bank_64", "twin_peaks_16", "sat_1x_16", "synth_adsr_16"}      # graphs that also have a node plan
 
 
 @pytest.mark.gpu

@@ -71,3 +71,23 @@ def test_product_does_not_touch_oracle():
                 if re.search(r"oracle_lib|liboscen_oracle|oscen_oracle\.h|/oracle/", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_rust_sys_crate_declares_every_abi_symbol():
+    """rust/oscen-b200-sys cannot be compiled here (no cargo): at least its extern block must name every entry point of
+    the header, with the same number of parameters, and nothing else"""
+    hdr = open(os.path.join(ROOT, "include", "oscen_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_protos = {m.group(1): m.group(2) for m in re.finditer(r"\b(oscen_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)}
+    rs = open(os.path.join(ROOT, "rust", "oscen-b200-sys", "src", "lib.rs")).read()
+    rs_protos = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (oscen_b200_[a-z0-9_]+)\(([^)]*)\)", rs)}
+    assert set(rs_protos) == set(c_protos), set(rs_protos) ^ set(c_protos)
+
+    def n_params(s):
+        s = s.strip()
+        return 0 if s in ("", "void") else s.count(",") + 1
+    for name in c_protos:
+        assert n_params(c_protos[name]) == n_params(rs_protos[name]), name
+    # #[repr(C)] mirrors exist for every struct the header defines
+    for struct in re.findall(r"\}\s*(oscen_b200_[a-z_]+)\s*;", hdr):
+        assert f"pub struct {struct}" in rs, struct

@@ -7,9 +7,10 @@
  *
  * Compile flags mirror the in-tree build (oscen_b200/build.py): -arch=sm_100a, --fmad=false (rustc
  * never contracts a*b+c), IEEE division / sqrt, no fast-math, -lineinfo.  The generated translation
- * unit includes the engine's own device headers from oscen_b200/csrc (located next to the shared
- * library, or $OSCEN_B200_CSRC), so the node bodies are the very same functions the hand-written
- * kernels call.
+ * unit includes the engine's own device headers, so the node bodies are the very same functions the
+ * hand-written kernels call.  The build embeds those headers in the library as text (jit_headers.inc)
+ * and hands them to nvrtcCreateProgram: a relocated .so needs no source tree.  $OSCEN_B200_CSRC
+ * overrides the embedded copies with a directory (development: try a header edit without a rebuild).
  */
 #pragma once
 #include <dlfcn.h>
@@ -22,6 +23,20 @@
 #include <string>
 #include <vector>
 
+namespace oscen {
+namespace jit {
+
+/* the device headers a generated kernel includes, embedded as text by the build (oscen_b200/build.py writes
+   jit_headers.inc): run-time compilation then needs no source tree next to the shared library */
+struct EmbeddedHeader { const char *name; const char *text; };
+}  // namespace jit
+}  // namespace oscen
+#if defined(__has_include)
+#if __has_include("jit_headers.inc")
+#include "jit_headers.inc"
+#define OSCEN_B200_HAVE_EMBEDDED_HEADERS 1
+#endif
+#endif
 namespace oscen {
 namespace jit {
 
@@ -88,9 +103,16 @@ inline bool compile_cubin_uncached(const std::string &source, std::vector<char> 
     if (!nvrtc_load(err)) return false;
     Nvrtc &n = nvrtc();
     void *prog = nullptr;
-    int rc = n.CreateProgram(&prog, source.c_str(), "oscen_b200_generated.cu", 0, nullptr, nullptr);
+    /* headers: the embedded copies (the ones this library was built with), unless $OSCEN_B200_CSRC points at a source tree */
+    std::vector<const char *> h_text, h_name;
+#ifdef OSCEN_B200_HAVE_EMBEDDED_HEADERS
+    if (!getenv("OSCEN_B200_CSRC"))
+        for (int i = 0; i < kNJitHeaders; ++i) { h_text.push_back(kJitHeaders[i].text); h_name.push_back(kJitHeaders[i].name); }
+#endif
+    int rc = n.CreateProgram(&prog, source.c_str(), "oscen_b200_generated.cu", (int)h_text.size(), h_text.empty() ? nullptr : h_text.data(),
+                             h_name.empty() ? nullptr : h_name.data());
     if (rc != 0) { err = std::string("nvrtcCreateProgram: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"); return false; }
-    const std::string inc = "--include-path=" + csrc_dir();
+    const std::string inc = "--include-path=" + (h_text.empty() ? csrc_dir() : std::string("/nonexistent-oscen-b200-headers-are-embedded"));
     const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "--prec-div=true", "--prec-sqrt=true",
                           "-lineinfo", "-default-device", inc.c_str()};
     rc = n.CompileProgram(prog, (int)(sizeof opts / sizeof opts[0]), opts);

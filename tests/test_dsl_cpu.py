@@ -692,3 +692,27 @@ def test_c_abi_header_is_valid_c_and_cxx(tmp_path):
     hdr = os.path.join(root, "include", "oscen_b200.h")
     for lang, std in (("c", "-std=c99"), ("c", "-std=c11"), ("c++", "-std=c++17")):
         subprocess.check_call(["gcc", "-x", lang, std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", hdr])
+
+
+def test_generated_kernel_compiles_from_a_relocated_library(tmp_path):
+    """the device headers a generated kernel includes are embedded in the shared library (build.py -> jit_headers.inc ->
+    jit.hpp): a library copied away from its source tree still compiles a generated kernel, cross-rate edges included"""
+    import shutil
+    import subprocess
+    import sys
+    from oscen_b200 import abi
+    lib = tmp_path / "liboscen_b200.so"
+    shutil.copy(abi.LIB, lib)
+    code = ("from oscen_b200 import abi\n"
+            "import sys\n"
+            "for p in sys.argv[1:]:\n"
+            "    n = abi.Graph(open(p).read()).jit_check()\n"
+            "    assert n > 10000, (p, n)\n"
+            "    print(p, n)\n")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, OSCEN_B200_LIB=str(lib), PYTHONPATH=os.path.dirname(here))
+    env.pop("OSCEN_B200_CSRC", None)
+    r = subprocess.run([sys.executable, "-c", code, os.path.join(here, "graphs", "voice_fm3.graph"), os.path.join(here, "graphs", "sat_4x.graph")],
+                       env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "voice_fm3" in r.stdout and "sat_4x" in r.stdout

@@ -275,6 +275,19 @@ int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_co
    NVRTC (returns the sm_100a cubin size; the compiler log / error goes to `log`).  Neither needs a GPU. */
 int  oscen_b200_graph_codegen(const oscen_b200_graph *g, char *dst, size_t cap);
 int  oscen_b200_graph_jit_check(const oscen_b200_graph *g, char *log, size_t log_cap);
+/* what an engine of this graph at `sample_rate` would hand to NVRTC and start from (Delay rings are sized by the sample
+   rate, so the state layout depends on it): the generated source, the state words of one voice after new() + init(sr)
+   (field order = the SoA rows of oscen_b200_read_state), the dynamic shared memory of the kernel.  Host only, no GPU:
+   offline inspection, and the CPU suite's host-executed kernel check (tests/host_kernel.py).  Any output may be NULL.
+   Returns 0, or OSCEN_B200_E_ARG when a buffer is too small (the needed sizes are still written). */
+typedef struct {
+    uint32_t source_len;        /* bytes of the generated source, without the NUL */
+    uint32_t n_state;           /* state words per voice (stream-input LCG words included) */
+    uint32_t dyn_smem_bytes;    /* dynamic shared memory per CTA */
+    uint32_t inner_factor;      /* 1, or the graph's oversampling factor */
+} oscen_b200_kernel_info;
+int  oscen_b200_graph_kernel_info(const oscen_b200_graph *g, float sample_rate, oscen_b200_kernel_info *info,
+                                  char *source, size_t source_cap, uint32_t *state_words, size_t state_cap);
 
 /* counters: kernels launched by this engine since create; bytes copied H2D / D2H */
 typedef struct {

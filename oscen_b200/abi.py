@@ -40,6 +40,7 @@ SYMBOLS = [
     "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
     "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
+    "oscen_b200_graph_kernel_info",
 ]
 
 
@@ -47,6 +48,10 @@ class Config(C.Structure):
     _fields_ = [("graph_kind", C.c_uint32), ("n_voices", C.c_uint32), ("voices_per_instance", C.c_uint32),
                 ("sample_rate", C.c_float), ("device", C.c_int32), ("plan", C.c_uint32), ("keep", C.c_uint32),
                 ("reserved", C.c_uint32)]
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [("source_len", C.c_uint32), ("n_state", C.c_uint32), ("dyn_smem_bytes", C.c_uint32), ("inner_factor", C.c_uint32)]
 
 
 class Event(C.Structure):
@@ -133,6 +138,7 @@ def load():
     L.oscen_b200_graph_has_midi.argtypes = [vp]
     L.oscen_b200_graph_codegen.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_jit_check.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.oscen_b200_graph_kernel_info.argtypes = [vp, C.c_float, C.POINTER(KernelInfo), C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
     _lib = L
     return L
 
@@ -190,6 +196,17 @@ class Graph:
         if n < 0:
             raise EngineError(f"graph_codegen rc={n}")
         return buf.value.decode()
+
+    def kernel_info(self, sample_rate=48000.0):
+        """(generated source, initial state words of one voice [n_state] u32, KernelInfo) of an engine at this sample rate"""
+        info = KernelInfo()
+        self.L.oscen_b200_graph_kernel_info(self.h, sample_rate, C.byref(info), None, 0, None, 0)
+        src = C.create_string_buffer(info.source_len + 1)
+        words = (C.c_uint32 * info.n_state)()
+        rc = self.L.oscen_b200_graph_kernel_info(self.h, sample_rate, C.byref(info), src, len(src), words, info.n_state)
+        if rc != 0:
+            raise EngineError(f"graph_kernel_info rc={rc}")
+        return src.value.decode(), np.frombuffer(words, dtype=np.uint32).copy(), info
 
     def jit_check(self):
         """compile the generated kernel with NVRTC for sm_100a (no GPU needed); returns the cubin size"""

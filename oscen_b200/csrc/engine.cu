@@ -727,6 +727,24 @@ int oscen_b200_graph_jit_check(const oscen_b200_graph *g, char *log, size_t log_
     if (log && log_cap) { strncpy(log, msg.c_str(), log_cap - 1); log[log_cap - 1] = 0; }
     return ok ? (int)cubin.size() : OSCEN_B200_E_JIT;
 }
+int oscen_b200_graph_kernel_info(const oscen_b200_graph *g, float sample_rate, oscen_b200_kernel_info *info,
+                                 char *source, size_t source_cap, uint32_t *state_words, size_t state_cap) {
+    if (!g || !(sample_rate > 0.0f)) return OSCEN_B200_E_ARG;
+    plan::Graph pg = g->g;                                   /* the same steps as create_impl, up to the device */
+    plan::assign_state_layout(pg, sample_rate);
+    const std::string src = codegen::fused_kernel_source(pg, g->p, kJitKernelName);
+    uint32_t n_state = pg.n_state + (pg.stream_input.empty() ? 0u : 2u);
+    if (n_state == 0) n_state = 1;
+    const std::vector<uint32_t> init = initial_state(OSCEN_B200_GRAPH_CUSTOM, sample_rate, &pg, n_state);
+    if (info) {
+        info->source_len = (uint32_t)src.size(); info->n_state = n_state;
+        info->dyn_smem_bytes = (uint32_t)codegen::dyn_smem_bytes(pg); info->inner_factor = 1u << pg.inner_log2;
+    }
+    int rc = 0;
+    if (source) { if (src.size() + 1 > source_cap) rc = OSCEN_B200_E_ARG; else memcpy(source, src.c_str(), src.size() + 1); }
+    if (state_words) { if (init.size() > state_cap) rc = OSCEN_B200_E_ARG; else memcpy(state_words, init.data(), init.size() * sizeof(uint32_t)); }
+    return rc;
+}
 int oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out) {
     if (!g) { g_create_error = "null graph"; return OSCEN_B200_E_ARG; }
     return create_impl(cfg, g, out);

@@ -66,6 +66,15 @@ pub struct oscen_b200_input_info {
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
+pub struct oscen_b200_kernel_info {
+    pub source_len: u32,
+    pub n_state: u32,
+    pub dyn_smem_bytes: u32,
+    pub inner_factor: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
 pub struct oscen_b200_stats {
     pub kernel_launches: u64,
     pub graph_launches: u64,
@@ -111,6 +120,7 @@ extern "C" {
     pub fn oscen_b200_create_from_graph(g: *const oscen_b200_graph, cfg: *const oscen_b200_config, out: *mut *mut oscen_b200_engine) -> c_int;
     pub fn oscen_b200_graph_codegen(g: *const oscen_b200_graph, dst: *mut c_char, cap: usize) -> c_int;
     pub fn oscen_b200_graph_jit_check(g: *const oscen_b200_graph, log: *mut c_char, log_cap: usize) -> c_int;
+    pub fn oscen_b200_graph_kernel_info(g: *const oscen_b200_graph, sample_rate: f32, info: *mut oscen_b200_kernel_info, source: *mut c_char, source_cap: usize, state_words: *mut u32, state_cap: usize) -> c_int;
     pub fn oscen_b200_get_stats(e: *const oscen_b200_engine, out: *mut oscen_b200_stats) -> c_int;
     pub fn oscen_b200_last_block_ms(e: *mut oscen_b200_engine, ms: *mut f32) -> c_int;
     pub fn oscen_b200_enable_timing(e: *mut oscen_b200_engine, on: c_int) -> c_int;

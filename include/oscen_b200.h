@@ -271,6 +271,16 @@ int  oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t input_id, o
                             libnvrtc.so.12 and the engine's device headers next to the library).
    Both are bit-identical.  The graph object may be freed afterwards. */
 int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out);
+/* `external NAME: AudioAsset;` slots (oscen-graph-compiler/src/parse.rs:447-456; the generated graph's
+   `graph.<name>.load_wav(..)` handle, oscen-lib/src/asset/mod.rs): the slots of a graph in declaration order, and the
+   run-time load — `interleaved` is frames x channels f32 at the engine's sample rate (decoding / rate conversion stay with
+   the caller); a mono SamplePlayer takes channel 0 (sample_player/mod.rs:36-49).  One buffer per slot per engine, shared
+   by its voices; every player bound to the slot restarts at the next block (mod.rs:107-112); frames == 0 empties the slot.
+   Graphs with a SamplePlayer run as generated kernels (OSCEN_B200_PLAN_FUSED). */
+#define OSCEN_B200_MAX_ASSETS 4
+uint32_t oscen_b200_graph_n_assets(const oscen_b200_graph *g);
+int  oscen_b200_graph_asset_id(const oscen_b200_graph *g, const char *name);
+int  oscen_b200_load_asset(oscen_b200_engine *e, uint32_t asset_id, const float *interleaved, uint32_t frames, uint32_t channels);
 /* the generated CUDA source of PLAN_FUSED (returns its length), and a compile-only check of it with
    NVRTC (returns the sm_100a cubin size; the compiler log / error goes to `log`).  Neither needs a GPU. */
 int  oscen_b200_graph_codegen(const oscen_b200_graph *g, char *dst, size_t cap);

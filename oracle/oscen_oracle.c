@@ -362,6 +362,28 @@ void orc_osc_process(orc_osc *o) {
     o->phase = fmodf(o->phase, 1.0f);
 }
 
+/* ============================================================ SamplePlayer == */
+/* sample_player/mod.rs:77-84 */
+void orc_sample_player_new(orc_sample_player *p) { memset(p, 0, sizeof *p); }
+/* sample_player/mod.rs:36-49 with F = f32 (F::CHANNELS == 1): sc = 0 for a mono file, else min(0, src_ch - 1) = 0 */
+void orc_sample_player_build_mono(float *dst, const float *interleaved, size_t frames, size_t channels) {
+    for (size_t t = 0; t < frames; ++t) dst[t] = interleaved[t * channels];
+}
+void orc_sample_player_publish(orc_sample_player *p, const float *samples, size_t frames) {
+    p->pending = samples; p->pending_len = frames; p->has_pending = 1;
+}
+/* sample_player/mod.rs:104-127 */
+void orc_sample_player_process(orc_sample_player *p) {
+    if (p->has_pending) {                       /* buf.take(): swap, reset the playhead */
+        p->current = p->pending; p->current_len = p->pending_len; p->has_pending = 0;
+        p->playhead = 0;
+    }
+    if (p->current_len == 0) { p->output = 0.0f; return; }
+    p->output = p->current[p->playhead];
+    p->playhead += 1;
+    if (p->playhead >= p->current_len) p->playhead = 0;
+}
+
 /* ============================================================== FmOperator == */
 /* fm_operator.rs:35-49 */
 void orc_fmop_new(orc_fmop *o) {

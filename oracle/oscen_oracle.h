@@ -149,6 +149,21 @@ void orc_delay_prepare(orc_delay *d);
 void orc_delay_process(orc_delay *d);
 void orc_delay_free(orc_delay *d);
 
+/* -------------------------------------------------------- SamplePlayer -- */
+/* oscen-lib/src/sample_player/mod.rs:64-127 (mono, F = f32).  `pending` stands for the handoff slot: a buffer published
+   by orc_sample_player_publish is picked up by the next process(), which resets the playhead */
+typedef struct {
+    float output;
+    const float *current; size_t current_len;
+    const float *pending; size_t pending_len; int has_pending;
+    size_t playhead;
+} orc_sample_player;
+void orc_sample_player_new(orc_sample_player *p);
+/* SamplePlayerConsumer::build for F = f32 (mod.rs:36-49): channel 0 of an interleaved source; `dst` holds `frames` floats */
+void orc_sample_player_build_mono(float *dst, const float *interleaved, size_t frames, size_t channels);
+void orc_sample_player_publish(orc_sample_player *p, const float *samples, size_t frames);   /* the caller keeps `samples` alive */
+void orc_sample_player_process(orc_sample_player *p);
+
 /* -------------------------------------------------- halfband FIR cascade -- */
 /* oscen-lib/src/resample/sinc_fir.rs:95-266, coeffs.rs:17-34 */
 typedef struct { float history[24]; size_t head; } orc_hb_down;   /* Halfband2xDownStage */

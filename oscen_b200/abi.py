@@ -40,7 +40,7 @@ SYMBOLS = [
     "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
     "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
-    "oscen_b200_graph_kernel_info",
+    "oscen_b200_graph_kernel_info", "oscen_b200_graph_n_assets", "oscen_b200_graph_asset_id", "oscen_b200_load_asset",
 ]
 
 
@@ -138,6 +138,10 @@ def load():
     L.oscen_b200_graph_has_midi.argtypes = [vp]
     L.oscen_b200_graph_codegen.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_jit_check.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.oscen_b200_graph_n_assets.argtypes = [vp]
+    L.oscen_b200_graph_n_assets.restype = C.c_uint32
+    L.oscen_b200_graph_asset_id.argtypes = [vp, C.c_char_p]
+    L.oscen_b200_load_asset.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     L.oscen_b200_graph_kernel_info.argtypes = [vp, C.c_float, C.POINTER(KernelInfo), C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
     _lib = L
     return L
@@ -221,6 +225,16 @@ class Graph:
         if i < 0:
             raise KeyError(name)
         return i
+
+    def asset_id(self, name):
+        """index of the `external NAME: AudioAsset;` slot"""
+        i = self.L.oscen_b200_graph_asset_id(self.h, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def n_assets(self):
+        return self.L.oscen_b200_graph_n_assets(self.h)
 
     def input_info(self, input_id):
         info = InputInfo()
@@ -346,6 +360,19 @@ class Engine:
         msgs = np.ascontiguousarray(msgs)
         if msgs.size:
             self._chk(self.L.oscen_b200_push_midi_batch(self.h, msgs.ctypes.data, msgs.size), "push_midi_batch")
+
+    def load_asset(self, slot, samples):
+        """graph.<slot>.load(..): samples [frames] (mono) or [frames][channels] f32 at the engine's sample rate; every
+        SamplePlayer bound to the slot restarts at the next block.  `slot`: name (DSL engines) or index."""
+        if isinstance(slot, str):
+            if self.graph is None:
+                raise EngineError("load_asset by name needs an engine created from a DSL graph")
+            slot = self.graph.asset_id(slot)
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        if a.ndim == 1:
+            a = a[:, None]
+        assert a.ndim == 2
+        self._chk(self.L.oscen_b200_load_asset(self.h, slot, a.ctypes.data if a.size else None, a.shape[0], max(a.shape[1], 1)), "load_asset")
 
     def stream_in(self, input_id, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32)

@@ -191,6 +191,18 @@ struct Emitter {
                 line(1, "float *ring" + std::to_string(i) + " = a.state + (size_t)(" + base + " + 3u) * n + vs;    /* [" + std::to_string(nd.ring_cap) + " slots][voices] */");
                 line(1, "float " + S(i) + " = " + N(i) + ".output;    /* persists across frames: a feedback edge reads the previous frame's value */");
                 break;
+            case T::SamplePlayer: {
+                /* the playhead restarts when the slot was (re)loaded since the last block; a slot that shrank below an old
+                   playhead cannot be read out of range either way */
+                const std::string k = std::to_string(nd.asset);
+                if (nd.asset >= 0) {
+                    line(1, "const float *buf" + std::to_string(i) + " = a.assets->data[" + k + "]; const uint32_t len" + std::to_string(i) + " = a.assets->frames[" + k + "];");
+                    line(1, "uint32_t " + N(i) + " = a.assets->reset[" + k + "] ? 0u : __float_as_uint(a.state[(size_t)" + base + " * n + vs]);");
+                    line(1, "if (" + N(i) + " >= len" + std::to_string(i) + ") " + N(i) + " = 0u;");
+                } else {
+                    line(1, "const float *buf" + std::to_string(i) + " = nullptr; const uint32_t len" + std::to_string(i) + " = 0u; uint32_t " + N(i) + " = 0u;    /* `buf` is not connected: silence */");
+                }
+            } break;
             case T::Up: case T::Down:
                 line(1, edge_type(i) + " " + N(i) + "; " + N(i) + ".load(a.state, " + base + ", n, vs, dyn + " + std::to_string(smem_off) + "u * kCta);");
                 smem_off += edge_smem_floats(nd);
@@ -287,6 +299,7 @@ struct Emitter {
                 line(ind, S(i) + " = delay_process<" + (P_is_const(i, 0) ? "false" : "true") + ", " + (P_is_const(i, 1) ? "false" : "true") + ">(" + N(i) + ", ring" + std::to_string(i) +
                           ", (size_t)n, " + std::to_string(nd.ring_cap) + "u, " + lit(nd.max_delay) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ");" + cm);
                 break;
+            case T::SamplePlayer: line(ind, o + "sample_player_process(" + N(i) + ", buf" + std::to_string(i) + ", len" + std::to_string(i) + ");" + cm); break;
             case T::Gain: line(ind, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
             case T::AddValue: line(ind, o + IN(i, 0, -1) + " + " + P(i, 0) + ";" + cm); break;
             case T::Mixer: line(ind, o + IN(i, 0, -1) + " + " + IN(i, 1, -1) + ";" + cm); break;
@@ -377,6 +390,7 @@ struct Emitter {
                 line(2, "a.state[(size_t)(" + base + " + 0u) * n + v] = __uint_as_float(" + N(i) + ".write_pos); a.state[(size_t)(" + base + " + 1u) * n + v] = __uint_as_float(" + N(i) +
                         ".counter); a.state[(size_t)(" + base + " + 2u) * n + v] = " + N(i) + ".output;");
                 break;
+            case T::SamplePlayer: line(2, "a.state[(size_t)" + base + " * n + v] = __uint_as_float(" + N(i) + ");"); break;
             case T::Up: case T::Down: line(2, N(i) + ".store(a.state, " + base + ", n, v);"); break;
             default:
                 if (is_polyblep(nd.type)) line(2, "a.state[(size_t)" + base + " * n + v] = " + N(i) + ";");

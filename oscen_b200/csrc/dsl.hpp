@@ -30,8 +30,11 @@
  * Polyphony: a text may hold several `graph! { }` blocks; an outer graph of the reference's polyphonic
  * shape (voices = [Voice::new(); N] + the MIDI chain) lowers to the voice graph's plan (lower_polyphonic).
  *
+ * Assets: `external NAME: AudioAsset;` declares a slot the host loads audio into at run time
+ * (oscen_b200_load_asset); `NAME -> player.buf` binds it to a SamplePlayer (generated kernels only).
+ *
  * Reported as errors (never silently ignored): `/ N` rates, mixed factors, node arrays outside the
- * polyphonic shape, nested scalar graphs, `external` assets, typed endpoints, free-function calls in
+ * polyphonic shape, externals other than AudioAsset, typed endpoints, free-function calls in
  * sources (they name user Rust code).
  *
  * Host-only C++, no CUDA types: unit-tested on the CPU through oscen_b200_graph_compile().
@@ -206,8 +209,10 @@ struct InputDecl { Kind kind; std::string name; bool has_def = false; float def 
 struct OutputDecl { Kind kind; std::string name; Tok at; };
 struct NodeDecl { std::string name, type, ctor; std::vector<float> args; bool args_ok = true; bool bare = false; int array = 0; int rate = 0; Tok at; };
 struct Conn { std::string policy; ExprP src, dst; int via = 0; /* 0 none, 1 samples, 2 node */ float via_samples = 0.0f; std::string via_node; Tok at; };
+struct ExternalDecl { std::string name, type; Tok at; };     /* `external sample: AudioAsset;` (parse.rs:447-456) */
 struct Ast {
     std::string name;
+    std::vector<ExternalDecl> externals;
     std::vector<InputDecl> inputs;
     std::vector<OutputDecl> outputs;
     std::vector<NodeDecl> nodes;
@@ -295,7 +300,11 @@ private:
         } else if (t.s == "nih_params") { ++pos; expect(";");
         } else if (t.s == "input") { ++pos; input_decl(ast);
         } else if (t.s == "output") { ++pos; output_decl(ast);
-        } else if (t.s == "external") { err.at(t, "`external` asset slots are not supported by the node plan");
+        } else if (t.s == "external") {
+            ++pos;
+            ExternalDecl d; d.at = t;
+            if (!ident(d.name, "the name of the external slot") || !expect(":") || !ident(d.type, "the slot's type (AudioAsset)")) return;
+            if (expect(";")) ast.externals.push_back(d);
         } else if (t.s == "node" || t.s == "nodes") {
             ++pos;
             if (accept("{")) { while (!err.set && !is_punct("}") && cur().kind != Tok::End) { if (accept(";")) continue; node_decl(ast); } expect("}"); }
@@ -523,7 +532,7 @@ struct TypeInfo {
 };
 
 /* endpoints as the reference structs declare them (#[input(..)] / #[output(..)] fields):
-   oscen-lib/src/{envelope/adsr.rs:20-38, filters/tpt/mod.rs:12-24, oscillators/mod.rs:88-103, gain/mod.rs:5-12},
+   oscen-lib/src/{envelope/adsr.rs:20-38, filters/tpt/mod.rs:12-24, oscillators/mod.rs:88-103, gain/mod.rs:5-12, sample_player/mod.rs:64-72},
    examples/fm-synth/src/nodes/{fm_operator.rs:12-31, crossfade.rs:8-18, mixer.rs:4-12, add_value.rs:5-13},
    examples/nih-twin-peaks/src/lp18_filter.rs:7-42, examples/oversampled-saturator/src/main.rs:31-38.
    `standin` = parameter slot read when a stream input has no stream source; `def` = the field's constructor default. */
@@ -552,6 +561,7 @@ inline const TypeInfo *type_info(const std::string &type) {
         {"Crossfade", {{"input", Kind::Stream, false, 0, -1, 0}, {"mix", Kind::Value, false, 0, -1, 0}, {"output_a", Kind::Stream, true, 0, -1, 0},
                        {"output_b", Kind::Stream, true, 1, -1, 0}}, false},
         {"HardClip", {{"input", Kind::Stream, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
+        {"SamplePlayer", {{"buf", Kind::Asset, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
     };
     for (const TypeInfo &t : reg) if (type == t.type) return &t;
     return nullptr;
@@ -565,7 +575,7 @@ inline std::string node_library_text() {
         {"PolyBlepOscillator", "sine(frequency, amplitude) | saw(..) | square(..) | triangle(..)"},
         {"LP18Filter", "new(cutoff, resonance)"}, {"IirLowpass", "new(cutoff, q)"}, {"Oscillator", "sine(frequency, amplitude) | square(..) | saw(..)"},
         {"Delay", "new(delay_samples, feedback) | from_seconds(seconds, feedback, sample_rate)"}, {"Gain", "new(gain)"}, {"AddValue", "new(value)"},
-        {"Mixer", "new()"}, {"Crossfade", "new()"}, {"HardClip", "new()"}};
+        {"Mixer", "new()"}, {"Crossfade", "new()"}, {"HardClip", "new()"}, {"SamplePlayer", "new()"}};
     std::string out;
     for (const auto &c : ctors) {
         const TypeInfo *ti = type_info(c[0]);
@@ -575,6 +585,7 @@ inline std::string node_library_text() {
             char b[128];
             if (ep.is_out) snprintf(b, sizeof b, "    output %s: %s\n", ep.name, "stream");
             else if (ep.kind == Kind::Event) snprintf(b, sizeof b, "    input  %s: event\n", ep.name);
+            else if (ep.kind == Kind::Asset) snprintf(b, sizeof b, "    input  %s: asset (an `external NAME: AudioAsset;` slot; unconnected: silence)\n", ep.name);
             else snprintf(b, sizeof b, "    input  %s: %s (unconnected: %s)\n", ep.name, ep.kind == Kind::Value ? "value" : "stream",
                           (std::string(c[1]).find(ep.name) != std::string::npos) ? "the constructor argument" : (std::to_string(ep.def).c_str()));
             out += b;
@@ -617,6 +628,13 @@ public:
                 g.event_input = d.name; break;
             default: err.at(d.at, "asset inputs are not supported by the node plan"); return false;
             }
+        }
+        /* `external NAME: AudioAsset;` — a slot the host loads audio into at run time (oscen_b200_load_asset) */
+        for (const ExternalDecl &d : ast.externals) {
+            if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
+            if (d.type != "AudioAsset") { err.at(d.at, "external `" + d.name + "`: only AudioAsset slots are supported (found `" + d.type + "`)"); return false; }
+            if (g.assets.size() >= 4) { err.at(d.at, "more than 4 external asset slots (OSCEN_B200_MAX_ASSETS)"); return false; }
+            names[d.name] = 'x'; g.assets.push_back(d.name);
         }
         for (const OutputDecl &d : ast.outputs) {
             if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
@@ -677,7 +695,7 @@ private:
             g.inner_log2 = rate_log2;
         }
         const TypeInfo *ti = type_info(d.type);
-        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (known: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, Oscillator, LP18Filter, IirLowpass, Delay, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
+        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (known: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, Oscillator, LP18Filter, IirLowpass, Delay, SamplePlayer, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
         if (!d.args_ok) { err.at(d.at, "constructor arguments of `" + d.name + "` must be numeric literals"); return false; }
         plan::Node n{};
         n.name = d.name; n.gate = false; n.rate_log2 = rate_log2;
@@ -726,6 +744,7 @@ private:
         else if (t == "Mixer") { n.type = plan::NodeType::Mixer; ok = ctor("new", 0); }
         else if (t == "Crossfade") { n.type = plan::NodeType::Crossfade; ok = ctor("new", 0); }
         else if (t == "HardClip") { n.type = plan::NodeType::HardClip; ok = ctor("new", 0); }
+        else if (t == "SamplePlayer") { n.type = plan::NodeType::SamplePlayer; ok = ctor("new", 0); }
         if (err.set) return false;
         if (!ok) { err.at(d.at, "unknown constructor `" + d.type + "::" + d.ctor + "`"); return false; }
         names[d.name] = 'n'; node_id[d.name] = (int)g.nodes.size();
@@ -819,6 +838,7 @@ private:
             if (it == names.end()) { err.at(e.at, "cannot resolve the source of this connection (unknown node or endpoint name `" + e.name + "`?)"); return false; }
             if (it->second == 'o') { err.at(e.at, "graph output `" + e.name + "` cannot be a connection source"); return false; }
             if (it->second == 'n') { err.at(e.at, "`" + e.name + "` is a node: name one of its outputs (`" + e.name + ".output`)"); return false; }
+            if (it->second == 'x') { err.at(e.at, "`" + e.name + "` is an external asset slot: it connects to an asset endpoint only (`" + e.name + " -> player.buf`)"); return false; }
             if (e.name == g.stream_input) { out.k = Operand::Stream; out.s.node = plan::kGraphInput; out.s.port = 0; return true; }
             if (e.name == g.event_input) { is_event = true; return true; }
             out.k = Operand::Value; out.pid = value_id[e.name]; return true;
@@ -862,6 +882,19 @@ private:
     }
 
     bool connection(const Conn &c) {
+        /* `sample -> player.buf`: an external asset slot bound to a node's asset endpoint (not a per-frame edge: the node
+           reads whatever buffer the slot holds, sample_player/mod.rs:104-112) */
+        if (c.src->k == Expr::Ident && names.count(c.src->name) && names[c.src->name] == 'x') {
+            const Expr &d = *c.dst;
+            if (c.via) { err.at(c.at, "a `-> [..] ->` edge carries a stream"); return false; }
+            if (d.k != Expr::Field || d.a->k != Expr::Ident || !node_id.count(d.a->name)) { err.at(d.at, "an external asset connects to a node's asset endpoint (`" + c.src->name + " -> player.buf`)"); return false; }
+            const int nid = node_id[d.a->name];
+            const Endpoint *ep = find_ep(nid, d.name);
+            if (!ep) { err.at(d.at, "node `" + d.a->name + "` has no endpoint `" + d.name + "`"); return false; }
+            if (ep->is_out || ep->kind != Kind::Asset) { err.at(c.at, std::string("Type mismatch in connection: source is Asset but destination expects ") + kind_name(ep->kind)); return false; }
+            for (size_t k = 0; k < g.assets.size(); ++k) if (g.assets[k] == c.src->name) g.nodes[nid].asset = (int)k;
+            return true;
+        }
         Operand src; bool src_event = false;
         if (!source(*c.src, src, src_event)) return false;
         if (c.via) {
@@ -916,6 +949,7 @@ private:
         if (ep->is_out) { err.at(d.at, "`" + d.a->name + "." + d.name + "` is an output: it cannot be a connection destination"); return false; }
         plan::Node &n = g.nodes[nid];
         switch (ep->kind) {
+        case Kind::Asset: return mismatch(Kind::Asset);
         case Kind::Event:
             if (sk != Kind::Event) return mismatch(Kind::Event);
             n.gate = true; return true;
@@ -1122,6 +1156,7 @@ struct Inliner {
     bool flatten(const Ast &g, Ast &out) {
         if (++depth > 16) { Tok t; err.at(t, "nested graphs: recursion deeper than 16 levels (a graph that contains itself?)"); return false; }
         out.name = g.name;
+        for (const ExternalDecl &d : g.externals) out.externals.push_back(d);
         for (const InputDecl &d : g.inputs) out.inputs.push_back(d);
         for (const OutputDecl &d : g.outputs) out.outputs.push_back(d);
         std::vector<const NodeDecl *> nested;
@@ -1140,6 +1175,7 @@ struct Inliner {
             if (nd->ctor != "new" || !nd->args.empty()) { err.at(nd->at, "a graph is instantiated with `" + nd->type + "` or `" + nd->type + "::new()`"); return false; }
             Ast child;
             { Inliner sub{all, err, depth}; if (!sub.flatten(*find_graph(all, nd->type), child)) return false; }
+            if (!child.externals.empty()) { err.at(nd->at, "nested graph `" + nd->type + "` declares an `external` asset slot: declare it in the top-level graph"); return false; }
             const std::string &inst = nd->name;
             /* what the parent connects INTO the instance, per child input (statement order) */
             std::map<std::string, std::vector<ExprP>> bound;
@@ -1361,6 +1397,12 @@ inline std::string describe(const plan::Graph &g, const plan::Plan &p) {
     if (g.vpi) s += "polyphony: " + std::to_string(g.vpi) + " voices per instance" + (g.midi ? ", MIDI front -> frequency = input " + std::to_string(g.midi_freq_input) + ", gate" : "") + "\n";
     if (!g.stream_input.empty()) s += "stream input: " + g.stream_input + "\n";
     if (!g.event_input.empty()) s += "event input: " + g.event_input + "\n";
+    for (size_t k = 0; k < g.assets.size(); ++k) {
+        s += "external " + std::to_string(k) + ": " + g.assets[k] + " (AudioAsset) ->";
+        bool any = false;
+        for (const plan::Node &nd : g.nodes) if (nd.asset == (int)k) { s += std::string(any ? ", " : " ") + nd.name + ".buf"; any = true; }
+        s += any ? "\n" : " (not connected)\n";
+    }
     s += "output: " + g.output_name + " <- " + g.nodes[g.output.node].name + "\n";
     s += "state words per voice: " + std::to_string(g.n_state) + "\n";
     for (size_t k = 0; k < p.launches.size(); ++k) {

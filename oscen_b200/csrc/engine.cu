@@ -171,6 +171,12 @@ struct oscen_b200_engine {
     bool has_stream_in = false;          /* the graph declares a per-voice stream input */
     uint32_t lcg_field = 0;              /* first of the two state words of the device-side input LCG */
     jit::Kernel jit;                     /* DSL-compiled graph, PLAN_FUSED: the kernel codegen.hpp generated, compiled by NVRTC */
+    /* `external NAME: AudioAsset;` slots of a DSL graph (engine_types.h AssetTable) */
+    uint32_t n_assets = 0;
+    AssetTable h_assets{};
+    AssetTable *d_assets = nullptr;
+    float *d_asset_buf[kMaxAssets] = {};
+    bool asset_reset_pending = false;    /* a slot was loaded since the last block: its players restart, then the flags are cleared */
 
     /* node plan */
     plan::Graph graph;
@@ -295,6 +301,7 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
     a.stream_in = e->stream_in_ptr;
     a.voice_out = e->d_voice_out; a.inst_out = e->d_inst_out; a.inst_state = e->d_inst_state;
     a.mix_partial = e->d_mix_partial;
+    a.assets = e->d_assets;
     for (uint32_t i = 0; i < kMaxInputs; ++i) a.u.p[i] = e->uni[i];
     a.u.sr = e->cfg.sample_rate;
     if (e->cfg.graph_kind == OSCEN_B200_GRAPH_FM_VOICE) {
@@ -515,6 +522,8 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evk) cudaEventDestroy(e->evk);
     cudaFree(e->d_flush);
+    cudaFree(e->d_assets);
+    for (float *b : e->d_asset_buf) cudaFree(b);
     cudaFree(e->d_midi_msgs); cudaFree(e->d_midi_keys_in); cudaFree(e->d_midi_keys); cudaFree(e->d_midi_idx_in); cudaFree(e->d_midi_idx);
     cudaFree(e->d_cub_tmp); cudaFree(e->d_alloc_word); cudaFree(e->d_alloc_age); cudaFree(e->d_alloc_cur_age);
     cudaFree(e->d_h_note); cudaFree(e->d_h_freq); cudaFree(e->d_note_freq);
@@ -553,6 +562,10 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
                 g_create_error = "PLAN_NODES: the feedback edge into `" + nd.name + "` needs the per-sample walk (node kernels render whole blocks): set plan = OSCEN_B200_PLAN_FUSED";
                 return OSCEN_B200_E_ARG;
             }
+        if (cfg->plan == OSCEN_B200_PLAN_NODES)
+            for (const plan::Node &nd : pg.nodes) if (nd.type == plan::NodeType::SamplePlayer) {
+                g_create_error = "PLAN_NODES: `" + nd.name + "` (SamplePlayer) runs in a generated kernel: set plan = OSCEN_B200_PLAN_FUSED"; return OSCEN_B200_E_ARG;
+            }
         if (cfg->plan == OSCEN_B200_PLAN_FUSED) {
             /* generate the fused kernel and compile it for sm_100a before any device memory is taken */
             jk.source = codegen::fused_kernel_source(pg, pp, kJitKernelName);
@@ -585,6 +598,7 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         e->midi_ok = pg.midi; e->midi_freq_input = pg.midi_freq_input;
         e->n_inputs = (uint32_t)pg.inputs.size();
         e->lcg_field = pg.n_state; e->n_state = pg.n_state + (e->has_stream_in ? 2u : 0u);
+        e->n_assets = (uint32_t)pg.assets.size();
         if (e->n_state == 0) e->n_state = 1;                      /* stateless graph: keep the allocation non-empty */
     } else {
         e->n_inputs = kind < 7 ? kNInputs[kind] : 0u; e->n_state = n_state_of(kind);
@@ -598,6 +612,10 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         CK(e, cudaSetDevice(cfg->device));
         CK(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         CK(e, cudaMalloc(&e->d_pv, (size_t)std::max<uint32_t>(e->n_inputs, 1u) * n * sizeof(float)));
+        if (e->n_assets) {                                         /* every slot starts empty: its players are silent */
+            CK(e, cudaMalloc(&e->d_assets, sizeof(AssetTable)));
+            CK(e, cudaMemset(e->d_assets, 0, sizeof(AssetTable)));
+        }
         CK(e, cudaMalloc(&e->d_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
         CK(e, cudaMallocHost(&e->h_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
         CK(e, cudaMalloc(&e->d_state, (size_t)e->n_state * n * sizeof(float)));
@@ -693,6 +711,12 @@ int oscen_b200_graph_describe(const oscen_b200_graph *g, char *dst, size_t cap) 
 uint32_t oscen_b200_graph_voices_per_instance(const oscen_b200_graph *g) { return g ? (g->g.vpi ? g->g.vpi : 1u) : 0u; }
 int oscen_b200_graph_has_midi(const oscen_b200_graph *g) { return g && g->g.midi ? 1 : 0; }
 uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g) { return g ? (uint32_t)g->g.inputs.size() : 0u; }
+uint32_t oscen_b200_graph_n_assets(const oscen_b200_graph *g) { return g ? (uint32_t)g->g.assets.size() : 0u; }
+int oscen_b200_graph_asset_id(const oscen_b200_graph *g, const char *name) {
+    if (!g || !name) return OSCEN_B200_E_ARG;
+    for (size_t i = 0; i < g->g.assets.size(); ++i) if (g->g.assets[i] == name) return (int)i;
+    return OSCEN_B200_E_ARG;
+}
 int oscen_b200_graph_input_id(const oscen_b200_graph *g, const char *name) {
     if (!g || !name) return OSCEN_B200_E_ARG;
     for (const auto &al : g->g.aliases) if (al.first == name) return (int)al.second;      /* the outer graph's names first */
@@ -1125,8 +1149,41 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             if (e->ramps[i].remaining == 0) { rc = fill_row(e, i, 0, n, e->uni[i]); if (rc) return rc; }
         }
     }
+    if (e->asset_reset_pending) {
+        /* the block just enqueued restarted the players of the freshly loaded slots; later blocks carry on (stream order) */
+        for (uint32_t k = 0; k < kMaxAssets; ++k) e->h_assets.reset[k] = 0u;
+        CK(e, cudaMemcpyAsync(e->d_assets, &e->h_assets, sizeof(AssetTable), cudaMemcpyHostToDevice, e->stream));
+        e->asset_reset_pending = false;
+    }
     e->last_frames = frames;
     e->stats.blocks++;
+    return 0;
+}
+
+/* graph.<slot>.load(..) (oscen-lib/src/asset/mod.rs; sample_player/mod.rs:36-49,104-112): publish a new buffer into an
+   `external NAME: AudioAsset;` slot.  `interleaved` holds frames x channels f32 at the engine's sample rate (decoding and
+   rate conversion stay with the caller); a mono SamplePlayer takes channel 0.  Every player bound to the slot restarts at
+   the next block, for every voice of the engine.  frames == 0 empties the slot (silence).  Synchronises the stream. */
+int oscen_b200_load_asset(oscen_b200_engine *e, uint32_t asset_id, const float *interleaved, uint32_t frames, uint32_t channels) {
+    if (!e) return OSCEN_B200_E_ARG;
+    if (asset_id >= e->n_assets) return arg_error(e, "load_asset: the graph declares no such external slot");
+    if (frames && (!interleaved || channels == 0)) return arg_error(e, "load_asset: null samples / zero channels");
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaStreamSynchronize(e->stream));                       /* no block in flight still reads the old buffer */
+    float *fresh = nullptr;
+    if (frames) {
+        std::vector<float> mono(frames);
+        for (uint32_t t = 0; t < frames; ++t) mono[t] = interleaved[(size_t)t * channels];
+        CK(e, cudaMalloc(&fresh, (size_t)frames * sizeof(float)));
+        const cudaError_t c = cudaMemcpy(fresh, mono.data(), (size_t)frames * sizeof(float), cudaMemcpyHostToDevice);
+        if (c != cudaSuccess) { cudaFree(fresh); CK(e, c); }
+        e->stats.h2d_bytes += (uint64_t)frames * sizeof(float);
+    }
+    cudaFree(e->d_asset_buf[asset_id]);
+    e->d_asset_buf[asset_id] = fresh;
+    e->h_assets.data[asset_id] = fresh; e->h_assets.frames[asset_id] = frames; e->h_assets.reset[asset_id] = 1u;
+    CK(e, cudaMemcpy(e->d_assets, &e->h_assets, sizeof(AssetTable), cudaMemcpyHostToDevice));
+    e->asset_reset_pending = true;
     return 0;
 }
 

@@ -52,6 +52,17 @@ enum : uint32_t { EP_CUR = 0, EP_TGT = 32, EP_DEC = 64, EP_REL = 96, EP_ORE = 12
                   EP_MRE = 192, EP_MIM = 224, EP_RELEASED = 256, EP_STEP = 257, EP_LASTF = 258,
                   EP_NSTATE = 259 };
 
+/* `external NAME: AudioAsset;` slots of a DSL graph: one mono buffer per slot, shared by every voice of the engine (the
+   reference's AssetSlot holds one Arc<Vec<f32>> per graph instance; a bank plays one sample set).  Lives in device memory
+   so that a load between blocks changes no kernel argument.  `reset[k]` is set for the first block after a load: the
+   next process() picks the buffer up and restarts its playhead (sample_player/mod.rs:107-112). */
+constexpr uint32_t kMaxAssets = 4;
+struct AssetTable {
+    const float *data[kMaxAssets];
+    uint32_t frames[kMaxAssets];
+    uint32_t reset[kMaxAssets];
+};
+
 struct Uniform {
     float p[kMaxInputs];                 /* uniform value of every value input */
     AdsrDerived env[4];                  /* host-derived ADSR step data for uniform a/d/r */
@@ -73,6 +84,7 @@ struct KernelArgs {
     float *inst_out;                     /* [512][n_inst][channels] or null */
     float *inst_state;                   /* [n_inst] instance-level state (EPIANO tremolo phase) */
     float *mix_partial;                  /* [n_cta][512][channels] */
+    const AssetTable *assets;            /* DSL graphs with `external` slots, else null */
     Uniform u;
 };
 

@@ -585,4 +585,15 @@ OSC_D void tremolo_process(float &phase, float input, float rate, float depth, f
     phase = fractf(phase + inc);
 }
 
+/* ---- SamplePlayer, mono (oscen-lib/src/sample_player/mod.rs:104-127): loops the slot's buffer; an empty / never
+   loaded slot is silence.  The swap-and-reset of `buf.take()` is the caller's `playhead = 0` on the first block after a
+   load (engine_types.h AssetTable::reset). */
+OSC_HD float sample_player_process(uint32_t &playhead, const float *buf, uint32_t len) {
+    if (len == 0u) return 0.0f;
+    const float y = buf[playhead];
+    playhead += 1u;
+    if (playhead >= len) playhead = 0u;
+    return y;
+}
+
 }  // namespace oscen

@@ -48,6 +48,8 @@ enum class NodeType : uint8_t {
                       graphs WITH a feedback edge run as generated kernels only */
     Up,            /* cross-rate stream edge outer -> inner (`* N` destination): StreamUpsampler of `policy`   */
     Down,          /* cross-rate stream edge inner -> outer: StreamDownsampler of `policy` (generated kernels only) */
+    SamplePlayer,  /* SamplePlayer (mono): loops the buffer loaded into asset slot `asset` (`external s: AudioAsset; s -> p.buf`);
+                      generated kernels only */
 };
 enum : int { kPolicySinc = 0, kPolicySincIir = 1, kPolicyLinear = 2, kPolicyLatch = 3 };   /* == OSCEN_B200_POLICY_* */
 
@@ -91,6 +93,7 @@ struct Node {
     int policy = 0;                  /* Up / Down: connection policy (kPolicy*) */
     uint32_t ring_cap = 0;           /* Delay: ring capacity in samples (power of two), set by assign_state_layout() */
     float max_delay = 0.0f;          /* Delay: the reference ring's capacity - 1 (the clamp of apply_parameter_updates) */
+    int asset = kNone;               /* SamplePlayer: index of the `external` asset slot connected to `buf` (kNone: never loaded, silent) */
 };
 
 /* a value input of a DSL-compiled graph (`input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];`) */
@@ -116,6 +119,7 @@ struct Graph {
     bool midi = false;               /* midi_in -> MidiParser -> VoiceAllocator<N> -> [MidiVoiceHandler; N] feeds the voices */
     uint32_t midi_freq_input = 0;    /* the voice input `voice_handlers.frequency` is connected to */
     std::vector<std::pair<std::string, uint32_t>> aliases;   /* outer value-input name -> voice input id (broadcast edges) */
+    std::vector<std::string> assets; /* `external NAME: AudioAsset;` slots in declaration order (engine: oscen_b200_load_asset) */
 };
 
 struct Launch {
@@ -146,10 +150,11 @@ inline uint32_t n_state_words(const Node &nd) {
     case NodeType::IirLowpass: return 8;      /* b0 b1 b2 a1 a2 v1 v2 frame_counter */
     case NodeType::OscSine: case NodeType::OscSquare: case NodeType::OscSaw: return 1;
     case NodeType::Delay: return 3u + nd.ring_cap;   /* write_pos frame_counter output + the ring */
+    case NodeType::SamplePlayer: return 1;    /* playhead */
     default: return 0;
     }
 }
-inline bool node_plan_has_kernel(NodeType t) { return t != NodeType::Up && t != NodeType::Down; }
+inline bool node_plan_has_kernel(NodeType t) { return t != NodeType::Up && t != NodeType::Down && t != NodeType::SamplePlayer; }
 /* Delay::prepare (delay/mod.rs:59-69): RingBuffer::new(min((2 * sr) as usize, 88200)) in PowerOfTwo mode */
 inline uint32_t delay_reference_capacity(float sample_rate) {
     const float t = 2.0f * sample_rate;
@@ -221,6 +226,7 @@ inline const char *type_name(NodeType t) {
     case NodeType::Delay: return "Delay";
     case NodeType::Up: return "UpEdge";
     case NodeType::Down: return "DownEdge";
+    case NodeType::SamplePlayer: return "SamplePlayer";
     case NodeType::Lp18: return "LP18Filter";
     case NodeType::Gain: return "Gain";
     case NodeType::AddValue: return "AddValue";

@@ -182,6 +182,14 @@ public:
     /* set_<name>_immediate(v) / set_<name>_with_ramp(v, frames) */
     void set_immediate(const std::string &name, float v) { set_value(input(name), v); }
     void set_with_ramp(const std::string &name, float v, uint32_t frames) { set_value_with_ramp(input(name), v, frames); }
+    /* graph.<slot>.load(..) of an `external <slot>: AudioAsset;` (asset/mod.rs): frames x channels f32 at the bank's sample
+       rate; the SamplePlayers bound to the slot restart at the next block */
+    void load_asset(const std::string &slot, const std::vector<float> &interleaved, uint32_t channels = 1) {
+        const int id = oscen_b200_graph_asset_id(g_, slot.c_str());
+        if (id < 0) throw std::runtime_error("graph has no external slot `" + slot + "`");
+        const uint32_t ch = channels ? channels : 1u;
+        check(oscen_b200_load_asset(raw(), (uint32_t)id, interleaved.data(), (uint32_t)(interleaved.size() / ch), ch), raw(), "load_asset");
+    }
     std::string describe() const {
         std::string s(1 << 16, '\0');
         oscen_b200_graph_describe(g_, &s[0], s.size());

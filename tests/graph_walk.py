@@ -129,6 +129,22 @@ def delay(delay_samples, feedback, sr):
     return Node(st, L.orc_delay_process)
 
 
+def sample_player():
+    """SamplePlayer::new() (mono); .publish(array) = the slot's load handle, picked up by the next process()"""
+    L = O.lib()
+    st = O.SamplePlayer()
+    L.orc_sample_player_new(C.byref(st))
+    n = Node(st, L.orc_sample_player_process)
+    n._bufs = []
+
+    def publish(samples):
+        a = np.ascontiguousarray(samples, dtype=np.float32)
+        n._bufs.append(a)                                   # the oracle borrows the memory
+        L.orc_sample_player_publish(C.byref(st), a.ctypes.data, a.size)
+    n.publish = publish
+    return n
+
+
 def render(make_voice, n_voices, frames, values=None, gates=None, stream_in=None):
     """make_voice(v) -> (frame_fn, gate_fn); frame_fn(values_of_voice: dict, x: f32) -> f32 output;
     gate_fn(scalar) handles a gate event BEFORE that frame's process (derive(Node) process_event_inputs).

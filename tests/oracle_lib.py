@@ -82,6 +82,11 @@ class Delay(C.Structure):
                                                                                          ("frames_per_update", C.c_size_t), ("frame_counter", C.c_size_t)]
 
 
+class SamplePlayer(C.Structure):
+    _fields_ = [("output", C.c_float), ("current", C.c_void_p), ("current_len", C.c_size_t), ("pending", C.c_void_p),
+                ("pending_len", C.c_size_t), ("has_pending", C.c_int), ("playhead", C.c_size_t)]
+
+
 class NaiveOsc(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("phase", "frequency", "frequency_mod", "amplitude", "output")] + [("waveform", C.c_int), ("sample_rate", C.c_float)]
 
@@ -154,6 +159,8 @@ def lib():
         L.orc_iirlp_new.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.orc_delay_new.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.orc_osc_new.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int]
+        L.orc_sample_player_publish.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_sample_player_build_mono.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
         L.orc_ring_init.argtypes = [C.c_void_p, C.c_size_t]
         L.orc_ring_push.argtypes = [C.c_void_p, C.c_float]
         L.orc_ring_get.argtypes = [C.c_void_p, C.c_float]

@@ -177,7 +177,16 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
     ("output stream out; output stream out2; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "one stream output per graph"),
     ("output stream out; input a: stream; input b: stream; connection a -> out;", "one stream input per graph"),
     ("input audio: stream: Frame<2>; output stream out; connection audio -> out;", "typed endpoints"),
-    ("output stream out; external ir: AudioAsset; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "`external` asset slots"),
+    ("output stream out; external ir: ImpulseResponse; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "only AudioAsset slots are supported (found `ImpulseResponse`)"),
+    ("output stream out; external s: AudioAsset; node o = PolyBlepOscillator::saw(1.0, 1.0); connection s -> o.frequency; connection o.output -> out;",
+     "Type mismatch in connection: source is Asset but destination expects Value"),
+    ("output stream out; external s: AudioAsset; node p = SamplePlayer::new(); connection s -> out;", "an external asset connects to a node's asset endpoint"),
+    ("output stream out; external s: AudioAsset; node p = SamplePlayer::new(); connection s * 2.0 -> p.buf; connection p.output -> out;", "is an external asset slot: it connects to an asset endpoint only"),
+    (ONE_OSC + "node p = SamplePlayer::new(); connection o.output -> p.buf; connection p.output -> out;", "Type mismatch in connection: source is Stream but destination expects Asset"),
+    ("output stream out; external s: AudioAsset; external s: AudioAsset; node p = SamplePlayer::new(); connection p.output -> out;", "duplicate name `s`"),
+    ("output stream out; external a: AudioAsset; external b: AudioAsset; external c: AudioAsset; external d: AudioAsset; external e: AudioAsset; "
+     "node p = SamplePlayer::new(); connection p.output -> out;", "more than 4 external asset slots"),
+    ("output stream out; node p = SamplePlayer::new(1.0); connection p.output -> out;", "SamplePlayer::new takes 0 argument(s), found 1"),
     ("output stream out; name: Late; node o = PolyBlepOscillator::saw(1.0, 1.0); connection o.output -> out;", "`name:` must be the first item"),
     (ONE_OSC + "connection [cubic] o.output -> out;", "unknown connection policy `cubic`"),
     ("output stream out; /* never closed", "unterminated block comment"),
@@ -414,6 +423,29 @@ def test_node_plan_refuses_feedback_and_multirate_graphs():
     assert "multirate" in str(ei.value)
 
 
+def test_external_asset_slot_and_sample_player_plan():
+    """`external NAME: AudioAsset;` + `NAME -> player.buf` (oscen-lib/tests/sample_player_graph.rs:15-31): the slot table, the
+    one-word player state, the generated kernel compiles for sm_100a, and the node plan refuses the graph by name"""
+    g = abi.Graph(text("player.graph"))
+    d = g.describe()
+    assert "external 0: sample (AudioAsset) -> player.buf" in d and "state words per voice: 1" in d
+    assert g.launches() == ["0: SamplePlayer [player]"]
+    assert g.n_assets() == 1 and g.asset_id("sample") == 0
+    with pytest.raises(KeyError):
+        g.asset_id("nope")
+    src = g.codegen()
+    assert "sample_player_process(" in src and "a.assets->reset[0]" in src
+    assert g.jit_check() > 10000
+    with pytest.raises(abi.EngineError) as ei:
+        abi.Engine.from_graph(g, 64, plan=abi.PLAN_NODES)
+    assert "SamplePlayer" in str(ei.value) and "PLAN_FUSED" in str(ei.value)
+    # a slot nobody reads and a player nobody feeds are both legal (the reference emits silence for the latter)
+    g2 = abi.Graph("output stream out; external spare: AudioAsset; node p = SamplePlayer::new() * 2; connection p.output -> out;")
+    assert "external 0: spare (AudioAsset) -> (not connected)" in g2.describe()
+    assert "`buf` is not connected: silence" in g2.codegen()
+    assert g2.jit_check() > 10000
+
+
 # ------------------------------------------------------------------ the front end under sanitizers + fuzzing
 @pytest.fixture(scope="module")
 def graphc(tmp_path_factory):
@@ -644,13 +676,13 @@ def test_graphc_lists_the_node_library(graphc):
     assert r.returncode == 0
     for frag in ("AdsrEnvelope::new(attack, decay, sustain, release)", "input  gate: event", "FmOperator::new()",
                  "input  envelope: stream (unconnected: 1.000000)", "Delay::new(delay_samples, feedback) | from_seconds",
-                 "input  pulse_width: value (unconnected: 0.500000)", "HardClip::new()"):
+                 "input  pulse_width: value (unconnected: 0.500000)", "HardClip::new()", "SamplePlayer::new()", "input  buf: asset"):
         assert frag in r.stdout, frag
     # every type the listing names is one the front end accepts, with the listed endpoints
     for type_name in re.findall(r"^(\w+)::", r.stdout, re.M):
         ctor = {"AdsrEnvelope": "new(0.1, 0.1, 0.5, 0.1)", "FmOperator": "new()", "TptFilter": "new(1000.0, 0.7)", "PolyBlepOscillator": "sine(1.0, 1.0)",
                 "LP18Filter": "new(1000.0, 0.5)", "IirLowpass": "new(1000.0, 0.7)", "Oscillator": "sine(1.0, 1.0)", "Delay": "new(1.0, 0.0)",
-                "Gain": "new(1.0)", "AddValue": "new(0.0)", "Mixer": "new()", "Crossfade": "new()", "HardClip": "new()"}[type_name]
+                "Gain": "new(1.0)", "AddValue": "new(0.0)", "Mixer": "new()", "Crossfade": "new()", "HardClip": "new()", "SamplePlayer": "new()"}[type_name]
         out = "output_a" if type_name == "Crossfade" else "output"
         abi.Graph(f"output stream o; node n = {type_name}::{ctor}; connection n.{out} -> o;")
 

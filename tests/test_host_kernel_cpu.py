@@ -132,3 +132,96 @@ def test_host_executed_random_graph_kernels_match_the_oracle_walk(kind, seed):
         got.append(eng.read_voice_out())
     got = np.concatenate(got)
     assert np.array_equal(got, want), (kind, seed, float(np.nanmax(np.abs(got - want))), src)
+
+
+def test_host_executed_tpt_filter_matches_the_reference_impulse_response():
+    """the reference's one golden waveform (filters/tpt/mod.rs:152-161,227-264, committed in tests/golden/reference_kats.json)
+    against the generated kernel's TptFilter body, at the reference's 44.1 kHz"""
+    import json
+    k = json.load(open(os.path.join(os.path.dirname(GRAPHS), "golden", "reference_kats.json")))["tpt_impulse_response"]
+    src = f"input audio_in: stream; output stream out; node f = TptFilter::new({k['cutoff']!r}, {k['q']!r}); connection audio_in -> f.input; connection f.output -> out;"
+    x = np.zeros((8, 4), dtype=np.float32); x[0, :] = 1.0
+    eng = HostEngine(src, 4, 1, k["sample_rate"])
+    eng.stream_in(0, x); eng.process_block(8)
+    y = eng.read_voice_out()
+    for v in range(4):
+        assert np.abs(y[:, v] - np.array(k["output"], dtype=np.float32)).max() <= k["epsilon"], y[:, v]
+
+
+# ------------------------------------------------------------ `external` asset slots and SamplePlayer
+def test_host_executed_sample_player_graph_reproduces_the_reference_graph_test():
+    """oscen-lib/tests/sample_player_graph.rs:64-124 on the generated kernel: silent before any load, buffer A looped
+    (across a block boundary), then a load of B restarts the playhead and B loops — every voice of the bank alike"""
+    a = np.array([0.1, -0.2, 0.3, -0.4, 0.5], dtype=np.float32)
+    b = np.array([0.9, 0.8, 0.7], dtype=np.float32)
+    eng = HostEngine(text("player.graph"), 70, 1, 44100.0)
+    eng.process_block(8)
+    assert (eng.read_voice_out() == 0.0).all()
+    eng.load_asset("sample", a)
+    eng.process_block(7); y1 = eng.read_voice_out()
+    eng.process_block(3); y2 = eng.read_voice_out()
+    want = np.concatenate([a, a])
+    assert np.array_equal(np.concatenate([y1, y2]), np.repeat(want[:, None], 70, axis=1))
+    eng.load_asset("sample", np.stack([b, -b], axis=1))           # a stereo source: a mono player takes channel 0
+    eng.process_block(6)
+    assert np.array_equal(eng.read_voice_out(), np.repeat(np.concatenate([b, b])[:, None], 70, axis=1))
+    eng.load_asset("sample", np.zeros(0, dtype=np.float32))       # an empty buffer: silence again
+    eng.process_block(4)
+    assert (eng.read_voice_out() == 0.0).all()
+
+
+PLAYERS_DSL = """
+    input level: value = 0.5;
+    input cutoff: value = 900.0;
+    output stream out;
+    external loop_a: AudioAsset;
+    external loop_b: AudioAsset;
+    node pa = SamplePlayer::new();
+    node pb = SamplePlayer::new();
+    node idle = SamplePlayer::new();
+    node filt = TptFilter::new(900.0, 0.8);
+    connection loop_a -> pa.buf;
+    connection loop_b -> pb.buf;
+    connection pa.output * level + idle.output -> filt.input;
+    connection cutoff -> filt.cutoff;
+    connection filt.output + pb.output * 0.25 -> out;
+"""
+
+
+def test_host_executed_two_sample_players_through_a_filter_match_the_oracle_walk():
+    """two slots loaded at different times (one reloaded with a SHORTER buffer mid-run), a player whose `buf` is not
+    connected (silence), per-voice level and cutoff — against a walk over the oracle's SamplePlayer and TptFilter"""
+    import graph_walk as W
+    n, sr = 5, 48000.0
+    f32 = np.float32
+    rng = np.random.default_rng(7)
+    bufs = {k: rng.uniform(-1, 1, size).astype(np.float32) for k, size in (("a1", 37), ("b1", 11), ("a2", 5))}
+    level = (0.3 + 0.1 * np.arange(n)).astype(np.float32)
+    cutoff = (500.0 + 300.0 * np.arange(n)).astype(np.float32)
+    script = [(20, {}), (50, {"loop_a": "a1"}), (41, {"loop_b": "b1"}), (64, {"loop_a": "a2"})]      # (frames, loads before the block)
+
+    eng = HostEngine(PLAYERS_DSL, n, 1, sr)
+    eng.set_value(eng.graph.input_id("level"), level)
+    eng.set_value(eng.graph.input_id("cutoff"), cutoff)
+    got = []
+    for frames, loads in script:
+        for slot, key in loads.items():
+            eng.load_asset(slot, bufs[key])
+        eng.process_block(frames); got.append(eng.read_voice_out())
+    got = np.concatenate(got)
+
+    want = np.zeros_like(got)
+    for v in range(n):
+        pa, pb, idle, filt = W.sample_player(), W.sample_player(), W.sample_player(), W.tpt(900.0, 0.8, sr)
+        slots = {"loop_a": pa, "loop_b": pb}
+        f = 0
+        for frames, loads in script:
+            for slot, key in loads.items():
+                slots[slot].publish(bufs[key])
+            for _ in range(frames):
+                a, b, i = pa.process(), pb.process(), idle.process()
+                filt.set(input=f32(f32(a * level[v]) + i), cutoff=cutoff[v])
+                want[f, v] = f32(filt.process() + f32(b * f32(0.25)))
+                f += 1
+    assert np.abs(want).max() > 0.05
+    assert np.array_equal(got, want), float(np.abs(got - want).max())

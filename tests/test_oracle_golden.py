@@ -660,3 +660,52 @@ def test_iir_lowpass_reference_tests():
     L.orc_iirlp_new(C.byref(f), 100.0, q); f.sample_rate = 48000.0; L.orc_iirlp_prepare(C.byref(f))
     f.input = 1e-20; L.orc_iirlp_process(C.byref(f))
     assert f.output == 0.0
+
+
+def _player_run(p, n):
+    out = []
+    for _ in range(n):
+        O.lib().orc_sample_player_process(C.byref(p)); out.append(p.output)
+    return np.array(out, dtype=np.float32)
+
+
+def test_sample_player_reference_tests():
+    """sample_player/tests.rs:35-71,138-155 (mono cases) and tests/sample_player_graph.rs:64-124: in-order looping playback,
+    playhead reset on swap, silence when unloaded, channel 0 of a multi-channel source — the reference's epsilon is 1e-6,
+    the copies are exact"""
+    L = O.lib()
+    f32 = np.float32
+
+    def buf(v):
+        return np.array(v, dtype=np.float32)
+
+    p = O.SamplePlayer(); L.orc_sample_player_new(C.byref(p))
+    a = buf([0.1, 0.2, 0.3])
+    L.orc_sample_player_publish(C.byref(p), a.ctypes.data, a.size)
+    assert np.array_equal(_player_run(p, 7), buf([0.1, 0.2, 0.3, 0.1, 0.2, 0.3, 0.1]))
+
+    p = O.SamplePlayer(); L.orc_sample_player_new(C.byref(p))
+    a, b = buf([0.1, 0.2, 0.3, 0.4]), buf([0.8, 0.9])
+    L.orc_sample_player_publish(C.byref(p), a.ctypes.data, a.size)
+    assert np.array_equal(_player_run(p, 2), buf([0.1, 0.2]))
+    L.orc_sample_player_publish(C.byref(p), b.ctypes.data, b.size)
+    assert np.array_equal(_player_run(p, 3), buf([0.8, 0.9, 0.8]))
+
+    p = O.SamplePlayer(); L.orc_sample_player_new(C.byref(p))
+    assert (_player_run(p, 4) == f32(0.0)).all()
+
+    inter = buf([0.1, 0.9, 0.2, 0.8])                                 # L = [0.1, 0.2], R = [0.9, 0.8]: a downmix would give 0.5
+    mono = np.zeros(2, dtype=np.float32)
+    L.orc_sample_player_build_mono(mono.ctypes.data, inter.ctypes.data, 2, 2)
+    p = O.SamplePlayer(); L.orc_sample_player_new(C.byref(p))
+    L.orc_sample_player_publish(C.byref(p), mono.ctypes.data, 2)
+    assert np.array_equal(_player_run(p, 2), buf([0.1, 0.2]))
+
+    # the graph test: silent before any load, A looped twice, then B looped twice from its start
+    p = O.SamplePlayer(); L.orc_sample_player_new(C.byref(p))
+    a, b = buf([0.1, -0.2, 0.3, -0.4, 0.5]), buf([0.9, 0.8, 0.7])
+    assert (_player_run(p, 8) == f32(0.0)).all()
+    L.orc_sample_player_publish(C.byref(p), a.ctypes.data, a.size)
+    assert np.array_equal(_player_run(p, 10), np.concatenate([a, a]))
+    L.orc_sample_player_publish(C.byref(p), b.ctypes.data, b.size)
+    assert np.array_equal(_player_run(p, 6), np.concatenate([b, b]))

@@ -62,8 +62,13 @@ OSC_HD float fractf(float x) {
 }
 /* keep a loop-invariant value in a register (stops the compiler from re-loading it from the
    constant bank inside the frame loop, where LDC latency is exposed) */
+#if defined(__CUDACC__)
 OSC_D float pin(float x) { asm volatile("" : "+f"(x)); return x; }
 OSC_D uint32_t pin(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+#else   /* plain C++ (tests/host_kernel.py compiles these headers with g++): nothing to pin */
+inline float pin(float x) { return x; }
+inline uint32_t pin(uint32_t x) { return x; }
+#endif
 
 /* tanf only runs when a filter coefficient has to be recomputed (parameter changes): on the device
    it is a real call, so the ~700-instruction fdlibm body is not replicated into every unrolled

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from host_kernel import HostEngine
+from host_kernel import HostEngine, HostFmEngine
 from parity_util import lcg_noise, lcg_uniform, seq_sum_f32
 from test_parity_gpu import _fm_bank_script
 
@@ -225,3 +225,44 @@ def test_host_executed_two_sample_players_through_a_filter_match_the_oracle_walk
                 f += 1
     assert np.abs(want).max() > 0.05
     assert np.array_equal(got, want), float(np.abs(got - want).max())
+
+
+# ------------------------------------------------------------ the hand-written fused FMVoice kernel (the one bench.py times)
+def test_host_executed_hand_written_fm_kernel_matches_oracle_bank_both_instantiations():
+    """kernel_fm.cuh on the host, 136 voices = 17 instances of 8: (1) BASELINE config 2's steady state — per-voice
+    frequency, everything else uniform, gates only: the GENERAL=false instantiation (uniform values and ADSR step data
+    from the kernel arguments); (2) the events-and-ramps script of the GPU parity test: GENERAL=true.  Per-voice output
+    and instance fold bit-identical to the oracle; both instantiations agree with the kernel generated from the DSL text"""
+    from parity_util import lcg_ints
+    n, vpi = 136, 8
+    notes = 36 + lcg_ints(n, 1, 60)
+    freq = (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32)
+    vel = (0.25 + 0.75 * lcg_uniform(n, 2)).astype(np.float32)
+
+    def steady(b):
+        b.set_value(0, freq)
+        b.set_value(3, 0.3)                                       # op3_feedback, uniform
+        out = []
+        for blk in range(3):
+            if blk == 0:
+                b.push_events([(v, int(3 + v % 90), GATE, float(vel[v])) for v in range(n)])
+            if blk == 2:
+                b.push_events([(v, int(v % 64), GATE, 0.0) for v in range(0, n, 2)])
+                b.push_events([(v, 5, 0, float(freq[v] * 0.5)) for v in range(1, n, 3)])     # a frequency event keeps GENERAL=false
+            b.process_block(96)
+            out.append((b.read_voice_out(), b.read_instance_out()))
+        return np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out])
+
+    ref, hand, gen = O.OracleBank(O.K_FM, n, vpi), HostFmEngine(n, vpi), HostEngine(text("voice_fm3.graph"), n, vpi)
+    (vr, ir), (vh, ih), (vg, ig) = steady(ref), steady(hand), steady(gen)
+    assert hand.last_general is False
+    assert np.abs(vr).max() > 0.05
+    assert np.array_equal(vh, vr) and np.array_equal(ih, ir), float(np.abs(vh - vr).max())
+    assert np.array_equal(vg, vr) and np.array_equal(ig, ir)
+
+    ref, hand = O.OracleBank(O.K_FM, n, vpi), HostFmEngine(n, vpi)
+    (vr, ir, mr), (vh, ih, mh) = [_fm_bank_script(b, n, blocks=3, frames=128) for b in (ref, hand)]
+    assert hand.last_general is True
+    assert np.array_equal(vh, vr) and np.array_equal(ih, ir), float(np.abs(vh - vr).max())
+    scale = np.abs(ir.astype(np.float64)).sum(axis=1)
+    assert (np.abs(mh.astype(np.float64) - mr.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()

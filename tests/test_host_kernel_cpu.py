@@ -1,8 +1,10 @@
 """CPU parity tests of the GENERATED kernels, executed on the host (tests/host_kernel.py): the CUDA text codegen.hpp
 emits for a graph — the text an engine hands to NVRTC — is compiled by g++ against a stand-in CUDA runtime header and
 the engine's own device headers, run as 64-thread CTAs of OS threads, and compared bit for bit with the oracle.  The
-same scripts as the GPU parity tests (tests/test_dsl_gpu.py), at sizes a host finishes in seconds: a code generator or
-node-body regression shows up here, before any GPU time is spent.  The GPU tests remain the parity tests proper."""
+DSL parity tests proper live in tests/test_dsl_gpu.py, whose every test also has a host-executed variant in the CPU suite;
+here are the cases that exist only on the host: the differential fuzzer at host sizes, the reference's TptFilter known
+answer, the SamplePlayer graphs, and the HAND-WRITTEN fused FMVoice kernel (the one bench.py times).  A code-generator
+or node-body regression shows up here before any GPU time is spent.  The GPU tests remain the parity tests proper."""
 import os
 
 import numpy as np
@@ -20,83 +22,6 @@ GRAPHS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "graphs")
 def text(name):
     with open(os.path.join(GRAPHS, name)) as f:
         return f.read()
-
-
-def test_host_executed_fm_voice_kernel_matches_oracle_bank_voices_instances_and_mix():
-    """BASELINE config 2's graph from its DSL text: 136 voices = 17 instances of 8 over three CTAs (the last one partly
-    filled), gates, two ramps across blocks, frame-accurate value events — per-voice output and the in-order instance
-    fold bit-identical to the oracle, the mix bus within the reduction-order tolerance of the GPU test"""
-    n, vpi = 136, 8
-    ref, host = O.OracleBank(O.K_FM, n, vpi), HostEngine(text("voice_fm3.graph"), n, vpi)
-    (vr, ir, mr), (vh, ih, mh) = [_fm_bank_script(b, n, blocks=3, frames=128) for b in (ref, host)]
-    assert np.abs(vr).max() > 0.05
-    assert np.array_equal(vh, vr), float(np.abs(vh - vr).max())
-    assert np.array_equal(ih, ir)
-    assert np.array_equal(seq_sum_f32(vh.reshape(vh.shape[0], n // vpi, vpi), axis=2), ih[:, :, 0])
-    scale = np.abs(ir.astype(np.float64)).sum(axis=1)
-    assert (np.abs(mh.astype(np.float64) - mr.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()
-
-
-@pytest.mark.parametrize("file,kind", [("synth.graph", O.K_SYNTH), ("synth_adsr.graph", O.K_SYNTH_ADSR),
-                                       ("sat_1x.graph", O.K_SAT1), ("twin_peaks.graph", O.K_TWIN), ("sat_4x.graph", O.K_SAT4)])
-def test_host_executed_reference_graph_kernels_match_oracle_banks(file, kind):
-    n = 70
-    ref, host = O.OracleBank(kind, n, 1), HostEngine(text(file), n, 1)
-    x = np.stack([lcg_noise(512, 77 + v) for v in range(n)], axis=1) if kind == O.K_TWIN else None
-
-    def script(b):
-        out = []
-        if kind in (O.K_SYNTH, O.K_SYNTH_ADSR):
-            b.set_value(2, (80.0 + 9.0 * np.arange(n)).astype(np.float32))
-            b.set_value(3, (400.0 + 50.0 * np.arange(n)).astype(np.float32))
-        elif kind == O.K_SAT1:
-            b.set_value(0, (500.0 + 20.0 * np.arange(n)).astype(np.float32))
-        elif kind == O.K_SAT4:
-            b.set_value(0, (2000.0 * (0.5 + lcg_uniform(n, 5))).astype(np.float32))
-        for blk, frames in enumerate((200, 50, 90)):
-            if kind == O.K_TWIN:
-                b.stream_in(0, x[blk * 100:blk * 100 + frames])
-            if kind == O.K_SYNTH_ADSR and blk < 2:
-                b.push_events([(v, (v + 3 * blk) % 50, GATE, 0.9 if blk == 0 else 0.0) for v in range(n)])
-            if blk == 1 and kind not in (O.K_SAT1, O.K_SAT4):
-                b.set_value_ramp(0, 7.0 if kind != O.K_TWIN else 1200.0, 70)            # spans the block boundary
-                b.push_events([(5, 40, 1, 0.3 if kind != O.K_TWIN else 2500.0)])        # a value event at frame 40
-            b.process_block(frames)
-            out.append(b.read_voice_out())
-        return np.concatenate(out)
-
-    yr, yh = script(ref), script(host)
-    assert np.abs(yr).max() > 0.01
-    assert np.array_equal(yh, yr), float(np.abs(yh - yr).max())
-
-
-CLIP_DSL = """
-    input audio_in: stream;
-    output stream out;
-    node g = Gain::new(1.0) * {factor};
-    connection {prefix}audio_in -> g.input;
-    connection {prefix}g.output.clamp(-0.7, 0.7) -> out;
-"""
-
-
-@pytest.mark.parametrize("factor", [2, 4, 8])
-@pytest.mark.parametrize("policy", ["sinc", "sinc_iir", "linear", "latch"])
-def test_host_executed_clip_oversampled_family_matches_oracle(policy, factor):
-    """every connection policy x factor of the reference's ClipOversampled graphs (oscen-lib/tests/multirate_graph.rs:282-325),
-    resampler state (FIR rings in the CTA's dynamic shared memory for [sinc]) handed across three blocks"""
-    n = 6
-    pol = {"sinc": O.POLICY_SINC, "sinc_iir": O.POLICY_SINC_IIR, "linear": O.POLICY_LINEAR, "latch": O.POLICY_LATCH}[policy]
-    ref = O.OracleBank(O.k_clip_os(pol, factor), n, 1)
-    host = HostEngine(CLIP_DSL.format(factor=factor, prefix="" if policy == "sinc" else f"[{policy}] "), n, 1)
-    x = np.stack([lcg_noise(300, 900 + v) for v in range(n)], axis=1) * np.float32(1.4)
-    pos, outs_r, outs_h = 0, [], []
-    for frames in (128, 22, 150):
-        for b, outs in ((ref, outs_r), (host, outs_h)):
-            b.stream_in(0, x[pos:pos + frames]); b.process_block(frames); outs.append(b.read_voice_out())
-        pos += frames
-    yr, yh = np.concatenate(outs_r), np.concatenate(outs_h)
-    assert np.abs(yr).max() > 0.5
-    assert np.array_equal(yh, yr), (policy, factor, float(np.abs(yh - yr).max()))
 
 
 @pytest.mark.parametrize("kind", ["plain", "feedback", "multirate"])

@@ -1,0 +1,46 @@
+"""Differential fuzz of the generated kernels WITHOUT a GPU: random graphs (tests/random_graphs.py) -> DSL text -> generated CUDA text
+-> executed on the host (tests/host_kernel.py) vs the per-sample walk over the oracle.  TEST TOOL.
+    PYTHONPATH=tests:. python tools/fuzz_host_kernels.py FIRST_SEED LAST_SEED"""
+import sys, time
+import numpy as np
+import random_graphs as R
+import oracle_lib as O
+from parity_util import lcg_noise
+from host_kernel import HostEngine
+from oscen_b200 import abi
+GATE = O.EV_GATE
+def run(kind, seed):
+    rng = np.random.default_rng(777000 + seed)
+    rg = R.make_graph(rng, feedback=(kind == "feedback"), multirate=(kind == "multirate"))
+    src = rg.dsl()
+    n, frames = 2, 72
+    g = abi.Graph(src)
+    vals = {name: (d * (1.0 + 0.1 * np.arange(n))).astype(np.float32) for name, d in rg.values.items()}
+    x = np.stack([lcg_noise(frames, 300 + seed * 8 + v) for v in range(n)], axis=1) if rg.has_input else None
+    gates = [(v, 2 + 3 * v, 0.5 + 0.1 * v) for v in range(n)] + [(v, 50 + v, 0.0) for v in range(n)] if rg.has_gate else []
+    want = rg.walk(n, frames, vals, gates, x)
+    if not np.isfinite(want).all(): return "skip"
+    eng = HostEngine(g, n)
+    for name, arr in vals.items(): eng.set_value(g.input_id(name), arr)
+    got = []
+    for lo, hi in ((0, 29), (29, 72)):
+        if x is not None: eng.stream_in(0, x[lo:hi])
+        ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
+        if ev: eng.push_events(ev)
+        eng.process_block(hi - lo)
+        got.append(eng.read_voice_out())
+    got = np.concatenate(got)
+    if np.array_equal(got, want): return "ok"
+    print("MISMATCH", kind, seed, float(np.nanmax(np.abs(got - want))), "\n", src, flush=True)
+    return "MISMATCH"
+lo, hi = int(sys.argv[1]), int(sys.argv[2])
+tally = {}
+t0 = time.time()
+for seed in range(lo, hi):
+    for kind in ("plain", "feedback", "multirate"):
+        try:
+            r = run(kind, seed)
+        except Exception as ex:
+            r = "EXC"; print("EXC", kind, seed, repr(ex)[:300], flush=True)
+        tally[(kind, r)] = tally.get((kind, r), 0) + 1
+print(sorted(tally.items()), "%.0fs" % (time.time() - t0), flush=True)

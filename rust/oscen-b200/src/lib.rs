@@ -44,6 +44,12 @@ impl Graph {
     pub fn voices_per_instance(&self) -> u32 {
         unsafe { sys::oscen_b200_graph_voices_per_instance(self.raw) }
     }
+    /// index of an `external NAME: AudioAsset;` slot
+    pub fn asset_id(&self, name: &str) -> Option<u32> {
+        let c = CString::new(name).ok()?;
+        let id = unsafe { sys::oscen_b200_graph_asset_id(self.raw, c.as_ptr()) };
+        (id >= 0).then_some(id as u32)
+    }
 }
 impl Drop for Graph {
     fn drop(&mut self) {
@@ -121,6 +127,14 @@ impl Bank {
     /// `midi_in.try_push(raw_midi_event(bytes))` on one instance of a polyphonic graph
     pub fn push_midi(&mut self, instance: u32, frame_offset: u32, bytes: &[u8]) -> Result<()> {
         self.check(unsafe { sys::oscen_b200_push_midi(self.raw, instance, frame_offset, bytes.as_ptr(), bytes.len() as u32) }, "push_midi")
+    }
+    /// `graph.<slot>.load(..)` of an `external <slot>: AudioAsset;`: `interleaved` holds frames x channels f32 at the
+    /// bank's sample rate; the SamplePlayers bound to the slot restart at the next block
+    pub fn load_asset(&mut self, slot: &str, interleaved: &[f32], channels: u32) -> Result<()> {
+        let id = self.graph.asset_id(slot).ok_or_else(|| Error(format!("graph has no external slot `{slot}`")))?;
+        let ch = channels.max(1);
+        let frames = (interleaved.len() as u32) / ch;
+        self.check(unsafe { sys::oscen_b200_load_asset(self.raw, id, interleaved.as_ptr(), frames, ch) }, "load_asset")
     }
     /// `process_block(frames)`, frames <= MAX_BLOCK_SIZE
     pub fn process_block(&mut self, frames: u32) -> Result<()> {

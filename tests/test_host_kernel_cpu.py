@@ -2,7 +2,8 @@
 emits for a graph — the text an engine hands to NVRTC — is compiled by g++ against a stand-in CUDA runtime header and
 the engine's own device headers, run as 64-thread CTAs of OS threads, and compared bit for bit with the oracle.  The
 DSL parity tests proper live in tests/test_dsl_gpu.py, whose every test also has a host-executed variant in the CPU suite;
-here are the cases that exist only on the host: the differential fuzzer at host sizes, the reference's TptFilter known
+here are the cases that exist only on the host: the differential fuzzer at host sizes (generated kernels, and node plans
+for the graphs that have one — tests/csrc/host_nodes_runner.cpp), the reference's TptFilter known
 answer, the SamplePlayer graphs, and the HAND-WRITTEN fused FMVoice kernel (the one bench.py times).  A code-generator
 or node-body regression shows up here before any GPU time is spent.  The GPU tests remain the parity tests proper."""
 import os
@@ -11,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from host_kernel import HostEngine, HostFmEngine
+from host_kernel import HostEngine, HostFmEngine, HostNodePlanEngine
 from parity_util import lcg_noise, lcg_uniform, seq_sum_f32
 from test_parity_gpu import _fm_bank_script
 
@@ -43,20 +44,24 @@ def test_host_executed_random_graph_kernels_match_the_oracle_walk(kind, seed):
     want = rg.walk(n, frames, vals, gates, x)
     if not np.isfinite(want).all():
         pytest.skip("this random graph diverges: nothing to compare")
-    eng = HostEngine(g, n)
-    for name, arr in vals.items():
-        eng.set_value(g.input_id(name), arr)
-    got = []
-    for lo, hi in ((0, 33), (33, 80)):
-        if x is not None:
-            eng.stream_in(0, x[lo:hi])
-        ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
-        if ev:
-            eng.push_events(ev)
-        eng.process_block(hi - lo)
-        got.append(eng.read_voice_out())
-    got = np.concatenate(got)
-    assert np.array_equal(got, want), (kind, seed, float(np.nanmax(np.abs(got - want))), src)
+    engines = [("generated kernel", HostEngine(g, n))]
+    if kind == "plain":                                       # same-rate graphs without feedback also run as node plans
+        engines.append(("node plan", HostNodePlanEngine(src, n)))
+    for label, eng in engines:
+        for name, arr in vals.items():
+            eng.set_value(g.input_id(name), arr)
+        got = []
+        for lo, hi in ((0, 33), (33, 80)):
+            if x is not None:
+                eng.stream_in(0, x[lo:hi])
+            ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
+            if ev:
+                eng.push_events(ev)
+            eng.process_block(hi - lo)
+            got.append(eng.read_voice_out())
+        got = np.concatenate(got)
+        assert np.array_equal(got, want), (kind, seed, label, float(np.nanmax(np.abs(got - want))), src)
+        eng.close()
 
 
 def test_host_executed_tpt_filter_matches_the_reference_impulse_response():

@@ -6,7 +6,7 @@ import numpy as np
 import random_graphs as R
 import oracle_lib as O
 from parity_util import lcg_noise
-from host_kernel import HostEngine
+from host_kernel import HostEngine, HostNodePlanEngine
 from oscen_b200 import abi
 GATE = O.EV_GATE
 def run(kind, seed):
@@ -20,19 +20,22 @@ def run(kind, seed):
     gates = [(v, 2 + 3 * v, 0.5 + 0.1 * v) for v in range(n)] + [(v, 50 + v, 0.0) for v in range(n)] if rg.has_gate else []
     want = rg.walk(n, frames, vals, gates, x)
     if not np.isfinite(want).all(): return "skip"
-    eng = HostEngine(g, n)
-    for name, arr in vals.items(): eng.set_value(g.input_id(name), arr)
-    got = []
-    for lo, hi in ((0, 29), (29, 72)):
-        if x is not None: eng.stream_in(0, x[lo:hi])
-        ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
-        if ev: eng.push_events(ev)
-        eng.process_block(hi - lo)
-        got.append(eng.read_voice_out())
-    got = np.concatenate(got)
-    if np.array_equal(got, want): return "ok"
-    print("MISMATCH", kind, seed, float(np.nanmax(np.abs(got - want))), "\n", src, flush=True)
-    return "MISMATCH"
+    engines = [("generated kernel", HostEngine(g, n))] + ([("node plan", HostNodePlanEngine(src, n))] if kind == "plain" else [])
+    for label, eng in engines:
+        for name, arr in vals.items(): eng.set_value(g.input_id(name), arr)
+        got = []
+        for lo, hi in ((0, 29), (29, 72)):
+            if x is not None: eng.stream_in(0, x[lo:hi])
+            ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
+            if ev: eng.push_events(ev)
+            eng.process_block(hi - lo)
+            got.append(eng.read_voice_out())
+        got = np.concatenate(got)
+        eng.close()
+        if not np.array_equal(got, want):
+            print("MISMATCH", kind, seed, label, float(np.nanmax(np.abs(got - want))), "\n", src, flush=True)
+            return "MISMATCH"
+    return "ok"
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
 tally = {}
 t0 = time.time()

@@ -249,9 +249,9 @@ struct Emitter {
         for (int i = 0; i < n_nodes; ++i) {
             const plan::Node &nd = g.nodes[i];
             if (nd.type == T::Adsr && !(P_is_const(i, 0) && P_is_const(i, 1) && P_is_const(i, 3)))
-                line(4, "if (changed && adsr_derived_stale(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ")) adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", sr);");
+                line(4, "if (changed && adsr_derived_stale(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ")) adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", " + SR(i) + ");");
             if (nd.type == T::FmOperator && !(P_is_const(i, 0) && P_is_const(i, 1)))
-                line(4, "if (changed) " + N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", sr);");
+                line(4, "if (changed) " + N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");");    /* an inner-rate node runs at sr * N */
         }
         bool any_gate = false;
         for (int i = 0; i < n_nodes; ++i) any_gate |= g.nodes[i].type == T::Adsr && g.nodes[i].gate;

@@ -33,7 +33,10 @@
  * Assets: `external NAME: AudioAsset;` declares a slot the host loads audio into at run time
  * (oscen_b200_load_asset); `NAME -> player.buf` binds it to a SamplePlayer (generated kernels only).
  *
- * Reported as errors (never silently ignored): `/ N` rates, mixed factors, node arrays outside the
+ * Node arrays of library types (`[T::new(); N]`, `nodes[k].ep`) are unrolled into scalar nodes with the reference's
+ * Broadcast / Parallel / FanIn edge shapes (ArrayExpander).
+ *
+ * Reported as errors (never silently ignored): `/ N` rates, mixed factors, arrays of graphs outside the
  * polyphonic shape, externals other than AudioAsset, typed endpoints, free-function calls in
  * sources (they name user Rust code).
  *
@@ -486,6 +489,7 @@ private:
         ExprP e(new Expr); e->at = cur();
         if (accept("(")) { e = additive(); expect(")"); return postfix(std::move(e)); }
         if (cur().kind == Tok::Num) { e->k = Expr::Literal; e->lit = cur().num; ++pos; return e; }
+        if (is_punct("-") && peek(1).kind == Tok::Num) { e->k = Expr::Literal; e->lit = -peek(1).num; pos += 2; return e; }   /* `x * -1.0` */
         if (cur().kind != Tok::Ident) { err.at(cur(), "expected a connection endpoint or expression"); return e; }
         std::string path = cur().s; ++pos;
         bool multi = false;
@@ -507,7 +511,18 @@ private:
     }
     ExprP postfix(ExprP e) {
         for (;;) {
-            if (is_punct("[")) { err.at(cur(), "array-indexed endpoints (`voices[i]`) are not supported by the node plan"); return e; }
+            if (is_punct("[")) {
+                /* `oscs[2]`: one element of a node array (ast.rs: Indexed); arrays are unrolled into scalar nodes named
+                   `oscs[0]` .. `oscs[N-1]` before lowering (expand_node_arrays), so the index folds into the name */
+                if (e->k != Expr::Ident || peek(1).kind != Tok::Num || !(peek(2).kind == Tok::Punct && peek(2).s == "]")) {
+                    err.at(cur(), "array-indexed endpoints take the form `nodes[<integer literal>].endpoint`"); return e;
+                }
+                const float idx = peek(1).num;
+                if (idx < 0.0f || idx != (float)(int)idx) { err.at(peek(1), "an array index must be a non-negative integer literal"); return e; }
+                e->name += "[" + std::to_string((int)idx) + "]";
+                pos += 3;
+                continue;
+            }
             if (!is_punct(".")) return e;
             ++pos;
             ExprP f(new Expr); f->at = cur();
@@ -1085,6 +1100,94 @@ inline ExprP clone_expr(const Expr &e) {
     if (e.b) c->b = clone_expr(*e.b);
     return c;
 }
+inline const Ast *find_graph(const std::vector<Ast> &all, const std::string &name);
+
+/* Node arrays of library types — `oscs = [PolyBlepOscillator::saw(440.0, 0.6); 4]` (oscen-lib/tests/array_test.rs,
+   array_fanin_stream_input.rs, multirate_array_fanout.rs) — are unrolled into scalar nodes `oscs[0]` .. `oscs[N-1]`, and
+   every connection that names the array without an index takes the shape ir/graph.rs:48-78 gives it:
+     scalar -> array.ep   Broadcast: one edge per element (a cross-rate broadcast gets one resampler per element here where
+                          the reference shares one — same input, same state, same values)
+     array.ep -> scalar   FanIn: `let mut sum = 0.0; for i { sum += elt }` (codegen/emit_edge.rs:208-233), summed at the
+                          source rate, then ONE resampler if the edge crosses rates
+     array.ep -> array.ep Parallel: element k to element k, for k < min(N, M)
+   Arrays of GRAPHS stay with lower_polyphonic (the engine's voices_per_instance axis). */
+struct ArrayExpander {
+    Error &err;
+    std::map<std::string, int> arrays;
+    static ExprP field_of(const std::string &node, const std::string &field, const Tok &at) {
+        ExprP id(new Expr); id->k = Expr::Ident; id->name = node; id->at = at;
+        ExprP f(new Expr); f->k = Expr::Field; f->name = field; f->at = at; f->a = std::move(id);
+        return f;
+    }
+    /* N if `e` is `array.endpoint` without an index, else 0 */
+    int array_endpoint(const Expr &e) const {
+        if (e.k != Expr::Field || !e.a || e.a->k != Expr::Ident) return 0;
+        auto it = arrays.find(e.a->name);
+        return it == arrays.end() ? 0 : it->second;
+    }
+    bool mentions_array(const Expr &e) const {
+        if (e.k == Expr::Ident && arrays.count(e.name)) return true;
+        if (array_endpoint(e)) return true;
+        return (e.a && mentions_array(*e.a)) || (e.b && mentions_array(*e.b));
+    }
+    static Conn like(const Conn &c) {
+        Conn k; k.policy = c.policy; k.via = c.via; k.via_samples = c.via_samples; k.via_node = c.via_node; k.at = c.at;
+        return k;
+    }
+    bool run(Ast &g) {
+        arrays.clear();
+        std::vector<NodeDecl> nodes;
+        for (const NodeDecl &d : g.nodes) {
+            if (d.array > 0 && type_info(d.type)) {
+                if (d.array > 64) { err.at(d.at, "node array `" + d.name + "`: more than 64 elements"); return false; }
+                if (arrays.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
+                arrays[d.name] = d.array;
+                for (int k = 0; k < d.array; ++k) { NodeDecl e = d; e.array = 0; e.name = d.name + "[" + std::to_string(k) + "]"; nodes.push_back(e); }
+            } else nodes.push_back(d);
+        }
+        if (arrays.empty()) return true;
+        g.nodes.swap(nodes);
+        std::vector<Conn> conns;
+        for (Conn &c : g.conns) {
+            const int sn = array_endpoint(*c.src), dn = array_endpoint(*c.dst);
+            if (!sn && mentions_array(*c.src)) {
+                err.at(c.at, "a node array inside a source expression: name its elements (`oscs[0].output + oscs[1].output`) or connect `array.endpoint` on its own"); return false;
+            }
+            if (!dn && mentions_array(*c.dst)) { err.at(c.at, "a node array is connected through one of its endpoints (`array.endpoint`)"); return false; }
+            if ((sn || dn) && c.via) { err.at(c.at, "feedback edges (`-> [..] ->`) take scalar endpoints: index the array elements"); return false; }
+            if (!sn && !dn) { conns.push_back(std::move(c)); continue; }
+            if (dn && !sn) {                                          /* Broadcast */
+                for (int k = 0; k < dn; ++k) {
+                    Conn e = like(c);
+                    e.src = clone_expr(*c.src);
+                    e.dst = field_of(c.dst->a->name + "[" + std::to_string(k) + "]", c.dst->name, c.dst->at);
+                    conns.push_back(std::move(e));
+                }
+            } else if (dn && sn) {                                    /* Parallel */
+                for (int k = 0; k < std::min(sn, dn); ++k) {
+                    Conn e = like(c);
+                    e.src = field_of(c.src->a->name + "[" + std::to_string(k) + "]", c.src->name, c.src->at);
+                    e.dst = field_of(c.dst->a->name + "[" + std::to_string(k) + "]", c.dst->name, c.dst->at);
+                    conns.push_back(std::move(e));
+                }
+            } else {                                                  /* FanIn: 0.0 + e0 + e1 + ... */
+                ExprP acc(new Expr); acc->k = Expr::Literal; acc->lit = 0.0f; acc->at = c.src->at;
+                for (int k = 0; k < sn; ++k) {
+                    ExprP b(new Expr); b->k = Expr::Binary; b->op = '+'; b->at = c.src->at;
+                    b->a = std::move(acc);
+                    b->b = field_of(c.src->a->name + "[" + std::to_string(k) + "]", c.src->name, c.src->at);
+                    acc = std::move(b);
+                }
+                Conn e = like(c);
+                e.src = std::move(acc); e.dst = clone_expr(*c.dst);
+                conns.push_back(std::move(e));
+            }
+        }
+        g.conns.swap(conns);
+        return true;
+    }
+};
+
 inline const Ast *find_graph(const std::vector<Ast> &all, const std::string &name) {
     for (const Ast &a : all) if (a.name == name) return &a;
     return nullptr;
@@ -1360,6 +1463,7 @@ inline bool compile(const char *text, plan::Graph &g, std::string &error, const 
     Parser p(toks, err);
     if (!p.parse(graphs)) { error = err.text(); return false; }
     if (graphs.empty()) { error = "1:1: no graph in the text"; return false; }
+    { ArrayExpander ax{err, {}}; for (Ast &a : graphs) if (!ax.run(a)) { error = err.text(); return false; } }
     const Ast *chosen = &graphs.back();
     if (top_name && *top_name) {
         chosen = find_graph(graphs, top_name);

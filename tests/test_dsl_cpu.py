@@ -155,7 +155,7 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
     ("output stream out; node a = PolyBlepOscillator::saw(1.0, 1.0) * 2; node f = TptFilter::new(500.0, 0.7); node c = HardClip::new() * 2; "
      "connection a.output -> f.input; connection f.output -> c.input; connection c.output -> out;", "cannot feed it again in the same frame"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6) * 3; connection o.output -> out;", "rate factor must be in {1, 2, 4, 8}"),
-    ("output stream out; node v = [PolyBlepOscillator::saw(2000.0, 0.6); 4]; connection v.output -> out;", "is not a graph of this text"),
+    ("output stream out; node v = [UserVoice::new(); 4]; connection v.output -> out;", "is not a graph of this text"),
     ("output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6)\n connection o.output -> out;", "2:2: expected `;`"),
     (ONE_OSC + "connection o.output -> [4] -> out;", "must end at a node input"),
     (ONE_OSC + "node g = Gain::new(1.0); connection o.output -> [g] -> g.input; connection g.output -> out;", "does not implement AllowsFeedback (only Delay does)"),

@@ -196,3 +196,13 @@ def test_host_executed_hand_written_fm_kernel_matches_oracle_bank_both_instantia
     assert np.array_equal(vh, vr) and np.array_equal(ih, ir), float(np.abs(vh - vr).max())
     scale = np.abs(ir.astype(np.float64)).sum(axis=1)
     assert (np.abs(mh.astype(np.float64) - mr.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()
+
+
+@pytest.mark.parametrize("seed", [1047, 1131])
+def test_host_fuzzer_findings_stay_fixed(seed):
+    """the two multirate graphs of tools/fuzz_host_kernels.py (seeds 777000 + 1047 / 1131) that exposed the inner-rate
+    FmOperator / AdsrEnvelope re-derivation at the wrong sample rate (see tests/test_zz_regressions.py)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GRAPHS), "..", "tools"))
+    import fuzz_host_kernels as F
+    assert F.run("multirate", seed) == "ok"

@@ -1,0 +1,62 @@
+"""Regressions found by the host-side differential fuzzer (tools/fuzz_host_kernels.py), kept as explicit cases on the GPU
+(`-m gpu`, generated kernel) and on the host-executed kernel (CPU suite).
+(The file name sorts last on purpose: the GPU variants were added after the round's GPU budget was spent.)"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_dsl_gpu import dsl_engine, fused_plan  # noqa: F401  (fixture)
+
+GATE = O.EV_GATE
+SR = 48000.0
+
+INNER_PARAMS = """
+    input ratio: value = 1.5;
+    input attack: value = 0.003;
+    input gate: event;
+    output stream out;
+    nodes {
+        env = AdsrEnvelope::new(0.003, 0.004, 0.5, 0.002) * 4;
+        op = FmOperator::new() * 4;
+        clip = HardClip::new() * 4;
+    }
+    connections {
+        gate -> env.gate;
+        attack -> env.attack;                    // an inner-rate envelope whose times come from a value input
+        ratio -> op.ratio;                       // an inner-rate operator whose increment comes from a value input
+        330.0 -> op.base_freq;
+        env.output -> op.envelope;
+        op.output -> clip.input;
+        [sinc] clip.output -> out;
+    }
+"""
+
+
+def test_inner_rate_nodes_keep_their_rate_when_a_frame_carries_events(fused_plan):
+    """seeds 777000+1047 / +1131 of the host fuzzer: on a frame that carries an event or a ramp the generated kernel
+    re-derives an FmOperator's phase increment and an AdsrEnvelope's step data from their value inputs — for a `* N` node
+    that must happen at sr * N (codegen/emit_struct.rs:578-581), not at the graph's rate.  Properties that need no
+    oracle: a value event that rewrites the value already there changes nothing, and any block split renders the same"""
+    n, frames = 4, 160
+    ratio = (1.0 + 0.25 * np.arange(n)).astype(np.float32)
+    attack = (0.002 + 0.001 * np.arange(n)).astype(np.float32)
+    gates = [(v, 3 + 2 * v, GATE, 0.8) for v in range(n)] + [(v, 90 + v, GATE, 0.0) for v in range(n)]
+
+    def render(blocks, extra_events=()):
+        eng = dsl_engine(INNER_PARAMS, n, 1, SR, plan=fused_plan)
+        eng.set_value(0, ratio); eng.set_value(1, attack)
+        out, pos = [], 0
+        for b in blocks:
+            ev = [(v, f - pos, i, s) for v, f, i, s in list(gates) + list(extra_events) if pos <= f < pos + b]
+            if ev:
+                eng.push_events(ev)
+            eng.process_block(b); out.append(eng.read_voice_out()); pos += b
+        return np.concatenate(out)
+
+    base = render((frames,))
+    assert np.abs(base).max() > 0.05
+    assert np.array_equal(render((41, 7, 112)), base)                                     # block == per-sample for any split
+    same_value = [(v, 30 + v, 0, float(ratio[v])) for v in range(n)] + [(v, 50, 1, float(attack[v])) for v in range(n)]
+    assert np.array_equal(render((frames,), same_value), base)                            # rewriting a value with itself is a no-op
+    # and the rate really is 4 x: one octave up in `ratio` is not what a wrong rate would look like — compare with base_freq doubled
+    assert not np.array_equal(render((frames,), [(v, 30 + v, 0, float(ratio[v] * 2.0)) for v in range(n)]), base)

@@ -36,14 +36,15 @@ def run(kind, seed):
             print("MISMATCH", kind, seed, label, float(np.nanmax(np.abs(got - want))), "\n", src, flush=True)
             return "MISMATCH"
     return "ok"
-lo, hi = int(sys.argv[1]), int(sys.argv[2])
-tally = {}
-t0 = time.time()
-for seed in range(lo, hi):
-    for kind in ("plain", "feedback", "multirate"):
-        try:
-            r = run(kind, seed)
-        except Exception as ex:
-            r = "EXC"; print("EXC", kind, seed, repr(ex)[:300], flush=True)
-        tally[(kind, r)] = tally.get((kind, r), 0) + 1
-print(sorted(tally.items()), "%.0fs" % (time.time() - t0), flush=True)
+if __name__ == "__main__":
+    lo, hi = int(sys.argv[1]), int(sys.argv[2])
+    tally = {}
+    t0 = time.time()
+    for seed in range(lo, hi):
+        for kind in ("plain", "feedback", "multirate"):
+            try:
+                r = run(kind, seed)
+            except Exception as ex:
+                r = "EXC"; print("EXC", kind, seed, repr(ex)[:300], flush=True)
+            tally[(kind, r)] = tally.get((kind, r), 0) + 1
+    print(sorted(tally.items()), "%.0fs" % (time.time() - t0), flush=True)

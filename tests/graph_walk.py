@@ -148,7 +148,8 @@ def sample_player():
 def render(make_voice, n_voices, frames, values=None, gates=None, stream_in=None):
     """make_voice(v) -> (frame_fn, gate_fn); frame_fn(values_of_voice: dict, x: f32) -> f32 output;
     gate_fn(scalar) handles a gate event BEFORE that frame's process (derive(Node) process_event_inputs).
-    values: {name: scalar | [n_voices] array | callable(frame) -> scalar}; gates: [(voice, frame, scalar)]"""
+    values: {name: scalar | [n_voices] array | callable(frame) -> scalar | callable(frame, voice) with .per_voice = True};
+    gates: [(voice, frame, scalar)]"""
     out = np.zeros((frames, n_voices), dtype=np.float32)
     values = values or {}
     by_voice = {}
@@ -160,7 +161,7 @@ def render(make_voice, n_voices, frames, values=None, gates=None, stream_in=None
             vals = {}
             for k, val in values.items():
                 if callable(val):
-                    vals[k] = f32(val(f))
+                    vals[k] = f32(val(f, v)) if getattr(val, "per_voice", False) else f32(val(f))
                 elif np.ndim(val) == 0:
                     vals[k] = f32(val)
                 else:

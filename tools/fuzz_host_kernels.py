@@ -1,6 +1,7 @@
 """Differential fuzz of the generated kernels WITHOUT a GPU: random graphs (tests/random_graphs.py) -> DSL text -> generated CUDA text
 -> executed on the host (tests/host_kernel.py) vs the per-sample walk over the oracle.  TEST TOOL.
-    PYTHONPATH=tests:. python tools/fuzz_host_kernels.py FIRST_SEED LAST_SEED"""
+    PYTHONPATH=tests:. python tools/fuzz_host_kernels.py FIRST_SEED LAST_SEED [--ramps]
+--ramps: on odd seeds the first value input is uniform and ramps (set_<v>_with_ramp) across the block boundary."""
 import sys, time
 import numpy as np
 import random_graphs as R
@@ -9,7 +10,7 @@ from parity_util import lcg_noise
 from host_kernel import HostEngine, HostNodePlanEngine
 from oscen_b200 import abi
 GATE = O.EV_GATE
-def run(kind, seed):
+def run(kind, seed, ramps=False):
     rng = np.random.default_rng(777000 + seed)
     rg = R.make_graph(rng, feedback=(kind == "feedback"), multirate=(kind == "multirate"))
     src = rg.dsl()
@@ -18,15 +19,47 @@ def run(kind, seed):
     vals = {name: (d * (1.0 + 0.1 * np.arange(n))).astype(np.float32) for name, d in rg.values.items()}
     x = np.stack([lcg_noise(frames, 300 + seed * 8 + v) for v in range(n)], axis=1) if rg.has_input else None
     gates = [(v, 2 + 3 * v, 0.5 + 0.1 * v) for v in range(n)] + [(v, 50 + v, 0.0) for v in range(n)] if rg.has_gate else []
+    # odd seeds: the first value input is uniform and RAMPS (set_<v>_with_ramp) from frame 0 across the block boundary
+    ramp = None
+    if ramps and seed % 2 == 1 and rg.values:
+        import ctypes as C
+        name = sorted(rg.values)[0]
+        d = float(np.float32(rg.values[name]))
+        r = O.Ramp(); O.lib().orc_ramp_new(C.byref(r), d)
+        O.lib().orc_ramp_set_with_ramp(C.byref(r), float(np.float32(d * 1.5 + 0.1)), 45)
+        table = []
+        for _ in range(frames):
+            O.lib().orc_ramp_tick(C.byref(r)); table.append(np.float32(r.current))
+        ramp = (name, d, float(np.float32(d * 1.5 + 0.1)), 45)
+        vals = dict(vals); vals[name] = (lambda f, table=table: table[f])
+    # seeds divisible by 3 (with --ramps): frame-accurate VALUE EVENTS on the last value input, one per voice at its own frame
+    value_events = []
+    if ramps and seed % 3 == 0 and rg.values:
+        name = sorted(rg.values)[-1]
+        if not (ramp and ramp[0] == name):
+            base = np.asarray(vals[name], dtype=np.float32)
+            new = (base * np.float32(0.7) + np.float32(0.05)).astype(np.float32)
+            when = [17 + 9 * v for v in range(n)]                       # voice 1's lands right before the block boundary
+            step = lambda f, v, base=base, new=new, when=when: (new[v] if f >= when[v] else base[v])
+            step.per_voice = True
+            vals = dict(vals); vals[name] = step
+            value_events = [(v, when[v], name, float(new[v])) for v in range(n)]
     want = rg.walk(n, frames, vals, gates, x)
     if not np.isfinite(want).all(): return "skip"
     engines = [("generated kernel", HostEngine(g, n))] + ([("node plan", HostNodePlanEngine(src, n))] if kind == "plain" else [])
     for label, eng in engines:
-        for name, arr in vals.items(): eng.set_value(g.input_id(name), arr)
+        for name, arr in vals.items():
+            if ramp and name == ramp[0]:
+                eng.set_value(g.input_id(name), ramp[1]); eng.set_value_ramp(g.input_id(name), ramp[2], ramp[3])
+            elif callable(arr):
+                eng.set_value(g.input_id(name), base)
+            else:
+                eng.set_value(g.input_id(name), arr)
         got = []
         for lo, hi in ((0, 29), (29, 72)):
             if x is not None: eng.stream_in(0, x[lo:hi])
             ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
+            ev += [(v, f - lo, g.input_id(nm), s) for v, f, nm, s in value_events if lo <= f < hi]
             if ev: eng.push_events(ev)
             eng.process_block(hi - lo)
             got.append(eng.read_voice_out())
@@ -38,12 +71,13 @@ def run(kind, seed):
     return "ok"
 if __name__ == "__main__":
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
+    ramps = "--ramps" in sys.argv
     tally = {}
     t0 = time.time()
     for seed in range(lo, hi):
         for kind in ("plain", "feedback", "multirate"):
             try:
-                r = run(kind, seed)
+                r = run(kind, seed, ramps)
             except Exception as ex:
                 r = "EXC"; print("EXC", kind, seed, repr(ex)[:300], flush=True)
             tally[(kind, r)] = tally.get((kind, r), 0) + 1

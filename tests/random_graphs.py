@@ -227,10 +227,25 @@ def _stateless(fn):
     return lambda o, ins: fn(ins)
 
 
-def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False, multirate=False):
+# extended mode: value endpoints the base generator leaves at their constructor values, by kind of quantity
+EXT_ENDPOINTS = {
+    "polyblep": [("frequency", "freq")], "osc": [("frequency", "freq")],
+    "adsr": [("attack", "time"), ("decay", "time"), ("release", "time")],
+    "lp18": [("cutoff", "freq"), ("fmod", "unit")], "iirlp": [("cutoff", "freq")],
+    "delay": [("delay_samples", "samples"), ("feedback", "unit")],
+}
+EXT_RANGES = {"freq": (100.0, 3000.0), "time": (0.0005, 0.003), "unit": (0.05, 0.6), "samples": (0.0, 35.0)}
+
+
+def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False, multirate=False, extended=False):
     """multirate: nodes [a, b) run at 2^L x the graph's rate (`* N`); every stream edge between the two rates goes through
-    its own resampler of a random connection policy (one source per cross-rate endpoint: no fan-in across rates)"""
+    its own resampler of a random connection policy (one source per cross-rate endpoint: no fan-in across rates).
+    extended: additionally drives the value endpoints of EXT_ENDPOINTS (oscillator frequencies, envelope times, filter
+    cutoffs, delay time / feedback) from dedicated graph value inputs or literals.  The extra choices come from a second
+    generator seeded from `rng`'s state, so a seed yields the SAME base graph with and without the flag."""
     g = RandomGraph()
+    rng2 = np.random.default_rng(int(rng.bit_generator.state["state"]["state"]) & 0xFFFFFFFF) if extended else None
+    ext_values = {}
     n_nodes = n_nodes or int(rng.integers(3, 9))
     n_values = int(rng.integers(0, 4))
     for k in range(n_values):
@@ -427,10 +442,30 @@ def make_graph(rng, n_nodes=None, allow_delay=True, feedback=False, multirate=Fa
             nd["make"] = lambda ds=ds, fb=fb, sr_i=sr_i: W.delay(ds, fb, sr_i)
             conn("input", "stream", expr(i))
             nd["run"] = lambda o, ins: (o.set(input=ins.get("input", o.input)), o.process())[1]
+        if extended:
+            eps = []
+            for ep, vk in EXT_ENDPOINTS.get(t, []):
+                if ep in nd["conns"] or rng2.random() < 0.45:
+                    continue
+                lo_v, hi_v = EXT_RANGES[vk]
+                if rng2.random() < 0.7:                      # a dedicated graph value input per kind of quantity (shared by the nodes)
+                    name = "x" + vk
+                    if name not in ext_values:               # merged into g.values at the end: the base choices must not see them
+                        ext_values[name] = float(f32(rng2.uniform(lo_v, hi_v)))
+                    src = Src("value", name)
+                else:
+                    src = Src("lit", float(f32(rng2.uniform(lo_v, hi_v))))
+                nd["ep_kind"][ep] = "value"
+                nd["conns"][ep] = [src]
+                eps.append(ep)
+            if eps:
+                base_run = nd["run"]
+                nd["run"] = lambda o, ins, base_run=base_run, eps=eps: (o.set(**{k: ins[k] for k in eps if k in ins}), base_run(o, ins))[1]
         # drop inputs that could not be connected (nothing available yet)
         nd["conns"] = {ep: [s for s in srcs if s is not None or ep == "gate"] for ep, srcs in nd["conns"].items()}
         nd["conns"] = {ep: srcs for ep, srcs in nd["conns"].items() if srcs}
         g.nodes.append(nd)
+    g.values.update(ext_values)
     # feedback vias: `nJ.out -> [N] -> nI.<stream input>` with I an ancestor of J (or J itself), so the edge closes a cycle
     if feedback:
         def ancestors(j):

@@ -1,7 +1,9 @@
 """Differential fuzz of the generated kernels WITHOUT a GPU: random graphs (tests/random_graphs.py) -> DSL text -> generated CUDA text
 -> executed on the host (tests/host_kernel.py) vs the per-sample walk over the oracle.  TEST TOOL.
     PYTHONPATH=tests:. python tools/fuzz_host_kernels.py FIRST_SEED LAST_SEED [--ramps]
---ramps: on odd seeds the first value input is uniform and ramps (set_<v>_with_ramp) across the block boundary."""
+--ramps: on odd seeds the first value input is uniform and ramps (set_<v>_with_ramp) across the block boundary; on seeds
+divisible by 3 the last value input takes frame-accurate per-voice value events.
+--extended: oscillator frequencies, envelope times, filter cutoffs, delay time / feedback also come from value inputs."""
 import sys, time
 import numpy as np
 import random_graphs as R
@@ -10,9 +12,9 @@ from parity_util import lcg_noise
 from host_kernel import HostEngine, HostNodePlanEngine
 from oscen_b200 import abi
 GATE = O.EV_GATE
-def run(kind, seed, ramps=False):
+def run(kind, seed, ramps=False, extended=False):
     rng = np.random.default_rng(777000 + seed)
-    rg = R.make_graph(rng, feedback=(kind == "feedback"), multirate=(kind == "multirate"))
+    rg = R.make_graph(rng, feedback=(kind == "feedback"), multirate=(kind == "multirate"), extended=extended)
     src = rg.dsl()
     n, frames = 2, 72
     g = abi.Graph(src)
@@ -72,12 +74,13 @@ def run(kind, seed, ramps=False):
 if __name__ == "__main__":
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
     ramps = "--ramps" in sys.argv
+    extended = "--extended" in sys.argv
     tally = {}
     t0 = time.time()
     for seed in range(lo, hi):
         for kind in ("plain", "feedback", "multirate"):
             try:
-                r = run(kind, seed, ramps)
+                r = run(kind, seed, ramps, extended)
             except Exception as ex:
                 r = "EXC"; print("EXC", kind, seed, repr(ex)[:300], flush=True)
             tally[(kind, r)] = tally.get((kind, r), 0) + 1

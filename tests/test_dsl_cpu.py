@@ -486,6 +486,10 @@ def test_front_end_survives_mutated_graphs(graphc):
     corpus = [text(f) for f in ("voice_fm3.graph", "synth_adsr.graph", "twin_peaks.graph", "sat_4x.graph")]
     corpus.append(text("voice_fm3.graph") + text("poly_fm8.graph"))
     corpus.append(FEEDBACK)
+    corpus.append(text("player.graph"))                       # `external` slots, SamplePlayer
+    corpus.append("input value f = 1.0; input gate: event; output stream out; nodes { o = [PolyBlepOscillator::saw(440.0, 0.6); 4] * 2; "
+                  "e = [AdsrEnvelope::new(0.01, 0.1, 0.5, 0.2); 4]; v = [Gain::new(1.0); 3] * 2; } connections { gate -> e.gate; f -> o.frequency_mod; "
+                  "o.output -> v.input; [linear] e[1].output * -0.5 -> v[0].gain; [sinc] v.output -> out; }")      # node arrays, indices, negative literals
     junk = ["->", "[", "]", "{", "}", "(", ")", ";", ":", "::", "..", ",", "=", "*", "/", "+", "-", ".", "<", ">", "!", "graph", "input", "output",
             "node", "nodes", "connection", "connections", "value", "stream", "event", "name", "ramp", "0", "8", "1e39", "-0.0", "4294967296",
             "99999999999999999999", "x", "gate", "Delay::new(1.0, 0.0)", "[sinc]", "[x]", "\"s", "/*", "//", "\x00", "é"]

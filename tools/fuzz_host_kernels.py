@@ -17,6 +17,9 @@ def run(kind, seed, ramps=False, extended=False):
     rg = R.make_graph(rng, feedback=(kind == "feedback"), multirate=(kind == "multirate"), extended=extended)
     src = rg.dsl()
     n, frames = 2, 72
+    vpi = 1
+    if ramps and seed % 4 == 0:                                # instances of two voices: the in-order instance fold is checked too
+        n, vpi = 4, 2
     g = abi.Graph(src)
     vals = {name: (d * (1.0 + 0.1 * np.arange(n))).astype(np.float32) for name, d in rg.values.items()}
     x = np.stack([lcg_noise(frames, 300 + seed * 8 + v) for v in range(n)], axis=1) if rg.has_input else None
@@ -48,7 +51,7 @@ def run(kind, seed, ramps=False, extended=False):
             value_events = [(v, when[v], name, float(new[v])) for v in range(n)]
     want = rg.walk(n, frames, vals, gates, x)
     if not np.isfinite(want).all(): return "skip"
-    engines = [("generated kernel", HostEngine(g, n))] + ([("node plan", HostNodePlanEngine(src, n))] if kind == "plain" else [])
+    engines = [("generated kernel", HostEngine(g, n, vpi))] + ([("node plan", HostNodePlanEngine(src, n, vpi))] if kind == "plain" else [])
     for label, eng in engines:
         for name, arr in vals.items():
             if ramp and name == ramp[0]:
@@ -57,16 +60,22 @@ def run(kind, seed, ramps=False, extended=False):
                 eng.set_value(g.input_id(name), base)
             else:
                 eng.set_value(g.input_id(name), arr)
-        got = []
+        got, inst = [], []
         for lo, hi in ((0, 29), (29, 72)):
             if x is not None: eng.stream_in(0, x[lo:hi])
             ev = [(v, f - lo, GATE, s) for v, f, s in gates if lo <= f < hi]
             ev += [(v, f - lo, g.input_id(nm), s) for v, f, nm, s in value_events if lo <= f < hi]
             if ev: eng.push_events(ev)
             eng.process_block(hi - lo)
-            got.append(eng.read_voice_out())
-        got = np.concatenate(got)
+            got.append(eng.read_voice_out()); inst.append(eng.read_instance_out())
+        got, inst = np.concatenate(got), np.concatenate(inst)
         eng.close()
+        fold = np.zeros((frames, n // vpi), dtype=np.float32)     # `.iter().map(|v| v.out).sum()` in voice order
+        for k in range(vpi):
+            fold = fold + want.reshape(frames, n // vpi, vpi)[:, :, k]
+        if not np.array_equal(inst[:, :, 0], fold):
+            print("MISMATCH (instance fold)", kind, seed, label, flush=True)
+            return "MISMATCH"
         if not np.array_equal(got, want):
             print("MISMATCH", kind, seed, label, float(np.nanmax(np.abs(got - want))), "\n", src, flush=True)
             return "MISMATCH"

@@ -275,8 +275,7 @@ int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_co
    `graph.<name>.load_wav(..)` handle, oscen-lib/src/asset/mod.rs): the slots of a graph in declaration order, and the
    run-time load — `interleaved` is frames x channels f32 at the engine's sample rate (decoding / rate conversion stay with
    the caller); a mono SamplePlayer takes channel 0 (sample_player/mod.rs:36-49).  One buffer per slot per engine, shared
-   by its voices; every player bound to the slot restarts at the next block (mod.rs:107-112); frames == 0 empties the slot.
-   Graphs with a SamplePlayer run as generated kernels (OSCEN_B200_PLAN_FUSED). */
+   by its voices; every player bound to the slot restarts at the next block (mod.rs:107-112); frames == 0 empties the slot. */
 #define OSCEN_B200_MAX_ASSETS 4
 uint32_t oscen_b200_graph_n_assets(const oscen_b200_graph *g);
 int  oscen_b200_graph_asset_id(const oscen_b200_graph *g, const char *name);

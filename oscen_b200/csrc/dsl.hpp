@@ -31,7 +31,7 @@
  * shape (voices = [Voice::new(); N] + the MIDI chain) lowers to the voice graph's plan (lower_polyphonic).
  *
  * Assets: `external NAME: AudioAsset;` declares a slot the host loads audio into at run time
- * (oscen_b200_load_asset); `NAME -> player.buf` binds it to a SamplePlayer (generated kernels only).
+ * (oscen_b200_load_asset); `NAME -> player.buf` binds it to a SamplePlayer.
  *
  * Node arrays of library types (`[T::new(); N]`, `nodes[k].ep`) are unrolled into scalar nodes with the reference's
  * Broadcast / Parallel / FanIn edge shapes (ArrayExpander).

@@ -408,6 +408,9 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         for (int k = 0; k < plan::kMaxParams; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
         a.gate = nd.gate ? 1u : 0u; a.q = nd.cst[1];
         if (nd.type == plan::NodeType::Delay) { a.gate = nd.ring_cap; a.q = nd.max_delay; }
+        if (nd.type == plan::NodeType::SamplePlayer) {            /* the slot table rides in in1, the slot index in gate */
+            a.in1 = reinterpret_cast<const float *>(e->d_assets); a.gate = nd.asset >= 0 ? (uint32_t)nd.asset : 0xFFFFFFFFu;
+        }
         return a;
     };
     for (const plan::Launch &l : p.launches) {
@@ -429,6 +432,7 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         case plan::NodeType::OscSaw: osc_node_kernel<OSC_SAW><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::IirLowpass: iirlp_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::Delay: delay_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::SamplePlayer: sample_player_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         default:
             for (uint32_t k = 0; k < cnt; ++k) {                       /* stateless nodes: one stream kernel each */
                 const NodeArgs &a = a4.n[k];
@@ -561,10 +565,6 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
             for (const plan::Node &nd : pg.nodes) for (int k = 0; k < plan::kMaxStreamIn; ++k) if (nd.in[k].node >= 0 && nd.fb[k]) {
                 g_create_error = "PLAN_NODES: the feedback edge into `" + nd.name + "` needs the per-sample walk (node kernels render whole blocks): set plan = OSCEN_B200_PLAN_FUSED";
                 return OSCEN_B200_E_ARG;
-            }
-        if (cfg->plan == OSCEN_B200_PLAN_NODES)
-            for (const plan::Node &nd : pg.nodes) if (nd.type == plan::NodeType::SamplePlayer) {
-                g_create_error = "PLAN_NODES: `" + nd.name + "` (SamplePlayer) runs in a generated kernel: set plan = OSCEN_B200_PLAN_FUSED"; return OSCEN_B200_E_ARG;
             }
         if (cfg->plan == OSCEN_B200_PLAN_FUSED) {
             /* generate the fused kernel and compile it for sm_100a before any device memory is taken */

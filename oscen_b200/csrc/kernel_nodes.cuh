@@ -329,6 +329,24 @@ __global__ void __launch_bounds__(kCta) delay_node_kernel(const __grid_constant_
     a.state[(size_t)(a.state_base + 2u) * n + v] = s.output;
 }
 
+/* ---- SamplePlayer (mono): no stream or value inputs; the slot table travels in NodeArgs.in1 (a `const AssetTable *`),
+        the slot index in NodeArgs.gate (0xFFFFFFFF: `buf` is not connected — silence); state = the playhead */
+__global__ void __launch_bounds__(kCta) sample_player_node_kernel(const __grid_constant__ NodeArgs4 args) {
+    const NodeArgs &a = args.n[blockIdx.y];
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t frames = a.ctl->frames;
+    const AssetTable *tab = reinterpret_cast<const AssetTable *>(a.in1);
+    const bool bound = a.gate != 0xFFFFFFFFu && tab != nullptr;
+    const float *buf = bound ? tab->data[a.gate] : nullptr;
+    const uint32_t len = bound ? tab->frames[a.gate] : 0u;
+    uint32_t playhead = (bound && tab->reset[a.gate]) ? 0u : __float_as_uint(a.state[(size_t)a.state_base * n + v]);
+    if (playhead >= len) playhead = 0u;
+    for (uint32_t f = 0; f < frames; ++f) __stcs(a.out0 + (size_t)f * n + v, sample_player_process(playhead, buf, len));
+    a.state[(size_t)a.state_base * n + v] = __uint_as_float(playhead);
+}
+
 /* ---- stateless nodes */
 enum : int {
     EW_GAIN = 0,        /* Gain: in0 * (value | constant)        gain/mod.rs:30-35      */

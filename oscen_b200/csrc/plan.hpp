@@ -48,8 +48,7 @@ enum class NodeType : uint8_t {
                       graphs WITH a feedback edge run as generated kernels only */
     Up,            /* cross-rate stream edge outer -> inner (`* N` destination): StreamUpsampler of `policy`   */
     Down,          /* cross-rate stream edge inner -> outer: StreamDownsampler of `policy` (generated kernels only) */
-    SamplePlayer,  /* SamplePlayer (mono): loops the buffer loaded into asset slot `asset` (`external s: AudioAsset; s -> p.buf`);
-                      generated kernels only */
+    SamplePlayer,  /* SamplePlayer (mono): loops the buffer loaded into asset slot `asset` (`external s: AudioAsset; s -> p.buf`) */
 };
 enum : int { kPolicySinc = 0, kPolicySincIir = 1, kPolicyLinear = 2, kPolicyLatch = 3 };   /* == OSCEN_B200_POLICY_* */
 
@@ -154,7 +153,7 @@ inline uint32_t n_state_words(const Node &nd) {
     default: return 0;
     }
 }
-inline bool node_plan_has_kernel(NodeType t) { return t != NodeType::Up && t != NodeType::Down && t != NodeType::SamplePlayer; }
+inline bool node_plan_has_kernel(NodeType t) { return t != NodeType::Up && t != NodeType::Down; }
 /* Delay::prepare (delay/mod.rs:59-69): RingBuffer::new(min((2 * sr) as usize, 88200)) in PowerOfTwo mode */
 inline uint32_t delay_reference_capacity(float sample_rate) {
     const float t = 2.0f * sample_rate;

@@ -43,7 +43,8 @@ extern "C" void oscen_host_plan_free(void *h) { delete (HostPlan *)h; }
 extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi, float sample_rate, float *state, float *pv,
                                          const Event *events, uint32_t n_events, const float *ptab, uint32_t ramp_mask,
                                          uint32_t frames, const float *stream_in, int has_value_events, float *voice_out,
-                                         float *inst_out, float *mix_partial) {
+                                         float *inst_out, float *mix_partial, const float *const *asset_data,
+                                         const uint32_t *asset_frames, const uint32_t *asset_reset) {
     HostPlan *h = (HostPlan *)handle;
     const plan::Graph &g = h->g;
     const plan::Plan &p = h->p;
@@ -59,6 +60,8 @@ extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi,
     }
     BlockCtl ctl{};
     ctl.frames = frames; ctl.n_events = n_events; ctl.ramp_mask = ramp_mask; ctl.lcg_on = 0;
+    AssetTable assets{};
+    for (uint32_t k = 0; k < kMaxAssets && asset_data; ++k) { assets.data[k] = asset_data[k]; assets.frames[k] = asset_frames[k]; assets.reset[k] = asset_reset[k]; }
     const uint32_t grid = (n + kCta - 1) / kCta;
     const bool vec = !has_value_events && (n % 4u == 0u);
     auto S = [&](int i) { return h->streams[(size_t)i].data(); };
@@ -78,6 +81,9 @@ extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi,
         for (int k = 0; k < plan::kMaxParams; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
         a.gate = nd.gate ? 1u : 0u; a.q = nd.cst[1];
         if (nd.type == plan::NodeType::Delay) { a.gate = nd.ring_cap; a.q = nd.max_delay; }
+        if (nd.type == plan::NodeType::SamplePlayer) {
+            a.in1 = reinterpret_cast<const float *>(&assets); a.gate = nd.asset >= 0 ? (uint32_t)nd.asset : 0xFFFFFFFFu;
+        }
         return a;
     };
     using T = plan::NodeType;
@@ -100,6 +106,7 @@ extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi,
         case T::OscSaw: NODE_LAUNCH(osc_node_kernel<OSC_SAW>); break;
         case T::IirLowpass: NODE_LAUNCH(iirlp_node_kernel); break;
         case T::Delay: NODE_LAUNCH(delay_node_kernel); break;
+        case T::SamplePlayer: NODE_LAUNCH(sample_player_node_kernel); break;
 #undef NODE_LAUNCH
         default:
             for (uint32_t k = 0; k < cnt; ++k) {

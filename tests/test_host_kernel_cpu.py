@@ -79,12 +79,13 @@ def test_host_executed_tpt_filter_matches_the_reference_impulse_response():
 
 
 # ------------------------------------------------------------ `external` asset slots and SamplePlayer
-def test_host_executed_sample_player_graph_reproduces_the_reference_graph_test():
-    """oscen-lib/tests/sample_player_graph.rs:64-124 on the generated kernel: silent before any load, buffer A looped
-    (across a block boundary), then a load of B restarts the playhead and B loops — every voice of the bank alike"""
+@pytest.mark.parametrize("engine", [HostEngine, HostNodePlanEngine], ids=["generated_kernel", "node_plan"])
+def test_host_executed_sample_player_graph_reproduces_the_reference_graph_test(engine):
+    """oscen-lib/tests/sample_player_graph.rs:64-124 on the generated kernel and on the node plan: silent before any load,
+    buffer A looped (across a block boundary), then a load of B restarts the playhead and B loops — every voice alike"""
     a = np.array([0.1, -0.2, 0.3, -0.4, 0.5], dtype=np.float32)
     b = np.array([0.9, 0.8, 0.7], dtype=np.float32)
-    eng = HostEngine(text("player.graph"), 70, 1, 44100.0)
+    eng = engine(text("player.graph"), 70, 1, 44100.0)
     eng.process_block(8)
     assert (eng.read_voice_out() == 0.0).all()
     eng.load_asset("sample", a)
@@ -118,7 +119,8 @@ PLAYERS_DSL = """
 """
 
 
-def test_host_executed_two_sample_players_through_a_filter_match_the_oracle_walk():
+@pytest.mark.parametrize("engine", [HostEngine, HostNodePlanEngine], ids=["generated_kernel", "node_plan"])
+def test_host_executed_two_sample_players_through_a_filter_match_the_oracle_walk(engine):
     """two slots loaded at different times (one reloaded with a SHORTER buffer mid-run), a player whose `buf` is not
     connected (silence), per-voice level and cutoff — against a walk over the oracle's SamplePlayer and TptFilter"""
     import graph_walk as W
@@ -130,7 +132,7 @@ def test_host_executed_two_sample_players_through_a_filter_match_the_oracle_walk
     cutoff = (500.0 + 300.0 * np.arange(n)).astype(np.float32)
     script = [(20, {}), (50, {"loop_a": "a1"}), (41, {"loop_b": "b1"}), (64, {"loop_a": "a2"})]      # (frames, loads before the block)
 
-    eng = HostEngine(PLAYERS_DSL, n, 1, sr)
+    eng = engine(PLAYERS_DSL, n, 1, sr)
     eng.set_value(eng.graph.input_id("level"), level)
     eng.set_value(eng.graph.input_id("cutoff"), cutoff)
     got = []

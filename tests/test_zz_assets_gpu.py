@@ -15,13 +15,18 @@ GRAPHS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "graphs")
 f32 = np.float32
 
 
-def test_sample_player_graph_reproduces_the_reference_graph_test_on_the_gpu():
+@pytest.fixture(params=[0, 1], ids=["generated_fused_kernel", "node_plan"])
+def plan(request):
+    return request.param
+
+
+def test_sample_player_graph_reproduces_the_reference_graph_test_on_the_gpu(plan):
     """oscen-lib/tests/sample_player_graph.rs:64-124 for every voice of a 1000-voice bank"""
     from oscen_b200 import abi
     n = 1000
     a = np.array([0.1, -0.2, 0.3, -0.4, 0.5], dtype=np.float32)
     b = np.array([0.9, 0.8, 0.7], dtype=np.float32)
-    eng = abi.Engine.from_graph(open(os.path.join(GRAPHS, "player.graph")).read(), n, 1, 44100.0, plan=abi.PLAN_FUSED)
+    eng = abi.Engine.from_graph(open(os.path.join(GRAPHS, "player.graph")).read(), n, 1, 44100.0, plan=plan)
     eng.process_block(8)
     assert (eng.read_voice_out() == 0.0).all()
     eng.load_asset("sample", a)
@@ -38,7 +43,7 @@ def test_sample_player_graph_reproduces_the_reference_graph_test_on_the_gpu():
         eng.load_asset(3, a)                                        # the graph declares one slot
 
 
-def test_two_sample_players_through_a_filter_match_the_oracle_walk_on_the_gpu():
+def test_two_sample_players_through_a_filter_match_the_oracle_walk_on_the_gpu(plan):
     from oscen_b200 import abi
     n, sr = 5, 48000.0
     rng = np.random.default_rng(7)
@@ -47,7 +52,7 @@ def test_two_sample_players_through_a_filter_match_the_oracle_walk_on_the_gpu():
     cutoff = (500.0 + 300.0 * np.arange(n)).astype(np.float32)
     script = [(20, {}), (50, {"loop_a": "a1"}), (41, {"loop_b": "b1"}), (64, {"loop_a": "a2"})]
     g = abi.Graph(PLAYERS_DSL)
-    eng = abi.Engine.from_graph(g, n, 1, sr, plan=abi.PLAN_FUSED)
+    eng = abi.Engine.from_graph(g, n, 1, sr, plan=plan)
     eng.set_value(g.input_id("level"), level)
     eng.set_value(g.input_id("cutoff"), cutoff)
     got = []

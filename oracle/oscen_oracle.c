@@ -1285,6 +1285,10 @@ int orc_bank_set_value_ramp(orc_bank *b, uint32_t id, float target, uint32_t fra
     return 0;
 }
 int orc_bank_push_events(orc_bank *b, const orc_event *ev, size_t n) {
+    /* a ramped graph input is ONE ValueRampState read through .current every frame (emit_node.rs:317-321): a per-voice
+       write to it has no counterpart in the generated struct — refused, like a per-voice orc_bank_set_value on it */
+    for (size_t i = 0; i < n; ++i)
+        if (ev[i].input_id != ORC_EV_GATE && ev[i].input_id < MAX_IN && b->ramped[ev[i].input_id]) return -2;
     for (size_t i = 0; i < n; ++i) {
         uint32_t v = ev[i].voice;
         if (v >= b->n_voices) return -1;

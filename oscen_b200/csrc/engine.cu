@@ -815,6 +815,12 @@ int oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, siz
     for (size_t i = 0; i < n; ++i) {
         if (ev[i].voice >= e->cfg.n_voices) return arg_error(e, "push_events: voice out of range");
         if (ev[i].input_id != kEventGate && ev[i].input_id >= e->n_inputs) return arg_error(e, "push_events: input id");
+        /* a ramped input is ONE ValueRampState for the whole bank, read through .current every frame (emit_node.rs:317-321):
+           a per-voice write to it is as undefined as a per-voice set_value on it (refused there too) */
+        if (ev[i].input_id != kEventGate && e->ramped[ev[i].input_id]) {
+            e->err = "push_events: a value event on a ramped input (set_value_ramp was used on it): a ramped input is one ValueRampState (uniform)";
+            return OSCEN_B200_E_STATE;
+        }
     }
     for (size_t i = 0; i < n; ++i) {
         e->pending.push_back(Event{ev[i].voice, ev[i].frame_offset, ev[i].input_id, ev[i].scalar});

@@ -709,3 +709,18 @@ def test_sample_player_reference_tests():
     assert np.array_equal(_player_run(p, 10), np.concatenate([a, a]))
     L.orc_sample_player_publish(C.byref(p), b.ctypes.data, b.size)
     assert np.array_equal(_player_run(p, 6), np.concatenate([b, b]))
+
+
+def test_bank_refuses_value_events_on_a_ramped_input():
+    """a ramped graph input is one ValueRampState read through `.current` every frame (codegen/emit_node.rs:317-321): the
+    bank API's per-voice value events have no meaning on it (found by tests/host_kernel.py: engine and oracle used to
+    disagree once the ramp had completed) — refused on both sides, like a per-voice set_value on it"""
+    b = O.OracleBank(O.K_SAT1, 3, 1)
+    b.set_value(0, 900.0)
+    b.push_events([(1, 4, 0, 700.0)])                     # fine while the input has never been ramped
+    b.process_block(16)
+    b.set_value_ramp(0, 2500.0, 8)
+    with pytest.raises(Exception):
+        b.push_events([(1, 4, 0, 700.0)])
+    b.push_events([(1, 4, 1, 0.5)])                       # another input is unaffected
+    b.process_block(16)

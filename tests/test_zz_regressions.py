@@ -60,3 +60,26 @@ def test_inner_rate_nodes_keep_their_rate_when_a_frame_carries_events(fused_plan
     assert np.array_equal(render((frames,), same_value), base)                            # rewriting a value with itself is a no-op
     # and the rate really is 4 x: one octave up in `ratio` is not what a wrong rate would look like — compare with base_freq doubled
     assert not np.array_equal(render((frames,), [(v, 30 + v, 0, float(ratio[v] * 2.0)) for v in range(n)]), base)
+
+
+def test_value_events_on_a_ramped_input_are_refused(fused_plan):
+    """found by running the sat graphs with a ramp AND value events on `frequency` through tests/host_kernel.py: once the
+    ramp had completed, the engine kept the event's value while the oracle went back to the ramp's `.current` (which the
+    generated struct reads every frame, codegen/emit_node.rs:317-321).  The combination has no counterpart in the
+    reference — a ramped input is one ValueRampState — so engine, oracle and host harness now all refuse it"""
+    import os
+    from oscen_b200 import abi
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "graphs", "sat_1x.graph")).read()
+    eng = dsl_engine(src, 4, 1, SR, plan=fused_plan)
+    eng.set_value(0, 900.0)
+    eng.push_events([(1, 4, 0, 700.0)])                    # fine while the input has never been ramped
+    eng.process_block(16)
+    eng.set_value_ramp(0, 2500.0, 8)
+    with pytest.raises(abi.EngineError):
+        eng.push_events([(1, 4, 0, 700.0)])
+    eng.push_events([(1, 4, 1, 0.5)])                      # the other input is unaffected
+    eng.process_block(16)
+    ref = O.OracleBank(O.K_SAT1, 4, 1)
+    ref.set_value(0, 900.0); ref.push_events([(1, 4, 0, 700.0)]); ref.process_block(16)
+    ref.set_value_ramp(0, 2500.0, 8); ref.push_events([(1, 4, 1, 0.5)]); ref.process_block(16)
+    assert np.array_equal(eng.read_voice_out(), ref.read_voice_out())

@@ -273,6 +273,15 @@ int  oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t input_id, o
                             libnvrtc.so.12 and the engine's device headers next to the library).
    Both are bit-identical.  The graph object may be freed afterwards. */
 int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out);
+/* (inspection, host only) the tables of a BUILT-IN graph kind: value-input defaults, the state words of one voice after
+   new() + init(sample_rate), output channels, dynamic shared memory of its fused kernel.  For tools and for the CPU suite's
+   host-executed kernel check (tests/host_kernel.py); OSCEN_B200_GRAPH_CUSTOM graphs answer oscen_b200_graph_kernel_info. */
+typedef struct {
+    uint32_t n_inputs, n_state, channels, dyn_smem_bytes, has_stream_in, reserved;
+} oscen_b200_kind_tables;
+int  oscen_b200_kind_info(uint32_t graph_kind, float sample_rate, oscen_b200_kind_tables *info,
+                          float *defaults /* [OSCEN_B200_MAX_INPUTS] or NULL */, uint32_t *state_words, size_t state_cap);
+
 /* `external NAME: AudioAsset;` slots (oscen-graph-compiler/src/parse.rs:447-456; the generated graph's
    `graph.<name>.load_wav(..)` handle, oscen-lib/src/asset/mod.rs): the slots of a graph in declaration order, and the
    run-time load — `interleaved` is frames x channels f32 at the engine's sample rate (decoding / rate conversion stay with

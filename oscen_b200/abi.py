@@ -40,7 +40,7 @@ SYMBOLS = [
     "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
     "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
-    "oscen_b200_graph_kernel_info", "oscen_b200_graph_n_assets", "oscen_b200_graph_asset_id", "oscen_b200_load_asset",
+    "oscen_b200_kind_info", "oscen_b200_graph_kernel_info", "oscen_b200_graph_n_assets", "oscen_b200_graph_asset_id", "oscen_b200_load_asset",
 ]
 
 
@@ -48,6 +48,23 @@ class Config(C.Structure):
     _fields_ = [("graph_kind", C.c_uint32), ("n_voices", C.c_uint32), ("voices_per_instance", C.c_uint32),
                 ("sample_rate", C.c_float), ("device", C.c_int32), ("plan", C.c_uint32), ("keep", C.c_uint32),
                 ("reserved", C.c_uint32)]
+
+
+class KindTables(C.Structure):
+    _fields_ = [("n_inputs", C.c_uint32), ("n_state", C.c_uint32), ("channels", C.c_uint32), ("dyn_smem_bytes", C.c_uint32),
+                ("has_stream_in", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def kind_info(graph_kind, sample_rate=48000.0):
+    """(KindTables, defaults [n_inputs] f32, initial state words of one voice [n_state] u32) of a built-in graph kind"""
+    L = load()
+    t = KindTables()
+    d = (C.c_float * 28)()
+    if L.oscen_b200_kind_info(graph_kind, sample_rate, C.byref(t), d, None, 0) != 0:
+        raise EngineError(f"kind_info: bad kind {graph_kind}")
+    w = (C.c_uint32 * max(t.n_state, 1))()
+    L.oscen_b200_kind_info(graph_kind, sample_rate, None, None, w, t.n_state)
+    return t, np.array(d[:t.n_inputs], dtype=np.float32), np.frombuffer(w, dtype=np.uint32)[:t.n_state].copy()
 
 
 class KernelInfo(C.Structure):
@@ -138,6 +155,7 @@ def load():
     L.oscen_b200_graph_has_midi.argtypes = [vp]
     L.oscen_b200_graph_codegen.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_jit_check.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.oscen_b200_kind_info.argtypes = [C.c_uint32, C.c_float, C.POINTER(KindTables), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_size_t]
     L.oscen_b200_graph_n_assets.argtypes = [vp]
     L.oscen_b200_graph_n_assets.restype = C.c_uint32
     L.oscen_b200_graph_asset_id.argtypes = [vp, C.c_char_p]

@@ -506,6 +506,27 @@ int oscen_b200_device_count(void) {
 
 uint32_t oscen_b200_n_inputs(uint32_t kind) { return kind < 7 ? kNInputs[kind] : 0; }
 
+int oscen_b200_kind_info(uint32_t kind, float sample_rate, oscen_b200_kind_tables *info, float *defaults, uint32_t *state_words, size_t state_cap) {
+    if (kind >= OSCEN_B200_GRAPH_CUSTOM || !(sample_rate > 0.0f)) return OSCEN_B200_E_ARG;
+    const uint32_t n_state = n_state_of(kind);
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->n_inputs = kind < 7 ? kNInputs[kind] : 0u; info->n_state = n_state;
+        info->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2u : 1u;
+        info->dyn_smem_bytes = (kind == OSCEN_B200_GRAPH_SAT_1X || kind == OSCEN_B200_GRAPH_SAT_4X) ? (uint32_t)kSatDyn
+                               : kind == OSCEN_B200_GRAPH_EPIANO ? (uint32_t)kEpDyn
+                               : is_clip(kind) ? (uint32_t)clip_dyn_bytes(clip_policy(kind), clip_log2f(kind)) : 0u;
+        info->has_stream_in = has_stream_in(kind) ? 1u : 0u;
+    }
+    if (defaults) for (uint32_t i = 0; i < kMaxInputs; ++i) defaults[i] = kind < 7 ? kDefaults[kind][i] : 0.0f;
+    if (state_words) {
+        if (n_state > state_cap) return OSCEN_B200_E_ARG;
+        const std::vector<uint32_t> init = initial_state(kind, sample_rate, nullptr, n_state);
+        memcpy(state_words, init.data(), init.size() * sizeof(uint32_t));
+    }
+    return 0;
+}
+
 const char *oscen_b200_last_error(const oscen_b200_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
 void oscen_b200_destroy(oscen_b200_engine *e) {

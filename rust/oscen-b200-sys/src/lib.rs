@@ -66,6 +66,17 @@ pub struct oscen_b200_input_info {
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
+pub struct oscen_b200_kind_tables {
+    pub n_inputs: u32,
+    pub n_state: u32,
+    pub channels: u32,
+    pub dyn_smem_bytes: u32,
+    pub has_stream_in: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
 pub struct oscen_b200_kernel_info {
     pub source_len: u32,
     pub n_state: u32,
@@ -120,6 +131,7 @@ extern "C" {
     pub fn oscen_b200_create_from_graph(g: *const oscen_b200_graph, cfg: *const oscen_b200_config, out: *mut *mut oscen_b200_engine) -> c_int;
     pub fn oscen_b200_graph_codegen(g: *const oscen_b200_graph, dst: *mut c_char, cap: usize) -> c_int;
     pub fn oscen_b200_graph_jit_check(g: *const oscen_b200_graph, log: *mut c_char, log_cap: usize) -> c_int;
+    pub fn oscen_b200_kind_info(graph_kind: u32, sample_rate: f32, info: *mut oscen_b200_kind_tables, defaults: *mut f32, state_words: *mut u32, state_cap: usize) -> c_int;
     pub fn oscen_b200_graph_n_assets(g: *const oscen_b200_graph) -> u32;
     pub fn oscen_b200_graph_asset_id(g: *const oscen_b200_graph, name: *const c_char) -> c_int;
     pub fn oscen_b200_load_asset(e: *mut oscen_b200_engine, asset_id: u32, interleaved: *const f32, frames: u32, channels: u32) -> c_int;

@@ -1,0 +1,65 @@
+/*
+ * tests/csrc/host_builtin_runner.cpp — TEST INFRASTRUCTURE.  Runs one block of a HAND-WRITTEN fused kernel of a built-in
+ * graph kind on the host (kernel_fm.cuh, kernel_others.cuh, kernel_resample.cuh compiled by g++ against
+ * tests/csrc/host_cuda/cuda_runtime.h): the dispatch restates engine.cu's launch_fused() / launch_clip().
+ */
+#include "kernel_fm.cuh"
+#include "kernel_others.cuh"
+#include "kernel_resample.cuh"
+
+namespace {
+using namespace oscen;
+template <int P> void clip_policy_launch(const KernelArgs &a, uint32_t grid, int l) {
+    switch (l) {
+    case 1: host_launch(grid, 1, kCta, [&]() { clip_kernel<P, 1>(a); }); break;
+    case 2: host_launch(grid, 1, kCta, [&]() { clip_kernel<P, 2>(a); }); break;
+    default: host_launch(grid, 1, kCta, [&]() { clip_kernel<P, 3>(a); }); break;
+    }
+}
+}  // namespace
+
+extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t n_voices, uint32_t vpi, float sample_rate, float *state,
+                                            float *pv, const oscen::Event *events, uint32_t n_events, const float *ptab, uint32_t ramp_mask,
+                                            uint32_t frames, const float *stream_in, float *voice_out, float *inst_out, float *inst_state,
+                                            float *mix_partial, const float *uniform_p) {
+    using namespace oscen;
+    if (n_voices == 0 || vpi == 0 || kCta % vpi != 0 || n_voices % vpi != 0 || frames > kMaxBlock) return -1;
+    BlockCtl ctl{};
+    ctl.frames = frames; ctl.n_events = n_events; ctl.ramp_mask = ramp_mask; ctl.lcg_on = 0;
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_voices = n_voices; a.vpi = vpi; a.n_inst = n_voices / vpi; a.channels = kind == 4u ? 2u : 1u;
+    a.state = state; a.pv = pv; a.events = events; a.ptab = ptab; a.ctl = &ctl; a.stream_in = stream_in;
+    a.voice_out = voice_out; a.inst_out = inst_out; a.inst_state = inst_state; a.mix_partial = mix_partial;
+    for (uint32_t i = 0; i < kMaxInputs; ++i) a.u.p[i] = uniform_p[i];
+    a.u.sr = sample_rate;
+    if (kind == 0u) {
+        const float *p = a.u.p;
+        adsr_derive(a.u.env[0], p[I_OP3_A], p[I_OP3_D], p[I_OP3_R], a.u.sr);
+        adsr_derive(a.u.env[1], p[I_OP2_A], p[I_OP2_D], p[I_OP2_R], a.u.sr);
+        adsr_derive(a.u.env[2], p[I_OP1_A], p[I_OP1_D], p[I_OP1_R], a.u.sr);
+        adsr_derive(a.u.env[3], p[I_F_A], p[I_F_D], p[I_F_R], a.u.sr);
+    }
+    const uint32_t grid = (n_voices + kCta - 1) / kCta;
+    switch (kind) {
+    case 0: if (general) host_launch(grid, 1, kCta, [&]() { fm_voice_kernel<true>(a); }); else host_launch(grid, 1, kCta, [&]() { fm_voice_kernel<false>(a); }); break;
+    case 1: host_launch(grid, 1, kCta, [&]() { twin_peaks_kernel(a); }); break;
+    case 2: host_launch(grid, 1, kCta, [&]() { sat_kernel<1>(a); }); break;
+    case 3: host_launch(grid, 1, kCta, [&]() { sat_kernel<4>(a); }); break;
+    case 4: host_launch(grid, 1, kCta, [&]() { epiano_kernel(a); }); break;
+    case 5: host_launch(grid, 1, kCta, [&]() { synth_kernel<false>(a); }); break;
+    case 6: host_launch(grid, 1, kCta, [&]() { synth_kernel<true>(a); }); break;
+    default: {
+        if (kind < 7u || kind > 19u) return -1;
+        if (kind == 7u) { host_launch(grid, 1, kCta, [&]() { clip_kernel<POL_LATCH, 0>(a); }); break; }
+        const int pol = (int)(kind - 8u) / 3, l = 1 + (int)(kind - 8u) % 3;
+        switch (pol) {
+        case POL_SINC: clip_policy_launch<POL_SINC>(a, grid, l); break;
+        case POL_SINC_IIR: clip_policy_launch<POL_SINC_IIR>(a, grid, l); break;
+        case POL_LINEAR: clip_policy_launch<POL_LINEAR>(a, grid, l); break;
+        default: clip_policy_launch<POL_LATCH>(a, grid, l); break;
+        }
+    } break;
+    }
+    return 0;
+}

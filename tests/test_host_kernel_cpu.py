@@ -208,3 +208,83 @@ def test_host_fuzzer_findings_stay_fixed(seed):
     sys.path.insert(0, os.path.join(os.path.dirname(GRAPHS), "..", "tools"))
     import fuzz_host_kernels as F
     assert F.run("multirate", seed) == "ok"
+
+
+# ------------------------------------------------------------ every other hand-written fused kernel (built-in graph kinds)
+@pytest.mark.parametrize("kind", [O.K_SYNTH, O.K_SYNTH_ADSR, O.K_SAT1, O.K_SAT4, O.K_TWIN], ids=["synth", "synth_adsr", "sat_1x", "sat_4x", "twin_peaks"])
+def test_host_executed_hand_written_kernels_match_oracle_banks(kind):
+    """kernel_others.cuh on the host (tests/csrc/host_builtin_runner.cpp restates launch_fused()), 70 voices over two CTAs:
+    per-voice values, gates, a ramp across a block boundary, per-voice value events — bit-identical to the oracle banks"""
+    from host_kernel import HostBuiltinEngine
+    n = 70
+    ref, host = O.OracleBank(kind, n, 1), HostBuiltinEngine(kind, n, 1)
+    x = np.stack([lcg_noise(512, 77 + v) for v in range(n)], axis=1) if kind == O.K_TWIN else None
+
+    def script(b):
+        out = []
+        if kind in (O.K_SYNTH, O.K_SYNTH_ADSR):
+            b.set_value(2, (80.0 + 9.0 * np.arange(n)).astype(np.float32)); b.set_value(3, (400.0 + 50.0 * np.arange(n)).astype(np.float32))
+        elif kind in (O.K_SAT1, O.K_SAT4):
+            b.set_value(0, (2000.0 * (0.5 + lcg_uniform(n, 5))).astype(np.float32))
+        for blk, frames in enumerate((200, 50, 90)):
+            if kind == O.K_TWIN:
+                b.stream_in(0, x[blk * 100:blk * 100 + frames])
+            if kind == O.K_SYNTH_ADSR and blk < 2:
+                b.push_events([(v, (v + 3 * blk) % 50, GATE, 0.9 if blk == 0 else 0.0) for v in range(n)])
+            if blk == 1 and kind not in (O.K_SAT1, O.K_SAT4):
+                b.set_value_ramp(0, 7.0 if kind != O.K_TWIN else 1200.0, 70)
+                b.push_events([(5, 40, 1, 0.3 if kind != O.K_TWIN else 2500.0)])
+            if blk == 1 and kind in (O.K_SAT1, O.K_SAT4):
+                b.set_value_ramp(1, 0.9, 70)                                              # amplitude ramps ...
+                b.push_events([(v, 7 + v % 30, 0, 900.0 + 10.0 * v) for v in range(n)])   # ... while every voice is retuned
+            b.process_block(frames); out.append(b.read_voice_out())
+        return np.concatenate(out)
+
+    yr, yh = script(ref), script(host)
+    assert np.abs(yr).max() > 0.01
+    assert np.array_equal(yh, yr), float(np.abs(yh - yr).max())
+
+
+def test_host_executed_electric_piano_kernel_matches_oracle_voices_and_stereo_instances():
+    """BASELINE configs[2]'s graph (kernel_others.cuh epiano_kernel: 32-harmonic voices, 16 per instance -> sum -> Tremolo ->
+    Frame<2>), 5 instances over two CTAs, driven by per-voice frequency + gate events (what the MIDI front emits), a value
+    change and a ramp on the tremolo depth: per-voice output and the stereo instance output bit-identical to the oracle"""
+    from host_kernel import HostBuiltinEngine
+    n, vpi = 80, 16
+    ref, host = O.OracleBank(O.K_EPIANO, n, vpi), HostBuiltinEngine(O.K_EPIANO, n, vpi)
+
+    def script(b):
+        out_v, out_i = [], []
+        freqs = (110.0 * 2.0 ** ((np.arange(n) % 29) / 12.0)).astype(np.float32)
+        ev = []
+        for v in range(0, n, 3):
+            ev.append((v, 2 + v % 40, 0, float(freqs[v])))
+            ev.append((v, 2 + v % 40, GATE, 0.4 + 0.005 * v))
+        b.push_events(ev)
+        for _ in range(2):
+            b.process_block(200); out_v.append(b.read_voice_out()); out_i.append(b.read_instance_out())
+        b.push_events([(v, 5 + v % 7, GATE, 0.0) for v in range(0, n, 6)])
+        b.set_value(3, 60.0)
+        b.set_value_ramp(7, 0.8, 150)
+        for _ in range(2):
+            b.process_block(120); out_v.append(b.read_voice_out()); out_i.append(b.read_instance_out())
+        return np.concatenate(out_v), np.concatenate(out_i)
+
+    (vr, ir), (vh, ih) = script(ref), script(host)
+    assert np.abs(ir).max() > 1e-3 and np.abs(ir[..., 0] - ir[..., 1]).max() > 1e-6
+    assert np.array_equal(vh, vr) and np.array_equal(ih, ir)
+
+
+@pytest.mark.parametrize("kind", range(7, 20))
+def test_host_executed_clip_kernels_match_oracle(kind):
+    """kernel_resample.cuh: ClipRef and the 12 ClipOversampled kinds (4 policies x {2, 4, 8}), state handed across blocks"""
+    from host_kernel import HostBuiltinEngine
+    n = 6
+    ref, host = O.OracleBank(kind, n, 1), HostBuiltinEngine(kind, n, 1)
+    x = np.stack([lcg_noise(300, 900 + v) for v in range(n)], axis=1) * np.float32(1.4)
+    pos, yr, yh = 0, [], []
+    for frames in (128, 22, 150):
+        for b, outs in ((ref, yr), (host, yh)):
+            b.stream_in(0, x[pos:pos + frames]); b.process_block(frames); outs.append(b.read_voice_out())
+        pos += frames
+    assert np.array_equal(np.concatenate(yh), np.concatenate(yr))

@@ -161,7 +161,8 @@ int  oscen_b200_set_value_ramp(oscen_b200_engine *e, uint32_t input_id, float ta
 /* events for the NEXT process_block; frame_offset >= frames of that block are dropped, more
    than 32 events per voice per block are dropped (ArrayVec<_,32>::try_push).  A value event on an
    input that set_value_ramp has been used on is refused (OSCEN_B200_E_STATE): a ramped input is one
-   ValueRampState for the whole bank, as for per-voice oscen_b200_set_value on it. */
+   ValueRampState for the whole bank, as for per-voice oscen_b200_set_value on it.  So is a value event on
+   OSCEN_B200_GRAPH_EPIANO's instance-level inputs 7 / 8 (the graph's Tremolo): set_value / set_value_ramp. */
 int  oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, size_t n);
 /* raw MIDI into instance `instance`'s MidiParser -> VoiceAllocator<N> -> MidiVoiceHandler chain
    (host-side integer logic; emits per-voice frequency + gate events) */

@@ -1280,6 +1280,8 @@ int orc_bank_set_value(orc_bank *b, uint32_t id, uint32_t first, uint32_t count,
 int orc_bank_set_value_ramp(orc_bank *b, uint32_t id, float target, uint32_t frames) {
     if (id >= (uint32_t)N_INPUTS[b->kind]) return -1;
     if (!b->uniform[id]) return -2;
+    for (uint32_t v = 0; v < b->n_voices; ++v)                    /* the mirror image of orc_bank_push_events' refusal */
+        for (uint32_t k = 0; k < b->npend[v]; ++k) if (b->pend[v][k].input_id == id) return -2;
     b->ramped[id] = 1;
     if (target != b->ramps[id].target) orc_ramp_set_with_ramp(&b->ramps[id], target, frames);
     return 0;
@@ -1289,6 +1291,9 @@ int orc_bank_push_events(orc_bank *b, const orc_event *ev, size_t n) {
        write to it has no counterpart in the generated struct — refused, like a per-voice orc_bank_set_value on it */
     for (size_t i = 0; i < n; ++i)
         if (ev[i].input_id != ORC_EV_GATE && ev[i].input_id < MAX_IN && b->ramped[ev[i].input_id]) return -2;
+    /* ElectricPianoGraph: vibrato_intensity / vibrato_speed feed the instance's Tremolo (main.rs:88-90), not a voice */
+    for (size_t i = 0; i < n; ++i)
+        if (b->kind == K_EPIANO && (ev[i].input_id == 7u || ev[i].input_id == 8u)) return -3;
     for (size_t i = 0; i < n; ++i) {
         uint32_t v = ev[i].voice;
         if (v >= b->n_voices) return -1;

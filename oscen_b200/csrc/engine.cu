@@ -819,6 +819,9 @@ int oscen_b200_set_value_ramp(oscen_b200_engine *e, uint32_t id, float target, u
     if (!e) return OSCEN_B200_E_ARG;
     if (id >= e->n_inputs) return arg_error(e, "set_value_ramp: id");
     if (!e->uniform[id]) { e->err = "set_value_ramp: input is not uniform"; return OSCEN_B200_E_STATE; }
+    for (const Event &p : e->pending) if (p.input_id == id) {     /* the mirror image of push_events' refusal */
+        e->err = "set_value_ramp: value events are pending on this input: a ramped input is one ValueRampState (uniform)"; return OSCEN_B200_E_STATE;
+    }
     e->ramped[id] = true;
     if (target != e->ramps[id].target) {
         e->ramps[id].set_with_ramp(target, frames);
@@ -838,6 +841,10 @@ int oscen_b200_push_events(oscen_b200_engine *e, const oscen_b200_event *ev, siz
         if (ev[i].input_id != kEventGate && ev[i].input_id >= e->n_inputs) return arg_error(e, "push_events: input id");
         /* a ramped input is ONE ValueRampState for the whole bank, read through .current every frame (emit_node.rs:317-321):
            a per-voice write to it is as undefined as a per-voice set_value on it (refused there too) */
+        /* ElectricPiano: vibrato_intensity / vibrato_speed feed the INSTANCE's Tremolo (main.rs:88-90), not a voice: a per-voice
+           event has no voice to land on (the kernel reads them once per output tile, from the instance's first voice) */
+        if (e->cfg.graph_kind == OSCEN_B200_GRAPH_EPIANO && (ev[i].input_id == 7u || ev[i].input_id == 8u))
+            return arg_error(e, "push_events: vibrato_intensity / vibrato_speed are instance-level inputs (the graph's Tremolo): use set_value / set_value_ramp");
         if (ev[i].input_id != kEventGate && e->ramped[ev[i].input_id]) {
             e->err = "push_events: a value event on a ramped input (set_value_ramp was used on it): a ramped input is one ValueRampState (uniform)";
             return OSCEN_B200_E_STATE;

@@ -74,6 +74,9 @@ def test_value_events_on_a_ramped_input_are_refused(fused_plan):
     eng.set_value(0, 900.0)
     eng.push_events([(1, 4, 0, 700.0)])                    # fine while the input has never been ramped
     eng.process_block(16)
+    with pytest.raises(abi.EngineError):
+        eng.set_value_ramp(0, 2500.0, 8)                   # the event left the input per-voice: a ramp needs a uniform input
+    eng.set_value(0, 900.0)
     eng.set_value_ramp(0, 2500.0, 8)
     with pytest.raises(abi.EngineError):
         eng.push_events([(1, 4, 0, 700.0)])
@@ -81,5 +84,5 @@ def test_value_events_on_a_ramped_input_are_refused(fused_plan):
     eng.process_block(16)
     ref = O.OracleBank(O.K_SAT1, 4, 1)
     ref.set_value(0, 900.0); ref.push_events([(1, 4, 0, 700.0)]); ref.process_block(16)
-    ref.set_value_ramp(0, 2500.0, 8); ref.push_events([(1, 4, 1, 0.5)]); ref.process_block(16)
+    ref.set_value(0, 900.0); ref.set_value_ramp(0, 2500.0, 8); ref.push_events([(1, 4, 1, 0.5)]); ref.process_block(16)
     assert np.array_equal(eng.read_voice_out(), ref.read_voice_out())

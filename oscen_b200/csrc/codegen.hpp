@@ -169,7 +169,7 @@ struct Emitter {
                 line(1, "AdsrDerived " + D(i) + "; adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", " + SR(i) + ");");
                 /* update_sustain_level()'s sustain-level / countdown-clamp part only changes with its inputs: refreshed at block
                    start and on frames where a value input moved or a gate arrived (nodes.cuh adsr_refresh), not every sample */
-                if (hoist_adsr) line(1, "AdsrHot h" + std::to_string(i) + "; adsr_refresh(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");");
+                if (hoist_adsr) line(1, "AdsrHot h" + std::to_string(i) + "; adsr_refresh<false>(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");");
                 break;
             case T::FmOperator:
                 line(1, "FmOpState " + N(i) + "; " + N(i) + ".phase = a.state[(size_t)(" + base + " + 0u) * n + vs]; " + N(i) + ".prev = a.state[(size_t)(" + base + " + 1u) * n + vs];");
@@ -219,6 +219,14 @@ struct Emitter {
             line(1, "                         ((unsigned long long)__float_as_uint(a.state[(size_t)(" + f + " + 1u) * n + vs]) << 32);");
         }
         line(1, "EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);");
+        {   /* a gate-off at frame 0 starts from the release length the previous block ended with (AdsrState::r_gate) */
+            bool any = false;
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr) {
+                if (!any) line(1, "const bool ev0 = ec.due(0u);");
+                any = true;
+                line(1, "adsr_begin_block(" + N(i) + ", " + D(i) + ", ev0);");
+            }
+        }
         line(1, "for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {");
         line(2, "const uint32_t fe = min(kTileF, frames - f0);");
         line(2, "for (uint32_t ff = 0; ff < fe; ++ff) {");

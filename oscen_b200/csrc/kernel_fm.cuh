@@ -97,15 +97,18 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
        sustain-level / countdown-clamp part of update_sustain_level() runs at block start and after
        gate events only (see adsr_refresh) */
     AdsrHot h3, h2, h1, hf;
-#define OSC_FM_REFRESH()                                                    \
+#define OSC_FM_REFRESH(COMMIT)                                              \
     do {                                                                    \
-        adsr_refresh(e3, h3, P[I_OP3_S], d3); adsr_refresh(e2, h2, P[I_OP2_S], d2); \
-        adsr_refresh(e1, h1, P[I_OP1_S], d1); adsr_refresh(ef, hf, P[I_F_S], df);   \
+        adsr_refresh<COMMIT>(e3, h3, P[I_OP3_S], d3); adsr_refresh<COMMIT>(e2, h2, P[I_OP2_S], d2); \
+        adsr_refresh<COMMIT>(e1, h1, P[I_OP1_S], d1); adsr_refresh<COMMIT>(ef, hf, P[I_F_S], df);   \
     } while (0)
-    OSC_FM_REFRESH();
-
     EventCursor ec;
     ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+    {   /* the release length a gate-off at frame 0 starts from is the previous block's (AdsrState::r_gate) */
+        const bool ev0 = ec.due(0u);
+        adsr_begin_block(e3, d3, ev0); adsr_begin_block(e2, d2, ev0); adsr_begin_block(e1, d1, ev0); adsr_begin_block(ef, df, ev0);
+    }
+    OSC_FM_REFRESH(false);
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                         }
                     }
                     OSC_FM_INCS();
-                    if (!GENERAL) OSC_FM_REFRESH();
+                    if (!GENERAL) OSC_FM_REFRESH(true);
                     ec.advance(j);
                 } else if (GENERAL && ramp_mask) {
                     if (adsr_derived_stale(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R])) adsr_derive_r(d3, P[I_OP3_A], P[I_OP3_D], P[I_OP3_R], sr);

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kCta) adsr_node_kernel(const __grid_constant__
     OSC_NODE_PROLOGUE(4)
     AdsrState s; adsr_load(s, a.state, a.state_base, n, v);
     AdsrDerived d; adsr_derive_r(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
-    AdsrHot h; adsr_refresh(s, h, prm.P[2], d);          /* re-run after every event / ramped frame */
+    adsr_begin_block(s, d, ec.due(0u));
+    AdsrHot h; adsr_refresh<false>(s, h, prm.P[2], d);   /* re-run after every event / ramped frame */
     for (uint32_t f = 0; f < frames; ++f) {
         const bool due = ec.due(f);
         if (ramp_mask | (uint32_t)due) {

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
     AdsrDerived d;
     adsr_derive_r(d, prm.P[4], prm.P[5], prm.P[7], sr);
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+    adsr_begin_block(env, d, ec.due(0u));
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);

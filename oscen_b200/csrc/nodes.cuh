@@ -92,6 +92,11 @@ constexpr float kAdsrCurveK = 4.6051702f;    /* adsr.rs:8 */
 struct AdsrState {
     uint32_t stage, rem;
     float level, vel;
+    uint32_t r_gate;          /* `release_samples` as cached by the last process() (adsr.rs:117-134): the countdown a gate-OFF
+                                 starts from (set_stage(Release), adsr.rs:136-157) — it lags `release` by one frame, which is
+                                 visible when the release time grows on the very frame of the note-off.  Equal to the derived
+                                 r_n at all times except from block start to the first processed frame, so it costs no
+                                 per-frame work; it travels in the upper bits of the stage word (state_io.cuh). */
 };
 /* recalculate_cached_steps(), adsr.rs:117-134 — a pure function of (attack, decay, release, sr) */
 struct AdsrDerived {
@@ -136,13 +141,20 @@ OSC_D void adsr_on_gate(AdsrState &s, float velocity, float attack_raw, float re
                         const AdsrDerived &d) {
     if (velocity > 0.0f) {
         s.vel = clampf(velocity, 0.0f, 1.0f);
+        s.r_gate = d.r_n;                                  /* gate-on runs update_sustain_level(): the cache is fresh again */
         if (attack_raw <= kAdsrMinTime) { s.level = 1.0f; s.stage = ST_DECAY; s.rem = d.d_n; }
         else { s.stage = ST_ATTACK; s.rem = d.a_n; }
     } else if (release_raw <= kAdsrMinTime) {
         s.stage = ST_IDLE; s.level = 0.0f; s.rem = 0u;
     } else {
-        s.stage = ST_RELEASE; s.rem = d.r_n;
+        s.stage = ST_RELEASE; s.rem = s.r_gate;            /* the length cached by the LAST process(); this frame's process()
+                                                              clamps it to the new one (adsr_refresh) */
     }
+}
+/* block start, after `d` was derived from the block's first inputs: a voice with no event at frame 0 is past its first
+   process() before any gate can arrive, so its cache is the new length already; a fresh state (0) knows no older one */
+OSC_D void adsr_begin_block(AdsrState &s, const AdsrDerived &d, bool event_at_frame0) {
+    if (!event_at_frame0 || s.r_gate == 0u) s.r_gate = d.r_n;
 }
 /* process(), adsr.rs:84-115 (apply_parameters + update_sustain_level), :209-250 (process_stage),
    :175-207 (complete_stage).  Returns `output`.
@@ -155,7 +167,11 @@ OSC_D void adsr_on_gate(AdsrState &s, float velocity, float attack_raw, float re
      * samples_remaining = max(min(samples_remaining, stage_len), 1)  — idempotent while the stage
        lengths are unchanged: the countdown only decreases or is reset to exactly a stage length. */
 struct AdsrHot { float sus; };
+/* COMMIT: the call belongs to a frame's process() (after its gate handlers), which re-caches the step counts; the
+   block-start call (before frame 0's events are seen) passes false */
+template <bool COMMIT = true>
 OSC_D void adsr_refresh(AdsrState &s, AdsrHot &h, float sustain_in, const AdsrDerived &d) {
+    if (COMMIT) s.r_gate = d.r_n;
     const float sustain = clampf(sustain_in, 0.0f, 1.0f);
     h.sus = clampf(sustain * s.vel, 0.0f, 1.0f);
     if (s.rem > 0u) {

@@ -10,13 +10,14 @@
 namespace oscen {
 
 OSC_D void adsr_load(AdsrState &s, const float *st, uint32_t base, uint32_t n, uint32_t v) {
-    s.stage = __float_as_uint(st[(size_t)(base + 0) * n + v]);
+    const uint32_t w = __float_as_uint(st[(size_t)(base + 0) * n + v]);      /* stage in bits 0-2, r_gate above */
+    s.stage = w & 7u; s.r_gate = w >> 3;
     s.rem = __float_as_uint(st[(size_t)(base + 1) * n + v]);
     s.level = st[(size_t)(base + 2) * n + v];
     s.vel = st[(size_t)(base + 3) * n + v];
 }
 OSC_D void adsr_store(const AdsrState &s, float *st, uint32_t base, uint32_t n, uint32_t v) {
-    st[(size_t)(base + 0) * n + v] = __uint_as_float(s.stage);
+    st[(size_t)(base + 0) * n + v] = __uint_as_float(s.stage | (umin(s.r_gate, 0x1FFFFFFFu) << 3));
     st[(size_t)(base + 1) * n + v] = __uint_as_float(s.rem);
     st[(size_t)(base + 2) * n + v] = s.level;
     st[(size_t)(base + 3) * n + v] = s.vel;

@@ -290,16 +290,12 @@ def test_host_executed_clip_kernels_match_oracle(kind):
     assert np.array_equal(np.concatenate(yh), np.concatenate(yr))
 
 
-@pytest.mark.xfail(strict=True, reason="known deviation (DESIGN.md §2): the kernels derive the release length from THIS frame's release "
-                                       "value; the reference's gate-off reads the length cached by the previous process()")
-def test_known_deviation_gate_off_on_the_frame_the_release_time_grows():
+def test_gate_off_on_the_frame_the_release_time_grows_uses_the_cached_length():
     """found by tools/fuzz_host_builtin.py.  AdsrEnvelope::handle_gate_event (adsr.rs:252-273): a gate-OFF calls
     set_stage(Release), which counts down from `release_samples` as cached by the last process() — so when `release` was
     raised since then (a host write between blocks with the note-off at frame 0, or a ramp / value event on the note-off's
-    frame) the reference still releases over min(old, new) samples.  Every back end here (shared adsr_on_gate in
-    nodes.cuh) uses the new length.  Shrinking the release, growing it on any other frame, and every other parameter change
-    are bit-identical (this test's siblings below).  The exact fix needs the previous release length in the persistent
-    state; it waits for a round with GPU time to measure the hot FM kernel."""
+    frame) the reference releases over min(old, new) samples.  The kernels used to start from the new length; the cached
+    one now travels in the upper bits of the ADSR stage word (nodes.cuh AdsrState::r_gate, state_io.cuh)."""
     import graph_walk as W
     src = ("input r: value = 0.004; input gate: event; output stream out; node env = AdsrEnvelope::new(0.002, 0.003, 0.6, 0.004); "
            "connection gate -> env.gate; connection r -> env.release; connection env.output -> out;")
@@ -323,7 +319,7 @@ def test_known_deviation_gate_off_on_the_frame_the_release_time_grows():
                                   "gate-off at frame 5 after the release grew", "gate-on at frame 0 after the attack changed", "decay grows while decaying",
                                   "attack shrinks while attacking", "sustain moves while sustaining"])
 def test_adsr_parameter_changes_mid_stage_match_the_reference(case):
-    """the siblings of the known deviation: every other way a time or level can change under a running envelope
+    """the siblings of the case above: every other way a time or level can change under a running envelope
     (update_sustain_level's countdown clamp, adsr.rs:84-115) is bit-identical"""
     import graph_walk as W
     src = ("input a: value = 0.002; input d: value = 0.003; input s: value = 0.6; input r: value = 0.004; input gate: event; output stream out; "

@@ -26,11 +26,6 @@ RANGES = {
     O.K_EPIANO: {0: (60, 1200), 1: (0, 100), 2: (0, 100), 3: (0, 100), 4: (0, 100), 5: (0, 100), 6: (0, 100), 7: (0, 1), 8: (0.5, 9)},
 }
 HAS_GATE = {O.K_FM, O.K_SYNTH_ADSR, O.K_EPIANO}
-# ADSR release inputs stay at their defaults here: a gate-off on the very frame a release time GROWS is a known deviation
-# (pinned by tests/test_host_kernel_cpu.py::test_known_deviation_gate_off_on_the_frame_the_release_time_grows)
-for _kind, _ids in ((O.K_FM, (7,)), (O.K_SYNTH_ADSR, (7,))):
-    for _i in _ids:
-        RANGES[_kind].pop(_i, None)
 
 
 def make_script(kind, seed):

@@ -290,7 +290,8 @@ def test_host_executed_clip_kernels_match_oracle(kind):
     assert np.array_equal(np.concatenate(yh), np.concatenate(yr))
 
 
-def test_gate_off_on_the_frame_the_release_time_grows_uses_the_cached_length():
+@pytest.mark.parametrize("engine", [HostEngine, HostNodePlanEngine], ids=["generated_kernel", "node_plan"])
+def test_gate_off_on_the_frame_the_release_time_grows_uses_the_cached_length(engine):
     """found by tools/fuzz_host_builtin.py.  AdsrEnvelope::handle_gate_event (adsr.rs:252-273): a gate-OFF calls
     set_stage(Release), which counts down from `release_samples` as cached by the last process() — so when `release` was
     raised since then (a host write between blocks with the note-off at frame 0, or a ramp / value event on the note-off's
@@ -299,7 +300,7 @@ def test_gate_off_on_the_frame_the_release_time_grows_uses_the_cached_length():
     import graph_walk as W
     src = ("input r: value = 0.004; input gate: event; output stream out; node env = AdsrEnvelope::new(0.002, 0.003, 0.6, 0.004); "
            "connection gate -> env.gate; connection r -> env.release; connection env.output -> out;")
-    eng = HostEngine(src, 1, 1)
+    eng = engine(src, 1, 1)
     env = W.adsr(0.002, 0.003, 0.6, 0.004, 48000.0)
     got, want = [], []
     for frames, rel, gates in ((200, 0.004, [(0, 0.9)]), (100, 0.008, [(0, 0.0)])):
@@ -318,7 +319,8 @@ def test_gate_off_on_the_frame_the_release_time_grows_uses_the_cached_length():
 @pytest.mark.parametrize("case", ["release grows while releasing", "release shrinks while releasing", "gate-off at frame 0 after the release shrank",
                                   "gate-off at frame 5 after the release grew", "gate-on at frame 0 after the attack changed", "decay grows while decaying",
                                   "attack shrinks while attacking", "sustain moves while sustaining"])
-def test_adsr_parameter_changes_mid_stage_match_the_reference(case):
+@pytest.mark.parametrize("engine", [HostEngine, HostNodePlanEngine], ids=["generated_kernel", "node_plan"])
+def test_adsr_parameter_changes_mid_stage_match_the_reference(case, engine):
     """the siblings of the case above: every other way a time or level can change under a running envelope
     (update_sustain_level's countdown clamp, adsr.rs:84-115) is bit-identical"""
     import graph_walk as W
@@ -336,7 +338,7 @@ def test_adsr_parameter_changes_mid_stage_match_the_reference(case):
         "sustain moves while sustaining": [(150, {}, [(0, 0.9)]), (100, {"s": 0.3}, []), (100, {"s": 0.8}, [])],
     }[case]
     field = {"a": "attack", "d": "decay", "s": "sustain", "r": "release"}
-    eng = HostEngine(src, 1, 1)
+    eng = engine(src, 1, 1)
     env = W.adsr(0.002, 0.003, 0.6, 0.004, 48000.0)
     got, want = [], []
     for frames, sets, gates in blocks:

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from test_dsl_gpu import dsl_engine, fused_plan  # noqa: F401  (fixture)
+from test_dsl_gpu import dsl_engine, fused_plan, plan  # noqa: F401  (fixtures)
 
 GATE = O.EV_GATE
 SR = 48000.0
@@ -86,3 +86,43 @@ def test_value_events_on_a_ramped_input_are_refused(fused_plan):
     ref.set_value(0, 900.0); ref.push_events([(1, 4, 0, 700.0)]); ref.process_block(16)
     ref.set_value(0, 900.0); ref.set_value_ramp(0, 2500.0, 8); ref.push_events([(1, 4, 1, 0.5)]); ref.process_block(16)
     assert np.array_equal(eng.read_voice_out(), ref.read_voice_out())
+
+
+def test_gate_off_starts_from_the_release_length_cached_by_the_previous_process(plan):
+    """found by tools/fuzz_host_builtin.py: AdsrEnvelope::handle_gate_event (adsr.rs:252-273) counts a release down from
+    `release_samples` as cached by the LAST process(), so a note-off on the frame where `release` grew — here: a host write
+    between blocks with the note-off at frame 0, and a value event on the note-off's frame — releases over the old length
+    (then clamped to the new one).  The length travels in the ADSR stage word across blocks (nodes.cuh AdsrState::r_gate)."""
+    import graph_walk as W
+    src = ("input r: value = 0.004; input gate: event; output stream out; node env = AdsrEnvelope::new(0.002, 0.003, 0.6, 0.004); "
+           "connection gate -> env.gate; connection r -> env.release; connection env.output -> out;")
+    n = 3
+    eng = dsl_engine(src, n, 1, SR, plan=plan)
+    envs = [W.adsr(0.002, 0.003, 0.6, 0.004, SR) for _ in range(n)]
+    rel = np.full(n, 0.004, dtype=np.float32)
+    got, want = [], []
+    # block 0: notes on.  block 1: release doubled by the host, voice 0 released at frame 0, voice 1 at frame 9.
+    # block 2: voice 2 gets a longer release by a value event on the frame of its note-off.
+    script = [(200, None, [(v, 0, GATE, 0.9) for v in range(n)]),
+              (100, 0.008, [(0, 0, GATE, 0.0), (1, 9, GATE, 0.0)]),
+              (120, None, [(2, 7, 0, 0.02), (2, 7, GATE, 0.0)])]
+    for frames, new_rel, events in script:
+        if new_rel is not None:
+            eng.set_value(0, new_rel); rel[:] = new_rel
+        eng.push_events(events)
+        eng.process_block(frames); got.append(eng.read_voice_out())
+        out = np.zeros((frames, n), dtype=np.float32)
+        for f in range(frames):
+            for v in range(n):
+                for ev, ef, ei, es in events:
+                    if ev == v and ef == f and ei == 0:
+                        rel[v] = es
+                envs[v].set(release=rel[v])
+                for ev, ef, ei, es in events:
+                    if ev == v and ef == f and ei == GATE:
+                        envs[v].on_gate(es)
+                out[f, v] = envs[v].process()
+        want.append(out)
+    got, want = np.concatenate(got), np.concatenate(want)
+    assert np.abs(want).max() > 0.5
+    assert np.array_equal(got, want), float(np.abs(got - want).max())

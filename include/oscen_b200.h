@@ -298,7 +298,7 @@ int  oscen_b200_graph_codegen(const oscen_b200_graph *g, char *dst, size_t cap);
 int  oscen_b200_graph_jit_check(const oscen_b200_graph *g, char *log, size_t log_cap);
 /* what an engine of this graph at `sample_rate` would hand to NVRTC and start from (Delay rings are sized by the sample
    rate, so the state layout depends on it): the generated source, the state words of one voice after new() + init(sr)
-   (field order = the SoA rows of oscen_b200_read_state), the dynamic shared memory of the kernel.  Host only, no GPU:
+   (field order = the SoA rows of oscen_b200_state_download), the dynamic shared memory of the kernel.  Host only, no GPU:
    offline inspection, and the CPU suite's host-executed kernel check (tests/host_kernel.py).  Any output may be NULL.
    Returns 0, or OSCEN_B200_E_ARG when a buffer is too small (the needed sizes are still written). */
 typedef struct {

@@ -354,3 +354,33 @@ def test_adsr_parameter_changes_mid_stage_match_the_reference(case, engine):
                     env.on_gate(g)
             want.append(env.process())
     assert np.array_equal(np.concatenate(got), np.array(want, dtype=np.float32))
+
+
+# ------------------------------------------------------------ the device-side MIDI front (midi_device.cuh)
+@pytest.mark.parametrize("kind,vpi", [(O.K_FM, 8), (O.K_EPIANO, 16)], ids=["fm_graph_8_voices", "electric_piano_16_voices"])
+@pytest.mark.parametrize("seed", range(4))
+def test_host_executed_device_midi_front_feeds_the_voice_kernels_like_the_oracle(kind, vpi, seed):
+    """raw MIDI in, audio out, entirely on host-executed device code: midi_front_kernel (parser -> VoiceAllocator<N> ->
+    [MidiVoiceHandler; N], one thread per instance; tests/csrc/host_midi_runner.cpp restates midi_device_run()) writes the
+    per-voice gate / frequency events, the hand-written voice kernel renders them — against the oracle bank fed the same
+    messages through its own MIDI chain.  Random streams with voice stealing, velocity-0 note-ons, controller noise, short
+    messages, more than 32 messages per instance per block and offsets beyond the block (_random_midi)."""
+    from host_kernel import HostBuiltinEngine, HostMidiFront
+    from test_parity_gpu import _random_midi
+    rng = np.random.default_rng(100 * kind + seed)
+    n_inst = 9 if kind == O.K_FM else 5                     # two CTAs' worth of voices, the second partly filled
+    n = n_inst * vpi
+    ref, host, front = O.OracleBank(kind, n, vpi), HostBuiltinEngine(kind, n, vpi), HostMidiFront(n, vpi, 0)
+    vr, vh, ir, ih = [], [], [], []
+    for blk, frames in enumerate((128, 60, 200)):
+        msgs = _random_midi(rng, n_inst, frames, 40 if blk == 0 else 8, 2 * vpi)
+        for inst, frame, data in msgs:
+            ref.push_midi(inst, frame, data)
+        host.push_events(front.run(msgs, frames))
+        ref.process_block(frames); host.process_block(frames)
+        vr.append(ref.read_voice_out()); vh.append(host.read_voice_out())
+        ir.append(ref.read_instance_out()); ih.append(host.read_instance_out())
+    assert np.abs(np.concatenate(vr)).max() > 0.01
+    assert np.array_equal(np.concatenate(vh), np.concatenate(vr))
+    assert np.array_equal(np.concatenate(ih), np.concatenate(ir))
+    front.close()

@@ -63,3 +63,12 @@ extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t
     }
     return 0;
 }
+
+/* the final mix bus: mix_reduce_kernel (kernels_common.cuh), one 256-thread CTA per output element, as launch_mix_reduce() */
+extern "C" int oscen_host_mix_reduce(const float *partial, float *mix, uint32_t n_cta, uint32_t channels, uint32_t frames) {
+    using namespace oscen;
+    BlockCtl ctl{};
+    ctl.frames = frames;
+    host_launch(frames * channels, 1, 256, [&]() { mix_reduce_kernel(partial, mix, n_cta, channels, &ctl); });
+    return 0;
+}

@@ -384,3 +384,21 @@ def test_host_executed_device_midi_front_feeds_the_voice_kernels_like_the_oracle
     assert np.array_equal(np.concatenate(vh), np.concatenate(vr))
     assert np.array_equal(np.concatenate(ih), np.concatenate(ir))
     front.close()
+
+
+def test_host_executed_mix_reduce_kernel_folds_the_cta_partials_in_its_fixed_shape():
+    """mix_reduce_kernel (kernels_common.cuh) on the host against its restatement in tests/host_kernel.py (which the mix-bus
+    assertions of the other host tests use) and, within the reduction-order tolerance, against the oracle's sequential sum:
+    mono (FM bank over three CTAs) and stereo (ElectricPiano)"""
+    from host_kernel import HostBuiltinEngine
+    for kind, n, vpi in ((O.K_FM, 136, 8), (O.K_EPIANO, 80, 16)):
+        ref, host = O.OracleBank(kind, n, vpi), HostBuiltinEngine(kind, n, vpi)
+        for b in (ref, host):
+            b.set_value(0, (110.0 * (1 + np.arange(n) % 24)).astype(np.float32))
+            b.push_events([(v, v % 20, GATE, 0.7) for v in range(n)])
+            b.process_block(48)
+        m_kernel, m_py, m_ref = host.read_mix_device_kernel(), host.read_mix(), ref.read_mix()
+        assert np.array_equal(m_kernel, m_py)
+        scale = np.abs(ref.read_instance_out().astype(np.float64)).sum(axis=1)
+        assert np.abs(m_ref).max() > 1e-3
+        assert (np.abs(m_kernel.astype(np.float64) - m_ref.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()

@@ -157,3 +157,42 @@ def test_node_array_plans_and_errors():
         with pytest.raises(abi.GraphCompileError) as ei:
             abi.Graph(src)
         assert frag in str(ei.value), str(ei.value)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_array_shapes_render_like_their_hand_unrolled_graphs(seed):
+    """arrays of random sizes N, M (1..6) with a Broadcast value edge, an indexed element, a Parallel edge (min(N, M)
+    elements) and a FanIn: the array text against the same graph written out node by node (CPU: host-executed kernel)"""
+    from host_kernel import HostEngine
+    rng = np.random.default_rng(4200 + seed)
+    n_osc, n_gain = int(rng.integers(1, 7)), int(rng.integers(1, 7))
+    k = int(rng.integers(0, n_osc))
+    freqs = [float(np.float32(rng.uniform(100, 900))) for _ in range(2)]
+    head = "input value spread = 0.01; input value level = 0.5; output stream out;\n"
+    arr = head + f"""nodes {{ oscs = [PolyBlepOscillator::saw({freqs[0]!r}, 0.4); {n_osc}]; gains = [Gain::new(0.7); {n_gain}]; lp = TptFilter::new(2500.0, 0.8); }}
+        connections {{
+            spread -> oscs.frequency_mod;
+            spread * 3.0 -> oscs[{k}].phase_mod;
+            oscs.output -> gains.input;
+            level -> gains.gain;
+            gains.output -> lp.input;
+            lp.output + oscs[{k}].output * 0.2 -> out;
+        }}"""
+    m = min(n_osc, n_gain)
+    nodes = "".join(f"o{i} = PolyBlepOscillator::saw({freqs[0]!r}, 0.4); " for i in range(n_osc)) + \
+        "".join(f"g{i} = Gain::new(0.7); " for i in range(n_gain)) + "lp = TptFilter::new(2500.0, 0.8);"
+    conns = "".join(f"spread -> o{i}.frequency_mod; " for i in range(n_osc)) + f"spread * 3.0 -> o{k}.phase_mod; " + \
+        "".join(f"o{i}.output -> g{i}.input; " for i in range(m)) + "".join(f"level -> g{i}.gain; " for i in range(n_gain)) + \
+        "0.0" + "".join(f" + g{i}.output" for i in range(n_gain)) + " -> lp.input; " + f"lp.output + o{k}.output * 0.2 -> out;"
+    flat = head + "nodes { " + nodes + " } connections { " + conns + " }"
+    n = 3
+    outs = []
+    for src in (arr, flat):
+        e = HostEngine(src, n, 1, SR)
+        e.set_value(0, (0.01 * (1 + np.arange(n))).astype(np.float32)); e.set_value(1, (0.3 + 0.2 * np.arange(n)).astype(np.float32))
+        y = []
+        for frames in (40, 57):
+            e.process_block(frames); y.append(e.read_voice_out())
+        outs.append(np.concatenate(y))
+    assert np.abs(outs[0]).max() > 0.01
+    assert np.array_equal(outs[0], outs[1]), (n_osc, n_gain, k)

@@ -18,6 +18,19 @@ template <int P> void clip_policy_launch(const KernelArgs &a, uint32_t grid, int
 }
 }  // namespace
 
+
+/* stream_in_lcg: the graph's stream input is generated on the device from the per-voice LCG state (BlockCtl.lcg_on) */
+static uint32_t g_lcg_on = 0, g_lcg_field = 0;
+extern "C" void oscen_host_set_lcg(uint32_t on, uint32_t field) { g_lcg_on = on; g_lcg_field = field; }
+/* oscen_b200_stream_in_lcg's lcg_seed_kernel (engine.cu), restated: the LCG state words of every voice */
+extern "C" void oscen_host_lcg_seed(float *state, uint32_t n, unsigned long long seed, uint32_t voice_offset, uint32_t field) {
+    for (uint32_t v = 0; v < n; ++v) {
+        const unsigned long long s = oscen::lcg_seed_state(seed + (unsigned long long)(voice_offset + v));
+        state[(size_t)(field + 0) * n + v] = __uint_as_float((uint32_t)(s & 0xffffffffull));
+        state[(size_t)(field + 1) * n + v] = __uint_as_float((uint32_t)(s >> 32));
+    }
+}
+
 extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t n_voices, uint32_t vpi, float sample_rate, float *state,
                                             float *pv, const oscen::Event *events, uint32_t n_events, const float *ptab, uint32_t ramp_mask,
                                             uint32_t frames, const float *stream_in, float *voice_out, float *inst_out, float *inst_state,
@@ -25,7 +38,7 @@ extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t
     using namespace oscen;
     if (n_voices == 0 || vpi == 0 || kCta % vpi != 0 || n_voices % vpi != 0 || frames > kMaxBlock) return -1;
     BlockCtl ctl{};
-    ctl.frames = frames; ctl.n_events = n_events; ctl.ramp_mask = ramp_mask; ctl.lcg_on = 0;
+    ctl.frames = frames; ctl.n_events = n_events; ctl.ramp_mask = ramp_mask; ctl.lcg_on = g_lcg_on;
     KernelArgs a;
     memset(&a, 0, sizeof a);
     a.n_voices = n_voices; a.vpi = vpi; a.n_inst = n_voices / vpi; a.channels = kind == 4u ? 2u : 1u;

@@ -27,6 +27,11 @@ void launch_ew(const NodeArgs &n, uint32_t grid, bool vec) {
 }
 }  // namespace
 
+
+/* stream_in_lcg: the graph's stream input is generated on the device from the per-voice LCG state (BlockCtl.lcg_on) */
+static uint32_t g_lcg_on = 0, g_lcg_field = 0;
+extern "C" void oscen_host_set_lcg(uint32_t on, uint32_t field) { g_lcg_on = on; g_lcg_field = field; }
+
 extern "C" void *oscen_host_plan_create(const char *text, float sample_rate, char *err, size_t err_cap) {
     HostPlan *h = new HostPlan();
     std::string e;
@@ -59,15 +64,21 @@ extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi,
         h->n_voices = n;
     }
     BlockCtl ctl{};
-    ctl.frames = frames; ctl.n_events = n_events; ctl.ramp_mask = ramp_mask; ctl.lcg_on = 0;
+    ctl.frames = frames; ctl.n_events = n_events; ctl.ramp_mask = ramp_mask; ctl.lcg_on = g_lcg_on;
     AssetTable assets{};
     for (uint32_t k = 0; k < kMaxAssets && asset_data; ++k) { assets.data[k] = asset_data[k]; assets.frames[k] = asset_frames[k]; assets.reset[k] = asset_reset[k]; }
     const uint32_t grid = (n + kCta - 1) / kCta;
     const bool vec = !has_value_events && (n % 4u == 0u);
     auto S = [&](int i) { return h->streams[(size_t)i].data(); };
+    const float *gin = stream_in;
+    if (g_lcg_on && !g.stream_input.empty()) {                 /* launch_plan(): the LCG source node fills a stream of its own */
+        float *dst = S(p.n_streams);
+        host_launch(grid, 1, kCta, [&]() { lcg_source_kernel(state, dst, &ctl, n, g_lcg_field); });
+        gin = dst;
+    }
     auto resolve = [&](const plan::StreamRef &r) -> float * {
         if (r.node == plan::kNone) return nullptr;
-        if (r.node == plan::kGraphInput) return const_cast<float *>(stream_in);
+        if (r.node == plan::kGraphInput) return const_cast<float *>(gin);
         return S(p.first_stream[r.node] + r.port);
     };
     auto args_of = [&](int idx) {

@@ -402,3 +402,20 @@ def test_host_executed_mix_reduce_kernel_folds_the_cta_partials_in_its_fixed_sha
         scale = np.abs(ref.read_instance_out().astype(np.float64)).sum(axis=1)
         assert np.abs(m_ref).max() > 1e-3
         assert (np.abs(m_kernel.astype(np.float64) - m_ref.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()
+
+
+def test_host_executed_twin_peaks_kernel_with_the_device_generated_input():
+    """BASELINE configs[3]'s input path: audio_in generated on the device by the per-voice LCG (stream_in_lcg; the two LCG
+    state words persist across blocks) — the hand-written twin_peaks_kernel against the oracle fed the same noise"""
+    from host_kernel import HostBuiltinEngine
+    n = 70
+    ref, host = O.OracleBank(O.K_TWIN, n, 1), HostBuiltinEngine(O.K_TWIN, n, 1)
+    x = np.stack([lcg_noise(300, 1000 + 7 + v) for v in range(n)], axis=1)
+    host.stream_in_lcg(0, 1000, 7)
+    pos, yr, yh = 0, [], []
+    for frames in (128, 22, 150):
+        ref.stream_in(0, x[pos:pos + frames]); ref.process_block(frames); yr.append(ref.read_voice_out())
+        host.process_block(frames); yh.append(host.read_voice_out())
+        pos += frames
+    assert np.abs(np.concatenate(yr)).max() > 0.1
+    assert np.array_equal(np.concatenate(yh), np.concatenate(yr))

@@ -428,9 +428,9 @@ def test_external_asset_slot_and_sample_player_plan():
     one-word player state, the generated kernel compiles for sm_100a, and the node plan has a launch for the player"""
     g = abi.Graph(text("player.graph"))
     d = g.describe()
-    assert "external 0: sample (AudioAsset) -> player.buf" in d and "state words per voice: 1" in d
-    assert g.launches() == ["0: SamplePlayer [player]"]
-    assert g.n_assets() == 1 and g.asset_id("sample") == 0
+    assert "external 0: clip (AudioAsset) -> deck.buf" in d and "state words per voice: 1" in d
+    assert g.launches() == ["0: SamplePlayer [deck]"]
+    assert g.n_assets() == 1 and g.asset_id("clip") == 0
     with pytest.raises(KeyError):
         g.asset_id("nope")
     src = g.codegen()

@@ -88,15 +88,15 @@ def test_host_executed_sample_player_graph_reproduces_the_reference_graph_test(e
     eng = engine(text("player.graph"), 70, 1, 44100.0)
     eng.process_block(8)
     assert (eng.read_voice_out() == 0.0).all()
-    eng.load_asset("sample", a)
+    eng.load_asset("clip", a)
     eng.process_block(7); y1 = eng.read_voice_out()
     eng.process_block(3); y2 = eng.read_voice_out()
     want = np.concatenate([a, a])
     assert np.array_equal(np.concatenate([y1, y2]), np.repeat(want[:, None], 70, axis=1))
-    eng.load_asset("sample", np.stack([b, -b], axis=1))           # a stereo source: a mono player takes channel 0
+    eng.load_asset("clip", np.stack([b, -b], axis=1))           # a stereo source: a mono player takes channel 0
     eng.process_block(6)
     assert np.array_equal(eng.read_voice_out(), np.repeat(np.concatenate([b, b])[:, None], 70, axis=1))
-    eng.load_asset("sample", np.zeros(0, dtype=np.float32))       # an empty buffer: silence again
+    eng.load_asset("clip", np.zeros(0, dtype=np.float32))       # an empty buffer: silence again
     eng.process_block(4)
     assert (eng.read_voice_out() == 0.0).all()
 

@@ -29,14 +29,14 @@ def test_sample_player_graph_reproduces_the_reference_graph_test_on_the_gpu(plan
     eng = abi.Engine.from_graph(open(os.path.join(GRAPHS, "player.graph")).read(), n, 1, 44100.0, plan=plan)
     eng.process_block(8)
     assert (eng.read_voice_out() == 0.0).all()
-    eng.load_asset("sample", a)
+    eng.load_asset("clip", a)
     eng.process_block(7); y1 = eng.read_voice_out()
     eng.process_block(3); y2 = eng.read_voice_out()
     assert np.array_equal(np.concatenate([y1, y2]), np.repeat(np.concatenate([a, a])[:, None], n, axis=1))
-    eng.load_asset("sample", np.stack([b, -b], axis=1))           # stereo source: a mono player takes channel 0
+    eng.load_asset("clip", np.stack([b, -b], axis=1))           # stereo source: a mono player takes channel 0
     eng.process_block(6)
     assert np.array_equal(eng.read_voice_out(), np.repeat(np.concatenate([b, b])[:, None], n, axis=1))
-    eng.load_asset("sample", np.zeros(0, dtype=np.float32))
+    eng.load_asset("clip", np.zeros(0, dtype=np.float32))
     eng.process_block(4)
     assert (eng.read_voice_out() == 0.0).all()
     with pytest.raises(abi.EngineError):

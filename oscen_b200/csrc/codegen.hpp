@@ -17,6 +17,7 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <cstdarg>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,6 +26,18 @@
 
 namespace oscen {
 namespace codegen {
+
+/* printf into a std::string: a line can never be cut short (an unterminated trailing comment would swallow the next line) */
+inline std::string fmt(const char *f, ...) {
+    va_list ap, ap2;
+    va_start(ap, f); va_copy(ap2, ap);
+    const int n = vsnprintf(nullptr, 0, f, ap);
+    va_end(ap);
+    std::string out((size_t)(n > 0 ? n : 0), '\0');
+    if (n > 0) vsnprintf(&out[0], (size_t)n + 1, f, ap2);
+    va_end(ap2);
+    return out;
+}
 
 inline std::string lit(float v) {
     uint32_t u; memcpy(&u, &v, 4);
@@ -125,7 +138,6 @@ struct Emitter {
         const int n_nodes = (int)g.nodes.size();
         const uint32_t ni = (uint32_t)g.inputs.size();
         const bool has_in = !g.stream_input.empty();
-        char b[256];
         line(0, "/* generated by oscen_b200 codegen.hpp from graph `" + (g.name.empty() ? std::string("<anonymous>") : g.name) + "` — do not edit */");
         const bool multirate = g.inner_log2 > 0;
         const int NI = 1 << g.inner_log2;
@@ -133,8 +145,7 @@ struct Emitter {
         line(0, "using namespace oscen;");
         /* min_blocks CTAs of 64 threads per SM: 8 caps the kernel at 128 registers per thread, so that the 1024 CTAs of a
            65 536-voice bank (6.9 per SM) are resident in one wave */
-        snprintf(b, sizeof b, "extern \"C\" __global__ void __launch_bounds__(kCta, %d) %s(const __grid_constant__ KernelArgs a) {", min_blocks, kernel_name);
-        line(0, b);
+        line(0, fmt("extern \"C\" __global__ void __launch_bounds__(kCta, %d) %s(const __grid_constant__ KernelArgs a) {", min_blocks, kernel_name));
         line(1, "__shared__ float tile[kTileF * kTileW];");
         line(1, "__shared__ float isum[kTileF * kCta];");
         line(1, "const uint32_t n = a.n_voices;");
@@ -151,10 +162,10 @@ struct Emitter {
             line(1, "(void)sri; (void)dyn;");
         }
         /* ---- value inputs */
-        snprintf(b, sizeof b, "float P[%u];", ni ? ni : 1u); line(1, b);
+        line(1, fmt("float P[%u];", ni ? ni : 1u));
         for (uint32_t i = 0; i < ni; ++i) {
-            if ((uniform_mask >> i) & 1u) { snprintf(b, sizeof b, "P[%u] = 0.0f;    /* %s: uniform, read from a.u.p[%u] */", i, g.inputs[i].name.c_str(), i); line(1, b); continue; }
-            snprintf(b, sizeof b, "P[%u] = a.pv[(size_t)%uu * n + vs];    /* %s */", i, i, g.inputs[i].name.c_str()); line(1, b);
+            if ((uniform_mask >> i) & 1u) { line(1, fmt("P[%u] = 0.0f;    /* %s: uniform, read from a.u.p[%u] */", i, g.inputs[i].name.c_str(), i)); continue; }
+            line(1, fmt("P[%u] = a.pv[(size_t)%uu * n + vs];    /* %s */", i, i, g.inputs[i].name.c_str()));
         }
         if (!ni) line(1, "P[0] = 0.0f;");
         /* ---- node state: HBM -> registers */
@@ -237,7 +248,7 @@ struct Emitter {
         if (ni) {
             line(4, "if (ramp_mask) {");
             line(5, "const float *row = a.ptab + (size_t)f * kMaxInputs;");
-            for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { snprintf(b, sizeof b, "if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i); line(5, b); }
+            for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(5, fmt("if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i)); }
             line(4, "}");
         }
         /* ---- this frame's events: value edges are assigned before process_event_inputs() */
@@ -248,8 +259,8 @@ struct Emitter {
         line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
         line(6, "const Event e = ec.ev[q];");
         line(6, "if (e.input_id == kEventGate) continue;");
-        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { snprintf(b, sizeof b, "if (e.input_id == %uu) P[%u] = e.scalar;", i, i); line(6, b); }
-        snprintf(b, sizeof b, "if (e.input_id < %uu) a.pv[(size_t)e.input_id * n + v] = e.scalar;", ni); line(6, b);
+        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(6, fmt("if (e.input_id == %uu) P[%u] = e.scalar;", i, i)); }
+        line(6, fmt("if (e.input_id < %uu) a.pv[(size_t)e.input_id * n + v] = e.scalar;", ni));
         line(5, "}");
         line(4, "}");
         line(4, "const bool changed = (ramp_mask != 0u) || due;    /* a value input may have moved this frame */");

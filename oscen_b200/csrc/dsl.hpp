@@ -92,6 +92,8 @@ inline bool lex(const char *src, std::vector<Tok> &out, Error &err) {
         if (isalpha((unsigned char)*p) || *p == '_') {
             const char *q = p;
             while (isalnum((unsigned char)*q) || *q == '_') ++q;
+            /* names travel into fixed 64-byte fields (oscen_b200_input_info.name) and into the generated kernel's text */
+            if (q - p > 63) { err.at(t, "identifier longer than 63 characters"); return false; }
             t.kind = Tok::Ident; t.s.assign(p, q); adv((int)(q - p));
         } else if (isdigit((unsigned char)*p)) {
             /* Rust numeric literal: digits with `_`, optional fraction, exponent, type suffix.
@@ -452,6 +454,7 @@ private:
             if (c.policy != "latch" && c.policy != "linear" && c.policy != "sinc" && c.policy != "sinc_iir") { err.at(c.at, "unknown connection policy `" + c.policy + "`"); return; }
             if (!expect("]")) return;
         }
+        expr_depth = 0; expr_ops = 0;
         c.src = additive();
         if (err.set || !expect("->")) return;
         if (is_punct("[")) {
@@ -464,14 +467,24 @@ private:
             ++pos;
             if (!expect("]") || !expect("->")) return;
         }
+        expr_depth = 0; expr_ops = 0;
         c.dst = additive();
         if (err.set) return;
         if (expect(";")) ast.conns.push_back(std::move(c));
     }
     /* parse.rs:989-1029: + - below * /, left associative; a `-` that starts `->` ends the expression */
+    /* run-time text: the recursion (and the tree every later pass walks recursively) is bounded — a source nested
+       deeper than kMaxExprDepth parentheses or longer than kMaxExprOps operators is a diagnostic, not a stack overflow */
+    static constexpr int kMaxExprDepth = 64, kMaxExprOps = 1024;
+    int expr_depth = 0, expr_ops = 0;
+    bool count_op() {
+        if (++expr_ops > kMaxExprOps) { err.at(cur(), "expression too long (more than 1024 operators in one connection)"); return false; }
+        return true;
+    }
     ExprP additive() {
         ExprP l = multiplicative();
         while (!err.set && (is_punct("+") || is_punct("-"))) {
+            if (!count_op()) return l;
             ExprP e(new Expr); e->k = Expr::Binary; e->op = cur().s[0]; e->at = cur(); ++pos;
             e->a = std::move(l); e->b = multiplicative(); l = std::move(e);
         }
@@ -480,6 +493,7 @@ private:
     ExprP multiplicative() {
         ExprP l = primary();
         while (!err.set && (is_punct("*") || is_punct("/"))) {
+            if (!count_op()) return l;
             ExprP e(new Expr); e->k = Expr::Binary; e->op = cur().s[0]; e->at = cur(); ++pos;
             e->a = std::move(l); e->b = primary(); l = std::move(e);
         }
@@ -487,7 +501,14 @@ private:
     }
     ExprP primary() {
         ExprP e(new Expr); e->at = cur();
-        if (accept("(")) { e = additive(); expect(")"); return postfix(std::move(e)); }
+        if (is_punct("(")) {
+            if (expr_depth >= kMaxExprDepth) { err.at(cur(), "expression nested deeper than 64 parentheses"); return e; }
+            ++pos; ++expr_depth;
+            e = additive();
+            --expr_depth;
+            if (err.set) return e;
+            expect(")"); return postfix(std::move(e));
+        }
         if (cur().kind == Tok::Num) { e->k = Expr::Literal; e->lit = cur().num; ++pos; return e; }
         if (is_punct("-") && peek(1).kind == Tok::Num) { e->k = Expr::Literal; e->lit = -peek(1).num; pos += 2; return e; }   /* `x * -1.0` */
         if (cur().kind != Tok::Ident) { err.at(cur(), "expected a connection endpoint or expression"); return e; }
@@ -524,6 +545,7 @@ private:
                 continue;
             }
             if (!is_punct(".")) return e;
+            if (!count_op()) return e;
             ++pos;
             ExprP f(new Expr); f->at = cur();
             if (!ident(f->name, "a field or method name")) return e;

@@ -195,7 +195,6 @@ struct oscen_b200_engine {
     float *d_xchg = nullptr;
     PeerTable peers{};
     bool p2p = false;
-    uint32_t xchg_seq = 0;
     uint32_t *d_p2p_error = nullptr;
 
     /* stats / timing */
@@ -483,8 +482,14 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
     return 0;
 }
 
+/* the mix bus of this rank's voices; with a peer-memory exchange set up (comm_p2p_import) the same launch also is the
+   collective: compute (partial reduction) + exchange over NVLink peer memory in ONE kernel, either plan */
 int launch_mix_reduce(oscen_b200_engine *e, uint32_t frames) {
-    mix_reduce_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta_mix, e->channels, e->d_ctl);
+    if (e->p2p)
+        mix_exchange_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta_mix, e->channels, e->d_ctl,
+                                                        e->peers, (uint32_t)e->rank, (uint32_t)e->n_ranks, e->d_p2p_error + 2, e->d_p2p_error + 1, e->d_p2p_error);
+    else
+        mix_reduce_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta_mix, e->channels, e->d_ctl);
     (void)frames;
     e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
@@ -1134,16 +1139,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     if (e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
         rc = launch_fused(e, general); if (rc) return rc;
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
-        if (e->p2p) {
-            /* compute (partial reduction) + exchange over NVLink peer memory in one kernel */
-            e->xchg_seq += 1;
-            mix_exchange_kernel<<<kMaxBlock * e->channels, 256, 0, e->stream>>>(e->d_mix_partial, e->d_mix, e->n_cta_mix, e->channels, e->d_ctl,
-                                                            e->peers, (uint32_t)e->rank, (uint32_t)e->n_ranks, e->xchg_seq, e->d_p2p_error + 1, e->d_p2p_error);
-            e->stats.kernel_launches++;
-            CK(e, cudaGetLastError());
-        } else {
-            rc = launch_mix_reduce(e, frames); if (rc) return rc;
-        }
+        rc = launch_mix_reduce(e, frames); if (rc) return rc;
     } else {
         /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
         const int gi = has_value_events ? 1 : 0;
@@ -1170,7 +1166,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         e->stats.graph_launches++;
         e->stats.kernel_launches += e->graph_kernels[gi];
     }
-    if (e->comm && !(e->p2p && e->cfg.plan == OSCEN_B200_PLAN_FUSED)) {
+    if (e->comm && !e->p2p) {
         const int r = g_nccl.AllReduce(e->d_mix, e->d_mix, (size_t)frames * e->channels, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, e->stream);
         if (r != 0) { e->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return OSCEN_B200_E_NCCL; }
     }
@@ -1372,8 +1368,8 @@ int oscen_b200_comm_p2p_export(oscen_b200_engine *e, int n_ranks, void *handle64
     if (!e->d_xchg) {
         CK(e, cudaMalloc(&e->d_xchg, kXchgBytes));
         CK(e, cudaMemset(e->d_xchg, 0, kXchgBytes));
-        CK(e, cudaMalloc(&e->d_p2p_error, 2 * sizeof(uint32_t)));      /* [0] error flag, [1] CTA arrival counter */
-        CK(e, cudaMemset(e->d_p2p_error, 0, 2 * sizeof(uint32_t)));
+        CK(e, cudaMalloc(&e->d_p2p_error, 4 * sizeof(uint32_t)));      /* [0] error flag, [1] CTA arrival counter, [2] block sequence number */
+        CK(e, cudaMemset(e->d_p2p_error, 0, 4 * sizeof(uint32_t)));
     }
     cudaIpcMemHandle_t h;
     CK(e, cudaIpcGetMemHandle(&h, e->d_xchg));
@@ -1385,6 +1381,12 @@ int oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, cons
     if (!e || !handles || n_ranks < 1 || n_ranks > (int)kMaxRanks || rank < 0 || rank >= n_ranks) return OSCEN_B200_E_ARG;
     if (!e->d_xchg) { e->err = "comm_p2p_import: call comm_p2p_export first"; return OSCEN_B200_E_STATE; }
     CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    /* a fresh exchange: sequence numbers restart at 1, so no flag or datum of an earlier import may survive, and a
+       timeout recorded against an earlier peer set is forgotten.  The caller must put a barrier between the ranks'
+       imports and their first process_block (a peer's first flag store must not race this memset). */
+    CK(e, cudaMemset(e->d_xchg, 0, kXchgBytes));
+    CK(e, cudaMemset(e->d_p2p_error, 0, 4 * sizeof(uint32_t)));
     for (int r = 0; r < n_ranks; ++r) {
         if (r == rank) { e->peers.peer[r] = e->d_xchg; continue; }
         cudaIpcMemHandle_t h;
@@ -1393,7 +1395,7 @@ int oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, cons
         CK(e, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         e->peers.peer[r] = (float *)p;
     }
-    e->rank = rank; e->n_ranks = n_ranks; e->p2p = true; e->xchg_seq = 0;
+    e->rank = rank; e->n_ranks = n_ranks; e->p2p = true;
     for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }
@@ -1407,6 +1409,7 @@ int oscen_b200_comm_p2p_close(oscen_b200_engine *e) {
         e->peers.peer[r] = nullptr;
     }
     e->p2p = false;
+    if (e->d_p2p_error) CK(e, cudaMemset(e->d_p2p_error, 0, 4 * sizeof(uint32_t)));
     for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }

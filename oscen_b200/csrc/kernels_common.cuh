@@ -185,11 +185,14 @@ struct PeerTable { float *peer[kMaxRanks]; };
 __global__ void __launch_bounds__(256) mix_exchange_kernel(const float *__restrict__ partial, float *__restrict__ mix,
                                                              uint32_t n_cta, uint32_t channels, const BlockCtl *ctl,
                                                              const __grid_constant__ PeerTable peers, uint32_t rank,
-                                                             uint32_t n_ranks, uint32_t seq, uint32_t *counter,
+                                                             uint32_t n_ranks, uint32_t *seq_word, uint32_t *counter,
                                                              uint32_t *error_flag) {
     __shared__ float red[256];
     __shared__ uint32_t is_last;
     const uint32_t count = ctl->frames * channels;
+    /* the block's sequence number lives in device memory (so the launch is identical every block and can sit in a
+       captured CUDA graph); the last CTA to finish advances it, after every other CTA of this launch has read it */
+    const uint32_t seq = *seq_word + 1u;
     const uint32_t parity = seq & 1u;
     const uint32_t fc = blockIdx.x;                        /* one output element per CTA, as mix_reduce_kernel */
     /* 1. compute: fixed-shape reduction of this rank's CTA partials for element fc */
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(256) mix_exchange_kernel(const float *__restri
         for (uint32_t r = 0; r < n_ranks; ++r) s = s + __ldcv(mine + (size_t)r * 1024u + k);
         mix[k] = s;
     }
+    if (threadIdx.x == 0) *seq_word = seq;
 }
 
 __global__ void fill_u32_kernel(uint32_t *dst, size_t n, uint32_t value) {

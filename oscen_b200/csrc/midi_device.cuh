@@ -39,7 +39,7 @@ struct MidiFrontArgs {
     const MidiMsg *msgs;                 /* push order */
     const uint32_t *keys, *idx;          /* sorted by instance (stable) */
     uint32_t n_msgs, n_inst, vpi, frames;
-    /* allocator: word = (note + 1) | active << 8 | released << 9 per voice, age per voice, current_age per instance */
+    /* allocator: word = (note + 1) [9 bits: note is any u8, midi.rs:8-35] | active << 9 | released << 10 per voice, age per voice, current_age per instance */
     uint32_t *alloc_word, *alloc_age, *alloc_cur_age;
     int *h_note; float *h_freq;          /* MidiVoiceHandler.current_note / current_frequency per voice */
     const float *note_freq;              /* [128] midi_note_to_freq, tabulated by the host libm (midi.rs:69-72) */
@@ -115,15 +115,15 @@ __global__ void __launch_bounds__(128) midi_front_kernel(const MidiFrontArgs a) 
             float fv = (float)vel / 127.0f;
             fv = fv < 0.0f ? 0.0f : (fv > 1.0f ? 1.0f : fv);
             uint32_t pick = vpi;
-            for (uint32_t v = 0; v < vpi; ++v) if (!((word[v] >> 8) & 1u)) { pick = v; break; }     /* first inactive */
+            for (uint32_t v = 0; v < vpi; ++v) if (!((word[v] >> 9) & 1u)) { pick = v; break; }     /* first inactive */
             if (pick == vpi) {                       /* min_by_key((released ? 0 : 1, age)), first minimum */
                 uint32_t bp = 2u, ba = 0u;
                 for (uint32_t v = 0; v < vpi; ++v) {
-                    const uint32_t p = ((word[v] >> 9) & 1u) ? 0u : 1u;
+                    const uint32_t p = ((word[v] >> 10) & 1u) ? 0u : 1u;
                     if (p < bp || (p == bp && age[v] < ba)) { pick = v; bp = p; ba = age[v]; }
                 }
             }
-            word[pick] = (note + 1u) | (1u << 8); age[pick] = current_age++;
+            word[pick] = (note + 1u) | (1u << 9); age[pick] = current_age++;
             q_voice[nq] = (uint8_t)pick; q_kind[nq] = 1; q_note[nq] = (uint8_t)note; q_vel[nq] = fv; ++nq;
         }
         /* then VoiceAllocator::on_note_off (voice_allocator.rs:126-136) */
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(128) midi_front_kernel(const MidiFrontArgs a) 
             const uint32_t len = r >> 24, status = r & 0xF0u, note = (r >> 8) & 0xFFu, vel = (r >> 16) & 0xFFu;
             if (len < 3u || !(status == 0x80u || (status == 0x90u && vel == 0u))) continue;
             for (uint32_t v = 0; v < vpi; ++v) {
-                if (((word[v] >> 8) & 3u) == 1u && (word[v] & 0xFFu) == note + 1u) {   /* active, not released, this note */
+                if (((word[v] >> 9) & 3u) == 1u && (word[v] & 0x1FFu) == note + 1u) {   /* active, not released, this note */
                     q_voice[nq] = (uint8_t)v; q_kind[nq] = 2; q_note[nq] = (uint8_t)note; q_vel[nq] = 0.0f; ++nq;
-                    word[v] = (1u << 8) | (1u << 9);                                   /* released, note = None */
+                    word[v] = (1u << 9) | (1u << 10);                                 /* released, note = None */
                     break;
                 }
             }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128) midi_front_kernel(const MidiFrontArgs a) 
         for (uint32_t v = 0; v < vpi; ++v) {
             bool touched = false;
             for (uint32_t k = 0; k < nq; ++k) if (q_voice[k] == v && q_kind[k] == 1) {
-                cur_note[v] = q_note[k]; cur_freq[v] = a.note_freq[q_note[k] & 127u]; touched = true;
+                cur_note[v] = q_note[k]; cur_freq[v] = a.note_freq[q_note[k]]; touched = true;
                 emit(v, f, kEventGate, q_vel[k]);
             }
             for (uint32_t k = 0; k < nq; ++k) if (q_voice[k] == v && q_kind[k] == 2) {

@@ -191,6 +191,11 @@ ONE_OSC = "output stream out; node o = PolyBlepOscillator::saw(2000.0, 0.6); "
     (ONE_OSC + "connection [cubic] o.output -> out;", "unknown connection policy `cubic`"),
     ("output stream out; /* never closed", "unterminated block comment"),
     (ONE_OSC + "connection o.output -> out; @", "unexpected character `@`"),
+    # run-time text must not be able to overflow the stack or a fixed buffer
+    (ONE_OSC + "connection " + "(" * 200000 + "o.output" + ")" * 200000 + " -> out;", "nested deeper than 64 parentheses"),
+    (ONE_OSC + "connection o.output" + " + o.output" * 5000 + " -> out;", "expression too long"),
+    (ONE_OSC + "connection o.output" + ".abs()" * 5000 + " -> out;", "expression too long"),
+    ("input " + "c" * 300 + ": value = 1.0; " + ONE_OSC + "connection o.output -> out;", "identifier longer than 63 characters"),
 ])
 def test_compile_errors(src, frag):
     with pytest.raises(abi.GraphCompileError) as ei:
@@ -198,6 +203,19 @@ def test_compile_errors(src, frag):
     msg = str(ei.value)
     assert frag in msg, msg
     assert re.match(r"^\d+:\d+: ", msg), msg          # every diagnostic carries line:col
+
+
+def test_longest_identifiers_survive_code_generation():
+    """63-character names (the lexer's cap) reach the generated kernel's text whole: every `/* name */` comment is closed and
+    every input is loaded (a 300-character name used to truncate a line inside its comment and swallow the next)"""
+    a, b = "a" * 63, "b" * 63
+    g = abi.Graph(f"input {a}: value = 100.0; input {b}: value = 0.5; output stream out; "
+                  f"node o = PolyBlepOscillator::saw(1.0, 1.0); connection {a} -> o.frequency; connection {b} -> o.amplitude; connection o.output -> out;")
+    src = g.codegen()
+    assert src.count("/*") == src.count("*/")
+    assert f"/* {a} */" in src and f"/* {b} */" in src and "P[0] = a.pv[" in src and "P[1] = a.pv[" in src
+    assert g.input_info(1)["name"] == b
+    assert g.jit_check() > 0
 
 
 def test_expressions_lower_to_one_operator_per_launch():

@@ -386,6 +386,30 @@ def test_host_executed_device_midi_front_feeds_the_voice_kernels_like_the_oracle
     front.close()
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_host_executed_device_midi_front_takes_data_bytes_with_the_high_bit_set(seed):
+    """note / velocity are any u8 in the reference (midi.rs:8-35): the device front must index its frequency table with the
+    full byte and keep note 255 distinguishable from "no note" in the allocator word"""
+    from host_kernel import HostBuiltinEngine, HostMidiFront
+    from test_parity_gpu import _random_midi
+    rng = np.random.default_rng(4200 + seed)
+    kind, vpi, n_inst = O.K_FM, 8, 5
+    n = n_inst * vpi
+    ref, host, front = O.OracleBank(kind, n, vpi), HostBuiltinEngine(kind, n, vpi), HostMidiFront(n, vpi, 0)
+    vr, vh = [], []
+    for blk, frames in enumerate((96, 64)):
+        msgs = _random_midi(rng, n_inst, frames, 30 if blk == 0 else 8, 2 * vpi, malformed=0.5)
+        assert any(d[1] >= 0x80 for _, _, d in msgs if len(d) > 1)
+        for inst, frame, data in msgs:
+            ref.push_midi(inst, frame, data)
+        host.push_events(front.run(msgs, frames))
+        ref.process_block(frames); host.process_block(frames)
+        vr.append(ref.read_voice_out()); vh.append(host.read_voice_out())
+    assert np.abs(np.concatenate(vr)).max() > 0.01
+    assert np.array_equal(np.concatenate(vh), np.concatenate(vr))
+    front.close()
+
+
 def test_host_executed_mix_reduce_kernel_folds_the_cta_partials_in_its_fixed_shape():
     """mix_reduce_kernel (kernels_common.cuh) on the host against its restatement in tests/host_kernel.py (which the mix-bus
     assertions of the other host tests use) and, within the reduction-order tolerance, against the oracle's sequential sum:

@@ -574,17 +574,21 @@ def test_clip_oversampled_full_size_1m_voices_round_trip_properties():
 
 
 # --------------------------------------------------------------- device-side MIDI front (SURVEY §8f.2)
-def _random_midi(rng, n_inst, frames, per_inst_max, n_notes):
+def _random_midi(rng, n_inst, frames, per_inst_max, n_notes, malformed=0.0):
     """[(instance, frame, bytes)] in push order: note-ons, note-offs, velocity-0 note-ons, controller noise,
-    some instances above the 32-slot queue, some offsets beyond the block"""
+    some instances above the 32-slot queue, some offsets beyond the block.  malformed > 0: that share of the messages
+    carries data bytes >= 0x80 (the reference's note / velocity are any u8, midi.rs:8-35: note 255 must still match its
+    note-off, a velocity byte of 200 clamps to 1.0)"""
     msgs = []
     for inst in range(n_inst):
         for _ in range(int(rng.integers(0, per_inst_max + 1))):
             frame = int(rng.integers(0, frames + 30))
             note = int(rng.integers(40, 40 + n_notes))
+            if malformed > 0.0 and rng.random() < malformed:
+                note = 256 - 1 - (note - 40) % 8                     # 255, 254, ...: few distinct notes, so that note-offs match
             r = rng.random()
             if r < 0.55:
-                data = [0x90 | int(rng.integers(0, 16)), note, int(rng.integers(1, 128))]
+                data = [0x90 | int(rng.integers(0, 16)), note, int(rng.integers(1, 256 if malformed > 0.0 else 128))]
             elif r < 0.85:
                 data = [0x80, note, 0]
             elif r < 0.93:

@@ -320,6 +320,12 @@ int  oscen_b200_last_block_ms(oscen_b200_engine *e, float *ms);
 int  oscen_b200_enable_timing(oscen_b200_engine *e, int on);
 /* device time of the last block's graph kernel alone (fused plan) / node sequence (node plan) */
 int  oscen_b200_last_kernel_ms(oscen_b200_engine *e, float *ms);
+/* the same two figures for EVERY block rendered since enable_timing(1) / the previous drain, oldest first, with one
+   synchronisation for the whole batch (a timed loop then never waits on the device per step).  Either array may be
+   NULL.  Returns the number of blocks written (<= cap); the engine keeps the last 4096 blocks. */
+int  oscen_b200_timing_drain(oscen_b200_engine *e, float *block_ms, float *kernel_ms, uint32_t cap);
+/* which graph kernel (variant) the last process_block launched, e.g. "fm_voice_fast_kernel<ramp>": a static string */
+const char *oscen_b200_last_kernel_name(const oscen_b200_engine *e);
 /* benchmarking aid: overwrite a 256 MiB scratch buffer on the engine stream so the next block
    starts with a cold L2 (126 MB) */
 int  oscen_b200_l2_flush(oscen_b200_engine *e);

@@ -36,7 +36,7 @@ SYMBOLS = [
     "oscen_b200_synchronize", "oscen_b200_read_voice_out", "oscen_b200_read_instance_out", "oscen_b200_read_mix",
     "oscen_b200_channels", "oscen_b200_latency_samples", "oscen_b200_n_inputs",
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
-    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
+    "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_timing_drain", "oscen_b200_last_kernel_name", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
     "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
     "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
@@ -134,6 +134,9 @@ def load():
     L.oscen_b200_enable_timing.argtypes = [vp, C.c_int]
     L.oscen_b200_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.oscen_b200_l2_flush.argtypes = [vp]
+    L.oscen_b200_timing_drain.argtypes = [vp, vp, vp, u32]
+    L.oscen_b200_last_kernel_name.argtypes = [vp]
+    L.oscen_b200_last_kernel_name.restype = C.c_char_p
     L.oscen_b200_comm_unique_id.argtypes = [vp]
     L.oscen_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.oscen_b200_comm_p2p_export.argtypes = [vp, C.c_int, vp]
@@ -451,6 +454,17 @@ class Engine:
         ms = C.c_float()
         self._chk(self.L.oscen_b200_last_kernel_ms(self.h, C.byref(ms)), "last_kernel_ms")
         return ms.value
+
+    def timing_drain(self, cap=4096):
+        """(block_ms, kernel_ms) float32 arrays of every block since enable_timing(True) / the previous drain; one sync"""
+        b = np.empty(cap, dtype=np.float32); k = np.empty(cap, dtype=np.float32)
+        n = self.L.oscen_b200_timing_drain(self.h, b.ctypes.data, k.ctypes.data, cap)
+        if n < 0:
+            self._chk(n, "timing_drain")
+        return b[:n].copy(), k[:n].copy()
+
+    def last_kernel_name(self):
+        return (self.L.oscen_b200_last_kernel_name(self.h) or b"").decode()
 
     def l2_flush(self):
         self._chk(self.L.oscen_b200_l2_flush(self.h), "l2_flush")

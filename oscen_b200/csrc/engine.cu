@@ -38,6 +38,7 @@ static_assert(kMaxInputs == OSCEN_B200_MAX_INPUTS, "input count");
 namespace {
 
 thread_local std::string g_create_error;
+constexpr uint32_t kTimingRing = 4096;
 
 const char *const kJitKernelName = "oscen_b200_generated_kernel";
 const uint32_t kNInputs[7] = {28, 3, 2, 2, 9, 4, 8};       /* clip graphs: no value inputs */
@@ -199,10 +200,15 @@ struct oscen_b200_engine {
 
     /* stats / timing */
     oscen_b200_stats stats{};
+    /* per-block CUDA events on the engine stream: a ring of {start, graph kernel done, block done}, read back in bulk by
+       timing_drain() so that a timed loop does not synchronise with the device every step */
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;
+    std::vector<cudaEvent_t> tev;                /* 3 per slot, created on demand */
+    uint32_t t_count = 0, t_drained = 0;         /* blocks recorded / already handed out since enable_timing(1) */
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk = nullptr;   /* the current block's slot */
     uint32_t *d_flush = nullptr;
     bool ev_valid = false;
+    const char *last_kernel = "";                /* the graph kernel (variant) the last block ran */
 };
 
 namespace {
@@ -348,20 +354,21 @@ int launch_fused(oscen_b200_engine *e, bool general) {
     e->n_cta_mix = grid;
     switch (e->cfg.graph_kind) {
     case OSCEN_B200_GRAPH_FM_VOICE:
-        if (general) fm_voice_kernel<true><<<grid, kCta, 0, e->stream>>>(a);
-        else fm_voice_kernel<false><<<grid, kCta, 0, e->stream>>>(a);
+        if (general) { fm_voice_kernel<true><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "fm_voice_kernel<true>"; }
+        else { fm_voice_kernel<false><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "fm_voice_kernel<false>"; }
         break;
-    case OSCEN_B200_GRAPH_TWIN_PEAKS: twin_peaks_kernel<<<grid, kCta, 0, e->stream>>>(a); break;
-    case OSCEN_B200_GRAPH_SAT_1X: sat_kernel<1><<<grid, kCta, kSatDyn, e->stream>>>(a); break;
-    case OSCEN_B200_GRAPH_SAT_4X: sat_kernel<4><<<grid, kCta, kSatDyn, e->stream>>>(a); break;
-    case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kCta, kEpDyn, e->stream>>>(a); break;
-    case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); break;
-    case OSCEN_B200_GRAPH_SYNTH_ADSR: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); break;
+    case OSCEN_B200_GRAPH_TWIN_PEAKS: twin_peaks_kernel<<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "twin_peaks_kernel"; break;
+    case OSCEN_B200_GRAPH_SAT_1X: sat_kernel<1><<<grid, kCta, kSatDyn, e->stream>>>(a); e->last_kernel = "sat_kernel<1>"; break;
+    case OSCEN_B200_GRAPH_SAT_4X: sat_kernel<4><<<grid, kCta, kSatDyn, e->stream>>>(a); e->last_kernel = "sat_kernel<4>"; break;
+    case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kCta, kEpDyn, e->stream>>>(a); e->last_kernel = "epiano_kernel"; break;
+    case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "synth_kernel<false>"; break;
+    case OSCEN_B200_GRAPH_SYNTH_ADSR: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "synth_kernel<true>"; break;
     case OSCEN_B200_GRAPH_CUSTOM: {
         const int rc = e->jit.launch(grid, kCta, (void *)e->stream, &a);
         if (rc != 0) { e->err = "cuLaunchKernel (generated kernel): " + jit::driver_error(rc); return OSCEN_B200_E_CUDA; }
+        e->last_kernel = kJitKernelName;
     } break;
-    default: launch_clip(e, a, grid); break;
+    default: launch_clip(e, a, grid); e->last_kernel = "clip_kernel"; break;
     }
     e->stats.kernel_launches++;
     CK(e, cudaGetLastError());
@@ -548,9 +555,7 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     cudaFree(e->d_events); cudaFree(e->d_ctl); cudaFree(e->d_stream_in);
     cudaFree(e->d_voice_out); cudaFree(e->d_inst_out); cudaFree(e->d_mix_partial); cudaFree(e->d_mix);
     cudaFreeHost(e->h_ptab); cudaFreeHost(e->h_events); cudaFreeHost(e->h_ctl); cudaFreeHost(e->h_mix);
-    if (e->ev0) cudaEventDestroy(e->ev0);
-    if (e->ev1) cudaEventDestroy(e->ev1);
-    if (e->evk) cudaEventDestroy(e->evk);
+    for (cudaEvent_t ev : e->tev) if (ev) cudaEventDestroy(ev);
     cudaFree(e->d_flush);
     cudaFree(e->d_assets);
     for (float *b : e->d_asset_buf) cudaFree(b);
@@ -660,7 +665,6 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         CK(e, cudaMalloc(&e->d_mix, (size_t)kMaxBlock * e->channels * sizeof(float)));
         CK(e, cudaMemsetAsync(e->d_mix, 0, (size_t)kMaxBlock * e->channels * sizeof(float), e->stream));
         CK(e, cudaMallocHost(&e->h_mix, (size_t)kMaxBlock * e->channels * sizeof(float) + 16));   /* + peer-timeout flag */
-        CK(e, cudaEventCreate(&e->ev0)); CK(e, cudaEventCreate(&e->ev1)); CK(e, cudaEventCreate(&e->evk));
         if (custom && cfg->plan == OSCEN_B200_PLAN_FUSED) {
             CK(e, cudaFree(nullptr));                              /* the runtime's primary context is current from here on */
             e->graph = pg; e->plan = pp;
@@ -1134,7 +1138,16 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         const int r = midi_device_run(e, frames); if (r) return r;
         e->ctl_on_device.n_events = 0xFFFFFFFFu;
     }
-    if (e->timing) CK(e, cudaEventRecord(e->ev0, e->stream));
+    if (e->timing) {
+        const uint32_t slot = e->t_count % kTimingRing;
+        if (e->tev.size() < (size_t)(slot + 1) * 3) {
+            const size_t at = e->tev.size();
+            e->tev.resize((size_t)(slot + 1) * 3, nullptr);
+            for (size_t k = at; k < e->tev.size(); ++k) CK(e, cudaEventCreate(&e->tev[k]));
+        }
+        e->ev0 = e->tev[slot * 3 + 0]; e->evk = e->tev[slot * 3 + 1]; e->ev1 = e->tev[slot * 3 + 2];
+        CK(e, cudaEventRecord(e->ev0, e->stream));
+    }
     int rc = 0;
     if (e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
         rc = launch_fused(e, general); if (rc) return rc;
@@ -1162,6 +1175,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             cudaGraphDestroy(g);
         }
         CK(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
+        e->last_kernel = "node plan (CUDA graph)";
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         e->stats.graph_launches++;
         e->stats.kernel_launches += e->graph_kernels[gi];
@@ -1170,7 +1184,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         const int r = g_nccl.AllReduce(e->d_mix, e->d_mix, (size_t)frames * e->channels, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, e->stream);
         if (r != 0) { e->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return OSCEN_B200_E_NCCL; }
     }
-    if (e->timing) { CK(e, cudaEventRecord(e->ev1, e->stream)); e->ev_valid = true; }
+    if (e->timing) { CK(e, cudaEventRecord(e->ev1, e->stream)); e->ev_valid = true; e->t_count++; }
     /* ramp-driven inputs end the block at their last per-frame value; the per-voice row is only
        read again once the input has stopped ramping, so it is refilled when the ramp completes */
     if (ramp_mask) {
@@ -1321,7 +1335,33 @@ int oscen_b200_get_stats(const oscen_b200_engine *e, oscen_b200_stats *out) {
     return 0;
 }
 
-int oscen_b200_enable_timing(oscen_b200_engine *e, int on) { if (!e) return OSCEN_B200_E_ARG; e->timing = on != 0; e->ev_valid = false; return 0; }
+int oscen_b200_enable_timing(oscen_b200_engine *e, int on) {
+    if (!e) return OSCEN_B200_E_ARG;
+    e->timing = on != 0; e->ev_valid = false; e->t_count = 0; e->t_drained = 0;
+    return 0;
+}
+
+/* device times of the blocks rendered since enable_timing(1) / the previous drain, oldest first: ONE synchronisation for
+   the whole batch.  Returns the number of blocks written (<= cap); blocks older than the ring (4096) are lost. */
+int oscen_b200_timing_drain(oscen_b200_engine *e, float *block_ms, float *kernel_ms, uint32_t cap) {
+    if (!e || (!block_ms && !kernel_ms)) return OSCEN_B200_E_ARG;
+    if (!e->timing || e->t_count == 0) return 0;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaEventSynchronize(e->ev1));
+    if (e->t_count - e->t_drained > kTimingRing) e->t_drained = e->t_count - kTimingRing;
+    uint32_t n = 0;
+    while (e->t_drained < e->t_count && n < cap) {
+        const uint32_t slot = e->t_drained % kTimingRing;
+        float ms = 0.0f;
+        if (block_ms) { CK(e, cudaEventElapsedTime(&ms, e->tev[slot * 3 + 0], e->tev[slot * 3 + 2])); block_ms[n] = ms; }
+        if (kernel_ms) { CK(e, cudaEventElapsedTime(&ms, e->tev[slot * 3 + 0], e->tev[slot * 3 + 1])); kernel_ms[n] = ms; }
+        ++n; e->t_drained++;
+    }
+    return (int)n;
+}
+
+/* name of the graph kernel (variant) the last process_block launched: static string, never NULL */
+const char *oscen_b200_last_kernel_name(const oscen_b200_engine *e) { return e ? e->last_kernel : ""; }
 
 int oscen_b200_last_block_ms(oscen_b200_engine *e, float *ms) {
     if (!e || !ms) return OSCEN_B200_E_ARG;

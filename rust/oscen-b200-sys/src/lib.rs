@@ -140,6 +140,8 @@ extern "C" {
     pub fn oscen_b200_last_block_ms(e: *mut oscen_b200_engine, ms: *mut f32) -> c_int;
     pub fn oscen_b200_enable_timing(e: *mut oscen_b200_engine, on: c_int) -> c_int;
     pub fn oscen_b200_last_kernel_ms(e: *mut oscen_b200_engine, ms: *mut f32) -> c_int;
+    pub fn oscen_b200_timing_drain(e: *mut oscen_b200_engine, block_ms: *mut f32, kernel_ms: *mut f32, cap: u32) -> c_int;
+    pub fn oscen_b200_last_kernel_name(e: *const oscen_b200_engine) -> *const c_char;
     pub fn oscen_b200_l2_flush(e: *mut oscen_b200_engine) -> c_int;
     pub fn oscen_b200_comm_unique_id(id128: *mut c_void) -> c_int;
     pub fn oscen_b200_comm_init(e: *mut oscen_b200_engine, rank: c_int, n_ranks: c_int, id128: *const c_void) -> c_int;

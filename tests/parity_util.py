@@ -50,3 +50,27 @@ def seq_sum_f32(x, axis):
     for i in range(x.shape[0]):
         acc = (acc + x[i]).astype(np.float32)
     return acc
+
+
+def lcg_noise_block(seeds, frames, state=None):
+    """lcg_noise() for a whole bank at once: seeds [n] (uint64) -> (x [frames, n] f32, state) — `state` continues the streams
+    across blocks.  Same values as lcg_noise(frames, seed) per column (the engine's stream_in_lcg / lcg_next)."""
+    with np.errstate(over="ignore"):
+        if state is None:
+            state = np.asarray(seeds, dtype=np.uint64) * np.uint64(2862933555777941757) + np.uint64(3037000493)
+        x = np.empty((frames, state.size), dtype=np.float32)
+        for f in range(frames):
+            state = state * np.uint64(6364136223846793005) + np.uint64(1442695040888963407)
+            x[f] = (state >> np.uint64(33)).astype(np.float32) / np.float32(2147483648.0) - np.float32(1.0)
+    return x, state
+
+
+def strided_instances(n_inst, inst_per_cta, count):
+    """`count` instance indices spread over ALL CTAs of the bank (one thread = one voice, 64-thread CTAs): consecutive picks
+    land in different CTAs and rotate through the positions inside a CTA, first and last instance included"""
+    n_cta = (n_inst + inst_per_cta - 1) // inst_per_cta
+    count = min(count, n_inst)
+    ctas = (np.arange(count, dtype=np.int64) * n_cta) // count
+    idx = np.minimum(ctas * inst_per_cta + (np.arange(count) % inst_per_cta), n_inst - 1)
+    idx[0] = 0; idx[-1] = n_inst - 1
+    return np.unique(idx)

@@ -289,38 +289,6 @@ def test_block_split_invariance_on_gpu():
     assert np.array_equal(ya, np.concatenate(y))
 
 
-def test_config2_full_size_65536_voices_properties():
-    """BASELINE config 2 at full size: oracle on a slice, exact fold / silence / determinism on all"""
-    n, vpi, frames = 65536, 8, 256
-    gpu = engine(O.K_FM, n, vpi)
-    notes = 36 + (np.arange(n) * 7) % 60
-    freq = (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32)
-    on = (np.arange(n) * 13) % frames
-    gpu.set_value(0, freq)
-    from oscen_b200 import abi
-    ev = np.zeros(n, dtype=abi.EVENT_DTYPE)
-    ev["voice"] = np.arange(n); ev["frame_offset"] = on; ev["input_id"] = GATE; ev["scalar"] = 0.5
-    gpu.push_events(ev)
-    gpu.process_block(frames)
-    v0 = gpu.read_voice_out(); i0 = gpu.read_instance_out()[:, :, 0]; m0 = gpu.read_mix()[:, 0]
-    # silent before each voice's gate-on frame
-    before = np.arange(frames)[:, None] < on[None, :]
-    assert np.all(v0[before] == 0.0)
-    assert np.array_equal(seq_sum_f32(v0.reshape(frames, n // vpi, vpi), axis=2), i0)
-    assert np.allclose(m0, i0.astype(np.float64).sum(axis=1), rtol=1e-4, atol=1e-3)
-    # slice parity: voices are independent, so an oracle bank of the first 64 voices must agree
-    ref = O.OracleBank(O.K_FM, 64, 8)
-    ref.set_value(0, freq[:64])
-    ref.push_events([(v, int(on[v]), GATE, 0.5) for v in range(64)])
-    ref.process_block(frames)
-    assert_close(v0[:, :64], ref.read_voice_out(), "config-2 slice")
-    # determinism: a second engine renders the identical bits
-    g2 = engine(O.K_FM, n, vpi)
-    g2.set_value(0, freq); g2.push_events(ev); g2.process_block(frames)
-    assert np.array_equal(g2.read_mix()[:, 0], m0)
-    assert np.array_equal(g2.read_voice_out(first_voice=n - 128, count=128), v0[:, n - 128:])
-
-
 # --------------------------------------------------------------- edge cases
 @pytest.mark.parametrize("n,vpi", [(8, 8), (72, 8), (130, 1), (96, 2), (48, 16), (4, 4)])
 @pytest.mark.parametrize("frames", [1, 7, 512])
@@ -396,73 +364,7 @@ def test_same_frame_note_on_and_off_and_retrigger():
     assert np.array_equal(yg, yr)
 
 
-# --------------------------------------------------------------- BASELINE configs 3-5 at full size
-def _slice_events(n_slice, frames, vel=0.7):
-    return [(v, (7 * v) % frames, GATE, vel) for v in range(n_slice)]
-
-
-def test_config4_full_size_twin_peaks_1m_voices():
-    """config 4: TwinPeaksGraph x 1 048 576 voices, device-generated LCG audio_in (seed 1000+voice)"""
-    n, frames = 1048576, 256
-    gpu = engine(O.K_TWIN, n, 1, keep=1)
-    gpu.stream_in_lcg(0, 1000, 0)
-    outs = []
-    for _ in range(2):
-        gpu.process_block(frames)
-        outs.append((gpu.read_voice_out(0, 96), gpu.read_voice_out(n - 64, 64), gpu.read_mix()[:, 0].copy()))
-    # slice parity against the oracle fed with the host-side LCG noise of the same seeds
-    for first, count, idx in ((0, 96, 0), (n - 64, 64, 1)):
-        ref = O.OracleBank(O.K_TWIN, count, 1)
-        x = np.stack([lcg_noise(2 * frames, 1000 + first + v) for v in range(count)], axis=1)
-        for b in range(2):
-            ref.stream_in(0, x[b * frames:(b + 1) * frames]); ref.process_block(frames)
-            assert np.array_equal(outs[b][idx], ref.read_voice_out()), (first, b)
-    # linear-ish sanity of the mix bus: finite, non-trivial, deterministic on a second engine
-    g2 = engine(O.K_TWIN, n, 1, keep=0)
-    g2.stream_in_lcg(0, 1000, 0)
-    g2.process_block(frames)
-    assert np.array_equal(g2.read_mix()[:, 0], outs[0][2]) and np.isfinite(outs[0][2]).all() and np.abs(outs[0][2]).max() > 1.0
-
-
-def test_config5_full_size_saturator_4x_262144_voices():
-    n, frames = 262144, 256
-    gpu = engine(O.K_SAT4, n, 1, keep=1)
-    f = (2000.0 * (0.5 + (np.arange(n) % 1000) / 1000.0)).astype(np.float32)
-    gpu.set_value(0, f)
-    ref = O.OracleBank(O.K_SAT4, 128, 1)
-    ref.set_value(0, f[:128])
-    for _ in range(2):
-        gpu.process_block(frames); ref.process_block(frames)
-        y = gpu.read_voice_out(0, 128)
-        assert np.array_equal(y, ref.read_voice_out())
-        tail = gpu.read_voice_out(n - 1000, 1000)
-        assert np.array_equal(tail[:, :24], gpu.read_voice_out(n - 2000, 24))      # same frequencies 1000 voices apart
-    assert gpu.latency_samples() == 8 and np.abs(y).max() > 0.3
-
-
-def test_config3_full_size_electric_piano_131072_instances():
-    """config 3: ElectricPianoGraph (16-voice polyphony) x 131 072 instances = 2 097 152 voices"""
-    n_inst, vpi, frames = 131072, 16, 256
-    n = n_inst * vpi
-    gpu = engine(O.K_EPIANO, n, vpi, keep=2)
-    from oscen_b200 import abi
-    notes = 36 + (np.arange(n) * 5) % 48
-    freq = (440.0 * np.exp2((notes - 69) / 12.0)).astype(np.float32)
-    gpu.set_value(0, freq)
-    ev = np.zeros(n // 4, dtype=abi.EVENT_DTYPE)                 # a quarter of the voices play
-    ev["voice"] = np.arange(0, n, 4); ev["frame_offset"] = (np.arange(n // 4) * 3) % frames
-    ev["input_id"] = GATE; ev["scalar"] = 0.6
-    gpu.push_events(ev)
-    ref = O.OracleBank(O.K_EPIANO, 4 * vpi, vpi)                   # first 4 instances
-    ref.set_value(0, freq[:4 * vpi])
-    ref.push_events([(int(v), int(fo), GATE, 0.6) for v, fo in zip(ev["voice"], ev["frame_offset"]) if v < 4 * vpi])
-    for _ in range(2):
-        gpu.process_block(frames); ref.process_block(frames)
-        io = gpu.read_instance_out(0, 4)
-        assert np.array_equal(io, ref.read_instance_out())
-    assert np.abs(io).max() > 1e-3 and np.abs(io[..., 0] - io[..., 1]).max() > 1e-6
-    mix = gpu.read_mix()
-    assert np.isfinite(mix).all() and np.abs(mix).max() > 1.0
+# BASELINE configs 2-5 at full size: tests/test_fullsize_gpu.py (strided samples over all CTAs + the whole bank's mix bus)
 
 
 # --------------------------------------------------------------- plan compiler: node plans of the other graphs

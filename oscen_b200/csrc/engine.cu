@@ -20,6 +20,8 @@
 #include "../../include/oscen_b200.h"
 #include "engine_types.h"
 #include "kernel_fm.cuh"
+#include "kernel_fm_seg.cuh"
+#include "fm_select.hpp"
 #include "kernel_nodes.cuh"
 #include "kernel_others.cuh"
 #include "kernel_resample.cuh"
@@ -128,7 +130,18 @@ struct oscen_b200_engine {
     bool ramped[kMaxInputs] = {};
     Ramp ramps[kMaxInputs];
     float *d_pv = nullptr;
-    float *d_ptab = nullptr, *h_ptab = nullptr;
+    float *d_ptab = nullptr;
+    float *d_utab = nullptr;             /* FMVoice, segmented kernel in ramp blocks: one FmRow per frame (kernel_fm_seg.cuh) */
+    FmBoundState fm_bounds;              /* fm_select.hpp: levels the previous block rendered with */
+    int fm_variant = FM_GENERAL;
+    /* pinned staging for per-block uploads (events, ramp tables): a ring, so that filling the next block's buffer never
+       waits for the previous block's copy — each slot carries an event recorded after its copy was enqueued */
+    static constexpr int kStage = 8;
+    void *stage_h[kStage] = {};
+    size_t stage_cap[kStage] = {};
+    cudaEvent_t stage_ev[kStage] = {};
+    bool stage_busy[kStage] = {};
+    int stage_next = 0;
 
     /* state */
     float *d_state = nullptr, *d_inst_state = nullptr;
@@ -148,7 +161,7 @@ struct oscen_b200_engine {
     int *d_h_note = nullptr; float *d_h_freq = nullptr, *d_note_freq = nullptr;
     uint32_t *d_ev_count = nullptr, *d_ev_offset = nullptr, *d_midi_dropped = nullptr;
     uint32_t seq = 0;
-    Event *d_events = nullptr, *h_events = nullptr;
+    Event *d_events = nullptr;
     size_t events_cap = 0;
     BlockCtl *d_ctl = nullptr, *h_ctl = nullptr;
     BlockCtl ctl_on_device{};
@@ -223,6 +236,28 @@ namespace {
     } while (0)
 
 int arg_error(oscen_b200_engine *e, const char *msg) { e->err = msg; return OSCEN_B200_E_ARG; }
+
+/* next slot of the pinned staging ring with room for `bytes`; *slot is handed to stage_submit after the copy is enqueued */
+int stage_acquire(oscen_b200_engine *e, size_t bytes, void **out, int *slot) {
+    const int k = e->stage_next;
+    e->stage_next = (k + 1) % oscen_b200_engine::kStage;
+    if (e->stage_busy[k]) { CK(e, cudaEventSynchronize(e->stage_ev[k])); e->stage_busy[k] = false; }
+    if (e->stage_cap[k] < bytes) {
+        if (e->stage_h[k]) cudaFreeHost(e->stage_h[k]);
+        e->stage_h[k] = nullptr; e->stage_cap[k] = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 2, 64 * 1024);
+        CK(e, cudaMallocHost(&e->stage_h[k], cap));
+        e->stage_cap[k] = cap;
+    }
+    if (!e->stage_ev[k]) CK(e, cudaEventCreateWithFlags(&e->stage_ev[k], cudaEventDisableTiming));
+    *out = e->stage_h[k]; *slot = k;
+    return 0;
+}
+int stage_submit(oscen_b200_engine *e, int slot) {
+    CK(e, cudaEventRecord(e->stage_ev[slot], e->stream));
+    e->stage_busy[slot] = true;
+    return 0;
+}
 
 /* initial SoA state of one voice after G::new() + G::init(sr) */
 std::vector<uint32_t> initial_state(uint32_t kind, float sr, const plan::Graph *custom, uint32_t n_state) {
@@ -307,6 +342,7 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
     a.voice_out = e->d_voice_out; a.inst_out = e->d_inst_out; a.inst_state = e->d_inst_state;
     a.mix_partial = e->d_mix_partial;
     a.assets = e->d_assets;
+    a.utab = e->d_utab;
     for (uint32_t i = 0; i < kMaxInputs; ++i) a.u.p[i] = e->uni[i];
     a.u.sr = e->cfg.sample_rate;
     if (e->cfg.graph_kind == OSCEN_B200_GRAPH_FM_VOICE) {
@@ -354,8 +390,15 @@ int launch_fused(oscen_b200_engine *e, bool general) {
     e->n_cta_mix = grid;
     switch (e->cfg.graph_kind) {
     case OSCEN_B200_GRAPH_FM_VOICE:
-        if (general) { fm_voice_kernel<true><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "fm_voice_kernel<true>"; }
-        else { fm_voice_kernel<false><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "fm_voice_kernel<false>"; }
+        (void)general;
+        switch (e->fm_variant) {                              /* chosen by fm_select_variant() in process_block */
+        case FM_SEG: fm_voice_seg_kernel<false, false><<<grid, kCta, 0, e->stream>>>(a); break;
+        case FM_SEG_FMOD: fm_voice_seg_kernel<false, true><<<grid, kCta, 0, e->stream>>>(a); break;
+        case FM_SEG_RAMP: fm_voice_seg_kernel<true, true><<<grid, kCta, 0, e->stream>>>(a); break;
+        case FM_LEGACY: fm_voice_kernel<false><<<grid, kCta, 0, e->stream>>>(a); break;
+        default: fm_voice_kernel<true><<<grid, kCta, 0, e->stream>>>(a); break;
+        }
+        e->last_kernel = fm_variant_name(e->fm_variant);
         break;
     case OSCEN_B200_GRAPH_TWIN_PEAKS: twin_peaks_kernel<<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "twin_peaks_kernel"; break;
     case OSCEN_B200_GRAPH_SAT_1X: sat_kernel<1><<<grid, kCta, kSatDyn, e->stream>>>(a); e->last_kernel = "sat_kernel<1>"; break;
@@ -554,7 +597,9 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
     cudaFree(e->d_events); cudaFree(e->d_ctl); cudaFree(e->d_stream_in);
     cudaFree(e->d_voice_out); cudaFree(e->d_inst_out); cudaFree(e->d_mix_partial); cudaFree(e->d_mix);
-    cudaFreeHost(e->h_ptab); cudaFreeHost(e->h_events); cudaFreeHost(e->h_ctl); cudaFreeHost(e->h_mix);
+    cudaFreeHost(e->h_ctl); cudaFreeHost(e->h_mix);
+    for (int k = 0; k < oscen_b200_engine::kStage; ++k) { if (e->stage_h[k]) cudaFreeHost(e->stage_h[k]); if (e->stage_ev[k]) cudaEventDestroy(e->stage_ev[k]); }
+    cudaFree(e->d_utab);
     for (cudaEvent_t ev : e->tev) if (ev) cudaEventDestroy(ev);
     cudaFree(e->d_flush);
     cudaFree(e->d_assets);
@@ -580,6 +625,9 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
     }
     if ((custom == nullptr) != (cfg->graph_kind != OSCEN_B200_GRAPH_CUSTOM)) {
         g_create_error = "OSCEN_B200_GRAPH_CUSTOM engines are created with oscen_b200_create_from_graph (and only those)"; return OSCEN_B200_E_ARG;
+    }
+    if ((cfg->keep & OSCEN_B200_KEEP_VOICE_OUT) && (uint64_t)cfg->n_voices * kMaxBlock > 0xFFFFFFFFull) {
+        g_create_error = "KEEP_VOICE_OUT: n_voices * 512 must fit 32 bits (<= 8 388 607 voices per engine)"; return OSCEN_B200_E_ARG;
     }
     if (cfg->graph_kind >= OSCEN_B200_GRAPH_COUNT || cfg->n_voices == 0 || cfg->voices_per_instance == 0 ||
         kCta % cfg->voices_per_instance != 0 || (cfg->voices_per_instance & (cfg->voices_per_instance - 1)) != 0 || cfg->n_voices % cfg->voices_per_instance != 0 ||
@@ -648,7 +696,7 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
             CK(e, cudaMemset(e->d_assets, 0, sizeof(AssetTable)));
         }
         CK(e, cudaMalloc(&e->d_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
-        CK(e, cudaMallocHost(&e->h_ptab, (size_t)kMaxBlock * kMaxInputs * sizeof(float)));
+        if (kind == OSCEN_B200_GRAPH_FM_VOICE) CK(e, cudaMalloc(&e->d_utab, (size_t)kMaxBlock * kFmRowFloats * sizeof(float)));
         CK(e, cudaMalloc(&e->d_state, (size_t)e->n_state * n * sizeof(float)));
         CK(e, cudaMalloc(&e->d_inst_state, (size_t)e->n_inst * sizeof(float)));
         CK(e, cudaMemsetAsync(e->d_inst_state, 0, (size_t)e->n_inst * sizeof(float), e->stream));
@@ -658,7 +706,6 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         CK(e, cudaMemcpyAsync(e->d_ctl, e->h_ctl, sizeof(BlockCtl), cudaMemcpyHostToDevice, e->stream));
         e->events_cap = 1024;
         CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
-        CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
         if (cfg->keep & OSCEN_B200_KEEP_VOICE_OUT) CK(e, cudaMalloc(&e->d_voice_out, (size_t)kMaxBlock * n * sizeof(float)));
         if (cfg->keep & OSCEN_B200_KEEP_INSTANCE_OUT) CK(e, cudaMalloc(&e->d_inst_out, (size_t)kMaxBlock * e->n_inst * e->channels * sizeof(float)));
         CK(e, cudaMalloc(&e->d_mix_partial, (size_t)e->n_cta * kMaxBlock * e->channels * sizeof(float)));
@@ -921,10 +968,9 @@ int midi_device_run(oscen_b200_engine *e, uint32_t frames) {
     /* every message yields at most a gate and a frequency event */
     if ((size_t)nm * 2 > e->events_cap) {
         CK(e, cudaStreamSynchronize(e->stream));
-        cudaFree(e->d_events); cudaFreeHost(e->h_events);
+        cudaFree(e->d_events);
         e->events_cap = (size_t)nm * 4;
         CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
-        CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
         for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     }
     /* pageable source: the copy is staged by the runtime before the call returns */
@@ -1048,44 +1094,55 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
        32-slot queue in PUSH order (try_push on a full ArrayVec drops, graph/types.rs:183-188), then
        process_block stages the queue sorted by frame_offset and never reaches offsets >= frames
        (codegen/mod.rs:836-872).  Value events are field assignments: no cap. */
-    std::vector<uint32_t> order(e->pending.size());
-    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-        const Event &a = e->pending[x], &b = e->pending[y];
-        if (a.voice != b.voice) return a.voice < b.voice;
-        if (a.frame != b.frame) return a.frame < b.frame;
-        return e->seqs[x] < e->seqs[y];
-    });
+    const size_t n_pend = e->pending.size();
+    /* already in (voice, frame) order, as a host that walks its voices produces it?  then arrival order is the tie-break
+       and the 65 536-event burst of a bank-wide note-on needs no sort */
+    bool sorted = true;
+    for (size_t i = 1; i < n_pend && sorted; ++i) {
+        const Event &a = e->pending[i - 1], &b = e->pending[i];
+        sorted = a.voice < b.voice || (a.voice == b.voice && a.frame <= b.frame);
+    }
+    std::vector<uint32_t> order;
+    if (!sorted) {
+        order.resize(n_pend);
+        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            const Event &a = e->pending[x], &b = e->pending[y];
+            if (a.voice != b.voice) return a.voice < b.voice;
+            if (a.frame != b.frame) return a.frame < b.frame;
+            return e->seqs[x] < e->seqs[y];
+        });
+    }
+    auto at = [&](size_t k) -> uint32_t { return sorted ? (uint32_t)k : order[k]; };
     uint32_t n_ev = 0;
     bool general = false, has_value_events = false;
-    {
-        if (order.size() > e->events_cap) {
+    Event *h_events = nullptr;
+    int ev_slot = -1;
+    if (n_pend) {
+        if (n_pend > e->events_cap) {
             CK(e, cudaStreamSynchronize(e->stream));
-            cudaFree(e->d_events); cudaFreeHost(e->h_events);
-            e->events_cap = order.size() * 2;
+            cudaFree(e->d_events); e->d_events = nullptr;
+            e->events_cap = n_pend * 2;
             CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
-            CK(e, cudaMallocHost(&e->h_events, e->events_cap * sizeof(Event)));
             for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
         }
-        /* the pinned staging buffer may still be in flight from the previous block */
-        if (!order.empty()) CK(e, cudaStreamSynchronize(e->stream));
+        { void *hp = nullptr; const int r = stage_acquire(e, n_pend * sizeof(Event), &hp, &ev_slot); if (r) return r; h_events = (Event *)hp; }
         std::vector<uint32_t> gate_seqs;
         size_t g0 = 0;
-        while (g0 < order.size()) {
+        while (g0 < n_pend) {
             size_t g1 = g0;
-            const uint32_t voice = e->pending[order[g0]].voice;
-            gate_seqs.clear();
-            while (g1 < order.size() && e->pending[order[g1]].voice == voice) {
-                if (e->pending[order[g1]].input_id == kEventGate) gate_seqs.push_back(e->seqs[order[g1]]);
-                ++g1;
-            }
+            const uint32_t voice = e->pending[at(g0)].voice;
+            uint32_t n_gates = 0;
+            while (g1 < n_pend && e->pending[at(g1)].voice == voice) { if (e->pending[at(g1)].input_id == kEventGate) ++n_gates; ++g1; }
             uint32_t seq_limit = 0xFFFFFFFFu;                  /* gates pushed at or after this seq found the queue full */
-            if (gate_seqs.size() > OSCEN_B200_MAX_EVENTS_PER_ENDPOINT) {
+            if (n_gates > OSCEN_B200_MAX_EVENTS_PER_ENDPOINT) {
+                gate_seqs.clear();
+                for (size_t k = g0; k < g1; ++k) if (e->pending[at(k)].input_id == kEventGate) gate_seqs.push_back(e->seqs[at(k)]);
                 std::nth_element(gate_seqs.begin(), gate_seqs.begin() + OSCEN_B200_MAX_EVENTS_PER_ENDPOINT, gate_seqs.end());
                 seq_limit = gate_seqs[OSCEN_B200_MAX_EVENTS_PER_ENDPOINT];
             }
             for (size_t k = g0; k < g1; ++k) {
-                const uint32_t idx = order[k];
+                const uint32_t idx = at(k);
                 const Event &x = e->pending[idx];
                 if (x.input_id == kEventGate && e->seqs[idx] >= seq_limit) { e->stats.events_dropped++; continue; }
                 if (x.frame >= frames) { e->stats.events_dropped++; continue; }
@@ -1093,7 +1150,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
                     e->uniform[x.input_id] = false; has_value_events = true;
                     if (x.input_id != 0u || kind != OSCEN_B200_GRAPH_FM_VOICE) general = true;
                 }
-                e->h_events[n_ev++] = x;
+                h_events[n_ev++] = x;
             }
             g0 = g1;
         }
@@ -1104,27 +1161,45 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
     uint32_t ramp_mask = 0;
     for (uint32_t i = 0; i < e->n_inputs; ++i)
         if (e->ramped[i] && e->ramps[i].remaining > 0) ramp_mask |= 1u << i;
+    float *h_ptab = nullptr;
+    int ptab_slot = -1;
     if (ramp_mask) {
-        CK(e, cudaStreamSynchronize(e->stream));
+        { void *hp = nullptr; const int r = stage_acquire(e, (size_t)frames * (kMaxInputs + kFmRowFloats) * sizeof(float), &hp, &ptab_slot); if (r) return r; h_ptab = (float *)hp; }
         for (uint32_t f = 0; f < frames; ++f)
             for (uint32_t i = 0; i < e->n_inputs; ++i) if ((ramp_mask >> i) & 1u) {
                 e->ramps[i].tick();
-                e->h_ptab[(size_t)f * kMaxInputs + i] = e->ramps[i].current;
+                h_ptab[(size_t)f * kMaxInputs + i] = e->ramps[i].current;
             }
-        CK(e, cudaMemcpyAsync(e->d_ptab, e->h_ptab, (size_t)frames * kMaxInputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        e->stats.h2d_bytes += (uint64_t)frames * kMaxInputs * sizeof(float);
-        general = true;
     }
     if (device_midi) { e->uniform[e->midi_freq_input] = false; has_value_events = true; }               /* per-voice `frequency` value events */
     for (uint32_t i = 1; i < e->n_inputs; ++i) if (!e->uniform[i]) general = true;
     if (kind != OSCEN_B200_GRAPH_FM_VOICE) general = true;
+    /* FMVoice: which kernel renders this block (fm_select.hpp), then the ramp table it reads */
+    bool upload_ptab = ramp_mask != 0;
+    if (kind == OSCEN_B200_GRAPH_FM_VOICE && e->cfg.plan == OSCEN_B200_PLAN_FUSED) {
+        e->fm_variant = fm_select_variant(general, ramp_mask, e->uni, h_ptab, frames, e->fm_bounds);
+        if (e->fm_variant == FM_SEG_RAMP) {
+            float *rows = h_ptab + (size_t)frames * kMaxInputs;
+            fm_fill_rows(ramp_mask, e->uni, h_ptab, frames, rows);
+            CK(e, cudaMemcpyAsync(e->d_utab, rows, (size_t)frames * kFmRowFloats * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            e->stats.h2d_bytes += (uint64_t)frames * kFmRowFloats * sizeof(float);
+            upload_ptab = false;
+        }
+    }
+    if (upload_ptab) {
+        CK(e, cudaMemcpyAsync(e->d_ptab, h_ptab, (size_t)frames * kMaxInputs * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += (uint64_t)frames * kMaxInputs * sizeof(float);
+    }
+    if (ptab_slot >= 0) { const int r = stage_submit(e, ptab_slot); if (r) return r; }
+    if (ramp_mask) general = true;
 
     /* ---- per-block control + events to the device */
     e->h_ctl->frames = frames; e->h_ctl->n_events = n_ev; e->h_ctl->ramp_mask = ramp_mask; e->h_ctl->lcg_on = e->lcg_on ? 1u : 0u;
     if (n_ev) {
-        CK(e, cudaMemcpyAsync(e->d_events, e->h_events, (size_t)n_ev * sizeof(Event), cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(e->d_events, h_events, (size_t)n_ev * sizeof(Event), cudaMemcpyHostToDevice, e->stream));
         e->stats.h2d_bytes += (uint64_t)n_ev * sizeof(Event);
     }
+    if (ev_slot >= 0) { const int r = stage_submit(e, ev_slot); if (r) return r; }
     if (memcmp(&e->ctl_on_device, e->h_ctl, sizeof(BlockCtl)) != 0) {
         /* BlockCtl only travels when it changed (steady-state blocks have no events / ramps) */
         e->ctl_on_device = *e->h_ctl;

@@ -85,6 +85,7 @@ struct KernelArgs {
     float *inst_state;                   /* [n_inst] instance-level state (EPIANO tremolo phase) */
     float *mix_partial;                  /* [n_cta][512][channels] */
     const AssetTable *assets;            /* DSL graphs with `external` slots, else null */
+    const float *utab;                   /* [512][12] per-frame uniform rows of fm_voice_seg_kernel<RAMP> (kernel_fm_seg.cuh FmRow) */
     Uniform u;
 };
 

@@ -65,9 +65,11 @@ OSC_HD float fractf(float x) {
 #if defined(__CUDACC__)
 OSC_D float pin(float x) { asm volatile("" : "+f"(x)); return x; }
 OSC_D uint32_t pin(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+OSC_D double pin(double x) { asm volatile("" : "+d"(x)); return x; }
 #else   /* plain C++ (tests/host_kernel.py compiles these headers with g++): nothing to pin */
 inline float pin(float x) { return x; }
 inline uint32_t pin(uint32_t x) { return x; }
+inline double pin(double x) { return x; }
 #endif
 
 /* tanf only runs when a filter coefficient has to be recomputed (parameter changes): on the device

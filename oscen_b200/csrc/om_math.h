@@ -317,6 +317,60 @@ OM_HD float om_cosf_u(float y) {
     return neg ? -res : res;
 }
 
+/* sinf for callers that GUARANTEE |y| < 120 (top12 < 0x42f) — no range test, no branch: the reduction of om_sinf's middle
+   path, then BOTH of its polynomials evaluated in IEEE double (independent chains: 2 DMUL + 3 DFMA and 2 DMUL + 4 DFMA) and
+   the quadrant's one selected.  No per-lane selection of 64-bit coefficients (10 FSEL and the constant moves that go with
+   them in om_sinf_u).  Same operations on the selected path as om_sinf, so the same bits as glibc;
+   tests/csrc/check_om_math.cpp sweeps it against the box's libm (0 mismatches over every f32 with |y| < 120).
+   Where the constants live matters in a frame loop that evaluates it three times: the six MULTIPLIER constants sit in the
+   constant bank (a DFMA takes one operand from there for free; as immediates they cost two moves each per use), the three
+   ADDEND constants come in through `k`, which a kernel fills once and pins in registers (om_sin_regs_pinned). */
+struct OmSinRegs { double s2, c3, c1; };
+#if defined(__CUDACC__)
+static __device__ __constant__ double om_sin_mul_dev[6] = { OM_HPI_INV, OM_HPI, OM_S3, OM_S1, OM_C4, OM_C2 };
+#endif
+#if defined(__CUDA_ARCH__)
+#define OM_SIN_MUL(i) om_sin_mul_dev[i]
+#else
+static const double om_sin_mul_host[6] = { OM_HPI_INV, OM_HPI, OM_S3, OM_S1, OM_C4, OM_C2 };
+#define OM_SIN_MUL(i) om_sin_mul_host[i]
+#endif
+#if defined(__CUDACC__)
+static __device__ __constant__ double om_sin_add_dev[3] = { OM_S2, OM_C3, OM_C1 };
+#endif
+OM_HD OmSinRegs om_sin_regs() {
+    OmSinRegs k;
+#if defined(__CUDA_ARCH__)
+    k.s2 = om_sin_add_dev[0]; k.c3 = om_sin_add_dev[1]; k.c1 = om_sin_add_dev[2];    /* loaded, not immediates: ptxas keeps a load's result live */
+#else
+    k.s2 = OM_S2; k.c3 = OM_C3; k.c1 = OM_C1;
+#endif
+    return k;
+}
+OM_HD float om_sinf_rk(float y, const OmSinRegs &k) {
+    double x = (double)y;
+    const double r = x * OM_SIN_MUL(0);
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = OM_MADD(-(double)n, OM_SIN_MUL(1), x);
+    const double x2 = x * x;
+    /* sine polynomial (n even) */
+    const double x3 = x * x2;
+    const double s1 = OM_MADD(x2, OM_SIN_MUL(2), k.s2);
+    const double x5 = x3 * x2;
+    const double s = OM_MADD(x3, OM_SIN_MUL(3), x);
+    const double rs = OM_MADD(x5, s1, s);
+    /* cosine polynomial (n odd) */
+    const double x4 = x2 * x2;
+    const double c2 = OM_MADD(x2, OM_SIN_MUL(4), k.c3);
+    const double c1 = OM_MADD(x2, k.c1, OM_C0);
+    const double x6 = x4 * x2;
+    const double c = OM_MADD(x4, OM_SIN_MUL(5), c1);
+    const double rc = OM_MADD(x6, c2, c);
+    const float res = (float)((n & 1) ? rc : rs);
+    return (n & 2) ? -res : res;
+}
+OM_HD float om_sinf_r(float y) { return om_sinf_rk(y, om_sin_regs()); }
+
 OM_HD float om_asfloat(uint32_t u) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(u);
@@ -372,6 +426,29 @@ OM_HD float om_k_tanf(float x, float y, int iy) {
     t = om_asfloat(om_asuint(t) & 0xfffff000u);
     s = 1.0f + t * z;
     return t + a * (s + t * v);
+}
+
+/* om_k_tanf(x, 0, 1) for 2^-13 <= x < 0.6744 (0x39000000 <= bits < 0x3f2ca140, x > 0): the polynomial core without the
+   range branches — every TptFilter coefficient refresh below ~10.3 kHz at 48 kHz lands here.  Same operations in the
+   same order (y = 0 terms kept: `0 + z*(..+0)` is exact for these positive operands), so the same bits. */
+OM_HD bool om_tanf_mid_ok(float x) {
+    const uint32_t ix = om_asuint(x);
+    return ix >= 0x39000000u && ix < 0x3f2ca140u;
+}
+OM_HD float om_k_tanf_mid(float x) {
+    const float T0 = 3.3333334327e-01f, T1 = 1.3333334029e-01f, T2 = 5.3968254477e-02f,
+                T3 = 2.1869488060e-02f, T4 = 8.8632395491e-03f, T5 = 3.5920790397e-03f,
+                T6 = 1.4562094584e-03f, T7 = 5.8804126456e-04f, T8 = 2.4646313977e-04f,
+                T9 = 7.8179444245e-05f, T10 = 7.1407252108e-05f, T11 = -1.8558637748e-05f,
+                T12 = 2.5907305826e-05f;
+    const float z = x * x;
+    const float w = z * z;
+    float r = T1 + w * (T3 + w * (T5 + w * (T7 + w * (T9 + w * T11))));
+    const float v = z * (T2 + w * (T4 + w * (T6 + w * (T8 + w * (T10 + w * T12)))));
+    const float s = z * x;
+    r = 0.0f + z * (s * (r + v) + 0.0f);
+    r += T0 * s;
+    return x + r;
 }
 
 /* tan in double, rounded once (fallback for |x| >= 3*pi/4; within 1 ulp of a faithful libm) */

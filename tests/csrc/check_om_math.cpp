@@ -58,6 +58,9 @@ int main(int argc, char **argv) {
     report("cosf[|x|<120]", sweep([](float x) { return om_cosf(x); }, [](float x) { return cosf(x); }, 0, F120 - 1, stride, nt));
     report("sinf_u[all]", sweep([](float x) { return om_sinf_u(x); }, [](float x) { return sinf(x); }, 0, FINF - 1, stride, nt));
     report("cosf_u[all]", sweep([](float x) { return om_cosf_u(x); }, [](float x) { return cosf(x); }, 0, FINF - 1, stride, nt));
+    report("sinf_r[|x|<120] (both polynomials, no range test)", sweep([](float x) { return om_sinf_r(x); }, [](float x) { return sinf(x); }, 0, F120 - 1, stride, nt));
+    // k_tanf_mid: only positive x in [2^-13, 0.6744) — compare against the general routine on that range
+    report("tanf_mid[2^-13<=x<0.6744]", sweep([](float x) { return x > 0.0f ? om_k_tanf_mid(x) : om_tanf(x); }, [](float x) { return om_tanf(x); }, 0x39000000u, 0x3f2ca140u - 1u, stride, nt));
     report("sinf[120<=|x|<inf]", sweep([](float x) { return om_sinf(x); }, [](float x) { return sinf(x); }, F120, FINF - 1, stride, nt));
     report("cosf[120<=|x|<inf]", sweep([](float x) { return om_cosf(x); }, [](float x) { return cosf(x); }, F120, FINF - 1, stride, nt));
     const uint32_t F2 = 0x40000000u, F12 = 0x41400000u;

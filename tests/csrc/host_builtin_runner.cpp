@@ -4,8 +4,11 @@
  * tests/csrc/host_cuda/cuda_runtime.h): the dispatch restates engine.cu's launch_fused() / launch_clip().
  */
 #include "kernel_fm.cuh"
+#include "kernel_fm_seg.cuh"
+#include "fm_select.hpp"
 #include "kernel_others.cuh"
 #include "kernel_resample.cuh"
+#include <vector>
 
 namespace {
 using namespace oscen;
@@ -31,6 +34,15 @@ extern "C" void oscen_host_lcg_seed(float *state, uint32_t n, unsigned long long
     }
 }
 
+/* FMVoice: which kernel variant the last block ran, and which engine's bound state the next block uses */
+static int g_last_variant = -1, g_force_variant = -1;
+static uint32_t g_bound_slot = 0;
+extern "C" int oscen_host_last_fm_variant(void) { return g_last_variant; }
+extern "C" void oscen_host_set_fm_slot(uint32_t slot) { g_bound_slot = slot; }
+/* tests: -1 = the product's choice; FM_GENERAL = always the general kernel; FM_LEGACY = the round-1 fast kernel wherever it applies
+   (what OSCEN_B200_FM_KERNEL=general|legacy does in the engine) */
+extern "C" void oscen_host_force_fm_variant(int v) { g_force_variant = v; }
+
 extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t n_voices, uint32_t vpi, float sample_rate, float *state,
                                             float *pv, const oscen::Event *events, uint32_t n_events, const float *ptab, uint32_t ramp_mask,
                                             uint32_t frames, const float *stream_in, float *voice_out, float *inst_out, float *inst_state,
@@ -54,8 +66,27 @@ extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t
         adsr_derive(a.u.env[3], p[I_F_A], p[I_F_D], p[I_F_R], a.u.sr);
     }
     const uint32_t grid = (n_voices + kCta - 1) / kCta;
+    std::vector<float> rows;
     switch (kind) {
-    case 0: if (general) host_launch(grid, 1, kCta, [&]() { fm_voice_kernel<true>(a); }); else host_launch(grid, 1, kCta, [&]() { fm_voice_kernel<false>(a); }); break;
+    case 0: {
+        /* the product's own choice (fm_select.hpp): `general` = per-voice inputs / value events off `frequency`; ramps are judged there */
+        static FmBoundState bounds[64];                         /* per harness engine: fm_bound_slot */
+        g_last_variant = fm_select_variant(general != 0, ramp_mask, a.u.p, ptab, frames, bounds[g_bound_slot % 64]);
+        if (g_force_variant == FM_GENERAL) g_last_variant = FM_GENERAL;
+        else if (g_force_variant == FM_LEGACY && g_last_variant != FM_GENERAL) g_last_variant = ramp_mask ? FM_GENERAL : FM_LEGACY;
+        if (g_last_variant == FM_SEG_RAMP) {
+            rows.resize((size_t)frames * kFmRowFloats);
+            fm_fill_rows(ramp_mask, a.u.p, ptab, frames, rows.data());
+            a.utab = rows.data();
+        }
+        switch (g_last_variant) {
+        case FM_SEG: host_launch(grid, 1, kCta, [&]() { fm_voice_seg_kernel<false, false>(a); }); break;
+        case FM_SEG_FMOD: host_launch(grid, 1, kCta, [&]() { fm_voice_seg_kernel<false, true>(a); }); break;
+        case FM_SEG_RAMP: host_launch(grid, 1, kCta, [&]() { fm_voice_seg_kernel<true, true>(a); }); break;
+        case FM_LEGACY: host_launch(grid, 1, kCta, [&]() { fm_voice_kernel<false>(a); }); break;
+        default: host_launch(grid, 1, kCta, [&]() { fm_voice_kernel<true>(a); }); break;
+        }
+    } break;
     case 1: host_launch(grid, 1, kCta, [&]() { twin_peaks_kernel(a); }); break;
     case 2: host_launch(grid, 1, kCta, [&]() { sat_kernel<1>(a); }); break;
     case 3: host_launch(grid, 1, kCta, [&]() { sat_kernel<4>(a); }); break;

@@ -160,11 +160,13 @@ def test_host_executed_two_sample_players_through_a_filter_match_the_oracle_walk
 
 
 # ------------------------------------------------------------ the hand-written fused FMVoice kernel (the one bench.py times)
-def test_host_executed_hand_written_fm_kernel_matches_oracle_bank_both_instantiations():
-    """kernel_fm.cuh on the host, 136 voices = 17 instances of 8: (1) BASELINE config 2's steady state — per-voice
-    frequency, everything else uniform, gates only: the GENERAL=false instantiation (uniform values and ADSR step data
-    from the kernel arguments); (2) the events-and-ramps script of the GPU parity test: GENERAL=true.  Per-voice output
-    and instance fold bit-identical to the oracle; both instantiations agree with the kernel generated from the DSL text"""
+@pytest.mark.parametrize("force", [None, "legacy", "general"], ids=["product_choice", "legacy_kernel", "general_kernel"])
+def test_host_executed_hand_written_fm_kernel_matches_oracle_bank_both_instantiations(force):
+    """kernel_fm.cuh / kernel_fm_seg.cuh on the host, 136 voices = 17 instances of 8: (1) BASELINE config 2's steady state —
+    per-voice frequency, everything else uniform, gates only: the segmented kernel (product choice), the round-1
+    GENERAL=false kernel ("legacy"), or fm_voice_kernel<true>; (2) the events-and-ramps script of the GPU parity test: the
+    segmented kernel's ramp variant, or GENERAL=true.  Per-voice output and instance fold bit-identical to the oracle; the
+    kernel generated from the DSL text agrees"""
     from parity_util import lcg_ints
     n, vpi = 136, 8
     notes = 36 + lcg_ints(n, 1, 60)
@@ -186,15 +188,19 @@ def test_host_executed_hand_written_fm_kernel_matches_oracle_bank_both_instantia
         return np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out])
 
     ref, hand, gen = O.OracleBank(O.K_FM, n, vpi), HostFmEngine(n, vpi), HostEngine(text("voice_fm3.graph"), n, vpi)
+    hand.force_variant = force
     (vr, ir), (vh, ih), (vg, ig) = steady(ref), steady(hand), steady(gen)
     assert hand.last_general is False
+    assert hand.variants == [{None: "seg", "legacy": "legacy", "general": "general"}[force]] * 3
     assert np.abs(vr).max() > 0.05
     assert np.array_equal(vh, vr) and np.array_equal(ih, ir), float(np.abs(vh - vr).max())
     assert np.array_equal(vg, vr) and np.array_equal(ig, ir)
 
     ref, hand = O.OracleBank(O.K_FM, n, vpi), HostFmEngine(n, vpi)
+    hand.force_variant = force
     (vr, ir, mr), (vh, ih, mh) = [_fm_bank_script(b, n, blocks=3, frames=128) for b in (ref, hand)]
-    assert hand.last_general is True
+    # block 0: nothing moves; blocks 1-2: ramps on op3_level and filter_env_amount (block 2 also retunes voices: `frequency` events)
+    assert hand.variants == {None: ["seg", "seg_ramp", "seg_ramp"], "legacy": ["legacy", "general", "general"], "general": ["general"] * 3}[force]
     assert np.array_equal(vh, vr) and np.array_equal(ih, ir), float(np.abs(vh - vr).max())
     scale = np.abs(ir.astype(np.float64)).sum(axis=1)
     assert (np.abs(mh.astype(np.float64) - mr.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()

@@ -29,7 +29,7 @@ def results(tmp_path_factory):
 
 @pytest.mark.parametrize("name", ["expf[|x|<=104]", "sinf[|x|<120]", "cosf[|x|<120]",
                                   "sinf[120<=|x|<inf]", "cosf[120<=|x|<inf]", "tanhf[|x|<=12]", "tanhf_u[|x|<=32]",
-                                  "sinf_u[all]", "cosf_u[all]",
+                                  "sinf_u[all]", "cosf_u[all]", "sinf_r[|x|<120]",
                                   "expf[adsr"])
 def test_bit_exact_against_glibc(results, name):
     n, bad, _ = results[name]
@@ -39,3 +39,9 @@ def test_bit_exact_against_glibc(results, name):
 def test_tanf_within_tolerance(results):
     n, bad, max_ulp = results["tanf[|x|<=2]"]
     assert bad / n < 1e-5 and max_ulp <= 2
+
+
+def test_tanf_mid_range_core_equals_the_general_routine(results):
+    """om_k_tanf_mid (the branch-free core the segmented FM kernel inlines) is bit-identical to om_tanf on its whole range"""
+    n, bad, _ = results["tanf_mid[2^-13<=x<0.6744]"]
+    assert n > 400_000 and bad == 0, (n, bad)

@@ -65,6 +65,66 @@ def make_script(kind, seed):
     return n, vpi, script, x
 
 
+def make_script_fm_uniform(seed):
+    """FMVoice scripts that stay on the SEGMENTED kernel's ground (kernel_fm_seg.cuh): `frequency` per voice, every other
+    input uniform, uniform set_value between blocks, ramps (the eight inputs the ramp variant follows, sometimes an envelope
+    time / ratio / sustain: those must fall back to the general kernel), gates and `frequency` events at random frames,
+    short envelope times (stage boundaries inside blocks, different per lane), now and then levels large enough to break
+    the sine-argument bound (general kernel again)"""
+    rng = np.random.default_rng(990000 + seed)
+    vpi = 8
+    n = vpi * int(rng.choice([1, 2, 4, 5, 9, 12]))
+    ranges = dict(RANGES[O.K_FM])
+    ranges.update({4: (0.0, 0.004), 5: (0.0005, 0.01), 7: (0.0, 0.01), 11: (0.0, 0.004), 12: (0.0005, 0.02), 14: (0.0005, 0.01),
+                   16: (0.0, 0.003), 17: (0.0005, 0.02), 19: (0.0, 0.02), 23: (0.0, 0.004), 24: (0.0005, 0.02), 26: (0.0005, 0.02)})
+    seg_ramp_ids = [2, 3, 9, 10, 20, 21, 22, 27]
+    ids = [i for i in sorted(ranges) if i != 0]
+    script = []
+    ramped = set()
+    for blk in range(int(rng.integers(3, 7))):
+        frames = int(rng.choice([1, 31, 32, 33, 64, 100, 129, 256]))
+        calls = []
+        if blk == 0:
+            calls.append(("set_value", 0, rng.uniform(60, 1500, n).astype(np.float32)))
+            for i in rng.choice(ids, size=6, replace=False):
+                lo, hi = ranges[int(i)]
+                calls.append(("set_value", int(i), float(np.float32(rng.uniform(lo, hi)))))
+        for _ in range(int(rng.integers(0, 3))):
+            r = rng.random()
+            if r < 0.45:
+                i = int(rng.choice(seg_ramp_ids if rng.random() < 0.85 else ids)); lo, hi = ranges[i]
+                calls.append(("set_value_ramp", i, float(np.float32(rng.uniform(lo, hi))), int(rng.choice([1, 5, 40, 150, 400]))))
+                ramped.add(i)
+            elif r < 0.8:
+                i = int(rng.choice([j for j in ids if j not in ramped])); lo, hi = ranges[i]
+                big = i in (2, 9) and rng.random() < 0.1
+                calls.append(("set_value", i, float(np.float32(rng.uniform(15, 30) if big else rng.uniform(lo, hi)))))
+            else:
+                ev = [(int(v), int(rng.integers(0, frames)), 0, float(np.float32(rng.uniform(60, 1500)))) for v in rng.choice(n, size=min(n, 3), replace=False)]
+                calls.append(("push_events", ev))
+        if rng.random() < 0.85:
+            k = int(rng.choice([1, 5, n]))
+            ev = [(int(v), int(rng.integers(0, frames)), GATE, float(np.float32(rng.choice([0.0, 0.3, 0.9])))) for v in rng.choice(n, size=min(n, k), replace=False)]
+            calls.append(("push_events", ev))
+        script.append((frames, calls))
+    return n, vpi, script, None
+
+
+def run_fm_uniform(seed, tally):
+    n, vpi, script, x = make_script_fm_uniform(seed)
+    hb = HostBuiltinEngine(O.K_FM, n, vpi)
+    (vr, ir), (vh, ih) = play(O.OracleBank(O.K_FM, n, vpi), script, x), play(hb, script, x)
+    for v in hb.variants:
+        tally[("variant", v)] = tally.get(("variant", v), 0) + 1
+    if not np.isfinite(vr).all():
+        return "skip"
+    if np.array_equal(vr, vh) and np.array_equal(ir, ih):
+        return "ok"
+    print("MISMATCH fm-uniform seed", seed, "n", n, "voice diff", float(np.nanmax(np.abs(vr - vh))), "inst equal", np.array_equal(ir, ih), hb.variants, flush=True)
+    describe(script)
+    return "MISMATCH"
+
+
 def play(b, script, x):
     ys, insts, pos = [], [], 0
     for frames, calls in script:
@@ -96,6 +156,15 @@ def run(kind, seed):
 if __name__ == "__main__":
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
     tally, t0 = {}, time.time()
+    if "--fm-uniform" in sys.argv:
+        for seed in range(lo, hi):
+            try:
+                r = run_fm_uniform(seed, tally)
+            except Exception as ex:
+                r = "EXC"; print("EXC fm-uniform", seed, repr(ex)[:300], flush=True)
+            tally[("fm-uniform", r)] = tally.get(("fm-uniform", r), 0) + 1
+        print(sorted(tally.items()), "%.0fs" % (time.time() - t0), flush=True)
+        sys.exit(0)
     for seed in range(lo, hi):
         for kind in sorted(RANGES):
             try:

@@ -634,7 +634,9 @@ def run(out):
             gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
         except Exception:
             gpu_uuid = None
-        sampler = ClockSampler(local_rank, gpu_uuid, 0.002 if world == 1 else 0.010)
+        # 10 ms: NVML queries take a driver-wide lock; polled faster, a query now and then stalls a launch for milliseconds
+        # (seen at 2 ms: one timed step in ~100 took 10-18 ms)
+        sampler = ClockSampler(local_rank, gpu_uuid, 0.010)
     else:
         sampler = NoSampler()
     sampler.begin()

@@ -343,6 +343,7 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
     a.mix_partial = e->d_mix_partial;
     a.assets = e->d_assets;
     a.utab = e->d_utab;
+    { static const bool no_skew = []() { const char *x = getenv("OSCEN_B200_FM_SKEW"); return x && x[0] == '0'; }(); a.pad0 = no_skew ? 1u : 0u; }   /* A/B only */
     for (uint32_t i = 0; i < kMaxInputs; ++i) a.u.p[i] = e->uni[i];
     a.u.sr = e->cfg.sample_rate;
     if (e->cfg.graph_kind == OSCEN_B200_GRAPH_FM_VOICE) {

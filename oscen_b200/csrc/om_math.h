@@ -370,6 +370,44 @@ OM_HD float om_sinf_rk(float y, const OmSinRegs &k) {
     return (n & 2) ? -res : res;
 }
 OM_HD float om_sinf_r(float y) { return om_sinf_rk(y, om_sin_regs()); }
+/* three independent om_sinf_rk evaluations written step by step across the three arguments: the compiler keeps the source
+   order of independent instructions, so the three conversion / FP64 chains (each ~200 cycles deep) overlap instead of
+   queueing behind one another.  Same operations per argument as om_sinf_rk. */
+OM_HD void om_sinf_rk3(float y0, float y1, float y2, const OmSinRegs &k, float &o0, float &o1, float &o2) {
+    double x[3] = { (double)y0, (double)y1, (double)y2 };
+    int n[3];
+    double x2[3], rs[3], rc[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 3; ++i) { const double r = x[i] * OM_SIN_MUL(0); n[i] = ((int32_t)r + 0x800000) >> 24; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 3; ++i) { x[i] = OM_MADD(-(double)n[i], OM_SIN_MUL(1), x[i]); x2[i] = x[i] * x[i]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 3; ++i) {
+        const double x3 = x[i] * x2[i];
+        const double s1 = OM_MADD(x2[i], OM_SIN_MUL(2), k.s2);
+        const double x5 = x3 * x2[i];
+        const double s = OM_MADD(x3, OM_SIN_MUL(3), x[i]);
+        rs[i] = OM_MADD(x5, s1, s);
+        const double x4 = x2[i] * x2[i];
+        const double c2 = OM_MADD(x2[i], OM_SIN_MUL(4), k.c3);
+        const double c1 = OM_MADD(x2[i], k.c1, OM_C0);
+        const double x6 = x4 * x2[i];
+        const double c = OM_MADD(x4, OM_SIN_MUL(5), c1);
+        rc[i] = OM_MADD(x6, c2, c);
+    }
+    float res[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 3; ++i) { const float t = (float)((n[i] & 1) ? rc[i] : rs[i]); res[i] = (n[i] & 2) ? -t : t; }
+    o0 = res[0]; o1 = res[1]; o2 = res[2];
+}
 
 OM_HD float om_asfloat(uint32_t u) {
 #if defined(__CUDA_ARCH__)

@@ -199,8 +199,8 @@ struct oscen_b200_engine {
     const float *captured_in = nullptr;      /* graph-input pointer / LCG mode baked into the captured CUDA graphs */
     bool captured_lcg = false;
     std::vector<float *> d_streams;
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   /* [0] no value events, [1] with */
-    uint64_t graph_kernels[2] = {0, 0};
+    cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};   /* [0] no value events, [1] with, [2] plain block: no event at all, no ramp */
+    uint64_t graph_kernels[3] = {0, 0, 0};
 
     /* multi-GPU */
     void *comm = nullptr;
@@ -355,8 +355,7 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
     }
 }
 
-constexpr size_t kSatDyn = (kTileF * kCta + 2 * 48 * kCta) * sizeof(float);
-constexpr size_t kEpDyn = (kTileF * kCta + kTileF * kTileW + kTileF * kCta * 2) * sizeof(float);
+constexpr size_t kEpDyn = kEpDynFloats * sizeof(float);
 
 /* the cross-rate clipper family: one instantiation per (policy, log2 factor) */
 template <int P, int L>
@@ -402,9 +401,9 @@ int launch_fused(oscen_b200_engine *e, bool general) {
         e->last_kernel = fm_variant_name(e->fm_variant);
         break;
     case OSCEN_B200_GRAPH_TWIN_PEAKS: twin_peaks_kernel<<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "twin_peaks_kernel"; break;
-    case OSCEN_B200_GRAPH_SAT_1X: sat_kernel<1><<<grid, kCta, kSatDyn, e->stream>>>(a); e->last_kernel = "sat_kernel<1>"; break;
-    case OSCEN_B200_GRAPH_SAT_4X: sat_kernel<4><<<grid, kCta, kSatDyn, e->stream>>>(a); e->last_kernel = "sat_kernel<4>"; break;
-    case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kCta, kEpDyn, e->stream>>>(a); e->last_kernel = "epiano_kernel"; break;
+    case OSCEN_B200_GRAPH_SAT_1X: sat_kernel<1><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "sat_kernel<1>"; break;
+    case OSCEN_B200_GRAPH_SAT_4X: sat_kernel<4><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "sat_kernel<4>"; break;
+    case OSCEN_B200_GRAPH_EPIANO: epiano_kernel<<<grid, kEpThreads, kEpDyn, e->stream>>>(a); e->last_kernel = "epiano_kernel"; break;
     case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "synth_kernel<false>"; break;
     case OSCEN_B200_GRAPH_SYNTH_ADSR: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "synth_kernel<true>"; break;
     case OSCEN_B200_GRAPH_CUSTOM: {
@@ -427,7 +426,10 @@ void launch_ew(oscen_b200_engine *e, const NodeArgs &n, bool vec) {
     e->stats.kernel_launches++;
 }
 
-int launch_plan(oscen_b200_engine *e, bool value_events) {
+/* A/B and tests: OSCEN_B200_NODE_PLAIN=0 keeps the generic node kernels on event-free blocks too */
+static const bool g_no_plain_nodes = []() { const char *x = getenv("OSCEN_B200_NODE_PLAIN"); return x && x[0] == '0'; }();
+
+int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
     const plan::Graph &g = e->graph;
     const plan::Plan &p = e->plan;
     float **S = e->d_streams.data();
@@ -469,9 +471,19 @@ int launch_plan(oscen_b200_engine *e, bool value_events) {
         for (uint32_t k = 0; k < cnt; ++k) a4.n[k] = args_of(l.nodes[k]);
         const dim3 g2(grid, cnt);
         switch (l.type) {
-        case plan::NodeType::Adsr: adsr_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
-        case plan::NodeType::FmOperator: fmop_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
-        case plan::NodeType::Tpt: tpt_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
+        case plan::NodeType::Adsr:
+            if (plain) adsr_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); else adsr_node_kernel<<<g2, kCta, 0, e->stream>>>(a4);
+            e->stats.kernel_launches++; break;
+        case plan::NodeType::FmOperator:
+            if (plain) fmop_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); else fmop_node_kernel<<<g2, kCta, 0, e->stream>>>(a4);
+            e->stats.kernel_launches++; break;
+        case plan::NodeType::Tpt: {
+            bool zero_fmod = true;                                      /* every filter of the wave: no f_mod stream, f_mod == 0 */
+            for (uint32_t k = 0; k < cnt; ++k) zero_fmod = zero_fmod && a4.n[k].in2 == nullptr && a4.n[k].pid[2] == kNoInput && a4.n[k].cst[2] == 0.0f;
+            if (plain && zero_fmod) tpt_node_plain_kernel<true><<<g2, kCta, 0, e->stream>>>(a4);
+            else if (plain) tpt_node_plain_kernel<false><<<g2, kCta, 0, e->stream>>>(a4);
+            else tpt_node_kernel<<<g2, kCta, 0, e->stream>>>(a4);
+            e->stats.kernel_launches++; } break;
         case plan::NodeType::PolyBlepSine: polyblep_node_kernel<WAVE_SINE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::PolyBlepSaw: polyblep_node_kernel<WAVE_SAW><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::PolyBlepSquare: polyblep_node_kernel<WAVE_SQUARE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
@@ -569,8 +581,7 @@ int oscen_b200_kind_info(uint32_t kind, float sample_rate, oscen_b200_kind_table
         memset(info, 0, sizeof *info);
         info->n_inputs = kind < 7 ? kNInputs[kind] : 0u; info->n_state = n_state;
         info->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2u : 1u;
-        info->dyn_smem_bytes = (kind == OSCEN_B200_GRAPH_SAT_1X || kind == OSCEN_B200_GRAPH_SAT_4X) ? (uint32_t)kSatDyn
-                               : kind == OSCEN_B200_GRAPH_EPIANO ? (uint32_t)kEpDyn
+        info->dyn_smem_bytes = kind == OSCEN_B200_GRAPH_EPIANO ? (uint32_t)kEpDyn
                                : is_clip(kind) ? (uint32_t)clip_dyn_bytes(clip_policy(kind), clip_log2f(kind)) : 0u;
         info->has_stream_in = has_stream_in(kind) ? 1u : 0u;
     }
@@ -726,8 +737,6 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
             for (auto &p : e->d_streams) CK(e, cudaMalloc(&p, (size_t)kMaxBlock * n * sizeof(float)));
             e->final_stream = e->d_streams[pp.first_stream[pg.output.node] + pg.output.port];
         }
-        CK(e, cudaFuncSetAttribute(sat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
-        CK(e, cudaFuncSetAttribute(sat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSatDyn));
         CK(e, cudaFuncSetAttribute(epiano_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEpDyn));
         if (is_clip(kind)) { KernelArgs none{}; launch_clip(e, none, 0, true); CK(e, cudaGetLastError()); }
         /* new() + init(sr): default inputs, initial node state */
@@ -1231,7 +1240,8 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         rc = launch_mix_reduce(e, frames); if (rc) return rc;
     } else {
         /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
-        const int gi = has_value_events ? 1 : 0;
+        const bool plain = n_ev == 0 && ramp_mask == 0 && !device_midi && !g_no_plain_nodes;
+        const int gi = plain ? 2 : (has_value_events ? 1 : 0);
         if (e->captured_in != e->stream_in_ptr || e->captured_lcg != e->lcg_on) {
             for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
             e->captured_in = e->stream_in_ptr; e->captured_lcg = e->lcg_on;
@@ -1240,7 +1250,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             cudaGraph_t g = nullptr;
             CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t before = e->stats.kernel_launches;
-            rc = launch_plan(e, has_value_events);
+            rc = launch_plan(e, has_value_events, plain);
             if (!rc) rc = launch_mix_reduce(e, frames);
             cudaError_t s = cudaStreamEndCapture(e->stream, &g);
             e->graph_kernels[gi] = e->stats.kernel_launches - before;

@@ -15,6 +15,7 @@
 #pragma once
 #include "kernels_common.cuh"
 #include "kernel_fm.cuh"
+#include "kernel_fm_seg.cuh"
 #include "kernel_others.cuh"
 
 namespace oscen {
@@ -346,6 +347,169 @@ __global__ void __launch_bounds__(kCta) sample_player_node_kernel(const __grid_c
     if (playhead >= len) playhead = 0u;
     for (uint32_t f = 0; f < frames; ++f) __stcs(a.out0 + (size_t)f * n + v, sample_player_process(playhead, buf, len));
     a.state[(size_t)a.state_base * n + v] = __uint_as_float(playhead);
+}
+
+/* =====================================================================================================================
+ * PLAIN variants: the block carries no event of any kind and no ramp (the host knows both before it launches, and a block
+ * of a held chord is exactly that), so every value input is a constant of the block and the frame loop needs no event
+ * cursor, no ramp test and no re-derivation.  The bodies are the lean forms of kernel_fm_seg.cuh (bounded-argument sine
+ * behind one range test, x - trunc(x) phase wrap, warp-uniform filter refresh, per-warp envelope segments); stream
+ * addressing is 32-bit (n_voices * 512 < 2^32 is checked at create).  Same operations per frame as the generic kernels
+ * above, so the same bits (tests/test_dsl_gpu.py node-plan cases run both).
+ * Stream inputs are register-prefetched two tiles deep (tile A is computed while tile B's loads are in flight), with the
+ * two tiles in alternating roles instead of a copy.
+ * ===================================================================================================================== */
+#define OSC_PLAIN_PROLOGUE(NP)                                                            \
+    const NodeArgs &a = args.n[blockIdx.y];                                               \
+    const uint32_t n = a.n_voices;                                                        \
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;                             \
+    if (v >= n) return;                                                                   \
+    const uint32_t frames = a.ctl->frames;                                                \
+    NodeParams<NP> prm; prm.load(a, v);
+/* tile of kPF frames of one stream into registers (zeros past the block) */
+#define OSC_PLAIN_LOAD(A, PA, F0)                                                                       \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                              \
+        const uint32_t f_ = (F0) + k;                                                                   \
+        A[k] = ((PA) != nullptr && f_ < frames) ? __ldcs((PA) + (f_ * n + v)) : 0.0f;                   \
+    }
+
+/* sinf behind ONE range test: the bounded-argument form (both polynomials, no coefficient selects) for |y| < 120, the
+   general routine (a call) beyond */
+OSC_D float om_sinf_uk(float y, const OmSinRegs &k) {
+    const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
+    if (top >= 0x42f) return om_sinf_slow(y);
+    return om_sinf_rk(y, k);
+}
+OSC_D float fmop_process_k(FmOpState &s, float phase_mod, float feedback, float envelope, float level, const OmSinRegs &sk) {
+    const float feedback_mod = s.prev * feedback;
+    const float total_phase_mod = phase_mod + feedback_mod;
+    const float phase_rad = (s.phase + total_phase_mod) * kTau;
+    const float out = om_sinf_uk(phase_rad, sk) * envelope * level;
+    s.prev = out;
+    const float ph = s.phase + s.inc;
+    s.phase = ph - truncf(ph);
+    return out;
+}
+
+/* ---- FmOperator, plain block */
+__global__ void __launch_bounds__(kCta) fmop_node_plain_kernel(const __grid_constant__ NodeArgs4 args) {
+    OSC_PLAIN_PROLOGUE(6)
+    const bool pm_stream = a.in0 != nullptr, en_stream = a.in1 != nullptr;
+    FmOpState s;
+    s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
+    s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
+    const OmSinRegs sk = om_sin_regs();
+    const float fb = prm.P[2], lvl = prm.P[3], pm_c = prm.P[4], en_c = prm.P[5];
+    float pmA[kPF], enA[kPF], pmB[kPF], enB[kPF];
+#define OSC_FMOP_TILE(PM, EN, F0)                                                                       \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                              \
+        const uint32_t f = (F0) + k;                                                                    \
+        if (f < frames) __stcs(a.out0 + (f * n + v), fmop_process_k(s, pm_stream ? PM[k] : pm_c, fb, en_stream ? EN[k] : en_c, lvl, sk)); \
+    }
+    OSC_PLAIN_LOAD(pmA, a.in0, 0u) OSC_PLAIN_LOAD(enA, a.in1, 0u)
+    for (uint32_t f0 = 0; f0 < frames; f0 += 2u * kPF) {
+        OSC_PLAIN_LOAD(pmB, a.in0, f0 + kPF) OSC_PLAIN_LOAD(enB, a.in1, f0 + kPF)
+        OSC_FMOP_TILE(pmA, enA, f0)
+        OSC_PLAIN_LOAD(pmA, a.in0, f0 + 2u * kPF) OSC_PLAIN_LOAD(enA, a.in1, f0 + 2u * kPF)
+        OSC_FMOP_TILE(pmB, enB, f0 + kPF)
+    }
+#undef OSC_FMOP_TILE
+    a.state[(size_t)(a.state_base + 0) * n + v] = s.phase; a.state[(size_t)(a.state_base + 1) * n + v] = s.prev;
+}
+
+/* ---- TptFilter, plain block.  ZERO_FMOD: no f_mod stream and the f_mod value is 0 — then the cutoff path is
+   clamp -> refresh test -> core, with the refresh warp-uniform (tpt_process_mod); otherwise the general tpt_process */
+template <bool ZERO_FMOD>
+__global__ void __launch_bounds__(kCta) tpt_node_plain_kernel(const __grid_constant__ NodeArgs4 args) {
+    const NodeArgs &a = args.n[blockIdx.y];
+    const uint32_t n = a.n_voices;
+    const uint32_t vt = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = vt < n;
+    const uint32_t v = active ? vt : 0u;                     /* the whole warp stays for the votes of tpt_process_mod */
+    const uint32_t frames = a.ctl->frames;
+    NodeParams<4> prm; prm.load(a, v);
+    TptState s; tpt_load(s, a.state, a.state_base, n, v);
+    const bool in_stream = a.in0 != nullptr, cut_stream = a.in1 != nullptr, fm_stream = a.in2 != nullptr;
+    const float sr = a.sr;
+    const float max_cutoff = fminf(sr * 0.5f - FLT_EPSILON, 20000.0f), period = 0.5f / sr, two_sr = 2.0f * sr;
+    const float qc = clampf(prm.P[0], 0.1f, 10.0f), inv_q = 1.0f / qc;
+    const float cut_c = prm.P[1], fm_c = prm.P[2], in_c = prm.P[3];
+    float xA[kPF], cA[kPF], xB[kPF], cB[kPF];
+    [[maybe_unused]] float mA[kPF], mB[kPF];
+#define OSC_TPT_TILE(X, C, M, F0)                                                                       \
+    _Pragma("unroll") for (uint32_t k = 0; k < kPF; ++k) {                                              \
+        const uint32_t f = (F0) + k;                                                                    \
+        if (f < frames) {                                                                               \
+            const float x_ = in_stream ? X[k] : in_c, c_ = cut_stream ? C[k] : cut_c;                   \
+            float y_;                                                                                   \
+            if (ZERO_FMOD) y_ = tpt_process_mod(s, x_, c_, qc, inv_q, max_cutoff, sr, two_sr, period);  \
+            else y_ = tpt_process(s, x_, c_, prm.P[0], fm_stream ? M[k] : fm_c, sr);                    \
+            if (active) __stcs(a.out0 + (f * n + v), y_);                                               \
+        }                                                                                               \
+    }
+    const float *in2 = ZERO_FMOD ? nullptr : a.in2;
+    OSC_PLAIN_LOAD(xA, a.in0, 0u) OSC_PLAIN_LOAD(cA, a.in1, 0u)
+    if (!ZERO_FMOD) { OSC_PLAIN_LOAD(mA, in2, 0u) }
+    for (uint32_t f0 = 0; f0 < frames; f0 += 2u * kPF) {
+        OSC_PLAIN_LOAD(xB, a.in0, f0 + kPF) OSC_PLAIN_LOAD(cB, a.in1, f0 + kPF)
+        if (!ZERO_FMOD) { OSC_PLAIN_LOAD(mB, in2, f0 + kPF) }
+        OSC_TPT_TILE(xA, cA, mA, f0)
+        OSC_PLAIN_LOAD(xA, a.in0, f0 + 2u * kPF) OSC_PLAIN_LOAD(cA, a.in1, f0 + 2u * kPF)
+        if (!ZERO_FMOD) { OSC_PLAIN_LOAD(mA, in2, f0 + 2u * kPF) }
+        OSC_TPT_TILE(xB, cB, mB, f0 + kPF)
+    }
+#undef OSC_TPT_TILE
+    if (active) tpt_store(s, a.state, a.state_base, n, v);
+}
+
+/* ---- AdsrEnvelope, plain block: no gate can arrive, so a stage only ends by running out.  Per warp: L = frames until the
+   first lane's timed stage completes (one REDUX.MIN); L plain frames — Attack / Decay lanes step their one-pole, Sustain /
+   Idle lanes hold a constant, Release lanes keep their per-frame division behind a warp-uniform test — then ONE general
+   frame (adsr_process_t) takes the stage transition.  A warp whose voices all sit in Sustain / Idle only stores. */
+__global__ void __launch_bounds__(kCta) adsr_node_plain_kernel(const __grid_constant__ NodeArgs4 args) {
+    const NodeArgs &a = args.n[blockIdx.y];
+    const uint32_t n = a.n_voices;
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = v < n;
+    const uint32_t vs = active ? v : 0u;                     /* the whole warp stays for the reductions */
+    const uint32_t frames = a.ctl->frames;
+    NodeParams<4> prm; prm.load(a, vs);
+    AdsrState s; adsr_load(s, a.state, a.state_base, n, vs);
+    AdsrDerived d; adsr_derive_r(d, prm.P[0], prm.P[1], prm.P[3], a.sr);
+    adsr_begin_block(s, d, false);
+    AdsrHot h; adsr_refresh<false>(s, h, prm.P[2], d);
+    const float sus = prm.P[2];
+    const uint32_t kBig = 0x7FFFFFFFu;
+    uint32_t idx = vs;                                       /* f * n + v */
+    uint32_t f = 0;
+    while (f < frames) {
+        const bool timed = (s.stage == ST_ATTACK) | (s.stage == ST_DECAY) | (s.stage == ST_RELEASE);
+        uint32_t np = timed ? (s.rem >= 2u ? s.rem - 1u : 0u) : kBig;
+        if (f == 0u) np = 0u;                                /* the block's first frame commits the caches (adsr_refresh<true>) */
+        const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), frames - f);
+        if (L > 0u) {
+            const bool ad = (s.stage == ST_ATTACK) | (s.stage == ST_DECAY), rl = s.stage == ST_RELEASE;
+            const float tg = s.stage == ST_ATTACK ? 1.0f : h.sus, kk = s.stage == ST_ATTACK ? d.a_k : d.d_k;
+            if (!__any_sync(0xffffffffu, rl)) {
+                if (!__any_sync(0xffffffffu, ad)) {
+                    const float y = s.level;
+                    for (uint32_t i = 0; i < L; ++i) { if (active) __stcs(a.out0 + idx, y); idx += n; }
+                } else {
+                    for (uint32_t i = 0; i < L; ++i) { const float y = adsr_ad(s, ad, tg, kk); if (active) __stcs(a.out0 + idx, y); idx += n; }
+                    if (ad) s.rem -= L;
+                }
+            } else {
+                for (uint32_t i = 0; i < L; ++i) { const float y = adsr_plain_rel(s, ad, rl, tg, kk); if (active) __stcs(a.out0 + idx, y); idx += n; }
+            }
+            f += L;
+            continue;
+        }
+        if (f == 0u) adsr_refresh<true>(s, h, sus, d);
+        const float y = adsr_process_t<false>(s, h, sus, d);
+        if (active) __stcs(a.out0 + idx, y);
+        idx += n; f += 1u;
+    }
+    if (active) adsr_store(s, a.state, a.state_base, n, v);
 }
 
 /* ---- stateless nodes */

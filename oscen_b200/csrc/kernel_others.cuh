@@ -25,8 +25,10 @@ struct SmallParams {
         }
     }
     OSC_D void value_event(const KernelArgs &a, const Event &e, uint32_t v) {
+        /* select form: written as `if (id == i) P[i] = x` the compiler turns the unrolled chain into ONE store with a run-time
+           index, and P moves from registers to local memory for the whole kernel (LDL in every frame) */
 #pragma unroll
-        for (uint32_t i = 0; i < NP; ++i) if (e.input_id == i) P[i] = e.scalar;
+        for (uint32_t i = 0; i < NP; ++i) P[i] = (e.input_id == i) ? e.scalar : P[i];
         if (e.input_id < NP) a.pv[(size_t)e.input_id * a.n_voices + v] = e.scalar;
     }
 };
@@ -90,13 +92,51 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
 
 /* ============================================================== SatGraph_{1x,4x} === */
 /* examples/oversampled-saturator/src/main.rs:64-80; multirate body codegen/emit_frame.rs:114-176 */
+
+/* Halfband2xDownStage::step (sinc_fir.rs:113-138) with the 24-sample history in REGISTERS.  A step pushes xs[0] = x[2m]
+   and xs[1] = x[2m + 1] and reads x[2m - d] for the even delays d = 0, 2, .., 22 and for d = 11 only (every other odd tap
+   of a halfband filter is zero), so the history splits into two polyphase shift registers: a[k] = x[2m - 2k] (the FIRST
+   sample of the step k steps ago, k = 0..11) and b[k] = x[2m + 1 - 2k] (its second sample, k = 0..6; b[6] is the centre
+   tap d = 11, b[0] the sample this step only stores).  Shifting by one entry per step is free once the frame loop is
+   unrolled (the compiler renames registers inside the unrolled body and moves 19 values per ring at the back edge); the
+   shared-memory ring this replaces cost 13 LDS + 4 STS per step and capped the kernel at 5 CTAs per SM
+   (profiles/r02_ncu_sat4x_smem_rings.md).  Same taps, same order of additions as hb_down_step: the same bits. */
+struct HbDownRegs { float a[12]; float b[7]; };
+OSC_D float hb_down_step_r(HbDownRegs &r, float x0, float x1) {
+#pragma unroll
+    for (int i = 11; i > 0; --i) r.a[i] = r.a[i - 1];
+    r.a[0] = x0;
+#pragma unroll
+    for (int i = 6; i > 0; --i) r.b[i] = r.b[i - 1];
+    r.b[0] = x1;
+    float acc = r.b[6] * kHbCenter;                          /* d = 11 */
+    acc = acc + (r.a[0] + r.a[11]) * kHb0;                   /* d = 0, 22 */
+    acc = acc + (r.a[1] + r.a[10]) * kHb1;
+    acc = acc + (r.a[2] + r.a[9]) * kHb2;
+    acc = acc + (r.a[3] + r.a[8]) * kHb3;
+    acc = acc + (r.a[4] + r.a[7]) * kHb4;
+    acc = acc + (r.a[5] + r.a[6]) * kHb5;                    /* d = 10, 12 */
+    return acc;
+}
+/* the stage's 24 state rows are chronological (row 23 = newest = x[2m + 1], row 22 - d = x[2m - d]).  The rows of the odd
+   delays 13 .. 21 are never read by a step (now or later: samples only get older) and are not maintained. */
+OSC_D void hb_down_load(HbDownRegs &r, const float *state, uint32_t first, uint32_t n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r.a[k] = state[(size_t)(first + 22u - 2u * k) * n + v];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) r.b[k] = state[(size_t)(first + 23u - 2u * k) * n + v];
+}
+OSC_D void hb_down_store(const HbDownRegs &r, float *state, uint32_t first, uint32_t n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) state[(size_t)(first + 22u - 2u * k) * n + v] = r.a[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) state[(size_t)(first + 23u - 2u * k) * n + v] = r.b[k];
+}
+
 template <int FACTOR>
 __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ float tile[kTileF * kTileW];
-    extern __shared__ float dyn[];                         /* isum [32][kCta] | h1 [48][kCta] | h2 [48][kCta] */
-    float *isum = dyn;
-    float *h1 = dyn + kTileF * kCta + threadIdx.x;
-    float *h2 = h1 + 48 * kCta;
+    __shared__ float isum[kTileF * kCta];
     const uint32_t n = a.n_voices;
     const uint32_t v = blockIdx.x * kCta + threadIdx.x;
     const bool active = v < n;
@@ -107,57 +147,49 @@ __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ Kerne
 
     SmallParams<2> prm; prm.load(a, vs);
     float phase = a.state[(size_t)SAT_PHASE * n + vs];
-    uint32_t head1 = 23u, head2 = 23u;                     /* chronological order, newest last */
-    if (FACTOR == 4) {
-        for (uint32_t i = 0; i < 24; ++i) {
-            const float t1 = a.state[(size_t)(SAT_H1 + i) * n + vs], t2 = a.state[(size_t)(SAT_H2 + i) * n + vs];
-            h1[i * kCta] = t1; h1[(i + 24) * kCta] = t1;
-            h2[i * kCta] = t2; h2[(i + 24) * kCta] = t2;
-        }
-    }
+    HbDownRegs r1, r2;                                     /* SincDownFir<4>: stage 0 (4x -> 2x), stage 1 (2x -> 1x) */
+    if (FACTOR == 4) { hb_down_load(r1, a.state, SAT_H1, n, vs); hb_down_load(r2, a.state, SAT_H2, n, vs); }
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
+    const bool keepv = active && a.voice_out != nullptr;
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
+        /* Inactive lanes of the last CTA render voice 0 again (no events, no stores): a frame body that updates the
+           register histories under `if (active)` makes every history value a two-way merge at the end of the frame, which
+           pins each shift to a real move; unconditional, the unrolled body renames them away. */
+#pragma unroll 4
         for (uint32_t ff = 0; ff < fe; ++ff) {
             const uint32_t f = f0 + ff;
-            float y = 0.0f;
-            if (active) {
-                prm.ramps(a, ramp_mask, f);
-                if (ec.due(f)) {
-                    const uint32_t j = ec.end_of_frame(f);
-                    for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
-                    ec.advance(j);
-                }
-                if (FACTOR == 1) {
-                    const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
-                    y = hardclip_process(o);
-                } else {
-                    float buf[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
-                        buf[i] = hardclip_process(o);
-                    }
-                    /* SincDownFir<4>::downsample: stage 0 twice, stage 1 once (sinc_fir.rs:233-249) */
-                    const float s0 = hb_down_step(h1, kCta, head1, buf[0], buf[1]);
-                    const float s1 = hb_down_step(h1, kCta, head1, buf[2], buf[3]);
-                    y = hb_down_step(h2, kCta, head2, s0, s1);
-                }
-                if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
+            float y;
+            prm.ramps(a, ramp_mask, f);
+            if (ec.due(f)) {
+                const uint32_t j = ec.end_of_frame(f);
+                for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
+                ec.advance(j);
             }
-            tile[ff * kTileW + col] = y;
+            if (FACTOR == 1) {
+                const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
+                y = hardclip_process(o);
+            } else {
+                float buf[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
+                    buf[i] = hardclip_process(o);
+                }
+                /* SincDownFir<4>::downsample: stage 0 twice, stage 1 once (sinc_fir.rs:233-249) */
+                const float s0 = hb_down_step_r(r1, buf[0], buf[1]);
+                const float s1 = hb_down_step_r(r1, buf[2], buf[3]);
+                y = hb_down_step_r(r2, s0, s1);
+            }
+            if (keepv) a.voice_out[f * n + v] = y;             /* n_voices * 512 < 2^32 (checked at create) */
+            tile[ff * kTileW + col] = active ? y : 0.0f;
         }
         tile_flush_mono(a, tile, isum, f0, fe);
     }
     if (active) {
         a.state[(size_t)SAT_PHASE * n + v] = phase;
-        if (FACTOR == 4) {
-            for (uint32_t i = 0; i < 24; ++i) {            /* store oldest -> newest */
-                a.state[(size_t)(SAT_H1 + i) * n + v] = h1[((head1 + 1u + i) % 24u) * kCta];
-                a.state[(size_t)(SAT_H2 + i) * n + v] = h2[((head2 + 1u + i) % 24u) * kCta];
-            }
-        }
+        if (FACTOR == 4) { hb_down_store(r1, a.state, SAT_H1, n, v); hb_down_store(r2, a.state, SAT_H2, n, v); }
     }
 }
 
@@ -239,65 +271,100 @@ __constant__ float kEpVel127[32] = {
     0.0f, 0.0f, 0.0f, 0.0f };
 
 #define EPS(field, i) S[(size_t)((field) + (i)) * n_stride]
-/* AmplitudeSource::on_gate for the harmonics [h0, h0+8) of one voice (registers) */
-OSC_D void ep_gate_chunk(float *S, size_t n_stride, uint32_t h0, float scalar, const float *P, float (&cur)[8], float (&ore)[8],
-                         float (&oim)[8], bool &released, uint32_t &step) {
-    if (scalar > 0.0f) {
-        const float velocity = scalar;
-        const float note = 60.0f;                                   /* note_pitch is never updated */
-        const float base_decay_rate = (100.0f - P[3]) / 40000.0f;
-        const float harmonic_scaling = 1.0f - ((100.0f - P[4]) / 200000.0f);
-        const float scaling_multiplier = (48.0f - note) / 12.0f;
-        const float key_scaling_factor = scaling_multiplier * (P[5] * 0.02f);
-        const float adjusted = (key_scaling_factor > 0.0f)
-            ? 1.0f - (base_decay_rate / (1.0f + key_scaling_factor))
-            : 1.0f - (base_decay_rate * (1.0f - key_scaling_factor));
-        float scaling = 1.0f;                                       /* scaling *= harmonic_scaling, i times */
-        for (uint32_t i = 0; i < h0; ++i) scaling *= harmonic_scaling;
-        const float rv = 0.999f - ((100.0f - P[6]) / 1000.0f);
-        float bs = -0.2f + (0.8f * (P[1] * 0.01f));
-        bs += velocity * P[2] * 0.01f * 0.5f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            EPS(EP_DEC, h0 + i) = adjusted * scaling; scaling *= harmonic_scaling;
-            EPS(EP_REL, h0 + i) = rv;
-            float amp = (kEpVel127[h0 + i] * velocity) + (kEpVel0[h0 + i] * (1.0f - velocity));
-            amp *= 1.0f + bs * (float)(h0 + i);
-            cur[i] = amp;
-            ore[i] = 1.0f; oim[i] = 0.0f;                           /* OscillatorBank::on_gate */
+/* The two rare per-voice transitions run out of line ON THE STATE ROWS IN HBM (the caller reloads the registers they
+   replace): inlined into the frame loop, their bodies (a 32-step product chain, eight double-precision cos / sin) cost the
+   loop more than a hundred registers.
+   AmplitudeSource::trigger_note + OscillatorBank::on_gate for the harmonics [h0, h0 + 8) of one voice, velocity > 0:
+   writes decay, release, current_value and the unit oscillators (electric_piano_voice.rs:112-123, 230-297). */
+static __device__ __noinline__ void ep_note_on_rows(float *S, size_t n_stride, uint32_t h0, float velocity, float brightness,
+                                                    float velocity_scaling, float decay_rate, float harmonic_decay, float key_scaling,
+                                                    float release_rate) {
+    const float note = 60.0f;                                   /* note_pitch is never updated */
+    const float base_decay_rate = (100.0f - decay_rate) / 40000.0f;
+    const float harmonic_scaling = 1.0f - ((100.0f - harmonic_decay) / 200000.0f);
+    const float scaling_multiplier = (48.0f - note) / 12.0f;
+    const float key_scaling_factor = scaling_multiplier * (key_scaling * 0.02f);
+    const float adjusted = (key_scaling_factor > 0.0f)
+        ? 1.0f - (base_decay_rate / (1.0f + key_scaling_factor))
+        : 1.0f - (base_decay_rate * (1.0f - key_scaling_factor));
+    float scaling = 1.0f;                                       /* scaling *= harmonic_scaling, i times */
+    for (uint32_t i = 0; i < h0; ++i) scaling *= harmonic_scaling;
+    const float rv = 0.999f - ((100.0f - release_rate) / 1000.0f);
+    float bs = -0.2f + (0.8f * (brightness * 0.01f));
+    bs += velocity * velocity_scaling * 0.01f * 0.5f;
+    for (uint32_t i = 0; i < 8u; ++i) {
+        EPS(EP_DEC, h0 + i) = adjusted * scaling; scaling *= harmonic_scaling;
+        EPS(EP_REL, h0 + i) = rv;
+        float amp = (kEpVel127[h0 + i] * velocity) + (kEpVel0[h0 + i] * (1.0f - velocity));
+        amp *= 1.0f + bs * (float)(h0 + i);
+        EPS(EP_CUR, h0 + i) = amp;
+        EPS(EP_ORE, h0 + i) = 1.0f; EPS(EP_OIM, h0 + i) = 0.0f;
+    }
+}
+/* address of a state row of this voice, computed where it is used: the empty asm keeps the compiler from hoisting dozens of
+   loop-invariant 64-bit row addresses above the frame loop (where they would be spilled to local memory) */
+OSC_D float *ep_row(float *S, size_t n_stride, uint32_t field) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(n_stride));
+#endif
+    return S + (size_t)field * n_stride;
+}
+/* OscillatorBank::update_multipliers past its early return (electric_piano_voice.rs:132-149): new rotation multipliers
+   and unit oscillators for the harmonics [h0, h0 + 8) */
+static __device__ __noinline__ void ep_multiplier_rows(float *S, size_t n_stride, uint32_t h0, float freq, float sr) {
+    const float nyquist = sr * 0.5f;
+    for (uint32_t i = 0; i < 8u; ++i) {
+        const float hf = freq * (float)(h0 + i + 1u);
+        float re = 1.0f, im = 0.0f;
+        if (hf < nyquist) {
+            const float angle = 2.0f * kPi * hf / sr;
+            re = om_cosf_u(angle); im = om_sinf_u(angle);
         }
-        released = false; step = 0u;
-    } else {
-        released = true; step = 0u;
+        EPS(EP_MRE, h0 + i) = re; EPS(EP_MIM, h0 + i) = im;
+        EPS(EP_ORE, h0 + i) = 1.0f; EPS(EP_OIM, h0 + i) = 0.0f;
     }
 }
 
 /*
- * One thread = one voice; the 259-word state sits in a [field][thread] shared-memory tile for the
- * block.  The 32 harmonics are processed in 4 chunks of 8 held in REGISTERS across a 32-frame
- * tile (chunk-major inside the tile): per frame and chunk, 8 lerps + 8 complex rotations run out
- * of registers, and the running output sum is carried through a per-thread accumulator row so the
- * f32 additions happen in exactly the reference order sum += osc[i].imag * amp[i], i = 0..31.
- * The per-frame control flow (interpolation step, release flag, gate / value events, multiplier
- * refresh) is replayed identically by every chunk pass.
+ * FOUR threads = one voice: lane q of a voice owns the harmonics [8q, 8q + 8) and keeps their 48 state words (current /
+ * target amplitude, oscillator and multiplier, each complex) in REGISTERS for the whole block — the voice state moves
+ * HBM -> registers -> HBM once per block (2 * 1036 B per voice) instead of once per 32-frame tile per harmonic chunk as in
+ * the first version (profiles/r02_ncu_epiano_v1_tiles.md: 8.9 GB of DRAM traffic per block, 835 SASS instructions per
+ * warp-frame of 32 voices, 12 warps per SM at 168 registers).
+ *
+ * The reference adds the 32 weighted harmonics in index order (sum += osc[i].imag * amp[i], i = 0..31,
+ * electric_piano_voice.rs:160-166); to keep that rounding order the partial sum travels through the voice's four lanes as a
+ * SYSTOLIC pipeline: in iteration j lane q renders frame j - q — its own eight rotations and amplitude steps need nothing
+ * from the other lanes — and then continues the sum lane q - 1 left for that frame one iteration earlier (one SHFL.UP per
+ * iteration).  All four lanes are busy except for three iterations at either end of the block.  Everything per-voice
+ * (interpolation step, release flag, last frequency, ramps, gate / value events) is replayed by each lane at its own
+ * frame, so the lanes never wait for each other.  64 voices per CTA as everywhere (256 threads), so the instance fold, the
+ * mix partials and the tile geometry are those of the other kernels.
+ *
+ * Flush per 32 frames: instance sums (voices in index order) by all threads, the tremolo's phase recurrence by one thread
+ * per instance (serial in time, 4 flops per frame), then sine / pan / Frame<2> outputs by all threads again.
  */
-__global__ void __launch_bounds__(kCta, 6) epiano_kernel(const __grid_constant__ KernelArgs a) {
-    extern __shared__ float dyn[];          /* acc [kTileF][kCta] | tile [kTileF][kTileW] | isum [kTileF*kCta*2] */
-    float *acc = dyn + threadIdx.x;
-    float *tile = dyn + kTileF * kCta;
+constexpr uint32_t kEpLanes = 4u;
+constexpr uint32_t kEpThreads = kCta * kEpLanes;
+constexpr uint32_t kEpDynFloats = kTileF * kTileW + kTileF * kCta * 2u + kTileF * kCta + kTileF * kCta;
+
+__global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_constant__ KernelArgs a) {
+    extern __shared__ float dyn[];          /* tile [kTileF][kTileW] | isum [kTileF][kCta][2] | ssum [kTileF][kCta] | tph [kTileF][kCta] */
+    float *tile = dyn;
     float *isum = tile + kTileF * kTileW;
+    float *ssum = isum + kTileF * kCta * 2u;
+    float *tph = ssum + kTileF * kCta;
     const uint32_t n = a.n_voices;
-    const uint32_t v = blockIdx.x * kCta + threadIdx.x;
+    const uint32_t vl = threadIdx.x / kEpLanes, q = threadIdx.x % kEpLanes, h0 = q * 8u;
+    const uint32_t v = blockIdx.x * kCta + vl;
     const bool active = v < n;
     const uint32_t vs = active ? v : 0u;
     const uint32_t frames = a.ctl->frames, ramp_mask = a.ctl->ramp_mask;
     const float sr = a.u.sr;
     const uint32_t vpi = a.vpi;
-    const uint32_t col = tile_col(threadIdx.x, vpi);
+    const uint32_t col = tile_col(vl, vpi);
 
     SmallParams<9> prm; prm.load(a, vs);
-    /* the 259-word voice state stays in HBM/L2 as SoA rows; each chunk pass pulls its 48 words into
-       registers per 32-frame tile (coalesced: a warp reads 128 contiguous bytes per field) */
     float *S = a.state + vs;
     const size_t n_stride = n;
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
@@ -305,119 +372,140 @@ __global__ void __launch_bounds__(kCta, 6) epiano_kernel(const __grid_constant__
     const uint32_t my_inst = blockIdx.x * ipc + threadIdx.x;
     float trem_phase = (threadIdx.x < ipc && my_inst < a.n_inst) ? a.inst_state[my_inst] : 0.0f;
 
+    float cur[8], tgt[8], ore[8], oim[8], mre[8], mim[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        cur[i] = EPS(EP_CUR, h0 + i); tgt[i] = EPS(EP_TGT, h0 + i);
+        ore[i] = EPS(EP_ORE, h0 + i); oim[i] = EPS(EP_OIM, h0 + i);
+        mre[i] = EPS(EP_MRE, h0 + i); mim[i] = EPS(EP_MIM, h0 + i);
+    }
+    uint32_t step = (uint32_t)EPS(EP_STEP, 0);
+    bool released = EPS(EP_RELEASED, 0) != 0.0f;
+    float lastf = EPS(EP_LASTF, 0);
+    float part = 0.0f;                                        /* this lane's running sum of the frame it rendered last */
+    const bool keepv = active && a.voice_out != nullptr;
+
+    uint32_t j = 0;                                           /* pipeline iteration: lane q renders frame j - q */
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        if (active) {
-            const uint32_t step0 = (uint32_t)EPS(EP_STEP, 0);
-            const bool rel0 = EPS(EP_RELEASED, 0) != 0.0f;
-            const float lastf0 = EPS(EP_LASTF, 0);
-            const SmallParams<9> prm0 = prm;
-            const EventCursor ec0 = ec;
-            uint32_t step = step0; bool released = rel0; float lastf = lastf0;
-            for (uint32_t h0 = 0; h0 < 32u; h0 += 8u) {
-                float cur[8], tgt[8], ore[8], oim[8], mre[8], mim[8];
+        const uint32_t j_end = f0 + fe + (kEpLanes - 1u);     /* lane 3 has then written frames [f0, f0 + fe) */
+        for (; j < j_end; ++j) {
+            float sum = __shfl_up_sync(0xffffffffu, part, 1);
+            if (q == 0u) sum = 0.0f;
+            const uint32_t f = j - q;                         /* j < q wraps: not a frame yet */
+            if (active && f < frames) {
+                prm.ramps(a, ramp_mask, f);
+                if (ec.due(f)) {
+                    const uint32_t je = ec.end_of_frame(f);
+                    for (uint32_t k = ec.i; k < je; ++k) if (ec.ev[k].input_id != kEventGate) prm.value_event(a, ec.ev[k], v);
+                    for (uint32_t k = ec.i; k < je; ++k) if (ec.ev[k].input_id == kEventGate) {
+                        const float vel = ec.ev[k].scalar;          /* AmplitudeSource::on_gate, OscillatorBank::on_gate */
+                        if (vel > 0.0f) {
+                            ep_note_on_rows(S, n_stride, h0, vel, prm.P[1], prm.P[2], prm.P[3], prm.P[4], prm.P[5], prm.P[6]);
+                            const float *row = ep_row(S, n_stride, EP_CUR + h0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    cur[i] = EPS(EP_CUR, h0 + i); tgt[i] = EPS(EP_TGT, h0 + i);
-                    ore[i] = EPS(EP_ORE, h0 + i); oim[i] = EPS(EP_OIM, h0 + i);
-                    mre[i] = EPS(EP_MRE, h0 + i); mim[i] = EPS(EP_MIM, h0 + i);
-                }
-                step = step0; released = rel0; lastf = lastf0; prm = prm0; ec = ec0;
-                for (uint32_t ff = 0; ff < fe; ++ff) {
-                    const uint32_t f = f0 + ff;
-                    prm.ramps(a, ramp_mask, f);
-                    if (ec.due(f)) {
-                        const uint32_t j = ec.end_of_frame(f);
-                        for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
-                        for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
-                            ep_gate_chunk(S, n_stride, h0, ec.ev[q].scalar, prm.P, cur, ore, oim, released, step);
-                        ec.advance(j);
-                    }
-                    /* AmplitudeSource::process, electric_piano_voice.rs:322-351 */
-                    if (step == 0u) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) tgt[i] = cur[i] * (released ? EPS(EP_REL, h0 + i) : EPS(EP_DEC, h0 + i));
-                    }
-                    if (step < 64u) {
-                        const float t = (float)(step + 1u) / 64.0f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) cur[i] = cur[i] * (1.0f - t) + tgt[i] * t;
-                        step += 1u;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) cur[i] = tgt[i];
+                            for (int i = 0; i < 8; ++i) { cur[i] = row[(size_t)i * n_stride]; ore[i] = 1.0f; oim[i] = 0.0f; }
+                            released = false;
+                        } else {
+                            released = true;
+                        }
                         step = 0u;
                     }
-                    /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
-                    const float freq = prm.P[0];
-                    if (freq > 0.0f && !(fabsf(lastf - freq) < 0.01f)) {
-                        lastf = freq;
-                        const float nyquist = sr * 0.5f;
+                    ec.advance(je);
+                }
+                /* AmplitudeSource::process, electric_piano_voice.rs:322-351 */
+                if (step == 0u) {
+                    const float *row = ep_row(S, n_stride, (released ? EP_REL : EP_DEC) + h0);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float hf = freq * (float)(h0 + i + 1);
-                            if (hf < nyquist) {
-                                const float angle = 2.0f * kPi * hf / sr;
-                                mre[i] = om_cosf_u(angle); mim[i] = om_sinf_u(angle);
-                            } else { mre[i] = 1.0f; mim[i] = 0.0f; }
-                            ore[i] = 1.0f; oim[i] = 0.0f;
-                        }
-                    }
-                    float sum = (h0 == 0u) ? 0.0f : acc[ff * kCta];
+                    for (int i = 0; i < 8; ++i) tgt[i] = cur[i] * row[(size_t)i * n_stride];
+                }
+                if (step < 64u) {
+                    const float t = (float)(step + 1u) / 64.0f;
+                    const float omt = 1.0f - t;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float nr = ore[i] * mre[i] - oim[i] * mim[i];
-                        const float ni = ore[i] * mim[i] + oim[i] * mre[i];
-                        ore[i] = nr; oim[i] = ni;
-                        sum += ni * cur[i];
-                    }
-                    acc[ff * kCta] = sum;
+                    for (int i = 0; i < 8; ++i) cur[i] = cur[i] * omt + tgt[i] * t;
+                    step += 1u;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cur[i] = tgt[i];
+                    step = 0u;
+                }
+                /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
+                const float freq = prm.P[0];
+                if (freq > 0.0f && !(fabsf(lastf - freq) < 0.01f)) {
+                    lastf = freq;
+                    ep_multiplier_rows(S, n_stride, h0, freq, sr);
+                    const float *row = ep_row(S, n_stride, EP_MRE + h0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { mre[i] = row[(size_t)i * n_stride]; mim[i] = row[(size_t)(i + 32) * n_stride]; ore[i] = 1.0f; oim[i] = 0.0f; }
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    EPS(EP_CUR, h0 + i) = cur[i]; EPS(EP_TGT, h0 + i) = tgt[i];
-                    EPS(EP_ORE, h0 + i) = ore[i]; EPS(EP_OIM, h0 + i) = oim[i];
-                    EPS(EP_MRE, h0 + i) = mre[i]; EPS(EP_MIM, h0 + i) = mim[i];
+                    const float nr = ore[i] * mre[i] - oim[i] * mim[i];
+                    const float ni = ore[i] * mim[i] + oim[i] * mre[i];
+                    ore[i] = nr; oim[i] = ni;
+                    sum += ni * cur[i];
                 }
+                part = sum;
             }
-            EPS(EP_STEP, 0) = (float)step; EPS(EP_RELEASED, 0) = released ? 1.0f : 0.0f; EPS(EP_LASTF, 0) = lastf;
-        }
-        for (uint32_t ff = 0; ff < fe; ++ff) {
-            const float y = active ? acc[ff * kCta] * 3.0f : 0.0f;       /* output scaling */
-            if (active && a.voice_out != nullptr) a.voice_out[(size_t)(f0 + ff) * n + v] = y;
-            tile[ff * kTileW + col] = y;
+            if (q == kEpLanes - 1u && f - f0 < fe) {          /* the voice's last lane owns the finished frame */
+                const float y = active ? sum * 3.0f : 0.0f;   /* output scaling */
+                if (keepv) a.voice_out[f * n + v] = y;        /* n_voices * 512 < 2^32 (checked at create) */
+                tile[(f - f0) * kTileW + col] = y;
+            }
         }
         /* ---- flush: instance sum (index order) -> Tremolo (sequential in time) -> Frame<2> */
         __syncthreads();
-        if (threadIdx.x < ipc) {
-            const uint32_t i = threadIdx.x;
-            const uint32_t c0 = tile_col(i * vpi, vpi);
-            const uint32_t v_first = min((blockIdx.x * ipc + i) * vpi, n - 1u);   /* instance-level inputs: first voice */
-            const float depth0 = a.pv[(size_t)7 * n + v_first];
-            const float rate0 = a.pv[(size_t)8 * n + v_first];
+        for (uint32_t t = threadIdx.x; t < fe * ipc; t += kEpThreads) {
+            const uint32_t ff = t / ipc, i = t - ff * ipc;
+            const float *row = tile + ff * kTileW + tile_col(i * vpi, vpi);
+            float s = 0.0f;
+            for (uint32_t k = 0; k < vpi; ++k) s = s + row[k];
+            ssum[ff * kCta + i] = s;
+        }
+        const uint32_t v_first = min((blockIdx.x * ipc + (threadIdx.x % ipc)) * vpi, n - 1u);   /* instance-level inputs: first voice */
+        const float depth0 = a.pv[(size_t)7 * n + v_first];
+        const float rate0 = a.pv[(size_t)8 * n + v_first];
+        if (threadIdx.x < ipc) {                               /* Tremolo phase: phase = fract(phase + rate / sr) per frame */
             for (uint32_t ff = 0; ff < fe; ++ff) {
-                const float depth = ((ramp_mask >> 7) & 1u) ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + 7] : depth0;
                 const float rate = ((ramp_mask >> 8) & 1u) ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + 8] : rate0;
-                const float *row = tile + ff * kTileW;
-                float s = 0.0f;
-                for (uint32_t j = 0; j < vpi; ++j) s = s + row[c0 + j];
-                float l, r;
-                tremolo_process(trem_phase, s, rate, depth, sr, l, r);
-                isum[(ff * kCta + i) * 2 + 0] = l; isum[(ff * kCta + i) * 2 + 1] = r;
-                if (a.inst_out != nullptr && my_inst < a.n_inst) {
-                    a.inst_out[((size_t)(f0 + ff) * a.n_inst + my_inst) * 2 + 0] = l;
-                    a.inst_out[((size_t)(f0 + ff) * a.n_inst + my_inst) * 2 + 1] = r;
-                }
+                tph[ff * kCta + threadIdx.x] = trem_phase;
+                const float inc = rate / sr;
+                trem_phase = fractf(trem_phase + inc);
             }
         }
         __syncthreads();
-        for (uint32_t t = threadIdx.x; t < fe * 2u; t += kCta) {   /* mix partial: in-order over the CTA's instances */
+        for (uint32_t t = threadIdx.x; t < fe * ipc; t += kEpThreads) {
+            const uint32_t ff = t / ipc, i = t - ff * ipc;
+            const float depth = ((ramp_mask >> 7) & 1u) ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + 7] : depth0;
+            float l, r;
+            tremolo_output(tph[ff * kCta + i], ssum[ff * kCta + i], depth, l, r);
+            isum[(ff * kCta + i) * 2 + 0] = l; isum[(ff * kCta + i) * 2 + 1] = r;
+            const uint32_t inst = blockIdx.x * ipc + i;
+            if (a.inst_out != nullptr && inst < a.n_inst) {
+                a.inst_out[((size_t)(f0 + ff) * a.n_inst + inst) * 2 + 0] = l;
+                a.inst_out[((size_t)(f0 + ff) * a.n_inst + inst) * 2 + 1] = r;
+            }
+        }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < fe * 2u; t += kEpThreads) {   /* mix partial: in-order over the CTA's instances */
             const uint32_t ff = t >> 1, c = t & 1u;
             float s = 0.0f;
             for (uint32_t i = 0; i < ipc; ++i) s = s + isum[(ff * kCta + i) * 2 + c];
             a.mix_partial[((size_t)blockIdx.x * kMaxBlock + f0 + ff) * 2 + c] = s;
         }
-        __syncthreads();
+        /* no barrier here: the next tile's frames only write `tile` (last read before the second barrier above), and `isum`
+           is not written again before the next flush's second barrier, which every thread reaches after its reads here */
+    }
+    if (active) {
+        float *row = ep_row(S, n_stride, h0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            row[(size_t)(EP_CUR + i) * n_stride] = cur[i]; row[(size_t)(EP_TGT + i) * n_stride] = tgt[i];
+            row[(size_t)(EP_ORE + i) * n_stride] = ore[i]; row[(size_t)(EP_OIM + i) * n_stride] = oim[i];
+            row[(size_t)(EP_MRE + i) * n_stride] = mre[i]; row[(size_t)(EP_MIM + i) * n_stride] = mim[i];
+        }
+        if (q == 0u) { EPS(EP_STEP, 0) = (float)step; EPS(EP_RELEASED, 0) = released ? 1.0f : 0.0f; EPS(EP_LASTF, 0) = lastf; }
     }
     if (threadIdx.x < ipc && my_inst < a.n_inst) a.inst_state[my_inst] = trem_phase;
 #undef EPS

@@ -48,8 +48,11 @@ OSC_HD uint32_t f32_as_u32(float x) {
 }
 OSC_HD uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 OSC_HD uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
-/* f32::rem_euclid(1.0): fmodf(x,1) is exact and equals x - trunc(x) (sign of zero kept) */
+/* f32::rem_euclid(1.0): fmodf(x,1) is exact and equals x - trunc(x) (sign of zero kept).  For 0 <= x < 2 (every phase
+   accumulator in normal operation) trunc(x) is 0 or 1 and the result is never negative, which avoids the slow-pipe FRND:
+   x in [0, 1) is returned as is (that keeps -0, what copysign(0, x) gives), x in [1, 2) is x - 1 (+0 at x = 1). */
 OSC_HD float rem_euclid1(float x) {
+    if (x >= 0.0f && x < 2.0f) return (x >= 1.0f) ? x - 1.0f : x;
     float r = x - truncf(x);
     if (r == 0.0f) r = copysignf(0.0f, x);
     return (r < 0.0f) ? r + 1.0f : r;
@@ -309,6 +312,11 @@ OSC_D float poly_blamp(float t, float dt) {
     if (t > 1.0f - dt) { const float x = (t - 1.0f) / dt + 1.0f; return (x * x * x) / 3.0f; }
     return 0.0f;
 }
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ float om_sinf_cold(float y) { return om_sinf_u(y); }
+#else
+static inline float om_sinf_cold(float y) { return om_sinf_u(y); }
+#endif
 template <int WAVE>
 OSC_D float polyblep_process(float &phase_state, float phase_mod, float frequency_in, float frequency_mod,
                              float amplitude, float pulse_width_in, float sample_rate) {
@@ -320,7 +328,7 @@ OSC_D float polyblep_process(float &phase_state, float phase_mod, float frequenc
     if (pulse_width <= 0.0f) pulse_width = 0.0001f;
     float value;
     if (frequency >= sample_rate * 0.25f) {
-        value = om_sinf_u(phase * kTau);
+        value = (WAVE == WAVE_SINE) ? om_sinf_u(phase * kTau) : om_sinf_cold(phase * kTau);   /* rare for the other waves: a call */
     } else if (WAVE == WAVE_SINE) {
         value = om_sinf_u(phase * kTau);
     } else if (WAVE == WAVE_SAW) {
@@ -606,6 +614,16 @@ OSC_D void tremolo_process(float &phase, float input, float rate, float depth, f
     out_r = input * (1.0f - pan);
     const float inc = rate / sample_rate;
     phase = fractf(phase + inc);
+}
+
+/* the same node split for a tile of frames: the phase recurrence is serial in time (the caller runs `phase =
+   fractf(phase + rate / sample_rate)` per frame), the outputs of a frame depend only on that frame's phase */
+OSC_D void tremolo_output(float phase, float input, float depth, float &out_l, float &out_r) {
+    const float lfo = om_sinf_u(phase * 2.0f * kPi);
+    const float scaled_depth = depth / 3.0f;
+    const float pan = 0.5f + lfo * scaled_depth;
+    out_l = input * pan;
+    out_r = input * (1.0f - pan);
 }
 
 /* ---- SamplePlayer, mono (oscen-lib/src/sample_player/mod.rs:104-127): loops the slot's buffer; an empty / never

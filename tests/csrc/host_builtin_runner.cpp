@@ -90,7 +90,7 @@ extern "C" int oscen_host_run_builtin_block(uint32_t kind, int general, uint32_t
     case 1: host_launch(grid, 1, kCta, [&]() { twin_peaks_kernel(a); }); break;
     case 2: host_launch(grid, 1, kCta, [&]() { sat_kernel<1>(a); }); break;
     case 3: host_launch(grid, 1, kCta, [&]() { sat_kernel<4>(a); }); break;
-    case 4: host_launch(grid, 1, kCta, [&]() { epiano_kernel(a); }); break;
+    case 4: host_launch(grid, 1, kEpThreads, [&]() { epiano_kernel(a); }); break;
     case 5: host_launch(grid, 1, kCta, [&]() { synth_kernel<false>(a); }); break;
     case 6: host_launch(grid, 1, kCta, [&]() { synth_kernel<true>(a); }); break;
     default: {

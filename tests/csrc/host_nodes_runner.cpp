@@ -69,6 +69,7 @@ extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi,
     for (uint32_t k = 0; k < kMaxAssets && asset_data; ++k) { assets.data[k] = asset_data[k]; assets.frames[k] = asset_frames[k]; assets.reset[k] = asset_reset[k]; }
     const uint32_t grid = (n + kCta - 1) / kCta;
     const bool vec = !has_value_events && (n % 4u == 0u);
+    const bool plain = n_events == 0 && ramp_mask == 0;
     auto S = [&](int i) { return h->streams[(size_t)i].data(); };
     const float *gin = stream_in;
     if (g_lcg_on && !g.stream_input.empty()) {                 /* launch_plan(): the LCG source node fills a stream of its own */
@@ -104,9 +105,16 @@ extern "C" int oscen_host_plan_run_block(void *handle, uint32_t n, uint32_t vpi,
         for (uint32_t k = 0; k < cnt; ++k) a4.n[k] = args_of(l.nodes[k]);
 #define NODE_LAUNCH(KERNEL) host_launch(grid, cnt, kCta, [&]() { KERNEL(a4); })
         switch (l.type) {
-        case T::Adsr: NODE_LAUNCH(adsr_node_kernel); break;
-        case T::FmOperator: NODE_LAUNCH(fmop_node_kernel); break;
-        case T::Tpt: NODE_LAUNCH(tpt_node_kernel); break;
+        /* launch_plan(): a block without events and ramps runs the plain variants */
+        case T::Adsr: if (plain) NODE_LAUNCH(adsr_node_plain_kernel); else NODE_LAUNCH(adsr_node_kernel); break;
+        case T::FmOperator: if (plain) NODE_LAUNCH(fmop_node_plain_kernel); else NODE_LAUNCH(fmop_node_kernel); break;
+        case T::Tpt: {
+            bool zero_fmod = true;
+            for (uint32_t k = 0; k < cnt; ++k) zero_fmod = zero_fmod && a4.n[k].in2 == nullptr && a4.n[k].pid[2] == kNoInput && a4.n[k].cst[2] == 0.0f;
+            if (plain && zero_fmod) NODE_LAUNCH(tpt_node_plain_kernel<true>);
+            else if (plain) NODE_LAUNCH(tpt_node_plain_kernel<false>);
+            else NODE_LAUNCH(tpt_node_kernel);
+        } break;
         case T::PolyBlepSine: NODE_LAUNCH(polyblep_node_kernel<WAVE_SINE>); break;
         case T::PolyBlepSaw: NODE_LAUNCH(polyblep_node_kernel<WAVE_SAW>); break;
         case T::PolyBlepSquare: NODE_LAUNCH(polyblep_node_kernel<WAVE_SQUARE>); break;

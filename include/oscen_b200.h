@@ -324,7 +324,9 @@ int  oscen_b200_last_kernel_ms(oscen_b200_engine *e, float *ms);
    synchronisation for the whole batch (a timed loop then never waits on the device per step).  Either array may be
    NULL.  Returns the number of blocks written (<= cap); the engine keeps the last 4096 blocks. */
 int  oscen_b200_timing_drain(oscen_b200_engine *e, float *block_ms, float *kernel_ms, uint32_t cap);
-/* which graph kernel (variant) the last process_block launched, e.g. "fm_voice_fast_kernel<ramp>": a static string */
+/* which graph kernel (variant) the last process_block launched, e.g. "fm_voice_seg_kernel<ramp=0,fmod=1>"; for the node
+   plan the captured launch sequence's stateful kernels, e.g. "node plan (CUDA graph): adsr_node_plain_kernel
+   fmop_node_tma_kernel ...".  Owned by the engine: valid until the next process_block / destroy */
 const char *oscen_b200_last_kernel_name(const oscen_b200_engine *e);
 /* benchmarking aid: overwrite a 256 MiB scratch buffer on the engine stream so the next block
    starts with a cold L2 (126 MB) */

@@ -8,6 +8,7 @@
  * There is NO CPU rendering path: without a CUDA device create() fails with E_NO_DEVICE.
  */
 #include <cuda_runtime.h>
+#include <cuda.h>              /* CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is fetched at run time */
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -199,8 +200,11 @@ struct oscen_b200_engine {
     const float *captured_in = nullptr;      /* graph-input pointer / LCG mode baked into the captured CUDA graphs */
     bool captured_lcg = false;
     std::vector<float *> d_streams;
+    CUtensorMap *d_tmaps = nullptr;          /* one TMA descriptor per stream buffer ([kMaxBlock][n_voices], box [kTmaF][kCta]); null: not built */
     cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};   /* [0] no value events, [1] with, [2] plain block: no event at all, no ramp */
     uint64_t graph_kernels[3] = {0, 0, 0};
+    std::string plan_names[3];               /* launch sequence of each captured variant (last_kernel_name) */
+    std::string *plan_log = nullptr;         /* where launch_plan records kernel names while capturing */
 
     /* multi-GPU */
     void *comm = nullptr;
@@ -343,7 +347,12 @@ void fill_args(oscen_b200_engine *e, KernelArgs &a) {
     a.mix_partial = e->d_mix_partial;
     a.assets = e->d_assets;
     a.utab = e->d_utab;
-    { static const bool no_skew = []() { const char *x = getenv("OSCEN_B200_FM_SKEW"); return x && x[0] == '0'; }(); a.pad0 = no_skew ? 1u : 0u; }   /* A/B only */
+    {   /* diagnostics switches, read per call so that a test can flip them between engines:
+           OSCEN_B200_FM_SKEW=0 (bit 0: segmented FM kernel without the skewed loop), OSCEN_B200_TMA_STATE=1 (bit 1: the
+           general / legacy FM kernels hand their state over with TMA bulk copies, kernel_fm.cuh) */
+        const char *x = getenv("OSCEN_B200_FM_SKEW"), *t = getenv("OSCEN_B200_TMA_STATE");
+        a.pad0 = ((x && x[0] == '0') ? 1u : 0u) | ((t && t[0] == '1') ? 2u : 0u);
+    }
     for (uint32_t i = 0; i < kMaxInputs; ++i) a.u.p[i] = e->uni[i];
     a.u.sr = e->cfg.sample_rate;
     if (e->cfg.graph_kind == OSCEN_B200_GRAPH_FM_VOICE) {
@@ -426,8 +435,39 @@ void launch_ew(oscen_b200_engine *e, const NodeArgs &n, bool vec) {
     e->stats.kernel_launches++;
 }
 
+/* TMA descriptors of the node plan's stream buffers (kernel_nodes.cuh, *_node_tma_kernel): each buffer is a 2-D f32 tensor
+   [kMaxBlock frames][n_voices], voice fastest, box = [kTmaF frames][kCta voices], no swizzle (a thread reads its own column),
+   out-of-range voices zero-filled.  The row pitch n_voices * 4 must be a multiple of 16 bytes; otherwise, or when the driver
+   has no cuTensorMapEncodeTiled, d_tmaps stays null and the register-prefetch kernels run.  OSCEN_B200_NODE_TMA=0 does the same. */
+int build_stream_tmaps(oscen_b200_engine *e) {
+    const char *sw = getenv("OSCEN_B200_NODE_TMA");
+    const uint32_t n = e->cfg.n_voices;
+    if ((sw && sw[0] == '0') || n % 4u != 0u) return 0;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return 0;
+    }
+    std::vector<CUtensorMap> maps(e->d_streams.size());
+    for (size_t i = 0; i < maps.size(); ++i) {
+        const cuuint64_t dims[2] = {n, kMaxBlock};
+        const cuuint64_t strides[1] = {(cuuint64_t)n * sizeof(float)};
+        const cuuint32_t box[2] = {kCta, kTmaF}, estr[2] = {1, 1};
+        const CUresult r = ((encode_fn)fn)(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e->d_streams[i], dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;                       /* no descriptors: the register-prefetch kernels run */
+    }
+    CK(e, cudaMalloc(&e->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+    CK(e, cudaMemcpy(e->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 /* A/B and tests: OSCEN_B200_NODE_PLAIN=0 keeps the generic node kernels on event-free blocks too */
-static const bool g_no_plain_nodes = []() { const char *x = getenv("OSCEN_B200_NODE_PLAIN"); return x && x[0] == '0'; }();
+static bool no_plain_nodes() { const char *x = getenv("OSCEN_B200_NODE_PLAIN"); return x && x[0] == '0'; }   /* read per block: a test flips it between engines */
 
 int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
     const plan::Graph &g = e->graph;
@@ -449,6 +489,18 @@ int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
         if (r.node == plan::kGraphInput) return const_cast<float *>(gin);
         return S[p.first_stream[r.node] + r.port];
     };
+    auto tmap_of = [&](const plan::StreamRef &r) -> const void * {     /* descriptor of an inter-node stream (not the graph input) */
+        if (!e->d_tmaps || r.node < 0) return nullptr;
+        return e->d_tmaps + (p.first_stream[r.node] + r.port);
+    };
+    /* a wave can run the TMA-tiled kernel when every connected stream of every node in it has a descriptor */
+    auto wave_has_tmaps = [&](const NodeArgs4 &w, uint32_t cnt) {
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const NodeArgs &x = w.n[k];
+            if (!x.tm_out0 || (x.in0 && !x.tm_in0) || (x.in1 && !x.tm_in1)) return false;
+        }
+        return true;
+    };
     auto args_of = [&](int idx) {
         const plan::Node &nd = g.nodes[idx];
         NodeArgs a{};
@@ -457,6 +509,8 @@ int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
         a.in0 = resolve(nd.in[0]); a.in1 = resolve(nd.in[1]); a.in2 = resolve(nd.in[2]);
         a.out0 = S[p.first_stream[idx]];
         a.out1 = plan::n_outputs(nd.type) > 1 ? S[p.first_stream[idx] + 1] : nullptr;
+        a.tm_in0 = tmap_of(nd.in[0]); a.tm_in1 = tmap_of(nd.in[1]);
+        a.tm_out0 = e->d_tmaps ? (const void *)(e->d_tmaps + p.first_stream[idx]) : nullptr;
         for (int k = 0; k < plan::kMaxParams; ++k) { a.pid[k] = nd.pid[k]; a.cst[k] = nd.cst[k]; }
         a.gate = nd.gate ? 1u : 0u; a.q = nd.cst[1];
         if (nd.type == plan::NodeType::Delay) { a.gate = nd.ring_cap; a.q = nd.max_delay; }
@@ -470,19 +524,24 @@ int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
         const uint32_t cnt = (uint32_t)l.nodes.size();
         for (uint32_t k = 0; k < cnt; ++k) a4.n[k] = args_of(l.nodes[k]);
         const dim3 g2(grid, cnt);
+        auto log = [&](const char *name) { if (e->plan_log) { *e->plan_log += ' '; *e->plan_log += name; } };
         switch (l.type) {
         case plan::NodeType::Adsr:
-            if (plain) adsr_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); else adsr_node_kernel<<<g2, kCta, 0, e->stream>>>(a4);
+            if (plain) { adsr_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("adsr_node_plain_kernel"); }
+            else { adsr_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("adsr_node_kernel"); }
             e->stats.kernel_launches++; break;
         case plan::NodeType::FmOperator:
-            if (plain) fmop_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); else fmop_node_kernel<<<g2, kCta, 0, e->stream>>>(a4);
+            if (plain && wave_has_tmaps(a4, cnt)) { fmop_node_tma_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("fmop_node_tma_kernel"); }
+            else if (plain) { fmop_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("fmop_node_plain_kernel"); }
+            else { fmop_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("fmop_node_kernel"); }
             e->stats.kernel_launches++; break;
         case plan::NodeType::Tpt: {
             bool zero_fmod = true;                                      /* every filter of the wave: no f_mod stream, f_mod == 0 */
             for (uint32_t k = 0; k < cnt; ++k) zero_fmod = zero_fmod && a4.n[k].in2 == nullptr && a4.n[k].pid[2] == kNoInput && a4.n[k].cst[2] == 0.0f;
-            if (plain && zero_fmod) tpt_node_plain_kernel<true><<<g2, kCta, 0, e->stream>>>(a4);
-            else if (plain) tpt_node_plain_kernel<false><<<g2, kCta, 0, e->stream>>>(a4);
-            else tpt_node_kernel<<<g2, kCta, 0, e->stream>>>(a4);
+            if (plain && zero_fmod && wave_has_tmaps(a4, cnt)) { tpt_node_tma_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("tpt_node_tma_kernel"); }
+            else if (plain && zero_fmod) { tpt_node_plain_kernel<true><<<g2, kCta, 0, e->stream>>>(a4); log("tpt_node_plain_kernel<zero_fmod>"); }
+            else if (plain) { tpt_node_plain_kernel<false><<<g2, kCta, 0, e->stream>>>(a4); log("tpt_node_plain_kernel<fmod>"); }
+            else { tpt_node_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("tpt_node_kernel"); }
             e->stats.kernel_launches++; } break;
         case plan::NodeType::PolyBlepSine: polyblep_node_kernel<WAVE_SINE><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
         case plan::NodeType::PolyBlepSaw: polyblep_node_kernel<WAVE_SAW><<<g2, kCta, 0, e->stream>>>(a4); e->stats.kernel_launches++; break;
@@ -606,6 +665,7 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     for (auto &g : e->graph_exec) if (g) cudaGraphExecDestroy(g);
     e->jit.unload();
     for (float *p : e->d_streams) cudaFree(p);
+    cudaFree(e->d_tmaps);
     cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
     cudaFree(e->d_events); cudaFree(e->d_ctl); cudaFree(e->d_stream_in);
     cudaFree(e->d_voice_out); cudaFree(e->d_inst_out); cudaFree(e->d_mix_partial); cudaFree(e->d_mix);
@@ -736,6 +796,7 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
             e->d_streams.resize((size_t)pp.n_streams + 1, nullptr);      /* + 1: device-generated graph input */
             for (auto &p : e->d_streams) CK(e, cudaMalloc(&p, (size_t)kMaxBlock * n * sizeof(float)));
             e->final_stream = e->d_streams[pp.first_stream[pg.output.node] + pg.output.port];
+            { const int r = build_stream_tmaps(e); if (r) return r; }
         }
         CK(e, cudaFuncSetAttribute(epiano_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEpDyn));
         if (is_clip(kind)) { KernelArgs none{}; launch_clip(e, none, 0, true); CK(e, cudaGetLastError()); }
@@ -1240,7 +1301,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         rc = launch_mix_reduce(e, frames); if (rc) return rc;
     } else {
         /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
-        const bool plain = n_ev == 0 && ramp_mask == 0 && !device_midi && !g_no_plain_nodes;
+        const bool plain = n_ev == 0 && ramp_mask == 0 && !device_midi && !no_plain_nodes();
         const int gi = plain ? 2 : (has_value_events ? 1 : 0);
         if (e->captured_in != e->stream_in_ptr || e->captured_lcg != e->lcg_on) {
             for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
@@ -1250,7 +1311,10 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             cudaGraph_t g = nullptr;
             CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t before = e->stats.kernel_launches;
+            e->plan_names[gi] = "node plan (CUDA graph):";
+            e->plan_log = &e->plan_names[gi];
             rc = launch_plan(e, has_value_events, plain);
+            e->plan_log = nullptr;
             if (!rc) rc = launch_mix_reduce(e, frames);
             cudaError_t s = cudaStreamEndCapture(e->stream, &g);
             e->graph_kernels[gi] = e->stats.kernel_launches - before;
@@ -1261,7 +1325,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             cudaGraphDestroy(g);
         }
         CK(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
-        e->last_kernel = "node plan (CUDA graph)";
+        e->last_kernel = e->plan_names[gi].c_str();               /* valid until the variant is captured again */
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         e->stats.graph_launches++;
         e->stats.kernel_launches += e->graph_kernels[gi];

@@ -15,15 +15,13 @@
 #include "kernels_common.cuh"
 #include "state_io.cuh"
 
-/* 1: move the per-voice state rows HBM <-> shared memory with TMA bulk copies (cp.async.bulk +
-   mbarrier) instead of per-thread coalesced loads/stores.  Built, bit-exact, measured SLOWER on
-   B200 (0.2736 vs 0.2652 ms per block at 65 536 voices; 3.76 vs 3.67 ms at 1 M): the state is
-   touched once per 256-frame block (1.4 B/voice-sample), so the extra barrier, the mbarrier wait
-   before the first instruction of the recurrence and the shared-memory round trip cost more than
-   the handful of LDG/STG they replace.  Off by default. */
-#ifndef OSCEN_B200_TMA_STATE
-#define OSCEN_B200_TMA_STATE 0
-#endif
+/* KernelArgs.pad0 bit 1 (engine: OSCEN_B200_TMA_STATE=1): move the per-voice state rows HBM <-> shared memory with TMA
+   bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS) instead of per-thread coalesced loads / stores — north_star's
+   "TMA for block-to-block state handoff".  Bit-exact (tests/test_parity_gpu.py runs both), measured SLOWER on B200 (0.2736
+   vs 0.2652 ms per block at 65 536 voices; 3.76 vs 3.67 ms at 1 M): the state is touched once per 256-frame block
+   (1.4 B/voice-sample), so the extra barrier, the mbarrier wait before the first instruction of the recurrence and the
+   shared-memory round trip cost more than the handful of LDG / STG they replace.  Off by default; a run-time switch so
+   that the one library the tests and the bench load carries, and keeps testing, both paths. */
 
 namespace oscen {
 
@@ -58,12 +56,8 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
 
     /* ---- state: block-to-block handoff through TMA bulk copies (HBM rows -> smem -> registers) */
     const float *sp = a.state; uint32_t sn = n, sv = vs;
-#if OSCEN_B200_TMA_STATE
-    const bool staged = state_stage_in(tile, &state_bar, a.state, FM_NSTATE, n, sp, sn, sv, vs);
-#else
-    const bool staged = false;           /* plain coalesced loads: measured 2-3 % faster, see DESIGN.md §4.4 */
-    (void)state_bar;
-#endif
+    bool staged = false;                 /* default: plain coalesced loads (measured 2-3 % faster) */
+    if (a.pad0 & 2u) staged = state_stage_in(tile, &state_bar, a.state, FM_NSTATE, n, sp, sn, sv, vs);
     AdsrState e3, e2, e1, ef;
     adsr_load(e3, sp, FM_E3, sn, sv); adsr_load(e2, sp, FM_E2, sn, sv);
     adsr_load(e1, sp, FM_E1, sn, sv); adsr_load(ef, sp, FM_EF, sn, sv);

@@ -41,6 +41,10 @@ struct NodeArgs {
     float sr;
     uint32_t gate;                          /* AdsrEnvelope: gate events are connected to this node */
     float q;                                /* stateless nodes: second literal (x.clamp(p, q)) */
+    /* TMA descriptors (CUtensorMap, 128 B each, in device memory) of the streams behind in0 / in1 / out0, viewed as 2-D
+       tensors [kMaxBlock frames][n_voices] with a box of [kTmaF frames][kCta voices]; null when the engine could not
+       build them (n_voices % 4 != 0: the row pitch must be a multiple of 16 bytes) */
+    const void *tm_in0, *tm_in1, *tm_out0;
 };
 struct NodeArgs4 { NodeArgs n[4]; };        /* blockIdx.y selects the node */
 
@@ -459,6 +463,113 @@ __global__ void __launch_bounds__(kCta) tpt_node_plain_kernel(const __grid_const
         OSC_TPT_TILE(xB, cB, mB, f0 + kPF)
     }
 #undef OSC_TPT_TILE
+    if (active) tpt_store(s, a.state, a.state_base, n, v);
+}
+
+/* =====================================================================================================================
+ * TMA-TILED variants of the plain FmOperator / TptFilter kernels (north_star: "staged through shared memory ... TMA").
+ * A CTA's 64 voices x kTmaF frames of every stream is one 2-D box: ONE elected thread issues
+ * `cp.async.bulk.tensor.2d` loads (SASS UTMALDG) into a 3-stage shared-memory ring, completion on an mbarrier per stage;
+ * the recurrence reads its inputs with LDS, writes its output tile with STS, and the same thread streams finished tiles out
+ * with `cp.async.bulk.tensor.2d` stores (UTMASTG, bulk async-group, double-buffered).  Against the register-prefetch
+ * kernels above this takes the stream address arithmetic, the bounds predicates and 32 prefetch registers per thread out of
+ * the serial loop (fmop: 96 -> ~60 registers, so 16 instead of 10 CTAs per SM hide the sine's FP64 / conversion latency).
+ * Voices past n_voices in the last CTA are zero-filled on load and clipped on store by the descriptor; frames past the
+ * block inside the last box are rows of the stream buffer nobody reads.
+ * ===================================================================================================================== */
+constexpr uint32_t kTmaF = 8;                 /* frames per box */
+constexpr uint32_t kTmaStages = 3;
+constexpr uint32_t kTmaTile = kTmaF * kCta;   /* floats per box */
+OSC_D void tma_load_2d(void *smem_dst, const void *tmap, uint32_t x, uint32_t y, unsigned long long *bar) {
+    OSC_PTX("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+OSC_D void tma_store_2d(const void *tmap, uint32_t x, uint32_t y, const void *smem_src) {
+    OSC_PTX("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(x), "r"(y), "r"(smem_u32(smem_src)) : "memory");
+}
+OSC_D void tma_store_commit() { OSC_PTX("cp.async.bulk.commit_group;" ::: "memory"); }
+OSC_D void tma_store_wait_read0() { OSC_PTX("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+OSC_D void tma_store_wait_all() { OSC_PTX("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+/* the tile pipeline shared by the two kernels: BODY(k, x0, x1) -> output sample of frame tile*kTmaF + k */
+#define OSC_TMA_PIPELINE(HAS0, HAS1, BODY)                                                                          \
+    __shared__ __align__(128) float in_ring[kTmaStages][2][kTmaTile];                                               \
+    __shared__ __align__(128) float out_ring[2][kTmaTile];                                                          \
+    __shared__ __align__(8) unsigned long long full_bar[kTmaStages];                                                \
+    const uint32_t v0 = blockIdx.x * kCta, tid = threadIdx.x;                                                       \
+    const uint32_t n_tiles = (frames + kTmaF - 1u) / kTmaF;                                                         \
+    const uint32_t tx_bytes = ((HAS0) ? kTmaTile * 4u : 0u) + ((HAS1) ? kTmaTile * 4u : 0u);                        \
+    if (tid == 0) { for (uint32_t st = 0; st < kTmaStages; ++st) mbar_init(&full_bar[st], 1u); }                    \
+    __syncthreads();                                                                                                \
+    auto issue = [&](uint32_t tile) {                                                                               \
+        const uint32_t st = tile % kTmaStages;                                                                      \
+        if (tx_bytes) {                                                                                             \
+            mbar_expect_tx(&full_bar[st], tx_bytes);                                                                \
+            if (HAS0) tma_load_2d(in_ring[st][0], a.tm_in0, v0, tile * kTmaF, &full_bar[st]);                       \
+            if (HAS1) tma_load_2d(in_ring[st][1], a.tm_in1, v0, tile * kTmaF, &full_bar[st]);                       \
+        }                                                                                                           \
+    };                                                                                                              \
+    if (tid == 0) for (uint32_t t0 = 0; t0 + 1u < kTmaStages && t0 < n_tiles; ++t0) issue(t0);                      \
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {                                                               \
+        const uint32_t st = tile % kTmaStages;                                                                      \
+        if (tid == 0 && tile + kTmaStages - 1u < n_tiles) issue(tile + kTmaStages - 1u);   /* stage of tile - 1: consumed */ \
+        if (tx_bytes) mbar_wait(&full_bar[st], (tile / kTmaStages) & 1u);                                           \
+        const float *x0p = in_ring[st][0] + tid, *x1p = in_ring[st][1] + tid;                                       \
+        float *op = out_ring[tile & 1u] + tid;                                                                      \
+        const uint32_t fe = min(kTmaF, frames - tile * kTmaF);                                                      \
+        _Pragma("unroll") for (uint32_t k = 0; k < kTmaF; ++k) {                                                    \
+            if (k < fe) {                                                                                           \
+                const float x0 = (HAS0) ? x0p[k * kCta] : 0.0f, x1 = (HAS1) ? x1p[k * kCta] : 0.0f;                 \
+                op[k * kCta] = BODY(x0, x1);                                                                        \
+            }                                                                                                       \
+        }                                                                                                           \
+        fence_async_smem();                               /* this thread's STS before the async proxy reads them */ \
+        if (tid == 0) tma_store_wait_read0();             /* the store of tile - 1 has read out_ring[(tile + 1) & 1] */ \
+        __syncthreads();                                                                                            \
+        if (tid == 0) { tma_store_2d(a.tm_out0, v0, tile * kTmaF, out_ring[tile & 1u]); tma_store_commit(); }       \
+    }                                                                                                               \
+    if (tid == 0) tma_store_wait_all();
+
+/* ---- FmOperator, plain block, TMA tiles */
+__global__ void __launch_bounds__(kCta) fmop_node_tma_kernel(const __grid_constant__ NodeArgs4 args) {
+    const NodeArgs &a = args.n[blockIdx.y];
+    const uint32_t n = a.n_voices;
+    const uint32_t vt = blockIdx.x * kCta + threadIdx.x;
+    const bool active = vt < n;
+    const uint32_t v = active ? vt : 0u;                     /* every thread of the CTA stays for the barriers */
+    const uint32_t frames = a.ctl->frames;
+    NodeParams<6> prm; prm.load(a, v);
+    const bool pm_stream = a.in0 != nullptr, en_stream = a.in1 != nullptr;
+    FmOpState s;
+    s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
+    s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
+    const OmSinRegs sk = om_sin_regs();
+    const float fb = prm.P[2], lvl = prm.P[3], pm_c = prm.P[4], en_c = prm.P[5];
+#define OSC_FMOP_BODY(X0, X1) fmop_process_k(s, pm_stream ? (X0) : pm_c, fb, en_stream ? (X1) : en_c, lvl, sk)
+    OSC_TMA_PIPELINE(pm_stream, en_stream, OSC_FMOP_BODY)
+#undef OSC_FMOP_BODY
+    if (active) { a.state[(size_t)(a.state_base + 0) * n + v] = s.phase; a.state[(size_t)(a.state_base + 1) * n + v] = s.prev; }
+}
+
+/* ---- TptFilter (no f_mod), plain block, TMA tiles */
+__global__ void __launch_bounds__(kCta) tpt_node_tma_kernel(const __grid_constant__ NodeArgs4 args) {
+    const NodeArgs &a = args.n[blockIdx.y];
+    const uint32_t n = a.n_voices;
+    const uint32_t vt = blockIdx.x * kCta + threadIdx.x;
+    const bool active = vt < n;
+    const uint32_t v = active ? vt : 0u;
+    const uint32_t frames = a.ctl->frames;
+    NodeParams<4> prm; prm.load(a, v);
+    TptState s; tpt_load(s, a.state, a.state_base, n, v);
+    const bool in_stream = a.in0 != nullptr, cut_stream = a.in1 != nullptr;
+    const float sr = a.sr;
+    const float max_cutoff = fminf(sr * 0.5f - FLT_EPSILON, 20000.0f), period = 0.5f / sr, two_sr = 2.0f * sr;
+    const float qc = clampf(prm.P[0], 0.1f, 10.0f), inv_q = 1.0f / qc;
+    const float cut_c = prm.P[1], in_c = prm.P[3];
+#define OSC_TPT_BODY(X0, X1) tpt_process_mod(s, in_stream ? (X0) : in_c, cut_stream ? (X1) : cut_c, qc, inv_q, max_cutoff, sr, two_sr, period)
+    OSC_TMA_PIPELINE(in_stream, cut_stream, OSC_TPT_BODY)
+#undef OSC_TPT_BODY
     if (active) tpt_store(s, a.state, a.state_base, n, v);
 }
 

@@ -262,13 +262,7 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
 /* examples/electric-piano/src/electric_piano_voice.rs (AmplitudeSource, OscillatorBank,
    ElectricPianoVoiceNode), tremolo.rs, main.rs:33-97 (16 voices -> sum -> Tremolo -> Frame<2>).
    Per-voice state (259 words) lives in a [field][thread] shared-memory tile for the block. */
-__constant__ float kEpVel0[32] = { 0.02f, 0.05f };
-__constant__ float kEpVel127[32] = {
-    0.150869f, 0.385766f, 0.215543f, 0.117811f, 0.100411f, 0.0128637f, 0.0288844f, 0.00243388f,
-    0.00963092f, 0.0035634f, 0.00256945f, 0.00184799f, 0.000399878f, 0.000660576f, 3.00995e-05f,
-    0.00021866f, 9.33705e-05f, 0.000177973f, 0.0002545f, 0.000323602f, 0.000779045f, 0.000116569f,
-    0.000772873f, 0.000364486f, 0.000248027f, 0.00018236f, 3.27292e-05f, 6.64988e-05f,
-    0.0f, 0.0f, 0.0f, 0.0f };
+/* the two reference spectra (kEpVel0 / kEpVel127) live in nodes.cuh, next to the per-node forms of these nodes */
 
 #define EPS(field, i) S[(size_t)((field) + (i)) * n_stride]
 /* The two rare per-voice transitions run out of line ON THE STATE ROWS IN HBM (the caller reloads the registers they

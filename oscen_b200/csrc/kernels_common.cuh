@@ -44,33 +44,40 @@ struct EventCursor {
    thread moves all rows HBM -> shared memory (completion on an mbarrier) at block start and
    shared memory -> HBM (bulk async-group) at block end.  Needs 16-byte aligned rows: n_voices % 4 == 0. */
 OSC_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+/* inline PTX exists for the device compile only; the host-executed test harness (tests/csrc/host_cuda) never takes a TMA
+   path (no descriptor, switch off), and must fault loudly if it ever did */
+#if defined(__CUDACC__)
+#define OSC_PTX(...) asm volatile(__VA_ARGS__)
+#else
+#define OSC_PTX(...) __trap()
+#endif
 OSC_D void mbar_init(unsigned long long *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    OSC_PTX("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    OSC_PTX("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 OSC_D void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    OSC_PTX("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 OSC_D void mbar_wait(unsigned long long *bar, uint32_t parity) {
     uint32_t ok = 0, spins = 0;
     do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        OSC_PTX("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (!ok && ++spins > (1u << 26)) __trap();          /* a lost completion must fault, not hang the GPU */
     } while (!ok);
 }
 OSC_D void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    OSC_PTX("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 OSC_D void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    OSC_PTX("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 OSC_D void bulk_commit_wait() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    OSC_PTX("cp.async.bulk.commit_group;" ::: "memory");
+    OSC_PTX("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
-OSC_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+OSC_D void fence_async_smem() { OSC_PTX("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 /* state handoff, load side: after the call `*sp / *sn / *sv` address this thread's state as
    sp[field * sn + sv] (shared-memory staging when the TMA path is usable, HBM otherwise) */

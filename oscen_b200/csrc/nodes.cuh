@@ -626,6 +626,107 @@ OSC_D void tremolo_output(float phase, float input, float depth, float &out_l, f
     out_r = input * (1.0f - pan);
 }
 
+/* ============================================ AmplitudeSource / OscillatorBank as graph nodes == */
+/* examples/electric-piano/src/electric_piano_voice.rs:6-352.  These are the per-node forms a DSL-compiled graph uses
+   (codegen.hpp): each node's state lives in its SoA rows in HBM and is walked IN PLACE, frame by frame (`S` = the row of
+   field 0 for this voice, rows `n` floats apart), and `amplitudes: [f32; 32]` is the one array-typed stream of the node
+   library — a 32-float local array between the two nodes.  The hand-written epiano_kernel (kernel_others.cuh) renders the
+   same arithmetic with the state in registers across four lanes per voice and is ~20x faster; this form exists so that
+   ElectricPianoGraph compiles from its own `graph!` text.  Same operations in the same order as the oracle. */
+__constant__ float kEpVel0[32] = { 0.02f, 0.05f };
+__constant__ float kEpVel127[32] = {
+    0.150869f, 0.385766f, 0.215543f, 0.117811f, 0.100411f, 0.0128637f, 0.0288844f, 0.00243388f,
+    0.00963092f, 0.0035634f, 0.00256945f, 0.00184799f, 0.000399878f, 0.000660576f, 3.00995e-05f,
+    0.00021866f, 9.33705e-05f, 0.000177973f, 0.0002545f, 0.000323602f, 0.000779045f, 0.000116569f,
+    0.000772873f, 0.000364486f, 0.000248027f, 0.00018236f, 3.27292e-05f, 6.64988e-05f,
+    0.0f, 0.0f, 0.0f, 0.0f };
+
+constexpr uint32_t kEpHarmonics = 32u;
+enum : uint32_t { AS_CUR = 0, AS_TGT = 32, AS_DEC = 64, AS_REL = 96, AS_RELEASED = 128, AS_STEP = 129, AS_NSTATE = 130 };
+enum : uint32_t { OB_ORE = 0, OB_OIM = 32, OB_MRE = 64, OB_MIM = 96, OB_LASTF = 128, OB_NSTATE = 129 };
+/* AmplitudeSource::on_gate -> trigger_note / release_note (electric_piano_voice.rs:230-318) */
+OSC_D void ampsrc_on_gate(float *S, size_t n, float scalar, float brightness, float velocity_scaling, float decay_rate,
+                          float harmonic_decay, float key_scaling, float release_rate) {
+    if (scalar > 0.0f) {
+        const float velocity = scalar;
+        const float note = 60.0f;                                   /* note_pitch is never updated */
+        const float base_decay_rate = (100.0f - decay_rate) / 40000.0f;
+        const float harmonic_scaling = 1.0f - ((100.0f - harmonic_decay) / 200000.0f);
+        const float scaling_multiplier = (48.0f - note) / 12.0f;
+        const float key_scaling_factor = scaling_multiplier * (key_scaling * 0.02f);
+        const float adjusted = (key_scaling_factor > 0.0f)
+            ? 1.0f - (base_decay_rate / (1.0f + key_scaling_factor))
+            : 1.0f - (base_decay_rate * (1.0f - key_scaling_factor));
+        const float rv = 0.999f - ((100.0f - release_rate) / 1000.0f);
+        float bs = -0.2f + (0.8f * (brightness * 0.01f));
+        bs += velocity * velocity_scaling * 0.01f * 0.5f;
+        float scaling = 1.0f;
+        for (uint32_t i = 0; i < kEpHarmonics; ++i) {
+            S[(size_t)(AS_DEC + i) * n] = adjusted * scaling; scaling *= harmonic_scaling;
+            S[(size_t)(AS_REL + i) * n] = rv;
+            float amp = (kEpVel127[i] * velocity) + (kEpVel0[i] * (1.0f - velocity));
+            amp *= 1.0f + bs * (float)i;
+            S[(size_t)(AS_CUR + i) * n] = amp;
+        }
+        S[(size_t)AS_RELEASED * n] = 0.0f;
+    } else {
+        S[(size_t)AS_RELEASED * n] = 1.0f;
+    }
+    S[(size_t)AS_STEP * n] = 0.0f;
+}
+/* AmplitudeSource::process (electric_piano_voice.rs:322-351): amps = this frame's `amplitudes` */
+OSC_D void ampsrc_process(float *S, size_t n, float *amps) {
+    uint32_t step = (uint32_t)S[(size_t)AS_STEP * n];
+    const bool released = S[(size_t)AS_RELEASED * n] != 0.0f;
+    if (step == 0u)
+        for (uint32_t i = 0; i < kEpHarmonics; ++i)
+            S[(size_t)(AS_TGT + i) * n] = S[(size_t)(AS_CUR + i) * n] * S[(size_t)((released ? AS_REL : AS_DEC) + i) * n];
+    if (step < 64u) {
+        const float t = (float)(step + 1u) / 64.0f;
+        for (uint32_t i = 0; i < kEpHarmonics; ++i) {
+            const float c = S[(size_t)(AS_CUR + i) * n] * (1.0f - t) + S[(size_t)(AS_TGT + i) * n] * t;
+            S[(size_t)(AS_CUR + i) * n] = c; amps[i] = c;
+        }
+        step += 1u;
+    } else {
+        for (uint32_t i = 0; i < kEpHarmonics; ++i) { const float c = S[(size_t)(AS_TGT + i) * n]; S[(size_t)(AS_CUR + i) * n] = c; amps[i] = c; }
+        step = 0u;
+    }
+    S[(size_t)AS_STEP * n] = (float)step;
+}
+/* OscillatorBank::on_gate (electric_piano_voice.rs:112-123): a note-on restarts the oscillators at zero phase */
+OSC_D void oscbank_on_gate(float *S, size_t n, float scalar) {
+    if (scalar > 0.0f)
+        for (uint32_t i = 0; i < kEpHarmonics; ++i) { S[(size_t)(OB_ORE + i) * n] = 1.0f; S[(size_t)(OB_OIM + i) * n] = 0.0f; }
+}
+/* OscillatorBank::process (electric_piano_voice.rs:127-170) */
+OSC_D float oscbank_process(float *S, size_t n, float frequency, float sample_rate, const float *amps) {
+    if (frequency > 0.0f && !(fabsf(S[(size_t)OB_LASTF * n] - frequency) < 0.01f)) {      /* update_multipliers */
+        S[(size_t)OB_LASTF * n] = frequency;
+        const float nyquist = sample_rate * 0.5f;
+        for (uint32_t i = 0; i < kEpHarmonics; ++i) {
+            const float hf = frequency * (float)(i + 1u);
+            float re = 1.0f, im = 0.0f;
+            if (hf < nyquist) {
+                const float angle = 2.0f * kPi * hf / sample_rate;
+                re = om_cosf_u(angle); im = om_sinf_u(angle);
+            }
+            S[(size_t)(OB_MRE + i) * n] = re; S[(size_t)(OB_MIM + i) * n] = im;
+            S[(size_t)(OB_ORE + i) * n] = 1.0f; S[(size_t)(OB_OIM + i) * n] = 0.0f;
+        }
+    }
+    float sum = 0.0f;
+    for (uint32_t i = 0; i < kEpHarmonics; ++i) {
+        const float ore = S[(size_t)(OB_ORE + i) * n], oim = S[(size_t)(OB_OIM + i) * n];
+        const float mre = S[(size_t)(OB_MRE + i) * n], mim = S[(size_t)(OB_MIM + i) * n];
+        const float nr = ore * mre - oim * mim;
+        const float ni = ore * mim + oim * mre;
+        S[(size_t)(OB_ORE + i) * n] = nr; S[(size_t)(OB_OIM + i) * n] = ni;
+        sum += ni * amps[i];
+    }
+    return sum * 3.0f;                                              /* output scaling */
+}
+
 /* ---- SamplePlayer, mono (oscen-lib/src/sample_player/mod.rs:104-127): loops the slot's buffer; an empty / never
    loaded slot is silence.  The swap-and-reset of `buf.take()` is the caller's `playhead = 0` on the first block after a
    load (engine_types.h AssetTable::reset). */

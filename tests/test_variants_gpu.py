@@ -1,0 +1,109 @@
+"""GPU parity of the kernel VARIANTS one engine can pick between for the same block — every one must produce the oracle's
+bits: node plan (generic kernels / plain register-prefetch kernels / TMA-tiled kernels, kernel_nodes.cuh) and the FMVoice
+state handoff (coalesced loads / TMA bulk copies, kernel_fm.cuh).  The variants are selected the way a user would: by bank
+shape (n_voices % 4), by what the block carries (events, ramps), and by the documented environment switches."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GATE = O.EV_GATE
+
+
+def fm_script(bank, n, blocks):
+    """gate-on burst in block 0, plain blocks, a ramp, plain again, gate-off, plain tail (block sizes not multiples of 8)"""
+    out = []
+    bank.set_value(0, (110.0 * 2.0 ** ((np.arange(n) % 37) / 12.0)).astype(np.float32))
+    for blk, frames in enumerate(blocks):
+        if blk == 0:
+            bank.push_events([(v, (7 * v) % frames, GATE, 0.3 + 0.7 * ((v * 13) % 17) / 17.0) for v in range(n)])
+        if blk == 3:
+            bank.set_value_ramp(21, 2400.0, 150)               # filter cutoff ramps across this block and the next
+        if blk == 5:
+            bank.push_events([(v, (3 * v) % frames, GATE, 0.0) for v in range(0, n, 2)])
+        bank.process_block(frames)
+        out.append((bank.read_voice_out(), bank.read_instance_out()))
+    return out
+
+
+@pytest.mark.parametrize("n,env", [
+    (256, {}),                                   # n % 4 == 0: plain blocks run the TMA-tiled FmOperator / TptFilter kernels
+    (256, {"OSCEN_B200_NODE_TMA": "0"}),         # same bank on the register-prefetch plain kernels
+    (256, {"OSCEN_B200_NODE_PLAIN": "0"}),       # and on the generic kernels only
+    (136, {}),                                   # partly filled last CTA (136 = 2 * 64 + 8), TMA clips the box
+    (130, {}),                                   # n % 4 != 0: no descriptors, plain kernels
+])
+def test_fm_node_plan_kernel_variants_match_oracle(n, env):
+    from oscen_b200 import abi
+    blocks = (200, 256, 100, 256, 77, 256, 33, 512)
+    old = {k: os.environ.get(k) for k in ("OSCEN_B200_NODE_TMA", "OSCEN_B200_NODE_PLAIN")}
+    try:
+        for k in old:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        vpi = 8 if n % 8 == 0 else 1
+        ref = O.OracleBank(O.K_FM, n, vpi)
+        gpu = abi.Engine(abi.GRAPH_FM_VOICE, n, vpi, 48000.0, 0, abi.PLAN_NODES, 3)
+        ro, go = fm_script(ref, n, blocks), fm_script(gpu, n, blocks)
+        gpu.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert max(float(np.abs(v).max()) for v, _ in ro) > 0.01
+    for blk, ((vr, ir), (vg, ig)) in enumerate(zip(ro, go)):
+        assert np.array_equal(vg, vr), (blk, float(np.abs(vg - vr).max()))
+        assert np.array_equal(ig, ir), blk
+
+
+def test_fm_node_plan_tma_kernels_are_the_ones_that_ran():
+    """the claim above is only worth something if the plain blocks of the n % 4 == 0 bank really launched TMA kernels:
+    the engine reports the launch sequence of its last captured plan"""
+    from oscen_b200 import abi
+    n = 256
+    gpu = abi.Engine(abi.GRAPH_FM_VOICE, n, 8, 48000.0, 0, abi.PLAN_NODES, 3)
+    gpu.set_value(0, 220.0)
+    gpu.push_events([(v, v % 64, GATE, 0.8) for v in range(n)])
+    gpu.process_block(128)
+    first = gpu.last_kernel_name()
+    gpu.process_block(128)
+    plain = gpu.last_kernel_name()
+    gpu.close()
+    assert "fmop_node_kernel" in first and "tma" not in first
+    assert "fmop_node_tma_kernel" in plain and "tpt_node_tma_kernel" in plain and "adsr_node_plain_kernel" in plain
+
+
+@pytest.mark.parametrize("n", [64, 200, 1024])
+def test_fm_general_kernel_with_tma_state_handoff_matches_oracle(n):
+    """OSCEN_B200_TMA_STATE=1: fm_voice_kernel<true> hands its 29 state rows over with cp.async.bulk + mbarrier"""
+    from oscen_b200 import abi
+    old = os.environ.get("OSCEN_B200_TMA_STATE")
+    try:
+        os.environ["OSCEN_B200_TMA_STATE"] = "1"
+        ref = O.OracleBank(O.K_FM, n, 8)
+        gpu = abi.Engine(abi.GRAPH_FM_VOICE, n, 8, 48000.0, 0, abi.PLAN_FUSED, 3)
+        outs = []
+        for b in (ref, gpu):
+            o = []
+            b.set_value(0, (110.0 * 2.0 ** ((np.arange(n) % 29) / 12.0)).astype(np.float32))
+            b.set_value(1, (1.0 + (np.arange(n) % 5)).astype(np.float32))       # op3_ratio per voice: the general kernel
+            b.push_events([(v, v % 100, GATE, 0.9) for v in range(n)])
+            for frames in (256, 100, 256):
+                b.process_block(frames); o.append(b.read_voice_out())
+            outs.append(np.concatenate(o))
+        name = gpu.last_kernel_name()
+        gpu.close()
+    finally:
+        if old is None:
+            os.environ.pop("OSCEN_B200_TMA_STATE", None)
+        else:
+            os.environ["OSCEN_B200_TMA_STATE"] = old
+    assert "fm_voice_kernel" in name, name
+    assert np.abs(outs[0]).max() > 0.01
+    assert np.array_equal(outs[1], outs[0]), float(np.abs(outs[1] - outs[0]).max())

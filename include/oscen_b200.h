@@ -256,6 +256,7 @@ uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g);
    outer declaration's default / ramp), the MIDI chain enables oscen_b200_push_midi / _push_midi_batch, and the
    voice sum is the engine's in-order instance fold.  cfg->voices_per_instance must be N or 0 for such a graph. */
 uint32_t oscen_b200_graph_voices_per_instance(const oscen_b200_graph *g);   /* N of the voice array, 1 if not polyphonic */
+uint32_t oscen_b200_graph_channels(const oscen_b200_graph *g);              /* lanes of the stream output: 1, or 2 for `output out: stream: Frame<2>;` (frame.rs:57-82) */
 int  oscen_b200_graph_has_midi(const oscen_b200_graph *g);
 int  oscen_b200_graph_input_id(const oscen_b200_graph *g, const char *name);          /* >= 0, or OSCEN_B200_E_ARG */
 typedef struct {

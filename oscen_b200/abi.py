@@ -39,7 +39,7 @@ SYMBOLS = [
     "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_timing_drain", "oscen_b200_last_kernel_name", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
     "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
     "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
-    "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_has_midi",
+    "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_channels", "oscen_b200_graph_has_midi",
     "oscen_b200_kind_info", "oscen_b200_graph_kernel_info", "oscen_b200_graph_n_assets", "oscen_b200_graph_asset_id", "oscen_b200_load_asset",
 ]
 
@@ -155,6 +155,8 @@ def load():
     L.oscen_b200_create_from_graph.argtypes = [vp, C.POINTER(Config), C.POINTER(vp)]
     L.oscen_b200_graph_voices_per_instance.argtypes = [vp]
     L.oscen_b200_graph_voices_per_instance.restype = u32
+    L.oscen_b200_graph_channels.argtypes = [vp]
+    L.oscen_b200_graph_channels.restype = u32
     L.oscen_b200_graph_has_midi.argtypes = [vp]
     L.oscen_b200_graph_codegen.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_jit_check.argtypes = [vp, C.c_char_p, C.c_size_t]
@@ -190,6 +192,7 @@ class Graph:
         self.h = h
         self.n_inputs = self.L.oscen_b200_graph_n_inputs(h)
         self.voices_per_instance = self.L.oscen_b200_graph_voices_per_instance(h)    # N of `voices = [Voice::new(); N]`, else 1
+        self.channels = self.L.oscen_b200_graph_channels(h)                          # 2 for a `stream: Frame<2>` output
         self.has_midi = bool(self.L.oscen_b200_graph_has_midi(h))
 
     def close(self):

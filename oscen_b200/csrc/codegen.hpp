@@ -147,7 +147,7 @@ struct Emitter {
            65 536-voice bank (6.9 per SM) are resident in one wave */
         line(0, fmt("extern \"C\" __global__ void __launch_bounds__(kCta, %d) %s(const __grid_constant__ KernelArgs a) {", min_blocks, kernel_name));
         line(1, "__shared__ float tile[kTileF * kTileW];");
-        line(1, "__shared__ float isum[kTileF * kCta];");
+        line(1, g.channels == 2 ? "__shared__ float isum[kTileF * kCta * 2];    /* stereo instance frames */" : "__shared__ float isum[kTileF * kCta];");
         line(1, "const uint32_t n = a.n_voices;");
         line(1, "const uint32_t v = blockIdx.x * kCta + threadIdx.x;");
         line(1, "const bool active = v < n;");
@@ -214,6 +214,10 @@ struct Emitter {
                     line(1, "const float *buf" + std::to_string(i) + " = nullptr; const uint32_t len" + std::to_string(i) + " = 0u; uint32_t " + N(i) + " = 0u;    /* `buf` is not connected: silence */");
                 }
             } break;
+            case T::AmpSource: case T::OscBank:
+                /* 130 / 129 state words: walked in place in their SoA rows (nodes.cuh), not held in registers */
+                line(1, "float *" + N(i) + " = a.state + (size_t)" + base + " * n + vs;");
+                break;
             case T::Up: case T::Down:
                 line(1, edge_type(i) + " " + N(i) + "; " + N(i) + ".load(a.state, " + base + ", n, vs, dyn + " + std::to_string(smem_off) + "u * kCta);");
                 smem_off += edge_smem_floats(nd);
@@ -228,6 +232,11 @@ struct Emitter {
             line(1, "const bool lcg_on = a.ctl->lcg_on != 0u;");
             line(1, "unsigned long long lcg = (unsigned long long)__float_as_uint(a.state[(size_t)(" + f + " + 0u) * n + vs]) |");
             line(1, "                         ((unsigned long long)__float_as_uint(a.state[(size_t)(" + f + " + 1u) * n + vs]) << 32);");
+        }
+        if (g.post_tremolo) {
+            line(1, "/* instance-level tail: voice sum -> Tremolo -> Frame<2>; one LFO phase per instance */");
+            line(1, "const uint32_t my_inst = blockIdx.x * (kCta / a.vpi) + threadIdx.x;");
+            line(1, "float trem_phase = (threadIdx.x < kCta / a.vpi && my_inst < a.n_inst) ? a.inst_state[my_inst] : 0.0f;");
         }
         line(1, "EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);");
         {   /* a gate-off at frame 0 starts from the release length the previous block ended with (AdsrState::r_gate) */
@@ -273,7 +282,7 @@ struct Emitter {
                 line(4, "if (changed) " + N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");");    /* an inner-rate node runs at sr * N */
         }
         bool any_gate = false;
-        for (int i = 0; i < n_nodes; ++i) any_gate |= g.nodes[i].type == T::Adsr && g.nodes[i].gate;
+        for (int i = 0; i < n_nodes; ++i) any_gate |= (g.nodes[i].type == T::Adsr || g.nodes[i].type == T::AmpSource || g.nodes[i].type == T::OscBank) && g.nodes[i].gate;
         line(4, "if (due) {");
         if (any_gate) {
             line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
@@ -281,6 +290,12 @@ struct Emitter {
             line(6, "const float gv = ec.ev[q].scalar;");
             for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr && g.nodes[i].gate)
                 line(6, "adsr_on_gate(" + N(i) + ", gv, " + P(i, 0) + ", " + P(i, 3) + ", " + D(i) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].gate) {
+                if (g.nodes[i].type == T::AmpSource)
+                    line(6, "ampsrc_on_gate(" + N(i) + ", (size_t)n, gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+                if (g.nodes[i].type == T::OscBank)
+                    line(6, "oscbank_on_gate(" + N(i) + ", (size_t)n, gv);    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+            }
             line(5, "}");
         }
         line(5, "ec.advance(ev_end);");
@@ -317,6 +332,14 @@ struct Emitter {
             case T::Delay:
                 line(ind, S(i) + " = delay_process<" + (P_is_const(i, 0) ? "false" : "true") + ", " + (P_is_const(i, 1) ? "false" : "true") + ">(" + N(i) + ", ring" + std::to_string(i) +
                           ", (size_t)n, " + std::to_string(nd.ring_cap) + "u, " + lit(nd.max_delay) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ");" + cm);
+                break;
+            case T::AmpSource:
+                line(ind, "float " + S(i) + "[32]; ampsrc_process(" + N(i) + ", (size_t)n, " + S(i) + ");" + cm + "    /* amplitudes: [f32; 32] */");
+                break;
+            case T::OscBank:
+                if (nd.in[0].node >= 0) line(ind, o + "oscbank_process(" + N(i) + ", (size_t)n, " + P(i, 0) + ", " + SR(i) + ", " + S(nd.in[0].node, nd.in[0].port) + ");" + cm);
+                else { line(ind, "const float z" + std::to_string(i) + "[32] = {};    /* `amplitudes` is not connected: [0.0; 32] */");
+                       line(ind, o + "oscbank_process(" + N(i) + ", (size_t)n, " + P(i, 0) + ", " + SR(i) + ", z" + std::to_string(i) + ");" + cm); }
                 break;
             case T::SamplePlayer: line(ind, o + "sample_player_process(" + N(i) + ", buf" + std::to_string(i) + ", len" + std::to_string(i) + ");" + cm); break;
             case T::Gain: line(ind, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
@@ -386,9 +409,15 @@ struct Emitter {
         line(3, "}");
         line(3, "tile[ff * kTileW + col] = y;");
         line(2, "}");
-        line(2, "tile_flush_mono(a, tile, isum, f0, fe);");
+        if (g.post_tremolo) {
+            auto pid = [&](int k) { return g.post_pid[k] == plan::kNoValue ? std::string("kNoPostInput") : std::to_string(g.post_pid[k]) + "u"; };
+            line(2, "tile_flush_tremolo(a, tile, isum, f0, fe, trem_phase, " + pid(0) + ", " + lit(g.post_cst[0]) + ", " + pid(1) + ", " + lit(g.post_cst[1]) + ");    /* rate, depth */");
+        } else {
+            line(2, "tile_flush_mono(a, tile, isum, f0, fe);");
+        }
         line(1, "}");
         /* ---- registers -> HBM */
+        if (g.post_tremolo) line(1, "if (threadIdx.x < kCta / a.vpi && my_inst < a.n_inst) a.inst_state[my_inst] = trem_phase;");
         line(1, "if (active) {");
         for (int i = 0; i < n_nodes; ++i) {
             const plan::Node &nd = g.nodes[i];

@@ -211,7 +211,7 @@ struct Expr {
 using ExprP = std::unique_ptr<Expr>;
 
 struct InputDecl { Kind kind; std::string name; bool has_def = false; float def = 0.0f; plan::ValueInput spec; Tok at; };
-struct OutputDecl { Kind kind; std::string name; Tok at; };
+struct OutputDecl { Kind kind; std::string name; Tok at; int lanes = 1;   /* `stream: Frame<N>` / `stream: [f32; N]` (parse.rs endpoint types) */ };
 struct NodeDecl { std::string name, type, ctor; std::vector<float> args; bool args_ok = true; bool bare = false; int array = 0; int rate = 0; Tok at; };
 struct Conn { std::string policy; ExprP src, dst; int via = 0; /* 0 none, 1 samples, 2 node */ float via_samples = 0.0f; std::string via_node; Tok at; };
 struct ExternalDecl { std::string name, type; Tok at; };     /* `external sample: AudioAsset;` (parse.rs:447-456) */
@@ -391,7 +391,24 @@ private:
             if (!endpoint_kind(first, d.kind)) { err.at(d.at, "unknown endpoint kind `" + first + "`"); return; }
             if (!ident(d.name, "an output name")) return;
         }
-        if (accept(":")) { err.at(cur(), "typed endpoints (`: [f32; N]`, `: Frame<N>`) are not supported by the node plan: streams are mono f32"); return; }
+        if (accept(":")) {                                   /* endpoint type: `f32`, `Frame<N>`, `[f32; N]` */
+            const Tok at = cur();
+            auto int_lit = [&](int &v) {
+                if (cur().kind != Tok::Num || !cur().is_int) { err.at(cur(), "expected an integer literal"); return false; }
+                v = (int)strtol(cur().s.c_str(), nullptr, 10); ++pos; return true;
+            };
+            if (accept("[")) {
+                std::string el;
+                if (!ident(el, "an element type") || el != "f32" || !expect(";") || !int_lit(d.lanes) || !expect("]")) { if (!err.set) err.at(at, "array-typed endpoints are `[f32; N]`"); return; }
+            } else {
+                std::string ty;
+                if (!ident(ty, "an endpoint type (`f32`, `Frame<N>`, `[f32; N]`)")) return;
+                if (ty == "Frame") { if (!expect("<") || !int_lit(d.lanes) || !expect(">")) return; }
+                else if (ty != "f32") { err.at(at, "unknown endpoint type `" + ty + "` (`f32`, `Frame<N>`, `[f32; N]`)"); return; }
+            }
+            if (d.kind != Kind::Stream) { err.at(at, "only stream endpoints carry a frame type"); return; }
+            if (d.lanes < 1 || d.lanes > 2) { err.at(at, "graph outputs are mono (`f32`, `Frame<1>`) or stereo (`Frame<2>`): the engine's instance and mix buses have 1 or 2 channels"); return; }
+        }
         if (expect(";")) ast.outputs.push_back(std::move(d));
     }
     /* `<name> = <constructor> [* N | / N];` (parse.rs:679-710); constructor = `Type::method(args)`,
@@ -561,7 +578,8 @@ private:
 };
 
 /* -------------------------------------------------------------------- node registry -- */
-struct Endpoint { const char *name; Kind kind; bool is_out; int slot; /* in: stream index or value slot; out: port */ int standin; float def; };
+struct Endpoint { const char *name; Kind kind; bool is_out; int slot; /* in: stream index or value slot; out: port */ int standin; float def;
+                  int width = 1;   /* lanes of a stream endpoint: `[f32; N]` fields are N wide (frame.rs) */ };
 struct TypeInfo {
     const char *type;
     std::vector<Endpoint> eps;
@@ -599,6 +617,13 @@ inline const TypeInfo *type_info(const std::string &type) {
                        {"output_b", Kind::Stream, true, 1, -1, 0}}, false},
         {"HardClip", {{"input", Kind::Stream, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, false},
         {"SamplePlayer", {{"buf", Kind::Asset, false, 0, -1, 0}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
+        /* examples/electric-piano/src/electric_piano_voice.rs:74-100,173-222: `amplitudes` is `[f32; NUM_HARMONICS]` on both sides */
+        {"AmplitudeSource", {{"frequency", Kind::Value, false, 0, -1, 440.0f}, {"gate", Kind::Event, false, 0, -1, 0}, {"brightness", Kind::Value, false, 1, -1, 30.0f},
+                             {"velocity_scaling", Kind::Value, false, 2, -1, 50.0f}, {"decay_rate", Kind::Value, false, 3, -1, 90.0f},
+                             {"harmonic_decay", Kind::Value, false, 4, -1, 70.0f}, {"key_scaling", Kind::Value, false, 5, -1, 50.0f},
+                             {"release_rate", Kind::Value, false, 6, -1, 40.0f}, {"amplitudes", Kind::Stream, true, 0, -1, 0, 32}}, true},
+        {"OscillatorBank", {{"frequency", Kind::Value, false, 0, -1, 440.0f}, {"gate", Kind::Event, false, 0, -1, 0},
+                            {"amplitudes", Kind::Stream, false, 0, -1, 0, 32}, {"output", Kind::Stream, true, 0, -1, 0}}, true},
     };
     for (const TypeInfo &t : reg) if (type == t.type) return &t;
     return nullptr;
@@ -677,6 +702,7 @@ public:
             if (names.count(d.name)) { err.at(d.at, "duplicate name `" + d.name + "`"); return false; }
             if (d.kind != Kind::Stream) { err.at(d.at, std::string("the node plan renders stream outputs only (`") + d.name + "` is " + kind_name(d.kind) + ")"); return false; }
             if (!g.output_name.empty()) { err.at(d.at, "the node plan renders one stream output per graph (`" + g.output_name + "` is already declared)"); return false; }
+            if (d.lanes != 1) { err.at(d.at, "a `Frame<2>` output needs a node that produces one: in this library that is the `Tremolo` after a polyphonic graph's voice sum"); return false; }
             names[d.name] = 'o'; g.output_name = d.name;
         }
         if (g.output_name.empty()) { Tok t; err.at(t, "graph declares no stream output"); return false; }
@@ -732,7 +758,7 @@ private:
             g.inner_log2 = rate_log2;
         }
         const TypeInfo *ti = type_info(d.type);
-        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (known: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, Oscillator, LP18Filter, IirLowpass, Delay, SamplePlayer, Gain, AddValue, Mixer, Crossfade, HardClip)"); return false; }
+        if (!ti) { err.at(d.at, "unknown node type `" + d.type + "` (known: AdsrEnvelope, FmOperator, TptFilter, PolyBlepOscillator, Oscillator, LP18Filter, IirLowpass, Delay, SamplePlayer, Gain, AddValue, Mixer, Crossfade, HardClip, AmplitudeSource, OscillatorBank)"); return false; }
         if (!d.args_ok) { err.at(d.at, "constructor arguments of `" + d.name + "` must be numeric literals"); return false; }
         plan::Node n{};
         n.name = d.name; n.gate = false; n.rate_log2 = rate_log2;
@@ -782,6 +808,8 @@ private:
         else if (t == "Crossfade") { n.type = plan::NodeType::Crossfade; ok = ctor("new", 0); }
         else if (t == "HardClip") { n.type = plan::NodeType::HardClip; ok = ctor("new", 0); }
         else if (t == "SamplePlayer") { n.type = plan::NodeType::SamplePlayer; ok = ctor("new", 0); }
+        else if (t == "AmplitudeSource") { n.type = plan::NodeType::AmpSource; ok = ctor("new", 0); }
+        else if (t == "OscillatorBank") { n.type = plan::NodeType::OscBank; ok = ctor("new", 0); }
         if (err.set) return false;
         if (!ok) { err.at(d.at, "unknown constructor `" + d.type + "::" + d.ctor + "`"); return false; }
         names[d.name] = 'n'; node_id[d.name] = (int)g.nodes.size();
@@ -789,6 +817,9 @@ private:
         return true;
     }
 
+    int width_of(const Operand &o) const {
+        return (o.k == Operand::Stream && o.s.node >= 0) ? plan::stream_width(g.nodes[o.s.node].type, o.s.port) : 1;
+    }
     const Endpoint *find_ep(int node, const std::string &name) const {
         for (const Endpoint &ep : info[node]->eps) if (name == ep.name) return &ep;
         return nullptr;
@@ -894,6 +925,7 @@ private:
             Operand l, r; bool le, re;
             if (!source(*e.a, l, le) || !source(*e.b, r, re)) return false;
             if (le || re) { err.at(e.at, "event endpoints cannot take part in arithmetic"); return false; }
+            if (width_of(l) > 1 || width_of(r) > 1) { err.at(e.at, "an array-typed stream (`[f32; N]`) connects one output to one input directly: no arithmetic on it"); return false; }
             out = binary(e.op, l, r, text_of(e), e.at); return !err.set;
         }
         case Expr::Method: {
@@ -901,6 +933,7 @@ private:
             Operand x; bool xe;
             if (!source(*e.a, x, xe)) return false;
             if (xe) { err.at(e.at, "event endpoints cannot take part in arithmetic"); return false; }
+            if (width_of(x) > 1) { err.at(e.at, "an array-typed stream (`[f32; N]`) connects one output to one input directly: no arithmetic on it"); return false; }
             struct { const char *m; O op; size_t n_args; } ms[] = {{"tanh", O::Tanh, 0}, {"abs", O::Abs, 0}, {"clamp", O::Clamp, 2}, {"min", O::MinV, 1}, {"max", O::MaxV, 1},
                                                                    {"sqrt", O::Sqrt, 0}, {"sin", O::Sin, 0}, {"cos", O::Cos, 0}, {"exp", O::Exp, 0}};
             for (auto &m : ms) if (e.name == m.m) {
@@ -960,6 +993,11 @@ private:
         }
         const Kind sk = src_event ? Kind::Event : src.kind();
         const Expr &d = *c.dst;
+        /* array-typed streams (`[f32; N]`): a plain edge between two endpoints of the same width — no arithmetic, no fan-in,
+           no resampler, no delay (the reference's Frame arithmetic is element-wise; nothing in its graphs uses it on arrays) */
+        const int sw = width_of(src);
+        auto width_name = [](int w) { return w == 1 ? std::string("f32") : "[f32; " + std::to_string(w) + "]"; };
+        if (sw > 1 && (c.src->k != Expr::Field || c.via)) { err.at(c.at, "an array-typed stream (`" + width_name(sw) + "`) connects one output to one input directly"); return false; }
         auto mismatch = [&](Kind dk) {
             err.at(c.at, std::string("Type mismatch in connection: source is ") + kind_name(sk) + " but destination expects " + kind_name(dk));
             return false;
@@ -973,6 +1011,7 @@ private:
             }
             if (sk == Kind::Event) return mismatch(Kind::Stream);
             if (src.fb) { err.at(c.at, "a `-> [..] ->` edge must end at a node input"); return false; }
+            if (sw > 1) { err.at(c.at, "Type mismatch in connection: source is " + width_name(sw) + " but the graph output is f32"); return false; }
             if (!cross_rate(c, src, 0, d.name)) return false;
             out_terms.push_back(src);
             return true;
@@ -998,6 +1037,14 @@ private:
             return true;
         default:
             if (sk == Kind::Event) return mismatch(Kind::Stream);
+            if (sw != ep->width) {
+                if (sk != Kind::Stream) return mismatch(Kind::Stream);
+                err.at(c.at, "Type mismatch in connection: source is " + width_name(sw) + " but `" + d.a->name + "." + d.name + "` expects " + width_name(ep->width)); return false;
+            }
+            if (sw > 1) {
+                if (!in_terms[nid][ep->slot].empty()) { err.at(c.at, "fan-in summing supports only scalar stream sources; `" + d.a->name + "." + d.name + "` is " + width_name(sw)); return false; }
+                if (rate_of(src) != g.nodes[nid].rate_log2) { err.at(c.at, "an array-typed stream cannot cross a rate boundary"); return false; }
+            }
             if (!cross_rate(c, src, g.nodes[nid].rate_log2, d.a->name + "." + d.name)) return false;
             in_terms[nid][ep->slot].push_back(src);
             return true;
@@ -1367,15 +1414,20 @@ inline bool is_polyphonic(const Ast &top) {
     return false;
 }
 inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::Graph &g, Error &err) {
-    const NodeDecl *voices = nullptr, *handlers = nullptr, *alloc = nullptr, *parser = nullptr;
+    const NodeDecl *voices = nullptr, *handlers = nullptr, *alloc = nullptr, *parser = nullptr, *post = nullptr;
     for (const NodeDecl &d : top.nodes) {
         if (d.rate) { err.at(d.at, "node rates on the nodes of a polyphonic graph are not supported (oversample inside the voice graph)"); return false; }
         if (d.type == "MidiParser" && !d.array) { parser = &d; continue; }
+        /* the instance-level tail: ONE Tremolo between the voice sum and a Frame<2> output (examples/electric-piano/src/main.rs:58,88-96) */
+        if (d.type == "Tremolo" && !d.array && !post) {
+            if (d.ctor != "new" || !d.args.empty()) { err.at(d.at, "Tremolo is constructed with `Tremolo::new()`"); return false; }
+            post = &d; continue;
+        }
         if (d.type == "VoiceAllocator" && !d.array) { alloc = &d; continue; }
         if (d.type == "MidiVoiceHandler" && d.array) { handlers = &d; continue; }
         if (d.array && find_graph(all, d.type) && !voices) { voices = &d; continue; }
         err.at(d.at, d.array ? "node array `" + d.name + "`: `" + d.type + "` is not a graph of this text (a polyphonic graph holds ONE array of a voice graph, plus MidiParser / VoiceAllocator / [MidiVoiceHandler; N])"
-                             : "node `" + d.name + "`: a polyphonic graph holds one voice array plus MidiParser / VoiceAllocator / [MidiVoiceHandler; N] only");
+                             : "node `" + d.name + "`: a polyphonic graph holds one voice array plus MidiParser / VoiceAllocator / [MidiVoiceHandler; N] and at most one Tremolo after the voice sum");
         return false;
     }
     if (!voices) { Tok t; err.at(t, "polyphonic graph without a voice array"); return false; }
@@ -1403,10 +1455,17 @@ inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::
         if (d.kind == Kind::Event) outer_midi = d.name;
         else if (d.kind != Kind::Value) { err.at(d.at, "a polyphonic graph takes value inputs (broadcast to the voices) and the MIDI event input"); return false; }
     }
+    std::vector<std::string> event_outs;                  /* `output note_on_out: event;`: accepted, nothing on the device consumes them */
+    int out_lanes = 1;
     for (const OutputDecl &d : top.outputs) {
+        if (d.kind == Kind::Event) { event_outs.push_back(d.name); continue; }
         if (d.kind != Kind::Stream || !outer_out.empty()) { err.at(d.at, "a polyphonic graph has one stream output (the voice sum)"); return false; }
-        outer_out = d.name;
+        outer_out = d.name; out_lanes = d.lanes;
+        if (d.lanes == 2 && !post) { err.at(d.at, "a `Frame<2>` output needs a node that produces one: `Tremolo` after the voice sum"); return false; }
+        if (d.lanes == 1 && post) { err.at(d.at, "Type mismatch in connection: `Tremolo.output` is Frame<2> but `" + d.name + "` is f32 (declare `output " + d.name + ": stream: Frame<2>;`)"); return false; }
     }
+    g.post_tremolo = post != nullptr;
+    g.channels = (uint32_t)out_lanes;
     auto voice_value_id = [&](const std::string &name) -> int {
         for (size_t i = 0; i < g.inputs.size(); ++i) if (g.inputs[i].name == name) return (int)i;
         return -1;
@@ -1415,15 +1474,45 @@ inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::
         if (!nd || e.k != Expr::Field || e.a->k != Expr::Ident || e.a->name != nd->name) return false;
         field = e.name; return true;
     };
-    bool freq_wired = false, gate_wired = false, out_wired = false;
+    bool freq_wired = false, gate_wired = false, out_wired = false, post_in = false, post_out = false;
     for (const Conn &c : top.conns) {
         if (c.via) { err.at(c.at, "feedback edges are not supported in a polyphonic graph"); return false; }
         std::string sf, df;
         const Expr &s = *c.src, &d = *c.dst;
         /* voices.<out> -> out : the in-order voice sum (the engine's instance fold) */
-        if (is_node(s, voices, sf) && d.k == Expr::Ident && d.name == outer_out) {
+        if (!post && is_node(s, voices, sf) && d.k == Expr::Ident && d.name == outer_out) {
             if (sf != g.output_name) { err.at(s.at, "`" + voice.name + "` has no stream output `" + sf + "`"); return false; }
             out_wired = true; continue;
+        }
+        /* voices.<out> -> tremolo.input (the voice sum, stream fan-in of an array source: emit_node.rs:463-466), tremolo.output -> out,
+           value -> tremolo.rate / .depth (instance-level value inputs: they get ids after the voice's own) */
+        if (post && is_node(d, post, df)) {
+            if (df == "input") {
+                if (!is_node(s, voices, sf) || sf != g.output_name) { err.at(s.at, "only the voice sum `" + voices->name + "." + g.output_name + "` can feed `" + post->name + ".input`"); return false; }
+                post_in = true; continue;
+            }
+            const int k = df == "rate" ? 0 : df == "depth" ? 1 : -1;
+            if (k < 0) { err.at(d.at, "node `" + post->name + "` has no endpoint `" + df + "` (Tremolo: input, rate, depth -> output)"); return false; }
+            if (s.k == Expr::Literal) { g.post_pid[k] = plan::kNoValue; g.post_cst[k] = s.lit; continue; }
+            if (s.k == Expr::Ident && outer_in.count(s.name) && outer_in[s.name]->kind == Kind::Value) {
+                if (g.inputs.size() >= 28) { err.at(s.at, "more than 28 value inputs (OSCEN_B200_MAX_INPUTS)"); return false; }
+                const InputDecl &od = *outer_in[s.name];
+                plan::ValueInput spec = od.spec; spec.name = s.name;
+                if (!od.has_def) spec.def = 0.0f;
+                g.post_pid[k] = (uint32_t)g.inputs.size();
+                g.inputs.push_back(spec);
+                continue;
+            }
+            err.at(s.at, "only a value input of the outer graph or a literal can feed `" + post->name + "." + df + "`"); return false;
+        }
+        if (post && is_node(s, post, sf)) {
+            if (sf != "output" || d.k != Expr::Ident || d.name != outer_out) { err.at(c.at, "`" + post->name + ".output` connects to the graph's stream output"); return false; }
+            post_out = true; continue;
+        }
+        /* parser.note_on / note_off -> an event output of the graph: a host-side tap with no consumer in the engine */
+        if (is_node(s, parser, sf) && d.k == Expr::Ident && std::find(event_outs.begin(), event_outs.end(), d.name) != event_outs.end()) {
+            if (sf != "note_on" && sf != "note_off") { err.at(s.at, "MidiParser has no output `" + sf + "` (note_on, note_off)"); return false; }
+            continue;
         }
         if (is_node(d, voices, df)) {
             /* handlers.frequency / handlers.gate -> voices.<input> */
@@ -1467,9 +1556,13 @@ inline bool lower_polyphonic(const Ast &top, const std::vector<Ast> &all, plan::
         err.at(c.at, "this connection is not part of the polyphonic pattern (MIDI chain, broadcast `value -> voices.input`, `voices.output -> out`)");
         return false;
     }
+    if (post) {
+        if (!post_in || !post_out) { err.at(post->at, "`" + post->name + "` must sit between the voice sum and the output (`" + voices->name + "." + g.output_name + " -> " + post->name + ".input; " + post->name + ".output -> " + outer_out + ";`)"); return false; }
+        out_wired = true;
+    }
     if (!out_wired) { Tok t; err.at(t, "`" + voices->name + "." + g.output_name + "` is not connected to the output"); return false; }
     if (g.midi && !(freq_wired && gate_wired)) { Tok t; err.at(t, "the MIDI front is declared but `" + handlers->name + ".frequency` / `.gate` are not connected to the voices"); return false; }
-    g.output_name = outer_out + " <- sum of " + std::to_string(g.vpi) + " x " + voice_name + "." + g.output_name;
+    g.output_name = outer_out + (post ? " <- Tremolo (Frame<2>)" : "") + " <- sum of " + std::to_string(g.vpi) + " x " + voice_name + "." + g.output_name;
     return true;
 }
 

@@ -312,6 +312,12 @@ std::vector<uint32_t> initial_state(uint32_t kind, float sr, const plan::Graph *
                 const uint32_t b = nd.state_base;
                 s[b + 0] = f.b0; s[b + 1] = f.b1; s[b + 2] = f.b2; s[b + 3] = f.a1; s[b + 4] = f.a2;       /* v1 v2 frame_counter = 0 */
             }
+            else if (nd.type == plan::NodeType::AmpSource) {
+                s[nd.state_base + AS_STEP] = 64.0f;              /* interpolation_step: INTERPOLATION_STEPS (electric_piano_voice.rs:218) */
+            }
+            else if (nd.type == plan::NodeType::OscBank) {        /* oscillators / multipliers: Complex::one() (electric_piano_voice.rs:104-105) */
+                for (uint32_t i = 0; i < kEpHarmonics; ++i) { s[nd.state_base + OB_ORE + i] = 1.0f; s[nd.state_base + OB_MRE + i] = 1.0f; }
+            }
             else if (nd.type == plan::NodeType::Lp18) {
                 Lp18State f; lp18_init(f, nd.init[0], nd.init[1], sr * (float)(1 << nd.rate_log2));
                 const uint32_t b = nd.state_base;
@@ -728,6 +734,14 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         else if (pg.inner_log2 > 0) {
             g_create_error = "PLAN_NODES: a multirate graph (`* N` nodes) runs as a generated kernel: set plan = OSCEN_B200_PLAN_FUSED"; return OSCEN_B200_E_ARG;
         }
+        if (cfg->plan == OSCEN_B200_PLAN_NODES) {
+            bool fused_only = pg.post_tremolo;
+            for (const plan::Node &nd : pg.nodes) fused_only = fused_only || plan::fused_only(nd.type);
+            if (fused_only) {
+                g_create_error = "PLAN_NODES: array-typed streams (`[f32; N]`) and the instance-level Tremolo -> Frame<2> tail exist in the generated kernel only (the node plan's stream buffers are one f32 per voice): set plan = OSCEN_B200_PLAN_FUSED";
+                return OSCEN_B200_E_ARG;
+            }
+        }
     } else if (cfg->plan == OSCEN_B200_PLAN_NODES) {
         std::string perr;
         if (!plan::for_kind(cfg->graph_kind, pg)) {
@@ -756,7 +770,7 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
         e->lcg_field = e->has_stream_in ? lcg_field(kind) : 0u;
     }
     e->n_inst = n / cfg->voices_per_instance;
-    e->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2 : 1;
+    e->channels = kind == OSCEN_B200_GRAPH_EPIANO ? 2 : (custom ? pg.channels : 1);
     e->n_cta = (n + kCta - 1) / kCta;
     e->n_cta_mix = e->n_cta;
     int rc = [&]() -> int {
@@ -857,6 +871,7 @@ int oscen_b200_graph_describe(const oscen_b200_graph *g, char *dst, size_t cap) 
     return (int)g->p.launches.size();
 }
 uint32_t oscen_b200_graph_voices_per_instance(const oscen_b200_graph *g) { return g ? (g->g.vpi ? g->g.vpi : 1u) : 0u; }
+uint32_t oscen_b200_graph_channels(const oscen_b200_graph *g) { return g ? g->g.channels : 0u; }
 int oscen_b200_graph_has_midi(const oscen_b200_graph *g) { return g && g->g.midi ? 1 : 0; }
 uint32_t oscen_b200_graph_n_inputs(const oscen_b200_graph *g) { return g ? (uint32_t)g->g.inputs.size() : 0u; }
 uint32_t oscen_b200_graph_n_assets(const oscen_b200_graph *g) { return g ? (uint32_t)g->g.assets.size() : 0u; }

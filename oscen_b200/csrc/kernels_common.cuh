@@ -114,6 +114,55 @@ OSC_D void state_stage_out(const float *stage, float *gstate, uint32_t n_fields,
 OSC_D uint32_t tile_col(uint32_t t, uint32_t vpi) { return vpi > 1u ? t + t / vpi : t; }
 
 /*
+ * Flush one tile of per-voice outputs of a polyphonic graph whose voice sum runs through ONE instance-level Tremolo into a
+ * Frame<2> output (examples/electric-piano/src/main.rs:88-96, tremolo.rs:41-61): per instance, the in-order voice sum, then
+ * the tremolo frame by frame (its LFO phase is the instance's one state word), then
+ *   inst_out[f][instance][2], mix_partial[cta][f][2] (instances folded in index order).
+ * rate / depth: a graph value input (read at the instance's first voice, or from the ramp table) or the constructor's
+ * literal.  tile: [kTileF][kTileW], isum: [kTileF][kCta][2].  All threads call.
+ */
+constexpr uint32_t kNoPostInput = 0xFFFFFFFFu;
+OSC_D void tile_flush_tremolo(const KernelArgs &a, const float *tile, float *isum, uint32_t f0, uint32_t fe, float &trem_phase,
+                              uint32_t rate_pid, float rate_cst, uint32_t depth_pid, float depth_cst) {
+    const uint32_t vpi = a.vpi, n = a.n_voices;
+    const uint32_t ipc = kCta / vpi;
+    const uint32_t ramp_mask = a.ctl->ramp_mask;
+    __syncthreads();
+    if (threadIdx.x < ipc) {
+        const uint32_t i = threadIdx.x;
+        const uint32_t inst = blockIdx.x * ipc + i;
+        const uint32_t c0 = tile_col(i * vpi, vpi);
+        const uint32_t v_first = min(inst * vpi, n - 1u);           /* instance-level inputs: the instance's first voice */
+        const float rate0 = rate_pid == kNoPostInput ? rate_cst : a.pv[(size_t)rate_pid * n + v_first];
+        const float depth0 = depth_pid == kNoPostInput ? depth_cst : a.pv[(size_t)depth_pid * n + v_first];
+        const bool rate_ramped = rate_pid != kNoPostInput && ((ramp_mask >> rate_pid) & 1u);
+        const bool depth_ramped = depth_pid != kNoPostInput && ((ramp_mask >> depth_pid) & 1u);
+        for (uint32_t ff = 0; ff < fe; ++ff) {
+            const float rate = rate_ramped ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + rate_pid] : rate0;
+            const float depth = depth_ramped ? a.ptab[(size_t)(f0 + ff) * kMaxInputs + depth_pid] : depth0;
+            const float *row = tile + ff * kTileW;
+            float s = 0.0f;
+            for (uint32_t j = 0; j < vpi; ++j) s = s + row[c0 + j];
+            float l, r;
+            tremolo_process(trem_phase, s, rate, depth, a.u.sr, l, r);
+            isum[(ff * kCta + i) * 2 + 0] = l; isum[(ff * kCta + i) * 2 + 1] = r;
+            if (a.inst_out != nullptr && inst < a.n_inst) {
+                a.inst_out[((size_t)(f0 + ff) * a.n_inst + inst) * 2 + 0] = l;
+                a.inst_out[((size_t)(f0 + ff) * a.n_inst + inst) * 2 + 1] = r;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < fe * 2u; t += kCta) {       /* mix partial: in-order over the CTA's instances */
+        const uint32_t ff = t >> 1, c = t & 1u;
+        float s = 0.0f;
+        for (uint32_t i = 0; i < ipc; ++i) s = s + isum[(ff * kCta + i) * 2 + c];
+        a.mix_partial[((size_t)blockIdx.x * kMaxBlock + f0 + ff) * 2 + c] = s;
+    }
+    __syncthreads();
+}
+
+/*
  * Flush one tile of per-voice outputs (mono):
  *   inst_out[f][instance] = sum over the instance's voices in index order (sequential f32
  *     fold == `.iter().map(|n| n.audio_out).sum()`, codegen/emit_node.rs:463-466)

@@ -49,6 +49,9 @@ enum class NodeType : uint8_t {
     Up,            /* cross-rate stream edge outer -> inner (`* N` destination): StreamUpsampler of `policy`   */
     Down,          /* cross-rate stream edge inner -> outer: StreamDownsampler of `policy` (generated kernels only) */
     SamplePlayer,  /* SamplePlayer (mono): loops the buffer loaded into asset slot `asset` (`external s: AudioAsset; s -> p.buf`) */
+    AmpSource,     /* electric-piano AmplitudeSource        value: frequency brightness velocity_scaling decay_rate harmonic_decay
+                      key_scaling release_rate; event: gate; output `amplitudes`: an ARRAY-typed stream, [f32; 32] per frame */
+    OscBank,       /* electric-piano OscillatorBank         stream: amplitudes ([f32; 32]); value: frequency; event: gate */
 };
 enum : int { kPolicySinc = 0, kPolicySincIir = 1, kPolicyLinear = 2, kPolicyLatch = 3 };   /* == OSCEN_B200_POLICY_* */
 
@@ -94,6 +97,11 @@ struct Node {
     float max_delay = 0.0f;          /* Delay: the reference ring's capacity - 1 (the clamp of apply_parameter_updates) */
     int asset = kNone;               /* SamplePlayer: index of the `external` asset slot connected to `buf` (kNone: never loaded, silent) */
 };
+/* lanes of a node's output stream: 1 for `f32`, N for an array-typed endpoint `[f32; N]` (oscen-lib/src/frame.rs, `#[output(stream)]
+   pub amplitudes: [f32; NUM_HARMONICS]`); a wide stream only connects endpoints of the same width */
+inline int stream_width(NodeType t, int /*port*/) { return t == NodeType::AmpSource ? 32 : 1; }
+/* node types that exist in the generated (fused) kernel only: their streams / state do not fit the node plan's one-f32-per-voice buffers */
+inline bool fused_only(NodeType t) { return t == NodeType::AmpSource || t == NodeType::OscBank; }
 
 /* a value input of a DSL-compiled graph (`input cutoff: value = 3000.0 [20.0..20000.0, log, ramp: 1323];`) */
 struct ValueInput {
@@ -119,6 +127,14 @@ struct Graph {
     uint32_t midi_freq_input = 0;    /* the voice input `voice_handlers.frequency` is connected to */
     std::vector<std::pair<std::string, uint32_t>> aliases;   /* outer value-input name -> voice input id (broadcast edges) */
     std::vector<std::string> assets; /* `external NAME: AudioAsset;` slots in declaration order (engine: oscen_b200_load_asset) */
+    /* instance-level tail of a polyphonic graph: `voices.output -> tremolo.input; tremolo.output -> out` with
+       `output out: stream: Frame<2>` (examples/electric-piano/src/main.rs:33-97).  The voice sum of an instance runs through
+       ONE Tremolo (tremolo.rs:5-61) whose output is a stereo frame: the engine's instance / mix outputs get 2 channels and
+       one state word per instance (the LFO phase).  pid / cst: rate, depth (a graph value input, or the constructor's 5.0 / 0.5) */
+    bool post_tremolo = false;
+    uint32_t post_pid[2] = {kNoValue, kNoValue};
+    float post_cst[2] = {5.0f, 0.5f};
+    uint32_t channels = 1;           /* lanes of the graph's stream output: 1, or 2 for `stream: Frame<2>` */
 };
 
 struct Launch {
@@ -150,6 +166,8 @@ inline uint32_t n_state_words(const Node &nd) {
     case NodeType::OscSine: case NodeType::OscSquare: case NodeType::OscSaw: return 1;
     case NodeType::Delay: return 3u + nd.ring_cap;   /* write_pos frame_counter output + the ring */
     case NodeType::SamplePlayer: return 1;    /* playhead */
+    case NodeType::AmpSource: return 130;     /* current / target / decay / release [32] + released + interpolation_step (nodes.cuh AS_*) */
+    case NodeType::OscBank: return 129;       /* oscillators / multipliers re, im [32] + last_frequency (nodes.cuh OB_*) */
     default: return 0;
     }
 }
@@ -226,6 +244,8 @@ inline const char *type_name(NodeType t) {
     case NodeType::Up: return "UpEdge";
     case NodeType::Down: return "DownEdge";
     case NodeType::SamplePlayer: return "SamplePlayer";
+    case NodeType::AmpSource: return "AmplitudeSource";
+    case NodeType::OscBank: return "OscillatorBank";
     case NodeType::Lp18: return "LP18Filter";
     case NodeType::Gain: return "Gain";
     case NodeType::AddValue: return "AddValue";

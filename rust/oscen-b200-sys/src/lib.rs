@@ -125,6 +125,7 @@ extern "C" {
     pub fn oscen_b200_graph_describe(g: *const oscen_b200_graph, dst: *mut c_char, cap: usize) -> c_int;
     pub fn oscen_b200_graph_n_inputs(g: *const oscen_b200_graph) -> u32;
     pub fn oscen_b200_graph_voices_per_instance(g: *const oscen_b200_graph) -> u32;
+    pub fn oscen_b200_graph_channels(g: *const oscen_b200_graph) -> u32;
     pub fn oscen_b200_graph_has_midi(g: *const oscen_b200_graph) -> c_int;
     pub fn oscen_b200_graph_input_id(g: *const oscen_b200_graph, name: *const c_char) -> c_int;
     pub fn oscen_b200_graph_input_info(g: *const oscen_b200_graph, input_id: u32, out: *mut oscen_b200_input_info) -> c_int;

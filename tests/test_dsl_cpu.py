@@ -377,6 +377,53 @@ def test_polyphonic_graph_errors(mutation, frag):
     assert frag in str(ei.value), str(ei.value)
 
 
+# ------------------------------------------------------------------ array-typed streams, Frame<2>, the instance-level tail
+def test_electric_piano_graph_compiles_from_the_reference_text():
+    """examples/electric-piano: `amplitudes: [f32; 32]` between AmplitudeSource and OscillatorBank (electric_piano_voice.rs:362-402),
+    16 voices -> sum -> Tremolo -> `output out: stream: Frame<2>` with event outputs tapped off the parser (main.rs:33-97)"""
+    g = abi.Graph(text("electric_piano.graph"))
+    assert g.voices_per_instance == 16 and g.has_midi and g.channels == 2
+    d = g.describe()
+    assert "graph ElectricPianoGraph" in d and "state words per voice: 259" in d
+    assert "out <- Tremolo (Frame<2>) <- sum of 16 x ElectricPianoVoiceNode.output" in d
+    # the voice's inputs keep the hand-written kernel's ids (OSCEN_B200_EP_*); the tremolo's follow them
+    assert [g.input_id(k) for k in ("frequency", "brightness", "velocity_scaling", "decay_rate", "harmonic_decay", "key_scaling",
+                                    "release_rate", "vibrato_intensity", "vibrato_speed")] == list(range(9))
+    assert g.input_info(7)["default"] == pytest.approx(0.3) and g.input_info(8)["default"] == 5.0
+    assert [l.split(":")[1].split("[")[0].strip() for l in g.launches()] == ["AmplitudeSource", "OscillatorBank"]
+    src = g.codegen()
+    assert "float s0[32]; ampsrc_process(" in src and "oscbank_process(" in src and "tile_flush_tremolo(a, tile, isum, f0, fe, trem_phase, 8u," in src
+    assert g.jit_check() > 10000
+    voice = abi.Graph(text("electric_piano.graph"), name="ElectricPianoVoiceNode")      # the voice graph alone: mono, 1 voice per instance
+    assert voice.channels == 1 and voice.voices_per_instance == 1 and voice.jit_check() > 10000
+    with pytest.raises(abi.EngineError) as ei:                                            # refused before any device is touched
+        abi.Engine.from_graph(g, 64, plan=abi.PLAN_NODES)
+    assert "array-typed streams" in str(ei.value) and "PLAN_FUSED" in str(ei.value)
+
+
+@pytest.mark.parametrize("mutation,frag", [
+    (("amplitude_source.amplitudes -> oscillator_bank.amplitudes;", "amplitude_source.amplitudes -> output;"), "source is [f32; 32] but the graph output is f32"),
+    (("amplitude_source.amplitudes -> oscillator_bank.amplitudes;", "oscillator_bank.output -> oscillator_bank.amplitudes;"), "source is f32 but `oscillator_bank.amplitudes` expects [f32; 32]"),
+    (("amplitude_source.amplitudes -> oscillator_bank.amplitudes;", "amplitude_source.amplitudes * 2.0 -> oscillator_bank.amplitudes;"), "connects one output to one input directly"),
+    (("amplitude_source.amplitudes -> oscillator_bank.amplitudes;",
+      "amplitude_source.amplitudes -> oscillator_bank.amplitudes; amplitude_source.amplitudes -> oscillator_bank.amplitudes;"), "fan-in summing supports only scalar"),
+    (("output out: stream: Frame<2>;", "output out: stream;"), "`Tremolo.output` is Frame<2> but `out` is f32"),
+    (("output out: stream: Frame<2>;", "output out: stream: Frame<3>;"), "mono (`f32`, `Frame<1>`) or stereo (`Frame<2>`)"),
+    (("output out: stream: Frame<2>;", "output out: stream: Complex;"), "unknown endpoint type `Complex`"),
+    (("tremolo.output -> out;", ""), "must sit between the voice sum and the output"),
+    (("vibrato_speed -> tremolo.rate;", "vibrato_speed -> tremolo.speed;"), "has no endpoint `speed`"),
+    (("tremolo = crate::tremolo::Tremolo::new();", "tremolo = crate::tremolo::Tremolo::new(); chorus = crate::tremolo::Tremolo::new();"), "at most one Tremolo"),
+    (("midi_parser.note_on -> note_on_out;", "midi_parser.velocity -> note_on_out;"), "MidiParser has no output `velocity`"),
+    (("output output: stream;", "output output: stream: Frame<2>;"), "needs a node that produces one"),
+])
+def test_array_stream_and_frame_output_errors(mutation, frag):
+    src = text("electric_piano.graph")
+    assert mutation[0] in src
+    with pytest.raises(abi.GraphCompileError) as ei:
+        abi.Graph(src.replace(mutation[0], mutation[1]))
+    assert frag in str(ei.value), str(ei.value)
+
+
 # ------------------------------------------------------------------ feedback edges and the rest of the node library
 FEEDBACK = """
     name: Echo;

@@ -281,6 +281,37 @@ def test_host_executed_electric_piano_kernel_matches_oracle_voices_and_stereo_in
     assert np.array_equal(vh, vr) and np.array_equal(ih, ir)
 
 
+def test_host_executed_electric_piano_graph_from_its_own_dsl_text_matches_oracle():
+    """ElectricPianoGraph compiled from the reference's two `graph!` blocks (tests/graphs/electric_piano.graph: an array-typed
+    [f32; 32] stream between AmplitudeSource and OscillatorBank, 16 voices -> sum -> Tremolo -> Frame<2>): the GENERATED
+    kernel, executed on the host, against the oracle's electric-piano bank — per-voice output and stereo instance output
+    bit-identical, same script as the hand-written kernel's test above"""
+    n, vpi = 80, 16
+    ref, host = O.OracleBank(O.K_EPIANO, n, vpi), HostEngine(text("electric_piano.graph"), n)
+    assert host.vpi == vpi and host.channels == 2
+
+    def script(b):
+        out_v, out_i = [], []
+        freqs = (110.0 * 2.0 ** ((np.arange(n) % 29) / 12.0)).astype(np.float32)
+        ev = []
+        for v in range(0, n, 3):
+            ev.append((v, 2 + v % 40, 0, float(freqs[v])))
+            ev.append((v, 2 + v % 40, GATE, 0.4 + 0.005 * v))
+        b.push_events(ev)
+        for _ in range(2):
+            b.process_block(200); out_v.append(b.read_voice_out()); out_i.append(b.read_instance_out())
+        b.push_events([(v, 5 + v % 7, GATE, 0.0) for v in range(0, n, 6)])
+        b.set_value(3, 60.0)
+        b.set_value_ramp(7, 0.8, 150)
+        for _ in range(2):
+            b.process_block(120); out_v.append(b.read_voice_out()); out_i.append(b.read_instance_out())
+        return np.concatenate(out_v), np.concatenate(out_i)
+
+    (vr, ir), (vh, ih) = script(ref), script(host)
+    assert np.abs(ir).max() > 1e-3 and np.abs(ir[..., 0] - ir[..., 1]).max() > 1e-6
+    assert np.array_equal(vh, vr) and np.array_equal(ih, ir)
+
+
 @pytest.mark.parametrize("kind", range(7, 20))
 def test_host_executed_clip_kernels_match_oracle(kind):
     """kernel_resample.cuh: ClipRef and the 12 ClipOversampled kinds (4 policies x {2, 4, 8}), state handed across blocks"""

@@ -147,7 +147,9 @@ struct Emitter {
            65 536-voice bank (6.9 per SM) are resident in one wave */
         line(0, fmt("extern \"C\" __global__ void __launch_bounds__(kCta, %d) %s(const __grid_constant__ KernelArgs a) {", min_blocks, kernel_name));
         line(1, "__shared__ float tile[kTileF * kTileW];");
-        line(1, g.channels == 2 ? "__shared__ float isum[kTileF * kCta * 2];    /* stereo instance frames */" : "__shared__ float isum[kTileF * kCta];");
+        /* (a name of its own for the stereo scratch: the host-executed test harness loads many generated kernels into one
+           process, where a function-local static of an inline function is ONE object per name) */
+        line(1, g.channels == 2 ? "__shared__ float isum2[kTileF * kCta * 2];    /* stereo instance frames */" : "__shared__ float isum[kTileF * kCta];");
         line(1, "const uint32_t n = a.n_voices;");
         line(1, "const uint32_t v = blockIdx.x * kCta + threadIdx.x;");
         line(1, "const bool active = v < n;");
@@ -411,7 +413,7 @@ struct Emitter {
         line(2, "}");
         if (g.post_tremolo) {
             auto pid = [&](int k) { return g.post_pid[k] == plan::kNoValue ? std::string("kNoPostInput") : std::to_string(g.post_pid[k]) + "u"; };
-            line(2, "tile_flush_tremolo(a, tile, isum, f0, fe, trem_phase, " + pid(0) + ", " + lit(g.post_cst[0]) + ", " + pid(1) + ", " + lit(g.post_cst[1]) + ");    /* rate, depth */");
+            line(2, "tile_flush_tremolo(a, tile, isum2, f0, fe, trem_phase, " + pid(0) + ", " + lit(g.post_cst[0]) + ", " + pid(1) + ", " + lit(g.post_cst[1]) + ");    /* rate, depth */");
         } else {
             line(2, "tile_flush_mono(a, tile, isum, f0, fe);");
         }

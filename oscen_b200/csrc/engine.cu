@@ -201,9 +201,13 @@ struct oscen_b200_engine {
     bool captured_lcg = false;
     std::vector<float *> d_streams;
     CUtensorMap *d_tmaps = nullptr;          /* one TMA descriptor per stream buffer ([kMaxBlock][n_voices], box [kTmaF][kCta]); null: not built */
-    cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};   /* [0] no value events, [1] with, [2] plain block: no event at all, no ramp */
-    uint64_t graph_kernels[3] = {0, 0, 0};
-    std::string plan_names[3];               /* launch sequence of each captured variant (last_kernel_name) */
+    /* captured launch sequences, one per (block carries value events?, block carries any event?, which inputs ramp): the
+       kernels a wave runs depend on all three (plain / TMA kernels need event-free blocks and none of the wave's inputs
+       ramping).  A handful of keys occur in practice (ramps start and stop rarely); the oldest entry goes when 12 are held. */
+    struct PlanVariant { uint64_t key = 0; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; std::string names; uint64_t last_use = 0; };
+    std::vector<PlanVariant> variants;
+    uint64_t variant_clock = 0;
+    void drop_variants() { for (PlanVariant &v : variants) if (v.exec) cudaGraphExecDestroy(v.exec); variants.clear(); }
     std::string *plan_log = nullptr;         /* where launch_plan records kernel names while capturing */
 
     /* multi-GPU */
@@ -247,11 +251,17 @@ int stage_acquire(oscen_b200_engine *e, size_t bytes, void **out, int *slot) {
     e->stage_next = (k + 1) % oscen_b200_engine::kStage;
     if (e->stage_busy[k]) { CK(e, cudaEventSynchronize(e->stage_ev[k])); e->stage_busy[k] = false; }
     if (e->stage_cap[k] < bytes) {
-        if (e->stage_h[k]) cudaFreeHost(e->stage_h[k]);
-        e->stage_h[k] = nullptr; e->stage_cap[k] = 0;
+        /* grow EVERY slot of the ring now: pinned allocations cost milliseconds, and a bank that sent one bank-wide burst
+           (note-on) will send another (note-off) that lands on a different slot — it must not pay for it inside a block */
         const size_t cap = std::max<size_t>(bytes + bytes / 2, 64 * 1024);
-        CK(e, cudaMallocHost(&e->stage_h[k], cap));
-        e->stage_cap[k] = cap;
+        for (int j = 0; j < oscen_b200_engine::kStage; ++j) {
+            if (e->stage_cap[j] >= cap) continue;
+            if (e->stage_busy[j]) { CK(e, cudaEventSynchronize(e->stage_ev[j])); e->stage_busy[j] = false; }
+            if (e->stage_h[j]) cudaFreeHost(e->stage_h[j]);
+            e->stage_h[j] = nullptr; e->stage_cap[j] = 0;
+            CK(e, cudaMallocHost(&e->stage_h[j], cap));
+            e->stage_cap[j] = cap;
+        }
     }
     if (!e->stage_ev[k]) CK(e, cudaEventCreateWithFlags(&e->stage_ev[k], cudaEventDisableTiming));
     *out = e->stage_h[k]; *slot = k;
@@ -475,7 +485,7 @@ int build_stream_tmaps(oscen_b200_engine *e) {
 /* A/B and tests: OSCEN_B200_NODE_PLAIN=0 keeps the generic node kernels on event-free blocks too */
 static bool no_plain_nodes() { const char *x = getenv("OSCEN_B200_NODE_PLAIN"); return x && x[0] == '0'; }   /* read per block: a test flips it between engines */
 
-int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
+int launch_plan(oscen_b200_engine *e, bool value_events, bool no_events, uint32_t ramp_mask) {
     const plan::Graph &g = e->graph;
     const plan::Plan &p = e->plan;
     float **S = e->d_streams.data();
@@ -531,6 +541,10 @@ int launch_plan(oscen_b200_engine *e, bool value_events, bool plain) {
         for (uint32_t k = 0; k < cnt; ++k) a4.n[k] = args_of(l.nodes[k]);
         const dim3 g2(grid, cnt);
         auto log = [&](const char *name) { if (e->plan_log) { *e->plan_log += ' '; *e->plan_log += name; } };
+        /* plain wave: the block carries no event and none of the wave's value inputs ramps in it */
+        bool plain = no_events;
+        for (uint32_t k = 0; k < cnt && plain; ++k)
+            for (int q = 0; q < plan::kMaxParams; ++q) if (a4.n[k].pid[q] != kNoInput && ((ramp_mask >> a4.n[k].pid[q]) & 1u)) plain = false;
         switch (l.type) {
         case plan::NodeType::Adsr:
             if (plain) { adsr_node_plain_kernel<<<g2, kCta, 0, e->stream>>>(a4); log("adsr_node_plain_kernel"); }
@@ -668,7 +682,7 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     if (e->p2p) for (int r = 0; r < e->n_ranks; ++r) if (r != e->rank && e->peers.peer[r]) cudaIpcCloseMemHandle(e->peers.peer[r]);
     cudaFree(e->d_xchg); cudaFree(e->d_p2p_error);
-    for (auto &g : e->graph_exec) if (g) cudaGraphExecDestroy(g);
+    e->drop_variants();
     e->jit.unload();
     for (float *p : e->d_streams) cudaFree(p);
     cudaFree(e->d_tmaps);
@@ -706,6 +720,9 @@ static int create_impl(const oscen_b200_config *cfg, const oscen_b200_graph *cus
     }
     if ((cfg->keep & OSCEN_B200_KEEP_VOICE_OUT) && (uint64_t)cfg->n_voices * kMaxBlock > 0xFFFFFFFFull) {
         g_create_error = "KEEP_VOICE_OUT: n_voices * 512 must fit 32 bits (<= 8 388 607 voices per engine)"; return OSCEN_B200_E_ARG;
+    }
+    if (cfg->plan == OSCEN_B200_PLAN_NODES && (uint64_t)cfg->n_voices * kMaxBlock > 0xFFFFFFFFull) {
+        g_create_error = "PLAN_NODES: n_voices * 512 must fit 32 bits (<= 8 388 607 voices per engine; the stream buffers are indexed with 32 bits)"; return OSCEN_B200_E_ARG;
     }
     if (cfg->graph_kind >= OSCEN_B200_GRAPH_COUNT || cfg->n_voices == 0 || cfg->voices_per_instance == 0 ||
         kCta % cfg->voices_per_instance != 0 || (cfg->voices_per_instance & (cfg->voices_per_instance - 1)) != 0 || cfg->n_voices % cfg->voices_per_instance != 0 ||
@@ -1057,7 +1074,7 @@ int midi_device_run(oscen_b200_engine *e, uint32_t frames) {
         cudaFree(e->d_events);
         e->events_cap = (size_t)nm * 4;
         CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
-        for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+        e->drop_variants();
     }
     /* pageable source: the copy is staged by the runtime before the call returns */
     CK(e, cudaMemcpyAsync(e->d_midi_msgs, e->midi_batch.data(), (size_t)nm * sizeof(MidiMsg), cudaMemcpyHostToDevice, e->stream));
@@ -1210,7 +1227,7 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
             cudaFree(e->d_events); e->d_events = nullptr;
             e->events_cap = n_pend * 2;
             CK(e, cudaMalloc(&e->d_events, e->events_cap * sizeof(Event)));
-            for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+            e->drop_variants();
         }
         { void *hp = nullptr; const int r = stage_acquire(e, n_pend * sizeof(Event), &hp, &ev_slot); if (r) return r; h_events = (Event *)hp; }
         std::vector<uint32_t> gate_seqs;
@@ -1316,34 +1333,49 @@ int oscen_b200_process_block(oscen_b200_engine *e, uint32_t frames) {
         rc = launch_mix_reduce(e, frames); if (rc) return rc;
     } else {
         /* the launch sequence is captured once (per variant) and replayed: per-block words live in BlockCtl */
-        const bool plain = n_ev == 0 && ramp_mask == 0 && !device_midi && !no_plain_nodes();
-        const int gi = plain ? 2 : (has_value_events ? 1 : 0);
+        const bool no_events = n_ev == 0 && !device_midi && !no_plain_nodes();
+        const uint64_t key = (uint64_t)ramp_mask | ((uint64_t)(has_value_events ? 1u : 0u) << 32) | ((uint64_t)(no_events ? 1u : 0u) << 33);
         if (e->captured_in != e->stream_in_ptr || e->captured_lcg != e->lcg_on) {
-            for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+            e->drop_variants();
             e->captured_in = e->stream_in_ptr; e->captured_lcg = e->lcg_on;
         }
-        if (!e->graph_exec[gi]) {
+        oscen_b200_engine::PlanVariant *var = nullptr;
+        for (auto &v : e->variants) if (v.key == key && v.exec) var = &v;
+        if (!var) {
+            if (e->variants.size() >= 12) {                        /* evict the least recently launched variant */
+                size_t old = 0;
+                for (size_t k = 1; k < e->variants.size(); ++k) if (e->variants[k].last_use < e->variants[old].last_use) old = k;
+                CK(e, cudaStreamSynchronize(e->stream));           /* its last launch may still be running */
+                if (e->variants[old].exec) cudaGraphExecDestroy(e->variants[old].exec);
+                e->variants.erase(e->variants.begin() + (long)old);
+            }
+            e->variants.emplace_back();
+            var = &e->variants.back();
+            var->key = key;
             cudaGraph_t g = nullptr;
-            CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            { const cudaError_t be = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal); if (be != cudaSuccess) { e->variants.pop_back(); CK(e, be); } }
             const uint64_t before = e->stats.kernel_launches;
-            e->plan_names[gi] = "node plan (CUDA graph):";
-            e->plan_log = &e->plan_names[gi];
-            rc = launch_plan(e, has_value_events, plain);
+            var->names = "node plan (CUDA graph):";
+            e->plan_log = &var->names;
+            rc = launch_plan(e, has_value_events, no_events, ramp_mask);
             e->plan_log = nullptr;
             if (!rc) rc = launch_mix_reduce(e, frames);
             cudaError_t s = cudaStreamEndCapture(e->stream, &g);
-            e->graph_kernels[gi] = e->stats.kernel_launches - before;
+            var->kernels = e->stats.kernel_launches - before;
             e->stats.kernel_launches = before;
+            if (rc || s != cudaSuccess) { e->variants.pop_back(); if (g) cudaGraphDestroy(g); }
             if (rc) return rc;
             CK(e, s);
-            CK(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
+            const cudaError_t ie = cudaGraphInstantiate(&var->exec, g, 0);
             cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { e->variants.pop_back(); CK(e, ie); }
         }
-        CK(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
-        e->last_kernel = e->plan_names[gi].c_str();               /* valid until the variant is captured again */
+        var->last_use = ++e->variant_clock;
+        CK(e, cudaGraphLaunch(var->exec, e->stream));
+        e->last_kernel = var->names.c_str();                       /* valid until the variant is evicted */
         if (e->timing) CK(e, cudaEventRecord(e->evk, e->stream));
         e->stats.graph_launches++;
-        e->stats.kernel_launches += e->graph_kernels[gi];
+        e->stats.kernel_launches += var->kernels;
     }
     if (e->comm && !e->p2p) {
         const int r = g_nccl.AllReduce(e->d_mix, e->d_mix, (size_t)frames * e->channels, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, e->stream);
@@ -1601,7 +1633,7 @@ int oscen_b200_comm_p2p_import(oscen_b200_engine *e, int rank, int n_ranks, cons
         e->peers.peer[r] = (float *)p;
     }
     e->rank = rank; e->n_ranks = n_ranks; e->p2p = true;
-    for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    e->drop_variants();
     return 0;
 }
 
@@ -1615,7 +1647,7 @@ int oscen_b200_comm_p2p_close(oscen_b200_engine *e) {
     }
     e->p2p = false;
     if (e->d_p2p_error) CK(e, cudaMemset(e->d_p2p_error, 0, 4 * sizeof(uint32_t)));
-    for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    e->drop_variants();
     return 0;
 }
 
@@ -1636,7 +1668,7 @@ int oscen_b200_comm_init(oscen_b200_engine *e, int rank, int n_ranks, const void
     const int r = g_nccl.CommInitRank(&e->comm, n_ranks, id, rank);
     if (r != 0) { e->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); e->comm = nullptr; return OSCEN_B200_E_NCCL; }
     e->rank = rank; e->n_ranks = n_ranks;
-    for (auto &g : e->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    e->drop_variants();
     return 0;
 }
 

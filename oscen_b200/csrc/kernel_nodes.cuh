@@ -756,8 +756,16 @@ __global__ void __launch_bounds__(kCta) instance_mix_node_kernel(const __grid_co
     const uint32_t col = tile_col(threadIdx.x, a.vpi);
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        for (uint32_t ff = 0; ff < fe; ++ff)
-            tile[ff * kTileW + col] = (v < n) ? __ldg(final_stream + (size_t)(f0 + ff) * n + v) : 0.0f;
+        if (fe == kTileF) {                                   /* full tile: 32 independent loads in flight per thread */
+            float x[kTileF];
+#pragma unroll
+            for (uint32_t ff = 0; ff < kTileF; ++ff) x[ff] = (v < n) ? __ldcs(final_stream + ((f0 + ff) * n + v)) : 0.0f;
+#pragma unroll
+            for (uint32_t ff = 0; ff < kTileF; ++ff) tile[ff * kTileW + col] = x[ff];
+        } else {
+            for (uint32_t ff = 0; ff < fe; ++ff)
+                tile[ff * kTileW + col] = (v < n) ? __ldcs(final_stream + ((f0 + ff) * n + v)) : 0.0f;
+        }
         tile_flush_mono(a, tile, isum, f0, fe);
     }
 }

@@ -392,7 +392,7 @@ def test_electric_piano_graph_compiles_from_the_reference_text():
     assert g.input_info(7)["default"] == pytest.approx(0.3) and g.input_info(8)["default"] == 5.0
     assert [l.split(":")[1].split("[")[0].strip() for l in g.launches()] == ["AmplitudeSource", "OscillatorBank"]
     src = g.codegen()
-    assert "float s0[32]; ampsrc_process(" in src and "oscbank_process(" in src and "tile_flush_tremolo(a, tile, isum, f0, fe, trem_phase, 8u," in src
+    assert "float s0[32]; ampsrc_process(" in src and "oscbank_process(" in src and "tile_flush_tremolo(a, tile, isum2, f0, fe, trem_phase, 8u," in src
     assert g.jit_check() > 10000
     voice = abi.Graph(text("electric_piano.graph"), name="ElectricPianoVoiceNode")      # the voice graph alone: mono, 1 voice per instance
     assert voice.channels == 1 and voice.voices_per_instance == 1 and voice.jit_check() > 10000

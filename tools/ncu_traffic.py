@@ -28,7 +28,7 @@ def main():
         total += float(row[i].replace(",", "")) * UNIT[units[i]]
     out = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     table = json.load(open(out)) if os.path.exists(out) else {}
-    table[key] = {"dram_bytes": int(total), "kernel": row[hdr.index("Kernel Name")], "time_us": row[hdr.index("gpu__time_duration.sum")],
+    table[key] = {"dram_bytes": int(total), "kernel": row[hdr.index("Kernel Name")], "time": row[hdr.index("gpu__time_duration.sum")] + " " + units[hdr.index("gpu__time_duration.sum")],
                   "source": source}
     json.dump(table, open(out, "w"), indent=1, sort_keys=True)
     print(key, int(total), table[key]["kernel"])

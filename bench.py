@@ -230,6 +230,15 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_capture(key):
+    """the whole committed capture record of `key` (profiles/ncu_traffic.json), or {}"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(key) or {}
+    except Exception:
+        return {}
+
+
 def ncu_traffic(key):
     """DRAM bytes (read + write) of one launch from a committed `ncu --set full` capture of THIS kernel at THIS size
     (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep): (bytes, source) or (None, None)"""

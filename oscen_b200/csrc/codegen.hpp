@@ -240,6 +240,11 @@ struct Emitter {
             line(1, "const uint32_t my_inst = blockIdx.x * (kCta / a.vpi) + threadIdx.x;");
             line(1, "float trem_phase = (threadIdx.x < kCta / a.vpi && my_inst < a.n_inst) ? a.inst_state[my_inst] : 0.0f;");
         }
+        {   /* FmOperator: the sine's three addend constants are loaded once and stay in registers (om_math.h om_sinf_rk) */
+            bool any_fm = false;
+            for (int i = 0; i < n_nodes; ++i) any_fm |= g.nodes[i].type == T::FmOperator;
+            if (any_fm) line(1, "const OmSinRegs sk = om_sin_regs();");
+        }
         line(1, "EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);");
         {   /* a gate-off at frame 0 starts from the release length the previous block ended with (AdsrState::r_gate) */
             bool any = false;
@@ -323,7 +328,7 @@ struct Emitter {
                 if (hoist_adsr) line(ind, o + "adsr_process_t<false>(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
                 else line(ind, o + "adsr_process(" + N(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
                 break;
-            case T::FmOperator: line(ind, o + "fmop_process(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ");" + cm); break;
+            case T::FmOperator: line(ind, o + "fmop_process_k(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ", sk);" + cm); break;
             case T::Tpt: line(ind, o + "tpt_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + IN(i, 1, 1) + ", " + P(i, 0) + ", " + IN(i, 2, 2) + ", " + SR(i) + ");" + cm); break;
             case T::Lp18: line(ind, o + "lp18_process(" + N(i) + ", " + IN(i, 0, 3) + ", " + P(i, 0) + ", " + P(i, 2) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm); break;
             case T::IirLowpass: line(ind, o + "iirlp_process(" + N(i) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");" + cm); break;

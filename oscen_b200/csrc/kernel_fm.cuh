@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
         adsr_refresh<COMMIT>(e3, h3, P[I_OP3_S], d3); adsr_refresh<COMMIT>(e2, h2, P[I_OP2_S], d2); \
         adsr_refresh<COMMIT>(e1, h1, P[I_OP1_S], d1); adsr_refresh<COMMIT>(ef, hf, P[I_F_S], df);   \
     } while (0)
+    const OmSinRegs sk = om_sin_regs();
     EventCursor ec;
     ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
     {   /* the release length a gate-off at frame 0 starts from is the previous block's (AdsrState::r_gate) */
@@ -164,13 +165,13 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                 const float envf = adsr_process_t<GENERAL>(ef, hf, P[I_F_S], df);
                 const float feg = envf * P[I_ENV_AMT];                 /* filter_env_gain: Gain */
                 const float cutoff = feg + P[I_CUTOFF];                /* cutoff_mod: AddValue  */
-                const float o3 = fmop_process(op3, 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL]);
+                const float o3 = fmop_process_k(op3, 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL], sk);
                 const float mix = clampf(P[I_ROUTE], 0.0f, 1.0f);      /* op3_route: Crossfade  */
                 const float xa = o3 * (1.0f - mix);
                 const float xb = o3 * mix;
-                const float o2 = fmop_process(op2, xa, P[I_OP2_FB], env2, P[I_OP2_LEVEL]);
+                const float o2 = fmop_process_k(op2, xa, P[I_OP2_FB], env2, P[I_OP2_LEVEL], sk);
                 const float pm1 = o2 + xb;                             /* op1_mod_mixer: Mixer  */
-                const float o1 = fmop_process(op1, pm1, 0.0f, env1, 1.0f);
+                const float o1 = fmop_process_k(op1, pm1, 0.0f, env1, 1.0f, sk);
                 const float lp = tpt_process(tp, o1, cutoff, P[I_RES], 0.0f, sr);
                 y = lp * 0.3f;                                         /* output_gain: Gain(0.3) */
                 if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;

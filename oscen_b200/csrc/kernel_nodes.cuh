@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
     FmOpState s;
     s.phase = a.state[(size_t)(a.state_base + 0) * n + v]; s.prev = a.state[(size_t)(a.state_base + 1) * n + v];
     s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr);
+    const OmSinRegs sk = om_sin_regs();
     float pm[kPF], en[kPF], pm_n[kPF], en_n[kPF];
     OSC_LOAD2(pm, en, a.in0, a.in1, 0u)
     for (uint32_t f0 = 0; f0 < frames; f0 += kPF) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kCta) fmop_node_kernel(const __grid_constant__
             if (f < frames) {
                 if (ramp_mask) { prm.ramps(a, ramp_mask, f); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
                 if (ec.due(f)) { ec.advance(prm.events(a, ec, f)); s.inc = fmop_phase_inc(prm.P[0], prm.P[1], a.sr); }
-                __stcs(a.out0 + (size_t)f * n + v, fmop_process(s, pm_stream ? pm[k] : prm.P[4], prm.P[2], en_stream ? en[k] : prm.P[5], prm.P[3]));
+                __stcs(a.out0 + (size_t)f * n + v, fmop_process_k(s, pm_stream ? pm[k] : prm.P[4], prm.P[2], en_stream ? en[k] : prm.P[5], prm.P[3], sk));
             }
         }
 #pragma unroll
@@ -376,24 +377,6 @@ __global__ void __launch_bounds__(kCta) sample_player_node_kernel(const __grid_c
         const uint32_t f_ = (F0) + k;                                                                   \
         A[k] = ((PA) != nullptr && f_ < frames) ? __ldcs((PA) + (f_ * n + v)) : 0.0f;                   \
     }
-
-/* sinf behind ONE range test: the bounded-argument form (both polynomials, no coefficient selects) for |y| < 120, the
-   general routine (a call) beyond */
-OSC_D float om_sinf_uk(float y, const OmSinRegs &k) {
-    const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
-    if (top >= 0x42f) return om_sinf_slow(y);
-    return om_sinf_rk(y, k);
-}
-OSC_D float fmop_process_k(FmOpState &s, float phase_mod, float feedback, float envelope, float level, const OmSinRegs &sk) {
-    const float feedback_mod = s.prev * feedback;
-    const float total_phase_mod = phase_mod + feedback_mod;
-    const float phase_rad = (s.phase + total_phase_mod) * kTau;
-    const float out = om_sinf_uk(phase_rad, sk) * envelope * level;
-    s.prev = out;
-    const float ph = s.phase + s.inc;
-    s.phase = ph - truncf(ph);
-    return out;
-}
 
 /* ---- FmOperator, plain block */
 __global__ void __launch_bounds__(kCta) fmop_node_plain_kernel(const __grid_constant__ NodeArgs4 args) {

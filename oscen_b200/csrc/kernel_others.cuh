@@ -413,16 +413,14 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 8; ++i) tgt[i] = cur[i] * row[(size_t)i * n_stride];
                 }
-                if (step < 64u) {
+                {   /* interpolate towards the target for 64 frames, then land on it (one frame in 65): select form — as a
+                       branch the two arms meet in 16 register moves per frame */
+                    const bool lerp = step < 64u;
                     const float t = (float)(step + 1u) / 64.0f;
                     const float omt = 1.0f - t;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = cur[i] * omt + tgt[i] * t;
-                    step += 1u;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = tgt[i];
-                    step = 0u;
+                    for (int i = 0; i < 8; ++i) { const float nc = cur[i] * omt + tgt[i] * t; cur[i] = lerp ? nc : tgt[i]; }
+                    step = lerp ? step + 1u : 0u;
                 }
                 /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
                 const float freq = prm.P[0];

@@ -247,6 +247,24 @@ OSC_D float fmop_process(FmOpState &s, float phase_mod, float feedback, float en
     return out;
 }
 
+/* sinf behind ONE range test: the bounded-argument form (both polynomials, no coefficient selects) for |y| < 120, the
+   general routine (a call) beyond */
+OSC_D float om_sinf_uk(float y, const OmSinRegs &k) {
+    const uint32_t top = (om_asuint(y) >> 20) & 0x7ff;
+    if (top >= 0x42f) return om_sinf_slow(y);
+    return om_sinf_rk(y, k);
+}
+OSC_D float fmop_process_k(FmOpState &s, float phase_mod, float feedback, float envelope, float level, const OmSinRegs &sk) {
+    const float feedback_mod = s.prev * feedback;
+    const float total_phase_mod = phase_mod + feedback_mod;
+    const float phase_rad = (s.phase + total_phase_mod) * kTau;
+    const float out = om_sinf_uk(phase_rad, sk) * envelope * level;
+    s.prev = out;
+    const float ph = s.phase + s.inc;
+    s.phase = ph - truncf(ph);
+    return out;
+}
+
 /* ==================================================================== TptFilter == */
 /* oscen-lib/src/filters/tpt/mod.rs:69-123 */
 struct TptState {

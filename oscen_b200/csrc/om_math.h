@@ -671,12 +671,9 @@ OM_HD float om_tanhf_u(float x) {
     float a = big ? 2.0f * ax : -2.0f * ax;                            /* expm1f argument */
     const uint32_t ha = om_asuint(a) & 0x7fffffffu;
     if (ha >= 0x4195b844u) return om_tanhf_slow(x);                    /* |a| >= 27 ln2: cold */
-    /* k */
-    int32_t k;
-    if (ha > 0x3eb17218u) {
-        const int32_t kg = (int32_t)(invln2 * a + (big ? 0.5f : -0.5f));
-        k = (ha < 0x3F851592u) ? (big ? 1 : -1) : kg;
-    } else k = 0;
+    /* k: select form (the conversion of an out-of-range product is discarded by the selects) */
+    const int32_t kg = (int32_t)(invln2 * a + (big ? 0.5f : -0.5f));
+    const int32_t k = (ha > 0x3eb17218u) ? ((ha < 0x3F851592u) ? (big ? 1 : -1) : kg) : 0;
     const bool tiny = ha < 0x33000000u;                                /* |a| < 2^-25: expm1f(a) = a */
     const float t0 = (float)k;
     const float hi = a - t0 * ln2_hi;
@@ -689,7 +686,19 @@ OM_HD float om_tanhf_u(float x) {
     const float tt = 3.0f - r1 * hfx;
     float e = hxs * ((r1 - tt) / (6.0f - xr * tt));
     float em1;
-    if (k == 0) {
+    if (!big) {
+        /* |x| < 1: the argument is in (-2, 0], so k is 0, -1, -2 or -3 — the three reconstructions of expm1f for those are
+           a handful of flops each: all three are computed and the lane's one selected, instead of a three-way divergent
+           branch in every warp whose voices are spread over the bands (a filter state under noise always is) */
+        const float m0 = xr - (xr * e - hxs);                          /* k == 0 */
+        float e2 = (xr * (e - c) - c);
+        e2 -= hxs;
+        const float m1 = 0.5f * (xr - e2) - 0.5f;                      /* k == -1 */
+        float y = one - (e2 - xr);                                     /* k <= -2 */
+        y = om_asfloat(om_asuint(y) + ((uint32_t)k << 23));
+        const float m2 = y - one;
+        em1 = (k == 0) ? m0 : ((k == -1) ? m1 : m2);
+    } else if (k == 0) {
         em1 = xr - (xr * e - hxs);
     } else {
         e = (xr * (e - c) - c);

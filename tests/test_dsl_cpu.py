@@ -265,7 +265,7 @@ def test_generated_kernel_walks_nodes_in_topological_order():
                  ("op1_mod_mixer", "op1_osc"), ("op1_osc", "filter"), ("env_filter", "filter_env_gain"),
                  ("filter_env_gain", "cutoff_mod"), ("cutoff_mod", "filter"), ("filter", "output_gain")]:
         assert pos[a] < pos[b], (a, b)
-    assert src.count("adsr_on_gate(") == 4 and src.count("fmop_process(") == 3
+    assert src.count("adsr_on_gate(") == 4 and src.count("fmop_process_k(") == 3
     # literals are emitted bit-exactly
     assert "0x3e99999au /* 0.300000012 */" in src      # output_gain = Gain::new(0.3)
 

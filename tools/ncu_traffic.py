@@ -28,7 +28,13 @@ def main():
         total += float(row[i].replace(",", "")) * UNIT[units[i]]
     out = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     table = json.load(open(out)) if os.path.exists(out) else {}
+    def metric(name):
+        return float(row[hdr.index(name)].replace(",", "")) if name in hdr else None
     table[key] = {"dram_bytes": int(total), "kernel": row[hdr.index("Kernel Name")], "time": row[hdr.index("gpu__time_duration.sum")] + " " + units[hdr.index("gpu__time_duration.sum")],
+                  "issue_active_pct": metric("sm__issue_active.avg.pct_of_peak_sustained_elapsed"),
+                  "warp_instructions": metric("smsp__inst_executed.sum"),
+                  "warps_active_pct": metric("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                  "registers_per_thread": metric("launch__registers_per_thread"),
                   "source": source}
     json.dump(table, open(out, "w"), indent=1, sort_keys=True)
     print(key, int(total), table[key]["kernel"])

@@ -692,8 +692,12 @@ def run(out):
         model = "N (node-granular): 4*(14 W + 14 R) + (2*116 + P)/256 bytes per voice-sample"
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(f"{dominant}@{n}")
+    cap = ncu_capture(f"{dominant}@{n}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
+                # what does bound the fused kernel, from the same committed capture: share of the SM's issue slots in use
+                "issue_active_frac": (cap.get("issue_active_pct") or 0.0) / 100.0 if cap else None,
+                "warp_instructions_per_launch": cap.get("warp_instructions") if cap else None,
                 "peak_source": peak_src, "kernel": dominant, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "byte_model": model,
                 "model_n_equivalent_frac": (MODEL_N_BYTES * n * FRAMES / (k_ms * 1e-3) / 1e9) / peak,

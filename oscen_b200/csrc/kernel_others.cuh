@@ -264,6 +264,19 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
    Per-voice state (259 words) lives in a [field][thread] shared-memory tile for the block. */
 /* the two reference spectra (kEpVel0 / kEpVel127) live in nodes.cuh, next to the per-node forms of these nodes */
 
+/* lanes per voice and harmonics per lane of epiano_kernel.  Measured on B200 at 131 072 instances x 16 voices
+   (profiles/r02_ab_epiano_lanes.log): 4 lanes x 8 harmonics (128 registers, 2 CTAs of 256 threads per SM) 3.38e10
+   voice-samples/s, 2 lanes x 16 harmonics (168 registers, 3 CTAs of 128 threads) 4.26e10 — the per-lane control flow
+   (event / ramp / step / frequency tests, tile write) is replicated per lane, so fewer, fatter lanes issue fewer
+   instructions per voice-sample, and 16 independent rotation chains per lane hide the FP32 latency at 12 warps per SM. */
+#ifndef OSCEN_B200_EP_LANES
+#define OSCEN_B200_EP_LANES 2
+#endif
+#ifndef OSCEN_B200_EP_MIN_BLOCKS
+#define OSCEN_B200_EP_MIN_BLOCKS 3                 /* CTAs per SM the register allocation aims at */
+#endif
+constexpr uint32_t kEpLanes = OSCEN_B200_EP_LANES;
+constexpr uint32_t kEpH = 32u / kEpLanes;
 #define EPS(field, i) S[(size_t)((field) + (i)) * n_stride]
 /* The two rare per-voice transitions run out of line ON THE STATE ROWS IN HBM (the caller reloads the registers they
    replace): inlined into the frame loop, their bodies (a 32-step product chain, eight double-precision cos / sin) cost the
@@ -286,7 +299,7 @@ static __device__ __noinline__ void ep_note_on_rows(float *S, size_t n_stride, u
     const float rv = 0.999f - ((100.0f - release_rate) / 1000.0f);
     float bs = -0.2f + (0.8f * (brightness * 0.01f));
     bs += velocity * velocity_scaling * 0.01f * 0.5f;
-    for (uint32_t i = 0; i < 8u; ++i) {
+    for (uint32_t i = 0; i < kEpH; ++i) {
         EPS(EP_DEC, h0 + i) = adjusted * scaling; scaling *= harmonic_scaling;
         EPS(EP_REL, h0 + i) = rv;
         float amp = (kEpVel127[h0 + i] * velocity) + (kEpVel0[h0 + i] * (1.0f - velocity));
@@ -307,7 +320,7 @@ OSC_D float *ep_row(float *S, size_t n_stride, uint32_t field) {
    and unit oscillators for the harmonics [h0, h0 + 8) */
 static __device__ __noinline__ void ep_multiplier_rows(float *S, size_t n_stride, uint32_t h0, float freq, float sr) {
     const float nyquist = sr * 0.5f;
-    for (uint32_t i = 0; i < 8u; ++i) {
+    for (uint32_t i = 0; i < kEpH; ++i) {
         const float hf = freq * (float)(h0 + i + 1u);
         float re = 1.0f, im = 0.0f;
         if (hf < nyquist) {
@@ -320,36 +333,35 @@ static __device__ __noinline__ void ep_multiplier_rows(float *S, size_t n_stride
 }
 
 /*
- * FOUR threads = one voice: lane q of a voice owns the harmonics [8q, 8q + 8) and keeps their 48 state words (current /
+ * kEpLanes (2) threads = one voice: lane q of a voice owns the harmonics [16q, 16q + 16) and keeps their 96 state words (current /
  * target amplitude, oscillator and multiplier, each complex) in REGISTERS for the whole block — the voice state moves
  * HBM -> registers -> HBM once per block (2 * 1036 B per voice) instead of once per 32-frame tile per harmonic chunk as in
  * the first version (profiles/r02_ncu_epiano_v1_tiles.md: 8.9 GB of DRAM traffic per block, 835 SASS instructions per
  * warp-frame of 32 voices, 12 warps per SM at 168 registers).
  *
  * The reference adds the 32 weighted harmonics in index order (sum += osc[i].imag * amp[i], i = 0..31,
- * electric_piano_voice.rs:160-166); to keep that rounding order the partial sum travels through the voice's four lanes as a
- * SYSTOLIC pipeline: in iteration j lane q renders frame j - q — its own eight rotations and amplitude steps need nothing
+ * electric_piano_voice.rs:160-166); to keep that rounding order the partial sum travels through the voice's lanes as a
+ * SYSTOLIC pipeline: in iteration j lane q renders frame j - q — its own rotations and amplitude steps need nothing
  * from the other lanes — and then continues the sum lane q - 1 left for that frame one iteration earlier (one SHFL.UP per
- * iteration).  All four lanes are busy except for three iterations at either end of the block.  Everything per-voice
+ * iteration).  All lanes are busy except for kEpLanes - 1 iterations at either end of the block.  Everything per-voice
  * (interpolation step, release flag, last frequency, ramps, gate / value events) is replayed by each lane at its own
- * frame, so the lanes never wait for each other.  64 voices per CTA as everywhere (256 threads), so the instance fold, the
+ * frame, so the lanes never wait for each other.  64 voices per CTA as everywhere (64 x kEpLanes threads), so the instance fold, the
  * mix partials and the tile geometry are those of the other kernels.
  *
  * Flush per 32 frames: instance sums (voices in index order) by all threads, the tremolo's phase recurrence by one thread
  * per instance (serial in time, 4 flops per frame), then sine / pan / Frame<2> outputs by all threads again.
  */
-constexpr uint32_t kEpLanes = 4u;
 constexpr uint32_t kEpThreads = kCta * kEpLanes;
 constexpr uint32_t kEpDynFloats = kTileF * kTileW + kTileF * kCta * 2u + kTileF * kCta + kTileF * kCta;
 
-__global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kEpThreads, OSCEN_B200_EP_MIN_BLOCKS) epiano_kernel(const __grid_constant__ KernelArgs a) {
     extern __shared__ float dyn[];          /* tile [kTileF][kTileW] | isum [kTileF][kCta][2] | ssum [kTileF][kCta] | tph [kTileF][kCta] */
     float *tile = dyn;
     float *isum = tile + kTileF * kTileW;
     float *ssum = isum + kTileF * kCta * 2u;
     float *tph = ssum + kTileF * kCta;
     const uint32_t n = a.n_voices;
-    const uint32_t vl = threadIdx.x / kEpLanes, q = threadIdx.x % kEpLanes, h0 = q * 8u;
+    const uint32_t vl = threadIdx.x / kEpLanes, q = threadIdx.x % kEpLanes, h0 = q * kEpH;
     const uint32_t v = blockIdx.x * kCta + vl;
     const bool active = v < n;
     const uint32_t vs = active ? v : 0u;
@@ -366,9 +378,9 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
     const uint32_t my_inst = blockIdx.x * ipc + threadIdx.x;
     float trem_phase = (threadIdx.x < ipc && my_inst < a.n_inst) ? a.inst_state[my_inst] : 0.0f;
 
-    float cur[8], tgt[8], ore[8], oim[8], mre[8], mim[8];
+    float cur[kEpH], tgt[kEpH], ore[kEpH], oim[kEpH], mre[kEpH], mim[kEpH];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < (int)kEpH; ++i) {
         cur[i] = EPS(EP_CUR, h0 + i); tgt[i] = EPS(EP_TGT, h0 + i);
         ore[i] = EPS(EP_ORE, h0 + i); oim[i] = EPS(EP_OIM, h0 + i);
         mre[i] = EPS(EP_MRE, h0 + i); mim[i] = EPS(EP_MIM, h0 + i);
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
                             ep_note_on_rows(S, n_stride, h0, vel, prm.P[1], prm.P[2], prm.P[3], prm.P[4], prm.P[5], prm.P[6]);
                             const float *row = ep_row(S, n_stride, EP_CUR + h0);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) { cur[i] = row[(size_t)i * n_stride]; ore[i] = 1.0f; oim[i] = 0.0f; }
+                            for (int i = 0; i < (int)kEpH; ++i) { cur[i] = row[(size_t)i * n_stride]; ore[i] = 1.0f; oim[i] = 0.0f; }
                             released = false;
                         } else {
                             released = true;
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
                 if (step == 0u) {
                     const float *row = ep_row(S, n_stride, (released ? EP_REL : EP_DEC) + h0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) tgt[i] = cur[i] * row[(size_t)i * n_stride];
+                    for (int i = 0; i < (int)kEpH; ++i) tgt[i] = cur[i] * row[(size_t)i * n_stride];
                 }
                 {   /* interpolate towards the target for 64 frames, then land on it (one frame in 65): select form — as a
                        branch the two arms meet in 16 register moves per frame */
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
                     const float t = (float)(step + 1u) / 64.0f;
                     const float omt = 1.0f - t;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { const float nc = cur[i] * omt + tgt[i] * t; cur[i] = lerp ? nc : tgt[i]; }
+                    for (int i = 0; i < (int)kEpH; ++i) { const float nc = cur[i] * omt + tgt[i] * t; cur[i] = lerp ? nc : tgt[i]; }
                     step = lerp ? step + 1u : 0u;
                 }
                 /* OscillatorBank::process, electric_piano_voice.rs:127-170 */
@@ -429,10 +441,10 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
                     ep_multiplier_rows(S, n_stride, h0, freq, sr);
                     const float *row = ep_row(S, n_stride, EP_MRE + h0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { mre[i] = row[(size_t)i * n_stride]; mim[i] = row[(size_t)(i + 32) * n_stride]; ore[i] = 1.0f; oim[i] = 0.0f; }
+                    for (int i = 0; i < (int)kEpH; ++i) { mre[i] = row[(size_t)i * n_stride]; mim[i] = row[(size_t)(i + 32) * n_stride]; ore[i] = 1.0f; oim[i] = 0.0f; }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < (int)kEpH; ++i) {
                     const float nr = ore[i] * mre[i] - oim[i] * mim[i];
                     const float ni = ore[i] * mim[i] + oim[i] * mre[i];
                     ore[i] = nr; oim[i] = ni;
@@ -492,7 +504,7 @@ __global__ void __launch_bounds__(kEpThreads, 2) epiano_kernel(const __grid_cons
     if (active) {
         float *row = ep_row(S, n_stride, h0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < (int)kEpH; ++i) {
             row[(size_t)(EP_CUR + i) * n_stride] = cur[i]; row[(size_t)(EP_TGT + i) * n_stride] = tgt[i];
             row[(size_t)(EP_ORE + i) * n_stride] = ore[i]; row[(size_t)(EP_OIM + i) * n_stride] = oim[i];
             row[(size_t)(EP_MRE + i) * n_stride] = mre[i]; row[(size_t)(EP_MIM + i) * n_stride] = mim[i];

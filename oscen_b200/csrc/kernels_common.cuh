@@ -181,7 +181,10 @@ OSC_D void tile_flush_mono(const KernelArgs &a, const float *tile, float *isum, 
         float s = 0.0f;
         const uint32_t c0 = tile_col(i * vpi, vpi);
         for (uint32_t j = 0; j < vpi; ++j) s = s + row[c0 + j];
-        isum[ff * kCta + i] = s;
+        /* rows of isum are rotated by their frame index: the fold below has the lanes of a warp on DIFFERENT frames reading
+           the same instance index, which in an unrotated [frame][kCta] array is one bank for all of them (a 32-way conflict
+           per load at vpi = 1: 2.6e8 conflict cycles per block in the TwinPeaks profile) */
+        isum[ff * kCta + ((i + ff) & (kCta - 1u))] = s;
         if (a.inst_out != nullptr && inst0 + i < a.n_inst)
             a.inst_out[(size_t)(f0 + ff) * a.n_inst + inst0 + i] = s;
     }
@@ -195,7 +198,7 @@ OSC_D void tile_flush_mono(const KernelArgs &a, const float *tile, float *isum, 
         if (ff < fe) {
             const uint32_t per = (ipc + TPF - 1u) / TPF;
             const uint32_t b = qd * per, e = min(b + per, ipc);
-            for (uint32_t i = b; i < e; ++i) s = s + isum[ff * kCta + i];
+            for (uint32_t i = b; i < e; ++i) s = s + isum[ff * kCta + ((i + ff) & (kCta - 1u))];
         }
         float tot = s;
 #pragma unroll

@@ -115,9 +115,8 @@ struct Emitter {
         const plan::Node &nd = g.nodes[i];
         return std::string(nd.type == plan::NodeType::Up ? "UpEdge<" : "DownEdge<") + std::to_string(nd.policy) + ", " + std::to_string(nd.rate_log2) + ">";
     }
-    static uint32_t edge_smem_floats(const plan::Node &nd) {
-        if (nd.policy != plan::kPolicySinc) return 0u;
-        return (nd.type == plan::NodeType::Up ? 24u : nd.type == plan::NodeType::Down ? 48u : 0u) * (uint32_t)nd.rate_log2;
+    static uint32_t edge_smem_floats(const plan::Node &) {
+        return 0u;       /* [sinc] edges keep their FIR histories in registers since round 2 (nodes.cuh HbUpRegs / HbDownRegs) */
     }
     static bool is_polyblep(plan::NodeType t) {
         return t == plan::NodeType::PolyBlepSine || t == plan::NodeType::PolyBlepSaw || t == plan::NodeType::PolyBlepSquare || t == plan::NodeType::PolyBlepTriangle;

@@ -93,45 +93,7 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
 /* ============================================================== SatGraph_{1x,4x} === */
 /* examples/oversampled-saturator/src/main.rs:64-80; multirate body codegen/emit_frame.rs:114-176 */
 
-/* Halfband2xDownStage::step (sinc_fir.rs:113-138) with the 24-sample history in REGISTERS.  A step pushes xs[0] = x[2m]
-   and xs[1] = x[2m + 1] and reads x[2m - d] for the even delays d = 0, 2, .., 22 and for d = 11 only (every other odd tap
-   of a halfband filter is zero), so the history splits into two polyphase shift registers: a[k] = x[2m - 2k] (the FIRST
-   sample of the step k steps ago, k = 0..11) and b[k] = x[2m + 1 - 2k] (its second sample, k = 0..6; b[6] is the centre
-   tap d = 11, b[0] the sample this step only stores).  Shifting by one entry per step is free once the frame loop is
-   unrolled (the compiler renames registers inside the unrolled body and moves 19 values per ring at the back edge); the
-   shared-memory ring this replaces cost 13 LDS + 4 STS per step and capped the kernel at 5 CTAs per SM
-   (profiles/r02_ncu_sat4x_smem_rings.md).  Same taps, same order of additions as hb_down_step: the same bits. */
-struct HbDownRegs { float a[12]; float b[7]; };
-OSC_D float hb_down_step_r(HbDownRegs &r, float x0, float x1) {
-#pragma unroll
-    for (int i = 11; i > 0; --i) r.a[i] = r.a[i - 1];
-    r.a[0] = x0;
-#pragma unroll
-    for (int i = 6; i > 0; --i) r.b[i] = r.b[i - 1];
-    r.b[0] = x1;
-    float acc = r.b[6] * kHbCenter;                          /* d = 11 */
-    acc = acc + (r.a[0] + r.a[11]) * kHb0;                   /* d = 0, 22 */
-    acc = acc + (r.a[1] + r.a[10]) * kHb1;
-    acc = acc + (r.a[2] + r.a[9]) * kHb2;
-    acc = acc + (r.a[3] + r.a[8]) * kHb3;
-    acc = acc + (r.a[4] + r.a[7]) * kHb4;
-    acc = acc + (r.a[5] + r.a[6]) * kHb5;                    /* d = 10, 12 */
-    return acc;
-}
-/* the stage's 24 state rows are chronological (row 23 = newest = x[2m + 1], row 22 - d = x[2m - d]).  The rows of the odd
-   delays 13 .. 21 are never read by a step (now or later: samples only get older) and are not maintained. */
-OSC_D void hb_down_load(HbDownRegs &r, const float *state, uint32_t first, uint32_t n, uint32_t v) {
-#pragma unroll
-    for (int k = 0; k < 12; ++k) r.a[k] = state[(size_t)(first + 22u - 2u * k) * n + v];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) r.b[k] = state[(size_t)(first + 23u - 2u * k) * n + v];
-}
-OSC_D void hb_down_store(const HbDownRegs &r, float *state, uint32_t first, uint32_t n, uint32_t v) {
-#pragma unroll
-    for (int k = 0; k < 12; ++k) state[(size_t)(first + 22u - 2u * k) * n + v] = r.a[k];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) state[(size_t)(first + 23u - 2u * k) * n + v] = r.b[k];
-}
+/* hb_down_step_r / HbDownRegs (register-resident halfband histories) live in nodes.cuh, next to the shared-memory form */
 
 template <int FACTOR>
 __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ KernelArgs a) {

@@ -10,10 +10,9 @@
  *     [linear]    LinearUp<N> / LinearDown<N>            resample/linear.rs:11-74
  *     [latch]     LatchUp<N> / LatchDown<N>              resample/latch.rs:6-54
  *
- * One thread = one voice, serial in time, like every other fused kernel.  FIR histories live in
- * shared memory as per-thread rings stored twice (no modulo on the 12/13 tap reads); the IIR
- * all-pass states live in registers.  State in HBM is [field][voice]; FIR rings are stored
- * chronologically (oldest first) so a block boundary normalises the ring head.
+ * One thread = one voice, serial in time, like every other fused kernel.  FIR histories are shift registers in
+ * REGISTERS (nodes.cuh HbUpRegs / HbDownRegs; shared-memory rings until round 2), like the IIR all-pass states.
+ * State in HBM is [field][voice]; FIR histories are stored chronologically (oldest first).
  */
 #pragma once
 #include "kernel_others.cuh"
@@ -34,9 +33,9 @@ OSC_HD constexpr uint32_t clip_n_state(int policy, int log2f) {
          : policy == POL_SINC_IIR ? 2u + 17u * (uint32_t)log2f
          : policy == POL_LINEAR ? 3u : 2u;
 }
-/* dynamic shared memory: isum [kTileF][kCta], then for [sinc] L x [24][kCta] up + L x [48][kCta] down */
-OSC_HD constexpr size_t clip_dyn_bytes(int policy, int log2f) {
-    return (size_t)(kTileF * kCta + (policy == POL_SINC ? 72u * (uint32_t)log2f * kCta : 0u)) * sizeof(float);
+/* dynamic shared memory: isum [kTileF][kCta] (the FIR histories left shared memory in round 2) */
+OSC_HD constexpr size_t clip_dyn_bytes(int /*policy*/, int /*log2f*/) {
+    return (size_t)(kTileF * kCta) * sizeof(float);
 }
 
 /* the test graphs' HardClip: clamp(+-0.7), no drive (multirate_graph.rs:35-40) */
@@ -50,8 +49,6 @@ __global__ void __launch_bounds__(kCta) clip_kernel(const __grid_constant__ Kern
     __shared__ float tile[kTileF * kTileW];
     extern __shared__ float dyn[];
     float *isum = dyn;
-    float *ring_up = dyn + kTileF * kCta + threadIdx.x;                /* stage s at + s * 24 * kCta */
-    float *ring_down = ring_up + L * 24 * (int)kCta;                   /* stage s at + s * 48 * kCta */
     const uint32_t n = a.n_voices;
     const uint32_t v = blockIdx.x * kCta + threadIdx.x;
     const bool active = v < n;
@@ -62,17 +59,15 @@ __global__ void __launch_bounds__(kCta) clip_kernel(const __grid_constant__ Kern
 
     unsigned long long lcg = (unsigned long long)__float_as_uint(a.state[(size_t)(CL_LCG + 0) * n + vs]) |
                              ((unsigned long long)__float_as_uint(a.state[(size_t)(CL_LCG + 1) * n + vs]) << 32);
-    uint32_t head_up[LS], head_down[LS];
+    HbUpRegs fir_up[LS];
+    HbDownRegs fir_down[LS];
     IirHb iir_up[LI], iir_down[LI];
     float lin_prev = 0.0f;
     if (POLICY == POL_SINC && L > 0) {
 #pragma unroll
         for (int s = 0; s < LS; ++s) {
-            float *ru = ring_up + s * 24 * (int)kCta, *rd = ring_down + s * 48 * (int)kCta;
-            const uint32_t bu = CL_STATE + 12u * s, bd = CL_STATE + 12u * L + 24u * s;
-            for (uint32_t i = 0; i < 12; ++i) { const float t = a.state[(size_t)(bu + i) * n + vs]; ru[i * kCta] = t; ru[(i + 12) * kCta] = t; }
-            for (uint32_t i = 0; i < 24; ++i) { const float t = a.state[(size_t)(bd + i) * n + vs]; rd[i * kCta] = t; rd[(i + 24) * kCta] = t; }
-            head_up[s] = 11u; head_down[s] = 23u;                      /* chronological order, newest last */
+            hb_up_load(fir_up[s], a.state, CL_STATE + 12u * (uint32_t)s, n, vs);
+            hb_down_load(fir_down[s], a.state, CL_STATE + 12u * (uint32_t)L + 24u * (uint32_t)s, n, vs);
         }
     }
     if (POLICY == POL_SINC_IIR && L > 0) {
@@ -114,7 +109,7 @@ __global__ void __launch_bounds__(kCta) clip_kernel(const __grid_constant__ Kern
                             float nx[N];
 #pragma unroll
                             for (int i = 0; i < N / 2; ++i) if (i < (1 << s))
-                                hb_up_step(ring_up + s * 24 * (int)kCta, (int)kCta, head_up[s], buf[i], nx[2 * i], nx[2 * i + 1]);
+                                hb_up_step_r(fir_up[s], buf[i], nx[2 * i], nx[2 * i + 1]);
 #pragma unroll
                             for (int i = 0; i < N; ++i) if (i < (2 << s)) buf[i] = nx[i];
                         }
@@ -147,7 +142,7 @@ __global__ void __launch_bounds__(kCta) clip_kernel(const __grid_constant__ Kern
                         for (int s = 0; s < L; ++s) {                  /* stage s consumes pairs in order */
 #pragma unroll
                             for (int i = 0; i < N / 2; ++i) if (i < (N >> (s + 1)))
-                                buf[i] = hb_down_step(ring_down + s * 48 * (int)kCta, (int)kCta, head_down[s], buf[2 * i], buf[2 * i + 1]);
+                                buf[i] = hb_down_step_r(fir_down[s], buf[2 * i], buf[2 * i + 1]);
                         }
                         y = buf[0];
                     } else if (POLICY == POL_SINC_IIR) {
@@ -178,10 +173,8 @@ __global__ void __launch_bounds__(kCta) clip_kernel(const __grid_constant__ Kern
         if (POLICY == POL_SINC && L > 0) {
 #pragma unroll
             for (int s = 0; s < LS; ++s) {
-                const float *ru = ring_up + s * 24 * (int)kCta, *rd = ring_down + s * 48 * (int)kCta;
-                const uint32_t bu = CL_STATE + 12u * s, bd = CL_STATE + 12u * L + 24u * s;
-                for (uint32_t i = 0; i < 12; ++i) a.state[(size_t)(bu + i) * n + v] = ru[((head_up[s] + 1u + i) % 12u) * kCta];
-                for (uint32_t i = 0; i < 24; ++i) a.state[(size_t)(bd + i) * n + v] = rd[((head_down[s] + 1u + i) % 24u) * kCta];
+                hb_up_store(fir_up[s], a.state, CL_STATE + 12u * (uint32_t)s, n, v);
+                hb_down_store(fir_down[s], a.state, CL_STATE + 12u * (uint32_t)L + 24u * (uint32_t)s, n, v);
             }
         }
         if (POLICY == POL_SINC_IIR && L > 0) {

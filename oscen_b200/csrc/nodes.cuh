@@ -596,6 +596,73 @@ OSC_D void hb_up_step(float *hist, int stride, uint32_t &head, float x, float &o
     out0 = acc * 2.0f;
 }
 
+/* Halfband2xDownStage::step (sinc_fir.rs:113-138) with the 24-sample history in REGISTERS.  A step pushes xs[0] = x[2m]
+   and xs[1] = x[2m + 1] and reads x[2m - d] for the even delays d = 0, 2, .., 22 and for d = 11 only (every other odd tap
+   of a halfband filter is zero), so the history splits into two polyphase shift registers: a[k] = x[2m - 2k] (the FIRST
+   sample of the step k steps ago, k = 0..11) and b[k] = x[2m + 1 - 2k] (its second sample, k = 0..6; b[6] is the centre
+   tap d = 11, b[0] the sample this step only stores).  Shifting by one entry per step is free once the frame loop is
+   unrolled (the compiler renames registers inside the unrolled body and moves 19 values per ring at the back edge); the
+   shared-memory ring this replaces cost 13 LDS + 4 STS per step and capped the kernel at 5 CTAs per SM
+   (profiles/r02_ncu_sat4x_smem_rings.md; every [sinc] cross-rate edge of the hand-written and the generated kernels
+   uses this form since round 2).  Same taps, same order of additions as hb_down_step: the same bits. */
+struct HbDownRegs { float a[12]; float b[7]; };
+OSC_D float hb_down_step_r(HbDownRegs &r, float x0, float x1) {
+#pragma unroll
+    for (int i = 11; i > 0; --i) r.a[i] = r.a[i - 1];
+    r.a[0] = x0;
+#pragma unroll
+    for (int i = 6; i > 0; --i) r.b[i] = r.b[i - 1];
+    r.b[0] = x1;
+    float acc = r.b[6] * kHbCenter;                          /* d = 11 */
+    acc = acc + (r.a[0] + r.a[11]) * kHb0;                   /* d = 0, 22 */
+    acc = acc + (r.a[1] + r.a[10]) * kHb1;
+    acc = acc + (r.a[2] + r.a[9]) * kHb2;
+    acc = acc + (r.a[3] + r.a[8]) * kHb3;
+    acc = acc + (r.a[4] + r.a[7]) * kHb4;
+    acc = acc + (r.a[5] + r.a[6]) * kHb5;                    /* d = 10, 12 */
+    return acc;
+}
+/* the stage's 24 state rows are chronological (row 23 = newest = x[2m + 1], row 22 - d = x[2m - d]).  The rows of the odd
+   delays 13 .. 21 are never read by a step (now or later: samples only get older) and are not maintained. */
+OSC_D void hb_down_load(HbDownRegs &r, const float *state, uint32_t first, uint32_t n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r.a[k] = state[(size_t)(first + 22u - 2u * k) * n + v];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) r.b[k] = state[(size_t)(first + 23u - 2u * k) * n + v];
+}
+OSC_D void hb_down_store(const HbDownRegs &r, float *state, uint32_t first, uint32_t n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) state[(size_t)(first + 22u - 2u * k) * n + v] = r.a[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) state[(size_t)(first + 23u - 2u * k) * n + v] = r.b[k];
+}
+
+/* Halfband2xUpStage::step with the 12-sample history in registers: h[d] = x[n - d].  The state rows are chronological
+   (row 11 = newest), as hb_up_step's ring is stored. */
+struct HbUpRegs { float h[12]; };
+OSC_D void hb_up_step_r(HbUpRegs &r, float x, float &out0, float &out1) {
+#pragma unroll
+    for (int i = 11; i > 0; --i) r.h[i] = r.h[i - 1];
+    r.h[0] = x;
+    out1 = r.h[5] * (2.0f * kHbCenter);
+    float acc = 0.0f;
+    acc = acc + (r.h[0] + r.h[11]) * kHb0;
+    acc = acc + (r.h[1] + r.h[10]) * kHb1;
+    acc = acc + (r.h[2] + r.h[9]) * kHb2;
+    acc = acc + (r.h[3] + r.h[8]) * kHb3;
+    acc = acc + (r.h[4] + r.h[7]) * kHb4;
+    acc = acc + (r.h[5] + r.h[6]) * kHb5;
+    out0 = acc * 2.0f;
+}
+OSC_D void hb_up_load(HbUpRegs &r, const float *state, uint32_t first, uint32_t n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r.h[k] = state[(size_t)(first + 11u - (uint32_t)k) * n + v];
+}
+OSC_D void hb_up_store(const HbUpRegs &r, float *state, uint32_t first, uint32_t n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) state[(size_t)(first + 11u - (uint32_t)k) * n + v] = r.h[k];
+}
+
 /* ===================================================================== IirHalfband2x == */
 /* oscen-lib/src/resample/halfband_iir.rs:24-143, coeffs.rs:47-54 */
 constexpr float kIirA0 = 0.1355741f, kIirA1 = 0.6975849f, kIirB0 = 0.4253804f, kIirB1 = 0.9055601f;

@@ -11,8 +11,9 @@
  *   [latch]     LatchUp<N> / LatchDown<N>                      resample/latch.rs:6-54
  *
  * Same arithmetic and the same HBM state layout as the hand-written clip_kernel (kernel_resample.cuh):
- * FIR histories are per-thread rings in shared memory stored twice (no modulo on the tap reads),
- * chronological (oldest first) in HBM; IIR all-pass sections and the linear `prev` live in registers.
+ * FIR histories are per-thread shift registers IN REGISTERS (nodes.cuh HbUpRegs / HbDownRegs; until round 2 they were
+ * shared-memory rings stored twice, which capped these kernels at 5 CTAs per SM), chronological (oldest first) in HBM;
+ * IIR all-pass sections and the linear `prev` live in registers as well.
  * Device functions only (the generated translation unit includes this file).
  */
 #pragma once
@@ -29,8 +30,8 @@ OSC_HD constexpr uint32_t up_edge_state_words(int policy, int l) {
 OSC_HD constexpr uint32_t down_edge_state_words(int policy, int l) {
     return policy == EDGE_SINC ? 24u * (uint32_t)l : policy == EDGE_SINC_IIR ? 9u * (uint32_t)l : 0u;
 }
-OSC_HD constexpr uint32_t up_edge_smem_floats(int policy, int l) { return policy == EDGE_SINC ? 24u * (uint32_t)l : 0u; }
-OSC_HD constexpr uint32_t down_edge_smem_floats(int policy, int l) { return policy == EDGE_SINC ? 48u * (uint32_t)l : 0u; }
+OSC_HD constexpr uint32_t up_edge_smem_floats(int /*policy*/, int /*l*/) { return 0u; }      /* no edge needs shared memory any more */
+OSC_HD constexpr uint32_t down_edge_smem_floats(int /*policy*/, int /*l*/) { return 0u; }
 
 OSC_D void iir_hb_load(IirHb &h, const float *p, size_t n, bool with_prev_odd) {
     h.a0 = {p[0], p[n]}; h.a1 = {p[2 * n], p[3 * n]};
@@ -48,20 +49,15 @@ template <int POLICY, int L>
 struct UpEdge {
     static constexpr int N = 1 << L;
     static constexpr int LS = L > 0 ? L : 1;
-    float *ring;                         /* [sinc] this thread's column of L x [24][kCta] */
-    uint32_t head[LS];
+    HbUpRegs fir[LS];                    /* [sinc] one 12-sample history per halfband stage */
     IirHb iir[LS];
     float prev;
 
-    OSC_D void load(const float *state, uint32_t base, uint32_t n, uint32_t vs, float *smem) {
-        ring = smem + threadIdx.x; prev = 0.0f;
+    OSC_D void load(const float *state, uint32_t base, uint32_t n, uint32_t vs, float * /*smem: unused since the histories moved to registers*/) {
+        prev = 0.0f;
         if (POLICY == EDGE_SINC) {
 #pragma unroll
-            for (int s = 0; s < L; ++s) {
-                float *r = ring + s * 24 * (int)kCta;
-                for (uint32_t i = 0; i < 12; ++i) { const float t = state[(size_t)(base + 12u * s + i) * n + vs]; r[i * kCta] = t; r[(i + 12) * kCta] = t; }
-                head[s] = 11u;            /* chronological order, newest last */
-            }
+            for (int s = 0; s < L; ++s) hb_up_load(fir[s], state, base + 12u * (uint32_t)s, n, vs);
         } else if (POLICY == EDGE_SINC_IIR) {
 #pragma unroll
             for (int s = 0; s < L; ++s) iir_hb_load(iir[s], state + (size_t)(base + 8u * s) * n + vs, n, false);
@@ -72,10 +68,7 @@ struct UpEdge {
     OSC_D void store(float *state, uint32_t base, uint32_t n, uint32_t v) const {
         if (POLICY == EDGE_SINC) {
 #pragma unroll
-            for (int s = 0; s < L; ++s) {
-                const float *r = ring + s * 24 * (int)kCta;
-                for (uint32_t i = 0; i < 12; ++i) state[(size_t)(base + 12u * s + i) * n + v] = r[((head[s] + 1u + i) % 12u) * kCta];
-            }
+            for (int s = 0; s < L; ++s) hb_up_store(fir[s], state, base + 12u * (uint32_t)s, n, v);
         } else if (POLICY == EDGE_SINC_IIR) {
 #pragma unroll
             for (int s = 0; s < L; ++s) iir_hb_store(iir[s], state + (size_t)(base + 8u * s) * n + v, n, false);
@@ -91,7 +84,7 @@ struct UpEdge {
                 float nx[N];
 #pragma unroll
                 for (int i = 0; i < N / 2; ++i) if (i < (1 << s))
-                    hb_up_step(ring + s * 24 * (int)kCta, (int)kCta, head[s], buf[i], nx[2 * i], nx[2 * i + 1]);
+                    hb_up_step_r(fir[s], buf[i], nx[2 * i], nx[2 * i + 1]);
 #pragma unroll
                 for (int i = 0; i < N; ++i) if (i < (2 << s)) buf[i] = nx[i];
             }
@@ -123,19 +116,13 @@ template <int POLICY, int L>
 struct DownEdge {
     static constexpr int N = 1 << L;
     static constexpr int LS = L > 0 ? L : 1;
-    float *ring;                         /* [sinc] this thread's column of L x [48][kCta] */
-    uint32_t head[LS];
+    HbDownRegs fir[LS];                  /* [sinc] one polyphase history (12 + 7 samples) per halfband stage */
     IirHb iir[LS];
 
-    OSC_D void load(const float *state, uint32_t base, uint32_t n, uint32_t vs, float *smem) {
-        ring = smem + threadIdx.x;
+    OSC_D void load(const float *state, uint32_t base, uint32_t n, uint32_t vs, float * /*smem: unused*/) {
         if (POLICY == EDGE_SINC) {
 #pragma unroll
-            for (int s = 0; s < L; ++s) {
-                float *r = ring + s * 48 * (int)kCta;
-                for (uint32_t i = 0; i < 24; ++i) { const float t = state[(size_t)(base + 24u * s + i) * n + vs]; r[i * kCta] = t; r[(i + 24) * kCta] = t; }
-                head[s] = 23u;
-            }
+            for (int s = 0; s < L; ++s) hb_down_load(fir[s], state, base + 24u * (uint32_t)s, n, vs);
         } else if (POLICY == EDGE_SINC_IIR) {
 #pragma unroll
             for (int s = 0; s < L; ++s) iir_hb_load(iir[s], state + (size_t)(base + 9u * s) * n + vs, n, true);
@@ -144,10 +131,7 @@ struct DownEdge {
     OSC_D void store(float *state, uint32_t base, uint32_t n, uint32_t v) const {
         if (POLICY == EDGE_SINC) {
 #pragma unroll
-            for (int s = 0; s < L; ++s) {
-                const float *r = ring + s * 48 * (int)kCta;
-                for (uint32_t i = 0; i < 24; ++i) state[(size_t)(base + 24u * s + i) * n + v] = r[((head[s] + 1u + i) % 24u) * kCta];
-            }
+            for (int s = 0; s < L; ++s) hb_down_store(fir[s], state, base + 24u * (uint32_t)s, n, v);
         } else if (POLICY == EDGE_SINC_IIR) {
 #pragma unroll
             for (int s = 0; s < L; ++s) iir_hb_store(iir[s], state + (size_t)(base + 9u * s) * n + v, n, true);
@@ -159,7 +143,7 @@ struct DownEdge {
             for (int s = 0; s < L; ++s) {                  /* stage s consumes pairs in order */
 #pragma unroll
                 for (int i = 0; i < N / 2; ++i) if (i < (N >> (s + 1)))
-                    buf[i] = hb_down_step(ring + s * 48 * (int)kCta, (int)kCta, head[s], buf[2 * i], buf[2 * i + 1]);
+                    buf[i] = hb_down_step_r(fir[s], buf[2 * i], buf[2 * i + 1]);
             }
             return buf[0];
         } else if (POLICY == EDGE_SINC_IIR) {

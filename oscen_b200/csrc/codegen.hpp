@@ -274,7 +274,9 @@ struct Emitter {
         line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
         line(6, "const Event e = ec.ev[q];");
         line(6, "if (e.input_id == kEventGate) continue;");
-        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(6, fmt("if (e.input_id == %uu) P[%u] = e.scalar;", i, i)); }
+        /* select form: `if (id == k) P[k] = x` chains are turned into ONE store with a run-time index by the compiler, which moves P
+           from registers to local memory for the whole kernel */
+        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(6, fmt("P[%u] = (e.input_id == %uu) ? e.scalar : P[%u];", i, i, i)); }
         line(6, fmt("if (e.input_id < %uu) a.pv[(size_t)e.input_id * n + v] = e.scalar;", ni));
         line(5, "}");
         line(4, "}");

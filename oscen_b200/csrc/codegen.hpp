@@ -253,80 +253,17 @@ struct Emitter {
                 line(1, "adsr_begin_block(" + N(i) + ", " + D(i) + ", ev0);");
             }
         }
-        line(1, "for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {");
-        line(2, "const uint32_t fe = min(kTileF, frames - f0);");
-        line(2, "for (uint32_t ff = 0; ff < fe; ++ff) {");
-        line(3, "const uint32_t f = f0 + ff;");
-        line(3, "float y = 0.0f;");
-        line(3, "if (active) {");
-        /* ---- tick_ramps: ramped inputs are read through `.current` (codegen/emit_node.rs:317-321) */
-        if (ni) {
-            line(4, "if (ramp_mask) {");
-            line(5, "const float *row = a.ptab + (size_t)f * kMaxInputs;");
-            for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(5, fmt("if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i)); }
-            line(4, "}");
-        }
-        /* ---- this frame's events: value edges are assigned before process_event_inputs() */
-        line(4, "const bool due = ec.due(f);");
-        line(4, "uint32_t ev_end = ec.i;");
-        line(4, "if (due) {");
-        line(5, "ev_end = ec.end_of_frame(f);");
-        line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
-        line(6, "const Event e = ec.ev[q];");
-        line(6, "if (e.input_id == kEventGate) continue;");
-        /* select form: `if (id == k) P[k] = x` chains are turned into ONE store with a run-time index by the compiler, which moves P
-           from registers to local memory for the whole kernel */
-        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(6, fmt("P[%u] = (e.input_id == %uu) ? e.scalar : P[%u];", i, i, i)); }
-        line(6, fmt("if (e.input_id < %uu) a.pv[(size_t)e.input_id * n + v] = e.scalar;", ni));
-        line(5, "}");
-        line(4, "}");
-        line(4, "const bool changed = (ramp_mask != 0u) || due;    /* a value input may have moved this frame */");
-        line(4, "(void)changed;");
-        for (int i = 0; i < n_nodes; ++i) {
-            const plan::Node &nd = g.nodes[i];
-            if (nd.type == T::Adsr && !(P_is_const(i, 0) && P_is_const(i, 1) && P_is_const(i, 3)))
-                line(4, "if (changed && adsr_derived_stale(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ")) adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", " + SR(i) + ");");
-            if (nd.type == T::FmOperator && !(P_is_const(i, 0) && P_is_const(i, 1)))
-                line(4, "if (changed) " + N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");");    /* an inner-rate node runs at sr * N */
-        }
-        bool any_gate = false;
-        for (int i = 0; i < n_nodes; ++i) any_gate |= (g.nodes[i].type == T::Adsr || g.nodes[i].type == T::AmpSource || g.nodes[i].type == T::OscBank) && g.nodes[i].gate;
-        line(4, "if (due) {");
-        if (any_gate) {
-            line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
-            line(6, "if (ec.ev[q].input_id != kEventGate) continue;");
-            line(6, "const float gv = ec.ev[q].scalar;");
-            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr && g.nodes[i].gate)
-                line(6, "adsr_on_gate(" + N(i) + ", gv, " + P(i, 0) + ", " + P(i, 3) + ", " + D(i) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
-            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].gate) {
-                if (g.nodes[i].type == T::AmpSource)
-                    line(6, "ampsrc_on_gate(" + N(i) + ", (size_t)n, gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
-                if (g.nodes[i].type == T::OscBank)
-                    line(6, "oscbank_on_gate(" + N(i) + ", (size_t)n, gv);    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
-            }
-            line(5, "}");
-        }
-        line(5, "ec.advance(ev_end);");
-        line(4, "}");
-        {
-            bool any_adsr = false;
-            for (int i = 0; i < n_nodes; ++i) any_adsr |= g.nodes[i].type == T::Adsr;
-            if (any_adsr && hoist_adsr) {
-                line(4, "if (changed) {");
-                for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
-                    line(5, "adsr_refresh(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");");
-                line(4, "}");
-            }
-        }
-        if (has_in) line(4, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
         /* ---- the walk: nodes in topological order (multirate graphs: per phase, emit_frame.rs:114-176) */
+        bool plain_mode = false;      /* emitting the plain-segment copy of the walk (segmented frame loop, below) */
         auto emit_node = [&](int i, int ind) {
             const plan::Node &nd = g.nodes[i];
             const std::string o = "const float " + S(i) + " = ";
             const std::string cm = "    /* " + nd.name + " */";
             switch (nd.type) {
             case T::Adsr:
-                if (hoist_adsr) line(ind, o + "adsr_process_t<false>(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
+                if (plain_mode) { const std::string k = std::to_string(i);
+                    line(ind, o + "any_rl ? adsr_plain_rel(" + N(i) + ", ad" + k + ", rl" + k + ", tg" + k + ", kk" + k + ") : adsr_ad(" + N(i) + ", ad" + k + ", tg" + k + ", kk" + k + ");" + cm); }
+                else if (hoist_adsr) line(ind, o + "adsr_process_t<false>(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
                 else line(ind, o + "adsr_process(" + N(i) + ", " + P(i, 2) + ", " + D(i) + ");" + cm);
                 break;
             case T::FmOperator: line(ind, o + "fmop_process_k(" + N(i) + ", " + IN(i, 0, 4) + ", " + P(i, 2) + ", " + IN(i, 1, 5) + ", " + P(i, 3) + ", sk);" + cm); break;
@@ -393,29 +330,149 @@ struct Emitter {
                 break;
             }
         };
-        if (!multirate) {
-            for (int i : p.order) emit_node(i, 4);
-        } else {
-            const std::vector<int> ph = phases();
-            const std::string ns = std::to_string(NI);
-            for (int i : p.order) if (ph[i] == 0) emit_node(i, 4);
-            for (int i : p.order) if (ph[i] == 1) {                       /* step 4: Up-edge warm-up */
-                line(4, "float u" + std::to_string(i) + "[" + ns + "]; " + N(i) + ".up(" + IN(i, 0, -1) + ", u" + std::to_string(i) + ");    /* " + g.nodes[i].name + " */");
+        /* the walk of one frame: nodes in topological order (multirate graphs: per phase, emit_frame.rs:114-176) */
+        auto emit_walk = [&](int ind) {
+            if (!multirate) {
+                for (int i : p.order) emit_node(i, ind);
+            } else {
+                const std::vector<int> ph = phases();
+                const std::string ns = std::to_string(NI);
+                for (int i : p.order) if (ph[i] == 0) emit_node(i, ind);
+                for (int i : p.order) if (ph[i] == 1) {                       /* step 4: Up-edge warm-up */
+                    line(ind, "float u" + std::to_string(i) + "[" + ns + "]; " + N(i) + ".up(" + IN(i, 0, -1) + ", u" + std::to_string(i) + ");    /* " + g.nodes[i].name + " */");
+                }
+                for (int i : p.order) if (ph[i] == 3) line(ind, "float w" + std::to_string(i) + "[" + ns + "];");      /* step 5: Down accumulators */
+                line(ind, "_Pragma(\"unroll\") for (int inner = 0; inner < " + ns + "; ++inner) {    /* step 6: N inner ticks */");
+                for (int i : p.order) if (ph[i] == 1) line(ind + 1, "const float " + S(i) + " = u" + std::to_string(i) + "[inner];");
+                for (int i : p.order) if (ph[i] == 2) emit_node(i, ind + 1);
+                for (int i : p.order) if (ph[i] == 3) line(ind + 1, "w" + std::to_string(i) + "[inner] = " + IN(i, 0, -1) + ";");
+                line(ind, "}");
+                for (int i : p.order) if (ph[i] == 3)                         /* step 7: downsample once per outer tick */
+                    line(ind, "const float " + S(i) + " = " + N(i) + ".down(w" + std::to_string(i) + ");    /* " + g.nodes[i].name + " */");
+                for (int i : p.order) if (ph[i] == 4) emit_node(i, ind);        /* step 7.5: post-inner outer nodes */
             }
-            for (int i : p.order) if (ph[i] == 3) line(4, "float w" + std::to_string(i) + "[" + ns + "];");      /* step 5: Down accumulators */
-            line(4, "_Pragma(\"unroll\") for (int inner = 0; inner < " + ns + "; ++inner) {    /* step 6: N inner ticks */");
-            for (int i : p.order) if (ph[i] == 1) line(5, "const float " + S(i) + " = u" + std::to_string(i) + "[inner];");
-            for (int i : p.order) if (ph[i] == 2) emit_node(i, 5);
-            for (int i : p.order) if (ph[i] == 3) line(5, "w" + std::to_string(i) + "[inner] = " + IN(i, 0, -1) + ";");
+        };
+        /* Segmented frame loop: per WARP, L = frames until the first lane's next event or envelope
+           stage completion (one REDUX.MIN); L plain frames walk the nodes with no ramp / event / `changed` code and the envelopes
+           in their segment form (Attack / Decay: one-pole step, Sustain / Idle: a constant, Release behind a warp-uniform test) —
+           the scheme of kernel_fm_seg.cuh, which itself follows the reference's sub-block split at event frames
+           (codegen/mod.rs:836-872); then ONE general frame (the full per-frame body below).  Frame 0 of a block and every
+           frame of a block with a ramping input are general.  Same operations per frame either way: the same bits. */
+        bool any_adsr_node = false, inner_adsr = false;
+        for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr) { any_adsr_node = true; inner_adsr |= g.nodes[i].rate_log2 > 0; }
+        /* (an envelope inside an oversampled section counts its stage down in inner ticks: such graphs keep the per-frame loop) */
+        const bool segmented = hoist_adsr && !inner_adsr && env_int("OSCEN_B200_JIT_SEGMENTS", 1) != 0;
+        line(1, "for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {");
+        line(2, "const uint32_t fe = min(kTileF, frames - f0);");
+        if (segmented) {
+            line(2, "uint32_t ff = 0;");
+            line(2, "while (ff < fe) {");
+            line(3, "const uint32_t f = f0 + ff;");
+            line(3, "{");
+            line(4, "uint32_t np = (ramp_mask != 0u || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);");
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
+                line(4, "np = oscen::umin(np, adsr_plain_frames(" + N(i) + "));");
+            line(4, "const uint32_t L = oscen::umin(__reduce_min_sync(0xffffffffu, np), fe - ff);");
+            line(4, "if (L > 0u) {");
+            std::string rl_any;
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr) {
+                const std::string k = std::to_string(i), h = "h" + k;
+                line(5, "const bool ad" + k + " = (" + N(i) + ".stage == ST_ATTACK) | (" + N(i) + ".stage == ST_DECAY), rl" + k + " = " + N(i) + ".stage == ST_RELEASE;");
+                line(5, "const float tg" + k + " = " + N(i) + ".stage == ST_ATTACK ? 1.0f : " + h + ".sus, kk" + k + " = " + N(i) + ".stage == ST_ATTACK ? " + D(i) + ".a_k : " + D(i) + ".d_k;");
+                rl_any += (rl_any.empty() ? "" : " | ") + std::string("rl") + k;
+            }
+            if (any_adsr_node) line(5, "const bool any_rl = __any_sync(0xffffffffu, " + rl_any + ");");
+            line(5, "for (uint32_t i_ = 0; i_ < L; ++i_) {");
+            line(6, "const uint32_t f = f0 + ff + i_;");
+            line(6, "float y = 0.0f;");
+            line(6, "if (active) {");
+            if (has_in) line(7, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
+            plain_mode = true;
+            emit_walk(7);
+            plain_mode = false;
+            line(7, "y = " + S(g.output.node, g.output.port) + ";    /* -> " + g.output_name + " */");
+            line(7, "if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;");
+            line(6, "}");
+            line(6, "tile[(ff + i_) * kTileW + col] = y;");
+            line(5, "}");
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
+                line(5, "if (!any_rl && ad" + std::to_string(i) + ") " + N(i) + ".rem -= L;    /* the Release form counts down per frame itself */");
+            line(5, "ff += L;");
+            line(5, "continue;");
             line(4, "}");
-            for (int i : p.order) if (ph[i] == 3)                         /* step 7: downsample once per outer tick */
-                line(4, "const float " + S(i) + " = " + N(i) + ".down(w" + std::to_string(i) + ");    /* " + g.nodes[i].name + " */");
-            for (int i : p.order) if (ph[i] == 4) emit_node(i, 4);        /* step 7.5: post-inner outer nodes */
+            line(3, "}");
+        } else {
+            line(2, "for (uint32_t ff = 0; ff < fe; ++ff) {");
+            line(3, "const uint32_t f = f0 + ff;");
         }
+        line(3, "float y = 0.0f;");
+        line(3, "if (active) {");
+        /* ---- tick_ramps: ramped inputs are read through `.current` (codegen/emit_node.rs:317-321) */
+        if (ni) {
+            line(4, "if (ramp_mask) {");
+            line(5, "const float *row = a.ptab + (size_t)f * kMaxInputs;");
+            for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(5, fmt("if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i)); }
+            line(4, "}");
+        }
+        /* ---- this frame's events: value edges are assigned before process_event_inputs() */
+        line(4, "const bool due = ec.due(f);");
+        line(4, "uint32_t ev_end = ec.i;");
+        line(4, "if (due) {");
+        line(5, "ev_end = ec.end_of_frame(f);");
+        line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
+        line(6, "const Event e = ec.ev[q];");
+        line(6, "if (e.input_id == kEventGate) continue;");
+        /* select form: `if (id == k) P[k] = x` chains are turned into ONE store with a run-time index by the compiler, which moves P
+           from registers to local memory for the whole kernel */
+        for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u)) { line(6, fmt("P[%u] = (e.input_id == %uu) ? e.scalar : P[%u];", i, i, i)); }
+        line(6, fmt("if (e.input_id < %uu) a.pv[(size_t)e.input_id * n + v] = e.scalar;", ni));
+        line(5, "}");
+        line(4, "}");
+        line(4, "const bool changed = (ramp_mask != 0u) || due;    /* a value input may have moved this frame */");
+        line(4, "(void)changed;");
+        for (int i = 0; i < n_nodes; ++i) {
+            const plan::Node &nd = g.nodes[i];
+            if (nd.type == T::Adsr && !(P_is_const(i, 0) && P_is_const(i, 1) && P_is_const(i, 3)))
+                line(4, "if (changed && adsr_derived_stale(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ")) adsr_derive_r(" + D(i) + ", " + P(i, 0) + ", " + P(i, 1) + ", " + P(i, 3) + ", " + SR(i) + ");");
+            if (nd.type == T::FmOperator && !(P_is_const(i, 0) && P_is_const(i, 1)))
+                line(4, "if (changed) " + N(i) + ".inc = fmop_phase_inc(" + P(i, 0) + ", " + P(i, 1) + ", " + SR(i) + ");");    /* an inner-rate node runs at sr * N */
+        }
+        bool any_gate = false;
+        for (int i = 0; i < n_nodes; ++i) any_gate |= (g.nodes[i].type == T::Adsr || g.nodes[i].type == T::AmpSource || g.nodes[i].type == T::OscBank) && g.nodes[i].gate;
+        line(4, "if (due) {");
+        if (any_gate) {
+            line(5, "for (uint32_t q = ec.i; q < ev_end; ++q) {");
+            line(6, "if (ec.ev[q].input_id != kEventGate) continue;");
+            line(6, "const float gv = ec.ev[q].scalar;");
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr && g.nodes[i].gate)
+                line(6, "adsr_on_gate(" + N(i) + ", gv, " + P(i, 0) + ", " + P(i, 3) + ", " + D(i) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+            for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].gate) {
+                if (g.nodes[i].type == T::AmpSource)
+                    line(6, "ampsrc_on_gate(" + N(i) + ", (size_t)n, gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+                if (g.nodes[i].type == T::OscBank)
+                    line(6, "oscbank_on_gate(" + N(i) + ", (size_t)n, gv);    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+            }
+            line(5, "}");
+        }
+        line(5, "ec.advance(ev_end);");
+        line(4, "}");
+        {
+            bool any_adsr = false;
+            for (int i = 0; i < n_nodes; ++i) any_adsr |= g.nodes[i].type == T::Adsr;
+            if (any_adsr && hoist_adsr) {
+                line(4, "if (changed) {");
+                for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
+                    line(5, "adsr_refresh(" + N(i) + ", h" + std::to_string(i) + ", " + P(i, 2) + ", " + D(i) + ");");
+                line(4, "}");
+            }
+        }
+        if (has_in) line(4, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
+        emit_walk(4);
         line(4, "y = " + S(g.output.node, g.output.port) + ";    /* -> " + g.output_name + " */");
         line(4, "if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;");
         line(3, "}");
         line(3, "tile[ff * kTileW + col] = y;");
+        if (segmented) line(3, "ff += 1u;");
         line(2, "}");
         if (g.post_tremolo) {
             auto pid = [&](int k) { return g.post_pid[k] == plan::kNoValue ? std::string("kNoPostInput") : std::to_string(g.post_pid[k]) + "u"; };

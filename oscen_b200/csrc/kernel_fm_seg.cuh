@@ -67,25 +67,6 @@ OSC_D float fmop_process_r(FmOpState &s, float phase_mod, float feedback, float 
     return out;
 }
 
-/* plain frame of one envelope when some lane of the warp is in Release: `ad` / `rl` = this lane is in Attack|Decay /
-   Release with rem >= 2 for the whole segment; a static lane (Sustain, Idle) keeps `level`.  The countdown runs per frame
-   here (the Release increment divides by it).  Segments without Release lanes use adsr_ad: no division — its slow path is
-   a call, and a call inside the frame loop would force loop-invariant constants to be rebuilt after it. */
-OSC_D float adsr_plain_rel(AdsrState &s, bool ad, bool rl, float tgt, float k) {
-    if (ad | rl) {
-        float delta;
-        if (rl) {
-            const float cur = clampf(s.level, 0.0f, 1.0f);
-            delta = (cur <= 0.0f) ? 0.0f : -cur / (float)s.rem;
-        } else {
-            delta = (tgt - s.level) * k;
-        }
-        s.level = clampf(s.level + delta, 0.0f, 1.0f);
-        s.rem -= 1u;
-    }
-    return s.level;
-}
-
 /* TptFilter::process with cutoff fixed for the segment (coefficients current): the five-line core (mod.rs:101-123) */
 OSC_D float tpt_core(TptState &s, float input) {
     const float high = (input - s.z0 * s.k - s.z1) * s.h;
@@ -135,16 +116,6 @@ struct FmStageA { float o3, env2, env1, envf; };
 struct FmStageB { float pm1, env1, envf; };
 struct FmConsts { float max_cutoff, sr, two_sr, period; };
 
-/* one-pole envelope frame for a lane in Attack|Decay, a no-op for a static lane (no lane of the warp is in Release) */
-/* The reference clamps the result to [0, 1] (adsr.rs:213-225); here the clamp is the identity and is left out: level and
-   tgt are in [0, 1] (or NaN, which both forms pass through), k = 1 - exp(-4.6051702 / n) <= 0.99 for every step count
-   n >= 1, so |RN(RN(tgt - level) * k)| < |tgt - level| and the exact sum lies strictly between level and tgt; rounding to
-   nearest is monotonic, so the rounded sum lies in [min(level, tgt), max(level, tgt)].  -0 is kept by both forms. */
-OSC_D float adsr_ad(AdsrState &s, bool ad, float tgt, float k) {
-    const float nl = s.level + (tgt - s.level) * k;
-    s.level = ad ? nl : s.level;
-    return s.level;
-}
 OSC_D FmStageA fm_stage_a(FmRegs &r, const FmEnvMode &m, float lvl3, float fb3, const OmSinRegs &sk) {
     FmStageA o;
     const float env3 = adsr_ad(r.e3, m.ad3, m.tg3, m.kk3);

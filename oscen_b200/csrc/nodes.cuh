@@ -226,6 +226,42 @@ OSC_D float adsr_process(AdsrState &s, float sustain_in, const AdsrDerived &d) {
     return adsr_process_t<true>(s, h, sustain_in, d);
 }
 
+/* ---- segment forms of the envelope (kernel_fm_seg.cuh, the plain node kernels, generated kernels): a warp runs L "plain"
+   frames between event / stage boundaries with each lane's stage fixed */
+/* frames this envelope can run before its stage completes (the completing frame itself is a general frame) */
+OSC_D uint32_t adsr_plain_frames(const AdsrState &s) {
+    const bool timed = (s.stage == ST_ATTACK) | (s.stage == ST_DECAY) | (s.stage == ST_RELEASE);
+    return timed ? (s.rem >= 2u ? s.rem - 1u : 0u) : 0x7FFFFFFFu;
+}
+/* plain frame of one envelope when some lane of the warp is in Release: `ad` / `rl` = this lane is in Attack|Decay /
+   Release with rem >= 2 for the whole segment; a static lane (Sustain, Idle) keeps `level`.  The countdown runs per frame
+   here (the Release increment divides by it).  Segments without Release lanes use adsr_ad: no division — its slow path is
+   a call, and a call inside the frame loop would force loop-invariant constants to be rebuilt after it. */
+OSC_D float adsr_plain_rel(AdsrState &s, bool ad, bool rl, float tgt, float k) {
+    if (ad | rl) {
+        float delta;
+        if (rl) {
+            const float cur = clampf(s.level, 0.0f, 1.0f);
+            delta = (cur <= 0.0f) ? 0.0f : -cur / (float)s.rem;
+        } else {
+            delta = (tgt - s.level) * k;
+        }
+        s.level = clampf(s.level + delta, 0.0f, 1.0f);
+        s.rem -= 1u;
+    }
+    return s.level;
+}
+
+/* one-pole envelope frame for a lane in Attack|Decay, a no-op for a static lane (no lane of the warp is in Release) */
+/* The reference clamps the result to [0, 1] (adsr.rs:213-225); here the clamp is the identity and is left out: level and
+   tgt are in [0, 1] (or NaN, which both forms pass through), k = 1 - exp(-4.6051702 / n) <= 0.99 for every step count
+   n >= 1, so |RN(RN(tgt - level) * k)| < |tgt - level| and the exact sum lies strictly between level and tgt; rounding to
+   nearest is monotonic, so the rounded sum lies in [min(level, tgt), max(level, tgt)].  -0 is kept by both forms. */
+OSC_D float adsr_ad(AdsrState &s, bool ad, float tgt, float k) {
+    const float nl = s.level + (tgt - s.level) * k;
+    s.level = ad ? nl : s.level;
+    return s.level;
+}
 /* =================================================================== FmOperator == */
 /* examples/fm-synth/src/nodes/fm_operator.rs:58-76 */
 struct FmOpState {

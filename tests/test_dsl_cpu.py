@@ -265,7 +265,9 @@ def test_generated_kernel_walks_nodes_in_topological_order():
                  ("op1_mod_mixer", "op1_osc"), ("op1_osc", "filter"), ("env_filter", "filter_env_gain"),
                  ("filter_env_gain", "cutoff_mod"), ("cutoff_mod", "filter"), ("filter", "output_gain")]:
         assert pos[a] < pos[b], (a, b)
-    assert src.count("adsr_on_gate(") == 4 and src.count("fmop_process_k(") == 3
+    # the walk is emitted twice: the plain-segment copy (envelopes in their segment form) and the general frame
+    assert src.count("adsr_on_gate(") == 4 and src.count("fmop_process_k(") == 6 and src.count("adsr_ad(") == 4
+    assert src.count("__reduce_min_sync(") == 1 and "oscen::umin(np, adsr_plain_frames(n0))" in src
     # literals are emitted bit-exactly
     assert "0x3e99999au /* 0.300000012 */" in src      # output_gain = Gain::new(0.3)
 
@@ -294,7 +296,7 @@ def test_multirate_lowering_inserts_one_resampler_per_cross_rate_edge():
     assert "state words per voice: 49" in d                    # phase + SincDownFir<4>: 2 stages x 24 taps (== the built-in SAT layout)
     src = g.codegen()
     assert "DownEdge<0, 2>" in src and "const float sri = sr * 4.0f;" in src and 'for (int inner = 0; inner < 4; ++inner)' in src
-    assert src.count(", sri);") == 1                           # only the oscillator sees the inner sample rate
+    assert src.count(", sri);") == 2                           # only the oscillator sees the inner sample rate (in both copies of the walk: plain segment + general frame)
     assert g.jit_check() > 10000
 
 

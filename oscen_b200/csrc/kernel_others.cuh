@@ -62,9 +62,29 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
 #pragma unroll 8
             for (uint32_t ff = 0; ff < fe; ++ff) isum[ff * kCta + threadIdx.x] = __ldcs(a.stream_in + (size_t)(f0 + ff) * n + v);
         }
-#pragma unroll 1
-        for (uint32_t ff = 0; ff < fe; ++ff) {
+        /* segmented like the generated kernels (codegen.hpp): per warp, L frames until the first lane's next value event run
+           without ramp / event code (so the filters' parameter tests are loop-invariant), then one general frame */
+        uint32_t ff = 0;
+        while (ff < fe) {
             const uint32_t f = f0 + ff;
+            const uint32_t np = ramp_mask != 0u ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);
+            const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
+            if (L > 0u) {
+#pragma unroll 1
+                for (uint32_t i = 0; i < L; ++i) {
+                    float y = 0.0f;
+                    if (active) {
+                        const float x = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? isum[(ff + i) * kCta + threadIdx.x] : 0.0f);
+                        const float ya = lp18_process(fa, x, prm.P[0], 0.0f, prm.P[2], sr);
+                        const float yb = lp18_process(fb, x, prm.P[1], 0.0f, prm.P[2], sr);
+                        y = ya - yb;
+                        if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;
+                    }
+                    tile[(ff + i) * kTileW + col] = y;
+                }
+                ff += L;
+                continue;
+            }
             float y = 0.0f;
             if (active) {
                 prm.ramps(a, ramp_mask, f);
@@ -80,6 +100,7 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
                 if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
             }
             tile[ff * kTileW + col] = y;
+            ff += 1u;
         }
         tile_flush_mono(a, tile, isum, f0, fe);
     }
@@ -118,35 +139,51 @@ __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ Kerne
         const uint32_t fe = min(kTileF, frames - f0);
         /* Inactive lanes of the last CTA render voice 0 again (no events, no stores): a frame body that updates the
            register histories under `if (active)` makes every history value a two-way merge at the end of the frame, which
-           pins each shift to a real move; unconditional, the unrolled body renames them away. */
-#pragma unroll 4
-        for (uint32_t ff = 0; ff < fe; ++ff) {
+           pins each shift to a real move; unconditional, the unrolled body renames them away.
+           Segmented like the generated kernels: per warp, L frames until the first lane's next value event run without ramp /
+           event code (frequency / sample-rate division and the other parameter work become loop-invariant), then one
+           general frame. */
+#define OSC_SAT_FRAME(FF)                                                                                              \
+        {                                                                                                              \
+            float y;                                                                                                   \
+            if (FACTOR == 1) {                                                                                         \
+                const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);     \
+                y = hardclip_process(o);                                                                               \
+            } else {                                                                                                   \
+                float buf[4];                                                                                          \
+                _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                                        \
+                    const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner); \
+                    buf[i] = hardclip_process(o);                                                                      \
+                }                                                                                                      \
+                /* SincDownFir<4>::downsample: stage 0 twice, stage 1 once (sinc_fir.rs:233-249) */                    \
+                const float s0 = hb_down_step_r(r1, buf[0], buf[1]);                                                   \
+                const float s1 = hb_down_step_r(r1, buf[2], buf[3]);                                                   \
+                y = hb_down_step_r(r2, s0, s1);                                                                        \
+            }                                                                                                          \
+            if (keepv) a.voice_out[(f0 + (FF)) * n + v] = y;   /* n_voices * 512 < 2^32 (checked at create) */          \
+            tile[(FF) * kTileW + col] = active ? y : 0.0f;                                                             \
+        }
+        uint32_t ff = 0;
+        while (ff < fe) {
             const uint32_t f = f0 + ff;
-            float y;
+            const uint32_t np = ramp_mask != 0u ? 0u : ec.next_frame - f;
+            const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
+            if (L > 0u) {
+#pragma unroll 4
+                for (uint32_t i = 0; i < L; ++i) OSC_SAT_FRAME(ff + i)
+                ff += L;
+                continue;
+            }
             prm.ramps(a, ramp_mask, f);
             if (ec.due(f)) {
                 const uint32_t j = ec.end_of_frame(f);
                 for (uint32_t q = ec.i; q < j; ++q) prm.value_event(a, ec.ev[q], v);
                 ec.advance(j);
             }
-            if (FACTOR == 1) {
-                const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
-                y = hardclip_process(o);
-            } else {
-                float buf[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float o = polyblep_process<WAVE_SAW>(phase, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr_inner);
-                    buf[i] = hardclip_process(o);
-                }
-                /* SincDownFir<4>::downsample: stage 0 twice, stage 1 once (sinc_fir.rs:233-249) */
-                const float s0 = hb_down_step_r(r1, buf[0], buf[1]);
-                const float s1 = hb_down_step_r(r1, buf[2], buf[3]);
-                y = hb_down_step_r(r2, s0, s1);
-            }
-            if (keepv) a.voice_out[f * n + v] = y;             /* n_voices * 512 < 2^32 (checked at create) */
-            tile[ff * kTileW + col] = active ? y : 0.0f;
+            OSC_SAT_FRAME(ff)
+            ff += 1u;
         }
+#undef OSC_SAT_FRAME
         tile_flush_mono(a, tile, isum, f0, fe);
     }
     if (active) {

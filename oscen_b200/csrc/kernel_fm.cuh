@@ -33,7 +33,7 @@ enum : uint32_t {   /* == OSCEN_B200_FM_* */
 };
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kCta, 8) fm_voice_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ __align__(128) float tile[kTileF * kTileW];    /* also the TMA staging area for the state rows */
     __shared__ float isum[kTileF * kCta];
     __shared__ __align__(8) unsigned long long state_bar;
@@ -107,8 +107,55 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        for (uint32_t ff = 0; ff < fe; ++ff) {
+        uint32_t ff = 0;
+        while (ff < fe) {
             const uint32_t f = f0 + ff;
+            /* ---- plain segment (round 2, the scheme of the generated kernels): per warp, L frames until the first lane's next
+               event or envelope stage completion run without ramp / event / staleness code, the envelopes in their segment
+               form; every per-voice parameter is loop-invariant there.  Frame 0 and ramp blocks stay per-frame. */
+            {
+                uint32_t np = (ramp_mask != 0u || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);
+                np = umin(umin(np, adsr_plain_frames(e3)), umin(adsr_plain_frames(e2), umin(adsr_plain_frames(e1), adsr_plain_frames(ef))));
+                const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
+                if (L > 0u) {
+#define OSC_FM_MODE(e, h, d, X)                                                                                      \
+                    const bool ad##X = (e.stage == ST_ATTACK) | (e.stage == ST_DECAY), rl##X = e.stage == ST_RELEASE;  \
+                    const float tg##X = e.stage == ST_ATTACK ? 1.0f : h.sus, kk##X = e.stage == ST_ATTACK ? d.a_k : d.d_k;
+                    OSC_FM_MODE(e3, h3, d3, 3) OSC_FM_MODE(e2, h2, d2, 2) OSC_FM_MODE(e1, h1, d1, 1) OSC_FM_MODE(ef, hf, df, F)
+#undef OSC_FM_MODE
+                    const bool any_rl = __any_sync(0xffffffffu, rl3 | rl2 | rl1 | rlF);
+                    for (uint32_t i = 0; i < L; ++i) {
+                        float y = 0.0f;
+                        if (active) {
+                            const float env3 = any_rl ? adsr_plain_rel(e3, ad3, rl3, tg3, kk3) : adsr_ad(e3, ad3, tg3, kk3);
+                            const float env2 = any_rl ? adsr_plain_rel(e2, ad2, rl2, tg2, kk2) : adsr_ad(e2, ad2, tg2, kk2);
+                            const float env1 = any_rl ? adsr_plain_rel(e1, ad1, rl1, tg1, kk1) : adsr_ad(e1, ad1, tg1, kk1);
+                            const float envf = any_rl ? adsr_plain_rel(ef, adF, rlF, tgF, kkF) : adsr_ad(ef, adF, tgF, kkF);
+                            const float feg = envf * P[I_ENV_AMT];
+                            const float cutoff = feg + P[I_CUTOFF];
+                            const float o3 = fmop_process_k(op3, 0.0f, P[I_OP3_FB], env3, P[I_OP3_LEVEL], sk);
+                            const float mix = clampf(P[I_ROUTE], 0.0f, 1.0f);
+                            const float xa = o3 * (1.0f - mix);
+                            const float xb = o3 * mix;
+                            const float o2 = fmop_process_k(op2, xa, P[I_OP2_FB], env2, P[I_OP2_LEVEL], sk);
+                            const float pm1 = o2 + xb;
+                            const float o1 = fmop_process_k(op1, pm1, 0.0f, env1, 1.0f, sk);
+                            const float lp = tpt_process(tp, o1, cutoff, P[I_RES], 0.0f, sr);
+                            y = lp * 0.3f;
+                            if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;
+                        }
+                        tile[(ff + i) * kTileW + col] = y;
+                    }
+                    if (!any_rl) {                                      /* the Release form counts down per frame itself */
+                        if (ad3) e3.rem -= L;
+                        if (ad2) e2.rem -= L;
+                        if (ad1) e1.rem -= L;
+                        if (adF) ef.rem -= L;
+                    }
+                    ff += L;
+                    continue;
+                }
+            }
             float y = 0.0f;
             if (active) {
                 if (GENERAL && ramp_mask) {               /* ramped inputs read `.current` */
@@ -126,7 +173,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                         if (e.input_id != kEventGate) {
                             if (GENERAL) {
 #pragma unroll
-                                for (uint32_t i = 0; i < I_FM_N; ++i) if (e.input_id == i) P[i] = e.scalar;
+                                for (uint32_t i = 0; i < I_FM_N; ++i) P[i] = (e.input_id == i) ? e.scalar : P[i];   /* select form: keeps P in registers */
                             } else {
                                 P[I_FREQ] = e.scalar;       /* host guarantees id == frequency */
                             }
@@ -177,6 +224,7 @@ __global__ void __launch_bounds__(kCta) fm_voice_kernel(const __grid_constant__ 
                 if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
             }
             tile[ff * kTileW + col] = y;
+            ff += 1u;
         }
         tile_flush_mono(a, tile, isum, f0, fe);
     }

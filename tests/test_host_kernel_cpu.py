@@ -206,6 +206,22 @@ def test_host_executed_hand_written_fm_kernel_matches_oracle_bank_both_instantia
     assert (np.abs(mh.astype(np.float64) - mr.astype(np.float64)) <= 1e-6 + 2e-6 * scale).all()
 
 
+def test_host_executed_generated_kernel_without_segments_matches_too(monkeypatch):
+    """OSCEN_B200_JIT_SEGMENTS=0: the generator's per-frame loop of round 1 (kept as the A/B and fallback form) renders the same
+    bits as the segmented default on a script with gates, a ramp and per-voice value events"""
+    n, vpi = 24, 8
+    outs = []
+    for seg in ("1", "0"):
+        monkeypatch.setenv("OSCEN_B200_JIT_SEGMENTS", seg)
+        eng = HostEngine(text("voice_fm3.graph"), n, vpi)
+        src = eng.graph.codegen()
+        assert ("__reduce_min_sync(" in src) == (seg == "1")
+        outs.append(_fm_bank_script(eng, n, blocks=3, frames=128))
+    ref = _fm_bank_script(O.OracleBank(O.K_FM, n, vpi), n, blocks=3, frames=128)
+    for got in outs:
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+
+
 @pytest.mark.parametrize("seed", [1047, 1131])
 def test_host_fuzzer_findings_stay_fixed(seed):
     """the two multirate graphs of tools/fuzz_host_kernels.py (seeds 777000 + 1047 / 1131) that exposed the inner-rate

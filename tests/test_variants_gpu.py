@@ -107,3 +107,41 @@ def test_fm_general_kernel_with_tma_state_handoff_matches_oracle(n):
     assert "fm_voice_kernel" in name, name
     assert np.abs(outs[0]).max() > 0.01
     assert np.array_equal(outs[1], outs[0]), float(np.abs(outs[1] - outs[0]).max())
+
+
+
+@pytest.mark.parametrize("graph_file,kind,vpi", [("voice_fm3.graph", O.K_FM, 8), ("synth_adsr.graph", O.K_SYNTH_ADSR, 1), ("sat_4x.graph", O.K_SAT4, 1)])
+def test_generated_kernel_with_and_without_segments_matches_oracle(graph_file, kind, vpi):
+    """OSCEN_B200_JIT_SEGMENTS=0|1: the generator's per-frame loop and its segmented default, against the oracle bank of the
+    same graph (gates where the graph has them, a value change between blocks, odd block sizes)"""
+    from oscen_b200 import abi
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "graphs", graph_file)).read()
+    n = 136 if vpi == 8 else 130
+    old = os.environ.get("OSCEN_B200_JIT_SEGMENTS")
+    outs = []
+    try:
+        for seg in ("1", "0", None):
+            if seg is None:
+                bank = O.OracleBank(kind, n, vpi)
+            else:
+                os.environ["OSCEN_B200_JIT_SEGMENTS"] = seg
+                bank = abi.Engine.from_graph(abi.Graph(text), n, vpi, plan=abi.PLAN_FUSED)
+            freq_id = 2 if kind == O.K_SYNTH_ADSR else 0
+            bank.set_value(freq_id, (110.0 * 2.0 ** ((np.arange(n) % 31) / 12.0)).astype(np.float32))
+            o = []
+            for blk, frames in enumerate((200, 77, 256, 130)):
+                if kind != O.K_SAT4 and blk in (0, 2):
+                    bank.push_events([(v, (5 * v) % frames, GATE, 0.8 if blk == 0 else 0.0) for v in range(n)])
+                if blk == 1:
+                    bank.push_events([(v, 10 + v % 40, freq_id, 200.0 + 3.0 * v) for v in range(0, n, 3)])
+                bank.process_block(frames); o.append(bank.read_voice_out())
+            outs.append(np.concatenate(o))
+    finally:
+        if old is None:
+            os.environ.pop("OSCEN_B200_JIT_SEGMENTS", None)
+        else:
+            os.environ["OSCEN_B200_JIT_SEGMENTS"] = old
+    assert np.abs(outs[2]).max() > 0.01
+    assert np.array_equal(outs[0], outs[2]), float(np.abs(outs[0] - outs[2]).max())
+    assert np.array_equal(outs[1], outs[2]), float(np.abs(outs[1] - outs[2]).max())
+

@@ -44,6 +44,10 @@ impl Graph {
     pub fn voices_per_instance(&self) -> u32 {
         unsafe { sys::oscen_b200_graph_voices_per_instance(self.raw) }
     }
+    /// lanes of the graph's stream output: 1, or 2 for `output out: stream: Frame<2>;` (oscen-lib/src/frame.rs:57-82)
+    pub fn channels(&self) -> u32 {
+        unsafe { sys::oscen_b200_graph_channels(self.raw) }
+    }
     /// index of an `external NAME: AudioAsset;` slot
     pub fn asset_id(&self, name: &str) -> Option<u32> {
         let c = CString::new(name).ok()?;

@@ -275,6 +275,18 @@ int  oscen_b200_graph_input_info(const oscen_b200_graph *g, uint32_t input_id, o
                             libnvrtc.so.12 and the engine's device headers next to the library).
    Both are bit-identical.  The graph object may be freed afterwards. */
 int  oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out);
+/* PLAN_FUSED engines of a compiled graph: generate, compile (NVRTC) and load a SECOND variant of the graph's kernel for the
+   value inputs that hold one value for every voice at the time of the call (defaults, broadcast oscen_b200_set_value,
+   declared ramps; the MIDI front's `frequency` input is never taken) — the reference's `pub <value>: f32` fields of ONE graph
+   instance are exactly that (codegen/mod.rs:1292-1392); per-voice values exist here only because a bank holds many
+   instances.  The variant reads those inputs from the kernel-argument constant bank instead of one register each (+5 % on
+   the generated FMVoice, profiles/r02_ab_generated_knobs.log).  It renders every block in which each of these inputs is
+   still uniform and not ramping; any other block (a per-voice set_value, a value event or a running ramp on one of them)
+   runs the general kernel — results are bit-identical either way, oscen_b200_last_kernel_name() says which ran.
+   Call it after the parameters are set up (it takes an NVRTC compile, so not from the audio callback); calling it again
+   re-specialises for the inputs uniform then.  *uniform_mask (may be NULL) receives the input ids taken, bit i = input i.
+   OSCEN_B200_E_STATE for built-in kinds (FMVoice picks its variant itself, fm_select.hpp) and PLAN_NODES engines. */
+int  oscen_b200_specialize(oscen_b200_engine *e, uint32_t *uniform_mask);
 /* (inspection, host only) the tables of a BUILT-IN graph kind: value-input defaults, the state words of one voice after
    new() + init(sample_rate), output channels, dynamic shared memory of its fused kernel.  For tools and for the CPU suite's
    host-executed kernel check (tests/host_kernel.py); OSCEN_B200_GRAPH_CUSTOM graphs answer oscen_b200_graph_kernel_info. */
@@ -310,6 +322,9 @@ typedef struct {
 } oscen_b200_kernel_info;
 int  oscen_b200_graph_kernel_info(const oscen_b200_graph *g, float sample_rate, oscen_b200_kernel_info *info,
                                   char *source, size_t source_cap, uint32_t *state_words, size_t state_cap);
+/* the generated source of the variant oscen_b200_specialize() compiles for `uniform_mask` (0 = the general kernel) at this
+   sample rate; returns its length (dst may be NULL to ask for it).  Host only. */
+int  oscen_b200_graph_kernel_source(const oscen_b200_graph *g, float sample_rate, uint32_t uniform_mask, char *dst, size_t cap);
 
 /* counters: kernels launched by this engine since create; bytes copied H2D / D2H */
 typedef struct {

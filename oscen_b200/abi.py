@@ -38,9 +38,9 @@ SYMBOLS = [
     "oscen_b200_state_bytes_per_voice", "oscen_b200_state_download", "oscen_b200_get_stats",
     "oscen_b200_last_block_ms", "oscen_b200_enable_timing", "oscen_b200_last_kernel_ms", "oscen_b200_timing_drain", "oscen_b200_last_kernel_name", "oscen_b200_l2_flush", "oscen_b200_comm_unique_id", "oscen_b200_comm_init", "oscen_b200_comm_p2p_export", "oscen_b200_comm_p2p_import", "oscen_b200_comm_p2p_close", "oscen_b200_plan_describe",
     "oscen_b200_graph_compile", "oscen_b200_graph_compile_named", "oscen_b200_graph_free", "oscen_b200_graph_describe", "oscen_b200_graph_n_inputs",
-    "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph",
+    "oscen_b200_graph_input_id", "oscen_b200_graph_input_info", "oscen_b200_create_from_graph", "oscen_b200_specialize",
     "oscen_b200_graph_codegen", "oscen_b200_graph_jit_check", "oscen_b200_graph_voices_per_instance", "oscen_b200_graph_channels", "oscen_b200_graph_has_midi",
-    "oscen_b200_kind_info", "oscen_b200_graph_kernel_info", "oscen_b200_graph_n_assets", "oscen_b200_graph_asset_id", "oscen_b200_load_asset",
+    "oscen_b200_kind_info", "oscen_b200_graph_kernel_info", "oscen_b200_graph_kernel_source", "oscen_b200_graph_n_assets", "oscen_b200_graph_asset_id", "oscen_b200_load_asset",
 ]
 
 
@@ -153,6 +153,7 @@ def load():
     L.oscen_b200_graph_input_id.argtypes = [vp, C.c_char_p]
     L.oscen_b200_graph_input_info.argtypes = [vp, u32, C.POINTER(InputInfo)]
     L.oscen_b200_create_from_graph.argtypes = [vp, C.POINTER(Config), C.POINTER(vp)]
+    L.oscen_b200_specialize.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.oscen_b200_graph_voices_per_instance.argtypes = [vp]
     L.oscen_b200_graph_voices_per_instance.restype = u32
     L.oscen_b200_graph_channels.argtypes = [vp]
@@ -165,6 +166,7 @@ def load():
     L.oscen_b200_graph_n_assets.restype = C.c_uint32
     L.oscen_b200_graph_asset_id.argtypes = [vp, C.c_char_p]
     L.oscen_b200_load_asset.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+    L.oscen_b200_graph_kernel_source.argtypes = [vp, C.c_float, C.c_uint32, C.c_char_p, C.c_size_t]
     L.oscen_b200_graph_kernel_info.argtypes = [vp, C.c_float, C.POINTER(KernelInfo), C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
     _lib = L
     return L
@@ -236,6 +238,15 @@ class Graph:
             raise EngineError(f"graph_kernel_info rc={rc}")
         return src.value.decode(), np.frombuffer(words, dtype=np.uint32).copy(), info
 
+    def kernel_source(self, sample_rate=48000.0, uniform_mask=0):
+        """the generated source of the variant Engine.specialize() compiles for `uniform_mask` (0 = the general kernel)"""
+        n = self.L.oscen_b200_graph_kernel_source(self.h, sample_rate, uniform_mask, None, 0)
+        if n < 0:
+            raise EngineError(f"graph_kernel_source rc={n}")
+        buf = C.create_string_buffer(n + 1)
+        self.L.oscen_b200_graph_kernel_source(self.h, sample_rate, uniform_mask, buf, len(buf))
+        return buf.value.decode()
+
     def jit_check(self):
         """compile the generated kernel with NVRTC for sm_100a (no GPU needed); returns the cubin size"""
         log = C.create_string_buffer(1 << 16)
@@ -303,6 +314,13 @@ class Engine:
         if voices_per_instance is None:
             voices_per_instance = graph.voices_per_instance
         return cls(GRAPH_CUSTOM, n_voices, voices_per_instance, sample_rate, device, plan, keep, graph=graph)
+
+    def specialize(self):
+        """compile the generated kernel's variant for the value inputs that are uniform over the voices now (PLAN_FUSED engines
+        of a DSL graph); returns the mask of input ids taken"""
+        m = C.c_uint32(0)
+        self._chk(self.L.oscen_b200_specialize(self.h, C.byref(m)), "specialize")
+        return int(m.value)
 
     def close(self):
         if getattr(self, "h", None):

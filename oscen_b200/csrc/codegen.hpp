@@ -60,8 +60,7 @@ struct Emitter {
     std::string P(int i, int k) const {
         const plan::Node &nd = g.nodes[i];
         if (nd.pid[k] == plan::kNoValue) return lit(nd.cst[k]);
-        /* EXPERIMENT (off by default, round-2 measurement): an input declared uniform-and-static reads the kernel-argument
-           constant bank at every use instead of occupying a register for the whole block */
+        /* specialised variant: a uniform input is read from the kernel-argument constant bank at every use */
         if ((uniform_mask >> nd.pid[k]) & 1u) return "a.u.p[" + std::to_string(nd.pid[k]) + "]";
         return "P[" + std::to_string(nd.pid[k]) + "]";
     }
@@ -126,14 +125,17 @@ struct Emitter {
     static int env_int(const char *name, int def) { const char *e = getenv(name); return e && *e ? atoi(e) : def; }
     bool hoist_adsr = true;
     int min_blocks = 8;
-    uint32_t uniform_mask = 0;       /* EXPERIMENT: OSCEN_B200_JIT_UNIFORM_MASK=0x... — the caller promises these inputs are uniform over
-                                        the voices and neither ramped nor written by value events while the kernel is in use */
+    uint32_t uniform_mask = 0;       /* the SPECIALISED variant (oscen_b200_specialize): these value inputs hold one value for every
+                                        voice, and are neither ramped nor written by value events in the blocks this kernel renders (the
+                                        engine checks that per block and falls back to the general variant); they are read from the
+                                        kernel-argument constant bank at every use instead of occupying a register each.
+                                        OSCEN_B200_JIT_UNIFORM_MASK=0x... ORs bits in for A/B runs (tools/ab_uniform.py) */
 
     std::string run(const char *kernel_name) {
         using T = plan::NodeType;
         hoist_adsr = env_int("OSCEN_B200_JIT_ADSR_HOIST", 1) != 0;
         min_blocks = env_int("OSCEN_B200_JIT_MIN_BLOCKS", 8);
-        { const char *e = getenv("OSCEN_B200_JIT_UNIFORM_MASK"); uniform_mask = e && *e ? (uint32_t)strtoul(e, nullptr, 0) : 0u; }
+        { const char *e = getenv("OSCEN_B200_JIT_UNIFORM_MASK"); if (e && *e) uniform_mask |= (uint32_t)strtoul(e, nullptr, 0); }
         const int n_nodes = (int)g.nodes.size();
         const uint32_t ni = (uint32_t)g.inputs.size();
         const bool has_in = !g.stream_input.empty();
@@ -528,8 +530,10 @@ inline size_t dyn_smem_bytes(const plan::Graph &g) {
     return floats * 64u * sizeof(float);      /* x kCta threads */
 }
 
-inline std::string fused_kernel_source(const plan::Graph &g, const plan::Plan &p, const char *kernel_name = "oscen_b200_generated_kernel") {
+inline std::string fused_kernel_source(const plan::Graph &g, const plan::Plan &p, const char *kernel_name = "oscen_b200_generated_kernel",
+                                       uint32_t uniform_mask = 0) {
     Emitter e(g, p);
+    e.uniform_mask = uniform_mask;
     return e.run(kernel_name);
 }
 

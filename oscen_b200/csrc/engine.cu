@@ -186,6 +186,9 @@ struct oscen_b200_engine {
     bool has_stream_in = false;          /* the graph declares a per-voice stream input */
     uint32_t lcg_field = 0;              /* first of the two state words of the device-side input LCG */
     jit::Kernel jit;                     /* DSL-compiled graph, PLAN_FUSED: the kernel codegen.hpp generated, compiled by NVRTC */
+    jit::Kernel jit_uni;                 /* oscen_b200_specialize: the variant that reads the inputs of jit_uni_mask from the constant bank */
+    uint32_t jit_uni_mask = 0;
+    std::string jit_uni_name;
     /* `external NAME: AudioAsset;` slots of a DSL graph (engine_types.h AssetTable) */
     uint32_t n_assets = 0;
     AssetTable h_assets{};
@@ -432,9 +435,14 @@ int launch_fused(oscen_b200_engine *e, bool general) {
     case OSCEN_B200_GRAPH_SYNTH: synth_kernel<false><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "synth_kernel<false>"; break;
     case OSCEN_B200_GRAPH_SYNTH_ADSR: synth_kernel<true><<<grid, kCta, 0, e->stream>>>(a); e->last_kernel = "synth_kernel<true>"; break;
     case OSCEN_B200_GRAPH_CUSTOM: {
-        const int rc = e->jit.launch(grid, kCta, (void *)e->stream, &a);
+        /* the specialised variant renders the blocks in which every input of its mask still holds one value for all voices
+           (value events and per-voice set_value clear `uniform`) and none of them ramps; `general` frames inside it
+           (gates, ramps or value events on the OTHER inputs) are handled by the kernel itself */
+        bool uni = e->jit_uni.function != nullptr && (e->h_ctl->ramp_mask & e->jit_uni_mask) == 0u;
+        for (uint32_t i = 0; uni && i < e->n_inputs; ++i) if (((e->jit_uni_mask >> i) & 1u) && !e->uniform[i]) uni = false;
+        const int rc = (uni ? e->jit_uni : e->jit).launch(grid, kCta, (void *)e->stream, &a);
         if (rc != 0) { e->err = "cuLaunchKernel (generated kernel): " + jit::driver_error(rc); return OSCEN_B200_E_CUDA; }
-        e->last_kernel = kJitKernelName;
+        e->last_kernel = uni ? e->jit_uni_name.c_str() : kJitKernelName;
     } break;
     default: launch_clip(e, a, grid); e->last_kernel = "clip_kernel"; break;
     }
@@ -683,7 +691,7 @@ void oscen_b200_destroy(oscen_b200_engine *e) {
     if (e->p2p) for (int r = 0; r < e->n_ranks; ++r) if (r != e->rank && e->peers.peer[r]) cudaIpcCloseMemHandle(e->peers.peer[r]);
     cudaFree(e->d_xchg); cudaFree(e->d_p2p_error);
     e->drop_variants();
-    e->jit.unload();
+    e->jit.unload(); e->jit_uni.unload();
     for (float *p : e->d_streams) cudaFree(p);
     cudaFree(e->d_tmaps);
     cudaFree(e->d_pv); cudaFree(e->d_ptab); cudaFree(e->d_state); cudaFree(e->d_inst_state);
@@ -931,6 +939,15 @@ int oscen_b200_graph_jit_check(const oscen_b200_graph *g, char *log, size_t log_
     if (log && log_cap) { strncpy(log, msg.c_str(), log_cap - 1); log[log_cap - 1] = 0; }
     return ok ? (int)cubin.size() : OSCEN_B200_E_JIT;
 }
+/* the source oscen_b200_specialize(mask) would compile for an engine at this sample rate (inspection / host-executed tests) */
+int oscen_b200_graph_kernel_source(const oscen_b200_graph *g, float sample_rate, uint32_t uniform_mask, char *dst, size_t cap) {
+    if (!g || !(sample_rate > 0.0f)) return OSCEN_B200_E_ARG;
+    plan::Graph pg = g->g;
+    plan::assign_state_layout(pg, sample_rate);
+    const std::string s = codegen::fused_kernel_source(pg, g->p, kJitKernelName, uniform_mask);
+    if (dst) { if (s.size() + 1 > cap) return OSCEN_B200_E_ARG; memcpy(dst, s.c_str(), s.size() + 1); }
+    return (int)s.size();
+}
 int oscen_b200_graph_kernel_info(const oscen_b200_graph *g, float sample_rate, oscen_b200_kernel_info *info,
                                  char *source, size_t source_cap, uint32_t *state_words, size_t state_cap) {
     if (!g || !(sample_rate > 0.0f)) return OSCEN_B200_E_ARG;
@@ -948,6 +965,37 @@ int oscen_b200_graph_kernel_info(const oscen_b200_graph *g, float sample_rate, o
     if (source) { if (src.size() + 1 > source_cap) rc = OSCEN_B200_E_ARG; else memcpy(source, src.c_str(), src.size() + 1); }
     if (state_words) { if (init.size() > state_cap) rc = OSCEN_B200_E_ARG; else memcpy(state_words, init.data(), init.size() * sizeof(uint32_t)); }
     return rc;
+}
+/* compile and load the variant of the generated kernel for the value inputs that hold one value for every voice now */
+int oscen_b200_specialize(oscen_b200_engine *e, uint32_t *uniform_mask) {
+    if (uniform_mask) *uniform_mask = 0;
+    if (!e) return OSCEN_B200_E_ARG;
+    if (e->cfg.graph_kind != OSCEN_B200_GRAPH_CUSTOM || e->cfg.plan != OSCEN_B200_PLAN_FUSED) {
+        e->err = "specialize: only a PLAN_FUSED engine of a compiled graph has a generated kernel (the built-in FMVoice picks its variant itself)";
+        return OSCEN_B200_E_STATE;
+    }
+    CK(e, cudaSetDevice(e->cfg.device));
+    uint32_t mask = 0;
+    for (uint32_t i = 0; i < e->n_inputs && i < 32u; ++i)
+        if (e->uniform[i] && !(e->midi_ok && i == e->midi_freq_input)) mask |= 1u << i;
+    for (const Event &x : e->pending) if (x.input_id != kEventGate && x.input_id < 32u) mask &= ~(1u << x.input_id);
+    if (mask == e->jit_uni_mask && (mask == 0u || e->jit_uni.function)) { if (uniform_mask) *uniform_mask = mask; return 0; }
+    CK(e, cudaStreamSynchronize(e->stream));                   /* the old variant may still be running */
+    e->jit_uni.unload(); e->jit_uni = jit::Kernel(); e->jit_uni_mask = 0;
+    if (mask != 0u) {
+        jit::Kernel jk;
+        jk.source = codegen::fused_kernel_source(e->graph, e->plan, kJitKernelName, mask);
+        jk.dyn_smem = e->jit.dyn_smem;
+        std::string jerr;
+        if (!jit::compile_cubin(jk.source, jk.cubin, jk.log, jerr)) { e->err = "specialize (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }
+        if (!jk.load(kJitKernelName, jerr)) { e->err = "specialize (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }
+        e->jit_uni = std::move(jk);
+        e->jit_uni_mask = mask;
+        char nm[96]; snprintf(nm, sizeof nm, "%s<uniform=0x%x>", kJitKernelName, mask);
+        e->jit_uni_name = nm;
+    }
+    if (uniform_mask) *uniform_mask = mask;
+    return 0;
 }
 int oscen_b200_create_from_graph(const oscen_b200_graph *g, const oscen_b200_config *cfg, oscen_b200_engine **out) {
     if (!g) { g_create_error = "null graph"; return OSCEN_B200_E_ARG; }

@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
 
 /* hb_down_step_r / HbDownRegs (register-resident halfband histories) live in nodes.cuh, next to the shared-memory form */
 
+#ifndef OSCEN_B200_SAT_UNROLL
+#define OSCEN_B200_SAT_UNROLL 2      /* A/B on B200 (profiles/r02_ab_sat_unroll.log): 1: 0.817, 2: 0.813, 3: 0.848, 4: 0.835, 8: 1.10 ms per 262 144-voice block */
+#endif
+#define OSC_PRAGMA_STR(x) _Pragma(#x)
+#define OSC_PRAGMA_UNROLL(n) OSC_PRAGMA_STR(unroll n)
+
 template <int FACTOR>
 __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ KernelArgs a) {
     __shared__ float tile[kTileF * kTileW];
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ Kerne
             const uint32_t np = ramp_mask != 0u ? 0u : ec.next_frame - f;
             const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
             if (L > 0u) {
-#pragma unroll 4
+OSC_PRAGMA_UNROLL(OSCEN_B200_SAT_UNROLL)
                 for (uint32_t i = 0; i < L; ++i) OSC_SAT_FRAME(ff + i)
                 ff += L;
                 continue;
@@ -212,13 +218,41 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
     AdsrState env; adsr_load(env, a.state, SY_ENV, n, vs);
     AdsrDerived d;
     adsr_derive_r(d, prm.P[4], prm.P[5], prm.P[7], sr);
+    AdsrHot hot; adsr_refresh<false>(env, hot, prm.P[6], d);
     EventCursor ec; ec.init(a.events, active ? a.ctl->n_events : 0u, vs);
     adsr_begin_block(env, d, ec.due(0u));
 
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        for (uint32_t ff = 0; ff < fe; ++ff) {
+        /* segmented like the generated kernels (codegen.hpp): per warp, L frames until the first lane's next event or
+           envelope stage completion run without ramp / event / stage code, then one general frame */
+        uint32_t ff = 0;
+        while (ff < fe) {
             const uint32_t f = f0 + ff;
+            uint32_t np = (ramp_mask != 0u || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);
+            if (WITH_ADSR) np = umin(np, adsr_plain_frames(env));
+            const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
+            if (L > 0u) {
+                const bool ad = (env.stage == ST_ATTACK) | (env.stage == ST_DECAY), rl = env.stage == ST_RELEASE;
+                const float tg = env.stage == ST_ATTACK ? 1.0f : hot.sus, kk = env.stage == ST_ATTACK ? d.a_k : d.d_k;
+                const bool any_rl = WITH_ADSR && __any_sync(0xffffffffu, rl);
+                for (uint32_t i = 0; i < L; ++i) {
+                    float y = 0.0f;
+                    if (active) {
+                        const float m = polyblep_process<WAVE_SINE>(ph_mod, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr);
+                        float g = 1.0f;
+                        if (WITH_ADSR) g = any_rl ? adsr_plain_rel(env, ad, rl, tg, kk) : adsr_ad(env, ad, tg, kk);
+                        const float c = polyblep_process<WAVE_SAW>(ph_car, 0.0f, prm.P[2], m, 0.5f, 0.5f, sr);
+                        const float lp = tpt_process(tp, c, prm.P[3], 0.707f, 0.0f, sr);
+                        y = WITH_ADSR ? lp * g : lp;             /* vca: Gain */
+                        if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;
+                    }
+                    tile[(ff + i) * kTileW + col] = y;
+                }
+                if (WITH_ADSR && !any_rl && ad) env.rem -= L;    /* the Release form counts down per frame itself */
+                ff += L;
+                continue;
+            }
             float y = 0.0f;
             if (active) {
                 prm.ramps(a, ramp_mask, f);
@@ -228,25 +262,25 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
                     j = ec.end_of_frame(f);
                     for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id != kEventGate) prm.value_event(a, ec.ev[q], v);
                 }
-                if (WITH_ADSR && adsr_derived_stale(d, prm.P[4], prm.P[5], prm.P[7])) adsr_derive_r(d, prm.P[4], prm.P[5], prm.P[7], sr);
+                const bool changed = (ramp_mask != 0u) || due;
+                if (WITH_ADSR && changed && adsr_derived_stale(d, prm.P[4], prm.P[5], prm.P[7])) adsr_derive_r(d, prm.P[4], prm.P[5], prm.P[7], sr);
                 if (due) {
                     if (WITH_ADSR)
                         for (uint32_t q = ec.i; q < j; ++q) if (ec.ev[q].input_id == kEventGate)
                             adsr_on_gate(env, ec.ev[q].scalar, prm.P[4], prm.P[7], d);
                     ec.advance(j);
                 }
+                if (WITH_ADSR && changed) adsr_refresh(env, hot, prm.P[6], d);
                 const float m = polyblep_process<WAVE_SINE>(ph_mod, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr);
+                float g = 1.0f;
+                if (WITH_ADSR) g = adsr_process_t<false>(env, hot, prm.P[6], d);
                 const float c = polyblep_process<WAVE_SAW>(ph_car, 0.0f, prm.P[2], m, 0.5f, 0.5f, sr);
                 const float lp = tpt_process(tp, c, prm.P[3], 0.707f, 0.0f, sr);
-                if (WITH_ADSR) {
-                    const float g = adsr_process(env, prm.P[6], d);
-                    y = lp * g;                                  /* vca: Gain */
-                } else {
-                    y = lp;
-                }
+                y = WITH_ADSR ? lp * g : lp;                     /* vca: Gain */
                 if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;
             }
             tile[ff * kTileW + col] = y;
+            ff += 1u;
         }
         tile_flush_mono(a, tile, isum, f0, fe);
     }

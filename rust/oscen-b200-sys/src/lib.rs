@@ -130,6 +130,7 @@ extern "C" {
     pub fn oscen_b200_graph_input_id(g: *const oscen_b200_graph, name: *const c_char) -> c_int;
     pub fn oscen_b200_graph_input_info(g: *const oscen_b200_graph, input_id: u32, out: *mut oscen_b200_input_info) -> c_int;
     pub fn oscen_b200_create_from_graph(g: *const oscen_b200_graph, cfg: *const oscen_b200_config, out: *mut *mut oscen_b200_engine) -> c_int;
+    pub fn oscen_b200_specialize(e: *mut oscen_b200_engine, uniform_mask: *mut u32) -> c_int;
     pub fn oscen_b200_graph_codegen(g: *const oscen_b200_graph, dst: *mut c_char, cap: usize) -> c_int;
     pub fn oscen_b200_graph_jit_check(g: *const oscen_b200_graph, log: *mut c_char, log_cap: usize) -> c_int;
     pub fn oscen_b200_kind_info(graph_kind: u32, sample_rate: f32, info: *mut oscen_b200_kind_tables, defaults: *mut f32, state_words: *mut u32, state_cap: usize) -> c_int;
@@ -137,6 +138,7 @@ extern "C" {
     pub fn oscen_b200_graph_asset_id(g: *const oscen_b200_graph, name: *const c_char) -> c_int;
     pub fn oscen_b200_load_asset(e: *mut oscen_b200_engine, asset_id: u32, interleaved: *const f32, frames: u32, channels: u32) -> c_int;
     pub fn oscen_b200_graph_kernel_info(g: *const oscen_b200_graph, sample_rate: f32, info: *mut oscen_b200_kernel_info, source: *mut c_char, source_cap: usize, state_words: *mut u32, state_cap: usize) -> c_int;
+    pub fn oscen_b200_graph_kernel_source(g: *const oscen_b200_graph, sample_rate: f32, uniform_mask: u32, dst: *mut c_char, cap: usize) -> c_int;
     pub fn oscen_b200_get_stats(e: *const oscen_b200_engine, out: *mut oscen_b200_stats) -> c_int;
     pub fn oscen_b200_last_block_ms(e: *mut oscen_b200_engine, ms: *mut f32) -> c_int;
     pub fn oscen_b200_enable_timing(e: *mut oscen_b200_engine, on: c_int) -> c_int;

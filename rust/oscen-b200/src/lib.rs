@@ -140,6 +140,13 @@ impl Bank {
         let frames = (interleaved.len() as u32) / ch;
         self.check(unsafe { sys::oscen_b200_load_asset(self.raw, id, interleaved.as_ptr(), frames, ch) }, "load_asset")
     }
+    /// (no reference counterpart) compile the kernel variant that reads the value inputs which hold one value for the whole
+    /// bank from the constant bank; returns the ids taken as a bit mask.  Not for the audio thread: it runs NVRTC.
+    pub fn specialize(&mut self) -> Result<u32> {
+        let mut mask = 0u32;
+        self.check(unsafe { sys::oscen_b200_specialize(self.raw, &mut mask) }, "specialize")?;
+        Ok(mask)
+    }
     /// `process_block(frames)`, frames <= MAX_BLOCK_SIZE
     pub fn process_block(&mut self, frames: u32) -> Result<()> {
         self.check(unsafe { sys::oscen_b200_process_block(self.raw, frames) }, "process_block")?;

@@ -19,7 +19,7 @@ CASES = [("voice_fm3.graph", abi.GRAPH_FM_VOICE, 8, 0), ("synth_adsr.graph", abi
          ("sat_4x.graph", abi.GRAPH_SAT_4X, 1, 0)]
 
 
-def run(e, n, freq_id, steps, has_gate, has_in):
+def run(e, n, freq_id, steps, has_gate, has_in, specialize=False):
     rng = np.random.default_rng(1)
     if has_in:
         e.stream_in_lcg(0, 1000, 0)
@@ -31,6 +31,8 @@ def run(e, n, freq_id, steps, has_gate, has_in):
         ev["voice"] = np.arange(n); ev["frame_offset"] = rng.integers(0, FRAMES, size=n)
         ev["input_id"] = abi.EVENT_GATE; ev["scalar"] = 0.8
         e.push_events(ev)
+    if specialize:
+        e.specialize()               # after the per-voice frequencies are in: they stay in registers
     e.enable_timing(True)
     for _ in range(3):
         e.l2_flush(); e.process_block(FRAMES)
@@ -57,15 +59,17 @@ def main():
         t0 = time.perf_counter()
         ways.append(("generated fused kernel (NVRTC)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_FUSED)))
         jit_s = time.perf_counter() - t0
+        ways.append(("generated fused kernel, specialised for the uniform inputs (oscen_b200_specialize)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_FUSED)))
         if "Edge [" not in g.describe():       # multirate graphs run as generated kernels only
             ways.append(("node plan (CUDA graph)", abi.Engine.from_graph(g, n, vpi, keep=keep, plan=abi.PLAN_NODES)))
         ways.append(("hand-written fused kernel", abi.Engine(kind, n, vpi, 48000.0, 0, abi.PLAN_FUSED, keep)))
         if os.environ.get("OSCEN_BENCH_WAYS") == "gen":
-            ways = ways[:1]
+            ways = ways[:2]
         for name, e in ways:
-            k_ms = run(e, n, freq_id, steps, has_gate, has_in)
+            k_ms = run(e, n, freq_id, steps, has_gate, has_in, specialize="specialised" in name)
             print(json.dumps({"graph": file, "way": name, "voices": n, "frames": FRAMES, "kernel_ms": k_ms,
                               "voice_samples_per_s": n * FRAMES / (k_ms * 1e-3),
+                              "kernel": e.last_kernel_name(),
                               "create_s_incl_nvrtc": jit_s if "NVRTC" in name else None}), flush=True)
             e.close()
 

@@ -117,6 +117,19 @@ struct Emitter {
     static uint32_t edge_smem_floats(const plan::Node &) {
         return 0u;       /* [sinc] edges keep their FIR histories in registers since round 2 (nodes.cuh HbUpRegs / HbDownRegs) */
     }
+    /* array-stream nodes (AmplitudeSource 130 words, OscillatorBank 129): their state is walked in place every frame, so for
+       the block it lives in a [word][thread] slice of dynamic shared memory (conflict-free: consecutive threads, consecutive
+       banks) and goes back to its SoA rows at the end — as long as the CTA's slices fit; beyond that the rows are walked in
+       HBM (round-2 first form, ~5x slower) */
+    static uint32_t array_state_words(const plan::Node &nd) {
+        return nd.type == plan::NodeType::AmpSource ? 130u : (nd.type == plan::NodeType::OscBank ? 129u : 0u);
+    }
+    static uint32_t array_smem_floats(const plan::Graph &g) {
+        uint32_t w = 0;
+        for (const plan::Node &nd : g.nodes) w += array_state_words(nd);
+        if (getenv("OSCEN_B200_JIT_ARRAY_SMEM") && getenv("OSCEN_B200_JIT_ARRAY_SMEM")[0] == '0') return 0u;
+        return (size_t)w * 64u * sizeof(float) <= 160u * 1024u ? w : 0u;
+    }
     static bool is_polyblep(plan::NodeType t) {
         return t == plan::NodeType::PolyBlepSine || t == plan::NodeType::PolyBlepSaw || t == plan::NodeType::PolyBlepSquare || t == plan::NodeType::PolyBlepTriangle;
     }
@@ -146,6 +159,13 @@ struct Emitter {
         line(0, "using namespace oscen;");
         /* min_blocks CTAs of 64 threads per SM: 8 caps the kernel at 128 registers per thread, so that the 1024 CTAs of a
            65 536-voice bank (6.9 per SM) are resident in one wave */
+        const uint32_t arr_floats = array_smem_floats(g);
+        const bool arr_smem = arr_floats > 0u;
+        const std::string arr_stride = arr_smem ? "(size_t)kCta" : "(size_t)n";
+        if (arr_smem) {            /* CTAs per SM are set by the shared-memory slices: let the register allocation follow */
+            const int fit = (int)((220u * 1024u) / ((size_t)arr_floats * 64u * sizeof(float) + 26u * 1024u));
+            min_blocks = fit < 1 ? 1 : (fit < min_blocks ? fit : min_blocks);
+        }
         line(0, fmt("extern \"C\" __global__ void __launch_bounds__(kCta, %d) %s(const __grid_constant__ KernelArgs a) {", min_blocks, kernel_name));
         line(1, "__shared__ float tile[kTileF * kTileW];");
         /* (a name of its own for the stereo scratch: the host-executed test harness loads many generated kernels into one
@@ -159,6 +179,7 @@ struct Emitter {
         line(1, "const float sr = a.u.sr;");
         line(1, "const uint32_t col = tile_col(threadIdx.x, a.vpi);");
         line(1, "(void)sr; (void)ramp_mask;");
+        if (arr_smem && !multirate) line(1, "extern __shared__ float dyn[];                 /* this block's state of the array-stream nodes, [word][thread] */");
         if (multirate) {
             line(1, "extern __shared__ float dyn[];                 /* FIR rings of the [sinc] cross-rate edges */");
             line(1, "const float sri = sr * " + std::to_string(NI) + ".0f;    /* inner-rate nodes: set_sample_rate(sr * N) */");
@@ -218,8 +239,15 @@ struct Emitter {
                 }
             } break;
             case T::AmpSource: case T::OscBank:
-                /* 130 / 129 state words: walked in place in their SoA rows (nodes.cuh), not held in registers */
-                line(1, "float *" + N(i) + " = a.state + (size_t)" + base + " * n + vs;");
+                /* 130 / 129 state words, walked in place (nodes.cuh), not held in registers */
+                if (arr_smem) {
+                    const std::string w = std::to_string(array_state_words(nd)) + "u";
+                    line(1, "float *" + N(i) + " = dyn + " + std::to_string(smem_off) + "u * kCta + threadIdx.x;    /* [word][thread] slice of shared memory */");
+                    line(1, "_Pragma(\"unroll 8\") for (uint32_t w_ = 0; w_ < " + w + "; ++w_) " + N(i) + "[(size_t)w_ * kCta] = a.state[(size_t)(" + base + " + w_) * n + vs];");
+                    smem_off += array_state_words(nd);
+                } else {
+                    line(1, "float *" + N(i) + " = a.state + (size_t)" + base + " * n + vs;    /* walked in its SoA rows in HBM */");
+                }
                 break;
             case T::Up: case T::Down:
                 line(1, edge_type(i) + " " + N(i) + "; " + N(i) + ".load(a.state, " + base + ", n, vs, dyn + " + std::to_string(smem_off) + "u * kCta);");
@@ -281,12 +309,12 @@ struct Emitter {
                           ", (size_t)n, " + std::to_string(nd.ring_cap) + "u, " + lit(nd.max_delay) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ");" + cm);
                 break;
             case T::AmpSource:
-                line(ind, "float " + S(i) + "[32]; ampsrc_process(" + N(i) + ", (size_t)n, " + S(i) + ");" + cm + "    /* amplitudes: [f32; 32] */");
+                line(ind, "float " + S(i) + "[32]; ampsrc_process(" + N(i) + ", " + arr_stride + ", " + S(i) + ");" + cm + "    /* amplitudes: [f32; 32] */");
                 break;
             case T::OscBank:
-                if (nd.in[0].node >= 0) line(ind, o + "oscbank_process(" + N(i) + ", (size_t)n, " + P(i, 0) + ", " + SR(i) + ", " + S(nd.in[0].node, nd.in[0].port) + ");" + cm);
+                if (nd.in[0].node >= 0) line(ind, o + "oscbank_process(" + N(i) + ", " + arr_stride + ", " + P(i, 0) + ", " + SR(i) + ", " + S(nd.in[0].node, nd.in[0].port) + ");" + cm);
                 else { line(ind, "const float z" + std::to_string(i) + "[32] = {};    /* `amplitudes` is not connected: [0.0; 32] */");
-                       line(ind, o + "oscbank_process(" + N(i) + ", (size_t)n, " + P(i, 0) + ", " + SR(i) + ", z" + std::to_string(i) + ");" + cm); }
+                       line(ind, o + "oscbank_process(" + N(i) + ", " + arr_stride + ", " + P(i, 0) + ", " + SR(i) + ", z" + std::to_string(i) + ");" + cm); }
                 break;
             case T::SamplePlayer: line(ind, o + "sample_player_process(" + N(i) + ", buf" + std::to_string(i) + ", len" + std::to_string(i) + ");" + cm); break;
             case T::Gain: line(ind, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
@@ -450,9 +478,9 @@ struct Emitter {
                 line(6, "adsr_on_gate(" + N(i) + ", gv, " + P(i, 0) + ", " + P(i, 3) + ", " + D(i) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
             for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].gate) {
                 if (g.nodes[i].type == T::AmpSource)
-                    line(6, "ampsrc_on_gate(" + N(i) + ", (size_t)n, gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+                    line(6, "ampsrc_on_gate(" + N(i) + ", " + arr_stride + ", gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
                 if (g.nodes[i].type == T::OscBank)
-                    line(6, "oscbank_on_gate(" + N(i) + ", (size_t)n, gv);    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+                    line(6, "oscbank_on_gate(" + N(i) + ", " + arr_stride + ", gv);    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
             }
             line(5, "}");
         }
@@ -491,6 +519,9 @@ struct Emitter {
             const std::string base = std::to_string(nd.state_base) + "u";
             switch (nd.type) {
             case T::Adsr: line(2, "adsr_store(" + N(i) + ", a.state, " + base + ", n, v);"); break;
+            case T::AmpSource: case T::OscBank:
+                if (arr_smem) line(2, "_Pragma(\"unroll 8\") for (uint32_t w_ = 0; w_ < " + std::to_string(array_state_words(nd)) + "u; ++w_) a.state[(size_t)(" + base + " + w_) * n + v] = " + N(i) + "[(size_t)w_ * kCta];");
+                break;
             case T::FmOperator:
                 line(2, "a.state[(size_t)(" + base + " + 0u) * n + v] = " + N(i) + ".phase; a.state[(size_t)(" + base + " + 1u) * n + v] = " + N(i) + ".prev;");
                 break;
@@ -523,10 +554,12 @@ struct Emitter {
     }
 };
 
-/* dynamic shared memory of the generated kernel: the FIR rings of its [sinc] cross-rate edges */
+/* dynamic shared memory of the generated kernel: the block-resident state of its array-stream nodes (the FIR histories of
+   [sinc] cross-rate edges moved to registers in round 2) */
 inline size_t dyn_smem_bytes(const plan::Graph &g) {
     size_t floats = 0;
     for (const plan::Node &nd : g.nodes) floats += Emitter::edge_smem_floats(nd);
+    floats += Emitter::array_smem_floats(g);  /* the block-resident state of AmplitudeSource / OscillatorBank nodes */
     return floats * 64u * sizeof(float);      /* x kCta threads */
 }
 

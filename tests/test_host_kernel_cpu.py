@@ -297,14 +297,21 @@ def test_host_executed_electric_piano_kernel_matches_oracle_voices_and_stereo_in
     assert np.array_equal(vh, vr) and np.array_equal(ih, ir)
 
 
-def test_host_executed_electric_piano_graph_from_its_own_dsl_text_matches_oracle():
+@pytest.mark.parametrize("array_smem", ["1", "0"], ids=["state_in_shared_memory", "state_walked_in_hbm_rows"])
+def test_host_executed_electric_piano_graph_from_its_own_dsl_text_matches_oracle(array_smem, monkeypatch):
     """ElectricPianoGraph compiled from the reference's two `graph!` blocks (tests/graphs/electric_piano.graph: an array-typed
     [f32; 32] stream between AmplitudeSource and OscillatorBank, 16 voices -> sum -> Tremolo -> Frame<2>): the GENERATED
     kernel, executed on the host, against the oracle's electric-piano bank — per-voice output and stereo instance output
-    bit-identical, same script as the hand-written kernel's test above"""
+    bit-identical, same script as the hand-written kernel's test above.  Both homes of the array nodes' 259 state words: the
+    block-resident [word][thread] slices of dynamic shared memory (default) and the SoA rows in HBM
+    (OSCEN_B200_JIT_ARRAY_SMEM=0, also the fallback of graphs whose slices do not fit)"""
+    monkeypatch.setenv("OSCEN_B200_JIT_ARRAY_SMEM", array_smem)
     n, vpi = 80, 16
     ref, host = O.OracleBank(O.K_EPIANO, n, vpi), HostEngine(text("electric_piano.graph"), n)
     assert host.vpi == vpi and host.channels == 2
+    src, _, info = host.graph.kernel_info(48000.0)
+    assert ("dyn + 130u * kCta + threadIdx.x" in src) == (array_smem == "1")
+    assert info.dyn_smem_bytes == (259 * 64 * 4 if array_smem == "1" else 0)
 
     def script(b):
         out_v, out_i = [], []

@@ -145,3 +145,39 @@ def test_generated_kernel_with_and_without_segments_matches_oracle(graph_file, k
     assert np.array_equal(outs[0], outs[2]), float(np.abs(outs[0] - outs[2]).max())
     assert np.array_equal(outs[1], outs[2]), float(np.abs(outs[1] - outs[2]).max())
 
+
+
+@pytest.mark.parametrize("array_smem", ["1", "0"])
+def test_generated_electric_piano_with_state_in_shared_memory_and_in_hbm_rows_matches_oracle(array_smem):
+    """OSCEN_B200_JIT_ARRAY_SMEM=0|1: where the generated kernel keeps the 259 state words of AmplitudeSource + OscillatorBank
+    for the block (HBM rows / a [word][thread] slice of dynamic shared memory): raw MIDI in, stereo frames out, against the
+    oracle's electric-piano bank; 70 instances = 1120 voices over 18 CTAs, the last one partly filled"""
+    from oscen_b200 import abi
+    from test_parity_gpu import _random_midi
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "graphs", "electric_piano.graph")).read()
+    n_inst, vpi = 70, 16
+    n = n_inst * vpi
+    old = os.environ.get("OSCEN_B200_JIT_ARRAY_SMEM")
+    try:
+        os.environ["OSCEN_B200_JIT_ARRAY_SMEM"] = array_smem
+        g = abi.Graph(text)
+        gen = abi.Engine.from_graph(g, n, plan=abi.PLAN_FUSED)
+    finally:
+        if old is None:
+            os.environ.pop("OSCEN_B200_JIT_ARRAY_SMEM", None)
+        else:
+            os.environ["OSCEN_B200_JIT_ARRAY_SMEM"] = old
+    ref = O.OracleBank(O.K_EPIANO, n, vpi)
+    rng = np.random.default_rng(23)
+    for blk, frames in enumerate((256, 130, 256)):
+        msgs = _random_midi(rng, n_inst, frames, 200 if blk == 0 else 30, 2 * vpi)
+        for b in (ref, gen):
+            for inst, frame, data in msgs:
+                b.push_midi(inst, frame, data)
+            if blk == 1:
+                b.set_value(g.input_id("decay_rate"), 55.0)
+            b.process_block(frames)
+        assert np.array_equal(gen.read_voice_out(), ref.read_voice_out()), blk
+        assert np.array_equal(gen.read_instance_out(), ref.read_instance_out()), blk
+    assert np.abs(ref.read_instance_out()).max() > 1e-3
+    gen.close()

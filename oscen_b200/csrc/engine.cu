@@ -985,7 +985,7 @@ int oscen_b200_specialize(oscen_b200_engine *e, uint32_t *uniform_mask) {
     if (mask != 0u) {
         jit::Kernel jk;
         jk.source = codegen::fused_kernel_source(e->graph, e->plan, kJitKernelName, mask);
-        jk.dyn_smem = e->jit.dyn_smem;
+        jk.dyn_smem = (unsigned)codegen::dyn_smem_bytes(e->graph);      /* decided with the source, like create */
         std::string jerr;
         if (!jit::compile_cubin(jk.source, jk.cubin, jk.log, jerr)) { e->err = "specialize (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }
         if (!jk.load(kJitKernelName, jerr)) { e->err = "specialize (generated kernel): " + jerr; return OSCEN_B200_E_JIT; }

@@ -305,6 +305,12 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
 #ifndef OSCEN_B200_EP_LANES
 #define OSCEN_B200_EP_LANES 2
 #endif
+#ifndef OSCEN_B200_EP_SEGMENTS
+#define OSCEN_B200_EP_SEGMENTS 0                   /* 1: per-warp plain segments like the other kernels — bit-identical and 4 % SLOWER here
+                                                      (13.2 vs 12.7 ms per 131 072 x 16-voice block, profiles/r02_ab_epiano_segments.log):
+                                                      the per-iteration tests it removes are a few instructions next to 16 harmonics x 12
+                                                      FP32 operations per lane, and the second copy of the body costs more than it saves */
+#endif
 #ifndef OSCEN_B200_EP_MIN_BLOCKS
 #define OSCEN_B200_EP_MIN_BLOCKS 3                 /* CTAs per SM the register allocation aims at */
 #endif
@@ -428,7 +434,46 @@ __global__ void __launch_bounds__(kEpThreads, OSCEN_B200_EP_MIN_BLOCKS) epiano_k
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
         const uint32_t j_end = f0 + fe + (kEpLanes - 1u);     /* lane 3 has then written frames [f0, f0 + fe) */
-        for (; j < j_end; ++j) {
+        while (j < j_end) {
+            /* (A/B form, off by default: see OSCEN_B200_EP_SEGMENTS) per warp, L pipeline iterations in which no lane has an event, a ramp, the
+               first frame of the block, an interpolation step that computes a target (step 0) or lands on it (step 64), or a
+               frame outside the block run the plain body — no event / step / frequency tests (the frequency only moves with
+               an event, a ramp or between blocks) and the interpolation without its select; then ONE general iteration. */
+            if (OSCEN_B200_EP_SEGMENTS) {
+                const uint32_t fq = j - q;                    /* j < q wraps: not a frame yet */
+                uint32_t np = 0u;
+                if (fq < frames && fq != 0u && ramp_mask == 0u) {
+                    np = frames - fq;
+                    if (active) np = umin(umin(np, ec.next_frame - fq), (step - 1u) < 63u ? 64u - step : 0u);
+                }
+                const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), j_end - j);
+                if (L > 0u) {
+                    for (uint32_t i_ = 0; i_ < L; ++i_) {
+                        float sum = __shfl_up_sync(0xffffffffu, part, 1);
+                        if (q == 0u) sum = 0.0f;
+                        const float t = (float)(step + 1u) / 64.0f;
+                        const float omt = 1.0f - t;
+#pragma unroll
+                        for (int i = 0; i < (int)kEpH; ++i) cur[i] = cur[i] * omt + tgt[i] * t;
+                        step += 1u;
+#pragma unroll
+                        for (int i = 0; i < (int)kEpH; ++i) {
+                            const float nr = ore[i] * mre[i] - oim[i] * mim[i];
+                            const float ni = ore[i] * mim[i] + oim[i] * mre[i];
+                            ore[i] = nr; oim[i] = ni;
+                            sum += ni * cur[i];
+                        }
+                        part = sum;
+                        if (q == kEpLanes - 1u) {             /* inside a segment the last lane's frame is always in this tile */
+                            const float y = active ? sum * 3.0f : 0.0f;
+                            if (keepv) a.voice_out[(fq + i_) * n + v] = y;
+                            tile[(fq + i_ - f0) * kTileW + col] = y;
+                        }
+                    }
+                    j += L;
+                    continue;
+                }
+            }
             float sum = __shfl_up_sync(0xffffffffu, part, 1);
             if (q == 0u) sum = 0.0f;
             const uint32_t f = j - q;                         /* j < q wraps: not a frame yet */
@@ -490,6 +535,7 @@ __global__ void __launch_bounds__(kEpThreads, OSCEN_B200_EP_MIN_BLOCKS) epiano_k
                 if (keepv) a.voice_out[f * n + v] = y;        /* n_voices * 512 < 2^32 (checked at create) */
                 tile[(f - f0) * kTileW + col] = y;
             }
+            j += 1u;
         }
         /* ---- flush: instance sum (index order) -> Tremolo (sequential in time) -> Frame<2> */
         __syncthreads();

@@ -12,7 +12,10 @@ from parity_util import lcg_noise
 from host_kernel import HostEngine, HostNodePlanEngine
 from oscen_b200 import abi
 GATE = O.EV_GATE
-def run(kind, seed, ramps=False, extended=False):
+BLOCKS = {"uniform": 0, "general": 0}        # blocks of the generated kernel rendered by each variant (--specialize)
+
+
+def run(kind, seed, ramps=False, extended=False, specialize=False):
     rng = np.random.default_rng(777000 + seed)
     rg = R.make_graph(rng, feedback=(kind == "feedback"), multirate=(kind == "multirate"), extended=extended)
     src = rg.dsl()
@@ -22,6 +25,11 @@ def run(kind, seed, ramps=False, extended=False):
         n, vpi = 4, 2
     g = abi.Graph(src)
     vals = {name: (d * (1.0 + 0.1 * np.arange(n))).astype(np.float32) for name, d in rg.values.items()}
+    uniform = set()
+    if specialize:                                             # --specialize: a random subset of the inputs holds ONE value for the bank
+        for name in sorted(rg.values):
+            if rng.random() < 0.6:
+                uniform.add(name); vals[name] = np.full(n, np.float32(rg.values[name]) * np.float32(1.25), dtype=np.float32)
     x = np.stack([lcg_noise(frames, 300 + seed * 8 + v) for v in range(n)], axis=1) if rg.has_input else None
     gates = [(v, 2 + 3 * v, 0.5 + 0.1 * v) for v in range(n)] + [(v, 50 + v, 0.0) for v in range(n)] if rg.has_gate else []
     # odd seeds: the first value input is uniform and RAMPS (set_<v>_with_ramp) from frame 0 across the block boundary
@@ -57,9 +65,13 @@ def run(kind, seed, ramps=False, extended=False):
             if ramp and name == ramp[0]:
                 eng.set_value(g.input_id(name), ramp[1]); eng.set_value_ramp(g.input_id(name), ramp[2], ramp[3])
             elif callable(arr):
-                eng.set_value(g.input_id(name), base)
+                eng.set_value(g.input_id(name), float(base[0]) if name in uniform else base)
+            elif name in uniform:
+                eng.set_value(g.input_id(name), float(arr[0]))                 # broadcast
             else:
                 eng.set_value(g.input_id(name), arr)
+        if specialize and label == "generated kernel":
+            eng.specialize()                   # oscen_b200_specialize: the constant-bank variant, picked per block with fallback
         got, inst = [], []
         for lo, hi in ((0, 29), (29, 72)):
             if x is not None: eng.stream_in(0, x[lo:hi])
@@ -67,6 +79,7 @@ def run(kind, seed, ramps=False, extended=False):
             ev += [(v, f - lo, g.input_id(nm), s) for v, f, nm, s in value_events if lo <= f < hi]
             if ev: eng.push_events(ev)
             eng.process_block(hi - lo)
+            if label == "generated kernel": BLOCKS[eng.last_kernel] += 1
             got.append(eng.read_voice_out()); inst.append(eng.read_instance_out())
         got, inst = np.concatenate(got), np.concatenate(inst)
         eng.close()
@@ -84,13 +97,14 @@ if __name__ == "__main__":
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
     ramps = "--ramps" in sys.argv
     extended = "--extended" in sys.argv
+    specialize = "--specialize" in sys.argv
     tally = {}
     t0 = time.time()
     for seed in range(lo, hi):
         for kind in ("plain", "feedback", "multirate"):
             try:
-                r = run(kind, seed, ramps, extended)
+                r = run(kind, seed, ramps, extended, specialize)
             except Exception as ex:
                 r = "EXC"; print("EXC", kind, seed, repr(ex)[:300], flush=True)
             tally[(kind, r)] = tally.get((kind, r), 0) + 1
-    print(sorted(tally.items()), "%.0fs" % (time.time() - t0), flush=True)
+    print(sorted(tally.items()), "%.0fs" % (time.time() - t0), ("blocks by variant: %s" % BLOCKS) if specialize else "", flush=True)

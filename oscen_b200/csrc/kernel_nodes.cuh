@@ -737,17 +737,24 @@ __global__ void __launch_bounds__(kCta) instance_mix_node_kernel(const __grid_co
     const uint32_t v = blockIdx.x * kCta + threadIdx.x;
     const uint32_t frames = a.ctl->frames;
     const uint32_t col = tile_col(threadIdx.x, a.vpi);
+    /* software-pipelined: the 32 independent loads of tile k + 1 are in flight while tile k is folded (three barriers and a
+       sequential per-instance fold): 0.41 -> see profiles/r02_ab_instance_mix_pipelined.log per 1 M-voice block */
+    float x[kTileF];
+    const bool on = v < n;
+    {
+        const uint32_t fe = min(kTileF, frames);
+#pragma unroll
+        for (uint32_t ff = 0; ff < kTileF; ++ff) x[ff] = (on && ff < fe) ? __ldcs(final_stream + (ff * n + v)) : 0.0f;
+    }
     for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {
         const uint32_t fe = min(kTileF, frames - f0);
-        if (fe == kTileF) {                                   /* full tile: 32 independent loads in flight per thread */
-            float x[kTileF];
 #pragma unroll
-            for (uint32_t ff = 0; ff < kTileF; ++ff) x[ff] = (v < n) ? __ldcs(final_stream + ((f0 + ff) * n + v)) : 0.0f;
+        for (uint32_t ff = 0; ff < kTileF; ++ff) tile[ff * kTileW + col] = x[ff];
+        const uint32_t f1 = f0 + kTileF;
+        if (f1 < frames) {
+            const uint32_t fe1 = min(kTileF, frames - f1);
 #pragma unroll
-            for (uint32_t ff = 0; ff < kTileF; ++ff) tile[ff * kTileW + col] = x[ff];
-        } else {
-            for (uint32_t ff = 0; ff < fe; ++ff)
-                tile[ff * kTileW + col] = (v < n) ? __ldcs(final_stream + ((f0 + ff) * n + v)) : 0.0f;
+            for (uint32_t ff = 0; ff < kTileF; ++ff) x[ff] = (on && ff < fe1) ? __ldcs(final_stream + ((f1 + ff) * n + v)) : 0.0f;
         }
         tile_flush_mono(a, tile, isum, f0, fe);
     }

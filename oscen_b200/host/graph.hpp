@@ -190,6 +190,14 @@ public:
         const uint32_t ch = channels ? channels : 1u;
         check(oscen_b200_load_asset(raw(), (uint32_t)id, interleaved.data(), (uint32_t)(interleaved.size() / ch), ch), raw(), "load_asset");
     }
+    /* (no reference counterpart: one reference instance has one f32 per value input) compile the kernel variant that reads the
+       value inputs which hold one value for the whole bank from the constant bank; returns the mask of the ids taken.  Runs
+       NVRTC: not for the audio thread */
+    uint32_t specialize() {
+        uint32_t mask = 0;
+        check(oscen_b200_specialize(raw(), &mask), raw(), "specialize");
+        return mask;
+    }
     std::string describe() const {
         std::string s(1 << 16, '\0');
         oscen_b200_graph_describe(g_, &s[0], s.size());

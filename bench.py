@@ -457,7 +457,7 @@ def kernels_report(names, kern_ms):
 
 # ------------------------------------------------------------------------------------------------ other configs
 def other_config_run(ctx, abi, shard, name, kind, n_total, vpi, state_words, n_inputs, steps, setup, scaling, keep=None,
-                     plan=None, mix="p2p", in_bytes=0, model_n=None):
+                     plan=None, mix="p2p", in_bytes=0, model_n=None, graph_file=None, specialize=False):
     """one BASELINE config at its own size: device-timed (L2 flushed), voices sharded over the ranks for N > 1"""
     world, rank = ctx.world, ctx.rank
     if scaling == "strong":
@@ -466,9 +466,19 @@ def other_config_run(ctx, abi, shard, name, kind, n_total, vpi, state_words, n_i
         first, n = rank * n_total, n_total
     keep = (abi.KEEP_INSTANCE_OUT if vpi > 1 else 0) if keep is None else keep
     plan = abi.PLAN_FUSED if plan is None else plan
-    eng = abi.Engine(kind, n, vpi, SR, ctx.local_rank, plan, keep)
+    if graph_file is None:
+        eng = abi.Engine(kind, n, vpi, SR, ctx.local_rank, plan, keep)
+    else:
+        # the graph compiler's path: the same graph from its `graph!` text, ONE kernel generated for it and compiled with NVRTC
+        text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "graphs", graph_file)).read()
+        eng = abi.Engine.from_graph(abi.Graph(text), n, vpi, SR, ctx.local_rank, keep, plan)
     mix_mode = shard.connect_mix_bus(eng, rank, world, mix)
     prepare = setup(eng, first, n)
+    if specialize:
+        # the variant for the bank-uniform inputs; `frequency` (input 0) is per voice in this workload — block 0 writes it — so it is
+        # marked per-voice before the call and stays in a register
+        eng.set_value(0, np.full(n, 440.0, dtype=np.float32))
+        eng.specialize()
     step_ms, kern_ms, names, _ = device_timed_pass(ctx, eng, prepare, steps, 3)
     dev_ms = ctx.max_over_ranks(float(np.sum(step_ms)))
     voices_all = n_total if scaling == "strong" else n_total * world
@@ -550,6 +560,19 @@ def other_configs(ctx, args, abi, shard):
                                     plan=abi.PLAN_NODES, model_n=MODEL_N_BYTES))
         out.append(other_config_run(ctx, abi, shard, "fm-synth FMVoice x 65 536 voices, NODE plan", abi.GRAPH_FM_VOICE, 65536, VPI, FM_STATE_WORDS, 1,
                                     steps, lambda e, f, n: S["fm"](e, f, n, 65536), "weak", plan=abi.PLAN_NODES, model_n=MODEL_N_BYTES))
+    if single:
+        # the graph compiler at bench scale: the two reference graphs from their own `graph!` text
+        for nm, kw in (("graph compiler: FMVoice from tests/graphs/voice_fm3.graph, generated kernel (NVRTC) + oscen_b200_specialize, 65 536 voices, blocks 3.. of the bench schedule (decay stages; from block 10 the ramp blocks, which a generated kernel renders on its per-frame path)",
+                        dict(kind=abi.GRAPH_FM_VOICE, n_total=65536, vpi=VPI, state_words=FM_STATE_WORDS, n_inputs=1, steps=steps,
+                             setup=lambda e, f, n: S["fm"](e, f, n, 65536), graph_file="voice_fm3.graph", specialize=True)),
+                       ("graph compiler: ElectricPiano from tests/graphs/electric_piano.graph (array-typed streams, Tremolo -> Frame<2>), generated kernel, 16 384 instances x 16 voices",
+                        dict(kind=abi.GRAPH_EPIANO, n_total=16384 * 16, vpi=16, state_words=259, n_inputs=9, steps=max(3, steps // 2),
+                             setup=S["epiano"], graph_file="electric_piano.graph"))):
+            try:
+                out.append(other_config_run(ctx, abi, shard, nm, kw.pop("kind"), kw.pop("n_total"), kw.pop("vpi"), kw.pop("state_words"),
+                                            kw.pop("n_inputs"), kw.pop("steps"), kw.pop("setup"), "weak", **kw))
+            except Exception as ex:              # a box without libnvrtc: reported, never silently replaced by another path
+                out.append({"config": nm, "error": repr(ex)[:300]})
     # north_star operating point: 1 250 000-class FM bank PER GPU (10 M voices on 8 GPUs), weak scaling
     n_ns = 1250048                      # a multiple of 64
     r = other_config_run(ctx, abi, shard, f"north_star point: fm-synth FMVoice x {n_ns} voices per GPU ({n_ns * ctx.world} voices on {ctx.world} GPU(s))",

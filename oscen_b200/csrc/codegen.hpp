@@ -394,11 +394,27 @@ struct Emitter {
         const bool segmented = hoist_adsr && !inner_adsr && env_int("OSCEN_B200_JIT_SEGMENTS", 1) != 0;
         line(1, "for (uint32_t f0 = 0; f0 < frames; f0 += kTileF) {");
         line(2, "const uint32_t fe = min(kTileF, frames - f0);");
+        /* Blocks with a ramping input: segments too, as long as no ramped input feeds a quantity this kernel derives outside
+           process() and keeps across frames — the envelopes' step data / clamped sustain (adsr_derive_r, adsr_refresh) and the FM
+           operators' phase increment (fmop_phase_inc).  Such a segment runs the plain walk with the frame's ramp row loaded
+           first (`tick_ramps`, codegen/mod.rs:878-914); every other node reads its parameters inside process() each frame
+           anyway.  OSCEN_B200_JIT_RAMP_SEGMENTS=0: ramp blocks on the per-frame path (A/B). */
+        uint32_t hoist_mask = 0;
+        for (int i = 0; i < n_nodes; ++i) {
+            const plan::Node &nd = g.nodes[i];
+            const int slots = nd.type == T::Adsr ? 4 : (nd.type == T::FmOperator ? 2 : 0);
+            for (int k = 0; k < slots; ++k) if (nd.pid[k] != plan::kNoValue) hoist_mask |= 1u << nd.pid[k];
+        }
+        const bool ramp_segments = segmented && ni > 0 && env_int("OSCEN_B200_JIT_RAMP_SEGMENTS", 1) != 0;
         if (segmented) {
             line(2, "uint32_t ff = 0;");
             line(2, "while (ff < fe) {");
             line(3, "const uint32_t f = f0 + ff;");
             line(3, "{");
+            if (ramp_segments) {
+                line(4, fmt("const bool ramp_seg = (ramp_mask & 0x%xu) == 0u;    /* no ramp on an input behind hoisted state */", hoist_mask));
+                line(4, "uint32_t np = ((ramp_mask != 0u && !ramp_seg) || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);");
+            } else
             line(4, "uint32_t np = (ramp_mask != 0u || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);");
             for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
                 line(4, "np = oscen::umin(np, adsr_plain_frames(" + N(i) + "));");
@@ -412,19 +428,30 @@ struct Emitter {
                 rl_any += (rl_any.empty() ? "" : " | ") + std::string("rl") + k;
             }
             if (any_adsr_node) line(5, "const bool any_rl = __any_sync(0xffffffffu, " + rl_any + ");");
-            line(5, "for (uint32_t i_ = 0; i_ < L; ++i_) {");
-            line(6, "const uint32_t f = f0 + ff + i_;");
-            line(6, "float y = 0.0f;");
-            line(6, "if (active) {");
-            if (has_in) line(7, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
-            plain_mode = true;
-            emit_walk(7);
-            plain_mode = false;
-            line(7, "y = " + S(g.output.node, g.output.port) + ";    /* -> " + g.output_name + " */");
-            line(7, "if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;");
-            line(6, "}");
-            line(6, "tile[(ff + i_) * kTileW + col] = y;");
-            line(5, "}");
+            for (int ramp_form = 0; ramp_form < (ramp_segments ? 2 : 1); ++ramp_form) {
+                /* two copies of the plain loop: without ramps nothing in it writes a parameter (so the compiler hoists every
+                   parameter-derived computation out of it); with ramps the frame's row is loaded first */
+                if (ramp_segments) line(5, ramp_form == 0 ? "if (ramp_mask == 0u) {" : "} else {");
+                line(5, "for (uint32_t i_ = 0; i_ < L; ++i_) {");
+                line(6, "const uint32_t f = f0 + ff + i_;");
+                line(6, "float y = 0.0f;");
+                line(6, "if (active) {");
+                if (ramp_form == 1) {
+                    line(7, "const float *row = a.ptab + (size_t)f * kMaxInputs;");
+                    for (uint32_t i = 0; i < ni; ++i) if (!((uniform_mask >> i) & 1u) && !((hoist_mask >> i) & 1u))
+                        line(7, fmt("if ((ramp_mask >> %u) & 1u) P[%u] = row[%u];", i, i, i));
+                }
+                if (has_in) line(7, "const float x_in = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? __ldcs(a.stream_in + (size_t)f * n + v) : 0.0f);");
+                plain_mode = true;
+                emit_walk(7);
+                plain_mode = false;
+                line(7, "y = " + S(g.output.node, g.output.port) + ";    /* -> " + g.output_name + " */");
+                line(7, "if (a.voice_out != nullptr) a.voice_out[(size_t)f * n + v] = y;");
+                line(6, "}");
+                line(6, "tile[(ff + i_) * kTileW + col] = y;");
+                line(5, "}");
+            }
+            if (ramp_segments) line(5, "}");
             for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].type == T::Adsr)
                 line(5, "if (!any_rl && ad" + std::to_string(i) + ") " + N(i) + ".rem -= L;    /* the Release form counts down per frame itself */");
             line(5, "ff += L;");

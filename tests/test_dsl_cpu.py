@@ -265,8 +265,13 @@ def test_generated_kernel_walks_nodes_in_topological_order():
                  ("op1_mod_mixer", "op1_osc"), ("op1_osc", "filter"), ("env_filter", "filter_env_gain"),
                  ("filter_env_gain", "cutoff_mod"), ("cutoff_mod", "filter"), ("filter", "output_gain")]:
         assert pos[a] < pos[b], (a, b)
-    # the walk is emitted twice: the plain-segment copy (envelopes in their segment form) and the general frame
-    assert src.count("adsr_on_gate(") == 4 and src.count("fmop_process_k(") == 6 and src.count("adsr_ad(") == 4
+    # the walk is emitted three times: the plain-segment copy (envelopes in their segment form), its twin that loads the frame's
+    # ramp row first (ramp blocks whose ramps stay off the envelopes' and the operators' hoisted state), and the general frame
+    assert src.count("adsr_on_gate(") == 4 and src.count("fmop_process_k(") == 9 and src.count("adsr_ad(") == 8
+    # hoisted state sits behind frequency, the three ratios and the sixteen envelope times / sustain levels
+    hoisted = [0, 1, 8, 15] + [4, 5, 6, 7, 11, 12, 13, 14, 16, 17, 18, 19, 23, 24, 25, 26]
+    assert "(ramp_mask & 0x%xu) == 0u" % sum(1 << i for i in hoisted) in src
+    assert "if ((ramp_mask >> 21) & 1u) P[21] = row[21];" in src and src.count("P[21] = row[21]") == 2 and src.count("P[4] = row[4]") == 1
     assert src.count("__reduce_min_sync(") == 1 and "oscen::umin(np, adsr_plain_frames(n0))" in src
     # literals are emitted bit-exactly
     assert "0x3e99999au /* 0.300000012 */" in src      # output_gain = Gain::new(0.3)
@@ -296,7 +301,7 @@ def test_multirate_lowering_inserts_one_resampler_per_cross_rate_edge():
     assert "state words per voice: 49" in d                    # phase + SincDownFir<4>: 2 stages x 24 taps (== the built-in SAT layout)
     src = g.codegen()
     assert "DownEdge<0, 2>" in src and "const float sri = sr * 4.0f;" in src and 'for (int inner = 0; inner < 4; ++inner)' in src
-    assert src.count(", sri);") == 2                           # only the oscillator sees the inner sample rate (in both copies of the walk: plain segment + general frame)
+    assert src.count(", sri);") == 3                           # only the oscillator sees the inner sample rate (in the three copies of the walk: plain segment, ramp segment, general frame)
     assert g.jit_check() > 10000
 
 

@@ -130,3 +130,64 @@ def test_specialize_is_refused_for_built_in_kinds_and_node_plans():
         with pytest.raises(abi.EngineError, match="specialize"):
             eng.specialize()
         eng.close()
+
+
+# ---------------------------------------------------------------------------- ramp blocks of the generated kernels
+def ramp_script(bank, n):
+    """gates, a long ramp on the filter cutoff (nothing derived outside process() hangs on it: ramp SEGMENTS), value events in
+    the middle of it, then a ramp on an envelope's attack time (hoisted step data: those blocks stay on the per-frame path)
+    together with a second cutoff ramp, note-offs and re-triggers while it runs"""
+    frames = 100
+    vo, io = [], []
+    bank.set_value(0, (110.0 * 2.0 ** ((np.arange(n) % 37) / 12.0)).astype(np.float32))
+    bank.set_value(ENV_AMOUNT, 700.0)
+    for blk in range(9):
+        if blk == 0:
+            bank.push_events([(v, (11 * v) % frames, GATE, 0.4 + 0.6 * ((v * 7) % 13) / 13.0) for v in range(n)])
+        if blk == 1:
+            bank.set_value_ramp(CUTOFF, 2600.0, 330)                  # blocks 1..4
+        if blk == 2:
+            bank.push_events([(v, 5 + (3 * v) % 90, OP2_LEVEL, 0.3 + 0.005 * v) for v in range(0, n, 4)])
+        if blk == 5:
+            bank.set_value_ramp(4, 0.03, 150)                         # op3_attack: blocks 5..6
+            bank.set_value_ramp(CUTOFF, 1500.0, 250)                  # blocks 5..7
+            bank.push_events([(v, (5 * v) % frames, GATE, 0.0) for v in range(0, n, 2)])
+        if blk == 6:
+            bank.push_events([(v, (7 * v) % frames, GATE, 0.9) for v in range(0, n, 4)])
+        bank.process_block(frames)
+        vo.append(bank.read_voice_out()); io.append(bank.read_instance_out())
+    return np.concatenate(vo), np.concatenate(io)
+
+
+@pytest.mark.parametrize("ramp_segments", ["1", "0"])
+def test_host_executed_generated_kernel_ramp_blocks_with_and_without_ramp_segments(ramp_segments, monkeypatch):
+    from host_kernel import HostEngine
+    monkeypatch.setenv("OSCEN_B200_JIT_RAMP_SEGMENTS", ramp_segments)
+    n, vpi = 72, 8
+    eng = HostEngine(open(os.path.join(GRAPHS, "voice_fm3.graph")).read(), n, vpi)
+    assert ("const bool ramp_seg" in eng.graph.codegen()) == (ramp_segments == "1")
+    ref, got = ramp_script(O.OracleBank(O.K_FM, n, vpi), n), ramp_script(eng, n)
+    assert np.abs(ref[0]).max() > 0.01
+    assert np.array_equal(got[0], ref[0]), float(np.abs(got[0] - ref[0]).max())
+    assert np.array_equal(got[1], ref[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ramp_segments", ["1", "0"])
+def test_generated_kernel_ramp_blocks_with_and_without_ramp_segments_on_device(ramp_segments):
+    from oscen_b200 import abi
+    n, vpi = 200, 8
+    old = os.environ.get("OSCEN_B200_JIT_RAMP_SEGMENTS")
+    try:
+        os.environ["OSCEN_B200_JIT_RAMP_SEGMENTS"] = ramp_segments
+        eng = abi.Engine.from_graph(abi.Graph(open(os.path.join(GRAPHS, "voice_fm3.graph")).read()), n, vpi, plan=abi.PLAN_FUSED)
+    finally:
+        if old is None:
+            os.environ.pop("OSCEN_B200_JIT_RAMP_SEGMENTS", None)
+        else:
+            os.environ["OSCEN_B200_JIT_RAMP_SEGMENTS"] = old
+    ref, got = ramp_script(O.OracleBank(O.K_FM, n, vpi), n), ramp_script(eng, n)
+    eng.close()
+    assert np.abs(ref[0]).max() > 0.01
+    assert np.array_equal(got[0], ref[0]), float(np.abs(got[0] - ref[0]).max())
+    assert np.array_equal(got[1], ref[1])

@@ -67,21 +67,27 @@ __global__ void __launch_bounds__(kCta) twin_peaks_kernel(const __grid_constant_
         uint32_t ff = 0;
         while (ff < fe) {
             const uint32_t f = f0 + ff;
-            const uint32_t np = ramp_mask != 0u ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);
+            /* (ramp blocks are segmented too: LP18Filter reads its parameters inside process(), nothing derived from them is
+               kept outside it — the plain loop's twin loads the frame's ramp row first; two copies, so that without ramps
+               nothing in the loop writes a parameter and the parameter tests stay loop-invariant) */
+            const uint32_t np = active ? ec.next_frame - f : 0x7FFFFFFFu;
             const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
             if (L > 0u) {
-#pragma unroll 1
-                for (uint32_t i = 0; i < L; ++i) {
-                    float y = 0.0f;
-                    if (active) {
-                        const float x = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? isum[(ff + i) * kCta + threadIdx.x] : 0.0f);
-                        const float ya = lp18_process(fa, x, prm.P[0], 0.0f, prm.P[2], sr);
-                        const float yb = lp18_process(fb, x, prm.P[1], 0.0f, prm.P[2], sr);
-                        y = ya - yb;
-                        if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;
-                    }
-                    tile[(ff + i) * kTileW + col] = y;
+#define OSC_TWIN_PLAIN_LOOP(RAMPS)                                                                                               \
+                _Pragma("unroll 1") for (uint32_t i = 0; i < L; ++i) {                                                         \
+                    float y = 0.0f;                                                                                              \
+                    if (active) {                                                                                                \
+                        if (RAMPS) prm.ramps(a, ramp_mask, f + i);                                                               \
+                        const float x = lcg_on ? lcg_next(lcg) : ((a.stream_in != nullptr) ? isum[(ff + i) * kCta + threadIdx.x] : 0.0f); \
+                        const float ya = lp18_process(fa, x, prm.P[0], 0.0f, prm.P[2], sr);                                      \
+                        const float yb = lp18_process(fb, x, prm.P[1], 0.0f, prm.P[2], sr);                                      \
+                        y = ya - yb;                                                                                             \
+                        if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;                                    \
+                    }                                                                                                            \
+                    tile[(ff + i) * kTileW + col] = y;                                                                           \
                 }
+                if (ramp_mask == 0u) { OSC_TWIN_PLAIN_LOOP(false) } else { OSC_TWIN_PLAIN_LOOP(true) }
+#undef OSC_TWIN_PLAIN_LOOP
                 ff += L;
                 continue;
             }
@@ -172,6 +178,9 @@ __global__ void __launch_bounds__(kCta) sat_kernel(const __grid_constant__ Kerne
         uint32_t ff = 0;
         while (ff < fe) {
             const uint32_t f = f0 + ff;
+            /* (ramp blocks stay per-frame here: a second copy of this kernel's unrolled plain loop for them costs the ramp-free
+               blocks 0.9 % — 0.821 vs 0.814 ms at config 5, profiles/r02_ab_ramp_blocks_handwritten.log — and the saturator's
+               benchmark workload never ramps; TwinPeaks and Synth have the second copy) */
             const uint32_t np = ramp_mask != 0u ? 0u : ec.next_frame - f;
             const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
             if (L > 0u) {
@@ -229,26 +238,33 @@ __global__ void __launch_bounds__(kCta) synth_kernel(const __grid_constant__ Ker
         uint32_t ff = 0;
         while (ff < fe) {
             const uint32_t f = f0 + ff;
-            uint32_t np = (ramp_mask != 0u || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);
+            /* (a block whose ramps stay off the envelope's inputs — attack, decay, sustain, release: the step data and the
+               clamped sustain are derived outside process() — is segmented too; its plain loop loads the frame's ramp row first) */
+            const bool ramp_seg = (ramp_mask & 0xF0u) == 0u;
+            uint32_t np = ((ramp_mask != 0u && !ramp_seg) || f == 0u) ? 0u : (active ? ec.next_frame - f : 0x7FFFFFFFu);
             if (WITH_ADSR) np = umin(np, adsr_plain_frames(env));
             const uint32_t L = umin(__reduce_min_sync(0xffffffffu, np), fe - ff);
             if (L > 0u) {
                 const bool ad = (env.stage == ST_ATTACK) | (env.stage == ST_DECAY), rl = env.stage == ST_RELEASE;
                 const float tg = env.stage == ST_ATTACK ? 1.0f : hot.sus, kk = env.stage == ST_ATTACK ? d.a_k : d.d_k;
                 const bool any_rl = WITH_ADSR && __any_sync(0xffffffffu, rl);
-                for (uint32_t i = 0; i < L; ++i) {
-                    float y = 0.0f;
-                    if (active) {
-                        const float m = polyblep_process<WAVE_SINE>(ph_mod, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr);
-                        float g = 1.0f;
-                        if (WITH_ADSR) g = any_rl ? adsr_plain_rel(env, ad, rl, tg, kk) : adsr_ad(env, ad, tg, kk);
-                        const float c = polyblep_process<WAVE_SAW>(ph_car, 0.0f, prm.P[2], m, 0.5f, 0.5f, sr);
-                        const float lp = tpt_process(tp, c, prm.P[3], 0.707f, 0.0f, sr);
-                        y = WITH_ADSR ? lp * g : lp;             /* vca: Gain */
-                        if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;
-                    }
-                    tile[(ff + i) * kTileW + col] = y;
+#define OSC_SYNTH_PLAIN_LOOP(RAMPS)                                                                                              \
+                for (uint32_t i = 0; i < L; ++i) {                                                                               \
+                    float y = 0.0f;                                                                                              \
+                    if (active) {                                                                                                \
+                        if (RAMPS) prm.ramps(a, ramp_mask, f + i);                                                               \
+                        const float m = polyblep_process<WAVE_SINE>(ph_mod, 0.0f, prm.P[0], 0.0f, prm.P[1], 0.5f, sr);           \
+                        float g = 1.0f;                                                                                          \
+                        if (WITH_ADSR) g = any_rl ? adsr_plain_rel(env, ad, rl, tg, kk) : adsr_ad(env, ad, tg, kk);              \
+                        const float c = polyblep_process<WAVE_SAW>(ph_car, 0.0f, prm.P[2], m, 0.5f, 0.5f, sr);                   \
+                        const float lp = tpt_process(tp, c, prm.P[3], 0.707f, 0.0f, sr);                                         \
+                        y = WITH_ADSR ? lp * g : lp;             /* vca: Gain */                                                 \
+                        if (a.voice_out != nullptr) a.voice_out[(size_t)(f + i) * n + v] = y;                                    \
+                    }                                                                                                            \
+                    tile[(ff + i) * kTileW + col] = y;                                                                           \
                 }
+                if (ramp_mask == 0u) { OSC_SYNTH_PLAIN_LOOP(false) } else { OSC_SYNTH_PLAIN_LOOP(true) }
+#undef OSC_SYNTH_PLAIN_LOOP
                 if (WITH_ADSR && !any_rl && ad) env.rem -= L;    /* the Release form counts down per frame itself */
                 ff += L;
                 continue;

@@ -821,3 +821,32 @@ def test_generated_kernel_compiles_from_a_relocated_library(tmp_path):
                        env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "voice_fm3" in r.stdout and "sat_4x" in r.stdout
+
+
+def test_param_specs_with_commas_and_the_three_setters():
+    """oscen-lib/tests/param_spec_test.rs: `[log, ramp: 100]` parses (commas inside the spec), and the ramped input has the three
+    generated setters — set_freq (the declared 100-frame ramp), set_freq_with_ramp (a custom length), set_freq_immediate — after
+    which `freq.current == 1000.0`.  (The reference graph declares no output; a bank has nothing to render without one, so
+    that text itself is refused with a diagnostic and the mirror adds `filter.output -> out`.)"""
+    from host_kernel import HostEngine
+    ref_text = """graph! { name: TestGraph; input value freq = 440.0 [log, ramp: 100];
+        nodes { osc = PolyBlepOscillator::saw(440.0, 0.6); filter = TptFilter::new(1000.0, 0.707); }
+        connections { freq -> osc.frequency_mod; osc.output -> filter.input; } }"""
+    with pytest.raises(abi.GraphCompileError, match="declares no stream output"):
+        abi.Graph(ref_text)
+    g = abi.Graph(ref_text.replace("nodes {", "output stream out; nodes {").replace("osc.output -> filter.input;", "osc.output -> filter.input; filter.output -> out;"))
+    info = g.input_info(g.input_id("freq"))
+    assert info["ramp"] == 100 and info["log"] and info["range"] is None and info["default"] == 440.0
+    eng = HostEngine(g, 3, sample_rate=44100.0)
+    fid = g.input_id("freq")
+    eng.set("freq", 880.0)                       # set_freq: the declared ramp
+    eng.process_block(40)
+    assert 440.0 < float(eng.ramps[fid].current) < 880.0 and eng.ramps[fid].frames_remaining == 60
+    eng.set_value_ramp(fid, 440.0, 50)           # set_freq_with_ramp
+    eng.process_block(50)
+    assert float(eng.ramps[fid].current) == 440.0 and eng.ramps[fid].frames_remaining == 0
+    eng.set_value(fid, 1000.0)                   # set_freq_immediate
+    eng.process_block(8)
+    assert float(eng.ramps[fid].current) == 1000.0 and float(eng.pv[fid, 0]) == 1000.0
+    import numpy as np
+    assert np.isfinite(eng.read_voice_out()).all()

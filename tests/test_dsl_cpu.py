@@ -850,3 +850,26 @@ def test_param_specs_with_commas_and_the_three_setters():
     assert float(eng.ramps[fid].current) == 1000.0 and float(eng.pv[fid, 0]) == 1000.0
     import numpy as np
     assert np.isfinite(eng.read_voice_out()).all()
+
+
+def test_multirate_parse_smoke_graphs_of_the_reference_compile():
+    """oscen-lib/tests/multirate_parse.rs: `* 4` on a node and a `[sinc]` connection policy compile; init at 44.1 and 48 kHz"""
+    for body, factor in (("osc = PolyBlepOscillator::saw(440.0, 0.6) * 4; } connections { osc.output -> audio_out;", 4),
+                         ("osc = PolyBlepOscillator::saw(440.0, 0.6) * 2; } connections { [sinc] osc.output -> audio_out;", 2)):
+        g = abi.Graph("graph! { name: Smoke; output stream audio_out; nodes { " + body + " } }")
+        assert g.launches()[1] == "1: DownEdge [osc.output -> audio_out [sinc down x%d]]" % factor
+        for sr in (44100.0, 48000.0):
+            _, words, info = g.kernel_info(sr)
+            assert info.inner_factor == factor and len(words) == info.n_state
+        assert g.jit_check() > 10000
+
+
+def test_type_validation_cases_of_the_reference():
+    """oscen-lib/tests/type_validation_test.rs: the valid graph's connections are accepted (value input -> a stream input,
+    stream -> stream); an OUTPUT as a destination and an INPUT as a source are compile errors (the two commented-out graphs)"""
+    head = "graph! { input value freq = 440.0; output stream out; nodes { osc = PolyBlepOscillator::saw(440.0, 0.6); filter = TptFilter::new(1000.0, 0.707); } connections { "
+    abi.Graph(head + "freq -> osc.frequency_mod; osc.output -> filter.input; filter.output -> out; } }")
+    with pytest.raises(abi.GraphCompileError, match="`osc.output` is an output: it cannot be a connection destination"):
+        abi.Graph(head + "freq -> osc.output; filter.output -> out; } }")
+    with pytest.raises(abi.GraphCompileError, match="`filter.input` is an input: it cannot be a connection source"):
+        abi.Graph(head + "filter.input -> osc.frequency; osc.output -> out; } }")

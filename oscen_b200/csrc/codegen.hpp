@@ -46,6 +46,9 @@ inline std::string lit(float v) {
     return b;
 }
 
+#ifndef OSCEN_B200_JIT_ARRAY_SMEM_DEFAULT
+#define OSCEN_B200_JIT_ARRAY_SMEM_DEFAULT 2
+#endif
 struct Emitter {
     const plan::Graph &g;
     const plan::Plan &p;
@@ -121,13 +124,18 @@ struct Emitter {
        the block it lives in a [word][thread] slice of dynamic shared memory (conflict-free: consecutive threads, consecutive
        banks) and goes back to its SoA rows at the end — as long as the CTA's slices fit; beyond that the rows are walked in
        HBM (round-2 first form, ~5x slower) */
+    /* OSCEN_B200_JIT_ARRAY_SMEM = 0: rows walked in HBM; 1: every word in shared memory; 2: the hot words (nodes.cuh AS_NHOT / OB_NHOT:
+       what each frame reads AND writes) in shared memory, the read-mostly cold words (decay / release factors, rotation
+       multipliers) in their HBM rows behind L1 — half the shared memory per CTA, so a third CTA fits an SM */
+    static int array_mode() { const char *e = getenv("OSCEN_B200_JIT_ARRAY_SMEM"); return e && *e ? atoi(e) : OSCEN_B200_JIT_ARRAY_SMEM_DEFAULT; }
     static uint32_t array_state_words(const plan::Node &nd) {
-        return nd.type == plan::NodeType::AmpSource ? 130u : (nd.type == plan::NodeType::OscBank ? 129u : 0u);
+        const bool hot_only = array_mode() == 2;
+        return nd.type == plan::NodeType::AmpSource ? (hot_only ? 66u : 130u) : (nd.type == plan::NodeType::OscBank ? (hot_only ? 65u : 129u) : 0u);
     }
     static uint32_t array_smem_floats(const plan::Graph &g) {
         uint32_t w = 0;
         for (const plan::Node &nd : g.nodes) w += array_state_words(nd);
-        if (getenv("OSCEN_B200_JIT_ARRAY_SMEM") && getenv("OSCEN_B200_JIT_ARRAY_SMEM")[0] == '0') return 0u;
+        if (array_mode() == 0) return 0u;
         return (size_t)w * 64u * sizeof(float) <= 160u * 1024u ? w : 0u;
     }
     static bool is_polyblep(plan::NodeType t) {
@@ -162,6 +170,8 @@ struct Emitter {
         const uint32_t arr_floats = array_smem_floats(g);
         const bool arr_smem = arr_floats > 0u;
         const std::string arr_stride = arr_smem ? "(size_t)kCta" : "(size_t)n";
+        const std::string cold_stride = (arr_smem && array_mode() != 2) ? "(size_t)kCta" : "(size_t)n";
+        auto cold = [&](int i) { return "c" + std::to_string(i) + ", " + cold_stride; };
         if (arr_smem) {            /* CTAs per SM are set by the shared-memory slices: let the register allocation follow */
             const int fit = (int)((220u * 1024u) / ((size_t)arr_floats * 64u * sizeof(float) + 26u * 1024u));
             min_blocks = fit < 1 ? 1 : (fit < min_blocks ? fit : min_blocks);
@@ -245,8 +255,11 @@ struct Emitter {
                     line(1, "float *" + N(i) + " = dyn + " + std::to_string(smem_off) + "u * kCta + threadIdx.x;    /* [word][thread] slice of shared memory */");
                     line(1, "_Pragma(\"unroll 8\") for (uint32_t w_ = 0; w_ < " + w + "; ++w_) " + N(i) + "[(size_t)w_ * kCta] = a.state[(size_t)(" + base + " + w_) * n + vs];");
                     smem_off += array_state_words(nd);
+                    if (array_mode() == 2) line(1, "float *c" + std::to_string(i) + " = a.state + (size_t)" + base + " * n + vs;    /* cold words: their SoA rows in HBM */");
+                    else line(1, "float *c" + std::to_string(i) + " = " + N(i) + ";");
                 } else {
                     line(1, "float *" + N(i) + " = a.state + (size_t)" + base + " * n + vs;    /* walked in its SoA rows in HBM */");
+                    line(1, "float *c" + std::to_string(i) + " = " + N(i) + ";");
                 }
                 break;
             case T::Up: case T::Down:
@@ -309,12 +322,12 @@ struct Emitter {
                           ", (size_t)n, " + std::to_string(nd.ring_cap) + "u, " + lit(nd.max_delay) + ", " + IN(i, 0, 2) + ", " + P(i, 0) + ", " + P(i, 1) + ");" + cm);
                 break;
             case T::AmpSource:
-                line(ind, "float " + S(i) + "[32]; ampsrc_process(" + N(i) + ", " + arr_stride + ", " + S(i) + ");" + cm + "    /* amplitudes: [f32; 32] */");
+                line(ind, "float " + S(i) + "[32]; ampsrc_process(" + N(i) + ", " + arr_stride + ", " + cold(i) + ", " + S(i) + ");" + cm + "    /* amplitudes: [f32; 32] */");
                 break;
             case T::OscBank:
-                if (nd.in[0].node >= 0) line(ind, o + "oscbank_process(" + N(i) + ", " + arr_stride + ", " + P(i, 0) + ", " + SR(i) + ", " + S(nd.in[0].node, nd.in[0].port) + ");" + cm);
+                if (nd.in[0].node >= 0) line(ind, o + "oscbank_process(" + N(i) + ", " + arr_stride + ", " + cold(i) + ", " + P(i, 0) + ", " + SR(i) + ", " + S(nd.in[0].node, nd.in[0].port) + ");" + cm);
                 else { line(ind, "const float z" + std::to_string(i) + "[32] = {};    /* `amplitudes` is not connected: [0.0; 32] */");
-                       line(ind, o + "oscbank_process(" + N(i) + ", " + arr_stride + ", " + P(i, 0) + ", " + SR(i) + ", z" + std::to_string(i) + ");" + cm); }
+                       line(ind, o + "oscbank_process(" + N(i) + ", " + arr_stride + ", " + cold(i) + ", " + P(i, 0) + ", " + SR(i) + ", z" + std::to_string(i) + ");" + cm); }
                 break;
             case T::SamplePlayer: line(ind, o + "sample_player_process(" + N(i) + ", buf" + std::to_string(i) + ", len" + std::to_string(i) + ");" + cm); break;
             case T::Gain: line(ind, o + IN(i, 0, -1) + " * " + (nd.in[1].node != plan::kNone ? IN(i, 1, 0) : P(i, 0)) + ";" + cm); break;
@@ -505,7 +518,7 @@ struct Emitter {
                 line(6, "adsr_on_gate(" + N(i) + ", gv, " + P(i, 0) + ", " + P(i, 3) + ", " + D(i) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
             for (int i = 0; i < n_nodes; ++i) if (g.nodes[i].gate) {
                 if (g.nodes[i].type == T::AmpSource)
-                    line(6, "ampsrc_on_gate(" + N(i) + ", " + arr_stride + ", gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
+                    line(6, "ampsrc_on_gate(" + N(i) + ", " + arr_stride + ", " + cold(i) + ", gv, " + P(i, 1) + ", " + P(i, 2) + ", " + P(i, 3) + ", " + P(i, 4) + ", " + P(i, 5) + ", " + P(i, 6) + ");    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
                 if (g.nodes[i].type == T::OscBank)
                     line(6, "oscbank_on_gate(" + N(i) + ", " + arr_stride + ", gv);    /* " + g.event_input + " -> " + g.nodes[i].name + ".gate */");
             }

@@ -763,10 +763,15 @@ __constant__ float kEpVel127[32] = {
     0.0f, 0.0f, 0.0f, 0.0f };
 
 constexpr uint32_t kEpHarmonics = 32u;
-enum : uint32_t { AS_CUR = 0, AS_TGT = 32, AS_DEC = 64, AS_REL = 96, AS_RELEASED = 128, AS_STEP = 129, AS_NSTATE = 130 };
-enum : uint32_t { OB_ORE = 0, OB_OIM = 32, OB_MRE = 64, OB_MIM = 96, OB_LASTF = 128, OB_NSTATE = 129 };
+/* State words of the two array nodes, HOT words first: the words every frame reads AND writes (amplitudes, targets, the step
+   counter; the unit oscillators).  The COLD words behind them are read-mostly — the per-note decay / release factors (read once
+   per 64-frame interpolation), the rotation multipliers (read every frame, written when the frequency moves) — and are reached
+   through a second (base, stride) pair, so that a generated kernel may keep only the hot words in shared memory for the block
+   and leave the cold ones in their HBM rows, cached by L1 (codegen.hpp).  With one home for all words both pairs are equal. */
+enum : uint32_t { AS_CUR = 0, AS_TGT = 32, AS_RELEASED = 64, AS_STEP = 65, AS_NHOT = 66, AS_DEC = 66, AS_REL = 98, AS_NSTATE = 130 };
+enum : uint32_t { OB_ORE = 0, OB_OIM = 32, OB_LASTF = 64, OB_NHOT = 65, OB_MRE = 65, OB_MIM = 97, OB_NSTATE = 129 };
 /* AmplitudeSource::on_gate -> trigger_note / release_note (electric_piano_voice.rs:230-318) */
-OSC_D void ampsrc_on_gate(float *S, size_t n, float scalar, float brightness, float velocity_scaling, float decay_rate,
+OSC_D void ampsrc_on_gate(float *S, size_t n, float *C, size_t cn, float scalar, float brightness, float velocity_scaling, float decay_rate,
                           float harmonic_decay, float key_scaling, float release_rate) {
     if (scalar > 0.0f) {
         const float velocity = scalar;
@@ -783,8 +788,8 @@ OSC_D void ampsrc_on_gate(float *S, size_t n, float scalar, float brightness, fl
         bs += velocity * velocity_scaling * 0.01f * 0.5f;
         float scaling = 1.0f;
         for (uint32_t i = 0; i < kEpHarmonics; ++i) {
-            S[(size_t)(AS_DEC + i) * n] = adjusted * scaling; scaling *= harmonic_scaling;
-            S[(size_t)(AS_REL + i) * n] = rv;
+            C[(size_t)(AS_DEC + i) * cn] = adjusted * scaling; scaling *= harmonic_scaling;
+            C[(size_t)(AS_REL + i) * cn] = rv;
             float amp = (kEpVel127[i] * velocity) + (kEpVel0[i] * (1.0f - velocity));
             amp *= 1.0f + bs * (float)i;
             S[(size_t)(AS_CUR + i) * n] = amp;
@@ -796,12 +801,12 @@ OSC_D void ampsrc_on_gate(float *S, size_t n, float scalar, float brightness, fl
     S[(size_t)AS_STEP * n] = 0.0f;
 }
 /* AmplitudeSource::process (electric_piano_voice.rs:322-351): amps = this frame's `amplitudes` */
-OSC_D void ampsrc_process(float *S, size_t n, float *amps) {
+OSC_D void ampsrc_process(float *S, size_t n, const float *C, size_t cn, float *amps) {
     uint32_t step = (uint32_t)S[(size_t)AS_STEP * n];
     const bool released = S[(size_t)AS_RELEASED * n] != 0.0f;
     if (step == 0u)
         for (uint32_t i = 0; i < kEpHarmonics; ++i)
-            S[(size_t)(AS_TGT + i) * n] = S[(size_t)(AS_CUR + i) * n] * S[(size_t)((released ? AS_REL : AS_DEC) + i) * n];
+            S[(size_t)(AS_TGT + i) * n] = S[(size_t)(AS_CUR + i) * n] * C[(size_t)((released ? AS_REL : AS_DEC) + i) * cn];
     if (step < 64u) {
         const float t = (float)(step + 1u) / 64.0f;
         for (uint32_t i = 0; i < kEpHarmonics; ++i) {
@@ -821,7 +826,7 @@ OSC_D void oscbank_on_gate(float *S, size_t n, float scalar) {
         for (uint32_t i = 0; i < kEpHarmonics; ++i) { S[(size_t)(OB_ORE + i) * n] = 1.0f; S[(size_t)(OB_OIM + i) * n] = 0.0f; }
 }
 /* OscillatorBank::process (electric_piano_voice.rs:127-170) */
-OSC_D float oscbank_process(float *S, size_t n, float frequency, float sample_rate, const float *amps) {
+OSC_D float oscbank_process(float *S, size_t n, float *C, size_t cn, float frequency, float sample_rate, const float *amps) {
     if (frequency > 0.0f && !(fabsf(S[(size_t)OB_LASTF * n] - frequency) < 0.01f)) {      /* update_multipliers */
         S[(size_t)OB_LASTF * n] = frequency;
         const float nyquist = sample_rate * 0.5f;
@@ -832,14 +837,14 @@ OSC_D float oscbank_process(float *S, size_t n, float frequency, float sample_ra
                 const float angle = 2.0f * kPi * hf / sample_rate;
                 re = om_cosf_u(angle); im = om_sinf_u(angle);
             }
-            S[(size_t)(OB_MRE + i) * n] = re; S[(size_t)(OB_MIM + i) * n] = im;
+            C[(size_t)(OB_MRE + i) * cn] = re; C[(size_t)(OB_MIM + i) * cn] = im;
             S[(size_t)(OB_ORE + i) * n] = 1.0f; S[(size_t)(OB_OIM + i) * n] = 0.0f;
         }
     }
     float sum = 0.0f;
     for (uint32_t i = 0; i < kEpHarmonics; ++i) {
         const float ore = S[(size_t)(OB_ORE + i) * n], oim = S[(size_t)(OB_OIM + i) * n];
-        const float mre = S[(size_t)(OB_MRE + i) * n], mim = S[(size_t)(OB_MIM + i) * n];
+        const float mre = C[(size_t)(OB_MRE + i) * cn], mim = C[(size_t)(OB_MIM + i) * cn];
         const float nr = ore * mre - oim * mim;
         const float ni = ore * mim + oim * mre;
         S[(size_t)(OB_ORE + i) * n] = nr; S[(size_t)(OB_OIM + i) * n] = ni;

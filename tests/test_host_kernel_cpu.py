@@ -297,7 +297,7 @@ def test_host_executed_electric_piano_kernel_matches_oracle_voices_and_stereo_in
     assert np.array_equal(vh, vr) and np.array_equal(ih, ir)
 
 
-@pytest.mark.parametrize("array_smem", ["1", "0"], ids=["state_in_shared_memory", "state_walked_in_hbm_rows"])
+@pytest.mark.parametrize("array_smem", ["1", "0", "2"], ids=["state_in_shared_memory", "state_walked_in_hbm_rows", "hot_words_in_shared_memory_cold_rows_in_hbm"])
 def test_host_executed_electric_piano_graph_from_its_own_dsl_text_matches_oracle(array_smem, monkeypatch):
     """ElectricPianoGraph compiled from the reference's two `graph!` blocks (tests/graphs/electric_piano.graph: an array-typed
     [f32; 32] stream between AmplitudeSource and OscillatorBank, 16 voices -> sum -> Tremolo -> Frame<2>): the GENERATED
@@ -310,8 +310,8 @@ def test_host_executed_electric_piano_graph_from_its_own_dsl_text_matches_oracle
     ref, host = O.OracleBank(O.K_EPIANO, n, vpi), HostEngine(text("electric_piano.graph"), n)
     assert host.vpi == vpi and host.channels == 2
     src, _, info = host.graph.kernel_info(48000.0)
-    assert ("dyn + 130u * kCta + threadIdx.x" in src) == (array_smem == "1")
-    assert info.dyn_smem_bytes == (259 * 64 * 4 if array_smem == "1" else 0)
+    assert ("dyn + 130u * kCta + threadIdx.x" in src) == (array_smem == "1") and ("dyn + 66u * kCta + threadIdx.x" in src) == (array_smem == "2")
+    assert info.dyn_smem_bytes == {"1": 259 * 64 * 4, "2": (66 + 65) * 64 * 4, "0": 0}[array_smem]
 
     def script(b):
         out_v, out_i = [], []

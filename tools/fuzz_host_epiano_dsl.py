@@ -2,12 +2,14 @@
 tests/graphs/electric_piano.graph, executed on the host, against the oracle bank.  OSCEN_B200_JIT_ARRAY_SMEM picks the home of the
 array nodes' state.   PYTHONPATH=tests:. python tools/fuzz_host_epiano_dsl.py FIRST LAST"""
 import sys, os
-sys.path.insert(0, '/root/repo/tests'); sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for d in ('tests', '', 'tools'):
+    sys.path.insert(0, os.path.join(ROOT, d))
 import numpy as np
 import oracle_lib as O
 from host_kernel import HostEngine
 import fuzz_host_builtin as F
-text = open('/root/repo/tests/graphs/electric_piano.graph').read()
+text = open(os.path.join(ROOT, 'tests', 'graphs', 'electric_piano.graph')).read()
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
 ok = bad = 0
 for seed in range(lo, hi):
